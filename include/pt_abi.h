@@ -1,0 +1,166 @@
+/* pt_abi.h -- C ABI of libpt_cuda: the drop-in boundary for phyastro/PathTracer's compute dispatch.
+ *
+ * Every entry point names the reference interface it stands in for.  Citations: `shader.comp:N` is
+ * src/shader.comp, `host:N` is src/pathtracer.cpp of the reference.
+ *
+ * The reference drives its kernel through a Vulkan compute pipeline whose whole interface is
+ *   set 0 binding 0 : std430 uniform block of 4097 floats            (shader.comp:19-27 == host:187-195)
+ *   set 0 binding 1 : rgba32f texel buffer of W*H texels, RMW         (shader.comp:29,1529-1532; host:2250-2269)
+ *   push constants  : 88 bytes                                        (shader.comp:31-52 == host:197-218)
+ *   source hook     : per-scene GLSL `float sdf(in vec3 p)` / `float sdfmaterial(in vec3 p)` pairs spliced into
+ *                     the shader before compilation                   (shader.comp:704-719; host:2004-2054)
+ * pt_ubo and pt_params below are bit-identical to those two blocks, so a maintainer of the reference can hand
+ * `&ubo` and `&pushConstant` to this library unchanged.
+ *
+ * All functions return PT_OK (0) or a negative pt_status; pt_last_error() gives the message (NVRTC log included).
+ * A pt_ctx is single-threaded; plain pointers and sizes only -- no C++ or torch types cross this boundary.
+ */
+#ifndef PT_ABI_H
+#define PT_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PT_MAX_OBJECTS_SIZE 1024   /* host:39  / shader.comp:11 */
+#define PT_MAX_SDFS_SIZE 768       /* host:40  / shader.comp:12 */
+#define PT_MAX_MATERIALS_SIZE 783  /* host:41  / shader.comp:13 */
+#define PT_MAX_LIGHTS_SIZE 128     /* host:42  / shader.comp:14 */
+#define PT_MAX_LIGHTIDS_SIZE 64    /* host:43  / shader.comp:15 */
+#define PT_CIE_SIZE 1323           /* 441 rows x 3, 360..800 nm (host:400-842) */
+#define PT_MAX_SDF_SNIPPETS 32     /* only set1 of the four 32-bit masks is ever filled (shader.comp:734-738) */
+
+/* == UniformBufferObject (host:187-195) == `ubo` block (shader.comp:19-27); counts and ids are stored as floats */
+typedef struct pt_ubo {
+    float numObjects[7]; /* spheres, planes, boxes, lenses, cyclides, sdfs, sampled lights (host:3733-3739) */
+    float objects[PT_MAX_OBJECTS_SIZE];
+    float sdfs[PT_MAX_SDFS_SIZE];
+    float materials[PT_MAX_MATERIALS_SIZE];
+    float lights[PT_MAX_LIGHTS_SIZE];
+    float lightIDs[PT_MAX_LIGHTIDS_SIZE];
+    float CIEXYZ1931[PT_CIE_SIZE];
+} pt_ubo; /* 4097 floats = 16388 bytes */
+
+/* == PushConstantValues (host:197-218) == PushConstants (shader.comp:31-52) */
+typedef struct pt_params {
+    int32_t resolution[2];   /*  0 */
+    int32_t frame;           /*  8 */
+    int32_t currentSamples;  /* 12 */
+    int32_t samplesPerFrame; /* 16 */
+    float FPS;               /* 20 */
+    float persistence;       /* 24 */
+    int32_t pathLength;      /* 28 */
+    float cameraAngle[2];    /* 32  = (-pitch, yaw) in degrees (host:3821) */
+    float cameraPosX;        /* 40 */
+    float cameraPosY;        /* 44 */
+    float cameraPosZ;        /* 48 */
+    int32_t ISO;             /* 52 */
+    float cameraSize;        /* 56 */
+    float apertureSize;      /* 60 */
+    float apertureDist;      /* 64 */
+    float lensRadius;        /* 68 */
+    float lensFocalLength;   /* 72 */
+    float lensThickness;     /* 76 */
+    float lensDistance;      /* 80 */
+    int32_t tonemap;         /* 84 */
+} pt_params; /* 88 bytes */
+
+typedef enum pt_status {
+    PT_OK = 0,
+    PT_ERR_ARG = -1,     /* bad argument / call order */
+    PT_ERR_COMPILE = -2, /* SDF translation or NVRTC failure (the reference only prints these: host:1835-1860) */
+    PT_ERR_CUDA = -3,    /* CUDA runtime/driver error (the reference throws std::runtime_error: host:4174-4179) */
+    PT_ERR_IO = -4,      /* file / JSON error */
+    PT_ERR_NOGPU = -5    /* no CUDA device: there is no CPU fallback */
+} pt_status;
+
+typedef enum pt_mode {
+    PT_MODE_STRICT = 0, /* canonical IEEE semantics (pt_math.h, no contraction): bit-exact against oracle/ */
+    PT_MODE_FAST = 1    /* fma contraction, MUFU intrinsics, approximate division: the throughput build */
+} pt_mode;
+
+typedef struct pt_ctx pt_ctx;
+
+/* ---- device context (replaces InitVulkan + CreateComputePipeline, host:2424-2455, 2056-2092) ---------------- */
+int pt_create(int device, pt_ctx** out);
+void pt_destroy(pt_ctx* ctx);
+const char* pt_last_error(const pt_ctx* ctx); /* ctx may be NULL: last error of a failed pt_create / loader call */
+int pt_set_mode(pt_ctx* ctx, int mode);       /* default PT_MODE_STRICT; takes effect at the next pt_set_scene */
+
+/* UpdateUniformBuffer + RecompileComputeShaders (host:3642-3811, 3836-3841, InsertSDF host:2004-2054).
+ * sdf_glsl[i] is scene["sdf"][i]["glsl"] unchanged; n_sdf must equal ubo->numObjects[5].  With n_sdf > 0 the
+ * kernel is rebuilt by NVRTC with the snippets translated against include/pt_glsl.h. */
+int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, int n_sdf);
+
+/* CreateTexelBuffer (host:2250-2269): library-owned W*H RGBA32F accumulation image, zero-filled */
+int pt_resize(pt_ctx* ctx, int width, int height);
+/* Same, but the caller owns the device memory (e.g. a torch tensor): W*H*4 floats, 16-byte aligned.  Not cleared. */
+int pt_bind_image(pt_ctx* ctx, void* device_rgba32f, int width, int height);
+int pt_clear(pt_ctx* ctx);
+
+/* One vkCmdDispatch (host:3586-3608, DrawFrame host:3843-3880): renders samplesPerFrame samples per pixel with
+ * sample indices frame-samplesPerFrame .. frame-1 and applies Accumulate() (shader.comp:1492-1507) to the image.
+ * Asynchronous on the context's stream. */
+int pt_dispatch(pt_ctx* ctx, const pt_params* params);
+
+/* Sample-split building block: adds the raw XYZ of sample indices
+ * first_sample .. first_sample+n_samples-1 to the image (no exposure, no mean).  pt_finalize then turns the sum
+ * over total_samples into the reference's units: sum / total * apertureSize^2 * ISO, w = 1. */
+int pt_dispatch_sum(pt_ctx* ctx, const pt_params* params, int first_sample, int n_samples);
+int pt_finalize(pt_ctx* ctx, const pt_params* params, int total_samples);
+
+/* Mapped texel memory (host:3491-3518 reads it through a persistent mapping): copies W*H*4 floats to the host.
+ * Synchronises the stream. */
+int pt_read_xyz(pt_ctx* ctx, float* rgba, size_t n_floats);
+int pt_sync(pt_ctx* ctx);
+void* pt_image_ptr(pt_ctx* ctx);    /* device pointer of the accumulation image */
+void* pt_stream_handle(pt_ctx* ctx); /* cudaStream_t the kernels are launched on */
+/* Device time of the kernels launched since the previous call (CUDA events on the context's stream), and how many */
+int pt_kernel_time(pt_ctx* ctx, float* ms, long long* launches);
+
+/* ---- convenience layer: the host code either side of the dispatch ------------------------------------------- */
+typedef struct pt_scene pt_scene; /* parsed scene file: the std::vectors of host:1118-1127 */
+
+/* ReadJSON + UpdateFromJSON (host:893-908, 2576-2722).  Same schema as scenes/ *.json; missing arrays are legal. */
+int pt_scene_load_json(const char* path, pt_scene** out);
+int pt_scene_parse_json(const char* text, pt_scene** out);
+void pt_scene_free(pt_scene* scene);
+int pt_scene_num_shots(const pt_scene* scene);
+int pt_scene_num_sdf(const pt_scene* scene);
+const char* pt_scene_sdf_glsl(const pt_scene* scene, int i);
+/* UpdateUniformBuffer (host:3642-3811) incl. the CIE table copy of CreateUniformBuffer (host:2230-2248) */
+int pt_scene_pack_ubo(const pt_scene* scene, pt_ubo* ubo);
+/* UpdatePushConstant (host:3813-3834) for camera shot `shot` (1-based, host:1170); the per-dispatch fields are
+ * set to the first offscreen dispatch: frame = currentSamples = samples_per_frame (host:4042-4048). */
+int pt_scene_pack_params(const pt_scene* scene, int shot, int width, int height, int samples_per_frame,
+                         int path_length, pt_params* params);
+
+/* Offscreen MainLoop (host:4005-4086): total_samples/samples_per_frame dispatches with the reference's
+ * frame/currentSamples bookkeeping. Blocks until done. */
+int pt_render(pt_ctx* ctx, const pt_params* base, int total_samples, int samples_per_frame);
+
+/* SaveRender + SavePPM (host:3491-3518, 918-933): display transform of shader.frag:31-93, 8-bit P6.
+ * pt_write_pfm writes the raw XYZ (or linear sRGB when to_rgb != 0) as a bottom-up PF file. */
+int pt_write_ppm(const char* path, const float* rgba, int width, int height, int tonemap);
+int pt_write_pfm(const char* path, const float* rgba, int width, int height, int to_rgb);
+
+/* ---- introspection used by the tests --------------------------------------------------------------------- */
+const float* pt_cie1931_table(void); /* 1323 floats */
+/* GLSL snippet -> CUDA/C++ text exactly as pt_set_scene feeds NVRTC (prelude + snippets + dispatchers).
+ * Returns the required size (including NUL); writes at most cap bytes. */
+long pt_sdf_translate(const char* const* sdf_glsl, int n_sdf, char* out, size_t cap);
+/* Compile-only check of the NVRTC path (needs no GPU): 0 on success, log via pt_last_error(NULL) */
+int pt_sdf_compile_check(const char* const* sdf_glsl, int n_sdf, int mode);
+/* Evaluate a pt_math.h function on the device: fn 0 sin,1 cos,2 acos,3 exp2,4 log2,5 exp,6 log,7 pow(x,y),8 PCG32 */
+int pt_math_eval(pt_ctx* ctx, int fn, const float* x, const float* y, float* out, size_t n);
+/* Evaluate SDF()/SDFMATERIAL() of the current scene at n points (xyz triples); set1 mask as given */
+int pt_sdf_eval(pt_ctx* ctx, const float* xyz, size_t n, unsigned set1, float* dist, float* material);
+const char* pt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PT_ABI_H */
