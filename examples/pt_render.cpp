@@ -1,0 +1,90 @@
+/* pt_render -- headless example host for libpt_cuda.
+ *
+ * The reference's offscreen mode asks four questions on stdin -- samples, samples per frame, path length, camera
+ * shot (host:3970-3978) -- then opens file dialogs for the scene and the output (host:3989,3492).  This CLI takes
+ * the same parameters as flags and drives the library through the C ABI only (include/pt_abi.h).
+ *
+ *   pt_render --scene scenes/scene0.json --width 512 --height 512 --spp 64 --spf 8 --path-length 5 --shot 1 \
+ *             [--fast] [--jit 0|1|2] [--device 0] [--out render.pfm|render.ppm] [--tonemap 3]
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "pt_abi.h"
+
+static int die(const char* what, pt_ctx* ctx) {
+    fprintf(stderr, "pt_render: %s: %s\n", what, pt_last_error(ctx));
+    return 1;
+}
+
+int main(int argc, char** argv) {
+    std::string scene_path = "scenes/scene0.json", out_path;
+    int width = 1280, height = 720, spp = 1000, spf = 1, path_length = 5, shot = 1, device = 0, tonemap = 3; /* host:30-31,1164-1174 */
+    int fast = 0, jit = -1;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        auto next = [&](const char* name) -> const char* {
+            if (i + 1 >= argc) { fprintf(stderr, "pt_render: %s needs a value\n", name); exit(2); }
+            return argv[++i];
+        };
+        if (a == "--scene") scene_path = next("--scene");
+        else if (a == "--width") width = atoi(next("--width"));
+        else if (a == "--height") height = atoi(next("--height"));
+        else if (a == "--spp") spp = atoi(next("--spp"));
+        else if (a == "--spf") spf = atoi(next("--spf"));
+        else if (a == "--path-length") path_length = atoi(next("--path-length"));
+        else if (a == "--shot") shot = atoi(next("--shot"));
+        else if (a == "--device") device = atoi(next("--device"));
+        else if (a == "--tonemap") tonemap = atoi(next("--tonemap"));
+        else if (a == "--out") out_path = next("--out");
+        else if (a == "--jit") jit = atoi(next("--jit"));
+        else if (a == "--fast") fast = 1;
+        else if (a == "--strict") fast = 0;
+        else { fprintf(stderr, "pt_render: unknown flag %s\n", a.c_str()); return 2; }
+    }
+    pt_scene* scene = nullptr;
+    if (pt_scene_load_json(scene_path.c_str(), &scene) != PT_OK) return die("load scene", nullptr);
+    pt_ubo ubo;
+    pt_params params;
+    if (pt_scene_pack_ubo(scene, &ubo) != PT_OK) return die("pack ubo", nullptr);
+    if (pt_scene_pack_params(scene, shot, width, height, spf, path_length, &params) != PT_OK) return die("pack params", nullptr);
+    params.tonemap = tonemap;
+    std::vector<const char*> sdf;
+    for (int i = 0; i < pt_scene_num_sdf(scene); i++) sdf.push_back(pt_scene_sdf_glsl(scene, i));
+
+    pt_ctx* ctx = nullptr;
+    if (pt_create(device, &ctx) != PT_OK) return die("create context", nullptr);
+    pt_set_mode(ctx, fast ? PT_MODE_FAST : PT_MODE_STRICT);
+    if (jit >= 0) pt_set_jit(ctx, jit);
+    auto t0 = std::chrono::steady_clock::now();
+    if (pt_set_scene(ctx, &ubo, sdf.data(), (int)sdf.size()) != PT_OK) return die("set scene", ctx);
+    auto t1 = std::chrono::steady_clock::now();
+    if (pt_resize(ctx, width, height) != PT_OK) return die("resize", ctx);
+    if (pt_render(ctx, &params, spp, spf) != PT_OK) return die("render", ctx);
+    auto t2 = std::chrono::steady_clock::now();
+    float ms = 0.0f;
+    long long launches = 0;
+    pt_kernel_time(ctx, &ms, &launches);
+    const double samples = (double)width * height * (double)(spp / spf * spf);
+    printf("{\"scene\": \"%s\", \"width\": %d, \"height\": %d, \"spp\": %d, \"spf\": %d, \"path_length\": %d, \"mode\": \"%s\", "
+           "\"compile_s\": %.3f, \"render_s\": %.3f, \"kernel_ms\": %.3f, \"launches\": %lld, \"msamples_per_s\": %.2f}\n",
+           scene_path.c_str(), width, height, spp, spf, path_length, fast ? "fast" : "strict",
+           std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count(), ms, launches,
+           samples / (ms * 1e-3) / 1e6);
+    if (!out_path.empty()) {
+        std::vector<float> img((size_t)width * height * 4);
+        if (pt_read_xyz(ctx, img.data(), img.size()) != PT_OK) return die("read back", ctx);
+        const bool ppm = out_path.size() > 4 && out_path.substr(out_path.size() - 4) == ".ppm";
+        int rc = ppm ? pt_write_ppm(out_path.c_str(), img.data(), width, height, tonemap)
+                     : pt_write_pfm(out_path.c_str(), img.data(), width, height, 0);
+        if (rc != PT_OK) { fprintf(stderr, "pt_render: cannot write %s\n", out_path.c_str()); return 1; }
+    }
+    pt_destroy(ctx);
+    pt_scene_free(scene);
+    return 0;
+}

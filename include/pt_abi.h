@@ -89,6 +89,10 @@ int pt_create(int device, pt_ctx** out);
 void pt_destroy(pt_ctx* ctx);
 const char* pt_last_error(const pt_ctx* ctx); /* ctx may be NULL: last error of a failed pt_create / loader call */
 int pt_set_mode(pt_ctx* ctx, int mode);       /* default PT_MODE_STRICT; takes effect at the next pt_set_scene */
+/* Run-time compilation policy (env PT_JIT overrides the default 1): 0 = statically compiled kernels only (scenes
+ * with SDF snippets are refused), 1 = NVRTC only for scenes with SDF snippets, 2 = always NVRTC, with the scene's
+ * primitive counts baked in so the intersection loops unroll. Takes effect at the next pt_set_scene. */
+int pt_set_jit(pt_ctx* ctx, int policy);
 
 /* UpdateUniformBuffer + RecompileComputeShaders (host:3642-3811, 3836-3841, InsertSDF host:2004-2054).
  * sdf_glsl[i] is scene["sdf"][i]["glsl"] unchanged; n_sdf must equal ubo->numObjects[5].  With n_sdf > 0 the
@@ -150,10 +154,11 @@ int pt_write_pfm(const char* path, const float* rgba, int width, int height, int
 /* ---- introspection used by the tests --------------------------------------------------------------------- */
 const float* pt_cie1931_table(void); /* 1323 floats */
 /* GLSL snippet -> CUDA/C++ text exactly as pt_set_scene feeds NVRTC (prelude + snippets + dispatchers).
- * Returns the required size (including NUL); writes at most cap bytes. */
-long pt_sdf_translate(const char* const* sdf_glsl, int n_sdf, char* out, size_t cap);
+ * sdfs_raw = ubo.sdfs (6 floats per SDF: position, bounding size).  The text also compiles with g++, which is how
+ * the CPU-side tests check the front end.  Returns the required size (including NUL); writes at most cap bytes. */
+long pt_sdf_translate(const char* const* sdf_glsl, int n_sdf, const float* sdfs_raw, char* out, size_t cap);
 /* Compile-only check of the NVRTC path (needs no GPU): 0 on success, log via pt_last_error(NULL) */
-int pt_sdf_compile_check(const char* const* sdf_glsl, int n_sdf, int mode);
+int pt_sdf_compile_check(const char* const* sdf_glsl, int n_sdf, const float* sdfs_raw, int mode);
 /* Evaluate a pt_math.h function on the device: fn 0 sin,1 cos,2 acos,3 exp2,4 log2,5 exp,6 log,7 pow(x,y),8 PCG32 */
 int pt_math_eval(pt_ctx* ctx, int fn, const float* x, const float* y, float* out, size_t n);
 /* Evaluate SDF()/SDFMATERIAL() of the current scene at n points (xyz triples); set1 mask as given */

@@ -1,0 +1,10 @@
+"""pathtracer_b200 -- Python bindings (ctypes) of libpt_cuda, the B200-native drop-in for PathTracer's compute kernel.
+
+Nothing in here computes: the hot path is hand-written sm_100a CUDA behind the C ABI of include/pt_abi.h.
+There is no CPU fallback; importing works anywhere, creating a Renderer needs a CUDA device and the built library.
+"""
+from .api import (LibraryNotBuilt, PtError, Renderer, Scene, build_library, lib, library_path, MODE_FAST, MODE_STRICT,
+                  PARAMS_DTYPE, UBO_FLOATS)
+
+__all__ = ['LibraryNotBuilt', 'PtError', 'Renderer', 'Scene', 'build_library', 'lib', 'library_path', 'MODE_FAST',
+           'MODE_STRICT', 'PARAMS_DTYPE', 'UBO_FLOATS']

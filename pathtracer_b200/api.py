@@ -1,0 +1,282 @@
+"""ctypes front-end of pathtracer_b200/lib/libpt_cuda.so (C ABI: include/pt_abi.h).
+
+Class and method names mirror the reference's host functions for this path (src/pathtracer.cpp):
+  Scene.load            ReadJSON + UpdateFromJSON            host:893-908, 2576-2722
+  Scene.pack_ubo        UpdateUniformBuffer                  host:3642-3811
+  Scene.pack_params     UpdatePushConstant                   host:3813-3834
+  Renderer.set_scene    UpdateUniformBuffer + RecompileComputeShaders (InsertSDF)   host:2004-2054, 3836-3841
+  Renderer.resize       CreateTexelBuffer                    host:2250-2269
+  Renderer.dispatch     one vkCmdDispatch of DrawFrame       host:3586-3608, 3843-3880
+  Renderer.render       offscreen MainLoop                   host:4005-4086
+  Renderer.read_xyz     mapped texel memory                  host:3491-3518
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MODE_STRICT, MODE_FAST = 0, 1
+UBO_FLOATS = 4097
+
+PARAMS_DTYPE = np.dtype([
+    ('resolution', '<i4', (2,)), ('frame', '<i4'), ('currentSamples', '<i4'), ('samplesPerFrame', '<i4'),
+    ('FPS', '<f4'), ('persistence', '<f4'), ('pathLength', '<i4'), ('cameraAngle', '<f4', (2,)),
+    ('cameraPosX', '<f4'), ('cameraPosY', '<f4'), ('cameraPosZ', '<f4'), ('ISO', '<i4'), ('cameraSize', '<f4'),
+    ('apertureSize', '<f4'), ('apertureDist', '<f4'), ('lensRadius', '<f4'), ('lensFocalLength', '<f4'),
+    ('lensThickness', '<f4'), ('lensDistance', '<f4'), ('tonemap', '<i4')])
+assert PARAMS_DTYPE.itemsize == 88
+
+
+class PtError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__('libpt_cuda error %d: %s' % (code, message))
+        self.code = code
+
+
+class LibraryNotBuilt(RuntimeError):
+    pass
+
+
+def library_path():
+    return os.path.join(HERE, 'lib', 'libpt_cuda.so')
+
+
+def build_library(verbose=False):
+    """make -C pathtracer_b200/csrc (nvcc -gencode arch=compute_100a,code=sm_100a; cross-compiles without a GPU)."""
+    r = subprocess.run(['make', '-C', os.path.join(HERE, 'csrc'), '-j8'], capture_output=not verbose, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('building libpt_cuda failed:\n%s\n%s' % (r.stdout or '', r.stderr or ''))
+
+
+_lib = None
+
+
+def lib():
+    """The loaded library. Raises LibraryNotBuilt (never falls back to anything) when the .so is missing."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise LibraryNotBuilt('%s not found: run `python -c "import __graft_entry__ as g; g.build()"` or '
+                                  '`make -C pathtracer_b200/csrc`. There is no CPU fallback.' % path)
+        L = C.CDLL(path)
+        vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+        L.pt_version.restype = C.c_char_p
+        L.pt_last_error.restype = C.c_char_p
+        L.pt_last_error.argtypes = [vp]
+        L.pt_create.argtypes = [ci, C.POINTER(vp)]
+        L.pt_destroy.argtypes = [vp]
+        L.pt_destroy.restype = None
+        L.pt_set_mode.argtypes = [vp, ci]
+        L.pt_set_jit.argtypes = [vp, ci]
+        L.pt_set_scene.argtypes = [vp, vp, C.POINTER(C.c_char_p), ci]
+        L.pt_resize.argtypes = [vp, ci, ci]
+        L.pt_bind_image.argtypes = [vp, vp, ci, ci]
+        L.pt_clear.argtypes = [vp]
+        L.pt_dispatch.argtypes = [vp, vp]
+        L.pt_dispatch_sum.argtypes = [vp, vp, ci, ci]
+        L.pt_finalize.argtypes = [vp, vp, ci]
+        L.pt_render.argtypes = [vp, vp, ci, ci]
+        L.pt_read_xyz.argtypes = [vp, vp, C.c_size_t]
+        L.pt_sync.argtypes = [vp]
+        L.pt_image_ptr.argtypes = [vp]
+        L.pt_image_ptr.restype = vp
+        L.pt_stream_handle.argtypes = [vp]
+        L.pt_stream_handle.restype = vp
+        L.pt_kernel_time.argtypes = [vp, C.POINTER(cf), C.POINTER(C.c_longlong)]
+        L.pt_scene_load_json.argtypes = [C.c_char_p, C.POINTER(vp)]
+        L.pt_scene_parse_json.argtypes = [C.c_char_p, C.POINTER(vp)]
+        L.pt_scene_free.argtypes = [vp]
+        L.pt_scene_free.restype = None
+        L.pt_scene_num_shots.argtypes = [vp]
+        L.pt_scene_num_sdf.argtypes = [vp]
+        L.pt_scene_sdf_glsl.argtypes = [vp, ci]
+        L.pt_scene_sdf_glsl.restype = C.c_char_p
+        L.pt_scene_pack_ubo.argtypes = [vp, vp]
+        L.pt_scene_pack_params.argtypes = [vp, ci, ci, ci, ci, ci, vp]
+        L.pt_write_ppm.argtypes = [C.c_char_p, vp, ci, ci, ci]
+        L.pt_write_pfm.argtypes = [C.c_char_p, vp, ci, ci, ci]
+        L.pt_cie1931_table.restype = C.POINTER(cf)
+        L.pt_sdf_translate.argtypes = [C.POINTER(C.c_char_p), ci, vp, C.c_char_p, C.c_size_t]
+        L.pt_sdf_translate.restype = C.c_long
+        L.pt_sdf_compile_check.argtypes = [C.POINTER(C.c_char_p), ci, vp, ci]
+        L.pt_math_eval.argtypes = [vp, ci, vp, vp, vp, C.c_size_t]
+        L.pt_sdf_eval.argtypes = [vp, vp, C.c_size_t, C.c_uint32, vp, vp]
+        _lib = L
+    return _lib
+
+
+def _check(rc, ctx=None):
+    if rc != 0:
+        raise PtError(rc, (lib().pt_last_error(ctx) or b'').decode(errors='replace'))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _c_strings(strings):
+    arr = (C.c_char_p * max(len(strings), 1))()
+    for i, s in enumerate(strings):
+        arr[i] = s if isinstance(s, bytes) else s.encode()
+    return arr
+
+
+def cie1931_table():
+    return np.ctypeslib.as_array(lib().pt_cie1931_table(), shape=(1323,)).copy()
+
+
+def sdf_translate(sources, sdfs_raw=None):
+    """The CUDA/C++ translation unit pt_set_scene hands to NVRTC for these snippets (pt_sdf_front.cpp)."""
+    L = lib()
+    raw = np.zeros(6 * max(len(sources), 1), dtype=np.float32) if sdfs_raw is None else np.ascontiguousarray(sdfs_raw, dtype=np.float32)
+    arr = _c_strings(sources)
+    n = L.pt_sdf_translate(arr, len(sources), _ptr(raw), None, 0)
+    if n < 0:
+        _check(int(n))
+    buf = C.create_string_buffer(int(n))
+    L.pt_sdf_translate(arr, len(sources), _ptr(raw), buf, int(n))
+    return buf.value.decode()
+
+
+def sdf_compile_check(sources, sdfs_raw=None, mode=MODE_STRICT):
+    """NVRTC compile-only check of the whole kernel with these snippets; needs no GPU."""
+    raw = np.zeros(6 * max(len(sources), 1), dtype=np.float32) if sdfs_raw is None else np.ascontiguousarray(sdfs_raw, dtype=np.float32)
+    _check(lib().pt_sdf_compile_check(_c_strings(sources), len(sources), _ptr(raw), mode))
+
+
+class Scene:
+    """A parsed scene file (same schema as the reference's scenes/*.json)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def load(cls, path):
+        h = C.c_void_p()
+        _check(lib().pt_scene_load_json(os.fspath(path).encode(), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def parse(cls, text):
+        h = C.c_void_p()
+        _check(lib().pt_scene_parse_json(text.encode() if isinstance(text, str) else text, C.byref(h)))
+        return cls(h)
+
+    def __del__(self):
+        if getattr(self, '_h', None) and _lib is not None:
+            _lib.pt_scene_free(self._h)
+            self._h = None
+
+    @property
+    def num_shots(self):
+        return lib().pt_scene_num_shots(self._h)
+
+    @property
+    def sdf_sources(self):
+        L = lib()
+        return [L.pt_scene_sdf_glsl(self._h, i) for i in range(L.pt_scene_num_sdf(self._h))]
+
+    def pack_ubo(self):
+        ubo = np.zeros(UBO_FLOATS, dtype=np.float32)
+        _check(lib().pt_scene_pack_ubo(self._h, _ptr(ubo)))
+        return ubo
+
+    def pack_params(self, shot=1, width=1280, height=720, spf=1, path_length=5):
+        p = np.zeros((), dtype=PARAMS_DTYPE)
+        _check(lib().pt_scene_pack_params(self._h, shot, width, height, spf, path_length, _ptr(p)))
+        return p
+
+
+class Renderer:
+    """One device context (pt_ctx). Fails loudly without a GPU: there is no CPU fallback."""
+
+    def __init__(self, device=0, mode=MODE_STRICT, jit=None):
+        self._ctx = C.c_void_p()
+        self.width = self.height = 0
+        _check(lib().pt_create(device, C.byref(self._ctx)))
+        _check(lib().pt_set_mode(self._ctx, mode), self._ctx)
+        if jit is not None:
+            _check(lib().pt_set_jit(self._ctx, jit), self._ctx)
+        self._keep = None
+
+    def close(self):
+        if getattr(self, '_ctx', None) and _lib is not None:
+            _lib.pt_destroy(self._ctx)
+            self._ctx = None
+
+    __del__ = close
+
+    def set_mode(self, mode):
+        _check(lib().pt_set_mode(self._ctx, mode), self._ctx)
+
+    def set_jit(self, policy):
+        _check(lib().pt_set_jit(self._ctx, policy), self._ctx)
+
+    def set_scene(self, ubo, sdf_sources=()):
+        ubo = np.ascontiguousarray(ubo, dtype=np.float32)
+        assert ubo.size == UBO_FLOATS
+        _check(lib().pt_set_scene(self._ctx, _ptr(ubo), _c_strings(list(sdf_sources)), len(sdf_sources)), self._ctx)
+
+    def resize(self, width, height):
+        _check(lib().pt_resize(self._ctx, width, height), self._ctx)
+        self.width, self.height = width, height
+        self._keep = None
+
+    def bind_image(self, tensor):
+        """Render into caller-owned device memory: a torch CUDA tensor of shape (H, W, 4), float32, contiguous."""
+        assert tensor.is_cuda and tensor.is_contiguous() and tensor.dim() == 3 and tensor.shape[2] == 4
+        h, w = int(tensor.shape[0]), int(tensor.shape[1])
+        _check(lib().pt_bind_image(self._ctx, C.c_void_p(tensor.data_ptr()), w, h), self._ctx)
+        self.width, self.height = w, h
+        self._keep = tensor
+
+    def clear(self):
+        _check(lib().pt_clear(self._ctx), self._ctx)
+
+    def dispatch(self, params):
+        _check(lib().pt_dispatch(self._ctx, _ptr(np.ascontiguousarray(params))), self._ctx)
+
+    def dispatch_sum(self, params, first_sample, n_samples):
+        _check(lib().pt_dispatch_sum(self._ctx, _ptr(np.ascontiguousarray(params)), first_sample, n_samples), self._ctx)
+
+    def finalize(self, params, total_samples):
+        _check(lib().pt_finalize(self._ctx, _ptr(np.ascontiguousarray(params)), total_samples), self._ctx)
+
+    def render(self, params, total_samples, spf):
+        _check(lib().pt_render(self._ctx, _ptr(np.ascontiguousarray(params)), total_samples, spf), self._ctx)
+
+    def sync(self):
+        _check(lib().pt_sync(self._ctx), self._ctx)
+
+    def read_xyz(self, out=None):
+        if out is None:
+            out = np.empty((self.height, self.width, 4), dtype=np.float32)
+        _check(lib().pt_read_xyz(self._ctx, _ptr(out), out.size), self._ctx)
+        return out
+
+    def kernel_time(self):
+        """(milliseconds of device time, number of kernel launches) since the previous call; CUDA events."""
+        ms, n = C.c_float(), C.c_longlong()
+        _check(lib().pt_kernel_time(self._ctx, C.byref(ms), C.byref(n)), self._ctx)
+        return ms.value, n.value
+
+    @property
+    def stream(self):
+        return lib().pt_stream_handle(self._ctx)
+
+    def math_eval(self, fn, x, y=None):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = None if y is None else np.ascontiguousarray(y, dtype=np.float32)
+        out = np.empty_like(x)
+        _check(lib().pt_math_eval(self._ctx, fn, _ptr(x), None if y is None else _ptr(y), _ptr(out), x.size), self._ctx)
+        return out
+
+    def sdf_eval(self, xyz, set1=1):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        n = xyz.shape[0]
+        d, m = np.empty(n, dtype=np.float32), np.empty(n, dtype=np.float32)
+        _check(lib().pt_sdf_eval(self._ctx, _ptr(xyz), n, set1, _ptr(d), _ptr(m)), self._ctx)
+        return d, m

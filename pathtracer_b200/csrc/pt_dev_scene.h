@@ -1,0 +1,127 @@
+/* pt_dev_scene.h -- the scene as the CUDA kernels read it.
+ *
+ * The reference's shader re-derives per-object constants for every ray: RotationMatrix() with six sin/cos per
+ * rotated primitive (shader.comp:339,371,636), lens cap geometry (shader.comp:423-431), bounding-sphere radii
+ * (shader.comp:887,899-905), the camera basis and the camera lens (shader.comp:1456,1409-1418) -- all functions
+ * of the uniform block and the push constants only.  libpt_cuda evaluates them ONCE on the host
+ * (pt_prepare.cpp), with the same pt_math.h functions and the same fp32 operation order the shader uses, so the
+ * hoisted values are bit-identical to what a per-ray evaluation would produce, and passes the result to the
+ * kernel as a __grid_constant__ parameter: it lives in the constant bank, where warp-uniform reads are free
+ * operands of the FP32 pipe.
+ *
+ * Plain C structs of floats/ints; shared by g++ (host), nvcc and NVRTC.
+ */
+#ifndef PT_DEV_SCENE_H
+#define PT_DEV_SCENE_H
+
+#define PT_DEV_MAX_SPHERES 48
+#define PT_DEV_MAX_PLANES 16
+#define PT_DEV_MAX_BOXES 32
+#define PT_DEV_MAX_LENSES 16
+#define PT_DEV_MAX_CYCLIDES 16
+#define PT_DEV_MAX_SDFS 32
+#define PT_DEV_MAX_LIGHT_SLOTS 65 /* lightIDs[0..numLights] inclusive: r == 1.0 reads one past */
+#define PT_DEV_MAX_MATERIALS 64
+#define PT_DEV_MAX_LIGHTS 64
+
+typedef struct PtDevSphere { /* shader.comp:59-64, 289-317 */
+    float px, py, pz, radius;
+    float r2;            /* radius * radius */
+    float materialID;    /* float(int(raw) - 1) */
+    float lightID;
+    float pad;
+} PtDevSphere;
+
+typedef struct PtDevPlane { /* shader.comp:66-70, 319-335: only pos.y matters */
+    float py, materialID, lightID, pad;
+} PtDevPlane;
+
+typedef struct PtDevBox { /* shader.comp:72-78, 337-364 */
+    float px, py, pz;
+    float bound2;        /* 0.25 * dot(size, size) (shader.comp:887) */
+    float m[9];          /* RotationMatrix(rotation), column-major: m[3*col + row] */
+    float sx, sy, sz;    /* size */
+    float materialID, lightID;
+    float pad[2];
+} PtDevBox;
+
+typedef struct PtDevLens { /* shader.comp:90-99, 366-448, 895-910 */
+    float px, py, pz;
+    float bound2;        /* bounding-sphere radius^2 (shader.comp:899-905) */
+    float m[9];          /* RotationMatrix(rotation) */
+    float sradius;       /* slice.radius = 2 * focalLength */
+    float sradius2;      /* sradius * sradius */
+    float sliceOffset;   /* sradius - lensThicknessHalf */
+    float shift;         /* localSlicePos - sliceSize - sliceOffset (shader.comp:377,379) */
+    float invertSide;    /* 1 when !isConverging (isSideInvert), else 0 */
+    float materialID, lightID;
+} PtDevLens;
+
+typedef struct PtDevCyclide { /* shader.comp:101-112, 633-679 */
+    float px, py, pz;
+    float brad;          /* packed brad^2 * maxscale^2 (host:3723-3725) */
+    float m[9];
+    float sx, sy, sz;    /* scale */
+    float a, b, c, d;
+    float materialID, lightID;
+    float pad[2];
+} PtDevCyclide;
+
+typedef struct PtDevSdf { /* shader.comp:114-117: bounding box */
+    float px, py, pz, sx, sy, sz, pad[2];
+} PtDevSdf;
+
+typedef struct PtDevLightSlot { /* what SampleRandomLightSource (shader.comp:1225-1285) returns for lightIDs[j] */
+    float px, py, pz;
+    float boundingRadius;
+    float lightID;       /* lightIDOut */
+    int objectID;        /* returned lightObjectID */
+    float pad[2];
+} PtDevLightSlot;
+
+typedef struct PtDevScene {
+    int nSpheres, nPlanes, nBoxes, nLenses, nCyclides, nSdfs, nLightSlots;
+    float numLights;     /* numObjects[6] as the float the shader multiplies with */
+    float invNumLights;  /* 1.0 / numObjects[6] (shader.comp:1289) */
+    int pad0[3];
+    PtDevSphere spheres[PT_DEV_MAX_SPHERES];
+    PtDevPlane planes[PT_DEV_MAX_PLANES];
+    PtDevBox boxes[PT_DEV_MAX_BOXES];
+    PtDevLens lenses[PT_DEV_MAX_LENSES];
+    PtDevCyclide cyclides[PT_DEV_MAX_CYCLIDES];
+    PtDevSdf sdfs[PT_DEV_MAX_SDFS];
+    PtDevLightSlot lightSlots[PT_DEV_MAX_LIGHT_SLOTS];
+} PtDevScene;
+
+/* Per-dispatch constants: the push constants (shader.comp:31-52) plus what Scene()/TracePathLens() derive from them */
+typedef struct PtDevParams {
+    int width, height;
+    int firstSample;       /* frame - samplesPerFrame: sample index of k = 0 (shader.comp:954) */
+    int samplesPerFrame;
+    int pathLength;
+    int accumMode;         /* 0 static running mean, 1 temporal EMA (shader.comp:1500-1506), 2 raw sum */
+    float accumN;          /* float(unitSamples) (mode 0, shader.comp:1504-1505) */
+    float accumNm1;        /* float(unitSamples - 1) */
+    float accumWeight;     /* EMA weight (mode 1) */
+    float spfFloat;        /* float(samplesPerFrame) */
+    float exposure;        /* apertureSize * apertureSize * float(ISO) (shader.comp:1519) */
+    float resX, resY;      /* float(resolution) */
+    float camPosX, camPosY, camPosZ;
+    float sensorScale;     /* -cameraSize * 0.5 (shader.comp:1457) */
+    float halfAperture;    /* 0.5 * apertureSize (shader.comp:1461) */
+    float apertureDist;
+    float camM[9];         /* RotationMatrix(vec3(cameraAngle, 0)), column-major */
+    PtDevLens camLens;     /* TracePathLens' lens object (shader.comp:1411-1418) */
+} PtDevParams;
+
+/* raw tables the kernel indexes with computed ids; a copy of the tail of the uniform block in global memory:
+ * flat float[4097] exactly like pt_ubo, so clamped flat indexing matches the oracle's Shader::at() */
+#define PT_UBO_FLOATS 4097
+#define PT_OFF_OBJ 7
+#define PT_OFF_SDF (7 + 1024)
+#define PT_OFF_MAT (PT_OFF_SDF + 768)
+#define PT_OFF_LGT (PT_OFF_MAT + 783)
+#define PT_OFF_LID (PT_OFF_LGT + 128)
+#define PT_OFF_CIE (PT_OFF_LID + 64)
+
+#endif /* PT_DEV_SCENE_H */

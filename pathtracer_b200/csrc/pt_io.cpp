@@ -1,0 +1,86 @@
+/* pt_io.cpp -- headless output: the reference's display transform + 8-bit PPM, and raw PFM.
+ *
+ * pt_write_ppm = SaveRender + SavePPM (host:3491-3518, 918-933) with the CPU twin of shader.frag:31-93
+ * (host:949-1071): Bradford E->D65, XYZ->linear sRGB, max(0), tonemap {0 none, 1 Reinhard, 2 ACES fit,
+ * 3 exp(-0.25/x)}, sRGB companding, byte = (char)(c * 255).  Buffer row 0 is the top scanline.
+ * pt_write_pfm keeps the float data ("PF", little-endian, bottom-up by the format's convention -> rows flipped).
+ * This is post-processing, outside the parity-gated kernel: it uses libm.
+ */
+#include <math.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "pt_abi.h"
+
+namespace {
+
+void xyz_to_linear_srgb(const float* xyz, float* rgb) {
+    /* v * M with GLSL/glm column-major constructors: component j = dot(v, column j) */
+    static const float E2D65[9] = {0.9531874f, -0.0265906f, 0.0238731f, -0.0382467f, 1.0288406f, 0.0094060f,
+                                   0.0026068f, -0.0030332f, 1.0892565f};
+    static const float X2R[9] = {3.2404542f, -1.5371385f, -0.4985314f, -0.9692660f, 1.8760108f, 0.0415560f,
+                                 0.0556434f, -0.2040259f, 1.0572252f};
+    float d[3];
+    for (int j = 0; j < 3; j++) d[j] = xyz[0] * E2D65[3 * j] + xyz[1] * E2D65[3 * j + 1] + xyz[2] * E2D65[3 * j + 2];
+    for (int j = 0; j < 3; j++) rgb[j] = d[0] * X2R[3 * j] + d[1] * X2R[3 * j + 1] + d[2] * X2R[3 * j + 2];
+}
+
+float tonemap_one(float x, int tonemap) {
+    if (tonemap == 1) return x / (1.0f + x);
+    if (tonemap == 2) return x * (2.51f * x + 0.03f) / (x * (2.43f * x + 0.59f) + 0.14f);
+    if (tonemap == 3) return expf(-0.25f / x);
+    return x;
+}
+
+float srgb_companding(float x) {
+    x = x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x);
+    return (x <= 0.0031308f) ? 12.92f * x : 1.055f * powf(x, 1.0f / 2.4f) - 0.055f;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pt_write_ppm(const char* path, const float* rgba, int width, int height, int tonemap) {
+    if (!path || !rgba || width <= 0 || height <= 0) return PT_ERR_ARG;
+    std::vector<unsigned char> bytes((size_t)width * (size_t)height * 3);
+    for (size_t i = 0; i < (size_t)width * (size_t)height; i++) {
+        float rgb[3];
+        xyz_to_linear_srgb(rgba + 4 * i, rgb);
+        for (int k = 0; k < 3; k++) {
+            float v = rgb[k] < 0.0f ? 0.0f : rgb[k]; /* glm::max(x, 0): NaN stays NaN -> companding clamps */
+            v = srgb_companding(tonemap_one(v, tonemap));
+            if (!(v == v)) v = 0.0f;
+            bytes[3 * i + k] = (unsigned char)(int)(v * 255.0);
+        }
+    }
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return PT_ERR_IO;
+    fprintf(fp, "P6\n%d\n%d\n255\n", width, height);
+    const size_t w = fwrite(bytes.data(), 1, bytes.size(), fp);
+    const int rc = (w == bytes.size() && fclose(fp) == 0) ? PT_OK : PT_ERR_IO;
+    return rc;
+}
+
+int pt_write_pfm(const char* path, const float* rgba, int width, int height, int to_rgb) {
+    if (!path || !rgba || width <= 0 || height <= 0) return PT_ERR_ARG;
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return PT_ERR_IO;
+    fprintf(fp, "PF\n%d %d\n-1.0\n", width, height);
+    std::vector<float> row((size_t)width * 3);
+    bool ok = true;
+    for (int y = height - 1; y >= 0 && ok; y--) { /* PFM stores the bottom scanline first */
+        for (int x = 0; x < width; x++) {
+            const float* t = rgba + 4 * ((size_t)x + (size_t)width * (size_t)y);
+            if (to_rgb) xyz_to_linear_srgb(t, &row[3 * (size_t)x]);
+            else { row[3 * (size_t)x] = t[0]; row[3 * (size_t)x + 1] = t[1]; row[3 * (size_t)x + 2] = t[2]; }
+        }
+        ok = fwrite(row.data(), sizeof(float), row.size(), fp) == row.size();
+    }
+    if (fclose(fp) != 0) ok = false;
+    return ok ? PT_OK : PT_ERR_IO;
+}
+
+} /* extern "C" */

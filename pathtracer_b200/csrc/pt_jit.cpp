@@ -1,0 +1,132 @@
+/* pt_jit.cpp -- run-time compilation of the megakernel with the scene's SDF snippets (NVRTC -> sm_100a cubin).
+ *
+ * Stands in for the reference's GLSLToSPIRV + vkCreateComputePipelines on every scene load
+ * (host:1811-1868, 2056-2092, RecompileComputeShaders host:3836-3841).  The translation unit handed to NVRTC is
+ *     #define PT_HAS_SDF 1 [+ baked primitive counts]
+ *     #include "pt_kernel.cuh"        (embedded in the library, see tools/embed_headers.py)
+ *     <output of pt_sdf_generate()>   (snippets + SDF()/SDFMATERIAL() dispatchers)
+ *     PT_DEFINE_RENDER_KERNEL(pt_render_jit)
+ * libnvrtc is dlopen'ed so that libpt_cuda.so loads (and the static kernels run) on a box without it; compiling
+ * needs no GPU, which is how the CPU-side tests exercise this path.
+ */
+#include <dlfcn.h>
+#include <stdlib.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "pt_internal.h"
+
+namespace {
+
+typedef struct _nvrtcProgram* nvrtcProgram;
+typedef int nvrtcResult;
+
+struct Nvrtc {
+    void* h = nullptr;
+    nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*);
+    nvrtcResult (*DestroyProgram)(nvrtcProgram*);
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*);
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*);
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char*);
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*);
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char*);
+    const char* (*GetErrorString)(nvrtcResult);
+    nvrtcResult (*Version)(int*, int*);
+    std::string where;
+};
+
+Nvrtc g_nvrtc;
+std::once_flag g_once;
+std::string g_load_error;
+
+void load_nvrtc() {
+    const char* env = getenv("PT_NVRTC_LIB");
+    const char* names[] = {env ? env : "libnvrtc.so.12", "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12",
+                           "/usr/local/cuda/lib64/libnvrtc.so", "libnvrtc.so", nullptr};
+    for (int i = 0; names[i] && !g_nvrtc.h; i++) {
+        g_nvrtc.h = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);
+        if (g_nvrtc.h) g_nvrtc.where = names[i];
+    }
+    if (!g_nvrtc.h) { g_load_error = "cannot load libnvrtc.so.12 (set PT_NVRTC_LIB)"; return; }
+#define PT_SYM(field, name)                                                       \
+    *(void**)(&g_nvrtc.field) = dlsym(g_nvrtc.h, name);                            \
+    if (!g_nvrtc.field) { g_load_error = std::string("libnvrtc lacks ") + name; g_nvrtc.h = nullptr; return; }
+    PT_SYM(CreateProgram, "nvrtcCreateProgram")
+    PT_SYM(DestroyProgram, "nvrtcDestroyProgram")
+    PT_SYM(CompileProgram, "nvrtcCompileProgram")
+    PT_SYM(GetCUBINSize, "nvrtcGetCUBINSize")
+    PT_SYM(GetCUBIN, "nvrtcGetCUBIN")
+    PT_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+    PT_SYM(GetProgramLog, "nvrtcGetProgramLog")
+    PT_SYM(GetErrorString, "nvrtcGetErrorString")
+    PT_SYM(Version, "nvrtcVersion")
+#undef PT_SYM
+}
+
+}  // namespace
+
+int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::vector<char>* cubin, std::string* log) {
+    std::call_once(g_once, load_nvrtc);
+    if (!g_nvrtc.h) { *log = g_load_error; return PT_ERR_COMPILE; }
+
+    std::string src;
+    src += opt.mode == PT_MODE_FAST ? "#define PT_FAST 1\n#define PT_KERNEL_NS ptk_jit_fast\n"
+                                    : "#define PT_KERNEL_NS ptk_jit_strict\n";
+    if (!sdf_unit.empty()) src += "#define PT_HAS_SDF 1\n";
+    if (opt.bake_counts) {
+        const char* names[6] = {"PT_N_SPHERES_CONST", "PT_N_PLANES_CONST", "PT_N_BOXES_CONST", "PT_N_LENSES_CONST",
+                                "PT_N_CYCLIDES_CONST", "PT_N_SDF_CONST"};
+        for (int i = 0; i < 6; i++) src += std::string("#define ") + names[i] + " " + std::to_string(opt.counts[i]) + "\n";
+    }
+    src += "#include \"pt_kernel.cuh\"\n";
+    src += sdf_unit;
+    src += "\nPT_DEFINE_RENDER_KERNEL(pt_render_jit)\n";
+    if (!sdf_unit.empty()) src += "PT_DEFINE_SDF_EVAL_KERNEL(pt_sdf_eval_jit)\n";
+
+    std::vector<const char*> hdr_names, hdr_texts;
+    for (int i = 0; i < pt_embedded_header_count; i++) {
+        hdr_names.push_back(pt_embedded_headers[i].name);
+        hdr_texts.push_back(pt_embedded_headers[i].text);
+    }
+    nvrtcProgram prog = nullptr;
+    nvrtcResult r = g_nvrtc.CreateProgram(&prog, src.c_str(), "pt_render_jit.cu", (int)hdr_names.size(), hdr_texts.data(),
+                                          hdr_names.data());
+    if (r != 0) { *log = std::string("nvrtcCreateProgram: ") + g_nvrtc.GetErrorString(r); return PT_ERR_COMPILE; }
+
+    std::vector<const char*> o = {"--gpu-architecture=sm_100a", "--std=c++17", "-default-device", "-lineinfo"};
+    if (opt.mode == PT_MODE_FAST) {
+        o.insert(o.end(), {"--fmad=true", "--prec-div=false", "--prec-sqrt=false", "--ftz=true"});
+    } else {
+        o.insert(o.end(), {"--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false"});
+    }
+    r = g_nvrtc.CompileProgram(prog, (int)o.size(), o.data());
+    size_t ls = 0;
+    g_nvrtc.GetProgramLogSize(prog, &ls);
+    std::string plog;
+    if (ls > 1) {
+        plog.resize(ls);
+        g_nvrtc.GetProgramLog(prog, &plog[0]);
+        while (!plog.empty() && plog.back() == '\0') plog.pop_back();
+    }
+    if (r != 0) {
+        *log = std::string("NVRTC: ") + g_nvrtc.GetErrorString(r) + "\n" + plog;
+        g_nvrtc.DestroyProgram(&prog);
+        return PT_ERR_COMPILE;
+    }
+    size_t cs = 0;
+    r = g_nvrtc.GetCUBINSize(prog, &cs);
+    if (r != 0 || cs == 0) {
+        *log = "NVRTC produced no cubin";
+        g_nvrtc.DestroyProgram(&prog);
+        return PT_ERR_COMPILE;
+    }
+    cubin->resize(cs);
+    g_nvrtc.GetCUBIN(prog, cubin->data());
+    g_nvrtc.DestroyProgram(&prog);
+    *log = plog;
+    return PT_OK;
+}

@@ -1,0 +1,934 @@
+/* pt_kernel.cuh -- the spectral path-tracing megakernel for sm_100a (hand-written CUDA; no GLSL translation).
+ *
+ * One source, compiled several ways:
+ *   * nvcc, PT_MODE_STRICT: -fmad=false -prec-div=true -prec-sqrt=true -ftz=false, transcendentals from pt_math.h.
+ *     Bit-exact against the CPU oracle (oracle/oracle.cpp), which is the parity gate.
+ *   * nvcc, PT_FAST: fma contraction, approximate division/sqrt, MUFU sin/cos/ex2/lg2.  The throughput build.
+ *   * NVRTC (pt_jit.cpp), either mode, with the scene's SDF snippets spliced in (PT_HAS_SDF) and optionally the
+ *     primitive counts baked in as compile-time constants (PT_N_*), so the intersection loops unroll and every
+ *     scene constant becomes an immediate constant-bank operand.
+ *
+ * What the kernel computes is the reference's shader.comp main() (shader.comp:1525-1533): per pixel,
+ * samplesPerFrame calls of Scene() (camera ray through the BK7 lens, hero-wavelength bundle, path tracing with
+ * MIS light sampling and Russian roulette, CIE XYZ projection), the exposure scale and Accumulate().
+ * Function names follow the shader; each carries the shader.comp lines it implements.
+ *
+ * How it differs from a transliteration (all of it result-preserving; see DESIGN.md "Kernel"):
+ *   - per-object constants (rotation matrices, lens cap geometry, bounding radii, camera basis, light sampling
+ *     cascade) arrive precomputed in constant memory (pt_dev_scene.h) instead of being rebuilt per ray;
+ *   - the shadow ray (LightSourceVisibilityCheck) shares the intersection code but skips normals and materials,
+ *     which it never uses; sphere tracing for it skips the 6 normal probes and the material evaluation;
+ *   - EvaluateBRDF's spectral term is evaluated once per bounce and reused for the light sample;
+ *   - the CIE table and the material/light tables are staged in shared memory (divergent indices);
+ *   - a warp covers an 8x4 pixel tile so primary rays stay coherent.
+ */
+#ifndef PT_KERNEL_CUH
+#define PT_KERNEL_CUH
+
+#include "pt_math.h"
+#include "pt_dev_scene.h"
+
+#ifndef PT_BLOCK_THREADS
+#define PT_BLOCK_THREADS 128
+#endif
+#ifndef PT_MIN_BLOCKS
+#define PT_MIN_BLOCKS 4
+#endif
+#ifndef PT_HAS_SDF
+#define PT_HAS_SDF 0
+#endif
+
+#define PT_DEV __device__ __forceinline__
+#define PT_DEV_NOINLINE __device__ __noinline__
+
+#define PT_CIE_FLOATS 1323
+
+/* primitive counts: compile-time constants when the JIT bakes them in, else fields of the scene */
+#ifdef PT_N_SPHERES_CONST
+#define PT_N_SPHERES(c) (PT_N_SPHERES_CONST)
+#define PT_N_PLANES(c) (PT_N_PLANES_CONST)
+#define PT_N_BOXES(c) (PT_N_BOXES_CONST)
+#define PT_N_LENSES(c) (PT_N_LENSES_CONST)
+#define PT_N_CYCLIDES(c) (PT_N_CYCLIDES_CONST)
+#define PT_N_SDF(c) (PT_N_SDF_CONST)
+#define PT_UNROLL_PRIMS _Pragma("unroll")
+#else
+#define PT_N_SPHERES(c) ((c).sc->nSpheres)
+#define PT_N_PLANES(c) ((c).sc->nPlanes)
+#define PT_N_BOXES(c) ((c).sc->nBoxes)
+#define PT_N_LENSES(c) ((c).sc->nLenses)
+#define PT_N_CYCLIDES(c) ((c).sc->nCyclides)
+#define PT_N_SDF(c) ((c).sc->nSdfs)
+#define PT_UNROLL_PRIMS
+#endif
+
+/* ---- mode-dependent primitives ------------------------------------------------------------------------------ */
+#ifdef PT_FAST
+#define PTK_SIN(x) __sinf(x)
+#define PTK_COS(x) __cosf(x)
+#define PTK_ACOS(x) acosf(x)
+#define PTK_EXP(x) __expf(x)
+#define PTK_POW(x, y) __powf(x, y)
+#define PTK_SQRT(x) sqrtf(x)
+#define PTK_DIV(a, b) __fdividef(a, b)
+#define PTK_MIN(x, y) fminf(x, y)
+#define PTK_MAX(x, y) fmaxf(x, y)
+#else
+#define PTK_SIN(x) pt_sin(x)
+#define PTK_COS(x) pt_cos(x)
+#define PTK_ACOS(x) pt_acos(x)
+#define PTK_EXP(x) pt_exp(x)
+#define PTK_POW(x, y) pt_pow(x, y)
+#define PTK_SQRT(x) sqrtf(x)          /* IEEE with -prec-sqrt=true */
+#define PTK_DIV(a, b) ((a) / (b))     /* IEEE with -prec-div=true */
+#define PTK_MIN(x, y) (((y) < (x)) ? (y) : (x)) /* GLSL min/max, NaN behaviour included */
+#define PTK_MAX(x, y) (((x) < (y)) ? (y) : (x))
+#endif
+
+#if PT_HAS_SDF
+/* provided by the generated translation unit (pt_sdf_front.cpp): the dispatchers InsertSDF builds (host:2004-2054) */
+__device__ float pt_sdf_dispatch(float px, float py, float pz, unsigned set1);
+__device__ float pt_sdfmaterial_dispatch(float px, float py, float pz, unsigned set1);
+#endif
+
+namespace PT_KERNEL_NS {
+
+struct V3 { float x, y, z; };
+struct V4 { float x, y, z, w; };
+
+PT_DEV V3 mk3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+PT_DEV V4 mk4(float x, float y, float z, float w) { V4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+PT_DEV V3 operator+(V3 a, V3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+PT_DEV V3 operator-(V3 a, V3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+PT_DEV V3 operator*(V3 a, V3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+PT_DEV V3 operator*(V3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+PT_DEV V3 operator*(float s, V3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
+PT_DEV V3 operator-(V3 a) { return mk3(-a.x, -a.y, -a.z); }
+PT_DEV V3 div3(V3 a, V3 b) { return mk3(PTK_DIV(a.x, b.x), PTK_DIV(a.y, b.y), PTK_DIV(a.z, b.z)); }
+PT_DEV V3 div3(V3 a, float s) { return mk3(PTK_DIV(a.x, s), PTK_DIV(a.y, s), PTK_DIV(a.z, s)); }
+PT_DEV V4 operator+(V4 a, V4 b) { return mk4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+PT_DEV V4 operator*(V4 a, V4 b) { return mk4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+PT_DEV V4 operator*(V4 a, float s) { return mk4(a.x * s, a.y * s, a.z * s, a.w * s); }
+PT_DEV float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+PT_DEV float length(V3 a) { return PTK_SQRT(dot(a, a)); }
+PT_DEV V3 normalize(V3 a) { return div3(a, length(a)); }
+PT_DEV V3 fma3(V3 a, float t, V3 c) { return mk3(fmaf(a.x, t, c.x), fmaf(a.y, t, c.y), fmaf(a.z, t, c.z)); }
+PT_DEV float gsign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
+PT_DEV float gstep(float e, float x) { return (x < e) ? 0.0f : 1.0f; }
+/* v * M (row vector times column-major matrix): component j = dot(v, column j) */
+PT_DEV V3 mulVM(V3 v, const float* m) {
+    return mk3(v.x * m[0] + v.y * m[1] + v.z * m[2], v.x * m[3] + v.y * m[4] + v.z * m[5],
+               v.x * m[6] + v.y * m[7] + v.z * m[8]);
+}
+/* M * v = col0*v.x + col1*v.y + col2*v.z */
+PT_DEV V3 mulMV(const float* m, V3 v) {
+    return mk3(m[0] * v.x + m[3] * v.y + m[6] * v.z, m[1] * v.x + m[4] * v.y + m[7] * v.z,
+               m[2] * v.x + m[5] * v.y + m[8] * v.z);
+}
+
+struct Ray { V3 origin, dir; };
+
+/* Everything a thread needs besides its registers */
+struct Ctx {
+    const PtDevScene* sc;   /* constant bank (kernel parameter) */
+    const PtDevParams* pr;  /* constant bank (kernel parameter) */
+    const float* ubo;       /* global: flat copy of the 4097-float uniform block */
+    const float* s_tab;     /* shared: ubo[PT_SH_BASE .. 4097) */
+};
+
+#define PT_SH_BASE (PT_OFF_MAT - 3) /* materials[-3..] (material index -1) up to the end of the CIE table */
+#define PT_SH_FLOATS (PT_UBO_FLOATS - PT_SH_BASE)
+
+/* clamped flat read of the uniform block: same rule as oracle Shader::at() */
+PT_DEV float uboAt(const Ctx& c, int flat) {
+    flat = flat < 0 ? 0 : (flat > PT_UBO_FLOATS - 1 ? PT_UBO_FLOATS - 1 : flat);
+    if (flat >= PT_SH_BASE) return c.s_tab[flat - PT_SH_BASE];
+    return __ldg(c.ubo + flat);
+}
+
+/* ---- RNG (shader.comp:937-958): pure uint32 arithmetic, bit-exact ------------------------------------------------ */
+PT_DEV void PCG32(unsigned& seed) {
+    unsigned state = seed * 747796405u + 2891336453u;
+    unsigned word = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
+    seed = (word >> 22u) ^ word;
+}
+PT_DEV float RandomFloatPCG32(unsigned& seed) {
+    PCG32(seed);
+    return __uint2float_rn(seed) * 2.3283064365386963e-10f; /* float(seed) / 2^32: exact scaling */
+}
+
+/* ---- spectral helpers ------------------------------------------------------------------------------------------ */
+/* shader.comp:129-140 */
+PT_DEV V3 WaveToXYZ(const Ctx& c, float wave) {
+    V3 XYZ = mk3(0.0f, 0.0f, 0.0f);
+    if ((wave >= 360.0f) && (wave <= 800.0f)) {
+        const float fl = floorf(wave);
+        const int index3 = 3 * __float2int_rz(fl - 360.0f);
+        const float a = wave - fl;
+        const float oma = 1.0f - a;
+        const float* t = c.s_tab + (PT_OFF_CIE - PT_SH_BASE) + index3; /* index3 in [0, 1320]; +5 stays in range for wave < 800 */
+        if (index3 + 5 < PT_CIE_FLOATS) {
+            XYZ = mk3(t[0] * oma + t[3] * a, t[1] * oma + t[4] * a, t[2] * oma + t[5] * a);
+        } else { /* wave == 800: reads clamp at the end of the block like the oracle */
+            const int b = PT_OFF_CIE + index3;
+            XYZ = mk3(uboAt(c, b) * oma + uboAt(c, b + 3) * a, uboAt(c, b + 1) * oma + uboAt(c, b + 4) * a,
+                      uboAt(c, b + 2) * oma + uboAt(c, b + 5) * a);
+        }
+    }
+    return XYZ;
+}
+
+/* shader.comp:971-974 */
+PT_DEV float gmod330(float x) { return x - 330.0f * floorf(PTK_DIV(x, 330.0f)); }
+PT_DEV V4 SampleWavelengths(float l_h) {
+    const float b = l_h - 390.0f;
+    return mk4(390.0f + gmod330(b + 82.5f), 390.0f + gmod330(b + 165.0f), 390.0f + gmod330(b + 247.5f),
+               390.0f + gmod330(b + 330.0f));
+}
+
+/* shader.comp:1030-1038 with EvaluateBRDF's "/ PI" (1075-1080): f = SPD / PI for the four wavelengths */
+PT_DEV V4 EvaluateBRDF(V4 l, float peak, float sigma, float invertf) {
+    const float den = 2.0f * sigma * sigma;
+    const float a = (float)__float2int_rz(invertf); /* int(mat.reflection.z) -> float for mix() */
+    const float oma = 1.0f - a;
+    float r[4];
+    const float lv[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float x = PTK_DIV(lv[i] - peak, den);
+        const float e = PTK_EXP(-x * x);
+        r[i] = PTK_DIV(e * oma + (1.0f - e) * a, PT_PI_F);
+    }
+    return mk4(r[0], r[1], r[2], r[3]);
+}
+
+/* shader.comp:1040-1055.  temperature/luminosity already clamped by max(., 0). */
+PT_DEV V4 Emit(V4 l, float temperature, float luminosity) {
+    const float peak = 4.0956746759e-6f * PTK_POW(temperature, 5.0f);
+    float r[4];
+    const float lv[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float lm = lv[i] * 1e-9f;
+        const float num = 1.1910429724e-16f * PTK_POW(lm, -5.0f);
+        const float den = PTK_EXP(PTK_DIV(0.014387768775f, lm * temperature)) - 1.0f;
+        r[i] = PTK_DIV(PTK_DIV(num, den), peak) * luminosity;
+    }
+    return mk4(r[0], r[1], r[2], r[3]);
+}
+
+/* shader.comp:1064-1073 */
+PT_DEV float RefractiveIndexBK7Glass(float l) {
+    l *= 1e-3f;
+    const float l2 = l * l;
+    float n2 = 1.0f;
+    n2 += PTK_DIV(1.03961212f * l2, l2 - 6.00069867e-3f);
+    n2 += PTK_DIV(0.231792344f * l2, l2 - 2.00179144e-2f);
+    n2 += PTK_DIV(1.01046945f * l2, l2 - 1.03560653e2f);
+    return PTK_SQRT(n2);
+}
+
+/* shader.comp:216-235: material / light lookup through the flat uniform block */
+PT_DEV void GetMaterialMix(const Ctx& c, float materialID, float& peak, float& sigma, float& invertf) {
+    const float fl = floorf(materialID);
+    const int i1 = 3 * __float2int_rz(fl);
+    const int i2 = 3 * __float2int_rz(ceilf(materialID));
+    const float x = materialID - fl;
+    const float omx = 1.0f - x;
+    peak = uboAt(c, PT_OFF_MAT + i1) * omx + uboAt(c, PT_OFF_MAT + i2) * x;
+    sigma = uboAt(c, PT_OFF_MAT + i1 + 1) * omx + uboAt(c, PT_OFF_MAT + i2 + 1) * x;
+    invertf = uboAt(c, PT_OFF_MAT + i1 + 2) * omx + uboAt(c, PT_OFF_MAT + i2 + 2) * x;
+}
+PT_DEV void GetLightMix(const Ctx& c, float lightID, float& temperature, float& luminosity) {
+    const int index = __float2int_rz(lightID);
+    if (index == -1) {
+        temperature = 5500.0f;
+        luminosity = 0.0f;
+        return;
+    }
+    temperature = uboAt(c, PT_OFF_LGT + 2 * index);
+    luminosity = uboAt(c, PT_OFF_LGT + 2 * index + 1);
+}
+
+/* ---- hit record -------------------------------------------------------------------------------------------- */
+struct Hit {
+    float t;          /* hitdist */
+    V3 normal;
+    float materialID;
+    float lightID;
+    int objectID;     /* global object index (LightSourceVisibilityCheck, shader.comp:1127) */
+};
+
+/* shader.comp:263-276 */
+PT_DEV bool BoundingSphere(const Ray& ray, float px, float py, float pz, float radius2) {
+    const V3 lo = mk3(ray.origin.x - px, ray.origin.y - py, ray.origin.z - pz);
+    const float b = dot(ray.dir, lo);
+    const float cc = dot(lo, lo) - radius2;
+    if ((b * b) < cc) return false;
+    if ((b >= 0.0f) && (cc >= 0.0f)) return false;
+    return true;
+}
+
+/* shader.comp:289-317 */
+template <bool kShadow>
+PT_DEV void SphereIntersection(const Ray& ray, const PtDevSphere& o, int objectID, Hit& h) {
+    const V3 lo = mk3(ray.origin.x - o.px, ray.origin.y - o.py, ray.origin.z - o.pz);
+    const float b = 2.0f * dot(ray.dir, lo);
+    const float cc = dot(lo, lo) - o.r2;
+    const float discriminant = b * b - 4.0f * cc;
+    if (discriminant < 0.0f) return;
+    const float sqrtD = PTK_SQRT(discriminant);
+    const float t1 = (-b - sqrtD) * 0.5f;
+    const float t2 = (-b + sqrtD) * 0.5f;
+    const float t = (t1 > 0.0f) ? t1 : t2;
+    if (t < 1e-4f) return;
+    if (t < h.t) {
+        h.t = t;
+        h.objectID = objectID;
+        if (!kShadow) {
+            const float isOutside = (t1 > 0.0f) ? 1.0f : -1.0f;
+            h.normal = normalize(fma3(ray.dir, t, lo) * isOutside);
+            h.materialID = o.materialID;
+            h.lightID = o.lightID;
+        }
+    }
+}
+
+/* shader.comp:319-335 */
+template <bool kShadow>
+PT_DEV void PlaneIntersection(const Ray& ray, const PtDevPlane& o, int objectID, Hit& h) {
+    const float loy = ray.origin.y - o.py;
+    const float t = PTK_DIV(-loy, ray.dir.y);
+    if (t < 1e-4f) return;
+    if (t < h.t) {
+        h.t = t;
+        h.objectID = objectID;
+        if (!kShadow) {
+            /* faceforward((0,1,0), dir, (0,1,0)): dot(Nref, I) = 0*dx + 1*dy + 0*dz */
+            const float d = 0.0f * ray.dir.x + 1.0f * ray.dir.y + 0.0f * ray.dir.z;
+            h.normal = (d < 0.0f) ? mk3(0.0f, 1.0f, 0.0f) : mk3(-0.0f, -1.0f, -0.0f);
+            h.materialID = o.materialID;
+            h.lightID = o.lightID;
+        }
+    }
+}
+
+/* shader.comp:337-364 */
+template <bool kShadow>
+PT_DEV void BoxIntersection(const Ray& ray, const PtDevBox& o, int objectID, Hit& h) {
+    const V3 lo = mulVM(mk3(ray.origin.x - o.px, ray.origin.y - o.py, ray.origin.z - o.pz), o.m);
+    const V3 dir = mulVM(ray.dir, o.m);
+    const V3 invdir = mk3(PTK_DIV(1.0f, dir.x), PTK_DIV(1.0f, dir.y), PTK_DIV(1.0f, dir.z));
+    const V3 a = mk3(fmaf(o.sx, -0.5f, -lo.x) * invdir.x, fmaf(o.sy, -0.5f, -lo.y) * invdir.y,
+                     fmaf(o.sz, -0.5f, -lo.z) * invdir.z);
+    const V3 b = mk3(fmaf(o.sx, 0.5f, -lo.x) * invdir.x, fmaf(o.sy, 0.5f, -lo.y) * invdir.y,
+                     fmaf(o.sz, 0.5f, -lo.z) * invdir.z);
+    const V3 tMin = mk3(PTK_MIN(a.x, b.x), PTK_MIN(a.y, b.y), PTK_MIN(a.z, b.z));
+    const V3 tMax = mk3(PTK_MAX(a.x, b.x), PTK_MAX(a.y, b.y), PTK_MAX(a.z, b.z));
+    const float t1 = PTK_MAX(PTK_MAX(tMin.x, tMin.y), tMin.z);
+    const float t2 = PTK_MIN(PTK_MIN(tMax.x, tMax.y), tMax.z);
+    const float t = (t1 < 0.0f) ? t2 : t1;
+    if ((t1 > t2) || (t < 1e-4f)) return;
+    if (t < h.t) {
+        h.t = t;
+        h.objectID = objectID;
+        if (!kShadow) {
+            const V3 p = mk3(fabsf(PTK_DIV(lo.x + dir.x * t, o.sx)), fabsf(PTK_DIV(lo.y + dir.y * t, o.sy)),
+                             fabsf(PTK_DIV(lo.z + dir.z * t, o.sz)));
+            const float pm = PTK_MAX(PTK_MAX(p.x, p.y), p.z);
+            const V3 n = mk3(gstep(pm, p.x) * -gsign(dir.x), gstep(pm, p.y) * -gsign(dir.y),
+                             gstep(pm, p.z) * -gsign(dir.z));
+            h.normal = mulMV(o.m, n);
+            h.materialID = o.materialID;
+            h.lightID = o.lightID;
+        }
+    }
+}
+
+/* shader.comp:366-417 for one cap; returns true when it became the closest hit */
+template <bool kShadow>
+PT_DEV bool SphereSliceIntersection(const V3& lo0, const V3& ldir, const PtDevLens& o, bool is1stSlice, int objectID,
+                                    Hit& h, int& isOutside) {
+    V3 lo = lo0;
+    if (is1stSlice) lo.x += o.shift; else lo.x -= o.shift;
+    const float b = 2.0f * dot(ldir, lo);
+    const float cc = dot(lo, lo) - o.sradius2;
+    const float discriminant = b * b - 4.0f * cc;
+    if (discriminant < 0.0f) return false;
+    const float sqrtD = PTK_SQRT(discriminant);
+    float t1 = (-b - sqrtD) * 0.5f;
+    float t2 = (-b + sqrtD) * 0.5f;
+    if (is1stSlice) {
+        t1 = (fmaf(ldir.x, t1, lo.x) > -o.sliceOffset) ? 1e6f : t1;
+        t2 = (fmaf(ldir.x, t2, lo.x) > -o.sliceOffset) ? 1e6f : t2;
+    } else {
+        t1 = (fmaf(ldir.x, t1, lo.x) < o.sliceOffset) ? 1e6f : t1;
+        t2 = (fmaf(ldir.x, t2, lo.x) < o.sliceOffset) ? 1e6f : t2;
+    }
+    float t = (t1 > 0.0f) ? t1 : 1e6f;
+    int isOut = 1;
+    if (t2 < t) {
+        t = t2;
+        isOut = -1;
+    }
+    if (t < 1e-4f) return false;
+    if (t < h.t) {
+        h.t = t;
+        h.objectID = objectID;
+        if (!kShadow) {
+            h.normal = mulMV(o.m, normalize(fma3(ldir, t, lo) * (float)isOut));
+            isOutside = (o.invertSide == 0.0f) ? isOut : -isOut;
+            h.materialID = o.materialID;
+            h.lightID = o.lightID;
+        }
+        return true;
+    }
+    return false;
+}
+
+/* shader.comp:419-448 */
+template <bool kShadow>
+PT_DEV void LensIntersection(const Ray& ray, const PtDevLens& o, int objectID, Hit& h, int& isOutside) {
+    const V3 lo = mulVM(mk3(ray.origin.x - o.px, ray.origin.y - o.py, ray.origin.z - o.pz), o.m);
+    const V3 ldir = mulVM(ray.dir, o.m);
+    SphereSliceIntersection<kShadow>(lo, ldir, o, true, objectID, h, isOutside);
+    SphereSliceIntersection<kShadow>(lo, ldir, o, false, objectID, h, isOutside);
+}
+
+/* ---- Dupin cyclide (shader.comp:450-541, 633-679) ------------------------------------------------------------ */
+PT_DEV float EvalCubic1(float b, float c, float d, float x) { return x * (x * (x * 1.0f + b) + c) + d; }
+PT_DEV float EvalQuadratic3(float b2, float c, float x) { return x * (x * 3.0f + b2) + c; }
+
+/* shader.comp:474-503: only roots.x is consumed by SolveQuartic, so only it is returned (the other two roots of
+ * the three-real-root branch never influence anything). */
+PT_DEV float SolveCubicFirstRoot(float b, float c, float d) {
+    const float ONEBYTHREE = 0.3333333f;
+    const float bdiv3 = b * ONEBYTHREE;
+    const float Q = c * ONEBYTHREE - bdiv3 * bdiv3;
+    const float R = 0.5f * bdiv3 * c - bdiv3 * bdiv3 * bdiv3 - 0.5f * d;
+    const float D = Q * Q * Q + R * R;
+    float root;
+    if (D > 0.0f) {
+        const float sD = PTK_SQRT(D);
+        const float u = R + sD;
+        const float v = R - sD;
+        const float S = gsign(u) * PTK_POW(fabsf(u), ONEBYTHREE);
+        const float T = gsign(v) * PTK_POW(fabsf(v), ONEBYTHREE);
+        root = S + T - bdiv3;
+    } else {
+        const float sqrtnegQ = PTK_SQRT(-Q);
+        const float thetadiv3 = PTK_ACOS(PTK_DIV(R, sqrtnegQ * sqrtnegQ * sqrtnegQ)) * ONEBYTHREE;
+        root = 2.0f * sqrtnegQ * PTK_COS(thetadiv3) - bdiv3;
+    }
+    const float b2 = 2.0f * b;
+#pragma unroll
+    for (int i = 0; i < 2; i++) root -= PTK_DIV(EvalCubic1(b, c, d, root), EvalQuadratic3(b2, c, root));
+    return root;
+}
+
+PT_DEV float QuarticNewton(float a, float b, float c, float d, float e, float a4, float b3, float c2, float x) {
+    const float q = x * (x * (x * (x * a + b) + c) + d) + e;
+    const float dq = x * (x * (x * a4 + b3) + c2) + d;
+    return x - PTK_DIV(q, dq);
+}
+
+/* shader.comp:505-541 + the root selection of 648-655: smallest positive real root, or 1e6 */
+PT_DEV float SolveQuarticNearest(float a, float b, float c, float d, float e) {
+    const float inva = PTK_DIV(1.0f, a);
+    const float inva2 = inva * 0.5f;
+    const float inva2a2 = inva2 * inva2;
+    const float bb = b * b;
+    const float p = -1.5f * bb * inva2a2 + c * inva;
+    const float q = bb * b * inva2a2 * inva2 - b * c * inva * inva2 + d * inva;
+    const float r = -0.1875f * bb * bb * inva2a2 * inva2a2 + 0.5f * c * bb * inva2a2 * inva2 - b * d * inva2a2 + e * inva;
+    const float sx = SolveCubicFirstRoot(0.5f * -p, -r, 0.5f * p * r - 0.125f * q * q);
+    const float s2subp = 2.0f * sx - p;
+    float t = 1e6f;
+    if (s2subp < 0.0f) return t;
+    const float invs2subp = -2.0f * sx - p;
+    const float sqrts2subp = PTK_SQRT(s2subp);
+    const float q2divsqrt = PTK_DIV(2.0f * q, sqrts2subp);
+    const float invaddq2div = invs2subp + q2divsqrt;
+    const float invsubq2div = invs2subp - q2divsqrt;
+    const float bdiv4a = 0.25f * inva * b;
+    const float a4 = 4.0f * a, b3 = 3.0f * b, c2 = 2.0f * c;
+    if (invaddq2div >= 0.0f) {
+        const float sq = PTK_SQRT(invaddq2div);
+        const float r0 = QuarticNewton(a, b, c, d, e, a4, b3, c2, 0.5f * (-sqrts2subp + 1.0f * sq) - bdiv4a);
+        const float r1 = QuarticNewton(a, b, c, d, e, a4, b3, c2, 0.5f * (-sqrts2subp + -1.0f * sq) - bdiv4a);
+        if ((r0 < t) && (r0 > 0.0f)) t = r0;
+        if ((r1 < t) && (r1 > 0.0f)) t = r1;
+    }
+    if (invsubq2div >= 0.0f) {
+        const float sq = PTK_SQRT(invsubq2div);
+        const float r2 = QuarticNewton(a, b, c, d, e, a4, b3, c2, 0.5f * (sqrts2subp + 1.0f * sq) - bdiv4a);
+        const float r3 = QuarticNewton(a, b, c, d, e, a4, b3, c2, 0.5f * (sqrts2subp + -1.0f * sq) - bdiv4a);
+        if ((r2 < t) && (r2 > 0.0f)) t = r2;
+        if ((r3 < t) && (r3 > 0.0f)) t = r3;
+    }
+    return t;
+}
+
+/* shader.comp:633-679 */
+template <bool kShadow>
+PT_DEV_NOINLINE void DupinCyclide(const Ray& ray, const PtDevCyclide& ob, int objectID, Hit& h) {
+    const V3 lo = mulVM(mk3(ray.origin.x - ob.px, ray.origin.y - ob.py, ray.origin.z - ob.pz), ob.m);
+    const V3 ld = mulVM(ray.dir, ob.m);
+    /* .xzy swizzle after the divide by scale */
+    const V3 o = mk3(PTK_DIV(lo.x, ob.sx), PTK_DIV(lo.z, ob.sz), PTK_DIV(lo.y, ob.sy));
+    const V3 d = mk3(PTK_DIV(ld.x, ob.sx), PTK_DIV(ld.z, ob.sz), PTK_DIV(ld.y, ob.sy));
+    const float A = ob.a, B = ob.b, C = ob.c, D = ob.d;
+    const V3 dd = d * d, oo = o * o, od = o * d;
+    const V3 dyzx = mk3(d.y, d.z, d.x), dzxy = mk3(d.z, d.x, d.y);
+    const V3 oyzx = mk3(o.y, o.z, o.x), ozxy = mk3(o.z, o.x, o.y);
+    const V3 dyzx2 = dyzx * dyzx, dzxy2 = dzxy * dzxy;
+    const float BBmDD = B * B - D * D;
+    const float a4 = dot(dd, dd) + 2.0f * dot(dd, dyzx2);
+    const float a3 = 4.0f * (dot(o, dd * d) + dot(od, dyzx2) + dot(od, dzxy2));
+    const float a2 = 6.0f * dot(oo, dd) + 8.0f * dot(od, oyzx * dyzx) + 2.0f * (dot(oo, dyzx2) + dot(oo, dzxy2)) +
+                     2.0f * BBmDD * dot(d, d) - 4.0f * (A * A * d.x * d.x + B * B * d.y * d.y);
+    const float a1 = 4.0f * (dot(oo * o, d) + dot(oo, oyzx * dyzx) + dot(oo, ozxy * dzxy) + 2.0f * A * C * D * d.x +
+                             BBmDD * dot(o, d) - 2.0f * (A * A * o.x * d.x + B * B * o.y * d.y));
+    const float a0 = dot(oo, oo) + 2.0f * dot(oo, oyzx * oyzx) + B * B * B * B + D * D * D * D - 2.0f * B * B * D * D -
+                     4.0f * C * C * D * D + 8.0f * A * C * D * o.x + 2.0f * BBmDD * dot(o, o) -
+                     4.0f * (A * A * o.x * o.x + B * B * o.y * o.y);
+    const float t = SolveQuarticNearest(a4, a3, a2, a1, a0);
+    if (t < h.t) {
+        h.t = t;
+        h.objectID = objectID;
+        if (!kShadow) {
+            const float x = o.x + d.x * t;
+            const float y = o.y + d.y * t;
+            const float z = o.z + d.z * t;
+            const float term1 = x * x + y * y + z * z + B * B - D * D;
+            V3 n;
+            n.x = 4.0f * (x * term1 - 2.0f * A * (A * x - C * D));
+            n.y = 4.0f * z * term1;
+            n.z = 4.0f * y * (term1 - 2.0f * B * B);
+            h.normal = normalize(n);
+            h.materialID = ob.materialID;
+            h.lightID = ob.lightID;
+        }
+    }
+}
+
+/* ---- SDF sphere tracing (shader.comp:704-860) ------------------------------------------------------------------ */
+#if PT_HAS_SDF
+PT_DEV float SDF(V3 p, unsigned set1) { return ::pt_sdf_dispatch(p.x, p.y, p.z, set1); }
+
+/* shader.comp:278-287 with box = SDF bounding box */
+PT_DEV void RayIntersectAABB(V3 origin, V3 invdir, const PtDevSdf& s, float& t1, float& t2) {
+    const V3 lo = mk3(origin.x - s.px, origin.y - s.py, origin.z - s.pz);
+    const V3 a = mk3(fmaf(s.sx, -0.5f, -lo.x) * invdir.x, fmaf(s.sy, -0.5f, -lo.y) * invdir.y,
+                     fmaf(s.sz, -0.5f, -lo.z) * invdir.z);
+    const V3 b = mk3(fmaf(s.sx, 0.5f, -lo.x) * invdir.x, fmaf(s.sy, 0.5f, -lo.y) * invdir.y,
+                     fmaf(s.sz, 0.5f, -lo.z) * invdir.z);
+    t1 = PTK_MAX(PTK_MAX(PTK_MIN(a.x, b.x), PTK_MIN(a.y, b.y)), PTK_MIN(a.z, b.z));
+    t2 = PTK_MIN(PTK_MIN(PTK_MAX(a.x, b.x), PTK_MAX(a.y, b.y)), PTK_MAX(a.z, b.z));
+}
+
+/* shader.comp:732-777 */
+PT_DEV bool SearchSDF(const Ctx& c, V3 p, V3 invdir, float& tMin, float& tMax, unsigned& set1) {
+    bool isFoundSDF = false;
+    set1 = 0u;
+    const int n = PT_N_SDF(c);
+    for (int i = 0; i < n; i++) {
+        float bx, by;
+        RayIntersectAABB(p, invdir, c.sc->sdfs[i], bx, by);
+        if ((bx > by) || (by < 0.0f)) continue;
+        const unsigned bit = 1u << (unsigned)i;
+        if (bx < tMin) {
+            isFoundSDF = true;
+            if (by < tMin) {
+                tMin = bx; tMax = by;
+                set1 = bit;
+            } else {
+                if (by < tMax) {
+                    tMin = bx;
+                    set1 += bit;
+                } else {
+                    tMin = bx; tMax = by;
+                    set1 += bit;
+                }
+            }
+        } else {
+            if (bx < tMax) {
+                isFoundSDF = true;
+                if (by > tMax) tMax = by;
+                set1 += bit;
+            }
+        }
+    }
+    return isFoundSDF;
+}
+
+/* shader.comp:779-860.  For shadow rays the normal probes and the material are skipped (never read). */
+template <bool kShadow>
+PT_DEV_NOINLINE void SphereTracing(const Ctx& c, const Ray& ray, Hit& h) {
+    const float MAXDIST = 1e5f;
+    float t = 1e-3f;
+    float insT = 0.0f;
+    const float omegaMax = 1.70f;
+    const float omegaSpeed = 0.20f;
+    float omega = omegaMax;
+    float previousRadius = 0.0f;
+    V3 p = ray.origin;
+    const V3 invdir = mk3(PTK_DIV(1.0f, ray.dir.x), PTK_DIV(1.0f, ray.dir.y), PTK_DIV(1.0f, ray.dir.z));
+    int points = 0;
+    float tMin = MAXDIST, tMax = MAXDIST;
+    unsigned set1 = 0u;
+    if (SearchSDF(c, p, invdir, tMin, tMax, set1)) {
+        t = PTK_MAX(tMin, t);
+        p = fma3(ray.dir, t, ray.origin);
+    } else {
+        return;
+    }
+    const float k = gsign(SDF(ray.origin, set1));
+
+    for (int i = 0; i < 512; i++) {
+        const float radius = SDF(p, set1);
+        if (insT > (fabsf(previousRadius) + fabsf(radius))) {
+            t -= insT;
+            omega = 1.0f;
+            insT = previousRadius * omega * k;
+            t += insT;
+            p = fma3(ray.dir, t, ray.origin);
+            continue;
+        }
+        if (fabsf(radius) < 1e-4f) break;
+        if (t > tMax) points += 1; else points = 0;
+        if (points >= 2) {
+            t = tMax + 1e-3f;
+            tMin = MAXDIST; tMax = MAXDIST;
+            if (SearchSDF(c, fma3(ray.dir, t, ray.origin), invdir, tMin, tMax, set1)) {
+                tMin += t; tMax += t;
+                t = PTK_MAX(tMin, t);
+                p = fma3(ray.dir, t, ray.origin);
+                continue;
+            } else {
+                return;
+            }
+        }
+        insT = radius * omega * k;
+        t += insT;
+        p = fma3(ray.dir, t, ray.origin);
+        const float omegaSpeedFactor = PTK_MIN(PTK_DIV(radius, previousRadius), 0.99f);
+        omega += omegaSpeed * (PTK_MIN(PTK_DIV(1.0f, 1.0f - omegaSpeedFactor), omegaMax) - omega);
+        previousRadius = radius;
+    }
+
+    if (t < h.t) {
+        h.t = t - 1e-3f;
+        h.objectID = -1;
+        if (!kShadow) {
+            p = fma3(ray.dir, t, ray.origin);
+            const float e = 1e-4f; /* shader.comp:721-730 */
+            const float nx = SDF(mk3(p.x + e, p.y + 0.0f, p.z + 0.0f), set1) - SDF(mk3(p.x - e, p.y - 0.0f, p.z - 0.0f), set1);
+            const float ny = SDF(mk3(p.x + 0.0f, p.y + e, p.z + 0.0f), set1) - SDF(mk3(p.x - 0.0f, p.y - e, p.z - 0.0f), set1);
+            const float nz = SDF(mk3(p.x + 0.0f, p.y + 0.0f, p.z + e), set1) - SDF(mk3(p.x - 0.0f, p.y - 0.0f, p.z - e), set1);
+            h.normal = normalize(mk3(nx, ny, nz));
+            h.materialID = ::pt_sdfmaterial_dispatch(p.x, p.y, p.z, set1);
+            h.lightID = -1.0f;
+        }
+    }
+}
+#endif /* PT_HAS_SDF */
+
+/* shader.comp:862-934 (kShadow = false) and 1121-1216 (kShadow = true): brute-force closest hit in type order */
+template <bool kShadow>
+PT_DEV void Intersection(const Ctx& c, const Ray& ray, Hit& h) {
+    const PtDevScene& sc = *c.sc;
+    h.t = 1e5f;
+    h.objectID = -1;
+    if (!kShadow) {
+        h.normal = mk3(0.0f, 0.0f, 0.0f);
+        h.materialID = 0.0f;
+        h.lightID = -1.0f;
+    }
+    int base = 0;
+    const int nS = PT_N_SPHERES(c);
+    PT_UNROLL_PRIMS
+    for (int i = 0; i < nS; i++) SphereIntersection<kShadow>(ray, sc.spheres[i], base + i, h);
+    base += nS;
+    const int nP = PT_N_PLANES(c);
+    PT_UNROLL_PRIMS
+    for (int i = 0; i < nP; i++) PlaneIntersection<kShadow>(ray, sc.planes[i], base + i, h);
+    base += nP;
+    const int nB = PT_N_BOXES(c);
+    PT_UNROLL_PRIMS
+    for (int i = 0; i < nB; i++) {
+        const PtDevBox& o = sc.boxes[i];
+        if (!BoundingSphere(ray, o.px, o.py, o.pz, o.bound2)) continue;
+        BoxIntersection<kShadow>(ray, o, base + i, h);
+    }
+    base += nB;
+    const int nL = PT_N_LENSES(c);
+    PT_UNROLL_PRIMS
+    for (int i = 0; i < nL; i++) {
+        const PtDevLens& o = sc.lenses[i];
+        if (!BoundingSphere(ray, o.px, o.py, o.pz, o.bound2)) continue;
+        int isOutside = 1;
+        LensIntersection<kShadow>(ray, o, base + i, h, isOutside);
+    }
+    base += nL;
+    const int nC = PT_N_CYCLIDES(c);
+    for (int i = 0; i < nC; i++) {
+        const PtDevCyclide& o = sc.cyclides[i];
+        if (!BoundingSphere(ray, o.px, o.py, o.pz, o.brad)) continue;
+        DupinCyclide<kShadow>(ray, o, base + i, h);
+    }
+#if PT_HAS_SDF
+    SphereTracing<kShadow>(c, ray, h);
+#endif
+}
+
+/* ---- sampling (shader.comp:976-1028, 1093-1119) ------------------------------------------------------------------ */
+PT_DEV V3 SampleCosineDirectionHemisphere(V3 normal, unsigned& seed) {
+    const float rx = RandomFloatPCG32(seed);
+    const float ry = RandomFloatPCG32(seed);
+    const float phi = 2.0f * PT_PI_F * ry;
+    const float sinTheta = 2.0f * rx - 1.0f;
+    const float cosTheta = PTK_SQRT(fmaf(-sinTheta, sinTheta, 1.0f));
+    const V3 u = mk3(PTK_COS(phi) * cosTheta, PTK_SIN(phi) * cosTheta, sinTheta);
+    return normalize(normal + u);
+}
+PT_DEV V3 SampleCosineUnitCone(unsigned& seed, float cosThetaMax) {
+    const float rx = RandomFloatPCG32(seed);
+    const float ry = RandomFloatPCG32(seed);
+    const float cosAlphaMax = 2.0f * cosThetaMax * cosThetaMax - 1.0f;
+    const float phi = 2.0f * PT_PI_F * ry;
+    const float cosTheta = (1.0f - cosAlphaMax) * rx + cosAlphaMax;
+    const float sinTheta = PTK_SQRT(fmaf(-cosTheta, cosTheta, 1.0f));
+    return normalize(mk3(PTK_COS(phi) * sinTheta, PTK_SIN(phi) * sinTheta, cosTheta + 1.0f));
+}
+PT_DEV V3 ToWorld(V3 v, V3 n) {
+    V3 b1 = mk3(0.0f, -1.0f, 0.0f);
+    V3 b2 = mk3(-1.0f, 0.0f, 0.0f);
+    if (n.z >= -0.9999999f) {
+        const float a = PTK_DIV(1.0f, 1.0f + n.z);
+        const float b = -n.x * n.y * a;
+        b1 = mk3(1.0f - (n.x * n.x * a), b, -n.x);
+        b2 = mk3(b, 1.0f - (n.y * n.y * a), -n.y);
+    }
+    return b1 * v.x + b2 * v.y + n * v.z;
+}
+
+/* ---- one path (shader.comp:1298-1407) --------------------------------------------------------------------------- */
+PT_DEV V4 TracePath(const Ctx& c, V4 l, Ray ray, unsigned& seed) {
+    const PtDevScene& sc = *c.sc;
+    V4 radiance = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    V4 rayradiance = mk4(1.0f, 1.0f, 1.0f, 1.0f);
+    float MISBRDFWeight = 1.0f;
+    const int pathLength = c.pr->pathLength;
+    for (int bounce = 0; bounce < pathLength; bounce++) {
+        /* TraceRay, shader.comp:1345-1391 */
+        Hit h;
+        Intersection<false>(c, ray, h);
+        if (!(h.t < 1e5f)) break; /* miss: black environment */
+        float temperature, luminosity;
+        GetLightMix(c, h.lightID, temperature, luminosity);
+        if (luminosity > 0.0f) { /* emitter hit terminates the path */
+            const V4 e = Emit(l, PTK_MAX(temperature, 0.0f), PTK_MAX(luminosity, 0.0f));
+            radiance = radiance + (e * rayradiance) * MISBRDFWeight;
+            break;
+        }
+        float peak, sigma, invertf;
+        GetMaterialMix(c, h.materialID, peak, sigma, invertf);
+        const V4 brdf = EvaluateBRDF(l, peak, sigma, invertf);
+
+        Ray outRay;
+        outRay.origin = fma3(ray.dir, h.t, ray.origin);
+        outRay.dir = SampleCosineDirectionHemisphere(h.normal, seed);
+        const float BRDFpdf = PTK_DIV(dot(outRay.dir, h.normal), PT_PI_F);
+
+        /* SampleLightSource, shader.comp:1298-1343 */
+        if (sc.numLights > 0.0f) {
+            const int randomLight = __float2int_rz(floorf(RandomFloatPCG32(seed) * sc.numLights));
+            const PtDevLightSlot& ls = sc.lightSlots[randomLight < sc.nLightSlots ? randomLight : sc.nLightSlots - 1];
+            const V3 toLight = mk3(ls.px - outRay.origin.x, ls.py - outRay.origin.y, ls.pz - outRay.origin.z);
+            const float invLightDistance = PTK_DIV(1.0f, length(toLight));
+            const V3 lightDir = toLight * invLightDistance;
+            const float sinthetaMax = PTK_MIN(ls.boundingRadius * invLightDistance, 1.0f);
+            const float costhetaMax = PTK_SQRT(1.0f - sinthetaMax * sinthetaMax);
+            Ray shadowRay;
+            shadowRay.origin = outRay.origin;
+            shadowRay.dir = ToWorld(SampleCosineUnitCone(seed, costhetaMax), lightDir);
+            float lightpdf = sc.invNumLights;
+            lightpdf *= PTK_DIV(dot(shadowRay.dir, lightDir), PT_PI_F * (1.0f - costhetaMax * costhetaMax));
+            MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + lightpdf * lightpdf);
+            const float costheta = dot(shadowRay.dir, h.normal);
+            const float deathProbability = 1.25f * PTK_MAX(MISBRDFWeight - 0.2f, 0.0f);
+            if (costheta >= 0.0f) {
+                if (RandomFloatPCG32(seed) > deathProbability) {
+                    Hit sh;
+                    Intersection<true>(c, shadowRay, sh);
+                    if (sh.objectID == ls.objectID) {
+                        float lt, ll;
+                        GetLightMix(c, ls.lightID, lt, ll);
+                        const V4 rr = rayradiance * mk4(PTK_DIV(brdf.x * costheta, lightpdf), PTK_DIV(brdf.y * costheta, lightpdf),
+                                                        PTK_DIV(brdf.z * costheta, lightpdf), PTK_DIV(brdf.w * costheta, lightpdf));
+                        const V4 e = Emit(l, PTK_MAX(lt, 0.0f), PTK_MAX(ll, 0.0f));
+                        radiance = radiance + (e * rr) * (1.0f - MISBRDFWeight);
+                    }
+                } else {
+                    MISBRDFWeight = 1.0f;
+                }
+            }
+        } else {
+            MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + 0.0f * 0.0f);
+        }
+
+        const float costheta = dot(outRay.dir, h.normal);
+        rayradiance = rayradiance * mk4(PTK_DIV(brdf.x * costheta, BRDFpdf), PTK_DIV(brdf.y * costheta, BRDFpdf),
+                                        PTK_DIV(brdf.z * costheta, BRDFpdf), PTK_DIV(brdf.w * costheta, BRDFpdf));
+        const float mx = PTK_MAX(rayradiance.x, PTK_MAX(rayradiance.y, PTK_MAX(rayradiance.z, rayradiance.w)));
+        const float rayProbability = PTK_MIN(PTK_MAX(mx, 0.0f), 0.99f);
+        if (RandomFloatPCG32(seed) > rayProbability) break;
+        rayradiance = rayradiance * PTK_DIV(1.0f, rayProbability);
+        ray = outRay;
+    }
+    return radiance;
+}
+
+/* shader.comp:1409-1444: two refractions through the camera's BK7 lens */
+PT_DEV void TracePathLens(const Ctx& c, float l, Ray& ray) {
+    const PtDevLens& lens = c.pr->camLens;
+#pragma unroll 1
+    for (int i = 0; i < 2; i++) {
+        Hit h;
+        h.t = 1e6f;
+        h.normal = mk3(0.0f, 0.0f, 0.0f);
+        h.materialID = 0.0f; h.lightID = -1.0f; h.objectID = -1;
+        int isOutside = 1;
+        LensIntersection<false>(ray, lens, 0, h, isOutside);
+        float n1 = 1.0f, n2 = 1.0f;
+        if (isOutside == 1) n2 = RefractiveIndexBK7Glass(l); else n1 = RefractiveIndexBK7Glass(l);
+        const float n12 = PTK_DIV(n1, n2);
+        l = l * n12;
+        ray.origin = fma3(ray.dir, h.t, ray.origin);
+        /* refract(I, N, eta), GLSL 4.50 8.5 */
+        const float ndi = dot(h.normal, ray.dir);
+        const float k = 1.0f - n12 * n12 * (1.0f - ndi * ndi);
+        if (k < 0.0f) {
+            ray.dir = mk3(0.0f, 0.0f, 0.0f);
+        } else {
+            const float f = n12 * ndi + PTK_SQRT(k);
+            ray.dir = mk3(n12 * ray.dir.x - f * h.normal.x, n12 * ray.dir.y - f * h.normal.y, n12 * ray.dir.z - f * h.normal.z);
+        }
+    }
+}
+
+/* shader.comp:1446-1490: one spectral path sample -> CIE XYZ */
+PT_DEV V3 Scene(const Ctx& c, unsigned xyx, unsigned xyy, float uvx, float uvy, int k) {
+    const PtDevParams& pr = *c.pr;
+    unsigned seed = (unsigned)(pr.firstSample + k); /* GenerateSeed, shader.comp:948-958 */
+    PCG32(seed);
+    seed += xyx + (unsigned)pr.width * xyy;
+
+    const float j1 = RandomFloatPCG32(seed);
+    const float j2 = RandomFloatPCG32(seed);
+    uvx = uvx + PTK_DIV(2.0f * j1 - 0.5f, pr.resX);
+    uvy = uvy + PTK_DIV(2.0f * j2 - 0.5f, pr.resY);
+    uvx *= pr.sensorScale;
+    uvy *= pr.sensorScale;
+    const V3 camPos = mk3(pr.camPosX, pr.camPosY, pr.camPosZ);
+    Ray ray;
+    ray.origin = camPos + mulVM(mk3(uvx, uvy, 0.0f), pr.camM);
+    /* SampleUniformUnitDisk, shader.comp:976-982 */
+    const float rx = RandomFloatPCG32(seed);
+    const float ry = RandomFloatPCG32(seed);
+    const float phi = 2.0f * PT_PI_F * ry;
+    const float dd = PTK_SQRT(rx);
+    const float diskx = pr.halfAperture * (dd * PTK_COS(phi));
+    const float disky = pr.halfAperture * (dd * PTK_SIN(phi));
+    const V3 pointOnAperture = camPos + mulVM(mk3(diskx, disky, pr.apertureDist), pr.camM);
+    ray.dir = normalize(pointOnAperture - ray.origin);
+
+    const float r5 = RandomFloatPCG32(seed);
+    const float l_h = 360.0f * (1.0f - r5) + 800.0f * r5; /* mix(360, 800, r) */
+    TracePathLens(c, l_h, ray);
+    const V4 l = SampleWavelengths(l_h);
+    const V4 radiance = TracePath(c, l, ray, seed);
+    const V3 w0 = WaveToXYZ(c, l.x), w1 = WaveToXYZ(c, l.y), w2 = WaveToXYZ(c, l.z), w3 = WaveToXYZ(c, l.w);
+    V3 color;
+    color.x = 0.0f + (radiance.x * w0.x + radiance.y * w1.x + radiance.z * w2.x + radiance.w * w3.x) * 330.0f * 0.25f;
+    color.y = 0.0f + (radiance.x * w0.y + radiance.y * w1.y + radiance.z * w2.y + radiance.w * w3.y) * 330.0f * 0.25f;
+    color.z = 0.0f + (radiance.x * w0.z + radiance.y * w1.z + radiance.z * w2.z + radiance.w * w3.z) * 330.0f * 0.25f;
+    if ((color.x != color.x) || (color.y != color.y) || (color.z != color.z)) return mk3(0.0f, 0.0f, 0.0f);
+    return color;
+}
+
+/* main() + Rendering() + Accumulate(), shader.comp:1492-1533.
+ * Grid: 2-D tiles of 16x8 pixels per 128-thread block; each warp owns an 8x4 sub-tile. */
+__device__ __forceinline__ void pt_render_body(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
+                                               float4* __restrict__ image, float* s_tab) {
+    for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int gy = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    if (gx >= pr.width || gy >= pr.height) return;
+
+    Ctx c;
+    c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
+
+    const unsigned xyx = (unsigned)gx;
+    const unsigned xyy = (unsigned)pr.height - (unsigned)gy; /* shader.comp:1510 */
+    const float uvx = PTK_DIV(2.0f * __uint2float_rn(xyx) - pr.resX, pr.resY);
+    const float uvy = PTK_DIV(2.0f * __uint2float_rn(xyy) - pr.resY, pr.resY);
+
+    V3 outColor = mk3(0.0f, 0.0f, 0.0f);
+    const int spf = pr.samplesPerFrame;
+#pragma unroll 1
+    for (int k = 0; k < spf; k++) outColor = outColor + Scene(c, xyx, xyy, uvx, uvy, k);
+
+    float4* texel = image + ((size_t)gx + (size_t)pr.width * (size_t)gy);
+    if (pr.accumMode == 2) { /* raw sum for the sample-split path (pt_dispatch_sum) */
+        float4 v = *texel;
+        v.x += outColor.x; v.y += outColor.y; v.z += outColor.z;
+        *texel = v;
+        return;
+    }
+    outColor = div3(outColor, pr.spfFloat);
+    outColor = outColor * pr.exposure;
+    const float4 in = *texel;
+    if (pr.accumMode == 1) {
+        const float w = pr.accumWeight;
+        outColor = mk3(((1.0f - w) * outColor.x) + (w * in.x), ((1.0f - w) * outColor.y) + (w * in.y),
+                       ((1.0f - w) * outColor.z) + (w * in.z));
+    } else {
+        const float n = pr.accumN, nm1 = pr.accumNm1;
+        outColor = mk3(PTK_DIV(nm1 * in.x + outColor.x, n), PTK_DIV(nm1 * in.y + outColor.y, n),
+                       PTK_DIV(nm1 * in.z + outColor.z, n));
+    }
+    *texel = make_float4(outColor.x, outColor.y, outColor.z, 1.0f);
+}
+
+} /* namespace PT_KERNEL_NS */
+
+/* the kernel entry point; PT_KERNEL_NAME distinguishes the strict / fast / JIT instances */
+#define PT_DEFINE_RENDER_KERNEL(name)                                                                        \
+    extern "C" __global__ void __launch_bounds__(PT_BLOCK_THREADS, PT_MIN_BLOCKS)                            \
+    name(const __grid_constant__ PtDevScene sc, const __grid_constant__ PtDevParams pr,                      \
+         const float* __restrict__ ubo, float4* __restrict__ image) {                                        \
+        __shared__ float s_tab[PT_SH_FLOATS];                                                                \
+        PT_KERNEL_NS::pt_render_body(sc, pr, ubo, image, s_tab);                                             \
+    }
+
+
+#if PT_HAS_SDF
+/* SDF()/SDFMATERIAL() at arbitrary points: used by the tests to compare the NVRTC build of the snippets with the
+ * CPU oracle's g++ build bit for bit (pt_sdf_eval) */
+#define PT_DEFINE_SDF_EVAL_KERNEL(name)                                                                      \
+    extern "C" __global__ void name(const float* __restrict__ xyz, unsigned long long n, unsigned set1,      \
+                                    float* __restrict__ dist, float* __restrict__ material) {                \
+        const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;              \
+        if (i >= n) return;                                                                                  \
+        const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];                                  \
+        if (dist) dist[i] = ::pt_sdf_dispatch(x, y, z, set1);                                                  \
+        if (material) material[i] = ::pt_sdfmaterial_dispatch(x, y, z, set1);                                  \
+    }
+#endif
+
+#endif /* PT_KERNEL_CUH */

@@ -1,0 +1,417 @@
+/* pt_lib.cpp -- the C ABI of libpt_cuda (include/pt_abi.h): device context, scene upload, dispatch, read-back.
+ *
+ * Replaces the Vulkan side of the reference's dispatch path: CreateUniformBuffer / CreateTexelBuffer /
+ * UpdateUniformBuffer / UpdatePushConstant / RecordComputeCommandBuffer / vkQueueSubmit
+ * (host:2230-2269, 3586-3608, 3642-3880).  One CUDA stream per context; every entry point returns a pt_status
+ * and leaves the message in pt_last_error().  There is no CPU fallback: without a CUDA device pt_create fails.
+ */
+#include <cuda_runtime_api.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "pt_internal.h"
+
+const std::string& pt_scene_last_error();
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct JitKernel {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kernel = nullptr;
+    cudaKernel_t sdf_eval = nullptr; /* only for scenes with SDF snippets */
+};
+
+}  // namespace
+
+struct pt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int mode = PT_MODE_STRICT;
+    int jit_policy = 1;      /* 0: never (static kernels only), 1: when the scene has SDFs, 2: always (baked counts) */
+    bool scene_set = false;
+    pt_ubo ubo;
+    PtDevScene dev_scene;
+    float* d_ubo = nullptr;   /* flat copy of the uniform block */
+    float* d_image = nullptr; /* accumulation image (RGBA32F) */
+    bool own_image = false;
+    int width = 0, height = 0;
+    JitKernel* active_jit = nullptr; /* null: statically compiled kernel */
+    std::map<std::string, JitKernel> jit_cache;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing_open = false;
+    long long launches = 0;
+    std::string error;
+};
+
+namespace {
+
+int fail(pt_ctx* ctx, int code, const std::string& msg) {
+    g_last_error = msg;
+    if (ctx) ctx->error = msg;
+    return code;
+}
+int cuda_fail(pt_ctx* ctx, cudaError_t e, const char* what) {
+    return fail(ctx, PT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define PT_CUDA(ctx, call)                                  \
+    do {                                                    \
+        cudaError_t e_ = (call);                            \
+        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); \
+    } while (0)
+
+int launch(pt_ctx* ctx, const PtDevParams& dp) {
+    if (!ctx->timing_open) {
+        PT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        ctx->timing_open = true;
+    }
+    if (ctx->active_jit) {
+        dim3 grid((unsigned)((dp.width + 15) / 16), (unsigned)((dp.height + 7) / 8), 1), block(128, 1, 1);
+        const float* ubo = ctx->d_ubo;
+        float* image = ctx->d_image;
+        void* args[4] = {(void*)&ctx->dev_scene, (void*)&dp, (void*)&ubo, (void*)&image};
+        PT_CUDA(ctx, cudaLaunchKernel((const void*)ctx->active_jit->kernel, grid, block, args, 0, ctx->stream));
+    } else if (ctx->mode == PT_MODE_FAST) {
+        pt_launch_fast(&ctx->dev_scene, &dp, ctx->d_ubo, ctx->d_image, ctx->stream);
+    } else {
+        pt_launch_strict(&ctx->dev_scene, &dp, ctx->d_ubo, ctx->d_image, ctx->stream);
+    }
+    PT_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return PT_OK;
+}
+
+int check_ready(pt_ctx* ctx, const pt_params* p) {
+    if (!ctx || !p) return fail(ctx, PT_ERR_ARG, "null argument");
+    if (!ctx->scene_set) return fail(ctx, PT_ERR_ARG, "pt_set_scene has not been called");
+    if (!ctx->d_image) return fail(ctx, PT_ERR_ARG, "no image: call pt_resize or pt_bind_image first");
+    if (p->resolution[0] != ctx->width || p->resolution[1] != ctx->height)
+        return fail(ctx, PT_ERR_ARG, "params.resolution does not match the image size");
+    return PT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pt_version(void) { return "libpt_cuda 0.1 (sm_100a)"; }
+
+const char* pt_last_error(const pt_ctx* ctx) {
+    if (ctx) return ctx->error.c_str();
+    if (g_last_error.empty()) return pt_scene_last_error().c_str();
+    return g_last_error.c_str();
+}
+
+int pt_create(int device, pt_ctx** out) {
+    if (!out) return fail(nullptr, PT_ERR_ARG, "pt_create: null out pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(nullptr, PT_ERR_NOGPU, std::string("no CUDA device available (libpt_cuda has no CPU fallback): ") +
+                                               cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, PT_ERR_ARG, "pt_create: device index out of range");
+    pt_ctx* ctx = new pt_ctx();
+    ctx->device = device;
+    const char* pol = getenv("PT_JIT");
+    if (pol && pol[0]) ctx->jit_policy = atoi(pol);
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&ctx->d_ubo, sizeof(pt_ubo))) != cudaSuccess) {
+        int rc = cuda_fail(nullptr, e, "pt_create");
+        pt_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return PT_OK;
+}
+
+void pt_destroy(pt_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->jit_cache)
+        if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
+    if (ctx->own_image && ctx->d_image) cudaFree(ctx->d_image);
+    if (ctx->d_ubo) cudaFree(ctx->d_ubo);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int pt_set_mode(pt_ctx* ctx, int mode) {
+    if (!ctx) return fail(nullptr, PT_ERR_ARG, "null context");
+    if (mode != PT_MODE_STRICT && mode != PT_MODE_FAST) return fail(ctx, PT_ERR_ARG, "unknown mode");
+    ctx->mode = mode;
+    ctx->scene_set = false; /* kernels are selected in pt_set_scene */
+    return PT_OK;
+}
+
+int pt_set_jit(pt_ctx* ctx, int policy) {
+    if (!ctx) return fail(nullptr, PT_ERR_ARG, "null context");
+    if (policy < 0 || policy > 2) return fail(ctx, PT_ERR_ARG, "jit policy must be 0, 1 or 2");
+    ctx->jit_policy = policy;
+    ctx->scene_set = false;
+    return PT_OK;
+}
+
+int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, int n_sdf) {
+    if (!ctx || !ubo) return fail(ctx, PT_ERR_ARG, "pt_set_scene: null argument");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::string err;
+    PtDevScene sc;
+    int rc = pt_prepare_scene(ubo, &sc, &err);
+    if (rc != PT_OK) return fail(ctx, rc, err);
+    if (n_sdf != sc.nSdfs)
+        return fail(ctx, PT_ERR_ARG, "pt_set_scene: n_sdf (" + std::to_string(n_sdf) + ") != ubo.numObjects[5] (" +
+                                         std::to_string(sc.nSdfs) + ")");
+    JitKernel* jit = nullptr;
+    const bool want_jit = (n_sdf > 0) || ctx->jit_policy == 2;
+    if (n_sdf > 0 && ctx->jit_policy == 0)
+        return fail(ctx, PT_ERR_COMPILE, "scene has SDF snippets but run-time compilation is disabled (PT_JIT=0)");
+    if (want_jit) {
+        std::string unit;
+        if (n_sdf > 0) {
+            rc = pt_sdf_generate(sdf_glsl, n_sdf, ubo->sdfs, &unit, &err);
+            if (rc != PT_OK) return fail(ctx, rc, err);
+        }
+        PtJitOptions opt;
+        opt.mode = ctx->mode;
+        opt.bake_counts = (ctx->jit_policy == 2);
+        const int counts[6] = {sc.nSpheres, sc.nPlanes, sc.nBoxes, sc.nLenses, sc.nCyclides, sc.nSdfs};
+        memcpy(opt.counts, counts, sizeof counts);
+        std::string key = std::to_string(opt.mode) + (opt.bake_counts ? "b" : "g");
+        if (opt.bake_counts)
+            for (int i = 0; i < 6; i++) key += "," + std::to_string(counts[i]);
+        key += "|" + unit;
+        auto it = ctx->jit_cache.find(key);
+        if (it == ctx->jit_cache.end()) {
+            std::vector<char> cubin;
+            std::string log;
+            rc = pt_jit_compile(unit, opt, &cubin, &log);
+            if (rc != PT_OK) return fail(ctx, rc, log);
+            JitKernel jk;
+            PT_CUDA(ctx, cudaLibraryLoadData(&jk.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+            cudaError_t e = cudaLibraryGetKernel(&jk.kernel, jk.lib, "pt_render_jit");
+            if (e != cudaSuccess) {
+                cudaLibraryUnload(jk.lib);
+                return cuda_fail(ctx, e, "cudaLibraryGetKernel(pt_render_jit)");
+            }
+            if (n_sdf > 0 && (e = cudaLibraryGetKernel(&jk.sdf_eval, jk.lib, "pt_sdf_eval_jit")) != cudaSuccess) {
+                cudaLibraryUnload(jk.lib);
+                return cuda_fail(ctx, e, "cudaLibraryGetKernel(pt_sdf_eval_jit)");
+            }
+            it = ctx->jit_cache.emplace(key, jk).first;
+        }
+        jit = &it->second;
+    }
+    ctx->ubo = *ubo;
+    ctx->dev_scene = sc;
+    ctx->active_jit = jit;
+    PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_ubo, &ctx->ubo, sizeof(pt_ubo), cudaMemcpyHostToDevice, ctx->stream));
+    PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); /* ctx->ubo may be overwritten by the next call */
+    ctx->scene_set = true;
+    ctx->error.clear();
+    return PT_OK;
+}
+
+int pt_resize(pt_ctx* ctx, int width, int height) {
+    if (!ctx || width <= 0 || height <= 0) return fail(ctx, PT_ERR_ARG, "pt_resize: bad size");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_image && ctx->d_image) cudaFree(ctx->d_image);
+    ctx->d_image = nullptr;
+    ctx->own_image = false;
+    const size_t bytes = (size_t)width * (size_t)height * 16;
+    PT_CUDA(ctx, cudaMalloc((void**)&ctx->d_image, bytes));
+    ctx->own_image = true;
+    ctx->width = width;
+    ctx->height = height;
+    /* the reference never clears a fresh texel buffer (n = 1 multiplies the old content by 0: SURVEY App. C-18);
+     * garbage NaNs would survive that, so the image starts at zero here */
+    PT_CUDA(ctx, cudaMemsetAsync(ctx->d_image, 0, bytes, ctx->stream));
+    return PT_OK;
+}
+
+int pt_bind_image(pt_ctx* ctx, void* device_rgba32f, int width, int height) {
+    if (!ctx || !device_rgba32f || width <= 0 || height <= 0) return fail(ctx, PT_ERR_ARG, "pt_bind_image: bad argument");
+    if (((uintptr_t)device_rgba32f & 15) != 0) return fail(ctx, PT_ERR_ARG, "pt_bind_image: pointer must be 16-byte aligned");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_image && ctx->d_image) cudaFree(ctx->d_image);
+    ctx->d_image = (float*)device_rgba32f;
+    ctx->own_image = false;
+    ctx->width = width;
+    ctx->height = height;
+    return PT_OK;
+}
+
+int pt_clear(pt_ctx* ctx) {
+    if (!ctx || !ctx->d_image) return fail(ctx, PT_ERR_ARG, "pt_clear: no image");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    PT_CUDA(ctx, cudaMemsetAsync(ctx->d_image, 0, (size_t)ctx->width * (size_t)ctx->height * 16, ctx->stream));
+    return PT_OK;
+}
+
+int pt_dispatch(pt_ctx* ctx, const pt_params* params) {
+    int rc = check_ready(ctx, params);
+    if (rc != PT_OK) return rc;
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    PtDevParams dp;
+    std::string err;
+    rc = pt_prepare_params(params, 0, 0, 0, &dp, &err);
+    if (rc != PT_OK) return fail(ctx, rc, err);
+    return launch(ctx, dp);
+}
+
+int pt_dispatch_sum(pt_ctx* ctx, const pt_params* params, int first_sample, int n_samples) {
+    int rc = check_ready(ctx, params);
+    if (rc != PT_OK) return rc;
+    if (n_samples <= 0) return fail(ctx, PT_ERR_ARG, "pt_dispatch_sum: n_samples must be positive");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    PtDevParams dp;
+    std::string err;
+    rc = pt_prepare_params(params, 2, first_sample, n_samples, &dp, &err);
+    if (rc != PT_OK) return fail(ctx, rc, err);
+    return launch(ctx, dp);
+}
+
+int pt_finalize(pt_ctx* ctx, const pt_params* params, int total_samples) {
+    int rc = check_ready(ctx, params);
+    if (rc != PT_OK) return rc;
+    if (total_samples <= 0) return fail(ctx, PT_ERR_ARG, "pt_finalize: total_samples must be positive");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const float exposure = params->apertureSize * params->apertureSize * (float)params->ISO;
+    pt_launch_finalize(ctx->d_image, ctx->width * ctx->height, 1.0f / (float)total_samples, exposure, ctx->stream);
+    PT_CUDA(ctx, cudaGetLastError());
+    return PT_OK;
+}
+
+int pt_render(pt_ctx* ctx, const pt_params* base, int total_samples, int samples_per_frame) {
+    if (!ctx || !base) return fail(ctx, PT_ERR_ARG, "pt_render: null argument");
+    if (samples_per_frame <= 0 || total_samples < samples_per_frame)
+        return fail(ctx, PT_ERR_ARG, "pt_render: need total_samples >= samples_per_frame > 0");
+    pt_params p = *base;
+    p.samplesPerFrame = samples_per_frame;
+    /* offscreen MainLoop bookkeeping (host:4042-4048): before dispatch j, frame = currentSamples = j * spf */
+    for (int j = 1; j * samples_per_frame <= total_samples; j++) {
+        p.frame = j * samples_per_frame;
+        p.currentSamples = j * samples_per_frame;
+        int rc = pt_dispatch(ctx, &p);
+        if (rc != PT_OK) return rc;
+    }
+    return pt_sync(ctx);
+}
+
+int pt_sync(pt_ctx* ctx) {
+    if (!ctx) return fail(nullptr, PT_ERR_ARG, "null context");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PT_OK;
+}
+
+int pt_read_xyz(pt_ctx* ctx, float* rgba, size_t n_floats) {
+    if (!ctx || !rgba || !ctx->d_image) return fail(ctx, PT_ERR_ARG, "pt_read_xyz: bad argument");
+    const size_t need = (size_t)ctx->width * (size_t)ctx->height * 4;
+    if (n_floats < need) return fail(ctx, PT_ERR_ARG, "pt_read_xyz: buffer too small");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    PT_CUDA(ctx, cudaMemcpyAsync(rgba, ctx->d_image, need * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PT_OK;
+}
+
+void* pt_image_ptr(pt_ctx* ctx) { return ctx ? (void*)ctx->d_image : nullptr; }
+void* pt_stream_handle(pt_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int pt_kernel_time(pt_ctx* ctx, float* ms, long long* launches) {
+    if (!ctx) return fail(nullptr, PT_ERR_ARG, "null context");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    float t = 0.0f;
+    if (ctx->timing_open) {
+        PT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        PT_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        PT_CUDA(ctx, cudaEventElapsedTime(&t, ctx->ev0, ctx->ev1));
+        ctx->timing_open = false;
+    }
+    if (ms) *ms = t;
+    if (launches) *launches = ctx->launches;
+    ctx->launches = 0;
+    return PT_OK;
+}
+
+long pt_sdf_translate(const char* const* sdf_glsl, int n_sdf, const float* sdfs_raw, char* out, size_t cap) {
+    std::string unit, err;
+    int rc = pt_sdf_generate(sdf_glsl, n_sdf, sdfs_raw, &unit, &err);
+    if (rc != PT_OK) { fail(nullptr, rc, err); return rc; }
+    if (out && cap > 0) {
+        size_t n = unit.size() < cap - 1 ? unit.size() : cap - 1;
+        memcpy(out, unit.data(), n);
+        out[n] = '\0';
+    }
+    return (long)unit.size() + 1;
+}
+
+int pt_sdf_compile_check(const char* const* sdf_glsl, int n_sdf, const float* sdfs_raw, int mode) {
+    std::string unit, err, log;
+    int rc = pt_sdf_generate(sdf_glsl, n_sdf, sdfs_raw, &unit, &err);
+    if (rc != PT_OK) return fail(nullptr, rc, err);
+    PtJitOptions opt;
+    opt.mode = mode;
+    opt.bake_counts = false;
+    memset(opt.counts, 0, sizeof opt.counts);
+    std::vector<char> cubin;
+    rc = pt_jit_compile(unit, opt, &cubin, &log);
+    if (rc != PT_OK) return fail(nullptr, rc, log);
+    g_last_error = log;
+    return PT_OK;
+}
+
+int pt_sdf_eval(pt_ctx* ctx, const float* xyz, size_t n, unsigned set1, float* dist, float* material) {
+    if (!ctx || !xyz || n == 0) return fail(ctx, PT_ERR_ARG, "pt_sdf_eval: bad argument");
+    if (!ctx->scene_set || !ctx->active_jit || !ctx->active_jit->sdf_eval)
+        return fail(ctx, PT_ERR_ARG, "pt_sdf_eval: the current scene has no SDF snippets");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    float *dx = nullptr, *dd = nullptr, *dm = nullptr;
+    PT_CUDA(ctx, cudaMalloc((void**)&dx, n * 12));
+    PT_CUDA(ctx, cudaMalloc((void**)&dd, n * 4));
+    PT_CUDA(ctx, cudaMalloc((void**)&dm, n * 4));
+    cudaMemcpyAsync(dx, xyz, n * 12, cudaMemcpyHostToDevice, ctx->stream);
+    unsigned long long nn = n;
+    const float* a0 = dx;
+    void* args[5] = {(void*)&a0, (void*)&nn, (void*)&set1, (void*)&dd, (void*)&dm};
+    cudaError_t e = cudaLaunchKernel((const void*)ctx->active_jit->sdf_eval, dim3((unsigned)((n + 127) / 128)), dim3(128), args,
+                                     0, ctx->stream);
+    if (e == cudaSuccess && dist) e = cudaMemcpyAsync(dist, dd, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && material) e = cudaMemcpyAsync(material, dm, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dx); cudaFree(dd); cudaFree(dm);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "pt_sdf_eval");
+    return PT_OK;
+}
+
+int pt_math_eval(pt_ctx* ctx, int fn, const float* x, const float* y, float* out, size_t n) {
+    if (!ctx || !x || !out) return fail(ctx, PT_ERR_ARG, "pt_math_eval: null argument");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    float *dx = nullptr, *dy = nullptr, *dout = nullptr;
+    PT_CUDA(ctx, cudaMalloc((void**)&dx, n * 4));
+    PT_CUDA(ctx, cudaMalloc((void**)&dy, n * 4));
+    PT_CUDA(ctx, cudaMalloc((void**)&dout, n * 4));
+    cudaMemcpyAsync(dx, x, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (y) cudaMemcpyAsync(dy, y, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    else cudaMemsetAsync(dy, 0, n * 4, ctx->stream);
+    pt_launch_math_eval(fn, dx, dy, dout, n, ctx->stream);
+    cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dx); cudaFree(dy); cudaFree(dout);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "pt_math_eval");
+    return PT_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,248 @@
+"""Parity proper: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Strict mode is bit-exact (memcmp of the XYZ buffers): integer RNG streams, pinned fp32 math and no contraction on
+both sides.  Fast mode forks paths at thresholds, so it is compared statistically:
+relRMSE = sqrt(mean((I-R)^2 / (R^2 + eps))), eps = (0.01 mean R)^2, against the noise floor between two strict
+renders with disjoint sample indices."""
+import numpy as np
+import pytest
+
+from conftest import scene_path, SCENES
+from oracle import oracle, pack
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_rmse(img, ref):
+    a, r = img[..., :3].astype(np.float64), ref[..., :3].astype(np.float64)
+    eps = (0.01 * r.mean()) ** 2
+    return float(np.sqrt(np.mean((a - r) ** 2 / (r ** 2 + eps))))
+
+
+@pytest.fixture(scope='module')
+def renderer(ptlib):
+    r = ptlib.Renderer(device=0, mode=ptlib.MODE_STRICT)
+    yield r
+    r.close()
+
+
+def gpu_render(ptlib, r, name, w, h, spp, spf, path_length=5, shot=1, mode=0, jit=None):
+    sc = ptlib.Scene.load(scene_path(name))
+    ubo = sc.pack_ubo()
+    p = sc.pack_params(shot, w, h, spf, path_length)
+    r.set_mode(mode)
+    if jit is not None:
+        r.set_jit(jit)
+    r.set_scene(ubo, sc.sdf_sources)
+    r.resize(w, h)
+    r.render(p, spp, spf)
+    return r.read_xyz(), ubo, p, [s.decode() for s in sc.sdf_sources]
+
+
+def assert_bit_equal(got, ref, what):
+    g, r = got.view(np.uint32), ref.view(np.uint32)
+    if not np.array_equal(g, r):
+        bad = np.argwhere(g != r)
+        y, x, c = bad[0]
+        raise AssertionError('%s: %d of %d floats differ; first at pixel (%d,%d) ch %d: gpu %r oracle %r' %
+                             (what, len(bad), g.size, x, y, c, got[y, x, c], ref[y, x, c]))
+
+
+def test_math_bit_equal_cpu_gpu(renderer):
+    rng = np.random.default_rng(0)
+    n = 1 << 20
+    cases = {0: rng.uniform(-7000, 7000, n), 1: rng.uniform(-7000, 7000, n), 2: rng.uniform(-1.0001, 1.0001, n),
+             3: rng.uniform(-160, 140, n), 4: np.exp2(rng.uniform(-150, 128, n)), 5: rng.uniform(-100, 90, n),
+             6: np.exp2(rng.uniform(-150, 128, n))}
+    special = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-45, 3.4e38, 0.5, -0.5, 4194304.0, 1e7], dtype=np.float32)
+    for fn, x in cases.items():
+        x = np.concatenate([x.astype(np.float32), special])
+        a, b = renderer.math_eval(fn, x), oracle.math_eval(fn, x)
+        both_nan = np.isnan(a) & np.isnan(b)
+        assert np.array_equal(a.view(np.uint32)[~both_nan], b.view(np.uint32)[~both_nan]), 'pt_math fn %d' % fn
+    x = np.abs(rng.uniform(0, 100, n)).astype(np.float32)
+    y = rng.uniform(-8, 8, n).astype(np.float32)
+    a, b = renderer.math_eval(7, x, y), oracle.math_eval(7, x, y)
+    both_nan = np.isnan(a) & np.isnan(b)
+    assert np.array_equal(a.view(np.uint32)[~both_nan], b.view(np.uint32)[~both_nan])
+
+
+def test_rng_bit_exact(renderer):
+    seeds = np.concatenate([np.arange(4096, dtype=np.uint32), np.random.default_rng(1).integers(0, 2 ** 32, 1 << 16, dtype=np.uint32),
+                            np.array([0xFFFFFFFF, 0xFFFFFF80, 0x12345678], dtype=np.uint32)])
+    out = renderer.math_eval(8, seeds.view(np.float32)).view(np.uint32)
+    s = seeds.astype(np.uint64)
+    state = (s * 747796405 + 2891336453) & 0xFFFFFFFF
+    word = (((state >> ((state >> 28) + 4)) ^ state) * 277803737) & 0xFFFFFFFF
+    want = (((word >> 22) ^ word) & 0xFFFFFFFF).astype(np.uint32)
+    assert np.array_equal(out, want)
+    f = renderer.math_eval(9, seeds.view(np.float32))
+    assert np.array_equal(f, want.astype(np.float32) / np.float32(4294967296.0))
+    assert f.max() <= 1.0
+
+
+@pytest.mark.parametrize('name,w,h,spp,spf', [('scene0', 128, 128, 1, 1), ('scene0', 96, 64, 8, 4), ('scene1', 160, 90, 4, 2),
+                                              ('scene2', 96, 64, 4, 4), ('scene0', 50, 37, 3, 1)])
+def test_strict_bit_exact_analytic_scenes(ptlib, renderer, name, w, h, spp, spf):
+    got, ubo, p, src = gpu_render(ptlib, renderer, name, w, h, spp, spf)
+    ref = oracle.Oracle(ubo, src).render(p, spp, spf)
+    assert_bit_equal(got, ref, '%s %dx%d %dspp/%d' % (name, w, h, spp, spf))
+    assert np.isfinite(got).all() and got[..., 3].min() == 1.0
+
+
+@pytest.mark.parametrize('name', ['scene3', 'scene4', 'scene5', 'scene6', 'scene7', 'scene8', 'scene9', 'scene10'])
+def test_strict_bit_exact_sdf_scenes(ptlib, renderer, name):
+    got, ubo, p, src = gpu_render(ptlib, renderer, name, 64, 48, 2, 2)
+    ref = oracle.Oracle(ubo, src).render(p, 2, 2)
+    assert_bit_equal(got, ref, name)
+
+
+def test_strict_bit_exact_cfg1_full(ptlib, renderer):
+    """BASELINE config 1: scenes/scene0.json at 512x512, 64 spp (8 dispatches of 8), the whole frame bit for bit."""
+    got, ubo, p, src = gpu_render(ptlib, renderer, 'scene0', 512, 512, 64, 8)
+    ref = oracle.Oracle(ubo, src).render(p, 64, 8)
+    assert_bit_equal(got, ref, 'cfg1')
+
+
+def test_strict_all_shots_and_long_paths(ptlib, renderer):
+    got, ubo, p, src = gpu_render(ptlib, renderer, 'scene10', 48, 32, 1, 1, path_length=32, shot=3)
+    assert_bit_equal(got, oracle.Oracle(ubo, src).render(p, 1, 1), 'scene10 shot 3 pathLength 32')
+    got, ubo, p, src = gpu_render(ptlib, renderer, 'scene8', 48, 32, 1, 1, path_length=32)
+    assert_bit_equal(got, oracle.Oracle(ubo, src).render(p, 1, 1), 'scene8 pathLength 32')
+    got, ubo, p, src = gpu_render(ptlib, renderer, 'scene0', 48, 32, 2, 1, shot=2)
+    assert_bit_equal(got, oracle.Oracle(ubo, src).render(p, 2, 1), 'scene0 shot 2')
+
+
+def test_jit_specialised_kernel_is_bit_exact_too(ptlib, renderer):
+    """jit policy 2 bakes the primitive counts in (unrolled loops): same bits as the generic kernel and the oracle."""
+    got, ubo, p, src = gpu_render(ptlib, renderer, 'scene0', 96, 64, 2, 2, jit=2)
+    ref = oracle.Oracle(ubo, src).render(p, 2, 2)
+    renderer.set_jit(1)
+    assert_bit_equal(got, ref, 'scene0 jit=2')
+
+
+def test_sdf_eval_bit_equal(ptlib, renderer):
+    for name in ('scene9', 'scene10', 'scene8', 'scene3'):
+        sc = ptlib.Scene.load(scene_path(name))
+        ubo = sc.pack_ubo()
+        renderer.set_mode(0)
+        renderer.set_scene(ubo, sc.sdf_sources)
+        pos, size = ubo[pack.OFF_SDF:pack.OFF_SDF + 3], ubo[pack.OFF_SDF + 3:pack.OFF_SDF + 6]
+        pts = (pos + (np.random.default_rng(11).random((200000, 3)) - 0.5) * size * 1.2).astype(np.float32)
+        d, m = renderer.sdf_eval(pts, 1)
+        d_ref, m_ref = oracle.Oracle(ubo, [s.decode() for s in sc.sdf_sources]).sdf_eval(pts, 1)
+        assert np.array_equal(d.view(np.uint32), d_ref.view(np.uint32)), name
+        assert np.array_equal(m.view(np.uint32), m_ref.view(np.uint32)), name
+
+
+def test_sum_mode_and_finalize(ptlib, renderer):
+    """pt_dispatch_sum over disjoint sample ranges + pt_finalize == the oracle's sum (bit-exact per range) and the
+    running-mean render of the same samples within fp32 summation-order tolerance."""
+    sc = ptlib.Scene.load(scene_path('scene0'))
+    ubo = sc.pack_ubo()
+    p = sc.pack_params(1, 64, 48, 4, 5)
+    renderer.set_mode(0)
+    renderer.set_scene(ubo)
+    renderer.resize(64, 48)
+    renderer.dispatch_sum(p, 0, 3)
+    renderer.dispatch_sum(p, 3, 5)
+    got = renderer.read_xyz()
+    o = oracle.Oracle(ubo)
+    ref = np.zeros((48, 64, 4), dtype=np.float32)
+    o.dispatch_sum(p, 0, 3, ref)
+    o.dispatch_sum(p, 3, 5, ref)
+    assert_bit_equal(got[..., :3].copy(), ref[..., :3].copy(), 'sum mode')
+    renderer.finalize(p, 8)
+    fin = renderer.read_xyz()
+    mean = o.render(p, 8, 4)
+    assert np.allclose(fin[..., :3], mean[..., :3], rtol=1e-5, atol=1e-8)
+    assert (fin[..., 3] == 1.0).all()
+
+
+def test_temporal_accumulation_branch(ptlib, renderer):
+    """Accumulate()'s interactive EMA branch (shader.comp:1500-1502): currentSamples == spf and frame > spf."""
+    sc = ptlib.Scene.load(scene_path('scene1'))
+    ubo = sc.pack_ubo()
+    p = sc.pack_params(1, 32, 24, 2, 5)
+    renderer.set_mode(0)
+    renderer.set_scene(ubo)
+    renderer.resize(32, 24)
+    renderer.dispatch(p)
+    q = p.copy()
+    q['frame'] = 6
+    q['currentSamples'] = 2
+    q['FPS'] = 30.0
+    renderer.dispatch(q)
+    got = renderer.read_xyz()
+    o = oracle.Oracle(ubo)
+    ref = np.zeros((24, 32, 4), dtype=np.float32)
+    o.dispatch(p, ref)
+    o.dispatch(q, ref)
+    assert_bit_equal(got, ref, 'EMA branch')
+
+
+def test_errors(ptlib, renderer):
+    sc = ptlib.Scene.load(scene_path('scene9'))
+    with pytest.raises(ptlib.PtError):
+        renderer.set_scene(sc.pack_ubo(), [])  # n_sdf mismatch
+    sc0 = ptlib.Scene.load(scene_path('scene0'))
+    renderer.set_scene(sc0.pack_ubo())
+    renderer.resize(16, 16)
+    with pytest.raises(ptlib.PtError):
+        renderer.dispatch(sc0.pack_params(1, 32, 32, 1, 5))  # resolution mismatch
+    bad = 'float sdf(in vec3 p) { return nope(p); }\nfloat sdfmaterial(in vec3 p) { return 0.0; }'
+    with pytest.raises(ptlib.PtError) as e:
+        renderer.set_scene(sc.pack_ubo(), [bad])
+    assert e.value.code == -2 and 'nope' in str(e.value)
+
+
+@pytest.mark.parametrize('name', ['scene0', 'scene1', 'scene9', 'scene10', 'scene8'])
+def test_fast_mode_statistically_equivalent(ptlib, renderer, name):
+    """fast vs strict at equal spp must be no further apart than two strict renders with disjoint sample indices."""
+    w, h, spp = 96, 64, 64
+    sc = ptlib.Scene.load(scene_path(name))
+    ubo = sc.pack_ubo()
+    p = sc.pack_params(1, w, h, spp, 5)
+
+    def run(mode, first):
+        renderer.set_mode(mode)
+        renderer.set_scene(ubo, sc.sdf_sources)
+        renderer.resize(w, h)
+        renderer.dispatch_sum(p, first, spp)
+        renderer.finalize(p, spp)
+        return renderer.read_xyz()
+
+    a, b, f = run(0, 0), run(0, 1 << 20), run(1, 0)
+    assert np.isfinite(f).all()
+    noise = rel_rmse(a, b)
+    diff = rel_rmse(f, a)
+    mean_rel = abs(f[..., 1].mean() - a[..., 1].mean()) / a[..., 1].mean()
+    print('%s: relRMSE strict A/B %.4f, fast/strict %.4f, mean Y rel diff %.4f' % (name, noise, diff, mean_rel))
+    assert diff <= 1.1 * noise + 1e-3
+    assert mean_rel < 0.03
+
+
+def test_full_size_properties_cfg2(ptlib, renderer):
+    """BASELINE config 2 resolution (1920x1080), fast mode: size-independent properties -- determinism (same inputs,
+    same bits), w == 1 everywhere, finite, and linearity of the sum mode (sum(0..8) == sum(0..4) + sum(4..8))."""
+    sc = ptlib.Scene.load(scene_path('scene1'))
+    ubo = sc.pack_ubo()
+    p = sc.pack_params(1, 1920, 1080, 4, 5)
+    renderer.set_mode(1)
+    renderer.set_scene(ubo)
+    renderer.resize(1920, 1080)
+    renderer.dispatch(p)
+    a = renderer.read_xyz()
+    renderer.clear()
+    renderer.dispatch(p)
+    b = renderer.read_xyz()
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.isfinite(a).all() and (a[..., 3] == 1.0).all() and a[..., 1].mean() > 0
+    renderer.clear()
+    renderer.dispatch_sum(p, 0, 8)
+    s8 = renderer.read_xyz()
+    renderer.clear()
+    renderer.dispatch_sum(p, 0, 4)
+    renderer.dispatch_sum(p, 4, 4)
+    s44 = renderer.read_xyz()
+    assert np.allclose(s8[..., :3], s44[..., :3], rtol=1e-5, atol=1e-6)

@@ -1,0 +1,230 @@
+"""Known-answer tests that pin the CPU oracle.  The reference ships no tests or golden vectors
+("parity unpinned"); these are first-principles checks: exact integer vectors for the PCG hash, exact float values
+for functions built from + - * / sqrt only, analytic checks for the rest."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import scene_path, SCENES
+from oracle import oracle, pack
+
+PCG_KAT = {0x00000000: 0x07bb2fe2, 0x00000001: 0xa8beea3c, 0x00000002: 0x7a7ecc88, 0x00000003: 0x7f0ef6bc,
+           0x0000003f: 0xa59978e9, 0x00000040: 0x85e59170, 0x000003ff: 0x21cccfa5, 0x00003fff: 0x78d103d9,
+           0x0000ffff: 0x07d6f4f8, 0xffffffff: 0xe62a4902, 0x12345678: 0x995312e1}
+
+
+def py_pcg32(s):
+    state = (s * 747796405 + 2891336453) & 0xFFFFFFFF
+    word = (((state >> ((state >> 28) + 4)) ^ state) * 277803737) & 0xFFFFFFFF
+    return ((word >> 22) ^ word) & 0xFFFFFFFF
+
+
+def test_pcg32_vectors():
+    L = oracle.lib()
+    for s, want in PCG_KAT.items():
+        assert L.oracle_pcg32(s) == want
+        assert py_pcg32(s) == want
+
+
+def _params(w, h, spf, frame):
+    p = np.zeros((), dtype=pack.PARAMS_DTYPE)
+    p['resolution'] = (w, h)
+    p['samplesPerFrame'] = spf
+    p['frame'] = frame
+    p['currentSamples'] = frame
+    return p
+
+
+@pytest.mark.parametrize('gid,k,spf,seed,states,floats', [
+    ((0, 0), 0, 1, 0x07bf2fe2, [0x3a20ffe8, 0xc12aaa0d, 0x2e2aba37, 0x18b7d9d6, 0xd7b1adea],
+     [0.22706604, 0.75455725, 0.18033947, 0.09655534, 0.84255493]),
+    ((255, 256), 0, 1, 0x07bd30e1, [0x7ad45138, 0xa7dc0c74, 0x3710a129, 0x8a56e437, 0x0aa413b4], None),
+    ((511, 511), 63, 64, 0xa5997ce8, [0x3f042acf, 0x0a7fac30, 0xa9c3fb33, 0xdcfd5027, 0x90df27c7], None),
+])
+def test_seed_and_first_draws(gid, k, spf, seed, states, floats):
+    import ctypes as C
+    L = oracle.lib()
+    p = _params(512, 512, spf, spf)
+    got = L.oracle_generate_seed(p.ctypes.data_as(C.c_void_p), gid[0], gid[1], k)
+    assert got == seed
+    s = C.c_uint32(got)
+    for i, st in enumerate(states):
+        f = L.oracle_random_float(C.byref(s))
+        assert s.value == st
+        assert f == np.float32(st) / np.float32(4294967296.0)
+        if floats:
+            assert abs(f - floats[i]) < 1e-7
+
+
+def test_random_float_can_be_one():
+    assert np.float32(0xFFFFFFFF) == np.float32(4294967296.0)
+    assert np.float32(np.uint32(0xFFFFFF80)) / np.float32(4294967296.0) == np.float32(1.0)
+
+
+def test_cie_table_pin():
+    t = pack.cie_table()
+    assert hashlib.md5(t.astype('<f4').tobytes()).hexdigest() == '534a779bb345832aa54e456e53c9b76f'
+    rows = t.reshape(441, 3).astype(np.float64)
+    assert np.allclose(rows.sum(axis=0), [106.86534529, 106.85687253, 106.89225085], atol=1e-6)
+    assert rows[555 - 360, 1] == 1.0
+    assert np.allclose(rows[550 - 360], [0.4334499, 0.9949501, 0.00875], atol=1e-7)
+
+
+def test_wave_to_xyz():
+    import ctypes as C
+    L = oracle.lib()
+    ubo = pack.pack_ubo(pack.load_scene(scene_path('scene0')))
+    out = np.zeros(3, dtype=np.float32)
+    L.oracle_wave_to_xyz(ubo.ctypes.data_as(C.c_void_p), 550.5, out.ctypes.data_as(C.c_void_p))
+    assert np.allclose(out, [0.4411226, 0.9958304, 0.0083926], atol=2e-7)
+    rows = pack.cie_table().reshape(441, 3)
+    want = rows[190] * np.float32(0.5) + rows[191] * np.float32(0.5)
+    assert np.array_equal(out, want)
+    for w in (359.9, 800.5):
+        L.oracle_wave_to_xyz(ubo.ctypes.data_as(C.c_void_p), w, out.ctypes.data_as(C.c_void_p))
+        assert not out.any()
+
+
+@pytest.mark.parametrize('lh,want', [(500.0, (582.5, 665.0, 417.5, 500.0)), (360.0, (442.5, 525.0, 607.5, 690.0)),
+                                     (800.0, (552.5, 635.0, 717.5, 470.0))])
+def test_sample_wavelengths(lh, want):
+    L = oracle.lib()
+    out = np.zeros(4, dtype=np.float32)
+    L.oracle_sample_wavelengths(lh, out.ctypes.data)
+    assert tuple(out) == want
+
+
+def test_bk7_index():
+    L = oracle.lib()
+    assert abs(L.oracle_bk7(400.0) - 1.5308485) < 2e-6
+    assert abs(L.oracle_bk7(587.56) - 1.5168) < 2e-5
+    assert abs(L.oracle_bk7(700.0) - 1.513064) < 2e-6
+
+
+def test_emit_at_wien_peak_equals_luminosity():
+    L = oracle.lib()
+    for T, lum in ((5500.0, 1.0), (3000.0, 20.0), (6500.0, 0.5)):
+        peak_nm = 2.8977729e6 / T
+        l4 = np.array([peak_nm] * 4, dtype=np.float32)
+        out = np.zeros(4, dtype=np.float32)
+        L.oracle_emit(l4.ctypes.data, T, lum, out.ctypes.data)
+        assert np.allclose(out, lum, rtol=2e-4)
+    # against float64 Planck at an off-peak wavelength
+    T, lam = 5500.0, 450.0
+    l4 = np.array([lam] * 4, dtype=np.float32)
+    out = np.zeros(4, dtype=np.float32)
+    L.oracle_emit(l4.ctypes.data, T, 1.0, out.ctypes.data)
+    lm = lam * 1e-9
+    want = (1.1910429724e-16 * lm ** -5 / (np.exp(0.014387768775 / (lm * T)) - 1)) / (4.0956746759e-6 * T ** 5)
+    assert np.allclose(out, want, rtol=1e-4)
+
+
+def test_spd():
+    L = oracle.lib()
+    l4 = np.array([550.0, 600.0, 500.0, 450.0], dtype=np.float32)
+    out = np.zeros(4, dtype=np.float32)
+    L.oracle_spd(l4.ctypes.data, 550.0, 10.0, 0, out.ctypes.data)
+    assert out[0] == 1.0
+    want = np.exp(-(((l4.astype(np.float64) - 550.0) / 200.0) ** 2))
+    assert np.allclose(out, want, rtol=1e-5)
+    inv = np.zeros(4, dtype=np.float32)
+    L.oracle_spd(l4.ctypes.data, 550.0, 10.0, 1, inv.ctypes.data)
+    assert np.allclose(inv, 1.0 - out, atol=1e-7)
+
+
+def test_rotation_matrix_is_orthonormal_and_matches_closed_form():
+    L = oracle.lib()
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        deg = rng.uniform(-360, 360, 3).astype(np.float32)
+        m = np.zeros(9, dtype=np.float32)
+        L.oracle_rotation_matrix(deg.ctypes.data, m.ctypes.data)
+        M = m.reshape(3, 3).T.astype(np.float64)  # columns -> math matrix
+        assert np.allclose(M @ M.T, np.eye(3), atol=1e-5)
+        a = np.deg2rad(deg.astype(np.float64))
+        sx, sy, sz, cx, cy, cz = *np.sin(a), *np.cos(a)
+        mX = np.array([[1, 0, 0], [0, cx, sx], [0, -sx, cx]])
+        mY = np.array([[cy, 0, -sy], [0, 1, 0], [sy, 0, cy]])
+        mZ = np.array([[cz, sz, 0], [-sz, cz, 0], [0, 0, 1]])
+        assert np.allclose(M, mX @ mY @ mZ, atol=2e-5)
+
+
+def test_closed_form_intersections():
+    scene = {'camera': {}, 'sphere': [{'position': [0, 0, 5], 'radius': 1.0, 'materialID': 2, 'lightID': 0}],
+             'plane': [{'position': [0, -1, 0], 'materialID': 1, 'lightID': 0}],
+             'box': [{'position': [4, 0, 0], 'rotation': [0, 0, 0], 'size': [2, 2, 2], 'materialID': 3, 'lightID': 0}],
+             'material': [{'reflection': {'peakWavelength': 550, 'sigma': 10, 'isInvert': False}}] * 3, 'light': []}
+    o = oracle.Oracle(pack.pack_ubo(scene))
+    t, out = o.intersect([0, 0, 0], [0, 0, 1])
+    assert abs(t - 4.0) < 1e-6 and np.allclose(out[:3], [0, 0, -1]) and out[3] == 1.0 and out[4] == -1.0
+    t, out = o.intersect([0, 0, 0], [0, -1, 0])
+    assert abs(t - 1.0) < 1e-6 and np.allclose(out[:3], [0, 1, 0]) and out[3] == 0.0
+    t, out = o.intersect([0, 0, 0], [1, 0, 0])
+    assert abs(t - 3.0) < 1e-6 and np.allclose(out[:3], [-1, 0, 0]) and out[3] == 2.0
+    t, out = o.intersect([0, 0, 0], [0, 1, 0])
+    assert t == np.float32(1e5)  # miss
+    t, out = o.intersect([0, 0, 5], [0, 0, 1])  # from inside the sphere: normal flips
+    assert abs(t - 1.0) < 1e-6 and np.allclose(out[:3], [0, 0, -1])
+
+
+def test_quartic_solver_on_known_roots():
+    L = oracle.lib()
+    roots = np.array([1.0, 2.5, -3.0, 4.0])
+    coef = np.poly(roots).astype(np.float32)  # a..e
+    r = np.zeros(4, dtype=np.float32)
+    real = np.zeros(4, dtype=np.int32)
+    L.oracle_solve_quartic(coef.ctypes.data, r.ctypes.data, real.ctypes.data)
+    assert real.all()
+    assert np.allclose(np.sort(r), np.sort(roots), atol=2e-3)
+
+
+def test_scene0_pack_known_values():
+    ubo = pack.pack_ubo(pack.load_scene(scene_path('scene0')))
+    assert list(ubo[:7]) == [3, 1, 1, 1, 1, 0, 1]
+    assert list(ubo[7:13]) == [0, 1, 0, 1, 1, 0]
+    assert ubo[pack.OFF_LID] == 2
+    cyc = 7 + 18 + 5 + 11 + 12
+    assert ubo[cyc + 13] == np.float32(2.25)  # 36 * 0.0625
+
+
+def test_white_furnace_like_energy_bound():
+    """A grey Lambertian sphere lit by a large emitter: every pixel stays finite and non-negative."""
+    o, sc = oracle.from_scene_file(scene_path('scene0'))
+    p = pack.pack_params(sc, 1, 48, 32, 8, 5)
+    img = o.render(p, 8, 8)
+    assert np.isfinite(img).all()
+    assert (img[..., 1] >= 0).all() and img[..., 3].min() == 1.0
+    assert 0.01 < img[..., 1].mean() < 10.0
+
+
+def test_running_mean_equals_single_dispatch_statistics():
+    """Accumulate(): 4 dispatches of 2 samples == mean of the same 8 sample indices (up to fp32 rounding)."""
+    o, sc = oracle.from_scene_file(scene_path('scene1'))
+    p = pack.pack_params(sc, 1, 32, 24, 2, 5)
+    a = o.render(p, 8, 2)
+    p8 = pack.pack_params(sc, 1, 32, 24, 8, 5)
+    b = o.render(p8, 8, 8)
+    assert np.allclose(a, b, rtol=2e-5, atol=1e-7)
+
+
+def test_per_sample_entry_matches_dispatch():
+    o, sc = oracle.from_scene_file(scene_path('scene0'))
+    p = pack.pack_params(sc, 1, 16, 16, 4, 5)
+    img = o.render(p, 4, 4)
+    s = o.samples(p, 5, 7, 0, 4)
+    acc = np.zeros(3, dtype=np.float32)
+    for k in range(4):
+        acc = acc + s[k]
+    acc = acc / np.float32(4)
+    expo = np.float32(p['apertureSize']) * np.float32(p['apertureSize']) * np.float32(int(p['ISO']))
+    assert np.array_equal((acc * expo).astype(np.float32), img[7, 5, :3])
+
+
+@pytest.mark.parametrize('name', SCENES)
+def test_all_scenes_render_finite(name):
+    o, sc = oracle.from_scene_file(scene_path(name))
+    p = pack.pack_params(sc, 1, 24, 16, 1, 5)
+    img = o.render(p, 1, 1)
+    assert np.isfinite(img).all()
+    assert img[..., :3].max() > 0.0

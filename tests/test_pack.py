@@ -1,0 +1,67 @@
+"""The C++ scene loader / packer behind the C ABI vs the independent numpy restatement in oracle/pack.py."""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import SCENES, scene_path
+from oracle import pack
+
+
+@pytest.mark.parametrize('name', SCENES)
+def test_ubo_and_params_bit_identical(ptlib, name):
+    sc = ptlib.Scene.load(scene_path(name))
+    ref_scene = pack.load_scene(scene_path(name))
+    ubo, ref = sc.pack_ubo(), pack.pack_ubo(ref_scene)
+    assert ubo.shape == (4097,) and ubo.nbytes == 16388
+    assert np.array_equal(ubo.view(np.uint32), ref.view(np.uint32))
+    for shot in range(1, sc.num_shots + 1):
+        p = sc.pack_params(shot, 640, 360, 3, 7)
+        q = pack.pack_params(ref_scene, shot, 640, 360, 3, 7)
+        assert p.tobytes() == q.tobytes()
+    assert [s.decode() for s in sc.sdf_sources] == pack.sdf_sources(ref_scene)
+
+
+def test_params_layout_is_the_push_constant_block(ptlib):
+    d = ptlib.PARAMS_DTYPE
+    offs = {n: d.fields[n][1] for n in d.names}
+    assert d.itemsize == 88
+    assert offs == {'resolution': 0, 'frame': 8, 'currentSamples': 12, 'samplesPerFrame': 16, 'FPS': 20,
+                    'persistence': 24, 'pathLength': 28, 'cameraAngle': 32, 'cameraPosX': 40, 'cameraPosY': 44,
+                    'cameraPosZ': 48, 'ISO': 52, 'cameraSize': 56, 'apertureSize': 60, 'apertureDist': 64,
+                    'lensRadius': 68, 'lensFocalLength': 72, 'lensThickness': 76, 'lensDistance': 80, 'tonemap': 84}
+
+
+def test_light_registration_quirk(ptlib):
+    """host:3704,3728: lenses and cyclides are registered as sampled lights iff planes[i].lightID > 0."""
+    s = pack.load_scene(scene_path('scene0'))
+    s['lens'][0]['lightID'] = 1          # emits when hit ...
+    ubo = ptlib.Scene.parse(json.dumps(s)).pack_ubo()
+    assert ubo[6] == 1                   # ... but is not sampled: plane 0 has lightID 0
+    s['plane'][0]['lightID'] = 1
+    ubo = ptlib.Scene.parse(json.dumps(s)).pack_ubo()
+    ref = pack.pack_ubo(s)
+    assert np.array_equal(ubo.view(np.uint32), ref.view(np.uint32))
+    assert ubo[6] == 4                   # sphere 2, plane 0, lens 0 and cyclide 0 (both keyed on plane 0)
+    assert list(ubo[pack.OFF_LID:pack.OFF_LID + 4]) == [2, 3, 5, 6]
+
+
+def test_missing_arrays_are_legal(ptlib):
+    ubo = ptlib.Scene.load(scene_path('scene8')).pack_ubo()   # no plane / box / lens / cyclide keys
+    assert list(ubo[:7]) == [2, 0, 0, 0, 0, 1, 1]
+
+
+def test_bad_scene_is_an_error(ptlib):
+    with pytest.raises(ptlib.PtError):
+        ptlib.Scene.parse('{"camera": {"numShots": 3, "position": [], "angle": []}}')
+    with pytest.raises(ptlib.PtError):
+        ptlib.Scene.parse('{not json')
+    with pytest.raises(ptlib.PtError):
+        ptlib.Scene.load('/nonexistent/scene.json')
+    with pytest.raises(ptlib.PtError):
+        ptlib.Scene.load(scene_path('scene0')).pack_params(shot=9)
+
+
+def test_cie_table_exported(ptlib):
+    from pathtracer_b200 import api
+    assert np.array_equal(api.cie1931_table(), pack.cie_table())
