@@ -1144,6 +1144,10 @@ struct Shader {
         object.rotation = v3(0.0f, 90.0f - pc.cameraAngle[1], pc.cameraAngle[0]);
         object.materialID = 0;
         object.lightID = 0;
+#ifdef PT_COUNT
+        Counters* saved_cnt = g_cnt; /* the camera lens is part of Scene()'s fixed cost */
+        g_cnt = nullptr;
+#endif
         for (int i = 0; i < 2; i++) {
             float hitdist = 1e6f;
             V3 normal = v3(0.0f);
@@ -1164,6 +1168,9 @@ struct Shader {
             ray.origin = vfma(ray.dir, v3(hitdist), ray.origin);
             ray.dir = refract(ray.dir, normal, n12);
         }
+#ifdef PT_COUNT
+        g_cnt = saved_cnt;
+#endif
     }
 
     /* shader.comp:1446-1490 */
@@ -1269,8 +1276,18 @@ int oracle_max_threads(void) {
 /* main() of shader.comp:1525-1533 for every texel: one vkCmdDispatch.  image = W*H RGBA32F, read-modify-write.
  * Only in-range texels are processed (the reference's `>` bounds test lets row H / column W run and store out
  * of range: SURVEY App. C-2; those stores are not reproduced).  counters may be NULL (needs -DPT_COUNT). */
+int oracle_dispatch_rows(const pt_ubo* ubo, const pt_params* pc, float* image, unsigned long long* counters,
+                         int row_start, int row_step);
 int oracle_dispatch(const pt_ubo* ubo, const pt_params* pc, float* image, unsigned long long* counters) {
+    return oracle_dispatch_rows(ubo, pc, image, counters, 0, 1);
+}
+
+/* Same, restricted to rows row_start, row_start + row_step, ... of the full-resolution frame: a bounded but
+ * representative sample of the workload for the CPU baseline timings of bench.py. */
+int oracle_dispatch_rows(const pt_ubo* ubo, const pt_params* pc, float* image, unsigned long long* counters,
+                         int row_start, int row_step) {
     const Shader sh = make_shader(ubo, pc);
+    if (row_step < 1 || row_start < 0) return -1;
     const int W = pc->resolution[0], H = pc->resolution[1];
     if (W <= 0 || H <= 0 || pc->samplesPerFrame <= 0) return -1;
 #ifdef _OPENMP
@@ -1289,7 +1306,7 @@ int oracle_dispatch(const pt_ubo* ubo, const pt_params* pc, float* image, unsign
         g_cnt = &local;
 #endif
 #pragma omp for schedule(dynamic, 1)
-        for (int gy = 0; gy < H; gy++) {
+        for (int gy = row_start; gy < H; gy += row_step) {
             for (int gx = 0; gx < W; gx++) {
                 float* texel = image + 4 * ((size_t)gx + (size_t)W * (size_t)gy);
                 V3 in = v3(texel[0], texel[1], texel[2]);

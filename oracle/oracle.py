@@ -36,6 +36,7 @@ def lib(count=False):
         L.oracle_sdf_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p]
         L.oracle_math_eval.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.oracle_dispatch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_dispatch_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.oracle_samples.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.oracle_dispatch_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.oracle_load_sdf.argtypes = [C.c_char_p]
@@ -63,14 +64,15 @@ class Oracle:
             raise RuntimeError('oracle: cannot load SDF dispatchers %s' % self.sdf_so)
         self.L.oracle_set_threads(int(self.threads))
 
-    def dispatch(self, params, image):
-        """One vkCmdDispatch: image (H,W,4) float32 is read-modify-written. Returns counters dict if count."""
+    def dispatch(self, params, image, row_start=0, row_step=1):
+        """One vkCmdDispatch: image (H,W,4) float32 is read-modify-written. Returns counters dict if count.
+        row_start/row_step restrict it to a strided subset of rows (bounded CPU-baseline samples)."""
         self._bind()
         assert image.dtype == np.float32 and image.flags.c_contiguous
         params = np.ascontiguousarray(params)
         n = self.L.oracle_num_counters()
         cnt = np.zeros(n, dtype=np.uint64)
-        rc = self.L.oracle_dispatch(_p(self.ubo), _p(params), _p(image), _p(cnt))
+        rc = self.L.oracle_dispatch_rows(_p(self.ubo), _p(params), _p(image), _p(cnt), row_start, row_step)
         if rc != 0:
             raise RuntimeError('oracle_dispatch failed: %d' % rc)
         if self.count:
