@@ -82,6 +82,18 @@ int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::ve
                                 "PT_N_CYCLIDES_CONST", "PT_N_SDF_CONST"};
         for (int i = 0; i < 6; i++) src += std::string("#define ") + names[i] + " " + std::to_string(opt.counts[i]) + "\n";
     }
+    /* Driver selection and tuning knobs (env overrides are for A/B measurements: bench.py, profiles/).
+     * Measured on B200 (profiles/r01_sched_ab.md): scenes without SDFs are fastest with the v1 driver (nested
+     * loops), scenes with SDFs with the v2 in-warp scheduler; the fast build wants 6 CTAs/SM, the strict one 4. */
+    struct Knob { const char* name; int dflt; };
+    const Knob knobs[] = {{"PT_SCHED", sdf_unit.empty() ? 0 : 1}, {"PT_SDF_REPS", 8}, {"PT_FEED_T", 12},
+                          {"PT_MIN_BLOCKS", opt.mode == PT_MODE_FAST ? 6 : 4}, {"PT_NO_UNROLL", 0}, {"PT_STATS", 0}};
+    for (const Knob& k : knobs) {
+        const char* v = getenv(k.name);
+        const int val = (v && v[0]) ? atoi(v) : k.dflt;
+        if (std::string(k.name) == "PT_STATS" && val == 0) continue;
+        src += std::string("#define ") + k.name + " " + std::to_string(val) + "\n";
+    }
     src += "#include \"pt_kernel.cuh\"\n";
     src += sdf_unit;
     src += "\nPT_DEFINE_RENDER_KERNEL(pt_render_jit)\n";
@@ -97,7 +109,7 @@ int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::ve
                                           hdr_names.data());
     if (r != 0) { *log = std::string("nvrtcCreateProgram: ") + g_nvrtc.GetErrorString(r); return PT_ERR_COMPILE; }
 
-    std::vector<const char*> o = {"--gpu-architecture=sm_100a", "--std=c++17", "-default-device", "-lineinfo"};
+    std::vector<const char*> o = {"--gpu-architecture=sm_100a", "--std=c++17", "-default-device", "-lineinfo", "--ptxas-options=-v"};
     if (opt.mode == PT_MODE_FAST) {
         o.insert(o.end(), {"--fmad=true", "--prec-div=false", "--prec-sqrt=false", "--ftz=true"});
     } else {
@@ -126,6 +138,12 @@ int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::ve
     }
     cubin->resize(cs);
     g_nvrtc.GetCUBIN(prog, cubin->data());
+    if (const char* dir = getenv("PT_JIT_DUMP")) { /* keep the generated source and the cubin (profiling: nvdisasm -g) */
+        static int serial = 0;
+        const std::string base = std::string(dir) + "/pt_render_jit_" + std::to_string(serial++);
+        if (FILE* f = fopen((base + ".cu").c_str(), "w")) { fwrite(src.data(), 1, src.size(), f); fclose(f); }
+        if (FILE* f = fopen((base + ".cubin").c_str(), "wb")) { fwrite(cubin->data(), 1, cubin->size(), f); fclose(f); }
+    }
     g_nvrtc.DestroyProgram(&prog);
     *log = plog;
     return PT_OK;

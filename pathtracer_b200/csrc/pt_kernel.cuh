@@ -51,7 +51,11 @@
 #define PT_N_LENSES(c) (PT_N_LENSES_CONST)
 #define PT_N_CYCLIDES(c) (PT_N_CYCLIDES_CONST)
 #define PT_N_SDF(c) (PT_N_SDF_CONST)
+#if defined(PT_NO_UNROLL) && PT_NO_UNROLL
+#define PT_UNROLL_PRIMS _Pragma("unroll 1")
+#else
 #define PT_UNROLL_PRIMS _Pragma("unroll")
+#endif
 #else
 #define PT_N_SPHERES(c) ((c).sc->nSpheres)
 #define PT_N_PLANES(c) ((c).sc->nPlanes)
@@ -73,6 +77,8 @@
 #define PTK_DIV(a, b) __fdividef(a, b)
 #define PTK_MIN(x, y) fminf(x, y)
 #define PTK_MAX(x, y) fmaxf(x, y)
+static __device__ __forceinline__ float ptk_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+static __device__ __forceinline__ float ptk_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #else
 #define PTK_SIN(x) pt_sin(x)
 #define PTK_COS(x) pt_cos(x)
@@ -105,13 +111,29 @@ PT_DEV V3 operator*(V3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
 PT_DEV V3 operator*(float s, V3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
 PT_DEV V3 operator-(V3 a) { return mk3(-a.x, -a.y, -a.z); }
 PT_DEV V3 div3(V3 a, V3 b) { return mk3(PTK_DIV(a.x, b.x), PTK_DIV(a.y, b.y), PTK_DIV(a.z, b.z)); }
+#ifdef PT_FAST /* one MUFU.RCP shared by the components */
+PT_DEV V3 div3(V3 a, float s) { const float r = ptk_rcp(s); return mk3(a.x * r, a.y * r, a.z * r); }
+#else
 PT_DEV V3 div3(V3 a, float s) { return mk3(PTK_DIV(a.x, s), PTK_DIV(a.y, s), PTK_DIV(a.z, s)); }
+#endif
 PT_DEV V4 operator+(V4 a, V4 b) { return mk4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 PT_DEV V4 operator*(V4 a, V4 b) { return mk4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
 PT_DEV V4 operator*(V4 a, float s) { return mk4(a.x * s, a.y * s, a.z * s, a.w * s); }
 PT_DEV float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 PT_DEV float length(V3 a) { return PTK_SQRT(dot(a, a)); }
-PT_DEV V3 normalize(V3 a) { return div3(a, length(a)); }
+#ifdef PT_FAST
+PT_DEV V3 normalize(V3 a) { const float r = ptk_rsqrt(dot(a, a)); return mk3(a.x * r, a.y * r, a.z * r); }
+#else
+PT_DEV V3 normalize(V3 a) { return div3(a, length(a)); } /* GLSL 4.50 8.5: v / length(v) */
+#endif
+/* (b * num) / den per component, the shape of `EvaluateBRDF(...) * costheta / pdf` (shader.comp:1332,1374) */
+#ifdef PT_FAST
+PT_DEV V4 mulDiv4(V4 b, float num, float den) { const float k = num * ptk_rcp(den); return mk4(b.x * k, b.y * k, b.z * k, b.w * k); }
+#else
+PT_DEV V4 mulDiv4(V4 b, float num, float den) {
+    return mk4(PTK_DIV(b.x * num, den), PTK_DIV(b.y * num, den), PTK_DIV(b.z * num, den), PTK_DIV(b.w * num, den));
+}
+#endif
 PT_DEV V3 fma3(V3 a, float t, V3 c) { return mk3(fmaf(a.x, t, c.x), fmaf(a.y, t, c.y), fmaf(a.z, t, c.z)); }
 PT_DEV float gsign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
 PT_DEV float gstep(float e, float x) { return (x < e) ? 0.0f : 1.0f; }
@@ -133,17 +155,15 @@ struct Ctx {
     const PtDevScene* sc;   /* constant bank (kernel parameter) */
     const PtDevParams* pr;  /* constant bank (kernel parameter) */
     const float* ubo;       /* global: flat copy of the 4097-float uniform block */
-    const float* s_tab;     /* shared: ubo[PT_SH_BASE .. 4097) */
+    const float* s_tab;     /* shared: the whole 4097-float uniform block */
 };
 
-#define PT_SH_BASE (PT_OFF_MAT - 3) /* materials[-3..] (material index -1) up to the end of the CIE table */
+#define PT_SH_BASE 0 /* the whole block is staged: 16 388 B of shared memory per CTA, one LDS per table read */
 #define PT_SH_FLOATS (PT_UBO_FLOATS - PT_SH_BASE)
 
 /* clamped flat read of the uniform block: same rule as oracle Shader::at() */
 PT_DEV float uboAt(const Ctx& c, int flat) {
-    flat = flat < 0 ? 0 : (flat > PT_UBO_FLOATS - 1 ? PT_UBO_FLOATS - 1 : flat);
-    if (flat >= PT_SH_BASE) return c.s_tab[flat - PT_SH_BASE];
-    return __ldg(c.ubo + flat);
+    return c.s_tab[min(max(flat, 0), PT_UBO_FLOATS - 1)];
 }
 
 /* ---- RNG (shader.comp:937-958): pure uint32 arithmetic, bit-exact ------------------------------------------------ */
@@ -158,7 +178,8 @@ PT_DEV float RandomFloatPCG32(unsigned& seed) {
 }
 
 /* ---- spectral helpers ------------------------------------------------------------------------------------------ */
-/* shader.comp:129-140 */
+/* shader.comp:129-140.  index3 <= 1320; the +3..+5 reads of wave == 800 run past the table and clamp to the last
+ * float of the block like the oracle's (unreachable in practice: the bundle lives on [390, 720)). */
 PT_DEV V3 WaveToXYZ(const Ctx& c, float wave) {
     V3 XYZ = mk3(0.0f, 0.0f, 0.0f);
     if ((wave >= 360.0f) && (wave <= 800.0f)) {
@@ -166,14 +187,9 @@ PT_DEV V3 WaveToXYZ(const Ctx& c, float wave) {
         const int index3 = 3 * __float2int_rz(fl - 360.0f);
         const float a = wave - fl;
         const float oma = 1.0f - a;
-        const float* t = c.s_tab + (PT_OFF_CIE - PT_SH_BASE) + index3; /* index3 in [0, 1320]; +5 stays in range for wave < 800 */
-        if (index3 + 5 < PT_CIE_FLOATS) {
-            XYZ = mk3(t[0] * oma + t[3] * a, t[1] * oma + t[4] * a, t[2] * oma + t[5] * a);
-        } else { /* wave == 800: reads clamp at the end of the block like the oracle */
-            const int b = PT_OFF_CIE + index3;
-            XYZ = mk3(uboAt(c, b) * oma + uboAt(c, b + 3) * a, uboAt(c, b + 1) * oma + uboAt(c, b + 4) * a,
-                      uboAt(c, b + 2) * oma + uboAt(c, b + 5) * a);
-        }
+        const float* t = c.s_tab + PT_OFF_CIE;
+        const int i3 = min(index3 + 3, PT_CIE_FLOATS - 1), i4 = min(index3 + 4, PT_CIE_FLOATS - 1), i5 = min(index3 + 5, PT_CIE_FLOATS - 1);
+        XYZ = mk3(t[index3] * oma + t[i3] * a, t[index3 + 1] * oma + t[i4] * a, t[index3 + 2] * oma + t[i5] * a);
     }
     return XYZ;
 }
@@ -193,20 +209,44 @@ PT_DEV V4 EvaluateBRDF(V4 l, float peak, float sigma, float invertf) {
     const float oma = 1.0f - a;
     float r[4];
     const float lv[4] = {l.x, l.y, l.z, l.w};
+#ifdef PT_FAST
+    const float rden = ptk_rcp(den);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float x = (lv[i] - peak) * rden;
+        const float e = PTK_EXP(-x * x);
+        r[i] = (e * oma + (1.0f - e) * a) * 0.318309886f;
+    }
+#else
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const float x = PTK_DIV(lv[i] - peak, den);
         const float e = PTK_EXP(-x * x);
         r[i] = PTK_DIV(e * oma + (1.0f - e) * a, PT_PI_F);
     }
+#endif
     return mk4(r[0], r[1], r[2], r[3]);
 }
 
 /* shader.comp:1040-1055.  temperature/luminosity already clamped by max(., 0). */
 PT_DEV V4 Emit(V4 l, float temperature, float luminosity) {
-    const float peak = 4.0956746759e-6f * PTK_POW(temperature, 5.0f);
     float r[4];
     const float lv[4] = {l.x, l.y, l.z, l.w};
+#ifdef PT_FAST
+    /* same formula with the powers as multiplications and shared reciprocals: lum/peak * c1 * lm^-5 / (e^(c2/(lm T)) - 1) */
+    const float t2 = temperature * temperature;
+    const float k = luminosity * ptk_rcp(4.0956746759e-6f * (t2 * t2 * temperature));
+    const float rT = ptk_rcp(temperature);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float rl = ptk_rcp(lv[i] * 1e-9f);
+        const float rl2 = rl * rl;
+        const float num = 1.1910429724e-16f * (rl2 * rl2 * rl);
+        const float den = PTK_EXP(0.014387768775f * rl * rT) - 1.0f;
+        r[i] = num * ptk_rcp(den) * k;
+    }
+#else
+    const float peak = 4.0956746759e-6f * PTK_POW(temperature, 5.0f);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const float lm = lv[i] * 1e-9f;
@@ -214,6 +254,7 @@ PT_DEV V4 Emit(V4 l, float temperature, float luminosity) {
         const float den = PTK_EXP(PTK_DIV(0.014387768775f, lm * temperature)) - 1.0f;
         r[i] = PTK_DIV(PTK_DIV(num, den), peak) * luminosity;
     }
+#endif
     return mk4(r[0], r[1], r[2], r[3]);
 }
 
@@ -270,8 +311,7 @@ PT_DEV bool BoundingSphere(const Ray& ray, float px, float py, float pz, float r
 }
 
 /* shader.comp:289-317 */
-template <bool kShadow>
-PT_DEV void SphereIntersection(const Ray& ray, const PtDevSphere& o, int objectID, Hit& h) {
+PT_DEV void SphereIntersection(const Ray& ray, const PtDevSphere& o, int objectID, Hit& h, const bool kShadow) {
     const V3 lo = mk3(ray.origin.x - o.px, ray.origin.y - o.py, ray.origin.z - o.pz);
     const float b = 2.0f * dot(ray.dir, lo);
     const float cc = dot(lo, lo) - o.r2;
@@ -295,8 +335,7 @@ PT_DEV void SphereIntersection(const Ray& ray, const PtDevSphere& o, int objectI
 }
 
 /* shader.comp:319-335 */
-template <bool kShadow>
-PT_DEV void PlaneIntersection(const Ray& ray, const PtDevPlane& o, int objectID, Hit& h) {
+PT_DEV void PlaneIntersection(const Ray& ray, const PtDevPlane& o, int objectID, Hit& h, const bool kShadow) {
     const float loy = ray.origin.y - o.py;
     const float t = PTK_DIV(-loy, ray.dir.y);
     if (t < 1e-4f) return;
@@ -314,8 +353,7 @@ PT_DEV void PlaneIntersection(const Ray& ray, const PtDevPlane& o, int objectID,
 }
 
 /* shader.comp:337-364 */
-template <bool kShadow>
-PT_DEV void BoxIntersection(const Ray& ray, const PtDevBox& o, int objectID, Hit& h) {
+PT_DEV void BoxIntersection(const Ray& ray, const PtDevBox& o, int objectID, Hit& h, const bool kShadow) {
     const V3 lo = mulVM(mk3(ray.origin.x - o.px, ray.origin.y - o.py, ray.origin.z - o.pz), o.m);
     const V3 dir = mulVM(ray.dir, o.m);
     const V3 invdir = mk3(PTK_DIV(1.0f, dir.x), PTK_DIV(1.0f, dir.y), PTK_DIV(1.0f, dir.z));
@@ -345,54 +383,46 @@ PT_DEV void BoxIntersection(const Ray& ray, const PtDevBox& o, int objectID, Hit
     }
 }
 
-/* shader.comp:366-417 for one cap; returns true when it became the closest hit */
-template <bool kShadow>
-PT_DEV bool SphereSliceIntersection(const V3& lo0, const V3& ldir, const PtDevLens& o, bool is1stSlice, int objectID,
-                                    Hit& h, int& isOutside) {
-    V3 lo = lo0;
-    if (is1stSlice) lo.x += o.shift; else lo.x -= o.shift;
-    const float b = 2.0f * dot(ldir, lo);
-    const float cc = dot(lo, lo) - o.sradius2;
-    const float discriminant = b * b - 4.0f * cc;
-    if (discriminant < 0.0f) return false;
-    const float sqrtD = PTK_SQRT(discriminant);
-    float t1 = (-b - sqrtD) * 0.5f;
-    float t2 = (-b + sqrtD) * 0.5f;
-    if (is1stSlice) {
-        t1 = (fmaf(ldir.x, t1, lo.x) > -o.sliceOffset) ? 1e6f : t1;
-        t2 = (fmaf(ldir.x, t2, lo.x) > -o.sliceOffset) ? 1e6f : t2;
-    } else {
-        t1 = (fmaf(ldir.x, t1, lo.x) < o.sliceOffset) ? 1e6f : t1;
-        t2 = (fmaf(ldir.x, t2, lo.x) < o.sliceOffset) ? 1e6f : t2;
-    }
-    float t = (t1 > 0.0f) ? t1 : 1e6f;
-    int isOut = 1;
-    if (t2 < t) {
-        t = t2;
-        isOut = -1;
-    }
-    if (t < 1e-4f) return false;
-    if (t < h.t) {
-        h.t = t;
-        h.objectID = objectID;
-        if (!kShadow) {
-            h.normal = mulMV(o.m, normalize(fma3(ldir, t, lo) * (float)isOut));
-            isOutside = (o.invertSide == 0.0f) ? isOut : -isOut;
-            h.materialID = o.materialID;
-            h.lightID = o.lightID;
-        }
-        return true;
-    }
-    return false;
-}
-
-/* shader.comp:419-448 */
-template <bool kShadow>
-PT_DEV void LensIntersection(const Ray& ray, const PtDevLens& o, int objectID, Hit& h, int& isOutside) {
-    const V3 lo = mulVM(mk3(ray.origin.x - o.px, ray.origin.y - o.py, ray.origin.z - o.pz), o.m);
+/* shader.comp:366-448: LensIntersection = the two spherical caps of SphereSliceIntersection, first slice then
+ * second.  The caps differ only by a sign s = +1 / -1 (origin shift `+= shift` / `-= shift`, cut test
+ * `x > -sliceOffset` / `x < sliceOffset`, i.e. `s*x > -sliceOffset`; multiplying by +-1 is exact), so one copy of
+ * the code runs twice: the kernel is instruction-cache bound, and this body is instantiated for the scene's
+ * lenses and for the camera lens. */
+PT_DEV void LensIntersection(const Ray& ray, const PtDevLens& o, int objectID, Hit& h, int& isOutside, const bool kShadow) {
+    const V3 lo0 = mulVM(mk3(ray.origin.x - o.px, ray.origin.y - o.py, ray.origin.z - o.pz), o.m);
     const V3 ldir = mulVM(ray.dir, o.m);
-    SphereSliceIntersection<kShadow>(lo, ldir, o, true, objectID, h, isOutside);
-    SphereSliceIntersection<kShadow>(lo, ldir, o, false, objectID, h, isOutside);
+#pragma unroll 1
+    for (int slice = 0; slice < 2; slice++) {
+        const float s = (slice == 0) ? 1.0f : -1.0f;
+        V3 lo = lo0;
+        lo.x += s * o.shift;
+        const float b = 2.0f * dot(ldir, lo);
+        const float cc = dot(lo, lo) - o.sradius2;
+        const float discriminant = b * b - 4.0f * cc;
+        if (discriminant < 0.0f) continue;
+        const float sqrtD = PTK_SQRT(discriminant);
+        float t1 = (-b - sqrtD) * 0.5f;
+        float t2 = (-b + sqrtD) * 0.5f;
+        t1 = ((s * fmaf(ldir.x, t1, lo.x)) > -o.sliceOffset) ? 1e6f : t1;
+        t2 = ((s * fmaf(ldir.x, t2, lo.x)) > -o.sliceOffset) ? 1e6f : t2;
+        float t = (t1 > 0.0f) ? t1 : 1e6f;
+        int isOut = 1;
+        if (t2 < t) {
+            t = t2;
+            isOut = -1;
+        }
+        if (t < 1e-4f) continue;
+        if (t < h.t) {
+            h.t = t;
+            h.objectID = objectID;
+            if (!kShadow) {
+                h.normal = mulMV(o.m, normalize(fma3(ldir, t, lo) * (float)isOut));
+                isOutside = (o.invertSide == 0.0f) ? isOut : -isOut;
+                h.materialID = o.materialID;
+                h.lightID = o.lightID;
+            }
+        }
+    }
 }
 
 /* ---- Dupin cyclide (shader.comp:450-541, 633-679) ------------------------------------------------------------ */
@@ -470,8 +500,7 @@ PT_DEV float SolveQuarticNearest(float a, float b, float c, float d, float e) {
 }
 
 /* shader.comp:633-679 */
-template <bool kShadow>
-PT_DEV_NOINLINE void DupinCyclide(const Ray& ray, const PtDevCyclide& ob, int objectID, Hit& h) {
+PT_DEV_NOINLINE void DupinCyclide(const Ray& ray, const PtDevCyclide& ob, int objectID, Hit& h, const bool kShadow) {
     const V3 lo = mulVM(mk3(ray.origin.x - ob.px, ray.origin.y - ob.py, ray.origin.z - ob.pz), ob.m);
     const V3 ld = mulVM(ray.dir, ob.m);
     /* .xzy swizzle after the divide by scale */
@@ -563,8 +592,7 @@ PT_DEV bool SearchSDF(const Ctx& c, V3 p, V3 invdir, float& tMin, float& tMax, u
 }
 
 /* shader.comp:779-860.  For shadow rays the normal probes and the material are skipped (never read). */
-template <bool kShadow>
-PT_DEV_NOINLINE void SphereTracing(const Ctx& c, const Ray& ray, Hit& h) {
+PT_DEV_NOINLINE void SphereTracing(const Ctx& c, const Ray& ray, Hit& h, const bool kShadow) {
     const float MAXDIST = 1e5f;
     float t = 1e-3f;
     float insT = 0.0f;
@@ -635,8 +663,7 @@ PT_DEV_NOINLINE void SphereTracing(const Ctx& c, const Ray& ray, Hit& h) {
 #endif /* PT_HAS_SDF */
 
 /* shader.comp:862-934 (kShadow = false) and 1121-1216 (kShadow = true): brute-force closest hit in type order */
-template <bool kShadow>
-PT_DEV void Intersection(const Ctx& c, const Ray& ray, Hit& h) {
+PT_DEV void IntersectionAnalytic(const Ctx& c, const Ray& ray, Hit& h, const bool kShadow) {
     const PtDevScene& sc = *c.sc;
     h.t = 1e5f;
     h.objectID = -1;
@@ -648,18 +675,18 @@ PT_DEV void Intersection(const Ctx& c, const Ray& ray, Hit& h) {
     int base = 0;
     const int nS = PT_N_SPHERES(c);
     PT_UNROLL_PRIMS
-    for (int i = 0; i < nS; i++) SphereIntersection<kShadow>(ray, sc.spheres[i], base + i, h);
+    for (int i = 0; i < nS; i++) SphereIntersection(ray, sc.spheres[i], base + i, h, kShadow);
     base += nS;
     const int nP = PT_N_PLANES(c);
     PT_UNROLL_PRIMS
-    for (int i = 0; i < nP; i++) PlaneIntersection<kShadow>(ray, sc.planes[i], base + i, h);
+    for (int i = 0; i < nP; i++) PlaneIntersection(ray, sc.planes[i], base + i, h, kShadow);
     base += nP;
     const int nB = PT_N_BOXES(c);
     PT_UNROLL_PRIMS
     for (int i = 0; i < nB; i++) {
         const PtDevBox& o = sc.boxes[i];
         if (!BoundingSphere(ray, o.px, o.py, o.pz, o.bound2)) continue;
-        BoxIntersection<kShadow>(ray, o, base + i, h);
+        BoxIntersection(ray, o, base + i, h, kShadow);
     }
     base += nB;
     const int nL = PT_N_LENSES(c);
@@ -668,17 +695,22 @@ PT_DEV void Intersection(const Ctx& c, const Ray& ray, Hit& h) {
         const PtDevLens& o = sc.lenses[i];
         if (!BoundingSphere(ray, o.px, o.py, o.pz, o.bound2)) continue;
         int isOutside = 1;
-        LensIntersection<kShadow>(ray, o, base + i, h, isOutside);
+        LensIntersection(ray, o, base + i, h, isOutside, kShadow);
     }
     base += nL;
     const int nC = PT_N_CYCLIDES(c);
     for (int i = 0; i < nC; i++) {
         const PtDevCyclide& o = sc.cyclides[i];
         if (!BoundingSphere(ray, o.px, o.py, o.pz, o.brad)) continue;
-        DupinCyclide<kShadow>(ray, o, base + i, h);
+        DupinCyclide(ray, o, base + i, h, kShadow);
     }
+}
+
+/* shader.comp:862-934 / 1121-1216 in one piece (used by the v1 driver) */
+PT_DEV void Intersection(const Ctx& c, const Ray& ray, Hit& h, const bool kShadow) {
+    IntersectionAnalytic(c, ray, h, kShadow);
 #if PT_HAS_SDF
-    SphereTracing<kShadow>(c, ray, h);
+    SphereTracing(c, ray, h, kShadow);
 #endif
 }
 
@@ -723,7 +755,7 @@ PT_DEV V4 TracePath(const Ctx& c, V4 l, Ray ray, unsigned& seed) {
     for (int bounce = 0; bounce < pathLength; bounce++) {
         /* TraceRay, shader.comp:1345-1391 */
         Hit h;
-        Intersection<false>(c, ray, h);
+        Intersection(c, ray, h, false);
         if (!(h.t < 1e5f)) break; /* miss: black environment */
         float temperature, luminosity;
         GetLightMix(c, h.lightID, temperature, luminosity);
@@ -761,12 +793,11 @@ PT_DEV V4 TracePath(const Ctx& c, V4 l, Ray ray, unsigned& seed) {
             if (costheta >= 0.0f) {
                 if (RandomFloatPCG32(seed) > deathProbability) {
                     Hit sh;
-                    Intersection<true>(c, shadowRay, sh);
+                    Intersection(c, shadowRay, sh, true);
                     if (sh.objectID == ls.objectID) {
                         float lt, ll;
                         GetLightMix(c, ls.lightID, lt, ll);
-                        const V4 rr = rayradiance * mk4(PTK_DIV(brdf.x * costheta, lightpdf), PTK_DIV(brdf.y * costheta, lightpdf),
-                                                        PTK_DIV(brdf.z * costheta, lightpdf), PTK_DIV(brdf.w * costheta, lightpdf));
+                        const V4 rr = rayradiance * mulDiv4(brdf, costheta, lightpdf);
                         const V4 e = Emit(l, PTK_MAX(lt, 0.0f), PTK_MAX(ll, 0.0f));
                         radiance = radiance + (e * rr) * (1.0f - MISBRDFWeight);
                     }
@@ -779,8 +810,7 @@ PT_DEV V4 TracePath(const Ctx& c, V4 l, Ray ray, unsigned& seed) {
         }
 
         const float costheta = dot(outRay.dir, h.normal);
-        rayradiance = rayradiance * mk4(PTK_DIV(brdf.x * costheta, BRDFpdf), PTK_DIV(brdf.y * costheta, BRDFpdf),
-                                        PTK_DIV(brdf.z * costheta, BRDFpdf), PTK_DIV(brdf.w * costheta, BRDFpdf));
+        rayradiance = rayradiance * mulDiv4(brdf, costheta, BRDFpdf);
         const float mx = PTK_MAX(rayradiance.x, PTK_MAX(rayradiance.y, PTK_MAX(rayradiance.z, rayradiance.w)));
         const float rayProbability = PTK_MIN(PTK_MAX(mx, 0.0f), 0.99f);
         if (RandomFloatPCG32(seed) > rayProbability) break;
@@ -800,7 +830,7 @@ PT_DEV void TracePathLens(const Ctx& c, float l, Ray& ray) {
         h.normal = mk3(0.0f, 0.0f, 0.0f);
         h.materialID = 0.0f; h.lightID = -1.0f; h.objectID = -1;
         int isOutside = 1;
-        LensIntersection<false>(ray, lens, 0, h, isOutside);
+        LensIntersection(ray, lens, 0, h, isOutside, false);
         float n1 = 1.0f, n2 = 1.0f;
         if (isOutside == 1) n2 = RefractiveIndexBK7Glass(l); else n1 = RefractiveIndexBK7Glass(l);
         const float n12 = PTK_DIV(n1, n2);
@@ -858,31 +888,8 @@ PT_DEV V3 Scene(const Ctx& c, unsigned xyx, unsigned xyy, float uvx, float uvy, 
     return color;
 }
 
-/* main() + Rendering() + Accumulate(), shader.comp:1492-1533.
- * Grid: 2-D tiles of 16x8 pixels per 128-thread block; each warp owns an 8x4 sub-tile. */
-__device__ __forceinline__ void pt_render_body(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
-                                               float4* __restrict__ image, float* s_tab) {
-    for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
-    __syncthreads();
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int gy = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
-    if (gx >= pr.width || gy >= pr.height) return;
-
-    Ctx c;
-    c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
-
-    const unsigned xyx = (unsigned)gx;
-    const unsigned xyy = (unsigned)pr.height - (unsigned)gy; /* shader.comp:1510 */
-    const float uvx = PTK_DIV(2.0f * __uint2float_rn(xyx) - pr.resX, pr.resY);
-    const float uvy = PTK_DIV(2.0f * __uint2float_rn(xyy) - pr.resY, pr.resY);
-
-    V3 outColor = mk3(0.0f, 0.0f, 0.0f);
-    const int spf = pr.samplesPerFrame;
-#pragma unroll 1
-    for (int k = 0; k < spf; k++) outColor = outColor + Scene(c, xyx, xyy, uvx, uvy, k);
-
+/* Rendering()'s tail + Accumulate() + imageStore, shader.comp:1492-1533 */
+PT_DEV void StoreTexel(const PtDevParams& pr, float4* __restrict__ image, int gx, int gy, V3 outColor) {
     float4* texel = image + ((size_t)gx + (size_t)pr.width * (size_t)gy);
     if (pr.accumMode == 2) { /* raw sum for the sample-split path (pt_dispatch_sum) */
         float4 v = *texel;
@@ -903,6 +910,391 @@ __device__ __forceinline__ void pt_render_body(const PtDevScene& sc, const PtDev
                        PTK_DIV(nm1 * in.z + outColor.z, n));
     }
     *texel = make_float4(outColor.x, outColor.y, outColor.z, 1.0f);
+}
+
+/* ---- driver v1: one thread = one pixel, nested sample / bounce loops (kept for A/B measurements, PT_SCHED=0) ----
+ * Grid: 2-D tiles of 16x8 pixels per 128-thread block; each warp owns an 8x4 sub-tile. */
+__device__ __forceinline__ void pt_render_body_v1(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
+                                                  float4* __restrict__ image, float* s_tab) {
+    for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int gy = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    if (gx >= pr.width || gy >= pr.height) return;
+
+    Ctx c;
+    c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
+
+    const unsigned xyx = (unsigned)gx;
+    const unsigned xyy = (unsigned)pr.height - (unsigned)gy; /* shader.comp:1510 */
+    const float uvx = PTK_DIV(2.0f * __uint2float_rn(xyx) - pr.resX, pr.resY);
+    const float uvy = PTK_DIV(2.0f * __uint2float_rn(xyy) - pr.resY, pr.resY);
+
+    V3 outColor = mk3(0.0f, 0.0f, 0.0f);
+    const int spf = pr.samplesPerFrame;
+#pragma unroll 1
+    for (int k = 0; k < spf; k++) outColor = outColor + Scene(c, xyx, xyy, uvx, uvy, k);
+    StoreTexel(pr, image, gx, gy, outColor);
+}
+
+/* ---- driver v2: in-warp scheduled state machine (default) ---------------------------------------------------------
+ * v1 leaves most lanes idle: a warp waits for its longest path at every sample, the shadow ray runs under a
+ * divergent branch, and with SDFs only the lanes whose ray entered a bounding box march, for 1..512 steps each
+ * (ncu on v1: 17.3 of 32 lanes active on scene1, 7.5 of 32 on the mandelbulb scene).
+ * Here every lane is a small state machine over the SAME per-lane arithmetic, in the same order (so strict mode
+ * stays bit-exact), and the warp executes one phase per iteration, chosen by ballot as the phase most lanes wait for:
+ *   NEW    camera ray + lens + wavelengths for the lane's next sample index        (Scene(), shader.comp:1446-1472)
+ *   ISECT  brute-force primitives for the lane's current ray, path OR shadow ray alike (one copy of the
+ *          intersection code runs at full width), then SearchSDF                   (shader.comp:862-924, 1121-1205)
+ *   SDF    ONE evaluation of the injected SDF(): sign probe, march step or one of the six normal probes -- every
+ *          consumer of the distance function funnels through this single site       (shader.comp:779-860, 721-730)
+ *   SHADE  emitter / BSDF sample / light sample with MIS / Russian roulette, or resolution of a pending shadow
+ *          ray; a finished path is projected to XYZ and the lane goes back to NEW  (shader.comp:1298-1407, 1477-1489)
+ * A lane that finishes early refills itself with its pixel's next sample instead of idling, so the expensive
+ * phases run with most lanes populated.  All state stays in registers: no queues, no HBM traffic. */
+enum { PT_ST_NEW = 0, PT_ST_ISECT = 1, PT_ST_SDF = 2, PT_ST_SHADE = 3, PT_ST_DONE = 4 };
+#ifdef PT_STATS
+/* scheduling statistics (debug builds only, env PT_STATS=1): per phase, [2p] = executions, [2p+1] = lanes served */
+} /* namespace */
+extern "C" __device__ unsigned long long pt_stats[16];
+namespace PT_KERNEL_NS {
+#define PT_STAT(p, mask) do { if ((threadIdx.x & 31) == 0) { atomicAdd(&pt_stats[2 * (p)], 1ull); atomicAdd(&pt_stats[2 * (p) + 1], (unsigned long long)__popc(mask)); } } while (0)
+#else
+#define PT_STAT(p, mask) do { } while (0)
+#endif
+enum { PT_SUB_SIGN = 0, PT_SUB_STEP = 1, PT_SUB_N0 = 2 }; /* N0..N5 = 2..7: +x -x +y -y +z -z */
+#ifndef PT_SDF_REPS
+#define PT_SDF_REPS 4
+#endif
+#ifndef PT_FEED_T
+#define PT_FEED_T 8
+#endif
+
+__device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
+                                                  float4* __restrict__ image, float* s_tab) {
+    for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int gy = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const bool inRange = (gx < pr.width) && (gy < pr.height);
+
+    Ctx c;
+    c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
+
+    const unsigned xyx = (unsigned)gx;
+    const unsigned xyy = (unsigned)pr.height - (unsigned)gy; /* shader.comp:1510 */
+    const float uvx0 = PTK_DIV(2.0f * __uint2float_rn(xyx) - pr.resX, pr.resY);
+    const float uvy0 = PTK_DIV(2.0f * __uint2float_rn(xyy) - pr.resY, pr.resY);
+    const int spf = pr.samplesPerFrame;
+    const int pathLength = pr.pathLength;
+    const V3 camPos = mk3(pr.camPosX, pr.camPosY, pr.camPosZ);
+
+    int st = (inRange && spf > 0) ? PT_ST_NEW : PT_ST_DONE;
+    int k = 0;
+    V3 outColor = mk3(0.0f, 0.0f, 0.0f);
+    /* per-sample state */
+    unsigned seed = 0u;
+    V4 l = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    V4 radiance = l, rayradiance = l;
+    float MISBRDFWeight = 1.0f;
+    int bounce = 0;
+    Ray ray;
+    ray.origin = mk3(0.0f, 0.0f, 0.0f);
+    ray.dir = ray.origin;
+    /* pending shadow ray (traced before the next path ray; LightSourceVisibilityCheck draws no random numbers) */
+    bool isShadow = false, pathAlive = false;
+    V3 shDir = ray.origin, nextDir = ray.origin;
+    V4 shContrib = l;
+    int shObj = 0;
+    Hit h;
+    h.t = 1e5f; h.normal = ray.origin; h.materialID = 0.0f; h.lightID = -1.0f; h.objectID = -1;
+#if PT_HAS_SDF
+    float mt = 0.0f, insT = 0.0f, omega = 1.7f, previousRadius = 0.0f, tMin = 1e5f, tMax = 1e5f, ksign = 0.0f;
+    float probe = 0.0f, nrm0 = 0.0f, nrm1 = 0.0f, nrm2 = 0.0f;
+    int points = 0, iter = 0, sub = PT_SUB_SIGN;
+    unsigned set1 = 0u;
+#endif
+
+    bool pendingFinish = false; /* a finished path whose radiance is still to be projected to XYZ (done in NEW) */
+
+    for (;;) {
+        const unsigned bNew = __ballot_sync(0xffffffffu, st == PT_ST_NEW);
+        const unsigned bIs = __ballot_sync(0xffffffffu, st == PT_ST_ISECT);
+        const unsigned bSh = __ballot_sync(0xffffffffu, st == PT_ST_SHADE);
+#if PT_HAS_SDF
+        const unsigned bSdf = __ballot_sync(0xffffffffu, st == PT_ST_SDF);
+#else
+        const unsigned bSdf = 0u;
+#endif
+        if ((bNew | bIs | bSdf | bSh) == 0u) break;
+        /* Phase selection.  Executing a phase costs the same whatever its population, so the expensive phase
+         * should run as full as possible.  With SDFs that is the SDF phase (tens of evaluations per ray against
+         * one intersect/shade per ray): the other three phases are "feeders" and run first whenever PT_FEED_T or
+         * more lanes wait in one of them (the fullest feeder wins; ties go to the later pipeline stage); only
+         * when every feeder is below the threshold do the marching lanes take their PT_SDF_REPS steps.  Without
+         * SDFs this degenerates to "the phase most lanes are waiting for". */
+        int phase = PT_ST_NEW, best = __popc(bNew);
+        if (__popc(bIs) >= best) { best = __popc(bIs); phase = PT_ST_ISECT; }
+        if (__popc(bSh) >= best) { best = __popc(bSh); phase = PT_ST_SHADE; }
+#if PT_HAS_SDF
+        if (bSdf != 0u && (best < PT_FEED_T || best == 0)) phase = PT_ST_SDF;
+#endif
+
+        PT_STAT(phase, phase == PT_ST_NEW ? bNew : (phase == PT_ST_ISECT ? bIs : (phase == PT_ST_SDF ? bSdf : bSh)));
+        if (phase == PT_ST_NEW) {
+            if (st == PT_ST_NEW) {
+                if (pendingFinish) { /* Scene()'s tail, shader.comp:1477-1489: radiance -> XYZ, drop NaNs */
+                    const V3 w0 = WaveToXYZ(c, l.x), w1 = WaveToXYZ(c, l.y), w2 = WaveToXYZ(c, l.z), w3 = WaveToXYZ(c, l.w);
+                    V3 color;
+                    color.x = 0.0f + (radiance.x * w0.x + radiance.y * w1.x + radiance.z * w2.x + radiance.w * w3.x) * 330.0f * 0.25f;
+                    color.y = 0.0f + (radiance.x * w0.y + radiance.y * w1.y + radiance.z * w2.y + radiance.w * w3.y) * 330.0f * 0.25f;
+                    color.z = 0.0f + (radiance.x * w0.z + radiance.y * w1.z + radiance.z * w2.z + radiance.w * w3.z) * 330.0f * 0.25f;
+                    if ((color.x != color.x) || (color.y != color.y) || (color.z != color.z)) color = mk3(0.0f, 0.0f, 0.0f);
+                    outColor = outColor + color;
+                    pendingFinish = false;
+                }
+                if (k < spf) { /* Scene(), shader.comp:1446-1472 */
+                    seed = (unsigned)(pr.firstSample + k); /* GenerateSeed, shader.comp:948-958 */
+                    PCG32(seed);
+                    seed += xyx + (unsigned)pr.width * xyy;
+                    k++;
+                    const float j1 = RandomFloatPCG32(seed);
+                    const float j2 = RandomFloatPCG32(seed);
+                    float uvx = uvx0 + PTK_DIV(2.0f * j1 - 0.5f, pr.resX);
+                    float uvy = uvy0 + PTK_DIV(2.0f * j2 - 0.5f, pr.resY);
+                    uvx *= pr.sensorScale;
+                    uvy *= pr.sensorScale;
+                    ray.origin = camPos + mulVM(mk3(uvx, uvy, 0.0f), pr.camM);
+                    const float rx = RandomFloatPCG32(seed);
+                    const float ry = RandomFloatPCG32(seed);
+                    const float phi = 2.0f * PT_PI_F * ry;
+                    const float dd = PTK_SQRT(rx);
+                    const float diskx = pr.halfAperture * (dd * PTK_COS(phi));
+                    const float disky = pr.halfAperture * (dd * PTK_SIN(phi));
+                    const V3 pointOnAperture = camPos + mulVM(mk3(diskx, disky, pr.apertureDist), pr.camM);
+                    ray.dir = normalize(pointOnAperture - ray.origin);
+                    const float r5 = RandomFloatPCG32(seed);
+                    const float l_h = 360.0f * (1.0f - r5) + 800.0f * r5;
+                    TracePathLens(c, l_h, ray);
+                    l = SampleWavelengths(l_h);
+                    radiance = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+                    rayradiance = mk4(1.0f, 1.0f, 1.0f, 1.0f);
+                    MISBRDFWeight = 1.0f;
+                    bounce = 0;
+                    isShadow = false;
+                    if (pathLength > 0) st = PT_ST_ISECT; else pendingFinish = true; /* stays in NEW */
+                } else {
+                    st = PT_ST_DONE;
+                }
+            }
+        } else if (phase == PT_ST_ISECT) {
+            if (st == PT_ST_ISECT) { /* Intersection / LightSourceVisibilityCheck up to the SDF part */
+                Ray r;
+                r.origin = ray.origin;
+                r.dir = isShadow ? shDir : ray.dir;
+                IntersectionAnalytic(c, r, h, isShadow);
+                st = PT_ST_SHADE;
+#if PT_HAS_SDF
+                /* SphereTracing's prologue, shader.comp:780-801 */
+                const V3 invdir = mk3(PTK_DIV(1.0f, r.dir.x), PTK_DIV(1.0f, r.dir.y), PTK_DIV(1.0f, r.dir.z));
+                tMin = 1e5f; tMax = 1e5f;
+                if (SearchSDF(c, r.origin, invdir, tMin, tMax, set1)) {
+                    mt = PTK_MAX(tMin, 1e-3f);
+                    insT = 0.0f; omega = 1.70f; previousRadius = 0.0f; points = 0; iter = 0;
+                    sub = PT_SUB_SIGN;
+                    st = PT_ST_SDF;
+                }
+#endif
+            }
+        }
+#if PT_HAS_SDF
+        else if (phase == PT_ST_SDF) {
+#pragma unroll 1
+            for (int rep = 0; rep < PT_SDF_REPS; rep++) {
+                if (st == PT_ST_SDF) {
+                    const V3 dir = isShadow ? shDir : ray.dir;
+                    V3 pe = ray.origin;
+                    if (sub != PT_SUB_SIGN) {
+                        pe = fma3(dir, mt, ray.origin);
+                        if (sub >= PT_SUB_N0) { /* CalculateNumericalSDFNormals, shader.comp:721-730: p +- h.xyy etc. */
+                            const int j = sub - PT_SUB_N0, axis = j >> 1;
+                            const float ex = (axis == 0) ? 1e-4f : 0.0f, ey = (axis == 1) ? 1e-4f : 0.0f, ez = (axis == 2) ? 1e-4f : 0.0f;
+                            pe = (j & 1) ? mk3(pe.x - ex, pe.y - ey, pe.z - ez) : mk3(pe.x + ex, pe.y + ey, pe.z + ez);
+                        }
+                    }
+                    const float d = SDF(pe, set1); /* the one SDF() site of the kernel */
+                    if (sub == PT_SUB_SIGN) { /* shader.comp:801 */
+                        ksign = gsign(d);
+                        sub = PT_SUB_STEP;
+                    } else if (sub == PT_SUB_STEP) { /* one iteration of the loop at shader.comp:803-849 */
+                        const float radius = d;
+                        bool finished = false, nohit = false;
+                        if (insT > (fabsf(previousRadius) + fabsf(radius))) {
+                            mt -= insT;
+                            omega = 1.0f;
+                            insT = previousRadius * omega * ksign;
+                            mt += insT;
+                        } else if (fabsf(radius) < 1e-4f) {
+                            finished = true;
+                        } else {
+                            if (mt > tMax) points += 1; else points = 0;
+                            if (points >= 2) {
+                                mt = tMax + 1e-3f;
+                                tMin = 1e5f; tMax = 1e5f;
+                                const V3 invdir = mk3(PTK_DIV(1.0f, dir.x), PTK_DIV(1.0f, dir.y), PTK_DIV(1.0f, dir.z));
+                                if (SearchSDF(c, fma3(dir, mt, ray.origin), invdir, tMin, tMax, set1)) {
+                                    tMin += mt; tMax += mt;
+                                    mt = PTK_MAX(tMin, mt);
+                                } else {
+                                    nohit = true;
+                                }
+                            } else {
+                                insT = radius * omega * ksign;
+                                mt += insT;
+                                const float omegaSpeedFactor = PTK_MIN(PTK_DIV(radius, previousRadius), 0.99f);
+                                omega += 0.20f * (PTK_MIN(PTK_DIV(1.0f, 1.0f - omegaSpeedFactor), 1.70f) - omega);
+                                previousRadius = radius;
+                            }
+                        }
+                        if (!finished && !nohit) {
+                            iter++;
+                            if (iter >= 512) finished = true; /* falls through to "hit" unconverged: SURVEY App. C-9 */
+                        }
+                        if (nohit) {
+                            st = PT_ST_SHADE;
+                        } else if (finished) { /* shader.comp:851-858 */
+                            if (mt < h.t) {
+                                h.t = mt - 1e-3f;
+                                h.objectID = -1;
+                                if (isShadow) st = PT_ST_SHADE; else sub = PT_SUB_N0;
+                            } else {
+                                st = PT_ST_SHADE;
+                            }
+                        }
+                    } else {
+                        const int j = sub - PT_SUB_N0;
+                        if ((j & 1) == 0) {
+                            probe = d;
+                        } else {
+                            const float g = probe - d;
+                            if (j == 1) nrm0 = g; else if (j == 3) nrm1 = g; else nrm2 = g;
+                        }
+                        sub++;
+                        if (j == 5) {
+                            const V3 p = fma3(dir, mt, ray.origin);
+                            h.normal = normalize(mk3(nrm0, nrm1, nrm2));
+                            h.materialID = ::pt_sdfmaterial_dispatch(p.x, p.y, p.z, set1);
+                            h.lightID = -1.0f;
+                            st = PT_ST_SHADE;
+                        }
+                    }
+                }
+            }
+        }
+#endif
+        else { /* PT_ST_SHADE */
+            if (st == PT_ST_SHADE) {
+                bool done = false; /* path finished: project it in the NEW phase */
+                if (isShadow) { /* LightSourceVisibilityCheck's verdict, shader.comp:1218-1222, 1328-1334 */
+                    if (h.objectID == shObj) radiance = radiance + shContrib;
+                    isShadow = false;
+                    if (pathAlive) { ray.dir = nextDir; st = PT_ST_ISECT; } else done = true;
+                } else if (!(h.t < 1e5f)) { /* TraceRay, shader.comp:1345-1391: miss */
+                    done = true;
+                } else {
+                    float emitT, emitL; /* the light Emit() is evaluated for: the one hit, or the one sampled */
+                    GetLightMix(c, h.lightID, emitT, emitL);
+                    const bool emitterHit = emitL > 0.0f; /* terminates the path, shader.comp:1359-1364 */
+                    bool needShadow = false, alive = false;
+                    V4 rr = rayradiance;
+                    float emitScale = MISBRDFWeight;
+                    V3 outOrigin = ray.origin, outDir = ray.dir;
+                    if (!emitterHit) {
+                        float peak, sigma, invertf;
+                        GetMaterialMix(c, h.materialID, peak, sigma, invertf);
+                        const V4 brdf = EvaluateBRDF(l, peak, sigma, invertf);
+                        outOrigin = fma3(ray.dir, h.t, ray.origin);
+                        outDir = SampleCosineDirectionHemisphere(h.normal, seed);
+                        const float BRDFpdf = PTK_DIV(dot(outDir, h.normal), PT_PI_F);
+                        if (sc.numLights > 0.0f) { /* SampleLightSource, shader.comp:1298-1343 */
+                            const int randomLight = __float2int_rz(floorf(RandomFloatPCG32(seed) * sc.numLights));
+                            const PtDevLightSlot& ls = sc.lightSlots[randomLight < sc.nLightSlots ? randomLight : sc.nLightSlots - 1];
+                            const V3 toLight = mk3(ls.px - outOrigin.x, ls.py - outOrigin.y, ls.pz - outOrigin.z);
+                            const float invLightDistance = PTK_DIV(1.0f, length(toLight));
+                            const V3 lightDir = toLight * invLightDistance;
+                            const float sinthetaMax = PTK_MIN(ls.boundingRadius * invLightDistance, 1.0f);
+                            const float costhetaMax = PTK_SQRT(1.0f - sinthetaMax * sinthetaMax);
+                            const V3 sdir = ToWorld(SampleCosineUnitCone(seed, costhetaMax), lightDir);
+                            float lightpdf = sc.invNumLights;
+                            lightpdf *= PTK_DIV(dot(sdir, lightDir), PT_PI_F * (1.0f - costhetaMax * costhetaMax));
+                            MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + lightpdf * lightpdf);
+                            const float costheta = dot(sdir, h.normal);
+                            const float deathProbability = 1.25f * PTK_MAX(MISBRDFWeight - 0.2f, 0.0f);
+                            if (costheta >= 0.0f) {
+                                if (RandomFloatPCG32(seed) > deathProbability) {
+                                    GetLightMix(c, ls.lightID, emitT, emitL);
+                                    rr = rayradiance * mulDiv4(brdf, costheta, lightpdf);
+                                    emitScale = 1.0f - MISBRDFWeight;
+                                    shDir = sdir;
+                                    shObj = ls.objectID;
+                                    needShadow = true;
+                                } else {
+                                    MISBRDFWeight = 1.0f;
+                                }
+                            }
+                        } else {
+                            MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + 0.0f * 0.0f);
+                        }
+                        const float costheta = dot(outDir, h.normal);
+                        rayradiance = rayradiance * mulDiv4(brdf, costheta, BRDFpdf);
+                        const float mx = PTK_MAX(rayradiance.x, PTK_MAX(rayradiance.y, PTK_MAX(rayradiance.z, rayradiance.w)));
+                        const float rayProbability = PTK_MIN(PTK_MAX(mx, 0.0f), 0.99f);
+                        alive = !(RandomFloatPCG32(seed) > rayProbability);
+                        if (alive) rayradiance = rayradiance * PTK_DIV(1.0f, rayProbability);
+                        bounce++;
+                        if (bounce >= pathLength) alive = false; /* TracePath's loop bound, shader.comp:1400 */
+                    }
+                    if (emitterHit || needShadow) { /* the one Emit() site: (Emit * rr) * scale in both uses */
+                        const V4 e = Emit(l, PTK_MAX(emitT, 0.0f), PTK_MAX(emitL, 0.0f));
+                        const V4 contrib = (e * rr) * emitScale;
+                        if (emitterHit) radiance = radiance + contrib; else shContrib = contrib;
+                    }
+                    ray.origin = outOrigin;
+                    if (emitterHit) {
+                        done = true;
+                    } else if (needShadow) {
+                        isShadow = true;
+                        nextDir = outDir;
+                        pathAlive = alive;
+                        st = PT_ST_ISECT;
+                    } else if (alive) {
+                        ray.dir = outDir;
+                        st = PT_ST_ISECT;
+                    } else {
+                        done = true;
+                    }
+                }
+                if (done) { pendingFinish = true; st = PT_ST_NEW; }
+            }
+        }
+    }
+    if (inRange) StoreTexel(pr, image, gx, gy, outColor);
+}
+
+#ifndef PT_SCHED
+#define PT_SCHED 1
+#endif
+__device__ __forceinline__ void pt_render_body(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
+                                               float4* __restrict__ image, float* s_tab) {
+#if PT_SCHED
+    pt_render_body_v2(sc, pr, ubo, image, s_tab);
+#else
+    pt_render_body_v1(sc, pr, ubo, image, s_tab);
+#endif
 }
 
 } /* namespace PT_KERNEL_NS */

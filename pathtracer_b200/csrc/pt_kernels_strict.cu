@@ -1,6 +1,9 @@
 /* pt_kernels_strict.cu -- the statically compiled STRICT instance of the megakernel (scenes without SDFs).
  * Compile flags (csrc/Makefile): -fmad=false -prec-div=true -prec-sqrt=true -ftz=false.  Bit-exact vs oracle/. */
 #define PT_KERNEL_NS ptk_strict
+#ifndef PT_SCHED
+#define PT_SCHED 0
+#endif
 #include "pt_kernel.cuh"
 
 PT_DEFINE_RENDER_KERNEL(pt_render_strict)

@@ -373,6 +373,30 @@ int pt_sdf_compile_check(const char* const* sdf_glsl, int n_sdf, const float* sd
     return PT_OK;
 }
 
+/* Compile (NVRTC, no GPU needed) exactly the kernel pt_set_scene would build for this scene, mode and jit policy.
+ * The ptxas report (registers, spills) is left in pt_last_error(NULL). */
+int pt_kernel_compile_check(const pt_ubo* ubo, const char* const* sdf_glsl, int n_sdf, int mode, int bake_counts) {
+    if (!ubo) return fail(nullptr, PT_ERR_ARG, "null ubo");
+    std::string unit, err, log;
+    PtDevScene sc;
+    int rc = pt_prepare_scene(ubo, &sc, &err);
+    if (rc != PT_OK) return fail(nullptr, rc, err);
+    if (n_sdf > 0) {
+        rc = pt_sdf_generate(sdf_glsl, n_sdf, ubo->sdfs, &unit, &err);
+        if (rc != PT_OK) return fail(nullptr, rc, err);
+    }
+    PtJitOptions opt;
+    opt.mode = mode;
+    opt.bake_counts = bake_counts != 0;
+    const int counts[6] = {sc.nSpheres, sc.nPlanes, sc.nBoxes, sc.nLenses, sc.nCyclides, sc.nSdfs};
+    memcpy(opt.counts, counts, sizeof counts);
+    std::vector<char> cubin;
+    rc = pt_jit_compile(unit, opt, &cubin, &log);
+    if (rc != PT_OK) return fail(nullptr, rc, log);
+    g_last_error = log;
+    return PT_OK;
+}
+
 int pt_sdf_eval(pt_ctx* ctx, const float* xyz, size_t n, unsigned set1, float* dist, float* material) {
     if (!ctx || !xyz || n == 0) return fail(ctx, PT_ERR_ARG, "pt_sdf_eval: bad argument");
     if (!ctx->scene_set || !ctx->active_jit || !ctx->active_jit->sdf_eval)
@@ -393,6 +417,20 @@ int pt_sdf_eval(pt_ctx* ctx, const float* xyz, size_t n, unsigned set1, float* d
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(dx); cudaFree(dd); cudaFree(dm);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "pt_sdf_eval");
+    return PT_OK;
+}
+
+/* debug: scheduling statistics of a kernel built with env PT_STATS=1 (16 counters; see pt_kernel.cuh) */
+int pt_debug_stats(pt_ctx* ctx, unsigned long long* out16, int reset) {
+    if (!ctx || !out16 || !ctx->active_jit) return fail(ctx, PT_ERR_ARG, "pt_debug_stats: needs a JIT kernel");
+    void* dptr = nullptr;
+    size_t bytes = 0;
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaError_t e = cudaLibraryGetGlobal(&dptr, &bytes, ctx->active_jit->lib, "pt_stats");
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "pt_stats symbol (build with PT_STATS=1)");
+    PT_CUDA(ctx, cudaMemcpy(out16, dptr, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (reset) PT_CUDA(ctx, cudaMemset(dptr, 0, 16 * sizeof(unsigned long long)));
     return PT_OK;
 }
 
