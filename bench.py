@@ -114,22 +114,25 @@ def oracle_for(scene_name, count=False, threads=0):
     return oracle.Oracle(pack.pack_ubo(scene), pack.sdf_sources(scene), count=count, threads=threads), scene
 
 
-def cpu_rate(scene_name, width, height, path_length, target_s, spf=1, first_dispatch=1):
-    """Times the CPU oracle (all host threads) on a strided-row sample of the full-resolution frame sized for about
-    target_s seconds.  Returns (samples/s, threads, description)."""
+def cpu_rate(scene_name, width, height, path_length, target_s, first_dispatch=1):
+    """Times the CPU oracle (all host threads) on a bounded sample of the workload sized for about target_s seconds:
+    a strided subset of the rows of the full-resolution frame (or, when one whole frame is too quick, several
+    samples per pixel of the whole frame).  Returns (samples/s, threads, description)."""
     from oracle import oracle, pack
     o, scene = oracle_for(scene_name)
-    p = pack.pack_params(scene, 1, width, height, spf, path_length, dispatch=first_dispatch)
-    img = np.zeros((height, width, 4), dtype=np.float32)
     threads = oracle.lib().oracle_max_threads()
+    img = np.zeros((height, width, 4), dtype=np.float32)
+    p = pack.pack_params(scene, 1, width, height, 1, path_length, dispatch=first_dispatch)
     step = max(height // max(2 * threads, 8), 1)      # probe: a few rows per thread
     t0 = time.perf_counter()
     o.dispatch(p, img, 0, step)
-    dt = time.perf_counter() - t0
-    rows = len(range(0, height, step))
-    rate = rows * width * spf / dt
-    want_rows = int(min(max(rate * target_s / (width * spf), rows), height))
-    step = max(height // want_rows, 1)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    rate = len(range(0, height, step)) * width / dt
+    want = rate * target_s                              # samples that fit the budget
+    spf = int(min(max(want // (width * height), 1), 64))
+    rows = int(min(max(want // (width * spf), 2 * threads), height))
+    step = max(height // rows, 1)
+    p = pack.pack_params(scene, 1, width, height, spf, path_length, dispatch=first_dispatch)
     img[:] = 0
     t0 = time.perf_counter()
     o.dispatch(p, img, 0, step)
@@ -163,7 +166,7 @@ def run_reference(args, wl):
     rates, desc, threads = [], '', 1
     t_all = time.perf_counter()
     for i in range(total):
-        rate, threads, desc = cpu_rate(scene_name, W, H, pl, per_step, spf=1, first_dispatch=1 + i)
+        rate, threads, desc = cpu_rate(scene_name, W, H, pl, per_step, first_dispatch=1 + i)
         if i >= args.warmup:
             rates.append(rate)
     wall = time.perf_counter() - t_all

@@ -159,6 +159,11 @@ const float* pt_cie1931_table(void); /* 1323 floats */
 long pt_sdf_translate(const char* const* sdf_glsl, int n_sdf, const float* sdfs_raw, char* out, size_t cap);
 /* Compile-only check of the NVRTC path (needs no GPU): 0 on success, log via pt_last_error(NULL) */
 int pt_sdf_compile_check(const char* const* sdf_glsl, int n_sdf, const float* sdfs_raw, int mode);
+/* Same for the whole kernel pt_set_scene would build for (ubo, snippets, mode); bake_counts as jit policy 2 */
+int pt_kernel_compile_check(const pt_ubo* ubo, const char* const* sdf_glsl, int n_sdf, int mode, int bake_counts);
+/* Scheduling statistics of a kernel built with env PT_STATS=1: per phase p of the v2 driver, out16[2p] = times the
+ * phase ran, out16[2p+1] = lanes it served (debug / profiles only) */
+int pt_debug_stats(pt_ctx* ctx, unsigned long long* out16, int reset);
 /* Evaluate a pt_math.h function on the device: fn 0 sin,1 cos,2 acos,3 exp2,4 log2,5 exp,6 log,7 pow(x,y),8 PCG32 */
 int pt_math_eval(pt_ctx* ctx, int fn, const float* x, const float* y, float* out, size_t n);
 /* Evaluate SDF()/SDFMATERIAL() of the current scene at n points (xyz triples); set1 mask as given */
