@@ -135,6 +135,10 @@ void pt_scene_free(pt_scene* scene);
 int pt_scene_num_shots(const pt_scene* scene);
 int pt_scene_num_sdf(const pt_scene* scene);
 const char* pt_scene_sdf_glsl(const pt_scene* scene, int i);
+/* UpdateToJSON + SaveScene (host:2724-2858, 3465-3472): the scene back as JSON text, reals rounded to 1e-5 like
+ * RoundDecimal (host:935-943).  pt_scene_to_json returns the size needed (incl. NUL) and writes at most cap bytes. */
+long pt_scene_to_json(const pt_scene* scene, char* out, size_t cap);
+int pt_scene_save_json(const pt_scene* scene, const char* path);
 /* UpdateUniformBuffer (host:3642-3811) incl. the CIE table copy of CreateUniformBuffer (host:2230-2248) */
 int pt_scene_pack_ubo(const pt_scene* scene, pt_ubo* ubo);
 /* UpdatePushConstant (host:3813-3834) for camera shot `shot` (1-based, host:1170); the per-dispatch fields are

@@ -95,6 +95,9 @@ def lib():
         L.pt_scene_sdf_glsl.argtypes = [vp, ci]
         L.pt_scene_sdf_glsl.restype = C.c_char_p
         L.pt_scene_pack_ubo.argtypes = [vp, vp]
+        L.pt_scene_to_json.argtypes = [vp, C.c_char_p, C.c_size_t]
+        L.pt_scene_to_json.restype = C.c_long
+        L.pt_scene_save_json.argtypes = [vp, C.c_char_p]
         L.pt_scene_pack_params.argtypes = [vp, ci, ci, ci, ci, ci, vp]
         L.pt_write_ppm.argtypes = [C.c_char_p, vp, ci, ci, ci]
         L.pt_write_pfm.argtypes = [C.c_char_p, vp, ci, ci, ci]
@@ -178,6 +181,18 @@ class Scene:
     def sdf_sources(self):
         L = lib()
         return [L.pt_scene_sdf_glsl(self._h, i) for i in range(L.pt_scene_num_sdf(self._h))]
+
+    def to_json(self):
+        """UpdateToJSON (host:2724-2858): the scene as JSON text, reals rounded to 1e-5."""
+        n = lib().pt_scene_to_json(self._h, None, 0)
+        if n < 0:
+            _check(int(n))
+        buf = C.create_string_buffer(int(n))
+        lib().pt_scene_to_json(self._h, buf, int(n))
+        return buf.value.decode()
+
+    def save(self, path):
+        _check(lib().pt_scene_save_json(self._h, os.fspath(path).encode()))
 
     def pack_ubo(self):
         ubo = np.zeros(UBO_FLOATS, dtype=np.float32)

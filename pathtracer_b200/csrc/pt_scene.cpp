@@ -187,6 +187,164 @@ const char* pt_scene_sdf_glsl(const pt_scene* scene, int i) {
     return scene->sdfs[(size_t)i].glsl.c_str();
 }
 
+/* UpdateToJSON + SaveScene (host:2724-2858, 3465-3472): same key order, reals rounded to 1e-5 by RoundDecimal
+ * (host:935-943: static_cast<int>(x * 1e5 +- 0.5) / 1e5), 4-space indentation.  Returns the size needed
+ * (including NUL); writes at most cap bytes. */
+long pt_scene_to_json(const pt_scene* s, char* out, size_t cap) {
+    if (!s) { g_error = "pt_scene_to_json: null scene"; return PT_ERR_ARG; }
+    auto num = [](double v) {
+        PtJson j;
+        j.type = PtJson::Number;
+        v = (v >= 0.0) ? (double)(int)(v * 1e5 + 0.5) : (double)(int)(v * 1e5 - 0.5);
+        j.num = v / 1e5;
+        return j;
+    };
+    auto integer = [](long long v) { PtJson j; j.type = PtJson::Number; j.num = (double)v; j.is_int = true; return j; };
+    auto boolean = [](bool v) { PtJson j; j.type = PtJson::Bool; j.b = v; return j; };
+    auto arr3 = [&](const float* v, int n) { PtJson j; j.type = PtJson::Array; for (int i = 0; i < n; i++) j.arr.push_back(num(v[i])); return j; };
+    auto object = []() { PtJson j; j.type = PtJson::Object; return j; };
+    auto array = []() { PtJson j; j.type = PtJson::Array; return j; };
+    PtJson root = object(), cam = object(), pos = array(), ang = array();
+    cam.obj.emplace_back("numShots", integer((long long)s->shots.size()));
+    for (const CameraShot& c : s->shots) { pos.arr.push_back(arr3(c.pos, 3)); ang.arr.push_back(arr3(c.angle, 2)); }
+    cam.obj.emplace_back("position", pos);
+    cam.obj.emplace_back("angle", ang);
+    cam.obj.emplace_back("ISO", integer(s->camera.ISO));
+    cam.obj.emplace_back("size", num(s->camera.size));
+    cam.obj.emplace_back("apertureSize", num(s->camera.apertureSize));
+    cam.obj.emplace_back("apertureDistance", num(s->camera.apertureDist));
+    cam.obj.emplace_back("lensRadius", num(s->camera.lensRadius));
+    cam.obj.emplace_back("lensFocalLength", num(s->camera.lensFocalLength));
+    cam.obj.emplace_back("lensThickness", num(s->camera.lensThickness));
+    cam.obj.emplace_back("lensDistance", num(s->camera.lensDistance));
+    root.obj.emplace_back("camera", cam);
+    auto ids = [&](PtJson& o, int materialID, int lightID) {
+        o.obj.emplace_back("materialID", integer(materialID));
+        o.obj.emplace_back("lightID", integer(lightID));
+    };
+    /* like nlohmann's operator[] on an index, an array key only exists when it has at least one element */
+    if (!s->spheres.empty()) {
+        PtJson a = array();
+        for (const Sphere& v : s->spheres) {
+            PtJson o = object();
+            o.obj.emplace_back("position", arr3(v.pos, 3));
+            o.obj.emplace_back("radius", num(v.radius));
+            ids(o, v.materialID, v.lightID);
+            a.arr.push_back(o);
+        }
+        root.obj.emplace_back("sphere", a);
+    }
+    if (!s->planes.empty()) {
+        PtJson a = array();
+        for (const Plane& v : s->planes) {
+            PtJson o = object();
+            o.obj.emplace_back("position", arr3(v.pos, 3));
+            ids(o, v.materialID, v.lightID);
+            a.arr.push_back(o);
+        }
+        root.obj.emplace_back("plane", a);
+    }
+    if (!s->boxes.empty()) {
+        PtJson a = array();
+        for (const Box& v : s->boxes) {
+            PtJson o = object();
+            o.obj.emplace_back("position", arr3(v.pos, 3));
+            o.obj.emplace_back("rotation", arr3(v.rotation, 3));
+            o.obj.emplace_back("size", arr3(v.size, 3));
+            ids(o, v.materialID, v.lightID);
+            a.arr.push_back(o);
+        }
+        root.obj.emplace_back("box", a);
+    }
+    if (!s->lenses.empty()) {
+        PtJson a = array();
+        for (const Lens& v : s->lenses) {
+            PtJson o = object();
+            o.obj.emplace_back("position", arr3(v.pos, 3));
+            o.obj.emplace_back("rotation", arr3(v.rotation, 3));
+            o.obj.emplace_back("radius", num(v.radius));
+            o.obj.emplace_back("focalLength", num(v.focalLength));
+            o.obj.emplace_back("thickness", num(v.thickness));
+            o.obj.emplace_back("isConverging", boolean(v.isConverging));
+            ids(o, v.materialID, v.lightID);
+            a.arr.push_back(o);
+        }
+        root.obj.emplace_back("lens", a);
+    }
+    if (!s->cyclides.empty()) {
+        PtJson a = array();
+        for (const Cyclide& v : s->cyclides) {
+            PtJson o = object();
+            o.obj.emplace_back("position", arr3(v.pos, 3));
+            o.obj.emplace_back("rotation", arr3(v.rotation, 3));
+            o.obj.emplace_back("scale", arr3(v.scale, 3));
+            o.obj.emplace_back("a", num(v.a));
+            o.obj.emplace_back("b", num(v.b));
+            o.obj.emplace_back("c", num(v.c));
+            o.obj.emplace_back("d", num(v.d));
+            o.obj.emplace_back("boundingRadius", num(v.brad));
+            ids(o, v.materialID, v.lightID);
+            a.arr.push_back(o);
+        }
+        root.obj.emplace_back("cyclide", a);
+    }
+    if (!s->sdfs.empty()) {
+        PtJson a = array();
+        for (const Sdf& v : s->sdfs) {
+            PtJson o = object(), g;
+            o.obj.emplace_back("position", arr3(v.pos, 3));
+            o.obj.emplace_back("boundingSize", arr3(v.size, 3));
+            g.type = PtJson::String;
+            g.str = v.glsl;
+            o.obj.emplace_back("glsl", g);
+            a.arr.push_back(o);
+        }
+        root.obj.emplace_back("sdf", a);
+    }
+    if (!s->materials.empty()) {
+        PtJson a = array();
+        for (const Material& v : s->materials) {
+            PtJson o = object(), r = object();
+            r.obj.emplace_back("peakWavelength", num(v.reflection[0]));
+            r.obj.emplace_back("sigma", num(v.reflection[1]));
+            r.obj.emplace_back("isInvert", boolean(v.reflection[2] != 0.0f));
+            o.obj.emplace_back("reflection", r);
+            a.arr.push_back(o);
+        }
+        root.obj.emplace_back("material", a);
+    }
+    if (!s->lights.empty()) {
+        PtJson a = array();
+        for (const Light& v : s->lights) {
+            PtJson o = object(), e = object();
+            e.obj.emplace_back("temperature", num(v.emission[0]));
+            e.obj.emplace_back("luminosity", num(v.emission[1]));
+            o.obj.emplace_back("emission", e);
+            a.arr.push_back(o);
+        }
+        root.obj.emplace_back("light", a);
+    }
+    const std::string text = pt_json_dump(root, 4);
+    if (out && cap > 0) {
+        const size_t n = text.size() < cap - 1 ? text.size() : cap - 1;
+        memcpy(out, text.data(), n);
+        out[n] = '\0';
+    }
+    return (long)text.size() + 1;
+}
+
+int pt_scene_save_json(const pt_scene* s, const char* path) {
+    if (!s || !path) { g_error = "pt_scene_save_json: null argument"; return PT_ERR_ARG; }
+    const long n = pt_scene_to_json(s, nullptr, 0);
+    if (n < 0) return (int)n;
+    std::string buf((size_t)n, '\0');
+    pt_scene_to_json(s, &buf[0], (size_t)n);
+    FILE* fp = fopen(path, "wb");
+    if (!fp) { g_error = std::string("cannot write ") + path; return PT_ERR_IO; }
+    const bool ok = fwrite(buf.data(), 1, (size_t)n - 1, fp) == (size_t)n - 1;
+    return (fclose(fp) == 0 && ok) ? PT_OK : PT_ERR_IO;
+}
+
 int pt_scene_pack_ubo(const pt_scene* s, pt_ubo* ubo) { /* host:3642-3811 */
     if (!s || !ubo) { g_error = "pt_scene_pack_ubo: null argument"; return PT_ERR_ARG; }
     std::vector<float> objects, sdfs, materials, lights, lightIDs;

@@ -65,3 +65,31 @@ def test_bad_scene_is_an_error(ptlib):
 def test_cie_table_exported(ptlib):
     from pathtracer_b200 import api
     assert np.array_equal(api.cie1931_table(), pack.cie_table())
+
+
+@pytest.mark.parametrize('name', SCENES)
+def test_scene_json_round_trip(ptlib, name, tmp_path):
+    """UpdateToJSON twin (host:2724-2858): load -> save -> load gives the same uniform block (the shipped files are
+    already rounded to 1e-5, the precision SaveScene writes) and the same key order as the shipped file."""
+    sc = ptlib.Scene.load(scene_path(name))
+    text = sc.to_json()
+    again = ptlib.Scene.parse(text)
+    assert np.array_equal(sc.pack_ubo().view(np.uint32), again.pack_ubo().view(np.uint32))
+    for shot in range(1, sc.num_shots + 1):
+        assert sc.pack_params(shot, 64, 64, 1, 5).tobytes() == again.pack_params(shot, 64, 64, 1, 5).tobytes()
+    assert [s for s in sc.sdf_sources] == [s for s in again.sdf_sources]
+    ours, ref = json.loads(text), json.load(open(scene_path(name)))
+    assert list(ours.keys()) == [k for k in ref.keys() if ref[k] != []]
+    assert list(ours['camera'].keys()) == list(ref['camera'].keys())
+    out = tmp_path / 'scene.json'
+    sc.save(out)
+    assert out.read_text() == text
+
+
+def test_round_decimal_semantics(ptlib):
+    s = pack.load_scene(scene_path('scene0'))
+    s['sphere'][0]['radius'] = 1.234567
+    s['sphere'][1]['position'] = [-0.000004, -1.999996, 2.5]
+    out = json.loads(ptlib.Scene.parse(json.dumps(s)).to_json())
+    assert out['sphere'][0]['radius'] == 1.23457
+    assert out['sphere'][1]['position'] == [0.0, -2.0, 2.5]
