@@ -195,6 +195,7 @@ def main():
     ap.add_argument('--spf', type=int, default=16, help='samples per pixel per step (one dispatch)')
     ap.add_argument('--mode', default='fast', choices=['fast', 'strict'])
     ap.add_argument('--jit', type=int, default=2, help='0 static kernels, 1 NVRTC for SDF scenes only, 2 NVRTC scene-specialised')
+    ap.add_argument('--pipeline', default='megakernel', choices=['megakernel', 'wavefront'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-flush', action='store_true')
     args = ap.parse_args()
@@ -219,7 +220,8 @@ def main():
     sc = pt.Scene.load(os.path.join(ROOT, 'scenes', scene_name + '.json'))
     ubo = sc.pack_ubo()
     params = sc.pack_params(1, W, H, args.spf, pl)
-    r = pt.Renderer(device=local_rank, mode=pt.MODE_FAST if args.mode == 'fast' else pt.MODE_STRICT, jit=args.jit)
+    r = pt.Renderer(device=local_rank, mode=pt.MODE_FAST if args.mode == 'fast' else pt.MODE_STRICT, jit=args.jit,
+                    pipeline=pt.PIPE_WAVEFRONT if args.pipeline == 'wavefront' else pt.PIPE_MEGAKERNEL)
     t0 = time.perf_counter()
     r.set_scene(ubo, sc.sdf_sources)
     compile_s = time.perf_counter() - t0
@@ -322,7 +324,7 @@ def main():
         'data': 'synthetic (reference scene files shipped in scenes/, no external assets)',
         'config': {'workload': wl, 'scene': 'scenes/%s.json' % scene_name, 'width': W, 'height': H, 'spf_per_step': spf,
                    'spp_timed': K * spf * world, 'spp_of_config': spp_cfg, 'path_length': pl, 'shot': 1, 'mode': args.mode,
-                   'jit': args.jit, 'l2': 'not flushed' if args.no_flush else 'flushed between steps (256 MiB fill)',
+                   'jit': args.jit, 'pipeline': args.pipeline, 'l2': 'not flushed' if args.no_flush else 'flushed between steps (256 MiB fill)',
                    'parallelism': 'sample-split x%d + 1 NCCL reduce' % world if world > 1 else 'single GPU',
                    'kernel_compile_s': round(compile_s, 3)},
         'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': 16388 + 88, 'd2h_bytes_per_step': W * H * 16,

@@ -82,6 +82,12 @@ typedef enum pt_mode {
     PT_MODE_FAST = 1    /* fma contraction, MUFU intrinsics, approximate division: the throughput build */
 } pt_mode;
 
+typedef enum pt_pipeline {
+    PT_PIPE_MEGAKERNEL = 0, /* one kernel per dispatch, path state in registers (pt_kernel.cuh) */
+    PT_PIPE_WAVEFRONT = 1   /* generate / intersect / march / shade / accumulate kernels over SoA path state in HBM,
+                               queues compacted by warp ballot (pt_wavefront.cuh); same results */
+} pt_pipeline;
+
 typedef struct pt_ctx pt_ctx;
 
 /* ---- device context (replaces InitVulkan + CreateComputePipeline, host:2424-2455, 2056-2092) ---------------- */
@@ -93,6 +99,9 @@ int pt_set_mode(pt_ctx* ctx, int mode);       /* default PT_MODE_STRICT; takes e
  * with SDF snippets are refused), 1 = NVRTC only for scenes with SDF snippets, 2 = always NVRTC, with the scene's
  * primitive counts baked in so the intersection loops unroll. Takes effect at the next pt_set_scene. */
 int pt_set_jit(pt_ctx* ctx, int policy);
+/* Megakernel (default) or wavefront pipeline; takes effect at the next pt_set_scene.  Both produce the same image
+ * (bit-identical in strict mode); profiles/ compares them per scene. */
+int pt_set_pipeline(pt_ctx* ctx, int pipeline);
 
 /* UpdateUniformBuffer + RecompileComputeShaders (host:3642-3811, 3836-3841, InsertSDF host:2004-2054).
  * sdf_glsl[i] is scene["sdf"][i]["glsl"] unchanged; n_sdf must equal ubo->numObjects[5].  With n_sdf > 0 the

@@ -18,6 +18,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 MODE_STRICT, MODE_FAST = 0, 1
+PIPE_MEGAKERNEL, PIPE_WAVEFRONT = 0, 1
 UBO_FLOATS = 4097
 
 PARAMS_DTYPE = np.dtype([
@@ -71,6 +72,7 @@ def lib():
         L.pt_destroy.restype = None
         L.pt_set_mode.argtypes = [vp, ci]
         L.pt_set_jit.argtypes = [vp, ci]
+        L.pt_set_pipeline.argtypes = [vp, ci]
         L.pt_set_scene.argtypes = [vp, vp, C.POINTER(C.c_char_p), ci]
         L.pt_resize.argtypes = [vp, ci, ci]
         L.pt_bind_image.argtypes = [vp, vp, ci, ci]
@@ -208,13 +210,15 @@ class Scene:
 class Renderer:
     """One device context (pt_ctx). Fails loudly without a GPU: there is no CPU fallback."""
 
-    def __init__(self, device=0, mode=MODE_STRICT, jit=None):
+    def __init__(self, device=0, mode=MODE_STRICT, jit=None, pipeline=PIPE_MEGAKERNEL):
         self._ctx = C.c_void_p()
         self.width = self.height = 0
         _check(lib().pt_create(device, C.byref(self._ctx)))
         _check(lib().pt_set_mode(self._ctx, mode), self._ctx)
         if jit is not None:
             _check(lib().pt_set_jit(self._ctx, jit), self._ctx)
+        if pipeline != PIPE_MEGAKERNEL:
+            _check(lib().pt_set_pipeline(self._ctx, pipeline), self._ctx)
         self._keep = None
 
     def close(self):
@@ -229,6 +233,10 @@ class Renderer:
 
     def set_jit(self, policy):
         _check(lib().pt_set_jit(self._ctx, policy), self._ctx)
+
+    def set_pipeline(self, pipeline):
+        """PIPE_MEGAKERNEL (default) or PIPE_WAVEFRONT; takes effect at the next set_scene."""
+        _check(lib().pt_set_pipeline(self._ctx, pipeline), self._ctx)
 
     def set_scene(self, ubo, sdf_sources=()):
         ubo = np.ascontiguousarray(ubo, dtype=np.float32)

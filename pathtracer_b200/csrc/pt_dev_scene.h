@@ -114,6 +114,27 @@ typedef struct PtDevParams {
     PtDevLens camLens;     /* TracePathLens' lens object (shader.comp:1411-1418) */
 } PtDevParams;
 
+/* Wavefront pipeline (pt_wavefront.cuh): device buffers of the path state, SoA.  Pointer types are spelled out on the
+ * device and opaque on the host (same layout). */
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+#define PT_WF_PTR(T) T*
+#else
+#define PT_WF_PTR(T) void*
+#endif
+typedef struct PtWf {
+    PT_WF_PTR(float4) rayO; PT_WF_PTR(float4) rayD; PT_WF_PTR(float4) wl; PT_WF_PTR(float4) rad; PT_WF_PTR(float4) thr;
+    PT_WF_PTR(float4) shD; PT_WF_PTR(float4) shC; PT_WF_PTR(float4) hit0; PT_WF_PTR(float4) hit1; PT_WF_PTR(float4) col;
+    PT_WF_PTR(float4) acc;
+    PT_WF_PTR(uint2) misc;
+    PT_WF_PTR(unsigned) qA; PT_WF_PTR(unsigned) qB; PT_WF_PTR(unsigned) qS; PT_WF_PTR(unsigned) qM;
+    PT_WF_PTR(unsigned) cnt;  /* [0] nA  [1] nB  [2] nS  [3] nM  [4] march head */
+    unsigned P, nPix;        /* paths in flight (pixels x samples of the chunk), pixels */
+    int chunkBase;           /* k of the chunk's first sample (sample index = firstSample + k) */
+    int chunkSamples;
+    int lastChunk;
+    int pad;
+} PtWf;
+
 /* raw tables the kernel indexes with computed ids; a copy of the tail of the uniform block in global memory:
  * flat float[4097] exactly like pt_ubo, so clamped flat indexing matches the oracle's Shader::at() */
 #define PT_UBO_FLOATS 4097

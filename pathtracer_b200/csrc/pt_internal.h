@@ -21,6 +21,7 @@ int pt_sdf_generate(const char* const* sdf_glsl, int n_sdf, const float* sdfs_ra
 struct PtJitOptions {
     int mode;            /* pt_mode */
     bool bake_counts;    /* compile primitive counts in as constants */
+    bool wavefront;      /* also build the wavefront pipeline's kernels (pt_wavefront.cuh) */
     int counts[6];       /* spheres, planes, boxes, lenses, cyclides, sdfs */
 };
 int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::vector<char>* cubin, std::string* log);

@@ -87,17 +87,19 @@ int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::ve
      * loops), scenes with SDFs with the v2 in-warp scheduler; the fast build wants 6 CTAs/SM, the strict one 4. */
     struct Knob { const char* name; int dflt; };
     const Knob knobs[] = {{"PT_SCHED", sdf_unit.empty() ? 0 : 1}, {"PT_SDF_REPS", 8}, {"PT_FEED_T", 12},
-                          {"PT_MIN_BLOCKS", opt.mode == PT_MODE_FAST ? 6 : 4}, {"PT_NO_UNROLL", 0}, {"PT_STATS", 0}};
+                          {"PT_MIN_BLOCKS", opt.mode == PT_MODE_FAST ? 6 : 4}, {"PT_NO_UNROLL", 0}, {"PT_STATS", 0},
+                          {"PT_WF_REFILL", 8}};
     for (const Knob& k : knobs) {
         const char* v = getenv(k.name);
         const int val = (v && v[0]) ? atoi(v) : k.dflt;
         if (std::string(k.name) == "PT_STATS" && val == 0) continue;
         src += std::string("#define ") + k.name + " " + std::to_string(val) + "\n";
     }
-    src += "#include \"pt_kernel.cuh\"\n";
+    src += opt.wavefront ? "#include \"pt_wavefront.cuh\"\n" : "#include \"pt_kernel.cuh\"\n";
     src += sdf_unit;
     src += "\nPT_DEFINE_RENDER_KERNEL(pt_render_jit)\n";
     if (!sdf_unit.empty()) src += "PT_DEFINE_SDF_EVAL_KERNEL(pt_sdf_eval_jit)\n";
+    if (opt.wavefront) src += "PT_DEFINE_WAVEFRONT_KERNELS\n";
 
     std::vector<const char*> hdr_names, hdr_texts;
     for (int i = 0; i < pt_embedded_header_count; i++) {

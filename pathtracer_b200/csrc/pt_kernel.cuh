@@ -939,22 +939,319 @@ __device__ __forceinline__ void pt_render_body_v1(const PtDevScene& sc, const Pt
     StoreTexel(pr, image, gx, gy, outColor);
 }
 
-/* ---- driver v2: in-warp scheduled state machine (default) ---------------------------------------------------------
+/* ---- the path as four phases over explicit per-path state --------------------------------------------------------
  * v1 leaves most lanes idle: a warp waits for its longest path at every sample, the shadow ray runs under a
  * divergent branch, and with SDFs only the lanes whose ray entered a bounding box march, for 1..512 steps each
  * (ncu on v1: 17.3 of 32 lanes active on scene1, 7.5 of 32 on the mandelbulb scene).
- * Here every lane is a small state machine over the SAME per-lane arithmetic, in the same order (so strict mode
- * stays bit-exact), and the warp executes one phase per iteration, chosen by ballot as the phase most lanes wait for:
- *   NEW    camera ray + lens + wavelengths for the lane's next sample index        (Scene(), shader.comp:1446-1472)
- *   ISECT  brute-force primitives for the lane's current ray, path OR shadow ray alike (one copy of the
- *          intersection code runs at full width), then SearchSDF                   (shader.comp:862-924, 1121-1205)
+ * Below, the SAME per-path arithmetic in the same order (so strict mode stays bit-exact) is cut into four phases
+ * that read and write an explicit PathState:
+ *   NEW    project the finished path to XYZ (Scene()'s tail, shader.comp:1477-1489), then camera ray + lens +
+ *          wavelengths for the next sample index                                    (shader.comp:1446-1472)
+ *   ISECT  brute-force primitives for the current ray, path OR shadow ray alike, then SearchSDF
+ *                                                                                  (shader.comp:862-924, 1121-1205)
  *   SDF    ONE evaluation of the injected SDF(): sign probe, march step or one of the six normal probes -- every
  *          consumer of the distance function funnels through this single site       (shader.comp:779-860, 721-730)
- *   SHADE  emitter / BSDF sample / light sample with MIS / Russian roulette, or resolution of a pending shadow
- *          ray; a finished path is projected to XYZ and the lane goes back to NEW  (shader.comp:1298-1407, 1477-1489)
- * A lane that finishes early refills itself with its pixel's next sample instead of idling, so the expensive
- * phases run with most lanes populated.  All state stays in registers: no queues, no HBM traffic. */
+ *   SHADE  emitter / BSDF sample / light sample with MIS / Russian roulette, or the verdict of a pending shadow
+ *          ray (traced before the next path ray; LightSourceVisibilityCheck draws no random numbers)
+ *                                                                                  (shader.comp:1298-1407)
+ * Two drivers run these phases: v2 keeps the state in registers and lets each warp execute, per iteration, the
+ * phase its lanes vote for; the wavefront pipeline keeps it in HBM (SoA) and runs one kernel per phase. */
 enum { PT_ST_NEW = 0, PT_ST_ISECT = 1, PT_ST_SDF = 2, PT_ST_SHADE = 3, PT_ST_DONE = 4 };
+enum { PT_SUB_SIGN = 0, PT_SUB_STEP = 1, PT_SUB_N0 = 2 }; /* N0..N5 = 2..7: +x -x +y -y +z -z */
+
+struct PathState {
+    Ray ray;            /* current path ray; while a shadow ray is pending ray.dir already holds the NEXT path direction */
+    V4 l;               /* the wavelength bundle */
+    V4 radiance, rayradiance;
+    float MISBRDFWeight;
+    unsigned seed;
+    int bounce;
+    bool isShadow;      /* the ray being traced is the shadow ray (origin = ray.origin, direction = shDir) */
+    bool pathAlive;     /* whether the path continues after the pending shadow ray */
+    bool pendingFinish; /* a finished path whose radiance is still to be projected to XYZ */
+    V3 shDir;
+    V4 shContrib;       /* added to radiance iff the shadow ray sees object shObj */
+    int shObj;
+    Hit h;
+};
+
+struct MarchState {     /* SphereTracing's locals, shader.comp:780-794 */
+    float mt, insT, omega, previousRadius, tMax, ksign;
+    float probe, nrm0, nrm1, nrm2;
+    int points, iter, sub;
+    unsigned set1;
+};
+
+PT_DEV void PathStateInit(PathState& ps) {
+    const V3 z3 = mk3(0.0f, 0.0f, 0.0f);
+    const V4 z4 = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    ps.ray.origin = z3; ps.ray.dir = z3; ps.l = z4; ps.radiance = z4; ps.rayradiance = z4;
+    ps.MISBRDFWeight = 1.0f; ps.seed = 0u; ps.bounce = 0;
+    ps.isShadow = false; ps.pathAlive = false; ps.pendingFinish = false;
+    ps.shDir = z3; ps.shContrib = z4; ps.shObj = 0;
+    ps.h.t = 1e5f; ps.h.normal = z3; ps.h.materialID = 0.0f; ps.h.lightID = -1.0f; ps.h.objectID = -1;
+}
+PT_DEV void MarchStateInit(MarchState& ms) {
+    ms.mt = 0.0f; ms.insT = 0.0f; ms.omega = 1.7f; ms.previousRadius = 0.0f; ms.tMax = 1e5f; ms.ksign = 0.0f;
+    ms.probe = 0.0f; ms.nrm0 = 0.0f; ms.nrm1 = 0.0f; ms.nrm2 = 0.0f;
+    ms.points = 0; ms.iter = 0; ms.sub = PT_SUB_SIGN; ms.set1 = 0u;
+}
+
+/* Scene()'s tail, shader.comp:1477-1489: radiance -> XYZ, NaNs dropped */
+PT_DEV V3 PathColor(const Ctx& c, const PathState& ps) {
+    const V3 w0 = WaveToXYZ(c, ps.l.x), w1 = WaveToXYZ(c, ps.l.y), w2 = WaveToXYZ(c, ps.l.z), w3 = WaveToXYZ(c, ps.l.w);
+    const V4 r = ps.radiance;
+    V3 color;
+    color.x = 0.0f + (r.x * w0.x + r.y * w1.x + r.z * w2.x + r.w * w3.x) * 330.0f * 0.25f;
+    color.y = 0.0f + (r.x * w0.y + r.y * w1.y + r.z * w2.y + r.w * w3.y) * 330.0f * 0.25f;
+    color.z = 0.0f + (r.x * w0.z + r.y * w1.z + r.z * w2.z + r.w * w3.z) * 330.0f * 0.25f;
+    if ((color.x != color.x) || (color.y != color.y) || (color.z != color.z)) color = mk3(0.0f, 0.0f, 0.0f);
+    return color;
+}
+
+/* NEW: Scene() up to TracePath, shader.comp:1446-1472, for sample index pr.firstSample + k of pixel (xyx, xyy).
+ * Returns the next phase (ISECT, or NEW again with pendingFinish when pathLength <= 0). */
+PT_DEV int PhaseNew(const Ctx& c, PathState& ps, unsigned xyx, unsigned xyy, int k) {
+    const PtDevParams& pr = *c.pr;
+    const V3 camPos = mk3(pr.camPosX, pr.camPosY, pr.camPosZ);
+    const float uvx0 = PTK_DIV(2.0f * __uint2float_rn(xyx) - pr.resX, pr.resY); /* shader.comp:1511 */
+    const float uvy0 = PTK_DIV(2.0f * __uint2float_rn(xyy) - pr.resY, pr.resY);
+    unsigned seed = (unsigned)(pr.firstSample + k); /* GenerateSeed, shader.comp:948-958 */
+    PCG32(seed);
+    seed += xyx + (unsigned)pr.width * xyy;
+    const float j1 = RandomFloatPCG32(seed);
+    const float j2 = RandomFloatPCG32(seed);
+    float uvx = uvx0 + PTK_DIV(2.0f * j1 - 0.5f, pr.resX);
+    float uvy = uvy0 + PTK_DIV(2.0f * j2 - 0.5f, pr.resY);
+    uvx *= pr.sensorScale;
+    uvy *= pr.sensorScale;
+    Ray ray;
+    ray.origin = camPos + mulVM(mk3(uvx, uvy, 0.0f), pr.camM);
+    const float rx = RandomFloatPCG32(seed); /* SampleUniformUnitDisk, shader.comp:976-982 */
+    const float ry = RandomFloatPCG32(seed);
+    const float phi = 2.0f * PT_PI_F * ry;
+    const float dd = PTK_SQRT(rx);
+    const float diskx = pr.halfAperture * (dd * PTK_COS(phi));
+    const float disky = pr.halfAperture * (dd * PTK_SIN(phi));
+    const V3 pointOnAperture = camPos + mulVM(mk3(diskx, disky, pr.apertureDist), pr.camM);
+    ray.dir = normalize(pointOnAperture - ray.origin);
+    const float r5 = RandomFloatPCG32(seed);
+    const float l_h = 360.0f * (1.0f - r5) + 800.0f * r5; /* mix(360, 800, r) */
+    TracePathLens(c, l_h, ray);
+    ps.ray = ray;
+    ps.l = SampleWavelengths(l_h);
+    ps.seed = seed;
+    ps.radiance = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    ps.rayradiance = mk4(1.0f, 1.0f, 1.0f, 1.0f);
+    ps.MISBRDFWeight = 1.0f;
+    ps.bounce = 0;
+    ps.isShadow = false;
+    if (pr.pathLength > 0) return PT_ST_ISECT;
+    ps.pendingFinish = true;
+    return PT_ST_NEW;
+}
+
+/* ISECT: Intersection / LightSourceVisibilityCheck up to (and with) SphereTracing's prologue */
+PT_DEV int PhaseIsect(const Ctx& c, PathState& ps, MarchState& ms) {
+    Ray r;
+    r.origin = ps.ray.origin;
+    r.dir = ps.isShadow ? ps.shDir : ps.ray.dir;
+    IntersectionAnalytic(c, r, ps.h, ps.isShadow);
+#if PT_HAS_SDF
+    const V3 invdir = mk3(PTK_DIV(1.0f, r.dir.x), PTK_DIV(1.0f, r.dir.y), PTK_DIV(1.0f, r.dir.z)); /* shader.comp:780-801 */
+    float tMin = 1e5f;
+    ms.tMax = 1e5f;
+    if (SearchSDF(c, r.origin, invdir, tMin, ms.tMax, ms.set1)) {
+        ms.mt = PTK_MAX(tMin, 1e-3f);
+        ms.insT = 0.0f; ms.omega = 1.70f; ms.previousRadius = 0.0f; ms.points = 0; ms.iter = 0;
+        ms.sub = PT_SUB_SIGN;
+        return PT_ST_SDF;
+    }
+#endif
+    return PT_ST_SHADE;
+}
+
+#if PT_HAS_SDF
+/* SDF: one SDF() evaluation and the bookkeeping around it.  Returns SDF (more to do) or SHADE. */
+PT_DEV int PhaseSdfEval(const Ctx& c, PathState& ps, MarchState& ms) {
+    const V3 dir = ps.isShadow ? ps.shDir : ps.ray.dir;
+    const V3 origin = ps.ray.origin;
+    V3 pe = origin;
+    if (ms.sub != PT_SUB_SIGN) {
+        pe = fma3(dir, ms.mt, origin);
+        if (ms.sub >= PT_SUB_N0) { /* CalculateNumericalSDFNormals, shader.comp:721-730: p +- h.xyy etc. */
+            const int j = ms.sub - PT_SUB_N0, axis = j >> 1;
+            const float ex = (axis == 0) ? 1e-4f : 0.0f, ey = (axis == 1) ? 1e-4f : 0.0f, ez = (axis == 2) ? 1e-4f : 0.0f;
+            pe = (j & 1) ? mk3(pe.x - ex, pe.y - ey, pe.z - ez) : mk3(pe.x + ex, pe.y + ey, pe.z + ez);
+        }
+    }
+    const float d = SDF(pe, ms.set1); /* the one SDF() site of the kernel */
+    if (ms.sub == PT_SUB_SIGN) { /* shader.comp:801 */
+        ms.ksign = gsign(d);
+        ms.sub = PT_SUB_STEP;
+        return PT_ST_SDF;
+    }
+    if (ms.sub == PT_SUB_STEP) { /* one iteration of the loop at shader.comp:803-849 */
+        const float radius = d;
+        bool finished = false, nohit = false;
+        if (ms.insT > (fabsf(ms.previousRadius) + fabsf(radius))) {
+            ms.mt -= ms.insT;
+            ms.omega = 1.0f;
+            ms.insT = ms.previousRadius * ms.omega * ms.ksign;
+            ms.mt += ms.insT;
+        } else if (fabsf(radius) < 1e-4f) {
+            finished = true;
+        } else {
+            if (ms.mt > ms.tMax) ms.points += 1; else ms.points = 0;
+            if (ms.points >= 2) {
+                ms.mt = ms.tMax + 1e-3f;
+                float tMin = 1e5f;
+                ms.tMax = 1e5f;
+                const V3 invdir = mk3(PTK_DIV(1.0f, dir.x), PTK_DIV(1.0f, dir.y), PTK_DIV(1.0f, dir.z));
+                if (SearchSDF(c, fma3(dir, ms.mt, origin), invdir, tMin, ms.tMax, ms.set1)) {
+                    tMin += ms.mt; ms.tMax += ms.mt;
+                    ms.mt = PTK_MAX(tMin, ms.mt);
+                } else {
+                    nohit = true;
+                }
+            } else {
+                ms.insT = radius * ms.omega * ms.ksign;
+                ms.mt += ms.insT;
+                const float omegaSpeedFactor = PTK_MIN(PTK_DIV(radius, ms.previousRadius), 0.99f);
+                ms.omega += 0.20f * (PTK_MIN(PTK_DIV(1.0f, 1.0f - omegaSpeedFactor), 1.70f) - ms.omega);
+                ms.previousRadius = radius;
+            }
+        }
+        if (!finished && !nohit) {
+            ms.iter++;
+            if (ms.iter >= 512) finished = true; /* falls through to "hit" unconverged: SURVEY App. C-9 */
+        }
+        if (nohit) return PT_ST_SHADE;
+        if (finished) { /* shader.comp:851-858 */
+            if (ms.mt < ps.h.t) {
+                ps.h.t = ms.mt - 1e-3f;
+                ps.h.objectID = -1;
+                if (ps.isShadow) return PT_ST_SHADE;
+                ms.sub = PT_SUB_N0;
+                return PT_ST_SDF;
+            }
+            return PT_ST_SHADE;
+        }
+        return PT_ST_SDF;
+    }
+    const int j = ms.sub - PT_SUB_N0;
+    if ((j & 1) == 0) {
+        ms.probe = d;
+    } else {
+        const float g = ms.probe - d;
+        if (j == 1) ms.nrm0 = g; else if (j == 3) ms.nrm1 = g; else ms.nrm2 = g;
+    }
+    ms.sub++;
+    if (j == 5) {
+        const V3 p = fma3(dir, ms.mt, origin);
+        ps.h.normal = normalize(mk3(ms.nrm0, ms.nrm1, ms.nrm2));
+        ps.h.materialID = ::pt_sdfmaterial_dispatch(p.x, p.y, p.z, ms.set1);
+        ps.h.lightID = -1.0f;
+        return PT_ST_SHADE;
+    }
+    return PT_ST_SDF;
+}
+#endif
+
+/* SHADE: TraceRay after Intersection (shader.comp:1352-1390) with SampleLightSource (1298-1343), or the verdict of
+ * the pending shadow ray (1218-1222, 1328-1334).  Returns ISECT (another ray to trace) or NEW (path finished). */
+PT_DEV int PhaseShade(const Ctx& c, PathState& ps) {
+    const PtDevScene& sc = *c.sc;
+    bool done = false;
+    int next = PT_ST_ISECT;
+    if (ps.isShadow) {
+        if (ps.h.objectID == ps.shObj) ps.radiance = ps.radiance + ps.shContrib;
+        ps.isShadow = false;
+        if (!ps.pathAlive) done = true;
+    } else if (!(ps.h.t < 1e5f)) { /* miss: black environment */
+        done = true;
+    } else {
+        float emitT, emitL; /* the light Emit() is evaluated for: the one hit, or the one sampled */
+        GetLightMix(c, ps.h.lightID, emitT, emitL);
+        const bool emitterHit = emitL > 0.0f; /* terminates the path, shader.comp:1359-1364 */
+        bool needShadow = false, alive = false;
+        V4 rr = ps.rayradiance;
+        float emitScale = ps.MISBRDFWeight;
+        V3 outOrigin = ps.ray.origin, outDir = ps.ray.dir;
+        if (!emitterHit) {
+            float peak, sigma, invertf;
+            GetMaterialMix(c, ps.h.materialID, peak, sigma, invertf);
+            const V4 brdf = EvaluateBRDF(ps.l, peak, sigma, invertf);
+            const V3 n = ps.h.normal;
+            outOrigin = fma3(ps.ray.dir, ps.h.t, ps.ray.origin);
+            outDir = SampleCosineDirectionHemisphere(n, ps.seed);
+            const float BRDFpdf = PTK_DIV(dot(outDir, n), PT_PI_F);
+            if (sc.numLights > 0.0f) { /* SampleLightSource, shader.comp:1298-1343 */
+                const int randomLight = __float2int_rz(floorf(RandomFloatPCG32(ps.seed) * sc.numLights));
+                const PtDevLightSlot& ls = sc.lightSlots[randomLight < sc.nLightSlots ? randomLight : sc.nLightSlots - 1];
+                const V3 toLight = mk3(ls.px - outOrigin.x, ls.py - outOrigin.y, ls.pz - outOrigin.z);
+                const float invLightDistance = PTK_DIV(1.0f, length(toLight));
+                const V3 lightDir = toLight * invLightDistance;
+                const float sinthetaMax = PTK_MIN(ls.boundingRadius * invLightDistance, 1.0f);
+                const float costhetaMax = PTK_SQRT(1.0f - sinthetaMax * sinthetaMax);
+                const V3 sdir = ToWorld(SampleCosineUnitCone(ps.seed, costhetaMax), lightDir);
+                float lightpdf = sc.invNumLights;
+                lightpdf *= PTK_DIV(dot(sdir, lightDir), PT_PI_F * (1.0f - costhetaMax * costhetaMax));
+                ps.MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + lightpdf * lightpdf);
+                const float costheta = dot(sdir, n);
+                const float deathProbability = 1.25f * PTK_MAX(ps.MISBRDFWeight - 0.2f, 0.0f);
+                if (costheta >= 0.0f) {
+                    if (RandomFloatPCG32(ps.seed) > deathProbability) {
+                        GetLightMix(c, ls.lightID, emitT, emitL);
+                        rr = ps.rayradiance * mulDiv4(brdf, costheta, lightpdf);
+                        emitScale = 1.0f - ps.MISBRDFWeight;
+                        ps.shDir = sdir;
+                        ps.shObj = ls.objectID;
+                        needShadow = true;
+                    } else {
+                        ps.MISBRDFWeight = 1.0f;
+                    }
+                }
+            } else {
+                ps.MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + 0.0f * 0.0f);
+            }
+            const float costheta = dot(outDir, n);
+            ps.rayradiance = ps.rayradiance * mulDiv4(brdf, costheta, BRDFpdf);
+            const V4 t4 = ps.rayradiance;
+            const float mx = PTK_MAX(t4.x, PTK_MAX(t4.y, PTK_MAX(t4.z, t4.w)));
+            const float rayProbability = PTK_MIN(PTK_MAX(mx, 0.0f), 0.99f);
+            alive = !(RandomFloatPCG32(ps.seed) > rayProbability);
+            if (alive) ps.rayradiance = ps.rayradiance * PTK_DIV(1.0f, rayProbability);
+            ps.bounce++;
+            if (ps.bounce >= c.pr->pathLength) alive = false; /* TracePath's loop bound, shader.comp:1400 */
+        }
+        if (emitterHit || needShadow) { /* the one Emit() site: (Emit * rr) * scale in both uses */
+            const V4 e = Emit(ps.l, PTK_MAX(emitT, 0.0f), PTK_MAX(emitL, 0.0f));
+            const V4 contrib = (e * rr) * emitScale;
+            if (emitterHit) ps.radiance = ps.radiance + contrib; else ps.shContrib = contrib;
+        }
+        ps.ray.origin = outOrigin;
+        ps.ray.dir = outDir; /* next path direction; a pending shadow ray travels along shDir */
+        if (emitterHit) {
+            done = true;
+        } else if (needShadow) {
+            ps.isShadow = true;
+            ps.pathAlive = alive;
+        } else if (!alive) {
+            done = true;
+        }
+    }
+    if (done) {
+        ps.pendingFinish = true;
+        next = PT_ST_NEW;
+    }
+    return next;
+}
+
+/* ---- driver v2: in-warp scheduled state machine, all state in registers ------------------------------------------
+ * Every lane runs the phases above for its own pixel; per iteration the warp executes ONE phase, chosen by ballot.
+ * A lane that finishes a path refills itself with its pixel's next sample index instead of idling, so the
+ * expensive phases run with more lanes populated than in v1.  No queues, no HBM traffic. */
 #ifdef PT_STATS
 /* scheduling statistics (debug builds only, env PT_STATS=1): per phase, [2p] = executions, [2p+1] = lanes served */
 } /* namespace */
@@ -964,12 +1261,11 @@ namespace PT_KERNEL_NS {
 #else
 #define PT_STAT(p, mask) do { } while (0)
 #endif
-enum { PT_SUB_SIGN = 0, PT_SUB_STEP = 1, PT_SUB_N0 = 2 }; /* N0..N5 = 2..7: +x -x +y -y +z -z */
 #ifndef PT_SDF_REPS
-#define PT_SDF_REPS 4
+#define PT_SDF_REPS 8
 #endif
 #ifndef PT_FEED_T
-#define PT_FEED_T 8
+#define PT_FEED_T 12
 #endif
 
 __device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
@@ -987,39 +1283,15 @@ __device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const Pt
 
     const unsigned xyx = (unsigned)gx;
     const unsigned xyy = (unsigned)pr.height - (unsigned)gy; /* shader.comp:1510 */
-    const float uvx0 = PTK_DIV(2.0f * __uint2float_rn(xyx) - pr.resX, pr.resY);
-    const float uvy0 = PTK_DIV(2.0f * __uint2float_rn(xyy) - pr.resY, pr.resY);
     const int spf = pr.samplesPerFrame;
-    const int pathLength = pr.pathLength;
-    const V3 camPos = mk3(pr.camPosX, pr.camPosY, pr.camPosZ);
 
     int st = (inRange && spf > 0) ? PT_ST_NEW : PT_ST_DONE;
     int k = 0;
     V3 outColor = mk3(0.0f, 0.0f, 0.0f);
-    /* per-sample state */
-    unsigned seed = 0u;
-    V4 l = mk4(0.0f, 0.0f, 0.0f, 0.0f);
-    V4 radiance = l, rayradiance = l;
-    float MISBRDFWeight = 1.0f;
-    int bounce = 0;
-    Ray ray;
-    ray.origin = mk3(0.0f, 0.0f, 0.0f);
-    ray.dir = ray.origin;
-    /* pending shadow ray (traced before the next path ray; LightSourceVisibilityCheck draws no random numbers) */
-    bool isShadow = false, pathAlive = false;
-    V3 shDir = ray.origin, nextDir = ray.origin;
-    V4 shContrib = l;
-    int shObj = 0;
-    Hit h;
-    h.t = 1e5f; h.normal = ray.origin; h.materialID = 0.0f; h.lightID = -1.0f; h.objectID = -1;
-#if PT_HAS_SDF
-    float mt = 0.0f, insT = 0.0f, omega = 1.7f, previousRadius = 0.0f, tMin = 1e5f, tMax = 1e5f, ksign = 0.0f;
-    float probe = 0.0f, nrm0 = 0.0f, nrm1 = 0.0f, nrm2 = 0.0f;
-    int points = 0, iter = 0, sub = PT_SUB_SIGN;
-    unsigned set1 = 0u;
-#endif
-
-    bool pendingFinish = false; /* a finished path whose radiance is still to be projected to XYZ (done in NEW) */
+    PathState ps;
+    PathStateInit(ps);
+    MarchState ms;
+    MarchStateInit(ms);
 
     for (;;) {
         const unsigned bNew = __ballot_sync(0xffffffffu, st == PT_ST_NEW);
@@ -1031,255 +1303,43 @@ __device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const Pt
         const unsigned bSdf = 0u;
 #endif
         if ((bNew | bIs | bSdf | bSh) == 0u) break;
-        /* Phase selection.  Executing a phase costs the same whatever its population, so the expensive phase
-         * should run as full as possible.  With SDFs that is the SDF phase (tens of evaluations per ray against
-         * one intersect/shade per ray): the other three phases are "feeders" and run first whenever PT_FEED_T or
-         * more lanes wait in one of them (the fullest feeder wins; ties go to the later pipeline stage); only
-         * when every feeder is below the threshold do the marching lanes take their PT_SDF_REPS steps.  Without
-         * SDFs this degenerates to "the phase most lanes are waiting for". */
+        /* Phase selection.  Executing a phase costs the same whatever its population.  The fullest of the three
+         * "feeder" phases wins (ties go to the later pipeline stage); lanes waiting in the SDF phase take their
+         * PT_SDF_REPS evaluations when every feeder has fewer than PT_FEED_T lanes waiting.  Without SDFs this
+         * is "the phase most lanes are waiting for". */
         int phase = PT_ST_NEW, best = __popc(bNew);
         if (__popc(bIs) >= best) { best = __popc(bIs); phase = PT_ST_ISECT; }
         if (__popc(bSh) >= best) { best = __popc(bSh); phase = PT_ST_SHADE; }
 #if PT_HAS_SDF
         if (bSdf != 0u && (best < PT_FEED_T || best == 0)) phase = PT_ST_SDF;
 #endif
-
         PT_STAT(phase, phase == PT_ST_NEW ? bNew : (phase == PT_ST_ISECT ? bIs : (phase == PT_ST_SDF ? bSdf : bSh)));
         if (phase == PT_ST_NEW) {
             if (st == PT_ST_NEW) {
-                if (pendingFinish) { /* Scene()'s tail, shader.comp:1477-1489: radiance -> XYZ, drop NaNs */
-                    const V3 w0 = WaveToXYZ(c, l.x), w1 = WaveToXYZ(c, l.y), w2 = WaveToXYZ(c, l.z), w3 = WaveToXYZ(c, l.w);
-                    V3 color;
-                    color.x = 0.0f + (radiance.x * w0.x + radiance.y * w1.x + radiance.z * w2.x + radiance.w * w3.x) * 330.0f * 0.25f;
-                    color.y = 0.0f + (radiance.x * w0.y + radiance.y * w1.y + radiance.z * w2.y + radiance.w * w3.y) * 330.0f * 0.25f;
-                    color.z = 0.0f + (radiance.x * w0.z + radiance.y * w1.z + radiance.z * w2.z + radiance.w * w3.z) * 330.0f * 0.25f;
-                    if ((color.x != color.x) || (color.y != color.y) || (color.z != color.z)) color = mk3(0.0f, 0.0f, 0.0f);
-                    outColor = outColor + color;
-                    pendingFinish = false;
+                if (ps.pendingFinish) {
+                    outColor = outColor + PathColor(c, ps);
+                    ps.pendingFinish = false;
                 }
-                if (k < spf) { /* Scene(), shader.comp:1446-1472 */
-                    seed = (unsigned)(pr.firstSample + k); /* GenerateSeed, shader.comp:948-958 */
-                    PCG32(seed);
-                    seed += xyx + (unsigned)pr.width * xyy;
+                if (k < spf) {
+                    st = PhaseNew(c, ps, xyx, xyy, k);
                     k++;
-                    const float j1 = RandomFloatPCG32(seed);
-                    const float j2 = RandomFloatPCG32(seed);
-                    float uvx = uvx0 + PTK_DIV(2.0f * j1 - 0.5f, pr.resX);
-                    float uvy = uvy0 + PTK_DIV(2.0f * j2 - 0.5f, pr.resY);
-                    uvx *= pr.sensorScale;
-                    uvy *= pr.sensorScale;
-                    ray.origin = camPos + mulVM(mk3(uvx, uvy, 0.0f), pr.camM);
-                    const float rx = RandomFloatPCG32(seed);
-                    const float ry = RandomFloatPCG32(seed);
-                    const float phi = 2.0f * PT_PI_F * ry;
-                    const float dd = PTK_SQRT(rx);
-                    const float diskx = pr.halfAperture * (dd * PTK_COS(phi));
-                    const float disky = pr.halfAperture * (dd * PTK_SIN(phi));
-                    const V3 pointOnAperture = camPos + mulVM(mk3(diskx, disky, pr.apertureDist), pr.camM);
-                    ray.dir = normalize(pointOnAperture - ray.origin);
-                    const float r5 = RandomFloatPCG32(seed);
-                    const float l_h = 360.0f * (1.0f - r5) + 800.0f * r5;
-                    TracePathLens(c, l_h, ray);
-                    l = SampleWavelengths(l_h);
-                    radiance = mk4(0.0f, 0.0f, 0.0f, 0.0f);
-                    rayradiance = mk4(1.0f, 1.0f, 1.0f, 1.0f);
-                    MISBRDFWeight = 1.0f;
-                    bounce = 0;
-                    isShadow = false;
-                    if (pathLength > 0) st = PT_ST_ISECT; else pendingFinish = true; /* stays in NEW */
                 } else {
                     st = PT_ST_DONE;
                 }
             }
         } else if (phase == PT_ST_ISECT) {
-            if (st == PT_ST_ISECT) { /* Intersection / LightSourceVisibilityCheck up to the SDF part */
-                Ray r;
-                r.origin = ray.origin;
-                r.dir = isShadow ? shDir : ray.dir;
-                IntersectionAnalytic(c, r, h, isShadow);
-                st = PT_ST_SHADE;
-#if PT_HAS_SDF
-                /* SphereTracing's prologue, shader.comp:780-801 */
-                const V3 invdir = mk3(PTK_DIV(1.0f, r.dir.x), PTK_DIV(1.0f, r.dir.y), PTK_DIV(1.0f, r.dir.z));
-                tMin = 1e5f; tMax = 1e5f;
-                if (SearchSDF(c, r.origin, invdir, tMin, tMax, set1)) {
-                    mt = PTK_MAX(tMin, 1e-3f);
-                    insT = 0.0f; omega = 1.70f; previousRadius = 0.0f; points = 0; iter = 0;
-                    sub = PT_SUB_SIGN;
-                    st = PT_ST_SDF;
-                }
-#endif
-            }
+            if (st == PT_ST_ISECT) st = PhaseIsect(c, ps, ms);
         }
 #if PT_HAS_SDF
         else if (phase == PT_ST_SDF) {
 #pragma unroll 1
             for (int rep = 0; rep < PT_SDF_REPS; rep++) {
-                if (st == PT_ST_SDF) {
-                    const V3 dir = isShadow ? shDir : ray.dir;
-                    V3 pe = ray.origin;
-                    if (sub != PT_SUB_SIGN) {
-                        pe = fma3(dir, mt, ray.origin);
-                        if (sub >= PT_SUB_N0) { /* CalculateNumericalSDFNormals, shader.comp:721-730: p +- h.xyy etc. */
-                            const int j = sub - PT_SUB_N0, axis = j >> 1;
-                            const float ex = (axis == 0) ? 1e-4f : 0.0f, ey = (axis == 1) ? 1e-4f : 0.0f, ez = (axis == 2) ? 1e-4f : 0.0f;
-                            pe = (j & 1) ? mk3(pe.x - ex, pe.y - ey, pe.z - ez) : mk3(pe.x + ex, pe.y + ey, pe.z + ez);
-                        }
-                    }
-                    const float d = SDF(pe, set1); /* the one SDF() site of the kernel */
-                    if (sub == PT_SUB_SIGN) { /* shader.comp:801 */
-                        ksign = gsign(d);
-                        sub = PT_SUB_STEP;
-                    } else if (sub == PT_SUB_STEP) { /* one iteration of the loop at shader.comp:803-849 */
-                        const float radius = d;
-                        bool finished = false, nohit = false;
-                        if (insT > (fabsf(previousRadius) + fabsf(radius))) {
-                            mt -= insT;
-                            omega = 1.0f;
-                            insT = previousRadius * omega * ksign;
-                            mt += insT;
-                        } else if (fabsf(radius) < 1e-4f) {
-                            finished = true;
-                        } else {
-                            if (mt > tMax) points += 1; else points = 0;
-                            if (points >= 2) {
-                                mt = tMax + 1e-3f;
-                                tMin = 1e5f; tMax = 1e5f;
-                                const V3 invdir = mk3(PTK_DIV(1.0f, dir.x), PTK_DIV(1.0f, dir.y), PTK_DIV(1.0f, dir.z));
-                                if (SearchSDF(c, fma3(dir, mt, ray.origin), invdir, tMin, tMax, set1)) {
-                                    tMin += mt; tMax += mt;
-                                    mt = PTK_MAX(tMin, mt);
-                                } else {
-                                    nohit = true;
-                                }
-                            } else {
-                                insT = radius * omega * ksign;
-                                mt += insT;
-                                const float omegaSpeedFactor = PTK_MIN(PTK_DIV(radius, previousRadius), 0.99f);
-                                omega += 0.20f * (PTK_MIN(PTK_DIV(1.0f, 1.0f - omegaSpeedFactor), 1.70f) - omega);
-                                previousRadius = radius;
-                            }
-                        }
-                        if (!finished && !nohit) {
-                            iter++;
-                            if (iter >= 512) finished = true; /* falls through to "hit" unconverged: SURVEY App. C-9 */
-                        }
-                        if (nohit) {
-                            st = PT_ST_SHADE;
-                        } else if (finished) { /* shader.comp:851-858 */
-                            if (mt < h.t) {
-                                h.t = mt - 1e-3f;
-                                h.objectID = -1;
-                                if (isShadow) st = PT_ST_SHADE; else sub = PT_SUB_N0;
-                            } else {
-                                st = PT_ST_SHADE;
-                            }
-                        }
-                    } else {
-                        const int j = sub - PT_SUB_N0;
-                        if ((j & 1) == 0) {
-                            probe = d;
-                        } else {
-                            const float g = probe - d;
-                            if (j == 1) nrm0 = g; else if (j == 3) nrm1 = g; else nrm2 = g;
-                        }
-                        sub++;
-                        if (j == 5) {
-                            const V3 p = fma3(dir, mt, ray.origin);
-                            h.normal = normalize(mk3(nrm0, nrm1, nrm2));
-                            h.materialID = ::pt_sdfmaterial_dispatch(p.x, p.y, p.z, set1);
-                            h.lightID = -1.0f;
-                            st = PT_ST_SHADE;
-                        }
-                    }
-                }
+                if (st == PT_ST_SDF) st = PhaseSdfEval(c, ps, ms);
             }
         }
 #endif
-        else { /* PT_ST_SHADE */
-            if (st == PT_ST_SHADE) {
-                bool done = false; /* path finished: project it in the NEW phase */
-                if (isShadow) { /* LightSourceVisibilityCheck's verdict, shader.comp:1218-1222, 1328-1334 */
-                    if (h.objectID == shObj) radiance = radiance + shContrib;
-                    isShadow = false;
-                    if (pathAlive) { ray.dir = nextDir; st = PT_ST_ISECT; } else done = true;
-                } else if (!(h.t < 1e5f)) { /* TraceRay, shader.comp:1345-1391: miss */
-                    done = true;
-                } else {
-                    float emitT, emitL; /* the light Emit() is evaluated for: the one hit, or the one sampled */
-                    GetLightMix(c, h.lightID, emitT, emitL);
-                    const bool emitterHit = emitL > 0.0f; /* terminates the path, shader.comp:1359-1364 */
-                    bool needShadow = false, alive = false;
-                    V4 rr = rayradiance;
-                    float emitScale = MISBRDFWeight;
-                    V3 outOrigin = ray.origin, outDir = ray.dir;
-                    if (!emitterHit) {
-                        float peak, sigma, invertf;
-                        GetMaterialMix(c, h.materialID, peak, sigma, invertf);
-                        const V4 brdf = EvaluateBRDF(l, peak, sigma, invertf);
-                        outOrigin = fma3(ray.dir, h.t, ray.origin);
-                        outDir = SampleCosineDirectionHemisphere(h.normal, seed);
-                        const float BRDFpdf = PTK_DIV(dot(outDir, h.normal), PT_PI_F);
-                        if (sc.numLights > 0.0f) { /* SampleLightSource, shader.comp:1298-1343 */
-                            const int randomLight = __float2int_rz(floorf(RandomFloatPCG32(seed) * sc.numLights));
-                            const PtDevLightSlot& ls = sc.lightSlots[randomLight < sc.nLightSlots ? randomLight : sc.nLightSlots - 1];
-                            const V3 toLight = mk3(ls.px - outOrigin.x, ls.py - outOrigin.y, ls.pz - outOrigin.z);
-                            const float invLightDistance = PTK_DIV(1.0f, length(toLight));
-                            const V3 lightDir = toLight * invLightDistance;
-                            const float sinthetaMax = PTK_MIN(ls.boundingRadius * invLightDistance, 1.0f);
-                            const float costhetaMax = PTK_SQRT(1.0f - sinthetaMax * sinthetaMax);
-                            const V3 sdir = ToWorld(SampleCosineUnitCone(seed, costhetaMax), lightDir);
-                            float lightpdf = sc.invNumLights;
-                            lightpdf *= PTK_DIV(dot(sdir, lightDir), PT_PI_F * (1.0f - costhetaMax * costhetaMax));
-                            MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + lightpdf * lightpdf);
-                            const float costheta = dot(sdir, h.normal);
-                            const float deathProbability = 1.25f * PTK_MAX(MISBRDFWeight - 0.2f, 0.0f);
-                            if (costheta >= 0.0f) {
-                                if (RandomFloatPCG32(seed) > deathProbability) {
-                                    GetLightMix(c, ls.lightID, emitT, emitL);
-                                    rr = rayradiance * mulDiv4(brdf, costheta, lightpdf);
-                                    emitScale = 1.0f - MISBRDFWeight;
-                                    shDir = sdir;
-                                    shObj = ls.objectID;
-                                    needShadow = true;
-                                } else {
-                                    MISBRDFWeight = 1.0f;
-                                }
-                            }
-                        } else {
-                            MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + 0.0f * 0.0f);
-                        }
-                        const float costheta = dot(outDir, h.normal);
-                        rayradiance = rayradiance * mulDiv4(brdf, costheta, BRDFpdf);
-                        const float mx = PTK_MAX(rayradiance.x, PTK_MAX(rayradiance.y, PTK_MAX(rayradiance.z, rayradiance.w)));
-                        const float rayProbability = PTK_MIN(PTK_MAX(mx, 0.0f), 0.99f);
-                        alive = !(RandomFloatPCG32(seed) > rayProbability);
-                        if (alive) rayradiance = rayradiance * PTK_DIV(1.0f, rayProbability);
-                        bounce++;
-                        if (bounce >= pathLength) alive = false; /* TracePath's loop bound, shader.comp:1400 */
-                    }
-                    if (emitterHit || needShadow) { /* the one Emit() site: (Emit * rr) * scale in both uses */
-                        const V4 e = Emit(l, PTK_MAX(emitT, 0.0f), PTK_MAX(emitL, 0.0f));
-                        const V4 contrib = (e * rr) * emitScale;
-                        if (emitterHit) radiance = radiance + contrib; else shContrib = contrib;
-                    }
-                    ray.origin = outOrigin;
-                    if (emitterHit) {
-                        done = true;
-                    } else if (needShadow) {
-                        isShadow = true;
-                        nextDir = outDir;
-                        pathAlive = alive;
-                        st = PT_ST_ISECT;
-                    } else if (alive) {
-                        ray.dir = outDir;
-                        st = PT_ST_ISECT;
-                    } else {
-                        done = true;
-                    }
-                }
-                if (done) { pendingFinish = true; st = PT_ST_NEW; }
-            }
+        else {
+            if (st == PT_ST_SHADE) st = PhaseShade(c, ps);
         }
     }
     if (inRange) StoreTexel(pr, image, gx, gy, outColor);

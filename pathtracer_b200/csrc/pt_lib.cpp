@@ -26,6 +26,9 @@ struct JitKernel {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kernel = nullptr;
     cudaKernel_t sdf_eval = nullptr; /* only for scenes with SDF snippets */
+    /* wavefront pipeline (pt_wavefront.cuh); wf_march only with SDF snippets */
+    cudaKernel_t wf_gen = nullptr, wf_isect = nullptr, wf_march = nullptr, wf_shade = nullptr, wf_final = nullptr,
+                 wf_ctl = nullptr;
 };
 
 }  // namespace
@@ -35,6 +38,10 @@ struct pt_ctx {
     cudaStream_t stream = nullptr;
     int mode = PT_MODE_STRICT;
     int jit_policy = 1;      /* 0: never (static kernels only), 1: when the scene has SDFs, 2: always (baked counts) */
+    int pipeline = PT_PIPE_MEGAKERNEL;
+    PtWf wf;                 /* wavefront buffers (lazily allocated) */
+    void* wf_block = nullptr;
+    size_t wf_paths = 0, wf_pixels = 0;
     bool scene_set = false;
     pt_ubo ubo;
     PtDevScene dev_scene;
@@ -66,7 +73,10 @@ int cuda_fail(pt_ctx* ctx, cudaError_t e, const char* what) {
         if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); \
     } while (0)
 
+int launch_wavefront(pt_ctx* ctx, const PtDevParams& dp);
+
 int launch(pt_ctx* ctx, const PtDevParams& dp) {
+    if (ctx->pipeline == PT_PIPE_WAVEFRONT) return launch_wavefront(ctx, dp);
     if (!ctx->timing_open) {
         PT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
         ctx->timing_open = true;
@@ -84,6 +94,97 @@ int launch(pt_ctx* ctx, const PtDevParams& dp) {
     }
     PT_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
+    return PT_OK;
+}
+
+/* (Re)allocate the SoA path state for `paths` paths over `pixels` pixels: one block, carved into arrays */
+int wf_alloc(pt_ctx* ctx, size_t paths, size_t pixels) {
+    if (ctx->wf_block && ctx->wf_paths >= paths && ctx->wf_pixels >= pixels) return PT_OK;
+    if (ctx->wf_block) { cudaFree(ctx->wf_block); ctx->wf_block = nullptr; }
+    const size_t f4 = paths * 16, total = 10 * f4 + pixels * 16 + paths * 8 + 4 * paths * 4 + 256;
+    PT_CUDA(ctx, cudaMalloc(&ctx->wf_block, total));
+    char* b = (char*)ctx->wf_block;
+    PtWf& w = ctx->wf;
+    void** f4s[10] = {&w.rayO, &w.rayD, &w.wl, &w.rad, &w.thr, &w.shD, &w.shC, &w.hit0, &w.hit1, &w.col};
+    for (int i = 0; i < 10; i++) { *f4s[i] = b; b += f4; }
+    w.acc = b; b += pixels * 16;
+    w.misc = b; b += paths * 8;
+    void** qs[4] = {&w.qA, &w.qB, &w.qS, &w.qM};
+    for (int i = 0; i < 4; i++) { *qs[i] = b; b += paths * 4; }
+    w.cnt = b;
+    ctx->wf_paths = paths;
+    ctx->wf_pixels = pixels;
+    return PT_OK;
+}
+
+/* One dispatch through the wavefront pipeline: chunks of samples x (GEN, per depth {ISECT, MARCH, SHADE} for the path
+ * rays and again for the shadow rays, FINAL).  Queue sizes stay on the device; every kernel is launched with a fixed
+ * persistent grid and reads its count there, so the host never synchronises inside a dispatch. */
+int launch_wavefront(pt_ctx* ctx, const PtDevParams& dp0) {
+    JitKernel* k = ctx->active_jit;
+    if (!k || !k->wf_gen) return fail(ctx, PT_ERR_ARG, "wavefront pipeline: kernels not built (call pt_set_scene after pt_set_pipeline)");
+    const size_t pixels = (size_t)dp0.width * (size_t)dp0.height;
+    size_t max_paths = 32u << 20;
+    if (const char* e = getenv("PT_WF_MAX_PATHS")) { if (atoll(e) > 0) max_paths = (size_t)atoll(e); }
+    int chunk = (int)(max_paths / pixels);
+    if (chunk < 1) chunk = 1;
+    if (chunk > dp0.samplesPerFrame) chunk = dp0.samplesPerFrame;
+    int rc = wf_alloc(ctx, pixels * (size_t)chunk, pixels);
+    if (rc != PT_OK) return rc;
+    if (!ctx->timing_open) {
+        PT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        ctx->timing_open = true;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const dim3 block(128, 1, 1), grid((unsigned)(sms * 8), 1, 1), one(1, 1, 1);
+    const float* ubo = ctx->d_ubo;
+    float* image = ctx->d_image;
+    PtDevParams dp = dp0;
+    PtWf w = ctx->wf;
+    w.nPix = (unsigned)pixels;
+    const bool has_sdf = ctx->dev_scene.nSdfs > 0;
+    auto run = [&](cudaKernel_t kern, const dim3& g, int which, int identity, int nargs) -> cudaError_t {
+        void* args[7] = {(void*)&ctx->dev_scene, (void*)&dp, (void*)&ubo, (void*)&w, (void*)&which, (void*)&identity, nullptr};
+        (void)nargs;
+        ctx->launches++;
+        return cudaLaunchKernel((const void*)kern, g, block, args, 0, ctx->stream);
+    };
+    auto ctl = [&](int op) -> cudaError_t {
+        void* args[2] = {(void*)&w, (void*)&op};
+        return cudaLaunchKernel((const void*)k->wf_ctl, one, dim3(32, 1, 1), args, 0, ctx->stream);
+    };
+    for (int base = 0; base < dp0.samplesPerFrame; base += chunk) {
+        const int ns = (dp0.samplesPerFrame - base < chunk) ? dp0.samplesPerFrame - base : chunk;
+        w.P = (unsigned)(pixels * (size_t)ns);
+        w.chunkBase = base;
+        w.chunkSamples = ns;
+        w.lastChunk = (base + ns >= dp0.samplesPerFrame) ? 1 : 0;
+        w.qA = ctx->wf.qA;
+        w.qB = ctx->wf.qB;
+        PT_CUDA(ctx, ctl(0));
+        PT_CUDA(ctx, run(k->wf_gen, grid, 0, 0, 4));
+        for (int depth = 0; depth < dp0.pathLength; depth++) {
+            const int identity = (depth == 0) ? 1 : 0;
+            PT_CUDA(ctx, run(k->wf_isect, grid, 0, identity, 6));
+            if (has_sdf) PT_CUDA(ctx, run(k->wf_march, grid, 0, 0, 4));
+            PT_CUDA(ctx, run(k->wf_shade, grid, 0, identity, 6));
+            if (ctx->dev_scene.numLights > 0.0f) { /* shadow rays of this depth */
+                if (has_sdf) PT_CUDA(ctx, ctl(1));
+                PT_CUDA(ctx, run(k->wf_isect, grid, 1, 0, 6));
+                if (has_sdf) PT_CUDA(ctx, run(k->wf_march, grid, 0, 0, 4));
+                PT_CUDA(ctx, run(k->wf_shade, grid, 1, 0, 6));
+            }
+            PT_CUDA(ctx, ctl(2));
+            void* t = w.qA; w.qA = w.qB; w.qB = t;
+        }
+        {
+            void* args[5] = {(void*)&ctx->dev_scene, (void*)&dp, (void*)&ubo, (void*)&w, (void*)&image};
+            ctx->launches++;
+            PT_CUDA(ctx, cudaLaunchKernel((const void*)k->wf_final, grid, block, args, 0, ctx->stream));
+        }
+    }
+    PT_CUDA(ctx, cudaGetLastError());
     return PT_OK;
 }
 
@@ -139,6 +240,7 @@ void pt_destroy(pt_ctx* ctx) {
     for (auto& kv : ctx->jit_cache)
         if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
     if (ctx->own_image && ctx->d_image) cudaFree(ctx->d_image);
+    if (ctx->wf_block) cudaFree(ctx->wf_block);
     if (ctx->d_ubo) cudaFree(ctx->d_ubo);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -162,6 +264,14 @@ int pt_set_jit(pt_ctx* ctx, int policy) {
     return PT_OK;
 }
 
+int pt_set_pipeline(pt_ctx* ctx, int pipeline) {
+    if (!ctx) return fail(nullptr, PT_ERR_ARG, "null context");
+    if (pipeline != PT_PIPE_MEGAKERNEL && pipeline != PT_PIPE_WAVEFRONT) return fail(ctx, PT_ERR_ARG, "unknown pipeline");
+    ctx->pipeline = pipeline;
+    ctx->scene_set = false;
+    return PT_OK;
+}
+
 int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, int n_sdf) {
     if (!ctx || !ubo) return fail(ctx, PT_ERR_ARG, "pt_set_scene: null argument");
     PT_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -173,9 +283,10 @@ int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, in
         return fail(ctx, PT_ERR_ARG, "pt_set_scene: n_sdf (" + std::to_string(n_sdf) + ") != ubo.numObjects[5] (" +
                                          std::to_string(sc.nSdfs) + ")");
     JitKernel* jit = nullptr;
-    const bool want_jit = (n_sdf > 0) || ctx->jit_policy == 2;
-    if (n_sdf > 0 && ctx->jit_policy == 0)
-        return fail(ctx, PT_ERR_COMPILE, "scene has SDF snippets but run-time compilation is disabled (PT_JIT=0)");
+    const bool wavefront = ctx->pipeline == PT_PIPE_WAVEFRONT;
+    const bool want_jit = (n_sdf > 0) || ctx->jit_policy == 2 || wavefront;
+    if ((n_sdf > 0 || wavefront) && ctx->jit_policy == 0)
+        return fail(ctx, PT_ERR_COMPILE, "scenes with SDF snippets and the wavefront pipeline need run-time compilation (PT_JIT=0 set)");
     if (want_jit) {
         std::string unit;
         if (n_sdf > 0) {
@@ -185,9 +296,10 @@ int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, in
         PtJitOptions opt;
         opt.mode = ctx->mode;
         opt.bake_counts = (ctx->jit_policy == 2);
+        opt.wavefront = wavefront;
         const int counts[6] = {sc.nSpheres, sc.nPlanes, sc.nBoxes, sc.nLenses, sc.nCyclides, sc.nSdfs};
         memcpy(opt.counts, counts, sizeof counts);
-        std::string key = std::to_string(opt.mode) + (opt.bake_counts ? "b" : "g");
+        std::string key = std::to_string(opt.mode) + (opt.bake_counts ? "b" : "g") + (wavefront ? "w" : "m");
         if (opt.bake_counts)
             for (int i = 0; i < 6; i++) key += "," + std::to_string(counts[i]);
         key += "|" + unit;
@@ -207,6 +319,18 @@ int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, in
             if (n_sdf > 0 && (e = cudaLibraryGetKernel(&jk.sdf_eval, jk.lib, "pt_sdf_eval_jit")) != cudaSuccess) {
                 cudaLibraryUnload(jk.lib);
                 return cuda_fail(ctx, e, "cudaLibraryGetKernel(pt_sdf_eval_jit)");
+            }
+            if (wavefront) {
+                struct { const char* name; cudaKernel_t* k; bool need; } wk[] = {
+                    {"pt_wf_gen", &jk.wf_gen, true}, {"pt_wf_isect", &jk.wf_isect, true}, {"pt_wf_march", &jk.wf_march, n_sdf > 0},
+                    {"pt_wf_shade", &jk.wf_shade, true}, {"pt_wf_final", &jk.wf_final, true}, {"pt_wf_ctl", &jk.wf_ctl, true}};
+                for (auto& x : wk) {
+                    if (!x.need) continue;
+                    if ((e = cudaLibraryGetKernel(x.k, jk.lib, x.name)) != cudaSuccess) {
+                        cudaLibraryUnload(jk.lib);
+                        return cuda_fail(ctx, e, x.name);
+                    }
+                }
             }
             it = ctx->jit_cache.emplace(key, jk).first;
         }
@@ -365,6 +489,7 @@ int pt_sdf_compile_check(const char* const* sdf_glsl, int n_sdf, const float* sd
     PtJitOptions opt;
     opt.mode = mode;
     opt.bake_counts = false;
+    opt.wavefront = false;
     memset(opt.counts, 0, sizeof opt.counts);
     std::vector<char> cubin;
     rc = pt_jit_compile(unit, opt, &cubin, &log);
@@ -386,8 +511,9 @@ int pt_kernel_compile_check(const pt_ubo* ubo, const char* const* sdf_glsl, int 
         if (rc != PT_OK) return fail(nullptr, rc, err);
     }
     PtJitOptions opt;
-    opt.mode = mode;
+    opt.mode = mode & 1;
     opt.bake_counts = bake_counts != 0;
+    opt.wavefront = (mode & 2) != 0; /* mode bit 1: also build the wavefront kernels */
     const int counts[6] = {sc.nSpheres, sc.nPlanes, sc.nBoxes, sc.nLenses, sc.nCyclides, sc.nSdfs};
     memcpy(opt.counts, counts, sizeof counts);
     std::vector<char> cubin;
