@@ -5,7 +5,8 @@
  * the same parameters as flags and drives the library through the C ABI only (include/pt_abi.h).
  *
  *   pt_render --scene scenes/scene0.json --width 512 --height 512 --spp 64 --spf 8 --path-length 5 --shot 1 \
- *             [--fast] [--jit 0|1|2] [--device 0] [--out render.pfm|render.ppm] [--tonemap 3]
+ *             [--fast] [--wavefront] [--jit 0|1|2] [--device 0] [--out render.pfm|render.ppm] [--tonemap 3]
+ *             [--resume checkpoint.pfm --done-samples N]      continue a run saved with --out checkpoint.pfm
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -25,7 +26,8 @@ static int die(const char* what, pt_ctx* ctx) {
 int main(int argc, char** argv) {
     std::string scene_path = "scenes/scene0.json", out_path;
     int width = 1280, height = 720, spp = 1000, spf = 1, path_length = 5, shot = 1, device = 0, tonemap = 3; /* host:30-31,1164-1174 */
-    int fast = 0, jit = -1;
+    int fast = 0, jit = -1, wavefront = 0, done = 0;
+    std::string resume_path;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&](const char* name) -> const char* {
@@ -44,6 +46,9 @@ int main(int argc, char** argv) {
         else if (a == "--out") out_path = next("--out");
         else if (a == "--jit") jit = atoi(next("--jit"));
         else if (a == "--fast") fast = 1;
+        else if (a == "--wavefront") wavefront = 1;
+        else if (a == "--resume") resume_path = next("--resume");            /* PFM checkpoint written by --out x.pfm */
+        else if (a == "--done-samples") done = atoi(next("--done-samples"));   /* samples per pixel already in it */
         else if (a == "--strict") fast = 0;
         else { fprintf(stderr, "pt_render: unknown flag %s\n", a.c_str()); return 2; }
     }
@@ -61,11 +66,17 @@ int main(int argc, char** argv) {
     if (pt_create(device, &ctx) != PT_OK) return die("create context", nullptr);
     pt_set_mode(ctx, fast ? PT_MODE_FAST : PT_MODE_STRICT);
     if (jit >= 0) pt_set_jit(ctx, jit);
+    if (wavefront) pt_set_pipeline(ctx, PT_PIPE_WAVEFRONT);
     auto t0 = std::chrono::steady_clock::now();
     if (pt_set_scene(ctx, &ubo, sdf.data(), (int)sdf.size()) != PT_OK) return die("set scene", ctx);
     auto t1 = std::chrono::steady_clock::now();
     if (pt_resize(ctx, width, height) != PT_OK) return die("resize", ctx);
-    if (pt_render(ctx, &params, spp, spf) != PT_OK) return die("render", ctx);
+    if (!resume_path.empty()) {
+        std::vector<float> ck((size_t)width * height * 4);
+        if (pt_read_pfm(resume_path.c_str(), ck.data(), width, height) != PT_OK) { fprintf(stderr, "pt_render: cannot read %s\n", resume_path.c_str()); return 1; }
+        if (pt_write_xyz(ctx, ck.data(), ck.size()) != PT_OK) return die("upload checkpoint", ctx);
+    }
+    if (pt_render_resume(ctx, &params, resume_path.empty() ? 0 : done, spp, spf) != PT_OK) return die("render", ctx);
     auto t2 = std::chrono::steady_clock::now();
     float ms = 0.0f;
     long long launches = 0;

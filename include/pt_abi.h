@@ -128,6 +128,9 @@ int pt_finalize(pt_ctx* ctx, const pt_params* params, int total_samples);
 /* Mapped texel memory (host:3491-3518 reads it through a persistent mapping): copies W*H*4 floats to the host.
  * Synchronises the stream. */
 int pt_read_xyz(pt_ctx* ctx, float* rgba, size_t n_floats);
+/* Checkpoint / resume (the accumulation image is the whole render state; the reference loses
+ * it on exit): upload a saved image, then continue with pt_render_resume / pt_dispatch from the sample count reached */
+int pt_write_xyz(pt_ctx* ctx, const float* rgba, size_t n_floats);
 int pt_sync(pt_ctx* ctx);
 void* pt_image_ptr(pt_ctx* ctx);    /* device pointer of the accumulation image */
 void* pt_stream_handle(pt_ctx* ctx); /* cudaStream_t the kernels are launched on */
@@ -158,11 +161,13 @@ int pt_scene_pack_params(const pt_scene* scene, int shot, int width, int height,
 /* Offscreen MainLoop (host:4005-4086): total_samples/samples_per_frame dispatches with the reference's
  * frame/currentSamples bookkeeping. Blocks until done. */
 int pt_render(pt_ctx* ctx, const pt_params* base, int total_samples, int samples_per_frame);
+int pt_render_resume(pt_ctx* ctx, const pt_params* base, int done_samples, int total_samples, int samples_per_frame);
 
 /* SaveRender + SavePPM (host:3491-3518, 918-933): display transform of shader.frag:31-93, 8-bit P6.
  * pt_write_pfm writes the raw XYZ (or linear sRGB when to_rgb != 0) as a bottom-up PF file. */
 int pt_write_ppm(const char* path, const float* rgba, int width, int height, int tonemap);
 int pt_write_pfm(const char* path, const float* rgba, int width, int height, int to_rgb);
+int pt_read_pfm(const char* path, float* rgba, int width, int height); /* reads a to_rgb = 0 file back (w = 1) */
 
 /* ---- introspection used by the tests --------------------------------------------------------------------- */
 const float* pt_cie1931_table(void); /* 1323 floats */

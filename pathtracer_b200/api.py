@@ -82,6 +82,9 @@ def lib():
         L.pt_finalize.argtypes = [vp, vp, ci]
         L.pt_render.argtypes = [vp, vp, ci, ci]
         L.pt_read_xyz.argtypes = [vp, vp, C.c_size_t]
+        L.pt_write_xyz.argtypes = [vp, vp, C.c_size_t]
+        L.pt_render_resume.argtypes = [vp, vp, ci, ci, ci]
+        L.pt_read_pfm.argtypes = [C.c_char_p, vp, ci, ci]
         L.pt_sync.argtypes = [vp]
         L.pt_image_ptr.argtypes = [vp]
         L.pt_image_ptr.restype = vp
@@ -279,6 +282,14 @@ class Renderer:
             out = np.empty((self.height, self.width, 4), dtype=np.float32)
         _check(lib().pt_read_xyz(self._ctx, _ptr(out), out.size), self._ctx)
         return out
+
+    def write_xyz(self, image):
+        """Upload a saved accumulation image (checkpoint resume)."""
+        image = np.ascontiguousarray(image, dtype=np.float32)
+        _check(lib().pt_write_xyz(self._ctx, _ptr(image), image.size), self._ctx)
+
+    def render_resume(self, params, done_samples, total_samples, spf):
+        _check(lib().pt_render_resume(self._ctx, _ptr(np.ascontiguousarray(params)), done_samples, total_samples, spf), self._ctx)
 
     def kernel_time(self):
         """(milliseconds of device time, number of kernel launches) since the previous call; CUDA events."""

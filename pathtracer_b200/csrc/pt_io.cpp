@@ -83,4 +83,31 @@ int pt_write_pfm(const char* path, const float* rgba, int width, int height, int
     return ok ? PT_OK : PT_ERR_IO;
 }
 
+/* Reads back what pt_write_pfm(..., to_rgb = 0) wrote: XYZ into the rgb of an RGBA buffer, w = 1 (checkpoints) */
+int pt_read_pfm(const char* path, float* rgba, int width, int height) {
+    if (!path || !rgba || width <= 0 || height <= 0) return PT_ERR_ARG;
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return PT_ERR_IO;
+    char magic[3] = {0, 0, 0};
+    int w = 0, h = 0;
+    float scale = 0.0f;
+    if (fscanf(fp, "%2s %d %d %f", magic, &w, &h, &scale) != 4 || magic[0] != 'P' || magic[1] != 'F' || w != width || h != height ||
+        !(scale < 0.0f)) { /* little-endian files have a negative scale */
+        fclose(fp);
+        return PT_ERR_IO;
+    }
+    fgetc(fp); /* the single whitespace after the header */
+    std::vector<float> row((size_t)width * 3);
+    bool ok = true;
+    for (int y = height - 1; y >= 0 && ok; y--) {
+        ok = fread(row.data(), sizeof(float), row.size(), fp) == row.size();
+        for (int x = 0; x < width && ok; x++) {
+            float* t = rgba + 4 * ((size_t)x + (size_t)width * (size_t)y);
+            t[0] = row[3 * (size_t)x]; t[1] = row[3 * (size_t)x + 1]; t[2] = row[3 * (size_t)x + 2]; t[3] = 1.0f;
+        }
+    }
+    fclose(fp);
+    return ok ? PT_OK : PT_ERR_IO;
+}
+
 } /* extern "C" */

@@ -419,13 +419,19 @@ int pt_finalize(pt_ctx* ctx, const pt_params* params, int total_samples) {
 }
 
 int pt_render(pt_ctx* ctx, const pt_params* base, int total_samples, int samples_per_frame) {
+    return pt_render_resume(ctx, base, 0, total_samples, samples_per_frame);
+}
+
+/* pt_render continuing a run that already holds done_samples samples per pixel in the image (a multiple of
+ * samples_per_frame): dispatches done/spf + 1 .. total/spf with the same bookkeeping. */
+int pt_render_resume(pt_ctx* ctx, const pt_params* base, int done_samples, int total_samples, int samples_per_frame) {
     if (!ctx || !base) return fail(ctx, PT_ERR_ARG, "pt_render: null argument");
-    if (samples_per_frame <= 0 || total_samples < samples_per_frame)
-        return fail(ctx, PT_ERR_ARG, "pt_render: need total_samples >= samples_per_frame > 0");
+    if (samples_per_frame <= 0 || total_samples < samples_per_frame || done_samples < 0 || done_samples % samples_per_frame != 0)
+        return fail(ctx, PT_ERR_ARG, "pt_render: need total_samples >= samples_per_frame > 0 and done_samples a multiple of it");
     pt_params p = *base;
     p.samplesPerFrame = samples_per_frame;
     /* offscreen MainLoop bookkeeping (host:4042-4048): before dispatch j, frame = currentSamples = j * spf */
-    for (int j = 1; j * samples_per_frame <= total_samples; j++) {
+    for (int j = done_samples / samples_per_frame + 1; j * samples_per_frame <= total_samples; j++) {
         p.frame = j * samples_per_frame;
         p.currentSamples = j * samples_per_frame;
         int rc = pt_dispatch(ctx, &p);
@@ -447,6 +453,18 @@ int pt_read_xyz(pt_ctx* ctx, float* rgba, size_t n_floats) {
     if (n_floats < need) return fail(ctx, PT_ERR_ARG, "pt_read_xyz: buffer too small");
     PT_CUDA(ctx, cudaSetDevice(ctx->device));
     PT_CUDA(ctx, cudaMemcpyAsync(rgba, ctx->d_image, need * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PT_OK;
+}
+
+/* Checkpoint / resume: the accumulation image IS the render state; uploading a saved one and
+ * continuing with frame/currentSamples where the saved run stopped resumes it exactly. */
+int pt_write_xyz(pt_ctx* ctx, const float* rgba, size_t n_floats) {
+    if (!ctx || !rgba || !ctx->d_image) return fail(ctx, PT_ERR_ARG, "pt_write_xyz: bad argument");
+    const size_t need = (size_t)ctx->width * (size_t)ctx->height * 4;
+    if (n_floats < need) return fail(ctx, PT_ERR_ARG, "pt_write_xyz: buffer too small");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_image, rgba, need * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PT_OK;
 }

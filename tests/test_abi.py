@@ -54,3 +54,37 @@ def test_product_does_not_reference_the_oracle():
                             if re.search(r'(import\s+oracle|from\s+oracle|#include\s*"[^"]*oracle|liboracle)', line):
                                 bad.append((f, line))
     assert not bad, bad
+
+
+def test_pfm_and_ppm_writers(ptlib, tmp_path):
+    """pt_write_pfm / pt_read_pfm round trip (bottom-up rows) and pt_write_ppm = SaveRender + SavePPM (host:3491-3518,
+    918-933) with the display transform of shader.frag:31-93, checked against a numpy restatement."""
+    import ctypes as C
+    import numpy as np
+    L = ptlib.lib()
+    rng = np.random.default_rng(4)
+    img = np.ones((5, 7, 4), dtype=np.float32)
+    img[..., :3] = rng.random((5, 7, 3)).astype(np.float32) * 2
+    pfm = str(tmp_path / 'a.pfm').encode()
+    assert L.pt_write_pfm(pfm, img.ctypes.data_as(C.c_void_p), 7, 5, 0) == 0
+    raw = open(pfm, 'rb').read()
+    assert raw.startswith(b'PF\n7 5\n-1.0\n')
+    body = np.frombuffer(raw[len(b'PF\n7 5\n-1.0\n'):], dtype='<f4').reshape(5, 7, 3)
+    assert np.array_equal(body[::-1], img[..., :3])          # PFM stores the bottom scanline first
+    back = np.zeros_like(img)
+    assert L.pt_read_pfm(pfm, back.ctypes.data_as(C.c_void_p), 7, 5) == 0 and np.array_equal(back, img)
+    ppm = str(tmp_path / 'a.ppm').encode()
+    for tm in (0, 1, 2, 3):
+        assert L.pt_write_ppm(ppm, img.ctypes.data_as(C.c_void_p), 7, 5, tm) == 0
+        raw = open(ppm, 'rb').read()
+        assert raw.startswith(b'P6\n7\n5\n255\n')
+        got = np.frombuffer(raw[len(b'P6\n7\n5\n255\n'):], dtype=np.uint8).reshape(5, 7, 3).astype(int)
+        xyz = img[..., :3].astype(np.float64)
+        e2d = np.array([[0.9531874, -0.0265906, 0.0238731], [-0.0382467, 1.0288406, 0.0094060], [0.0026068, -0.0030332, 1.0892565]])
+        x2r = np.array([[3.2404542, -1.5371385, -0.4985314], [-0.9692660, 1.8760108, 0.0415560], [0.0556434, -0.2040259, 1.0572252]])
+        rgb = np.maximum(xyz @ e2d.T @ x2r.T, 0)
+        with np.errstate(divide='ignore'):
+            rgb = [rgb, rgb / (1 + rgb), rgb * (2.51 * rgb + 0.03) / (rgb * (2.43 * rgb + 0.59) + 0.14), np.exp(-0.25 / rgb)][tm]
+        rgb = np.clip(rgb, 0, 1)
+        srgb = np.where(rgb <= 0.0031308, 12.92 * rgb, 1.055 * rgb ** (1 / 2.4) - 0.055)
+        assert np.abs(got - (srgb * 255).astype(int)).max() <= 1

@@ -293,3 +293,24 @@ def test_wavefront_matches_megakernel_fast_mode(ptlib, renderer, wf_renderer):
         mean_rel = abs(a[..., 1].mean() - b[..., 1].mean()) / a[..., 1].mean()
         print('%s: %.1f%% of pixels equal to 1e-3, mean Y rel diff %.5f' % (name, 100 * close, mean_rel))
         assert close > 0.7 and mean_rel < 0.01
+
+
+def test_checkpoint_resume_is_exact(ptlib, renderer, tmp_path):
+    """The accumulation image is the whole render state: save after 4 of 8 samples (PFM), upload into a fresh
+    context, continue -> the same bits as the uninterrupted run."""
+    import ctypes as C
+    got, ubo, p, src = gpu_render(ptlib, renderer, 'scene0', 64, 48, 8, 2)
+    half, *_ = gpu_render(ptlib, renderer, 'scene0', 64, 48, 4, 2)
+    path = str(tmp_path / 'ck.pfm').encode()
+    L = ptlib.lib()
+    assert L.pt_write_pfm(path, half.ctypes.data_as(C.c_void_p), 64, 48, 0) == 0
+    back = np.zeros_like(half)
+    assert L.pt_read_pfm(path, back.ctypes.data_as(C.c_void_p), 64, 48) == 0
+    assert np.array_equal(back.view(np.uint32), half.view(np.uint32))
+    r2 = ptlib.Renderer(device=0, mode=ptlib.MODE_STRICT)
+    r2.set_scene(ubo)
+    r2.resize(64, 48)
+    r2.write_xyz(back)
+    r2.render_resume(p, 4, 8, 2)
+    assert_bit_equal(r2.read_xyz(), got, 'resume')
+    r2.close()
