@@ -1262,10 +1262,10 @@ namespace PT_KERNEL_NS {
 #define PT_STAT(p, mask) do { } while (0)
 #endif
 #ifndef PT_SDF_REPS
-#define PT_SDF_REPS 8
+#define PT_SDF_REPS 16
 #endif
 #ifndef PT_FEED_T
-#define PT_FEED_T 12
+#define PT_FEED_T 8
 #endif
 
 __device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
