@@ -14,15 +14,13 @@
 #ifndef PT_DEV_SCENE_H
 #define PT_DEV_SCENE_H
 
-#define PT_DEV_MAX_SPHERES 48
-#define PT_DEV_MAX_PLANES 16
-#define PT_DEV_MAX_BOXES 32
-#define PT_DEV_MAX_LENSES 16
-#define PT_DEV_MAX_CYCLIDES 16
+/* Capacity = whatever fits the reference's uniform block (1024 object floats, 768 SDF floats: host:39-40), i.e. up to
+ * 170 spheres / 204 planes / 93 boxes / 85 lenses / 64 cyclides; only the first 32 SDFs are usable (set1 mask).
+ * The records of all types sit back to back in one pool, in the shader's type order; the worst case for the pool is
+ * a scene made of boxes only (20 pool floats per 11 uniform-block floats). */
 #define PT_DEV_MAX_SDFS 32
+#define PT_DEV_POOL_FLOATS (((1024 / 11) * 20) + 24 + PT_DEV_MAX_SDFS * 8)
 #define PT_DEV_MAX_LIGHT_SLOTS 65 /* lightIDs[0..numLights] inclusive: r == 1.0 reads one past */
-#define PT_DEV_MAX_MATERIALS 64
-#define PT_DEV_MAX_LIGHTS 64
 
 typedef struct PtDevSphere { /* shader.comp:59-64, 289-317 */
     float px, py, pz, radius;
@@ -83,13 +81,10 @@ typedef struct PtDevScene {
     int nSpheres, nPlanes, nBoxes, nLenses, nCyclides, nSdfs, nLightSlots;
     float numLights;     /* numObjects[6] as the float the shader multiplies with */
     float invNumLights;  /* 1.0 / numObjects[6] (shader.comp:1289) */
-    int pad0[3];
-    PtDevSphere spheres[PT_DEV_MAX_SPHERES];
-    PtDevPlane planes[PT_DEV_MAX_PLANES];
-    PtDevBox boxes[PT_DEV_MAX_BOXES];
-    PtDevLens lenses[PT_DEV_MAX_LENSES];
-    PtDevCyclide cyclides[PT_DEV_MAX_CYCLIDES];
-    PtDevSdf sdfs[PT_DEV_MAX_SDFS];
+    /* offsets (in floats) of each type's records inside pool; spheres start at 0 */
+    int offPlanes, offBoxes, offLenses, offCyclides, offSdfs;
+    int pad0[2];
+    float pool[PT_DEV_POOL_FLOATS]; /* PtDevSphere[], PtDevPlane[], PtDevBox[], PtDevLens[], PtDevCyclide[], PtDevSdf[] */
     PtDevLightSlot lightSlots[PT_DEV_MAX_LIGHT_SLOTS];
 } PtDevScene;
 

@@ -56,7 +56,17 @@
 #else
 #define PT_UNROLL_PRIMS _Pragma("unroll")
 #endif
+#define PT_OFF_PLANES(sc) (8 * PT_N_SPHERES_CONST)
+#define PT_OFF_BOXES(sc) (PT_OFF_PLANES(sc) + 4 * PT_N_PLANES_CONST)
+#define PT_OFF_LENSES(sc) (PT_OFF_BOXES(sc) + 20 * PT_N_BOXES_CONST)
+#define PT_OFF_CYCLIDES(sc) (PT_OFF_LENSES(sc) + 20 * PT_N_LENSES_CONST)
+#define PT_OFF_SDFS(sc) (PT_OFF_CYCLIDES(sc) + 24 * PT_N_CYCLIDES_CONST)
 #else
+#define PT_OFF_PLANES(sc) ((sc).offPlanes)
+#define PT_OFF_BOXES(sc) ((sc).offBoxes)
+#define PT_OFF_LENSES(sc) ((sc).offLenses)
+#define PT_OFF_CYCLIDES(sc) ((sc).offCyclides)
+#define PT_OFF_SDFS(sc) ((sc).offSdfs)
 #define PT_N_SPHERES(c) ((c).sc->nSpheres)
 #define PT_N_PLANES(c) ((c).sc->nPlanes)
 #define PT_N_BOXES(c) ((c).sc->nBoxes)
@@ -563,7 +573,7 @@ PT_DEV bool SearchSDF(const Ctx& c, V3 p, V3 invdir, float& tMin, float& tMax, u
     const int n = PT_N_SDF(c);
     for (int i = 0; i < n; i++) {
         float bx, by;
-        RayIntersectAABB(p, invdir, c.sc->sdfs[i], bx, by);
+        RayIntersectAABB(p, invdir, reinterpret_cast<const PtDevSdf*>(c.sc->pool + PT_OFF_SDFS(*c.sc))[i], bx, by);
         if ((bx > by) || (by < 0.0f)) continue;
         const unsigned bit = 1u << (unsigned)i;
         if (bx < tMin) {
@@ -675,16 +685,16 @@ PT_DEV void IntersectionAnalytic(const Ctx& c, const Ray& ray, Hit& h, const boo
     int base = 0;
     const int nS = PT_N_SPHERES(c);
     PT_UNROLL_PRIMS
-    for (int i = 0; i < nS; i++) SphereIntersection(ray, sc.spheres[i], base + i, h, kShadow);
+    for (int i = 0; i < nS; i++) SphereIntersection(ray, reinterpret_cast<const PtDevSphere*>(sc.pool)[i], base + i, h, kShadow);
     base += nS;
     const int nP = PT_N_PLANES(c);
     PT_UNROLL_PRIMS
-    for (int i = 0; i < nP; i++) PlaneIntersection(ray, sc.planes[i], base + i, h, kShadow);
+    for (int i = 0; i < nP; i++) PlaneIntersection(ray, reinterpret_cast<const PtDevPlane*>(sc.pool + PT_OFF_PLANES(sc))[i], base + i, h, kShadow);
     base += nP;
     const int nB = PT_N_BOXES(c);
     PT_UNROLL_PRIMS
     for (int i = 0; i < nB; i++) {
-        const PtDevBox& o = sc.boxes[i];
+        const PtDevBox& o = reinterpret_cast<const PtDevBox*>(sc.pool + PT_OFF_BOXES(sc))[i];
         if (!BoundingSphere(ray, o.px, o.py, o.pz, o.bound2)) continue;
         BoxIntersection(ray, o, base + i, h, kShadow);
     }
@@ -692,7 +702,7 @@ PT_DEV void IntersectionAnalytic(const Ctx& c, const Ray& ray, Hit& h, const boo
     const int nL = PT_N_LENSES(c);
     PT_UNROLL_PRIMS
     for (int i = 0; i < nL; i++) {
-        const PtDevLens& o = sc.lenses[i];
+        const PtDevLens& o = reinterpret_cast<const PtDevLens*>(sc.pool + PT_OFF_LENSES(sc))[i];
         if (!BoundingSphere(ray, o.px, o.py, o.pz, o.bound2)) continue;
         int isOutside = 1;
         LensIntersection(ray, o, base + i, h, isOutside, kShadow);
@@ -700,7 +710,7 @@ PT_DEV void IntersectionAnalytic(const Ctx& c, const Ray& ray, Hit& h, const boo
     base += nL;
     const int nC = PT_N_CYCLIDES(c);
     for (int i = 0; i < nC; i++) {
-        const PtDevCyclide& o = sc.cyclides[i];
+        const PtDevCyclide& o = reinterpret_cast<const PtDevCyclide*>(sc.pool + PT_OFF_CYCLIDES(sc))[i];
         if (!BoundingSphere(ray, o.px, o.py, o.pz, o.brad)) continue;
         DupinCyclide(ray, o, base + i, h, kShadow);
     }

@@ -79,17 +79,33 @@ int pt_prepare_scene(const pt_ubo* ubo, PtDevScene* sc, std::string* err) {
     auto count = [](float n) { int c = 0; while ((float)c < n && c < 100000) c++; return c; };
     const int nS = count(num[0]), nP = count(num[1]), nB = count(num[2]), nL = count(num[3]), nC = count(num[4]);
     const int nSdf = count(num[5]);
-    if (nS > PT_DEV_MAX_SPHERES || nP > PT_DEV_MAX_PLANES || nB > PT_DEV_MAX_BOXES || nL > PT_DEV_MAX_LENSES ||
-        nC > PT_DEV_MAX_CYCLIDES || nSdf > PT_DEV_MAX_SDFS) {
-        if (err) *err = "scene exceeds the device scene capacity (pt_dev_scene.h PT_DEV_MAX_*)";
+    /* anything the reference's 1024-float objects[] can describe fits the pool; counts that overrun the arrays
+     * (a hand-made ubo) are refused rather than read out of bounds */
+    if (6L * nS + 5L * nP + 11L * nB + 12L * nL + 16L * nC > PT_MAX_OBJECTS_SIZE || nSdf > PT_DEV_MAX_SDFS) {
+        if (err) *err = "numObjects[] describes more objects than the uniform block holds (or more than 32 SDFs)";
         return PT_ERR_ARG;
     }
     sc->nSpheres = nS; sc->nPlanes = nP; sc->nBoxes = nB; sc->nLenses = nL; sc->nCyclides = nC; sc->nSdfs = nSdf;
+    sc->offPlanes = 8 * nS;
+    sc->offBoxes = sc->offPlanes + 4 * nP;
+    sc->offLenses = sc->offBoxes + 20 * nB;
+    sc->offCyclides = sc->offLenses + 20 * nL;
+    sc->offSdfs = sc->offCyclides + 24 * nC;
+    if (sc->offSdfs + 8 * nSdf > PT_DEV_POOL_FLOATS) {
+        if (err) *err = "device scene pool overflow";
+        return PT_ERR_ARG;
+    }
+    PtDevSphere* spheres = reinterpret_cast<PtDevSphere*>(sc->pool);
+    PtDevPlane* planes = reinterpret_cast<PtDevPlane*>(sc->pool + sc->offPlanes);
+    PtDevBox* boxes = reinterpret_cast<PtDevBox*>(sc->pool + sc->offBoxes);
+    PtDevLens* lenses = reinterpret_cast<PtDevLens*>(sc->pool + sc->offLenses);
+    PtDevCyclide* cyclides = reinterpret_cast<PtDevCyclide*>(sc->pool + sc->offCyclides);
+    PtDevSdf* sdfs = reinterpret_cast<PtDevSdf*>(sc->pool + sc->offSdfs);
     const int iS = f2i(num[0]), iP = f2i(num[1]), iB = f2i(num[2]), iL = f2i(num[3]);
 
     int offset = 0;
     for (int i = 0; i < nS; i++) { /* UnpackSphere shader.comp:154-161 */
-        PtDevSphere& o = sc->spheres[i];
+        PtDevSphere& o = spheres[i];
         const int k = 6 * i;
         o.px = F.obj(k); o.py = F.obj(k + 1); o.pz = F.obj(k + 2); o.radius = F.obj(k + 3);
         o.r2 = o.radius * o.radius;
@@ -98,7 +114,7 @@ int pt_prepare_scene(const pt_ubo* ubo, PtDevScene* sc, std::string* err) {
     }
     offset += 6 * iS;
     for (int i = 0; i < nP; i++) { /* UnpackPlane shader.comp:163-169 */
-        PtDevPlane& o = sc->planes[i];
+        PtDevPlane& o = planes[i];
         const int k = 5 * i + offset;
         o.py = F.obj(k + 1);
         o.materialID = (float)(f2i(F.obj(k + 3)) - 1);
@@ -106,7 +122,7 @@ int pt_prepare_scene(const pt_ubo* ubo, PtDevScene* sc, std::string* err) {
     }
     offset += 5 * iP;
     for (int i = 0; i < nB; i++) { /* UnpackBox shader.comp:171-179 */
-        PtDevBox& o = sc->boxes[i];
+        PtDevBox& o = boxes[i];
         const int k = 11 * i + offset;
         o.px = F.obj(k); o.py = F.obj(k + 1); o.pz = F.obj(k + 2);
         rotation_matrix(F.obj(k + 3), F.obj(k + 4), F.obj(k + 5), o.m);
@@ -117,7 +133,7 @@ int pt_prepare_scene(const pt_ubo* ubo, PtDevScene* sc, std::string* err) {
     }
     offset += 11 * iB;
     for (int i = 0; i < nL; i++) { /* UnpackLens shader.comp:181-192 */
-        PtDevLens& o = sc->lenses[i];
+        PtDevLens& o = lenses[i];
         const int k = 12 * i + offset;
         prepare_lens(F.obj(k), F.obj(k + 1), F.obj(k + 2), F.obj(k + 3), F.obj(k + 4), F.obj(k + 5), F.obj(k + 6),
                      F.obj(k + 7), F.obj(k + 8), F.obj(k + 9) != 0.0f, &o);
@@ -126,7 +142,7 @@ int pt_prepare_scene(const pt_ubo* ubo, PtDevScene* sc, std::string* err) {
     }
     offset += 12 * iL;
     for (int i = 0; i < nC; i++) { /* UnpackCyclide shader.comp:194-207 */
-        PtDevCyclide& o = sc->cyclides[i];
+        PtDevCyclide& o = cyclides[i];
         const int k = 16 * i + offset;
         o.px = F.obj(k); o.py = F.obj(k + 1); o.pz = F.obj(k + 2);
         rotation_matrix(F.obj(k + 3), F.obj(k + 4), F.obj(k + 5), o.m);
@@ -137,7 +153,7 @@ int pt_prepare_scene(const pt_ubo* ubo, PtDevScene* sc, std::string* err) {
         o.lightID = (float)(f2i(F.obj(k + 15)) - 1);
     }
     for (int i = 0; i < nSdf; i++) { /* UnpackSDF shader.comp:209-214 */
-        PtDevSdf& o = sc->sdfs[i];
+        PtDevSdf& o = sdfs[i];
         o.px = F.at(PT_OFF_SDF, 6 * i); o.py = F.at(PT_OFF_SDF, 6 * i + 1); o.pz = F.at(PT_OFF_SDF, 6 * i + 2);
         o.sx = F.at(PT_OFF_SDF, 6 * i + 3); o.sy = F.at(PT_OFF_SDF, 6 * i + 4); o.sz = F.at(PT_OFF_SDF, 6 * i + 5);
     }

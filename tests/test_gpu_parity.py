@@ -314,3 +314,33 @@ def test_checkpoint_resume_is_exact(ptlib, renderer, tmp_path):
     r2.render_resume(p, 4, 8, 2)
     assert_bit_equal(r2.read_xyz(), got, 'resume')
     r2.close()
+
+
+def many_sphere_scene(n):
+    """The reference's uniform block holds up to 170 spheres (1024 object floats): a synthetic scene near that cap."""
+    import json
+    base = pack.load_scene(scene_path('scene0'))
+    rng = np.random.default_rng(5)
+    spheres = [{'position': [0.0, 6.0, -2.0], 'radius': 1.5, 'materialID': 1, 'lightID': 1}]
+    for i in range(n - 1):
+        x, z = (i % 13) - 6.0, (i // 13) - 6.0
+        spheres.append({'position': [x * 0.9, 0.3 + 0.2 * float(rng.random()), z * 0.9], 'radius': 0.3,
+                        'materialID': 1 + i % 3, 'lightID': 0})
+    scene = {'camera': base['camera'], 'sphere': spheres, 'plane': base['plane'], 'material': base['material'], 'light': base['light']}
+    return json.dumps(scene), scene
+
+
+@pytest.mark.parametrize('pipeline', [0, 1])
+def test_scene_at_the_uniform_block_capacity(ptlib, pipeline):
+    text, scene = many_sphere_scene(169)          # 169 * 6 + 5 = 1019 of 1024 object floats
+    sc = ptlib.Scene.parse(text)
+    ubo = sc.pack_ubo()
+    assert np.array_equal(ubo.view(np.uint32), pack.pack_ubo(scene).view(np.uint32)) and ubo[0] == 169
+    p = sc.pack_params(1, 64, 48, 2, 5)
+    r = ptlib.Renderer(device=0, mode=ptlib.MODE_STRICT, pipeline=pipeline)
+    r.set_scene(ubo)
+    r.resize(64, 48)
+    r.render(p, 2, 2)
+    got = r.read_xyz()
+    r.close()
+    assert_bit_equal(got, oracle.Oracle(ubo).render(p, 2, 2), '169 spheres, pipeline %d' % pipeline)

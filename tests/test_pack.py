@@ -93,3 +93,21 @@ def test_round_decimal_semantics(ptlib):
     out = json.loads(ptlib.Scene.parse(json.dumps(s)).to_json())
     assert out['sphere'][0]['radius'] == 1.23457
     assert out['sphere'][1]['position'] == [0.0, -2.0, 2.5]
+
+
+def test_capacity_is_the_uniform_block(ptlib):
+    """Any scene the reference's 1024-float objects[] can describe is accepted (170 spheres, or 93 boxes, ...); the
+    kernel for it builds (NVRTC, no GPU needed)."""
+    import ctypes as C
+    from pathtracer_b200 import api
+    base = pack.load_scene(scene_path('scene1'))
+    L = ptlib.lib()
+    L.pt_kernel_compile_check.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int]
+    for key, n in (('sphere', 170), ('box', 93), ('plane', 204)):
+        scene = {'camera': base['camera'], key: [dict(base[key][0]) for _ in range(n)], 'material': base['material'], 'light': base['light']}
+        ubo = ptlib.Scene.parse(json.dumps(scene)).pack_ubo()
+        assert np.array_equal(ubo.view(np.uint32), pack.pack_ubo(scene).view(np.uint32))
+        assert L.pt_kernel_compile_check(ubo.ctypes.data_as(C.c_void_p), api._c_strings([]), 0, 1, 0) == 0, L.pt_last_error(None)
+    bad = pack.pack_ubo(base)
+    bad[0] = 400.0   # a hand-made block claiming more spheres than objects[] holds
+    assert L.pt_kernel_compile_check(bad.ctypes.data_as(C.c_void_p), api._c_strings([]), 0, 1, 0) == -1
