@@ -1355,6 +1355,180 @@ __device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const Pt
     if (inRange) StoreTexel(pr, image, gx, gy, outColor);
 }
 
+#if PT_HAS_SDF
+/* ---- driver v2p: v2 + a march pool shared by the warps of a CTA --------------------------------------------------
+ * In v2 only the lanes of ONE warp that happen to be marching populate the SDF phase (ncu: 7 of 32 on the
+ * mandelbulb scene).  Here a lane whose ray entered an SDF box publishes the march as a job in shared memory
+ * (origin, direction, SphereTracing's locals: 24 words) and waits; whenever a warp runs the SDF phase, ALL its
+ * lanes -- whatever their own state -- claim pending jobs of ANY thread of the CTA (128-bit pending mask, claims by
+ * atomicAnd), advance them PT_SDF_REPS evaluations with the same PhaseSdfEval, and put them back or mark them done.
+ * The per-job arithmetic does not depend on who executes it, so strict mode stays bit-exact. */
+enum { PT_ST_WAIT = 5 };
+enum { PJ_OX = 0, PJ_OY, PJ_OZ, PJ_DX, PJ_DY, PJ_DZ, PJ_SHADOW, PJ_HT, PJ_MT, PJ_INST, PJ_OMEGA, PJ_PREV, PJ_TMAX, PJ_KSIGN,
+       PJ_PROBE, PJ_N0, PJ_N1, PJ_N2, PJ_POINTS, PJ_ITER, PJ_SUB, PJ_SET1, PJ_OBJ, PJ_MAT, PJ_DONE, PJ_FIELDS };
+#ifndef PT_POOL_MIN
+#define PT_POOL_MIN 24
+#endif
+
+__device__ __forceinline__ void pt_render_body_v2p(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
+                                                   float4* __restrict__ image, float* s_tab, float* s_job, unsigned* s_mask) {
+    for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
+    if (threadIdx.x < 4) s_mask[threadIdx.x] = 0u;
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int gy = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const bool inRange = (gx < pr.width) && (gy < pr.height);
+    const int tid = threadIdx.x;
+
+    Ctx c;
+    c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
+
+    const unsigned xyx = (unsigned)gx;
+    const unsigned xyy = (unsigned)pr.height - (unsigned)gy; /* shader.comp:1510 */
+    const int spf = pr.samplesPerFrame;
+
+    int st = (inRange && spf > 0) ? PT_ST_NEW : PT_ST_DONE;
+    int k = 0;
+    V3 outColor = mk3(0.0f, 0.0f, 0.0f);
+    PathState ps;
+    PathStateInit(ps);
+    volatile float* job = s_job;
+    volatile unsigned* vmask = s_mask;
+#define PJ(f, t) job[(f) * PT_BLOCK_THREADS + (t)]
+
+    for (;;) {
+        /* a finished job: take the hit back */
+        if (st == PT_ST_WAIT && PJ(PJ_DONE, tid) != 0.0f) {
+            ps.h.t = PJ(PJ_HT, tid);
+            ps.h.objectID = __float_as_int(PJ(PJ_OBJ, tid));
+            if (__float_as_int(PJ(PJ_SUB, tid)) == PT_SUB_N0 + 6) { /* a path ray hit the SDF: normal and material came with it */
+                ps.h.normal = mk3(PJ(PJ_N0, tid), PJ(PJ_N1, tid), PJ(PJ_N2, tid));
+                ps.h.materialID = PJ(PJ_MAT, tid);
+                ps.h.lightID = -1.0f;
+            }
+            st = PT_ST_SHADE;
+        }
+        const unsigned bNew = __ballot_sync(0xffffffffu, st == PT_ST_NEW);
+        const unsigned bIs = __ballot_sync(0xffffffffu, st == PT_ST_ISECT);
+        const unsigned bSh = __ballot_sync(0xffffffffu, st == PT_ST_SHADE);
+        const unsigned bWait = __ballot_sync(0xffffffffu, st == PT_ST_WAIT);
+        if ((bNew | bIs | bSh | bWait) == 0u) break;
+        /* one snapshot of the pending mask for the whole warp (lane 0's), so ranks and the vote are consistent */
+        const unsigned m0 = __shfl_sync(0xffffffffu, vmask[0], 0), m1 = __shfl_sync(0xffffffffu, vmask[1], 0),
+                       m2 = __shfl_sync(0xffffffffu, vmask[2], 0), m3 = __shfl_sync(0xffffffffu, vmask[3], 0);
+        const int pending = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+        int phase = PT_ST_NEW, best = __popc(bNew);
+        if (__popc(bIs) >= best) { best = __popc(bIs); phase = PT_ST_ISECT; }
+        if (__popc(bSh) >= best) { best = __popc(bSh); phase = PT_ST_SHADE; }
+        /* march when a (nearly) full warp's worth of jobs is waiting in the CTA, or when this warp's feeders are thin */
+        if (pending > 0 && (pending >= PT_POOL_MIN || best < PT_FEED_T)) phase = PT_ST_SDF;
+        if (best == 0 && phase != PT_ST_SDF) { /* everyone here waits on jobs other warps are running */
+            __nanosleep(200);
+            continue;
+        }
+        PT_STAT(phase, phase == PT_ST_NEW ? bNew : (phase == PT_ST_ISECT ? bIs : (phase == PT_ST_SDF ? 0u : bSh)));
+        if (phase == PT_ST_NEW) {
+            if (st == PT_ST_NEW) {
+                if (ps.pendingFinish) {
+                    outColor = outColor + PathColor(c, ps);
+                    ps.pendingFinish = false;
+                }
+                if (k < spf) {
+                    st = PhaseNew(c, ps, xyx, xyy, k);
+                    k++;
+                } else {
+                    st = PT_ST_DONE;
+                }
+            }
+        } else if (phase == PT_ST_ISECT) {
+            if (st == PT_ST_ISECT) {
+                MarchState ms;
+                st = PhaseIsect(c, ps, ms);
+                if (st == PT_ST_SDF) { /* publish the march as a job of the CTA's pool */
+                    const V3 d = ps.isShadow ? ps.shDir : ps.ray.dir;
+                    PJ(PJ_OX, tid) = ps.ray.origin.x; PJ(PJ_OY, tid) = ps.ray.origin.y; PJ(PJ_OZ, tid) = ps.ray.origin.z;
+                    PJ(PJ_DX, tid) = d.x; PJ(PJ_DY, tid) = d.y; PJ(PJ_DZ, tid) = d.z;
+                    PJ(PJ_SHADOW, tid) = ps.isShadow ? 1.0f : 0.0f;
+                    PJ(PJ_HT, tid) = ps.h.t;
+                    PJ(PJ_OBJ, tid) = __int_as_float(ps.h.objectID);
+                    PJ(PJ_MT, tid) = ms.mt; PJ(PJ_INST, tid) = ms.insT; PJ(PJ_OMEGA, tid) = ms.omega;
+                    PJ(PJ_PREV, tid) = ms.previousRadius; PJ(PJ_TMAX, tid) = ms.tMax; PJ(PJ_KSIGN, tid) = 0.0f;
+                    PJ(PJ_PROBE, tid) = 0.0f; PJ(PJ_N0, tid) = 0.0f; PJ(PJ_N1, tid) = 0.0f; PJ(PJ_N2, tid) = 0.0f;
+                    PJ(PJ_POINTS, tid) = __int_as_float(ms.points); PJ(PJ_ITER, tid) = __int_as_float(ms.iter);
+                    PJ(PJ_SUB, tid) = __int_as_float(ms.sub); PJ(PJ_SET1, tid) = __uint_as_float(ms.set1);
+                    PJ(PJ_DONE, tid) = 0.0f;
+                    __threadfence_block();
+                    atomicOr(&s_mask[warp], 1u << lane);
+                    st = PT_ST_WAIT;
+                }
+            }
+        } else if (phase == PT_ST_SDF) {
+            /* lane L takes the L-th pending job of the CTA (if it wins the atomicAnd against the other warps) */
+            int j = -1;
+            {
+                int r = lane;
+                const unsigned mm[4] = {m0, m1, m2, m3};
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const int n = __popc(mm[w]);
+                    if (j < 0 && r < n) j = w * 32 + (int)__fns(mm[w], 0u, r + 1);
+                    r -= n;
+                }
+            }
+            if (j >= 0) {
+                const unsigned bit = 1u << (j & 31);
+                if ((atomicAnd(&s_mask[j >> 5], ~bit) & bit) == 0u) j = -1; /* another warp got it */
+            }
+            if (j >= 0) {
+                __threadfence_block();
+                PathState js;
+                MarchState ms;
+                js.ray.origin = mk3(PJ(PJ_OX, j), PJ(PJ_OY, j), PJ(PJ_OZ, j));
+                js.ray.dir = mk3(PJ(PJ_DX, j), PJ(PJ_DY, j), PJ(PJ_DZ, j));
+                js.shDir = js.ray.dir;
+                js.isShadow = PJ(PJ_SHADOW, j) != 0.0f;
+                js.h.t = PJ(PJ_HT, j);
+                js.h.objectID = __float_as_int(PJ(PJ_OBJ, j));
+                js.h.normal = mk3(0.0f, 0.0f, 0.0f); js.h.materialID = 0.0f; js.h.lightID = -1.0f;
+                ms.mt = PJ(PJ_MT, j); ms.insT = PJ(PJ_INST, j); ms.omega = PJ(PJ_OMEGA, j); ms.previousRadius = PJ(PJ_PREV, j);
+                ms.tMax = PJ(PJ_TMAX, j); ms.ksign = PJ(PJ_KSIGN, j); ms.probe = PJ(PJ_PROBE, j);
+                ms.nrm0 = PJ(PJ_N0, j); ms.nrm1 = PJ(PJ_N1, j); ms.nrm2 = PJ(PJ_N2, j);
+                ms.points = __float_as_int(PJ(PJ_POINTS, j)); ms.iter = __float_as_int(PJ(PJ_ITER, j));
+                ms.sub = __float_as_int(PJ(PJ_SUB, j)); ms.set1 = __float_as_uint(PJ(PJ_SET1, j));
+                int jst = PT_ST_SDF;
+#pragma unroll 1
+                for (int rep = 0; rep < PT_SDF_REPS && jst == PT_ST_SDF; rep++) jst = PhaseSdfEval(c, js, ms);
+                PJ(PJ_HT, j) = js.h.t;
+                PJ(PJ_OBJ, j) = __int_as_float(js.h.objectID);
+                PJ(PJ_SUB, j) = __int_as_float(ms.sub);
+                if (jst == PT_ST_SDF) {
+                    PJ(PJ_MT, j) = ms.mt; PJ(PJ_INST, j) = ms.insT; PJ(PJ_OMEGA, j) = ms.omega; PJ(PJ_PREV, j) = ms.previousRadius;
+                    PJ(PJ_TMAX, j) = ms.tMax; PJ(PJ_KSIGN, j) = ms.ksign; PJ(PJ_PROBE, j) = ms.probe;
+                    PJ(PJ_N0, j) = ms.nrm0; PJ(PJ_N1, j) = ms.nrm1; PJ(PJ_N2, j) = ms.nrm2;
+                    PJ(PJ_POINTS, j) = __int_as_float(ms.points); PJ(PJ_ITER, j) = __int_as_float(ms.iter);
+                    PJ(PJ_SET1, j) = __uint_as_float(ms.set1);
+                    __threadfence_block();
+                    atomicOr(&s_mask[j >> 5], 1u << (j & 31));
+                } else {
+                    if (ms.sub == PT_SUB_N0 + 6) {
+                        PJ(PJ_N0, j) = js.h.normal.x; PJ(PJ_N1, j) = js.h.normal.y; PJ(PJ_N2, j) = js.h.normal.z;
+                        PJ(PJ_MAT, j) = js.h.materialID;
+                    }
+                    __threadfence_block();
+                    PJ(PJ_DONE, j) = 1.0f;
+                }
+            }
+        } else {
+            if (st == PT_ST_SHADE) st = PhaseShade(c, ps);
+        }
+    }
+#undef PJ
+    if (inRange) StoreTexel(pr, image, gx, gy, outColor);
+}
+#endif /* PT_HAS_SDF */
+
 #ifndef PT_SCHED
 #define PT_SCHED 1
 #endif
@@ -1369,7 +1543,18 @@ __device__ __forceinline__ void pt_render_body(const PtDevScene& sc, const PtDev
 
 } /* namespace PT_KERNEL_NS */
 
-/* the kernel entry point; PT_KERNEL_NAME distinguishes the strict / fast / JIT instances */
+/* the kernel entry point; the name distinguishes the strict / fast / JIT instances */
+#if PT_HAS_SDF && PT_SCHED == 2
+#define PT_DEFINE_RENDER_KERNEL(name)                                                                        \
+    extern "C" __global__ void __launch_bounds__(PT_BLOCK_THREADS, PT_MIN_BLOCKS)                            \
+    name(const __grid_constant__ PtDevScene sc, const __grid_constant__ PtDevParams pr,                      \
+         const float* __restrict__ ubo, float4* __restrict__ image) {                                        \
+        __shared__ float s_tab[PT_SH_FLOATS];                                                                \
+        __shared__ float s_job[PT_KERNEL_NS::PJ_FIELDS * PT_BLOCK_THREADS];                                  \
+        __shared__ unsigned s_mask[4];                                                                       \
+        PT_KERNEL_NS::pt_render_body_v2p(sc, pr, ubo, image, s_tab, s_job, s_mask);                          \
+    }
+#else
 #define PT_DEFINE_RENDER_KERNEL(name)                                                                        \
     extern "C" __global__ void __launch_bounds__(PT_BLOCK_THREADS, PT_MIN_BLOCKS)                            \
     name(const __grid_constant__ PtDevScene sc, const __grid_constant__ PtDevParams pr,                      \
@@ -1377,6 +1562,7 @@ __device__ __forceinline__ void pt_render_body(const PtDevScene& sc, const PtDev
         __shared__ float s_tab[PT_SH_FLOATS];                                                                \
         PT_KERNEL_NS::pt_render_body(sc, pr, ubo, image, s_tab);                                             \
     }
+#endif
 
 
 #if PT_HAS_SDF
