@@ -5,7 +5,7 @@
  * the same parameters as flags and drives the library through the C ABI only (include/pt_abi.h).
  *
  *   pt_render --scene scenes/scene0.json --width 512 --height 512 --spp 64 --spf 8 --path-length 5 --shot 1 \
- *             [--fast] [--wavefront] [--jit 0|1|2] [--device 0] [--out render.pfm|render.ppm] [--tonemap 3]
+ *             [--fast] [--wavefront] [--jit 0|1|2] [--device 0] [--out render.pfm|render.exr|render.ppm] [--tonemap 3]
  *             [--resume checkpoint.pfm --done-samples N]      continue a run saved with --out checkpoint.pfm
  */
 #include <stdio.h>
@@ -91,8 +91,10 @@ int main(int argc, char** argv) {
         std::vector<float> img((size_t)width * height * 4);
         if (pt_read_xyz(ctx, img.data(), img.size()) != PT_OK) return die("read back", ctx);
         const bool ppm = out_path.size() > 4 && out_path.substr(out_path.size() - 4) == ".ppm";
+        const bool exr = out_path.size() > 4 && out_path.substr(out_path.size() - 4) == ".exr";
         int rc = ppm ? pt_write_ppm(out_path.c_str(), img.data(), width, height, tonemap)
-                     : pt_write_pfm(out_path.c_str(), img.data(), width, height, 0);
+                     : (exr ? pt_write_exr(out_path.c_str(), img.data(), width, height, 1)
+                            : pt_write_pfm(out_path.c_str(), img.data(), width, height, 0));
         if (rc != PT_OK) { fprintf(stderr, "pt_render: cannot write %s\n", out_path.c_str()); return 1; }
     }
     pt_destroy(ctx);

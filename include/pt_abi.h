@@ -168,6 +168,8 @@ int pt_render_resume(pt_ctx* ctx, const pt_params* base, int done_samples, int t
 int pt_write_ppm(const char* path, const float* rgba, int width, int height, int tonemap);
 int pt_write_pfm(const char* path, const float* rgba, int width, int height, int to_rgb);
 int pt_read_pfm(const char* path, float* rgba, int width, int height); /* reads a to_rgb = 0 file back (w = 1) */
+/* OpenEXR (single-part scanline, uncompressed, 3 x FLOAT): channels R,G,B (linear sRGB) or X,Y,Z (to_rgb == 0) */
+int pt_write_exr(const char* path, const float* rgba, int width, int height, int to_rgb);
 
 /* ---- introspection used by the tests --------------------------------------------------------------------- */
 const float* pt_cie1931_table(void); /* 1323 floats */

@@ -106,6 +106,7 @@ def lib():
         L.pt_scene_pack_params.argtypes = [vp, ci, ci, ci, ci, ci, vp]
         L.pt_write_ppm.argtypes = [C.c_char_p, vp, ci, ci, ci]
         L.pt_write_pfm.argtypes = [C.c_char_p, vp, ci, ci, ci]
+        L.pt_write_exr.argtypes = [C.c_char_p, vp, ci, ci, ci]
         L.pt_cie1931_table.restype = C.POINTER(cf)
         L.pt_sdf_translate.argtypes = [C.POINTER(C.c_char_p), ci, vp, C.c_char_p, C.c_size_t]
         L.pt_sdf_translate.restype = C.c_long

@@ -7,7 +7,9 @@
  * This is post-processing, outside the parity-gated kernel: it uses libm.
  */
 #include <math.h>
+#include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <string>
 #include <vector>
@@ -78,6 +80,72 @@ int pt_write_pfm(const char* path, const float* rgba, int width, int height, int
             else { row[3 * (size_t)x] = t[0]; row[3 * (size_t)x + 1] = t[1]; row[3 * (size_t)x + 2] = t[2]; }
         }
         ok = fwrite(row.data(), sizeof(float), row.size(), fp) == row.size();
+    }
+    if (fclose(fp) != 0) ok = false;
+    return ok ? PT_OK : PT_ERR_IO;
+}
+
+/* OpenEXR 2 single-part scanline file, NO_COMPRESSION, three FLOAT channels: R,G,B (linear sRGB through the
+ * reference's Bradford + XYZ->sRGB matrices) when to_rgb != 0, else X,Y,Z (the raw accumulation buffer).
+ * Row 0 of the buffer is the top scanline = EXR's y = 0 (INCREASING_Y).  Written without any library: header
+ * attributes, one offset per scanline, then per scanline {y, byte count, channel rows in alphabetical order}. */
+int pt_write_exr(const char* path, const float* rgba, int width, int height, int to_rgb) {
+    if (!path || !rgba || width <= 0 || height <= 0) return PT_ERR_ARG;
+    std::string h;
+    auto put32 = [&](std::string& o, uint32_t v) { for (int i = 0; i < 4; i++) o.push_back((char)((v >> (8 * i)) & 0xff)); };
+    auto putf = [&](std::string& o, float f) { uint32_t u; memcpy(&u, &f, 4); put32(o, u); };
+    auto attr = [&](const char* name, const char* type, const std::string& value) {
+        h += name; h.push_back('\0'); h += type; h.push_back('\0');
+        put32(h, (uint32_t)value.size());
+        h += value;
+    };
+    put32(h, 20000630u); /* magic */
+    put32(h, 2u);        /* version 2, single-part scanline, no long names */
+    const char* names = to_rgb ? "BGR" : "XYZ"; /* alphabetical */
+    std::string ch;
+    for (int c = 0; c < 3; c++) {
+        ch.push_back(names[c]); ch.push_back('\0');
+        put32(ch, 2u);                      /* FLOAT */
+        ch.push_back(0); ch.push_back(0); ch.push_back(0); ch.push_back(0); /* pLinear + reserved */
+        put32(ch, 1u); put32(ch, 1u);       /* x/y sampling */
+    }
+    ch.push_back('\0');
+    attr("channels", "chlist", ch);
+    attr("compression", "compression", std::string(1, '\0'));
+    std::string win;
+    put32(win, 0u); put32(win, 0u); put32(win, (uint32_t)(width - 1)); put32(win, (uint32_t)(height - 1));
+    attr("dataWindow", "box2i", win);
+    attr("displayWindow", "box2i", win);
+    attr("lineOrder", "lineOrder", std::string(1, '\0'));
+    std::string one; putf(one, 1.0f);
+    attr("pixelAspectRatio", "float", one);
+    std::string c2; putf(c2, 0.0f); putf(c2, 0.0f);
+    attr("screenWindowCenter", "v2f", c2);
+    attr("screenWindowWidth", "float", one);
+    h.push_back('\0');
+    const uint64_t row_bytes = (uint64_t)width * 3 * 4, block = 8 + row_bytes;
+    const uint64_t first = h.size() + (uint64_t)height * 8;
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return PT_ERR_IO;
+    bool ok = fwrite(h.data(), 1, h.size(), fp) == h.size();
+    for (int y = 0; y < height && ok; y++) {
+        const uint64_t off = first + (uint64_t)y * block;
+        unsigned char b[8];
+        for (int i = 0; i < 8; i++) b[i] = (unsigned char)((off >> (8 * i)) & 0xff);
+        ok = fwrite(b, 1, 8, fp) == 8;
+    }
+    std::vector<float> row((size_t)width * 3);
+    for (int y = 0; y < height && ok; y++) {
+        std::string hd;
+        put32(hd, (uint32_t)y); put32(hd, (uint32_t)row_bytes);
+        ok = fwrite(hd.data(), 1, 8, fp) == 8;
+        for (int x = 0; x < width; x++) {
+            const float* t = rgba + 4 * ((size_t)x + (size_t)width * (size_t)y);
+            float v[3] = {t[0], t[1], t[2]};
+            if (to_rgb) { xyz_to_linear_srgb(t, v); const float r = v[0]; v[0] = v[2]; v[2] = r; } /* B, G, R */
+            row[(size_t)x] = v[0]; row[(size_t)width + x] = v[1]; row[2 * (size_t)width + x] = v[2];
+        }
+        ok = ok && fwrite(row.data(), 4, row.size(), fp) == row.size();
     }
     if (fclose(fp) != 0) ok = false;
     return ok ? PT_OK : PT_ERR_IO;
