@@ -108,6 +108,18 @@ class ClockSampler:
         return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def ncu_traffic(wl):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the workload's kernel, from the committed
+    `ncu --set full` capture of the same bench command (profiles/r01_final/ncu_summary_*.json); None if not captured."""
+    path = os.path.join(ROOT, 'profiles', 'r01_final', 'ncu_summary_%s.json' % wl.split('_')[0])
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return d['traffic_bytes_per_launch'] if d.get('workload') == wl else None
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def oracle_for(scene_name, count=False, threads=0):
     from oracle import oracle, pack
     scene = pack.load_scene(os.path.join(ROOT, 'scenes', scene_name + '.json'))
@@ -347,7 +359,7 @@ def main():
         achieved = kernel_rate * F / 1e12
         line['roofline'] = {
             'bound': 'fp32', 'achieved': achieved, 'peak': peak_max, 'unit': 'TFLOP/s', 'frac': achieved / peak_max,
-            'traffic': None, 'kernel': 'pt_render_jit' if args.jit == 2 or sc.sdf_sources else 'pt_render_' + args.mode,
+            'traffic': ncu_traffic(wl), 'kernel': 'pt_render_jit' if args.jit == 2 or sc.sdf_sources else 'pt_render_' + args.mode,
             'flops_per_sample_algorithmic': F, 'flops_counting_rule': 'SURVEY.md App. D v1 (source-level, as written in shader.comp)',
             'peak_basis': '148 SM x 128 FP32 lanes x 2 x %s sm_max_mhz (%s); FP32-issue roofline per SURVEY.md section 8d' % (
                 peaks.get('sm_max_mhz', 1965.0), peak_kind),
