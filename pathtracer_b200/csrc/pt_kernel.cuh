@@ -1258,6 +1258,25 @@ PT_DEV int PhaseShade(const Ctx& c, PathState& ps) {
     return next;
 }
 
+/* The two outcomes of a traced ray that need no shading work -- the verdict of a shadow ray and a path ray that left
+ * the scene -- exactly as PhaseShade handles them (shader.comp:1218-1222,1328-1334 and 1387-1389).  The in-warp
+ * drivers apply this right after the intersection / march phases, so the SHADE phase only ever runs real shading.
+ * Returns the next phase, or SHADE when the hit needs shading. */
+PT_DEV int PhaseTrivial(PathState& ps) {
+    if (ps.isShadow) {
+        if (ps.h.objectID == ps.shObj) ps.radiance = ps.radiance + ps.shContrib;
+        ps.isShadow = false;
+        if (ps.pathAlive) return PT_ST_ISECT;
+        ps.pendingFinish = true;
+        return PT_ST_NEW;
+    }
+    if (!(ps.h.t < 1e5f)) {
+        ps.pendingFinish = true;
+        return PT_ST_NEW;
+    }
+    return PT_ST_SHADE;
+}
+
 /* ---- driver v2: in-warp scheduled state machine, all state in registers ------------------------------------------
  * Every lane runs the phases above for its own pixel; per iteration the warp executes ONE phase, chosen by ballot.
  * A lane that finishes a path refills itself with its pixel's next sample index instead of idling, so the
@@ -1338,7 +1357,10 @@ __device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const Pt
                 }
             }
         } else if (phase == PT_ST_ISECT) {
-            if (st == PT_ST_ISECT) st = PhaseIsect(c, ps, ms);
+            if (st == PT_ST_ISECT) {
+                st = PhaseIsect(c, ps, ms);
+                if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
+            }
         }
 #if PT_HAS_SDF
         else if (phase == PT_ST_SDF) {
@@ -1346,6 +1368,7 @@ __device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const Pt
             for (int rep = 0; rep < PT_SDF_REPS; rep++) {
                 if (st == PT_ST_SDF) st = PhaseSdfEval(c, ps, ms);
             }
+            if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
         }
 #endif
         else {
@@ -1408,7 +1431,7 @@ __device__ __forceinline__ void pt_render_body_v2p(const PtDevScene& sc, const P
                 ps.h.materialID = PJ(PJ_MAT, tid);
                 ps.h.lightID = -1.0f;
             }
-            st = PT_ST_SHADE;
+            st = PhaseTrivial(ps);
         }
         const unsigned bNew = __ballot_sync(0xffffffffu, st == PT_ST_NEW);
         const unsigned bIs = __ballot_sync(0xffffffffu, st == PT_ST_ISECT);
@@ -1462,6 +1485,8 @@ __device__ __forceinline__ void pt_render_body_v2p(const PtDevScene& sc, const P
                     __threadfence_block();
                     atomicOr(&s_mask[warp], 1u << lane);
                     st = PT_ST_WAIT;
+                } else {
+                    st = PhaseTrivial(ps);
                 }
             }
         } else if (phase == PT_ST_SDF) {
