@@ -1082,73 +1082,90 @@ PT_DEV int PhaseIsect(const Ctx& c, PathState& ps, MarchState& ms) {
 }
 
 #if PT_HAS_SDF
-/* SDF: one SDF() evaluation and the bookkeeping around it.  Returns SDF (more to do) or SHADE. */
-PT_DEV int PhaseSdfEval(const Ctx& c, PathState& ps, MarchState& ms) {
-    const V3 dir = ps.isShadow ? ps.shDir : ps.ray.dir;
-    const V3 origin = ps.ray.origin;
-    V3 pe = origin;
-    if (ms.sub != PT_SUB_SIGN) {
-        pe = fma3(dir, ms.mt, origin);
-        if (ms.sub >= PT_SUB_N0) { /* CalculateNumericalSDFNormals, shader.comp:721-730: p +- h.xyy etc. */
-            const int j = ms.sub - PT_SUB_N0, axis = j >> 1;
-            const float ex = (axis == 0) ? 1e-4f : 0.0f, ey = (axis == 1) ? 1e-4f : 0.0f, ez = (axis == 2) ? 1e-4f : 0.0f;
-            pe = (j & 1) ? mk3(pe.x - ex, pe.y - ey, pe.z - ez) : mk3(pe.x + ex, pe.y + ey, pe.z + ez);
-        }
-    }
-    const float d = SDF(pe, ms.set1); /* the one SDF() site of the kernel */
-    if (ms.sub == PT_SUB_SIGN) { /* shader.comp:801 */
+/* The SDF phase in three pieces, so a driver can decide WHO evaluates the distance function at WHICH point:
+ * SdfMarchPoint (where the march wants its next evaluation), SdfProbePoint (the j-th of the six normal probes around
+ * p: +x -x +y -y +z -z, CalculateNumericalSDFNormals shader.comp:721-730) and SdfMarchConsume (SphereTracing's
+ * bookkeeping for one evaluated distance, shader.comp:801-858). */
+PT_DEV V3 SdfMarchPoint(const PathState& ps, const MarchState& ms) {
+    if (ms.sub == PT_SUB_SIGN) return ps.ray.origin; /* k = sign(SDF(ray.origin)), shader.comp:801 */
+    return fma3(ps.isShadow ? ps.shDir : ps.ray.dir, ms.mt, ps.ray.origin);
+}
+PT_DEV V3 SdfProbePoint(V3 p, int j) {
+    const int axis = j >> 1;
+    const float ex = (axis == 0) ? 1e-4f : 0.0f, ey = (axis == 1) ? 1e-4f : 0.0f, ez = (axis == 2) ? 1e-4f : 0.0f;
+    return (j & 1) ? mk3(p.x - ex, p.y - ey, p.z - ez) : mk3(p.x + ex, p.y + ey, p.z + ez);
+}
+/* One evaluated distance d for a march in sub-state SIGN or STEP.  Returns SDF (more to do; ms.sub == PT_SUB_N0
+ * means "converged on a path ray: the six normal probes are next") or SHADE. */
+PT_DEV int SdfMarchConsume(const Ctx& c, PathState& ps, MarchState& ms, float d) {
+    if (ms.sub == PT_SUB_SIGN) {
         ms.ksign = gsign(d);
         ms.sub = PT_SUB_STEP;
         return PT_ST_SDF;
     }
-    if (ms.sub == PT_SUB_STEP) { /* one iteration of the loop at shader.comp:803-849 */
-        const float radius = d;
-        bool finished = false, nohit = false;
-        if (ms.insT > (fabsf(ms.previousRadius) + fabsf(radius))) {
-            ms.mt -= ms.insT;
-            ms.omega = 1.0f;
-            ms.insT = ms.previousRadius * ms.omega * ms.ksign;
-            ms.mt += ms.insT;
-        } else if (fabsf(radius) < 1e-4f) {
-            finished = true;
-        } else {
-            if (ms.mt > ms.tMax) ms.points += 1; else ms.points = 0;
-            if (ms.points >= 2) {
-                ms.mt = ms.tMax + 1e-3f;
-                float tMin = 1e5f;
-                ms.tMax = 1e5f;
-                const V3 invdir = mk3(PTK_DIV(1.0f, dir.x), PTK_DIV(1.0f, dir.y), PTK_DIV(1.0f, dir.z));
-                if (SearchSDF(c, fma3(dir, ms.mt, origin), invdir, tMin, ms.tMax, ms.set1)) {
-                    tMin += ms.mt; ms.tMax += ms.mt;
-                    ms.mt = PTK_MAX(tMin, ms.mt);
-                } else {
-                    nohit = true;
-                }
+    /* one iteration of the loop at shader.comp:803-849 */
+    const V3 dir = ps.isShadow ? ps.shDir : ps.ray.dir;
+    const float radius = d;
+    bool finished = false, nohit = false;
+    if (ms.insT > (fabsf(ms.previousRadius) + fabsf(radius))) {
+        ms.mt -= ms.insT;
+        ms.omega = 1.0f;
+        ms.insT = ms.previousRadius * ms.omega * ms.ksign;
+        ms.mt += ms.insT;
+    } else if (fabsf(radius) < 1e-4f) {
+        finished = true;
+    } else {
+        if (ms.mt > ms.tMax) ms.points += 1; else ms.points = 0;
+        if (ms.points >= 2) {
+            ms.mt = ms.tMax + 1e-3f;
+            float tMin = 1e5f;
+            ms.tMax = 1e5f;
+            const V3 invdir = mk3(PTK_DIV(1.0f, dir.x), PTK_DIV(1.0f, dir.y), PTK_DIV(1.0f, dir.z));
+            if (SearchSDF(c, fma3(dir, ms.mt, ps.ray.origin), invdir, tMin, ms.tMax, ms.set1)) {
+                tMin += ms.mt; ms.tMax += ms.mt;
+                ms.mt = PTK_MAX(tMin, ms.mt);
             } else {
-                ms.insT = radius * ms.omega * ms.ksign;
-                ms.mt += ms.insT;
-                const float omegaSpeedFactor = PTK_MIN(PTK_DIV(radius, ms.previousRadius), 0.99f);
-                ms.omega += 0.20f * (PTK_MIN(PTK_DIV(1.0f, 1.0f - omegaSpeedFactor), 1.70f) - ms.omega);
-                ms.previousRadius = radius;
+                nohit = true;
             }
+        } else {
+            ms.insT = radius * ms.omega * ms.ksign;
+            ms.mt += ms.insT;
+            const float omegaSpeedFactor = PTK_MIN(PTK_DIV(radius, ms.previousRadius), 0.99f);
+            ms.omega += 0.20f * (PTK_MIN(PTK_DIV(1.0f, 1.0f - omegaSpeedFactor), 1.70f) - ms.omega);
+            ms.previousRadius = radius;
         }
-        if (!finished && !nohit) {
-            ms.iter++;
-            if (ms.iter >= 512) finished = true; /* falls through to "hit" unconverged: SURVEY App. C-9 */
-        }
-        if (nohit) return PT_ST_SHADE;
-        if (finished) { /* shader.comp:851-858 */
-            if (ms.mt < ps.h.t) {
-                ps.h.t = ms.mt - 1e-3f;
-                ps.h.objectID = -1;
-                if (ps.isShadow) return PT_ST_SHADE;
-                ms.sub = PT_SUB_N0;
-                return PT_ST_SDF;
-            }
-            return PT_ST_SHADE;
-        }
-        return PT_ST_SDF;
     }
+    if (!finished && !nohit) {
+        ms.iter++;
+        if (ms.iter >= 512) finished = true; /* falls through to "hit" unconverged: SURVEY App. C-9 */
+    }
+    if (nohit) return PT_ST_SHADE;
+    if (finished) { /* shader.comp:851-858 */
+        if (ms.mt < ps.h.t) {
+            ps.h.t = ms.mt - 1e-3f;
+            ps.h.objectID = -1;
+            if (ps.isShadow) return PT_ST_SHADE;
+            ms.sub = PT_SUB_N0;
+            return PT_ST_SDF;
+        }
+        return PT_ST_SHADE;
+    }
+    return PT_ST_SDF;
+}
+/* The hit of a converged path ray from its six probe values (shader.comp:853-857) */
+PT_DEV void SdfFinishHit(PathState& ps, const MarchState& ms, float e0, float e1, float e2, float e3, float e4, float e5) {
+    const V3 p = fma3(ps.ray.dir, ms.mt, ps.ray.origin);
+    ps.h.normal = normalize(mk3(e0 - e1, e2 - e3, e4 - e5));
+    ps.h.materialID = ::pt_sdfmaterial_dispatch(p.x, p.y, p.z, ms.set1);
+    ps.h.lightID = -1.0f;
+}
+
+/* SDF, one lane on its own: one SDF() evaluation and the bookkeeping around it.  Returns SDF (more to do) or SHADE. */
+PT_DEV int PhaseSdfEval(const Ctx& c, PathState& ps, MarchState& ms) {
+    const V3 pm = SdfMarchPoint(ps, ms);
+    const V3 pe = (ms.sub >= PT_SUB_N0) ? SdfProbePoint(pm, ms.sub - PT_SUB_N0) : pm;
+    const float d = SDF(pe, ms.set1); /* the one SDF() site of the kernel */
+    if (ms.sub < PT_SUB_N0) return SdfMarchConsume(c, ps, ms, d);
     const int j = ms.sub - PT_SUB_N0;
     if ((j & 1) == 0) {
         ms.probe = d;
@@ -1158,13 +1175,69 @@ PT_DEV int PhaseSdfEval(const Ctx& c, PathState& ps, MarchState& ms) {
     }
     ms.sub++;
     if (j == 5) {
-        const V3 p = fma3(dir, ms.mt, origin);
+        const V3 p = fma3(ps.ray.dir, ms.mt, ps.ray.origin);
         ps.h.normal = normalize(mk3(ms.nrm0, ms.nrm1, ms.nrm2));
         ps.h.materialID = ::pt_sdfmaterial_dispatch(p.x, p.y, p.z, ms.set1);
         ps.h.lightID = -1.0f;
         return PT_ST_SHADE;
     }
     return PT_ST_SDF;
+}
+
+/* SDF, the whole warp at once (v2 driver): per round every lane evaluates SDF() at most once -- marching lanes at
+ * their own next point, and, when some lanes have converged on a path ray, lanes 0..6m-1 at the six normal probes
+ * of the first m <= 5 of them (a marching lane drafted as a prober just advances one round later).  A converged
+ * ray's normal thus costs one round with six lanes busy instead of six rounds with one, and runs concurrently with
+ * the other lanes' marching.  Same evaluations, same arithmetic: bit-exact. */
+PT_DEV int PhaseSdfWarp(const Ctx& c, PathState& ps, MarchState& ms, int st, int rounds) {
+    const unsigned lane = threadIdx.x & 31u;
+#pragma unroll 1
+    for (int rep = 0; rep < rounds; rep++) {
+        const bool inSdf = (st == PT_ST_SDF);
+        const bool needN = inSdf && (ms.sub == PT_SUB_N0);
+        const unsigned needMask = __ballot_sync(0xffffffffu, needN);
+        if (__ballot_sync(0xffffffffu, inSdf) == 0u) break;
+        const int m = min(__popc(needMask), 5);
+        const bool prober = (int)lane < 6 * m;
+        V3 pe = ps.ray.origin;
+        unsigned set = ms.set1;
+        bool doEval = false;
+        if (m > 0) { /* warp-uniform */
+            const V3 ph = fma3(ps.ray.dir, ms.mt, ps.ray.origin); /* meaningful on the converged lanes */
+            const int slot = (int)lane / 6, probe = (int)lane - 6 * slot;
+            const int src = prober ? (int)__fns(needMask, 0u, slot + 1) : 0;
+            const float qx = __shfl_sync(0xffffffffu, ph.x, src), qy = __shfl_sync(0xffffffffu, ph.y, src),
+                        qz = __shfl_sync(0xffffffffu, ph.z, src);
+            const unsigned qs = __shfl_sync(0xffffffffu, ms.set1, src);
+            if (prober) {
+                pe = SdfProbePoint(mk3(qx, qy, qz), probe);
+                set = qs;
+                doEval = true;
+            }
+        }
+        const bool marching = inSdf && (ms.sub < PT_SUB_N0) && !prober;
+        if (marching) {
+            pe = SdfMarchPoint(ps, ms);
+            set = ms.set1;
+            doEval = true;
+        }
+        float d = 0.0f;
+        if (doEval) d = SDF(pe, set); /* the one SDF() site of the kernel */
+        if (marching) st = SdfMarchConsume(c, ps, ms, d);
+        if (m > 0) {
+            const int nr = __popc(needMask & ((1u << lane) - 1u));
+            const bool served = needN && (nr < m);
+            const int b0 = served ? 6 * nr : 0;
+            const float e0 = __shfl_sync(0xffffffffu, d, b0), e1 = __shfl_sync(0xffffffffu, d, b0 + 1),
+                        e2 = __shfl_sync(0xffffffffu, d, b0 + 2), e3 = __shfl_sync(0xffffffffu, d, b0 + 3),
+                        e4 = __shfl_sync(0xffffffffu, d, b0 + 4), e5 = __shfl_sync(0xffffffffu, d, b0 + 5);
+            if (served) {
+                SdfFinishHit(ps, ms, e0, e1, e2, e3, e4, e5);
+                st = PT_ST_SHADE;
+            }
+        }
+    }
+    return st;
 }
 #endif
 
@@ -1296,6 +1369,9 @@ namespace PT_KERNEL_NS {
 #ifndef PT_FEED_T
 #define PT_FEED_T 8
 #endif
+#ifndef PT_COOP_NORMALS
+#define PT_COOP_NORMALS 0 /* measured slower than one lane per ray on every SDF workload: profiles/r01_coop */
+#endif
 
 __device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
                                                   float4* __restrict__ image, float* s_tab) {
@@ -1364,10 +1440,14 @@ __device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const Pt
         }
 #if PT_HAS_SDF
         else if (phase == PT_ST_SDF) {
+#if PT_COOP_NORMALS
+            st = PhaseSdfWarp(c, ps, ms, st, PT_SDF_REPS);
+#else
 #pragma unroll 1
             for (int rep = 0; rep < PT_SDF_REPS; rep++) {
                 if (st == PT_ST_SDF) st = PhaseSdfEval(c, ps, ms);
             }
+#endif
             if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
         }
 #endif
