@@ -84,10 +84,12 @@ int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::ve
     }
     /* Driver selection and tuning knobs (env overrides are for A/B measurements: bench.py, profiles/).
      * Measured on B200 (profiles/r01_sched_ab.md): scenes without SDFs are fastest with the v1 driver (nested
-     * loops), scenes with SDFs with the v2 in-warp scheduler; the fast build wants 6 CTAs/SM, the strict one 4. */
+     * loops), scenes with SDFs with the v2 in-warp scheduler and rolled primitive loops (the kernel is instruction-
+     * cache bound); the fast build wants 6 CTAs/SM, the strict one 4. */
     struct Knob { const char* name; int dflt; };
     const Knob knobs[] = {{"PT_SCHED", sdf_unit.empty() ? 0 : 1}, {"PT_SDF_REPS", 16}, {"PT_FEED_T", 8},
-                          {"PT_MIN_BLOCKS", opt.mode == PT_MODE_FAST ? 6 : 4}, {"PT_NO_UNROLL", 0}, {"PT_STATS", 0},
+                          {"PT_MIN_BLOCKS", opt.mode == PT_MODE_FAST ? 6 : 4},
+                          {"PT_NO_UNROLL", sdf_unit.empty() ? 0 : 1}, {"PT_STATS", 0},
                           {"PT_WF_REFILL", 8}, {"PT_POOL_MIN", 24}, {"PT_COOP_NORMALS", 0}};
     for (const Knob& k : knobs) {
         const char* v = getenv(k.name);

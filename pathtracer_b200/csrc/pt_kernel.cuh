@@ -1007,14 +1007,23 @@ PT_DEV void MarchStateInit(MarchState& ms) {
     ms.points = 0; ms.iter = 0; ms.sub = PT_SUB_SIGN; ms.set1 = 0u;
 }
 
-/* Scene()'s tail, shader.comp:1477-1489: radiance -> XYZ, NaNs dropped */
+/* Scene()'s tail, shader.comp:1477-1489: radiance -> XYZ, NaNs dropped.  The four table look-ups run through one
+ * rolled loop body (instruction-cache footprint); the sum keeps the shader's order
+ * ((rad.x*W(l.x) + rad.y*W(l.y)) + rad.z*W(l.z)) + rad.w*W(l.w), the first product initialising it. */
 PT_DEV V3 PathColor(const Ctx& c, const PathState& ps) {
-    const V3 w0 = WaveToXYZ(c, ps.l.x), w1 = WaveToXYZ(c, ps.l.y), w2 = WaveToXYZ(c, ps.l.z), w3 = WaveToXYZ(c, ps.l.w);
-    const V4 r = ps.radiance;
+    V4 l = ps.l, r = ps.radiance;
+    V3 sum = mk3(0.0f, 0.0f, 0.0f);
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+        const V3 w = WaveToXYZ(c, l.x);
+        sum = (i == 0) ? mk3(r.x * w.x, r.x * w.y, r.x * w.z) : mk3(sum.x + r.x * w.x, sum.y + r.x * w.y, sum.z + r.x * w.z);
+        l = mk4(l.y, l.z, l.w, l.x);
+        r = mk4(r.y, r.z, r.w, r.x);
+    }
     V3 color;
-    color.x = 0.0f + (r.x * w0.x + r.y * w1.x + r.z * w2.x + r.w * w3.x) * 330.0f * 0.25f;
-    color.y = 0.0f + (r.x * w0.y + r.y * w1.y + r.z * w2.y + r.w * w3.y) * 330.0f * 0.25f;
-    color.z = 0.0f + (r.x * w0.z + r.y * w1.z + r.z * w2.z + r.w * w3.z) * 330.0f * 0.25f;
+    color.x = 0.0f + sum.x * 330.0f * 0.25f;
+    color.y = 0.0f + sum.y * 330.0f * 0.25f;
+    color.z = 0.0f + sum.z * 330.0f * 0.25f;
     if ((color.x != color.x) || (color.y != color.y) || (color.z != color.z)) color = mk3(0.0f, 0.0f, 0.0f);
     return color;
 }
