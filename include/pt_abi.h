@@ -128,6 +128,10 @@ int pt_finalize(pt_ctx* ctx, const pt_params* params, int total_samples);
 /* Mapped texel memory (host:3491-3518 reads it through a persistent mapping): copies W*H*4 floats to the host.
  * Synchronises the stream. */
 int pt_read_xyz(pt_ctx* ctx, float* rgba, size_t n_floats);
+/* The same without blocking: the image is snapshotted on the device and copied to `rgba` (pinned host memory) on a
+ * second stream while later dispatches run; pt_read_wait blocks until the most recent such copy has landed. */
+int pt_read_xyz_async(pt_ctx* ctx, float* rgba, size_t n_floats);
+int pt_read_wait(pt_ctx* ctx);
 /* Checkpoint / resume (the accumulation image is the whole render state; the reference loses
  * it on exit): upload a saved image, then continue with pt_render_resume / pt_dispatch from the sample count reached */
 int pt_write_xyz(pt_ctx* ctx, const float* rgba, size_t n_floats);

@@ -83,6 +83,8 @@ def lib():
         L.pt_render.argtypes = [vp, vp, ci, ci]
         L.pt_read_xyz.argtypes = [vp, vp, C.c_size_t]
         L.pt_write_xyz.argtypes = [vp, vp, C.c_size_t]
+        L.pt_read_xyz_async.argtypes = [vp, vp, C.c_size_t]
+        L.pt_read_wait.argtypes = [vp]
         L.pt_render_resume.argtypes = [vp, vp, ci, ci, ci]
         L.pt_read_pfm.argtypes = [C.c_char_p, vp, ci, ci]
         L.pt_sync.argtypes = [vp]
@@ -283,6 +285,13 @@ class Renderer:
             out = np.empty((self.height, self.width, 4), dtype=np.float32)
         _check(lib().pt_read_xyz(self._ctx, _ptr(out), out.size), self._ctx)
         return out
+
+    def read_xyz_async(self, out):
+        """Snapshot the image and copy it to `out` (a numpy view of pinned memory) while later dispatches run."""
+        _check(lib().pt_read_xyz_async(self._ctx, _ptr(out), out.size), self._ctx)
+
+    def read_wait(self):
+        _check(lib().pt_read_wait(self._ctx), self._ctx)
 
     def write_xyz(self, image):
         """Upload a saved accumulation image (checkpoint resume)."""

@@ -52,6 +52,12 @@ struct pt_ctx {
     JitKernel* active_jit = nullptr; /* null: statically compiled kernel */
     std::map<std::string, JitKernel> jit_cache;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    /* asynchronous read-back (pt_read_xyz_async): snapshot buffer, copy stream, ordering events */
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_snap = nullptr, ev_copied = nullptr;
+    float* d_snap = nullptr;
+    size_t snap_bytes = 0;
+    bool copy_pending = false;
     bool timing_open = false;
     long long launches = 0;
     std::string error;
@@ -241,6 +247,10 @@ void pt_destroy(pt_ctx* ctx) {
         if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
     if (ctx->own_image && ctx->d_image) cudaFree(ctx->d_image);
     if (ctx->wf_block) cudaFree(ctx->wf_block);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->ev_snap) cudaEventDestroy(ctx->ev_snap);
+    if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
+    if (ctx->d_snap) cudaFree(ctx->d_snap);
     if (ctx->d_ubo) cudaFree(ctx->d_ubo);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -454,6 +464,45 @@ int pt_read_xyz(pt_ctx* ctx, float* rgba, size_t n_floats) {
     PT_CUDA(ctx, cudaSetDevice(ctx->device));
     PT_CUDA(ctx, cudaMemcpyAsync(rgba, ctx->d_image, need * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PT_OK;
+}
+
+/* Read-back that overlaps the next dispatch: the image is snapshotted device-to-device on the compute stream (so later
+ * dispatches may go on modifying it) and the snapshot travels to the host on a second stream.  `rgba` should be pinned
+ * memory for the copy to be truly asynchronous; pt_read_wait() blocks until the last such copy has landed. */
+int pt_read_xyz_async(pt_ctx* ctx, float* rgba, size_t n_floats) {
+    if (!ctx || !rgba || !ctx->d_image) return fail(ctx, PT_ERR_ARG, "pt_read_xyz_async: bad argument");
+    const size_t need = (size_t)ctx->width * (size_t)ctx->height * 4, bytes = need * sizeof(float);
+    if (n_floats < need) return fail(ctx, PT_ERR_ARG, "pt_read_xyz_async: buffer too small");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) {
+        PT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        PT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_snap, cudaEventDisableTiming));
+        PT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
+    }
+    if (ctx->snap_bytes < bytes) {
+        PT_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        if (ctx->d_snap) cudaFree(ctx->d_snap);
+        ctx->d_snap = nullptr;
+        PT_CUDA(ctx, cudaMalloc((void**)&ctx->d_snap, bytes));
+        ctx->snap_bytes = bytes;
+    }
+    if (ctx->copy_pending) PT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0)); /* snapshot buffer is free again */
+    PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_snap, ctx->d_image, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    PT_CUDA(ctx, cudaEventRecord(ctx->ev_snap, ctx->stream));
+    PT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_snap, 0));
+    PT_CUDA(ctx, cudaMemcpyAsync(rgba, ctx->d_snap, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    PT_CUDA(ctx, cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+    ctx->copy_pending = true;
+    return PT_OK;
+}
+
+int pt_read_wait(pt_ctx* ctx) {
+    if (!ctx) return fail(nullptr, PT_ERR_ARG, "null context");
+    if (!ctx->copy_pending) return PT_OK;
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    PT_CUDA(ctx, cudaEventSynchronize(ctx->ev_copied));
+    ctx->copy_pending = false;
     return PT_OK;
 }
 

@@ -344,3 +344,34 @@ def test_scene_at_the_uniform_block_capacity(ptlib, pipeline):
     got = r.read_xyz()
     r.close()
     assert_bit_equal(got, oracle.Oracle(ubo).render(p, 2, 2), '169 spheres, pipeline %d' % pipeline)
+
+
+def test_async_readback_matches_blocking(ptlib, renderer):
+    """pt_read_xyz_async snapshots the image, so dispatches issued after it do not leak into the copy."""
+    import torch
+    sc = ptlib.Scene.load(scene_path('scene1'))
+    p = sc.pack_params(1, 256, 144, 2, 5)
+    renderer.set_mode(1)
+    renderer.set_scene(sc.pack_ubo())
+    renderer.resize(256, 144)
+    pinned = [torch.empty((144, 256, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    blocking = []
+    for j in (1, 2, 3):
+        q = p.copy(); q['frame'] = 2 * j; q['currentSamples'] = 2 * j
+        renderer.dispatch(q)
+        blocking.append(renderer.read_xyz())
+    renderer.clear()
+    for j in (1, 2, 3):
+        q = p.copy(); q['frame'] = 2 * j; q['currentSamples'] = 2 * j
+        renderer.dispatch(q)
+        renderer.read_xyz_async(pinned[j & 1].numpy())
+        renderer.read_wait()
+        assert np.array_equal(pinned[j & 1].numpy().view(np.uint32), blocking[j - 1].view(np.uint32))
+    # and with the copy genuinely in flight while the next dispatch runs
+    renderer.clear()
+    renderer.dispatch(p.copy())
+    renderer.read_xyz_async(pinned[0].numpy())
+    q2 = p.copy(); q2['frame'] = 4; q2['currentSamples'] = 4
+    renderer.dispatch(q2)
+    renderer.read_wait()
+    assert np.array_equal(pinned[0].numpy().view(np.uint32), blocking[0].view(np.uint32))
