@@ -12,7 +12,7 @@
  *   wl   [P] float4  the wavelength bundle                 rad   [P] float4  radiance
  *   thr  [P] float4  rayradiance (throughput)              shD   [P] float4  shadow dir xyz, shObj (int bits)
  *   shC  [P] float4  pending light contribution            hit0  [P] float4  t, normal xyz
- *   hit1 [P] float4  materialID, lightID, objectID bits    misc  [P] uint2   seed, bounce | isShadow<<16 | pathAlive<<17
+ *   hit1 [P] float4  materialID, lightID, objectID bits    misc  [P] uint2   seed, bounce | isShadow<<30 | pathAlive<<31
  *   col  [P] float4  XYZ of the finished path              acc   [nPix] float4 per-pixel sum, added in sample order
  * Queues hold path indices; pushes are warp-aggregated (ballot + popc prefix, one atomicAdd per warp).
  * Per bounce depth:  ISECT(qA) -> MARCH(qM) -> SHADE(qA: -> qS shadow rays, qB next depth, or finished)
@@ -58,12 +58,12 @@ PT_DEV void StageTable(const float* __restrict__ ubo, float* s_tab) {
 }
 
 PT_DEV unsigned PackMisc(const PathState& ps) {
-    return ((unsigned)ps.bounce & 0xffffu) | (ps.isShadow ? 0x10000u : 0u) | (ps.pathAlive ? 0x20000u : 0u);
+    return ((unsigned)ps.bounce & 0x3fffffffu) | (ps.isShadow ? 0x40000000u : 0u) | (ps.pathAlive ? 0x80000000u : 0u);
 }
 PT_DEV void UnpackMisc(unsigned v, PathState& ps) {
-    ps.bounce = (int)(v & 0xffffu);
-    ps.isShadow = (v & 0x10000u) != 0u;
-    ps.pathAlive = (v & 0x20000u) != 0u;
+    ps.bounce = (int)(v & 0x3fffffffu);
+    ps.isShadow = (v & 0x40000000u) != 0u;
+    ps.pathAlive = (v & 0x80000000u) != 0u;
 }
 
 /* the ray of path p as the intersection phases need it */
