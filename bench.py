@@ -366,7 +366,7 @@ def main():
         achieved = kernel_rate * F / 1e12
         line['roofline'] = {
             'bound': 'fp32', 'achieved': achieved, 'peak': peak_max, 'unit': 'TFLOP/s', 'frac': achieved / peak_max,
-            'traffic': ncu_traffic(wl), 'kernel': 'pt_render_jit' if args.jit == 2 or sc.sdf_sources else 'pt_render_' + args.mode,
+            'traffic': ncu_traffic(wl) if (args.mode == 'fast' and args.pipeline == 'megakernel' and args.jit == 2) else None, 'kernel': 'pt_render_jit' if args.jit == 2 or sc.sdf_sources else 'pt_render_' + args.mode,
             'flops_per_sample_algorithmic': F, 'flops_counting_rule': 'SURVEY.md App. D v1 (source-level, as written in shader.comp)',
             'peak_basis': '148 SM x 128 FP32 lanes x 2 x %s sm_max_mhz (%s); FP32-issue roofline per SURVEY.md section 8d' % (
                 peaks.get('sm_max_mhz', 1965.0), peak_kind),

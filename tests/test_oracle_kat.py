@@ -228,3 +228,37 @@ def test_all_scenes_render_finite(name):
     img = o.render(p, 1, 1)
     assert np.isfinite(img).all()
     assert img[..., :3].max() > 0.0
+
+
+def test_spectral_estimator_normalisation():
+    """Camera inside a huge emitting sphere: every path ends on the emitter at bounce 0, so the pixel value is
+    exposure * mean_k[ Emit(lambda_k) * CMF(lambda_k) ] * 330.  The hero wavelength is drawn on [360, 800] but wrapped
+    into [390, 720) (shader.comp:1469, 971-974): lambda_k - 390 = (u + 82.5 k) mod 330 with u uniform on
+    [-30, 410], so its density is 2/440 on an arc of 110 nm starting at (82.5 k - 30) mod 330 and 1/440 elsewhere,
+    while the estimator multiplies by 330 and averages the four.  The expectation is therefore the integral of
+    Emit * CMF * 330/440 * (1 + arcs(lambda)/4): a quirk that is part of the reference's observable behaviour."""
+    import ctypes as C
+    T, lum = 5500.0, 2.0
+    scene = {'camera': pack.load_scene(scene_path('scene0'))['camera'],
+             'sphere': [{'position': [0, 0, 0], 'radius': 500.0, 'materialID': 1, 'lightID': 1}],
+             'material': [{'reflection': {'peakWavelength': 550.0, 'sigma': 30.0, 'isInvert': False}}],
+             'light': [{'emission': {'temperature': T, 'luminosity': lum}}]}
+    ubo = pack.pack_ubo(scene)
+    p = pack.pack_params(scene, 1, 48, 32, 128, 5)
+    img = oracle.Oracle(ubo).render(p, 128, 128)
+    expo = float(p['apertureSize']) ** 2 * int(p['ISO'])
+    got = img[..., :3].astype(np.float64).mean(axis=(0, 1)) / expo
+    lam = np.arange(390.0, 720.0, 0.05)
+    L = oracle.lib()
+    emit = np.zeros(4, dtype=np.float32)
+    cmf = np.zeros(3, dtype=np.float32)
+    acc = np.zeros(3)
+    for l in lam[::20]:                       # 1 nm steps are plenty for smooth integrands
+        l4 = np.array([l] * 4, dtype=np.float32)
+        L.oracle_emit(l4.ctypes.data, T, lum, emit.ctypes.data)
+        L.oracle_wave_to_xyz(ubo.ctypes.data_as(C.c_void_p), float(l), cmf.ctypes.data_as(C.c_void_p))
+        x = l - 390.0
+        arcs = sum(1 for k in (1, 2, 3, 4) if ((x - (82.5 * k - 30.0)) % 330.0) <= 110.0)
+        acc += float(emit[0]) * cmf.astype(np.float64) * (330.0 / 440.0) * (1.0 + arcs / 4.0)
+    want = acc * 1.0                           # sum over 1 nm bins
+    assert np.allclose(got, want, rtol=0.015), (got, want)   # ~2e5 samples: Monte-Carlo error well below 1 %
