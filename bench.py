@@ -65,47 +65,60 @@ def flops_per_sample(cnt, scene_counts, c_sdf, c_mat):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md's clocks line)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md's clocks line).  The sampler is
+    started before the warm-up (nvidia-smi takes a moment to come up); only rows stamped inside [mark_begin, mark_end]
+    are used."""
 
     def __init__(self, index):
         self.rows = []
         self.proc = None
         self.index = index
+        self.t0 = self.t1 = None
 
     def start(self):
-        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+        q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits',
-                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([t.strip() for t in line.split(',')])
+            self.rows.append((time.time(), [t.strip() for t in line.split(',')]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc:
+            time.sleep(0.12)  # let the last rows of the window arrive
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        sm, mx, reasons, power = [], [], set(), []
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 - 0.05 <= t <= (self.t1 or t) + 0.1]
+        for r in inside or [r for _, r in self.rows[-3:]]:
             try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                power.append(float(r[3]))
             except (ValueError, IndexError):
                 continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
                 if v.lower().startswith('active'):
                     reasons.add(name)
         if not sm:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
-        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm)}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm),
+                'samples_in_timed_region': len(inside), 'power_w_max': max(power) if power else None}
 
 
 def ncu_traffic(wl):
@@ -259,17 +272,18 @@ def main():
             with torch.cuda.stream(ext):
                 flush.fill_(rank & 0xFF)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for i in range(Wm):
         step(i)
         flush_l2()
     r.sync()
     r.kernel_time()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    sampler.mark_begin()
     wall0 = time.perf_counter()
     dev_ms, launches = 0.0, 0
     for i in range(Wm, Wm + K):
@@ -294,6 +308,7 @@ def main():
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - wall0
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     total_ms = dev_ms + reduce_ms
     if world > 1:

@@ -19,8 +19,18 @@
  *   - the shadow ray (LightSourceVisibilityCheck) shares the intersection code but skips normals and materials,
  *     which it never uses; sphere tracing for it skips the 6 normal probes and the material evaluation;
  *   - EvaluateBRDF's spectral term is evaluated once per bounce and reused for the light sample;
- *   - the CIE table and the material/light tables are staged in shared memory (divergent indices);
+ *   - the whole uniform block (CIE table, material/light tables: divergent indices) is staged in shared memory;
  *   - a warp covers an 8x4 pixel tile so primary rays stay coherent.
+ *
+ * Layout of this file: value types and mode-dependent primitives; the shader's functions (RNG, spectral helpers,
+ * intersections, SDF search); then the DRIVERS that run them --
+ *   v1  (PT_SCHED 0)  nested sample / bounce loops per thread            default for scenes without SDFs
+ *   v2  (PT_SCHED 1)  four phases over explicit PathState, one phase per warp iteration chosen by ballot,
+ *                     lanes refill themselves with their pixel's next sample   default for scenes with SDFs
+ *   v2p (PT_SCHED 2)  v2 + a CTA-shared march pool (measured slower: profiles/r01_pool)
+ * -- and the kernel entry macros.  pt_wavefront.cuh runs the same phases as separate kernels over state in HBM.
+ * The kernel is instruction-cache bound (16-byte SASS, 28-45 KB per scene): single call sites and rolled loops
+ * are deliberate (profiles/README.md).
  */
 #ifndef PT_KERNEL_CUH
 #define PT_KERNEL_CUH
