@@ -34,8 +34,18 @@ WORKLOADS = {
     'cfg4a_scene10_menger_1080p_pl32': ('scene10', 1920, 1080, 1024, 32, 214, 0),
     'cfg4b_scene8_terrain_1080p_pl32': ('scene8', 1920, 1080, 1024, 32, 92, 0),
     'cfg5_scene10_4k': ('scene10', 3840, 2160, 16384, 5, 214, 0),
+    # beyond the shipped scenes (section 8f-3): primitive counts where the BVH replaces the scan; --bvh-min 0 = scan
+    'bvh_spheres169_1080p': ('synthetic/spheres169', 1920, 1080, 1024, 5, 0, 0),
+    'bvh_mixed74_1080p': ('synthetic/mixed74', 1920, 1080, 1024, 5, 0, 0),
 }
 N_SM, FP32_LANES = 148, 128
+
+
+def scene_file(name):
+    """'sceneN' -> the reference's shipped scenes/sceneN.json; 'synthetic/X' -> scenes_synthetic/X.json"""
+    if name.startswith('synthetic/'):
+        return os.path.join(ROOT, 'scenes_synthetic', name.split('/', 1)[1] + '.json')
+    return os.path.join(ROOT, 'scenes', name + '.json')
 
 
 def load_peaks():
@@ -135,7 +145,7 @@ def ncu_traffic(wl):
 
 def oracle_for(scene_name, count=False, threads=0):
     from oracle import oracle, pack
-    scene = pack.load_scene(os.path.join(ROOT, 'scenes', scene_name + '.json'))
+    scene = pack.load_scene(scene_file(scene_name))
     return oracle.Oracle(pack.pack_ubo(scene), pack.sdf_sources(scene), count=count, threads=threads), scene
 
 
@@ -200,7 +210,7 @@ def run_reference(args, wl):
         'impl': 'reference', 'metric': 'spectral path samples/sec', 'value': value, 'unit': 'samples/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * wall / max(total, 1), 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic (reference scene files shipped in scenes/)',
-        'config': {'workload': wl, 'scene': 'scenes/%s.json' % scene_name, 'width': W, 'height': H, 'path_length': pl,
+        'config': {'workload': wl, 'scene': os.path.relpath(scene_file(scene_name), ROOT), 'width': W, 'height': H, 'path_length': pl,
                    'spp_of_config': spp_cfg, 'note': 'CPU oracle port of shader.comp; each step = a strided-row sample of the frame'},
         'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': threads, 'kind': 'port', 'sample': desc},
         'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -221,6 +231,7 @@ def main():
     ap.add_argument('--mode', default='fast', choices=['fast', 'strict'])
     ap.add_argument('--jit', type=int, default=2, help='0 static kernels, 1 NVRTC for SDF scenes only, 2 NVRTC scene-specialised')
     ap.add_argument('--pipeline', default='megakernel', choices=['megakernel', 'wavefront'])
+    ap.add_argument('--bvh-min', type=int, default=None, help='bounded primitives from which the BVH replaces the scan (0: never)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-flush', action='store_true')
     args = ap.parse_args()
@@ -242,14 +253,17 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
-    sc = pt.Scene.load(os.path.join(ROOT, 'scenes', scene_name + '.json'))
+    sc = pt.Scene.load(scene_file(scene_name))
     ubo = sc.pack_ubo()
     params = sc.pack_params(1, W, H, args.spf, pl)
     r = pt.Renderer(device=local_rank, mode=pt.MODE_FAST if args.mode == 'fast' else pt.MODE_STRICT, jit=args.jit,
                     pipeline=pt.PIPE_WAVEFRONT if args.pipeline == 'wavefront' else pt.PIPE_MEGAKERNEL)
+    if args.bvh_min is not None:
+        r.set_bvh(args.bvh_min)
     t0 = time.perf_counter()
     r.set_scene(ubo, sc.sdf_sources)
     compile_s = time.perf_counter() - t0
+    bvh_active = r.bvh_active
     image = torch.zeros((H, W, 4), dtype=torch.float32, device='cuda')
     r.bind_image(image)
     ext = torch.cuda.ExternalStream(r.stream)
@@ -356,9 +370,9 @@ def main():
         'metric': 'spectral path samples/sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
         'ms_per_step': total_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic (reference scene files shipped in scenes/, no external assets)',
-        'config': {'workload': wl, 'scene': 'scenes/%s.json' % scene_name, 'width': W, 'height': H, 'spf_per_step': spf,
+        'config': {'workload': wl, 'scene': os.path.relpath(scene_file(scene_name), ROOT), 'width': W, 'height': H, 'spf_per_step': spf,
                    'spp_timed': K * spf * world, 'spp_of_config': spp_cfg, 'path_length': pl, 'shot': 1, 'mode': args.mode,
-                   'jit': args.jit, 'pipeline': args.pipeline, 'l2': 'not flushed' if args.no_flush else 'flushed between steps (256 MiB fill)',
+                   'jit': args.jit, 'pipeline': args.pipeline, 'closest_hit': 'bvh' if bvh_active else 'scan', 'l2': 'not flushed' if args.no_flush else 'flushed between steps (256 MiB fill)',
                    'parallelism': 'sample-split x%d + 1 NCCL reduce' % world if world > 1 else 'single GPU',
                    'kernel_compile_s': round(compile_s, 3)},
         'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': 16388 + 88, 'd2h_bytes_per_step': W * H * 16,

@@ -73,6 +73,8 @@ def lib():
         L.pt_set_mode.argtypes = [vp, ci]
         L.pt_set_jit.argtypes = [vp, ci]
         L.pt_set_pipeline.argtypes = [vp, ci]
+        L.pt_set_bvh.argtypes = [vp, ci]
+        L.pt_bvh_active.argtypes = [vp]
         L.pt_set_scene.argtypes = [vp, vp, C.POINTER(C.c_char_p), ci]
         L.pt_resize.argtypes = [vp, ci, ci]
         L.pt_bind_image.argtypes = [vp, vp, ci, ci]
@@ -243,6 +245,14 @@ class Renderer:
     def set_pipeline(self, pipeline):
         """PIPE_MEGAKERNEL (default) or PIPE_WAVEFRONT; takes effect at the next set_scene."""
         _check(lib().pt_set_pipeline(self._ctx, pipeline), self._ctx)
+
+    def set_bvh(self, min_prims):
+        """Bounded-primitive count from which the closest-hit search walks the BVH (<= 0: never); next set_scene."""
+        _check(lib().pt_set_bvh(self._ctx, min_prims), self._ctx)
+
+    @property
+    def bvh_active(self):
+        return bool(lib().pt_bvh_active(self._ctx))
 
     def set_scene(self, ubo, sdf_sources=()):
         ubo = np.ascontiguousarray(ubo, dtype=np.float32)

@@ -14,6 +14,10 @@ int pt_prepare_scene(const pt_ubo* ubo, PtDevScene* sc, std::string* err);
 int pt_prepare_params(const pt_params* p, int accum_mode, int first_sample, int n_samples, PtDevParams* d,
                       std::string* err);
 
+/* pt_bvh.cpp: BVH over the bounded primitives (layout: pt_bvh.h); blob = nodes + copy of the record pool */
+int pt_bvh_bounded_prims(const PtDevScene* sc);
+int pt_bvh_build(const PtDevScene* sc, std::vector<float>* blob, std::string* err);
+
 /* pt_sdf_front.cpp: GLSL snippets -> CUDA translation unit text (prelude + snippets + dispatchers) */
 int pt_sdf_generate(const char* const* sdf_glsl, int n_sdf, const float* sdfs_raw, std::string* out, std::string* err);
 
@@ -22,6 +26,7 @@ struct PtJitOptions {
     int mode;            /* pt_mode */
     bool bake_counts;    /* compile primitive counts in as constants */
     bool wavefront;      /* also build the wavefront pipeline's kernels (pt_wavefront.cuh) */
+    bool bvh;            /* closest hit through the BVH of pt_bvh.h instead of the brute-force scan */
     int counts[6];       /* spheres, planes, boxes, lenses, cyclides, sdfs */
 };
 int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::vector<char>* cubin, std::string* log);

@@ -77,6 +77,7 @@ int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::ve
     src += opt.mode == PT_MODE_FAST ? "#define PT_FAST 1\n#define PT_KERNEL_NS ptk_jit_fast\n"
                                     : "#define PT_KERNEL_NS ptk_jit_strict\n";
     if (!sdf_unit.empty()) src += "#define PT_HAS_SDF 1\n";
+    if (opt.bvh) src += "#define PT_BVH 1\n";
     if (opt.bake_counts) {
         const char* names[6] = {"PT_N_SPHERES_CONST", "PT_N_PLANES_CONST", "PT_N_BOXES_CONST", "PT_N_LENSES_CONST",
                                 "PT_N_CYCLIDES_CONST", "PT_N_SDF_CONST"};

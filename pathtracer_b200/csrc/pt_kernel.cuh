@@ -37,6 +37,12 @@
 
 #include "pt_math.h"
 #include "pt_dev_scene.h"
+#ifndef PT_BVH
+#define PT_BVH 0 /* 1: the JIT found enough bounded primitives for the tree of pt_bvh.h to pay (pt_lib.cpp) */
+#endif
+#if PT_BVH
+#include "pt_bvh.h"
+#endif
 
 #ifndef PT_BLOCK_THREADS
 #define PT_BLOCK_THREADS 128
@@ -320,6 +326,12 @@ struct Hit {
     int objectID;     /* global object index (LightSourceVisibilityCheck, shader.comp:1127) */
 };
 
+/* The reference scans primitives in index order with `if (t < hit.t)`: smallest t wins, ties go to the lowest index.
+ * The BVH visits them in ray order, so there the tie rule is spelled out (kTie); the in-order scan does not need it. */
+PT_DEV bool CloserHit(float t, int objectID, const Hit& h, const bool kTie) {
+    return (t < h.t) || (kTie && (t == h.t) && (objectID < h.objectID));
+}
+
 /* shader.comp:263-276 */
 PT_DEV bool BoundingSphere(const Ray& ray, float px, float py, float pz, float radius2) {
     const V3 lo = mk3(ray.origin.x - px, ray.origin.y - py, ray.origin.z - pz);
@@ -331,7 +343,7 @@ PT_DEV bool BoundingSphere(const Ray& ray, float px, float py, float pz, float r
 }
 
 /* shader.comp:289-317 */
-PT_DEV void SphereIntersection(const Ray& ray, const PtDevSphere& o, int objectID, Hit& h, const bool kShadow) {
+PT_DEV void SphereIntersection(const Ray& ray, const PtDevSphere& o, int objectID, Hit& h, const bool kShadow, const bool kTie = false) {
     const V3 lo = mk3(ray.origin.x - o.px, ray.origin.y - o.py, ray.origin.z - o.pz);
     const float b = 2.0f * dot(ray.dir, lo);
     const float cc = dot(lo, lo) - o.r2;
@@ -342,7 +354,7 @@ PT_DEV void SphereIntersection(const Ray& ray, const PtDevSphere& o, int objectI
     const float t2 = (-b + sqrtD) * 0.5f;
     const float t = (t1 > 0.0f) ? t1 : t2;
     if (t < 1e-4f) return;
-    if (t < h.t) {
+    if (CloserHit(t, objectID, h, kTie)) {
         h.t = t;
         h.objectID = objectID;
         if (!kShadow) {
@@ -355,11 +367,11 @@ PT_DEV void SphereIntersection(const Ray& ray, const PtDevSphere& o, int objectI
 }
 
 /* shader.comp:319-335 */
-PT_DEV void PlaneIntersection(const Ray& ray, const PtDevPlane& o, int objectID, Hit& h, const bool kShadow) {
+PT_DEV void PlaneIntersection(const Ray& ray, const PtDevPlane& o, int objectID, Hit& h, const bool kShadow, const bool kTie = false) {
     const float loy = ray.origin.y - o.py;
     const float t = PTK_DIV(-loy, ray.dir.y);
     if (t < 1e-4f) return;
-    if (t < h.t) {
+    if (CloserHit(t, objectID, h, kTie)) {
         h.t = t;
         h.objectID = objectID;
         if (!kShadow) {
@@ -373,7 +385,7 @@ PT_DEV void PlaneIntersection(const Ray& ray, const PtDevPlane& o, int objectID,
 }
 
 /* shader.comp:337-364 */
-PT_DEV void BoxIntersection(const Ray& ray, const PtDevBox& o, int objectID, Hit& h, const bool kShadow) {
+PT_DEV void BoxIntersection(const Ray& ray, const PtDevBox& o, int objectID, Hit& h, const bool kShadow, const bool kTie = false) {
     const V3 lo = mulVM(mk3(ray.origin.x - o.px, ray.origin.y - o.py, ray.origin.z - o.pz), o.m);
     const V3 dir = mulVM(ray.dir, o.m);
     const V3 invdir = mk3(PTK_DIV(1.0f, dir.x), PTK_DIV(1.0f, dir.y), PTK_DIV(1.0f, dir.z));
@@ -387,7 +399,7 @@ PT_DEV void BoxIntersection(const Ray& ray, const PtDevBox& o, int objectID, Hit
     const float t2 = PTK_MIN(PTK_MIN(tMax.x, tMax.y), tMax.z);
     const float t = (t1 < 0.0f) ? t2 : t1;
     if ((t1 > t2) || (t < 1e-4f)) return;
-    if (t < h.t) {
+    if (CloserHit(t, objectID, h, kTie)) {
         h.t = t;
         h.objectID = objectID;
         if (!kShadow) {
@@ -408,7 +420,7 @@ PT_DEV void BoxIntersection(const Ray& ray, const PtDevBox& o, int objectID, Hit
  * `x > -sliceOffset` / `x < sliceOffset`, i.e. `s*x > -sliceOffset`; multiplying by +-1 is exact), so one copy of
  * the code runs twice: the kernel is instruction-cache bound, and this body is instantiated for the scene's
  * lenses and for the camera lens. */
-PT_DEV void LensIntersection(const Ray& ray, const PtDevLens& o, int objectID, Hit& h, int& isOutside, const bool kShadow) {
+PT_DEV void LensIntersection(const Ray& ray, const PtDevLens& o, int objectID, Hit& h, int& isOutside, const bool kShadow, const bool kTie = false) {
     const V3 lo0 = mulVM(mk3(ray.origin.x - o.px, ray.origin.y - o.py, ray.origin.z - o.pz), o.m);
     const V3 ldir = mulVM(ray.dir, o.m);
 #pragma unroll 1
@@ -432,7 +444,7 @@ PT_DEV void LensIntersection(const Ray& ray, const PtDevLens& o, int objectID, H
             isOut = -1;
         }
         if (t < 1e-4f) continue;
-        if (t < h.t) {
+        if (CloserHit(t, objectID, h, kTie)) {
             h.t = t;
             h.objectID = objectID;
             if (!kShadow) {
@@ -520,7 +532,7 @@ PT_DEV float SolveQuarticNearest(float a, float b, float c, float d, float e) {
 }
 
 /* shader.comp:633-679 */
-PT_DEV_NOINLINE void DupinCyclide(const Ray& ray, const PtDevCyclide& ob, int objectID, Hit& h, const bool kShadow) {
+PT_DEV_NOINLINE void DupinCyclide(const Ray& ray, const PtDevCyclide& ob, int objectID, Hit& h, const bool kShadow, const bool kTie = false) {
     const V3 lo = mulVM(mk3(ray.origin.x - ob.px, ray.origin.y - ob.py, ray.origin.z - ob.pz), ob.m);
     const V3 ld = mulVM(ray.dir, ob.m);
     /* .xzy swizzle after the divide by scale */
@@ -542,7 +554,7 @@ PT_DEV_NOINLINE void DupinCyclide(const Ray& ray, const PtDevCyclide& ob, int ob
                      4.0f * C * C * D * D + 8.0f * A * C * D * o.x + 2.0f * BBmDD * dot(o, o) -
                      4.0f * (A * A * o.x * o.x + B * B * o.y * o.y);
     const float t = SolveQuarticNearest(a4, a3, a2, a1, a0);
-    if (t < h.t) {
+    if (CloserHit(t, objectID, h, kTie)) {
         h.t = t;
         h.objectID = objectID;
         if (!kShadow) {
@@ -682,7 +694,20 @@ PT_DEV_NOINLINE void SphereTracing(const Ctx& c, const Ray& ray, Hit& h, const b
 }
 #endif /* PT_HAS_SDF */
 
-/* shader.comp:862-934 (kShadow = false) and 1121-1216 (kShadow = true): brute-force closest hit in type order */
+#if PT_BVH
+/* a primitive record of the pool's global-memory copy, as 16-byte loads through the read-only path */
+template <class T>
+PT_DEV T LoadRecord(const float* p) {
+    alignas(16) T r;
+    float4* d = reinterpret_cast<float4*>(&r);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(T) / 16); k++) d[k] = __ldg(reinterpret_cast<const float4*>(p) + k);
+    return r;
+}
+#endif
+
+/* shader.comp:862-934 (kShadow = false) and 1121-1216 (kShadow = true): closest hit over the analytic primitives --
+ * the reference's brute-force scan in type order, or (PT_BVH) the same search through the tree of pt_bvh.h */
 PT_DEV void IntersectionAnalytic(const Ctx& c, const Ray& ray, Hit& h, const bool kShadow) {
     const PtDevScene& sc = *c.sc;
     h.t = 1e5f;
@@ -692,6 +717,39 @@ PT_DEV void IntersectionAnalytic(const Ctx& c, const Ray& ray, Hit& h, const boo
         h.materialID = 0.0f;
         h.lightID = -1.0f;
     }
+#if PT_BVH
+    /* planes (unbounded) in order, then the tree over everything else; the tie rule makes the order irrelevant */
+    const int nSb = PT_N_SPHERES(c), nPb = PT_N_PLANES(c), nBb = PT_N_BOXES(c), nLb = PT_N_LENSES(c), nCb = PT_N_CYCLIDES(c);
+    for (int i = 0; i < nPb; i++) PlaneIntersection(ray, reinterpret_cast<const PtDevPlane*>(sc.pool + PT_OFF_PLANES(sc))[i], nSb + i, h, kShadow);
+    const float* nodes = c.ubo + PT_BVH_UBO_OFF;
+    const float* recs = nodes + PT_BVH_NODE_FLOATS * (nSb + nBb + nLb + nCb - 1); /* the pool's copy in global memory */
+    const int offB = PT_OFF_BOXES(sc), offL = PT_OFF_LENSES(sc), offC = PT_OFF_CYCLIDES(sc);
+    pt_bvh_traverse(nodes, ray.origin.x, ray.origin.y, ray.origin.z, ray.dir.x, ray.dir.y, ray.dir.z, h.t, [&](int ref) {
+        const int type = ref >> 16, i = ref & 0xffff;
+        if (type == PT_BVH_SPHERE) {
+            const PtDevSphere o = LoadRecord<PtDevSphere>(recs + 8 * i);
+            SphereIntersection(ray, o, i, h, kShadow, true);
+        } else if (type == PT_BVH_BOX) {
+            if (nBb > 0) {
+                const PtDevBox o = LoadRecord<PtDevBox>(recs + offB + 20 * i);
+                if (BoundingSphere(ray, o.px, o.py, o.pz, o.bound2)) BoxIntersection(ray, o, nSb + nPb + i, h, kShadow, true);
+            }
+        } else if (type == PT_BVH_LENS) {
+            if (nLb > 0) {
+                const PtDevLens o = LoadRecord<PtDevLens>(recs + offL + 20 * i);
+                if (BoundingSphere(ray, o.px, o.py, o.pz, o.bound2)) {
+                    int isOutside = 1;
+                    LensIntersection(ray, o, nSb + nPb + nBb + i, h, isOutside, kShadow, true);
+                }
+            }
+        } else {
+            if (nCb > 0) {
+                const PtDevCyclide o = LoadRecord<PtDevCyclide>(recs + offC + 24 * i);
+                if (BoundingSphere(ray, o.px, o.py, o.pz, o.brad)) DupinCyclide(ray, o, nSb + nPb + nBb + nLb + i, h, kShadow, true);
+            }
+        }
+    });
+#else
     int base = 0;
     const int nS = PT_N_SPHERES(c);
     PT_UNROLL_PRIMS
@@ -724,6 +782,7 @@ PT_DEV void IntersectionAnalytic(const Ctx& c, const Ray& ray, Hit& h, const boo
         if (!BoundingSphere(ray, o.px, o.py, o.pz, o.brad)) continue;
         DupinCyclide(ray, o, base + i, h, kShadow);
     }
+#endif
 }
 
 /* shader.comp:862-934 / 1121-1216 in one piece (used by the v1 driver) */

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "pt_internal.h"
+#include "pt_bvh.h"
 
 const std::string& pt_scene_last_error();
 
@@ -39,6 +40,8 @@ struct pt_ctx {
     int mode = PT_MODE_STRICT;
     int jit_policy = 1;      /* 0: never (static kernels only), 1: when the scene has SDFs, 2: always (baked counts) */
     int pipeline = PT_PIPE_MEGAKERNEL;
+    int bvh_min = PT_BVH_DEFAULT_MIN_PRIMS; /* bounded primitives from which the BVH replaces the scan; <= 0: never */
+    bool bvh_active = false;
     PtWf wf;                 /* wavefront buffers (lazily allocated) */
     void* wf_block = nullptr;
     size_t wf_paths = 0, wf_pixels = 0;
@@ -228,9 +231,11 @@ int pt_create(int device, pt_ctx** out) {
     ctx->device = device;
     const char* pol = getenv("PT_JIT");
     if (pol && pol[0]) ctx->jit_policy = atoi(pol);
+    const char* bm = getenv("PT_BVH_MIN");
+    if (bm && bm[0]) ctx->bvh_min = atoi(bm);
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&ctx->d_ubo, sizeof(pt_ubo))) != cudaSuccess) {
+        (e = cudaMalloc((void**)&ctx->d_ubo, sizeof(float) * (PT_BVH_UBO_OFF + PT_BVH_MAX_FLOATS))) != cudaSuccess) {
         int rc = cuda_fail(nullptr, e, "pt_create");
         pt_destroy(ctx);
         return rc;
@@ -274,6 +279,15 @@ int pt_set_jit(pt_ctx* ctx, int policy) {
     return PT_OK;
 }
 
+int pt_set_bvh(pt_ctx* ctx, int min_prims) {
+    if (!ctx) return fail(nullptr, PT_ERR_ARG, "null context");
+    ctx->bvh_min = min_prims;
+    ctx->scene_set = false;
+    return PT_OK;
+}
+
+int pt_bvh_active(const pt_ctx* ctx) { return (ctx && ctx->scene_set && ctx->bvh_active) ? 1 : 0; }
+
 int pt_set_pipeline(pt_ctx* ctx, int pipeline) {
     if (!ctx) return fail(nullptr, PT_ERR_ARG, "null context");
     if (pipeline != PT_PIPE_MEGAKERNEL && pipeline != PT_PIPE_WAVEFRONT) return fail(ctx, PT_ERR_ARG, "unknown pipeline");
@@ -294,7 +308,17 @@ int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, in
                                          std::to_string(sc.nSdfs) + ")");
     JitKernel* jit = nullptr;
     const bool wavefront = ctx->pipeline == PT_PIPE_WAVEFRONT;
-    const bool want_jit = (n_sdf > 0) || ctx->jit_policy == 2 || wavefront;
+    /* enough bounded primitives for the tree to beat the scan (run-time compiled kernels only) */
+    const int n_bounded = pt_bvh_bounded_prims(&sc);
+    const bool bvh = ctx->jit_policy != 0 && ctx->bvh_min > 0 && n_bounded >= ctx->bvh_min && n_bounded >= 2 &&
+                     n_bounded <= PT_BVH_MAX_PRIMS;
+    std::vector<float> bvh_blob;
+    if (bvh) {
+        rc = pt_bvh_build(&sc, &bvh_blob, &err);
+        if (rc != PT_OK) return fail(ctx, rc, err);
+        if (bvh_blob.size() > (size_t)PT_BVH_MAX_FLOATS) return fail(ctx, PT_ERR_ARG, "BVH blob larger than its device buffer");
+    }
+    const bool want_jit = (n_sdf > 0) || ctx->jit_policy == 2 || wavefront || bvh;
     if ((n_sdf > 0 || wavefront) && ctx->jit_policy == 0)
         return fail(ctx, PT_ERR_COMPILE, "scenes with SDF snippets and the wavefront pipeline need run-time compilation (PT_JIT=0 set)");
     if (want_jit) {
@@ -307,9 +331,10 @@ int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, in
         opt.mode = ctx->mode;
         opt.bake_counts = (ctx->jit_policy == 2);
         opt.wavefront = wavefront;
+        opt.bvh = bvh;
         const int counts[6] = {sc.nSpheres, sc.nPlanes, sc.nBoxes, sc.nLenses, sc.nCyclides, sc.nSdfs};
         memcpy(opt.counts, counts, sizeof counts);
-        std::string key = std::to_string(opt.mode) + (opt.bake_counts ? "b" : "g") + (wavefront ? "w" : "m");
+        std::string key = std::to_string(opt.mode) + (opt.bake_counts ? "b" : "g") + (wavefront ? "w" : "m") + (bvh ? "B" : "");
         if (opt.bake_counts)
             for (int i = 0; i < 6; i++) key += "," + std::to_string(counts[i]);
         key += "|" + unit;
@@ -349,7 +374,11 @@ int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, in
     ctx->ubo = *ubo;
     ctx->dev_scene = sc;
     ctx->active_jit = jit;
+    ctx->bvh_active = bvh;
     PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_ubo, &ctx->ubo, sizeof(pt_ubo), cudaMemcpyHostToDevice, ctx->stream));
+    if (bvh)
+        PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_ubo + PT_BVH_UBO_OFF, bvh_blob.data(), bvh_blob.size() * sizeof(float),
+                                     cudaMemcpyHostToDevice, ctx->stream));
     PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); /* ctx->ubo may be overwritten by the next call */
     ctx->scene_set = true;
     ctx->error.clear();
@@ -557,6 +586,7 @@ int pt_sdf_compile_check(const char* const* sdf_glsl, int n_sdf, const float* sd
     opt.mode = mode;
     opt.bake_counts = false;
     opt.wavefront = false;
+    opt.bvh = false;
     memset(opt.counts, 0, sizeof opt.counts);
     std::vector<char> cubin;
     rc = pt_jit_compile(unit, opt, &cubin, &log);
@@ -581,6 +611,7 @@ int pt_kernel_compile_check(const pt_ubo* ubo, const char* const* sdf_glsl, int 
     opt.mode = mode & 1;
     opt.bake_counts = bake_counts != 0;
     opt.wavefront = (mode & 2) != 0; /* mode bit 1: also build the wavefront kernels */
+    opt.bvh = (mode & 4) != 0;       /* mode bit 2: closest hit through the BVH */
     const int counts[6] = {sc.nSpheres, sc.nPlanes, sc.nBoxes, sc.nLenses, sc.nCyclides, sc.nSdfs};
     memcpy(opt.counts, counts, sizeof counts);
     std::vector<char> cubin;

@@ -331,19 +331,79 @@ def many_sphere_scene(n):
 
 
 @pytest.mark.parametrize('pipeline', [0, 1])
-def test_scene_at_the_uniform_block_capacity(ptlib, pipeline):
+@pytest.mark.parametrize('bvh_min', [0, 12])
+def test_scene_at_the_uniform_block_capacity(ptlib, pipeline, bvh_min):
+    """169 spheres, through the reference's in-order scan (bvh_min 0) and through the BVH (the default from 12 bounded
+    primitives): both equal the oracle's brute-force result bit for bit."""
     text, scene = many_sphere_scene(169)          # 169 * 6 + 5 = 1019 of 1024 object floats
     sc = ptlib.Scene.parse(text)
     ubo = sc.pack_ubo()
     assert np.array_equal(ubo.view(np.uint32), pack.pack_ubo(scene).view(np.uint32)) and ubo[0] == 169
     p = sc.pack_params(1, 64, 48, 2, 5)
     r = ptlib.Renderer(device=0, mode=ptlib.MODE_STRICT, pipeline=pipeline)
+    r.set_bvh(bvh_min)
     r.set_scene(ubo)
+    assert r.bvh_active == (bvh_min > 0)
     r.resize(64, 48)
     r.render(p, 2, 2)
     got = r.read_xyz()
     r.close()
-    assert_bit_equal(got, oracle.Oracle(ubo).render(p, 2, 2), '169 spheres, pipeline %d' % pipeline)
+    assert_bit_equal(got, oracle.Oracle(ubo).render(p, 2, 2), '169 spheres, pipeline %d, bvh_min %d' % (pipeline, bvh_min))
+
+
+# ---- BVH (pt_bvh.h): the same closest-hit search as the reference's scan, section 8f-3 ---------------------------------
+def synthetic_path(name):
+    import os
+    from conftest import ROOT
+    return os.path.join(ROOT, 'scenes_synthetic', name + '.json')
+
+
+@pytest.mark.parametrize('name,w,h,spp,jit,pipeline', [
+    ('spheres169', 160, 120, 4, 1, 0), ('spheres169', 96, 64, 2, 2, 0), ('mixed74', 160, 120, 4, 1, 0),
+    ('mixed74', 96, 64, 2, 2, 0), ('mixed74', 64, 48, 2, 1, 1)])
+def test_bvh_strict_bit_exact(ptlib, name, w, h, spp, jit, pipeline):
+    """Spheres near the block's capacity, and a mix of 30 spheres / 20 rotated boxes / 12 lenses / 12 cyclides: the BVH
+    kernels (generic and count-specialised megakernel, wavefront) against the oracle's brute-force scan, all shots."""
+    sc = ptlib.Scene.load(synthetic_path(name))
+    ubo = sc.pack_ubo()
+    r = ptlib.Renderer(device=0, mode=ptlib.MODE_STRICT, jit=jit, pipeline=pipeline)
+    r.set_scene(ubo)
+    assert r.bvh_active
+    for shot in range(1, sc.num_shots + 1):
+        p = sc.pack_params(shot, w, h, spp, 5)
+        r.resize(w, h)
+        r.render(p, spp, spp)
+        assert_bit_equal(r.read_xyz(), oracle.Oracle(ubo).render(p, spp, spp), '%s shot %d (BVH)' % (name, shot))
+    r.close()
+
+
+@pytest.mark.parametrize('name', ['spheres169', 'mixed74'])
+def test_bvh_fast_mode_matches_the_scan(ptlib, name):
+    """Fast mode, tree vs scan on the same sample indices: the leaf arithmetic is the same code, so the images agree
+    far inside the Monte-Carlo noise floor (two scan renders with disjoint sample indices)."""
+    w, h, spp = 160, 120, 32
+    sc = ptlib.Scene.load(synthetic_path(name))
+    ubo = sc.pack_ubo()
+    p = sc.pack_params(1, w, h, spp, 5)
+
+    def run(bvh_min, first):
+        r = ptlib.Renderer(device=0, mode=ptlib.MODE_FAST, jit=2)
+        r.set_bvh(bvh_min)
+        r.set_scene(ubo)
+        assert r.bvh_active == (bvh_min > 0)
+        r.resize(w, h)
+        r.dispatch_sum(p, first, spp)
+        r.finalize(p, spp)
+        img = r.read_xyz()
+        r.close()
+        return img
+
+    scan, scan2, tree = run(0, 0), run(0, 1 << 20), run(12, 0)
+    noise, diff = rel_rmse(scan, scan2), rel_rmse(tree, scan)
+    same = float(np.mean(np.all(tree.view(np.uint32) == scan.view(np.uint32), axis=-1)))
+    print('%s: relRMSE scan A/B %.4f, tree/scan %.5f, identical pixels %.4f' % (name, noise, diff, same))
+    assert np.isfinite(tree).all()
+    assert diff <= 0.25 * noise + 1e-4
 
 
 def test_async_readback_matches_blocking(ptlib, renderer):
