@@ -2,12 +2,15 @@
  *
  * Full-sweep SAH, one primitive per leaf (170 primitives at most: the build is microseconds).  The boxes are
  * PADDED so that culling stays conservative with respect to the primitives' own fp32 arithmetic: the reference's
- * quadratic `b*b - 4*c` carries an absolute error of about 3e-7 * D^2 for a ray origin at distance D, so a sphere of
- * radius r "exists" for the shader out to sqrt(r^2 + 3e-7 D^2).  Every primitive's bounding radius is therefore
- * grown to sqrt(r^2 + 2^-19 S^2) + 2^-16 S, S = the scene's scale (4 x the diagonal of everything bounded, origin
- * included).  For rays that start inside that scale the tree returns bit for bit what the in-order scan returns
- * (tests/test_bvh.py, tests/test_gpu_parity.py); a ray launched from farther away -- only possible off an infinite
- * plane -- can differ on grazing hits that are themselves rounding noise of the reference.
+ * quadratic `b*b - 4*c` carries an absolute error of up to 2.4e-6 * D^2 for a ray origin at distance D, so a sphere of
+ * radius r "exists" for the shader out to sqrt(r^2 + 6e-7 D^2) at worst.  Every primitive's bounding radius is therefore
+ * grown to sqrt(r^2 + 2^-18 S^2) + 2^-16 S, S = the scene's scale (2 x the diagonal of everything bounded, origin
+ * included), which covers every ray that starts within S of the primitives.  Rays from farther away exist -- a path
+ * that hit the infinite ground plane near the horizon and bounces back -- and for them the shader's spheres are
+ * mostly rounding noise (tests/bvh_check.cpp: hits units away from the geometry at D = 5000); pt_bvh_traverse
+ * inflates every box per ray by 2^-9 (D - S) for those (header: centre and radius of the bounded set).
+ * With both, the tree returns bit for bit what the in-order scan returns (tests/test_bvh.py on the host,
+ * tests/test_gpu_parity.py::test_bvh_* on the GPU against the oracle's scan).
  */
 #include <algorithm>
 #include <string.h>
@@ -89,7 +92,7 @@ struct Builder {
 
 int pt_bvh_bounded_prims(const PtDevScene* sc) { return sc->nSpheres + sc->nBoxes + sc->nLenses + sc->nCyclides; }
 
-/* blob = (n - 1) nodes, then sc->pool[0 .. offSdfs) rounded up to a multiple of 4 floats */
+/* blob = header, (n - 1) nodes, then sc->pool[0 .. offSdfs) rounded up to a multiple of 4 floats */
 int pt_bvh_build(const PtDevScene* sc, std::vector<float>* blob, std::string* err) {
     const int n = pt_bvh_bounded_prims(sc);
     if (n < 2 || n > PT_BVH_MAX_PRIMS) {
@@ -139,7 +142,7 @@ int pt_bvh_build(const PtDevScene* sc, std::vector<float>* blob, std::string* er
         grow(sdfs[i].px, sdfs[i].py, sdfs[i].pz, 0.5f * fmaxf(fmaxf(fabsf(sdfs[i].sx), fabsf(sdfs[i].sy)), fabsf(sdfs[i].sz)));
     for (int i = 0; i < sc->nPlanes; i++) grow(0.0f, planes[i].py, 0.0f, 0.0f);
     const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
-    const float S = 4.0f * sqrtf(dx * dx + dy * dy + dz * dz);
+    const float S = 2.0f * sqrtf(dx * dx + dy * dy + dz * dz);
     if (!(S < 1e18f)) {
         if (err) *err = "pt_bvh_build: scene extent is not finite";
         return PT_ERR_ARG;
@@ -147,7 +150,7 @@ int pt_bvh_build(const PtDevScene* sc, std::vector<float>* blob, std::string* er
 
     Builder B;
     for (const Ball& b : balls) {
-        const float r = sqrtf(b.r * b.r + 1.9073486e-6f * S * S) + 1.5258789e-5f * S; /* 2^-19, 2^-16 */
+        const float r = sqrtf(b.r * b.r + PT_BVH_KAPPA * S * S) + 1.5258789e-5f * S; /* + 2^-16 S */
         Prim p;
         const float c[3] = {b.x, b.y, b.z};
         for (int k = 0; k < 3; k++) { p.lo[k] = c[k] - r; p.hi[k] = c[k] + r; p.c[k] = c[k]; }
@@ -163,7 +166,17 @@ int pt_bvh_build(const PtDevScene* sc, std::vector<float>* blob, std::string* er
         return PT_ERR_ARG;
     }
     const int poolFloats = (sc->offSdfs + 3) & ~3;
-    blob->assign(B.nodes.begin(), B.nodes.end());
+    /* header: centre and radius of everything bounded (for the far-origin inflation of pt_bvh_traverse) */
+    float blo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (const Ball& b : balls) {
+        const float c[3] = {b.x, b.y, b.z};
+        for (int k = 0; k < 3; k++) { blo[k] = std::min(blo[k], c[k] - b.r); bhi[k] = std::max(bhi[k], c[k] + b.r); }
+    }
+    const float C[3] = {0.5f * (blo[0] + bhi[0]), 0.5f * (blo[1] + bhi[1]), 0.5f * (blo[2] + bhi[2])};
+    const float ex = bhi[0] - blo[0], ey = bhi[1] - blo[1], ez = bhi[2] - blo[2];
+    const float R = 0.5f * sqrtf(ex * ex + ey * ey + ez * ez);
+    blob->assign({C[0], C[1], C[2], R - S});
+    blob->insert(blob->end(), B.nodes.begin(), B.nodes.end());
     blob->insert(blob->end(), sc->pool, sc->pool + poolFloats);
     return PT_OK;
 }

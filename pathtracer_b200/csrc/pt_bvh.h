@@ -12,9 +12,11 @@
  * Planes are infinite and stay outside the tree (scanned first, in order).
  *
  * Layout (built on the host by pt_bvh.cpp, appended to the device copy of the uniform block at float offset
- * PT_BVH_UBO_OFF): n-1 inner nodes of 64 bytes holding BOTH children's boxes, then a copy of the PtDevScene record
- * pool (per-lane primitive indices diverge, and divergent constant-bank reads serialise; from global memory the
- * records are __ldg'd as float4 and stay in L1).
+ * PT_BVH_UBO_OFF): a 16-byte header, n-1 inner nodes of 64 bytes holding BOTH children's boxes, then a copy of the
+ * PtDevScene record pool (per-lane primitive indices diverge, and divergent constant-bank reads serialise; from
+ * global memory the records are __ldg'd as float4 and stay in L1).
+ *      float4 header = (C.x, C.y, C.z, R - S)   centre and radius of everything bounded; S = the scale the static
+ *                                               padding of the boxes covers (pt_bvh.cpp)
  *      float4 a = (c0.min.x, c0.min.y, c0.min.z, c0.max.x)
  *      float4 b = (c0.max.y, c0.max.z, c1.min.x, c1.min.y)
  *      float4 c = (c1.min.z, c1.max.x, c1.max.y, c1.max.z)
@@ -27,11 +29,17 @@
 #include "pt_dev_scene.h"
 
 #define PT_BVH_UBO_OFF 4100      /* float offset inside the device ubo buffer: 16 400 B, 16-byte aligned */
+#define PT_BVH_HEADER_FLOATS 4
 #define PT_BVH_NODE_FLOATS 16
+/* fp32 noise of SphereIntersection's `b*b - 4*c`, relative to D^2 (D = distance of the ray origin): <= 6e-7 worst case
+ * (three roundings in each dot product).  tests/bvh_check.cpp sees the first tree/scan mismatches at 2^-21 = 4.8e-7
+ * (1 in 10^7 rays, D = 68 000) and none at 2^-20; 2^-18 = 3.8e-6 keeps a factor 6 over the bound. */
+#define PT_BVH_KAPPA 3.8146973e-6f
+#define PT_BVH_SQRT_KAPPA 1.953125e-3f
 #define PT_BVH_STACK 32          /* the builder bounds the depth at PT_BVH_MAX_DEPTH */
 #define PT_BVH_MAX_DEPTH 28
 #define PT_BVH_MAX_PRIMS 256     /* > the 170 spheres the uniform block can describe */
-#define PT_BVH_MAX_FLOATS (PT_BVH_NODE_FLOATS * PT_BVH_MAX_PRIMS + PT_DEV_POOL_FLOATS + 4)
+#define PT_BVH_MAX_FLOATS (PT_BVH_HEADER_FLOATS + PT_BVH_NODE_FLOATS * PT_BVH_MAX_PRIMS + PT_DEV_POOL_FLOATS + 4)
 #define PT_BVH_DEFAULT_MIN_PRIMS 12 /* bounded primitives from which the tree replaces the brute-force scan */
 
 enum { PT_BVH_SPHERE = 0, PT_BVH_BOX = 1, PT_BVH_LENS = 2, PT_BVH_CYCLIDE = 3 };
@@ -65,20 +73,32 @@ PT_BVH_HD int pt_bvh_float_as_int(float f) {
 }
 
 /* ray / box slabs; fminf/fmaxf drop the NaN of 0 * inf (origin on a slab plane, direction parallel to it) */
-PT_BVH_HD void pt_bvh_slab(float lox, float loy, float loz, float hix, float hiy, float hiz, float ox, float oy, float oz,
-                           float ix, float iy, float iz, float& tn, float& tf) {
-    const float ax = (lox - ox) * ix, bx = (hix - ox) * ix;
-    const float ay = (loy - oy) * iy, by = (hiy - oy) * iy;
-    const float az = (loz - oz) * iz, bz = (hiz - oz) * iz;
+PT_BVH_HD void pt_bvh_slab(float lox, float loy, float loz, float hix, float hiy, float hiz, float oxl, float oyl, float ozl,
+                           float oxh, float oyh, float ozh, float ix, float iy, float iz, float& tn, float& tf) {
+    const float ax = (lox - oxl) * ix, bx = (hix - oxh) * ix;
+    const float ay = (loy - oyl) * iy, by = (hiy - oyh) * iy;
+    const float az = (loz - ozl) * iz, bz = (hiz - ozh) * iz;
     tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
     tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
 }
 
-/* Walks the tree for the ray (o, d); calls leaf(ref) with ref = (type << 16) | index for every primitive whose padded
- * box the ray enters no later than tBest.  leaf() is expected to shrink tBest (it aliases the hit record's t). */
+/* Walks the tree (bvh = header, nodes) for the ray (o, d); calls leaf(ref) with ref = (type << 16) | index for every
+ * primitive whose padded box the ray enters no later than tBest.  leaf() is expected to shrink tBest (it aliases the
+ * hit record's t).
+ * The static padding of the boxes covers ray origins up to S from the primitives.  A ray that starts farther away --
+ * off an infinite plane, toward the horizon -- sees primitives whose quadratic is mostly rounding noise (a sphere
+ * "is" wherever b*b - 4*c happens to come out non-negative, units off at D = 5000); for it every box is inflated by
+ * e = sqrt(kappa) * (D - S), which bounds the growth of that noise band (d/dD of sqrt(r^2 + kappa D^2) <= sqrt(kappa)).
+ * The inflation is folded into the ray origin per axis side, so the slab test costs the same. */
 template <class Leaf>
-PT_BVH_HD void pt_bvh_traverse(const float* nodes, float ox, float oy, float oz, float dx, float dy, float dz,
+PT_BVH_HD void pt_bvh_traverse(const float* bvh, float ox, float oy, float oz, float dx, float dy, float dz,
                                const float& tBest, Leaf leaf) {
+    const PtBvhF4 hdr = pt_bvh_load4(bvh, 0);
+    const float* nodes = bvh + PT_BVH_HEADER_FLOATS;
+    const float cx = ox - hdr.x, cy = oy - hdr.y, cz = oz - hdr.z;
+    const float infl = PT_BVH_SQRT_KAPPA * fmaxf(sqrtf(cx * cx + cy * cy + cz * cz) + hdr.w, 0.0f);
+    const float oxl = ox + infl, oyl = oy + infl, ozl = oz + infl; /* lo - (o + e) = (lo - e) - o */
+    const float oxh = ox - infl, oyh = oy - infl, ozh = oz - infl;
     const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
     int sref[PT_BVH_STACK];
     float stn[PT_BVH_STACK];
@@ -89,8 +109,8 @@ PT_BVH_HD void pt_bvh_traverse(const float* nodes, float ox, float oy, float oz,
             const PtBvhF4 a = pt_bvh_load4(nodes, 4 * cur), b = pt_bvh_load4(nodes, 4 * cur + 1),
                           c = pt_bvh_load4(nodes, 4 * cur + 2), d = pt_bvh_load4(nodes, 4 * cur + 3);
             float n0, f0, n1, f1;
-            pt_bvh_slab(a.x, a.y, a.z, a.w, b.x, b.y, ox, oy, oz, ix, iy, iz, n0, f0);
-            pt_bvh_slab(b.z, b.w, c.x, c.y, c.z, c.w, ox, oy, oz, ix, iy, iz, n1, f1);
+            pt_bvh_slab(a.x, a.y, a.z, a.w, b.x, b.y, oxl, oyl, ozl, oxh, oyh, ozh, ix, iy, iz, n0, f0);
+            pt_bvh_slab(b.z, b.w, c.x, c.y, c.z, c.w, oxl, oyl, ozl, oxh, oyh, ozh, ix, iy, iz, n1, f1);
             const bool h0 = (n0 <= f0) && (f0 >= 0.0f) && (n0 <= tBest);
             const bool h1 = (n1 <= f1) && (f1 >= 0.0f) && (n1 <= tBest);
             const int r0 = pt_bvh_float_as_int(d.x), r1 = pt_bvh_float_as_int(d.y);

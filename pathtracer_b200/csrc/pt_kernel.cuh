@@ -721,10 +721,10 @@ PT_DEV void IntersectionAnalytic(const Ctx& c, const Ray& ray, Hit& h, const boo
     /* planes (unbounded) in order, then the tree over everything else; the tie rule makes the order irrelevant */
     const int nSb = PT_N_SPHERES(c), nPb = PT_N_PLANES(c), nBb = PT_N_BOXES(c), nLb = PT_N_LENSES(c), nCb = PT_N_CYCLIDES(c);
     for (int i = 0; i < nPb; i++) PlaneIntersection(ray, reinterpret_cast<const PtDevPlane*>(sc.pool + PT_OFF_PLANES(sc))[i], nSb + i, h, kShadow);
-    const float* nodes = c.ubo + PT_BVH_UBO_OFF;
-    const float* recs = nodes + PT_BVH_NODE_FLOATS * (nSb + nBb + nLb + nCb - 1); /* the pool's copy in global memory */
+    const float* bvh = c.ubo + PT_BVH_UBO_OFF;
+    const float* recs = bvh + PT_BVH_HEADER_FLOATS + PT_BVH_NODE_FLOATS * (nSb + nBb + nLb + nCb - 1); /* the pool's copy in global memory */
     const int offB = PT_OFF_BOXES(sc), offL = PT_OFF_LENSES(sc), offC = PT_OFF_CYCLIDES(sc);
-    pt_bvh_traverse(nodes, ray.origin.x, ray.origin.y, ray.origin.z, ray.dir.x, ray.dir.y, ray.dir.z, h.t, [&](int ref) {
+    pt_bvh_traverse(bvh, ray.origin.x, ray.origin.y, ray.origin.z, ray.dir.x, ray.dir.y, ray.dir.z, h.t, [&](int ref) {
         const int type = ref >> 16, i = ref & 0xffff;
         if (type == PT_BVH_SPHERE) {
             const PtDevSphere o = LoadRecord<PtDevSphere>(recs + 8 * i);

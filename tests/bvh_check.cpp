@@ -7,7 +7,8 @@
  * gives the strict kernels' rounding); boxes, lenses and cyclides are stood in for by the sphere BoundingSphere()
  * culls them with, which is what decides whether their intersection routine runs at all.
  *
- * usage: bvh_check <ubo.bin> <n_rays> <seed> <camx> <camy> <camz>     prints "rays N mismatches M visits V nodes K"
+ * usage: bvh_check <ubo.bin> <n_rays> <seed> <camx> <camy> <camz>     prints "rays N mismatches M visits V visits_near V2 prims K"
+ * (leaf tests per ray: all rays / rays that start within the scene's scale)
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -63,7 +64,7 @@ int main(int argc, char** argv) {
     std::vector<float> blob;
     if (pt_bvh_build(&sc, &blob, &err) != PT_OK) { fprintf(stderr, "build: %s\n", err.c_str()); return 2; }
     const int nPrims = pt_bvh_bounded_prims(&sc);
-    const float* nodes = blob.data();
+    const float* nodes = blob.data() + PT_BVH_HEADER_FLOATS;
     const float* recs = nodes + PT_BVH_NODE_FLOATS * (nPrims - 1);
     if (memcmp(recs, sc.pool, sizeof(float) * sc.offSdfs) != 0) { fprintf(stderr, "record copy differs from the pool\n"); return 1; }
 
@@ -99,11 +100,11 @@ int main(int argc, char** argv) {
     for (int i = 0; i < nPrims; i++)
         if (seen[i] != 1) { fprintf(stderr, "primitive %d referenced %d times\n", i, seen[i]); return 1; }
 
-    long mismatches = 0, visits = 0;
+    long mismatches = 0, visits = 0, visitsNear = 0, nNear = 0;
     float ro[3], rd[3];
     for (long r = 0; r < nRays; r++) {
         const Ball& target = balls[(size_t)(rnd() * (float)balls.size()) % balls.size()];
-        const int kind = (int)(r % 4);
+        const int kind = (int)(r % 5);
         if (kind == 0) { /* primary-like: from the camera toward a point near a primitive */
             memcpy(ro, cam, sizeof ro);
         } else if (kind == 1) { /* secondary: from a point on some primitive's surface */
@@ -113,6 +114,9 @@ int main(int argc, char** argv) {
             ro[0] = from.x + u[0] / len * rad; ro[1] = from.y + u[1] / len * rad; ro[2] = from.z + u[2] / len * rad;
         } else if (kind == 2) { /* from a point on the ground plane, well outside the cluster */
             ro[0] = (rnd() - 0.5f) * 60.0f; ro[1] = 0.0f; ro[2] = (rnd() - 0.5f) * 60.0f;
+        } else if (kind == 4) { /* from a far point of the ground plane (the horizon of a rendered frame): 1e2 .. 1e5 away */
+            const float dist = 100.0f * powf(10.0f, 3.0f * rnd()), phi = 6.2831853f * rnd();
+            ro[0] = dist * cosf(phi); ro[1] = 0.0f; ro[2] = dist * sinf(phi);
         } else { /* from inside a primitive */
             ro[0] = target.x; ro[1] = target.y; ro[2] = target.z;
         }
@@ -129,11 +133,13 @@ int main(int argc, char** argv) {
         float tA = 1e5f; int idA = -1;
         for (const Ball& b : balls) sphere_hit(b, ro, rd, tA, idA, false);
         float tB = 1e5f; int idB = -1;
-        pt_bvh_traverse(nodes, ro[0], ro[1], ro[2], rd[0], rd[1], rd[2], tB, [&](int ref) {
+        pt_bvh_traverse(blob.data(), ro[0], ro[1], ro[2], rd[0], rd[1], rd[2], tB, [&](int ref) {
             const int type = ref >> 16, idx = ref & 0xffff;
             visits++;
+            if (kind != 4) visitsNear++;
             sphere_hit(byType[type][idx], ro, rd, tB, idB, true);
         });
+        if (kind != 4) nNear++;
         if (memcmp(&tA, &tB, 4) != 0 || idA != idB) {
             if (mismatches < 5)
                 fprintf(stderr, "ray %ld kind %d: scan (%.9g, %d) tree (%.9g, %d) o=(%g %g %g) d=(%g %g %g)\n", r, kind, tA, idA, tB,
@@ -141,6 +147,7 @@ int main(int argc, char** argv) {
             mismatches++;
         }
     }
-    printf("rays %ld mismatches %ld visits %.3f prims %d\n", nRays, mismatches, (double)visits / (double)nRays, nPrims);
+    printf("rays %ld mismatches %ld visits %.3f visits_near %.3f prims %d\n", nRays, mismatches, (double)visits / (double)nRays,
+           (double)visitsNear / (double)(nNear > 0 ? nNear : 1), nPrims);
     return mismatches ? 1 : 0;
 }

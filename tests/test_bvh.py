@@ -46,7 +46,7 @@ def test_tree_equals_scan_on_sphere_carpets(checker, tmp_path, n, dups):
     res = run_checker(checker, tmp_path, scene, 300000, 7 + n, cam)
     assert res['mismatches'] == 0 and res['prims'] == n
     if n >= 169:
-        assert res['visits'] < 12.0, 'the tree should test a handful of the %d spheres per ray, not %.1f' % (n, res['visits'])
+        assert res['visits_near'] < 6.0, 'the tree should test a handful of the %d spheres per ray, not %.1f' % (n, res['visits_near'])
 
 
 def test_tree_equals_scan_on_a_mixed_scene(checker, tmp_path):
