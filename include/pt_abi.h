@@ -103,10 +103,10 @@ int pt_set_jit(pt_ctx* ctx, int policy);
  * (bit-identical in strict mode); profiles/ compares them per scene. */
 int pt_set_pipeline(pt_ctx* ctx, int pipeline);
 /* Closest-hit search of Intersection / LightSourceVisibilityCheck (shader.comp:862-934, 1121-1216): the reference scans
- * every primitive; from min_prims bounded primitives (spheres + boxes + lenses + cyclides; default 12, env PT_BVH_MIN)
- * libpt_cuda walks a host-built BVH instead (run-time compiled kernels only, i.e. not with jit policy 0).  Same
- * winner -- smallest t, ties to the lowest object index; bit-identical in strict mode.  min_prims <= 0 disables the
- * tree.  Takes effect at the next pt_set_scene; pt_bvh_active tells whether the current scene uses it. */
+ * every primitive; from min_prims spheres + boxes + lenses (default 12, env PT_BVH_MIN) libpt_cuda walks a host-built
+ * BVH over those instead (run-time compiled kernels only, i.e. not with jit policy 0); planes and cyclides are still
+ * scanned in order.  Same winner -- smallest t, ties to the lowest object index; bit-identical in strict mode.
+ * min_prims <= 0 disables the tree.  Takes effect at the next pt_set_scene; pt_bvh_active tells whether the current scene uses it. */
 int pt_set_bvh(pt_ctx* ctx, int min_prims);
 int pt_bvh_active(const pt_ctx* ctx);
 

@@ -30,6 +30,19 @@
 #include "pt_abi.h"
 #include "pt_math.h"
 
+#ifdef PT_ORACLE_BVH
+/* liboracle_bvh.so only: a CHECKER OF THE PRODUCT'S BVH (pathtracer_b200/csrc/pt_bvh.h, pt_bvh.cpp, which the
+ * Makefile compiles in).  The closest-hit search runs through that tree with this file's own primitive routines at
+ * the leaves; tests/test_bvh.py requires the rendered images to equal liboracle.so's (the literal in-order scan of
+ * shader.comp:862-934, 1121-1216) bit for bit.  liboracle.so itself contains none of this. */
+#include <cmath>
+#include <string>
+#include <vector>
+#include "pt_internal.h"
+#include "pt_bvh.h"
+static std::vector<float> g_bvh_blob;
+#endif
+
 namespace {
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -752,9 +765,66 @@ struct Shader {
         return boundingRadius;
     }
 
+#ifdef PT_ORACLE_BVH
+    /* Closest hit over the analytic primitives through the product's tree: planes in order, then every sphere, box
+     * and lens the traversal reaches, then the cyclides in order (not in the tree: pt_bvh.h).  Winner = smallest t,
+     * ties to the lowest object index -- the outcome of the in-order `t < hitdist` scan.  The primitive routines
+     * update on t < bound, so a lower-index candidate is offered the next float above hitdist as its bound (it then
+     * wins on t <= hitdist). */
+    void ClosestAnalyticBvh(const Ray& ray, float& hitdist, V3& normal, float& materialID, float& lightID, int& objectID) const {
+        const int nS = pt_f2i(numObjects(0)), nP = pt_f2i(numObjects(1)), nB = pt_f2i(numObjects(2)), nL = pt_f2i(numObjects(3));
+        const int offP = 6 * nS, offB = offP + 5 * nP, offL = offB + 11 * nB, offC = offL + 12 * nL;
+        for (int i = 0; i < nP; i++) {
+            Plane object;
+            UnpackPlane(object, i, offP);
+            if (PlaneIntersection(ray, object, hitdist, normal, materialID, lightID)) objectID = nS + i;
+        }
+        pt_bvh_traverse(g_bvh_blob.data(), ray.origin.x, ray.origin.y, ray.origin.z, ray.dir.x, ray.dir.y, ray.dir.z, hitdist,
+                        [&](int ref) {
+            const int type = ref >> 16, i = ref & 0xffff;
+            const int base = (type == PT_BVH_SPHERE) ? 0 : (type == PT_BVH_BOX) ? nS + nP : nS + nP + nB;
+            const int id = base + i;
+            float bound = (id < objectID) ? std::nextafterf(hitdist, 3.0e38f) : hitdist;
+            bool hit = false;
+            if (type == PT_BVH_SPHERE) {
+                Sphere object;
+                UnpackSphere(object, i);
+                hit = SphereIntersection(ray, object, bound, normal, materialID, lightID);
+            } else if (type == PT_BVH_BOX) {
+                Box object;
+                UnpackBox(object, i, offB);
+                if (BoundingSphere(ray, object.pos, 0.25f * dot(object.size, object.size)))
+                    hit = BoxIntersection(ray, object, bound, normal, materialID, lightID);
+            } else {
+                Lens object;
+                UnpackLens(object, i, offL);
+                int isOutside = 1;
+                if (BoundingSphere(ray, object.pos, LensBoundingRadius2(object)))
+                    hit = LensIntersection(ray, object, bound, normal, isOutside, materialID, lightID);
+            }
+            if (hit) { hitdist = bound; objectID = id; }
+        });
+        for (int i = 0; (float)i < numObjects(4); i++) {
+            Cyclide object;
+            UnpackCyclide(object, i, offC);
+            if (!BoundingSphere(ray, object.pos, object.brad)) continue;
+            if (DupinCyclide(ray, object, hitdist, normal, materialID, lightID)) objectID = nS + nP + nB + nL + i;
+        }
+    }
+#endif
+
     /* shader.comp:862-934 */
     float Intersection(const Ray& ray, V3& normal, float& materialID, float& lightID) const {
         CNT(C_RAYS_PATH, 1);
+#ifdef PT_ORACLE_BVH
+        if (!g_bvh_blob.empty()) {
+            float hd = MAXDIST;
+            int objectID = -1;
+            ClosestAnalyticBvh(ray, hd, normal, materialID, lightID, objectID);
+            SphereTracing(ray, hd, normal, materialID, lightID);
+            return hd;
+        }
+#endif
         float hitdist = MAXDIST;
         int offset = 0;
         for (int i = 0; (float)i < numObjects(0); i++) {
@@ -932,6 +1002,13 @@ struct Shader {
         float materialID = 0.0f;
         float lightID = -1.0f;
         int objectID = -1;
+#ifdef PT_ORACLE_BVH
+        if (!g_bvh_blob.empty()) {
+            ClosestAnalyticBvh(ray, hitdist, normal, materialID, lightID, objectID);
+            if (SphereTracing(ray, hitdist, normal, materialID, lightID)) objectID = -1;
+            return objectID == lightObjectID;
+        }
+#endif
         int offset = 0;
         int objectOffset = 0;
         for (int i = 0; (float)i < numObjects(0); i++) {
@@ -1263,6 +1340,20 @@ int oracle_load_sdf(const char* so_path) {
     g_sdfmat_fn = (sdf_dispatch_fn)dlsym(g_sdf_handle, "oracle_SDFMATERIAL");
     return (g_sdf_fn && g_sdfmat_fn) ? 0 : -2;
 }
+
+#ifdef PT_ORACLE_BVH
+/* Build the product's tree for this block (exactly what pt_set_scene does) and route the closest-hit search through
+ * it; ubo == NULL goes back to the in-order scan.  Returns the number of floats of the blob, < 0 on error. */
+int oracle_bvh_build(const pt_ubo* ubo) {
+    g_bvh_blob.clear();
+    if (!ubo) return 0;
+    static PtDevScene sc;
+    std::string err;
+    if (pt_prepare_scene(ubo, &sc, &err) != PT_OK) { fprintf(stderr, "oracle_bvh_build: %s\n", err.c_str()); return -1; }
+    if (pt_bvh_build(&sc, &g_bvh_blob, &err) != PT_OK) { fprintf(stderr, "oracle_bvh_build: %s\n", err.c_str()); g_bvh_blob.clear(); return -1; }
+    return (int)g_bvh_blob.size();
+}
+#endif
 
 void oracle_set_threads(int n) { g_threads = n; }
 int oracle_max_threads(void) {

@@ -14,8 +14,8 @@ def build():
     subprocess.run(['make', '-s', '-C', HERE], check=True)
 
 
-def lib(count=False):
-    name = 'liboracle_count.so' if count else 'liboracle.so'
+def lib(count=False, bvh=False):
+    name = 'liboracle_bvh.so' if bvh else ('liboracle_count.so' if count else 'liboracle.so')
     if name not in _libs:
         path = os.path.join(HERE, '_build', name)
         if not os.path.exists(path):
@@ -40,6 +40,8 @@ def lib(count=False):
         L.oracle_samples.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.oracle_dispatch_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.oracle_load_sdf.argtypes = [C.c_char_p]
+        if bvh:
+            L.oracle_bvh_build.argtypes = [C.c_void_p]
         _libs[name] = L
     return _libs[name]
 
@@ -51,8 +53,11 @@ def _p(a):
 class Oracle:
     """One scene bound to the CPU oracle. `ubo` float32[4097], `sdf_sources` list of GLSL strings."""
 
-    def __init__(self, ubo, sdf_sources=(), count=False, threads=0):
-        self.L = lib(count)
+    def __init__(self, ubo, sdf_sources=(), count=False, threads=0, bvh=False):
+        """bvh=True: liboracle_bvh.so, the checker that routes the closest-hit search through the PRODUCT's BVH
+        (pt_bvh.cpp) with the oracle's primitives at the leaves; must render what the plain oracle renders."""
+        self.L = lib(count, bvh)
+        self.bvh = bvh
         self.count = count
         self.ubo = np.ascontiguousarray(ubo, dtype=np.float32)
         assert self.ubo.size == pack.UBO_FLOATS
@@ -63,6 +68,8 @@ class Oracle:
         if self.L.oracle_load_sdf(self.sdf_so.encode()) != 0:
             raise RuntimeError('oracle: cannot load SDF dispatchers %s' % self.sdf_so)
         self.L.oracle_set_threads(int(self.threads))
+        if self.bvh and self.L.oracle_bvh_build(_p(self.ubo)) <= 0:
+            raise RuntimeError('oracle: cannot build the BVH for this scene')
 
     def dispatch(self, params, image, row_start=0, row_step=1):
         """One vkCmdDispatch: image (H,W,4) float32 is read-modify-written. Returns counters dict if count.

@@ -90,9 +90,10 @@ struct Builder {
 
 }  // namespace
 
-int pt_bvh_bounded_prims(const PtDevScene* sc) { return sc->nSpheres + sc->nBoxes + sc->nLenses + sc->nCyclides; }
+/* what goes into the tree: spheres, boxes, lenses (planes are unbounded; cyclides: see pt_bvh.h) */
+int pt_bvh_bounded_prims(const PtDevScene* sc) { return sc->nSpheres + sc->nBoxes + sc->nLenses; }
 
-/* blob = header, (n - 1) nodes, then sc->pool[0 .. offSdfs) rounded up to a multiple of 4 floats */
+/* blob = header, (n - 1) nodes, then sc->pool[0 .. offCyclides) rounded up to a multiple of 4 floats */
 int pt_bvh_build(const PtDevScene* sc, std::vector<float>* blob, std::string* err) {
     const int n = pt_bvh_bounded_prims(sc);
     if (n < 2 || n > PT_BVH_MAX_PRIMS) {
@@ -103,7 +104,6 @@ int pt_bvh_build(const PtDevScene* sc, std::vector<float>* blob, std::string* er
     const PtDevPlane* planes = reinterpret_cast<const PtDevPlane*>(sc->pool + sc->offPlanes);
     const PtDevBox* boxes = reinterpret_cast<const PtDevBox*>(sc->pool + sc->offBoxes);
     const PtDevLens* lenses = reinterpret_cast<const PtDevLens*>(sc->pool + sc->offLenses);
-    const PtDevCyclide* cyclides = reinterpret_cast<const PtDevCyclide*>(sc->pool + sc->offCyclides);
     const PtDevSdf* sdfs = reinterpret_cast<const PtDevSdf*>(sc->pool + sc->offSdfs);
 
     struct Ball { float x, y, z, r; int ref; };
@@ -122,15 +122,7 @@ int pt_bvh_build(const PtDevScene* sc, std::vector<float>* blob, std::string* er
         const float r = fmaxf(sqrtf(fmaxf(o.bound2, 0.0f)), sqrtf(axial * axial + across2));
         balls.push_back({o.px, o.py, o.pz, r, (PT_BVH_LENS << 16) | i});
     }
-    for (int i = 0; i < sc->nCyclides; i++) {
-        /* brad (packed squared, host:3723-3725) is the scene author's bound; also cover the surface itself:
-         * |p| <= |a| + |c| + |d| in the unit frame, times the largest scale */
-        const PtDevCyclide& o = cyclides[i];
-        const float ms = fmaxf(fmaxf(fabsf(o.sx), fabsf(o.sy)), fabsf(o.sz));
-        const float r = fmaxf(sqrtf(fmaxf(o.brad, 0.0f)), (fabsf(o.a) + fabsf(o.b) + fabsf(o.c) + fabsf(o.d)) * ms);
-        balls.push_back({o.px, o.py, o.pz, r, (PT_BVH_CYCLIDE << 16) | i});
-    }
-
+    const size_t firstLens = balls.size() - (size_t)sc->nLenses;
     /* scene scale: everything bounded, the SDF boxes, the plane heights and the origin */
     float lo[3] = {0.0f, 0.0f, 0.0f}, hi[3] = {0.0f, 0.0f, 0.0f};
     auto grow = [&](float x, float y, float z, float r) {
@@ -149,8 +141,12 @@ int pt_bvh_build(const PtDevScene* sc, std::vector<float>* blob, std::string* er
     }
 
     Builder B;
-    for (const Ball& b : balls) {
-        const float r = sqrtf(b.r * b.r + PT_BVH_KAPPA * S * S) + 1.5258789e-5f * S; /* + 2^-16 S */
+    for (size_t k = 0; k < balls.size(); k++) {
+        const Ball& b = balls[k];
+        /* spheres (and the culling spheres of boxes) carry the noise of a quadratic of radius r; a lens cap is cut
+         * from a sphere of radius 2f >> r, whose grazing hits wander by sqrt(kappa) S along the ray: linear padding */
+        const float r = (k >= firstLens) ? b.r + PT_BVH_SQRT_KAPPA * S + 1.5258789e-5f * S
+                                         : sqrtf(b.r * b.r + PT_BVH_KAPPA * S * S) + 1.5258789e-5f * S; /* + 2^-16 S */
         Prim p;
         const float c[3] = {b.x, b.y, b.z};
         for (int k = 0; k < 3; k++) { p.lo[k] = c[k] - r; p.hi[k] = c[k] + r; p.c[k] = c[k]; }
@@ -165,7 +161,7 @@ int pt_bvh_build(const PtDevScene* sc, std::vector<float>* blob, std::string* er
         if (err) *err = "pt_bvh_build: internal error";
         return PT_ERR_ARG;
     }
-    const int poolFloats = (sc->offSdfs + 3) & ~3;
+    const int poolFloats = (sc->offCyclides + 3) & ~3; /* spheres, planes, boxes, lenses */
     /* header: centre and radius of everything bounded (for the far-origin inflation of pt_bvh_traverse) */
     float blo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
     for (const Ball& b : balls) {

@@ -1,4 +1,4 @@
-/* pt_bvh.h -- bounding-volume hierarchy over the scene's bounded primitives (spheres, boxes, lenses, cyclides).
+/* pt_bvh.h -- bounding-volume hierarchy over the scene's spheres, boxes and lenses.
  *
  * The reference finds the closest hit by brute force over every primitive (Intersection shader.comp:862-934 and
  * LightSourceVisibilityCheck 1121-1216), which is right for its shipped scenes (<= 8 primitives) and quadratic
@@ -9,7 +9,11 @@
  *     `if (t < hit.t)` scan yields, so the visiting order cannot change the result;
  *   - node boxes are padded (pt_bvh.cpp) by more than the fp32 noise of the primitives' own quadratics, so culling
  *     a node never removes a primitive the brute-force scan would have reported.
- * Planes are infinite and stay outside the tree (scanned first, in order).
+ * Planes are infinite and stay outside the tree (scanned first, in order).  So do the Dupin cyclides (scanned last, in
+ * order): the reference's quartic solver (shader.comp:505-541) returns spurious roots anywhere along a ray that merely
+ * passes a cyclide's bounding sphere -- "hits" in mid-air, many units from the surface, which the in-order scan
+ * reports and which no box around the surface can anticipate (found by tests/test_bvh.py's oracle-through-the-tree
+ * check).  They are the rarest and by far the costliest primitive, behind a bounding-sphere cull of their own.
  *
  * Layout (built on the host by pt_bvh.cpp, appended to the device copy of the uniform block at float offset
  * PT_BVH_UBO_OFF): a 16-byte header, n-1 inner nodes of 64 bytes holding BOTH children's boxes, then a copy of the
@@ -40,9 +44,12 @@
 #define PT_BVH_MAX_DEPTH 28
 #define PT_BVH_MAX_PRIMS 256     /* > the 170 spheres the uniform block can describe */
 #define PT_BVH_MAX_FLOATS (PT_BVH_HEADER_FLOATS + PT_BVH_NODE_FLOATS * PT_BVH_MAX_PRIMS + PT_DEV_POOL_FLOATS + 4)
-#define PT_BVH_DEFAULT_MIN_PRIMS 12 /* bounded primitives from which the tree replaces the brute-force scan */
+#ifndef PT_BVH_WHILE_WHILE
+#define PT_BVH_WHILE_WHILE 0     /* loop shape of pt_bvh_traverse; A/B on B200: profiles/r01_bvh */
+#endif
+#define PT_BVH_DEFAULT_MIN_PRIMS 12 /* spheres + boxes + lenses from which the tree replaces the brute-force scan */
 
-enum { PT_BVH_SPHERE = 0, PT_BVH_BOX = 1, PT_BVH_LENS = 2, PT_BVH_CYCLIDE = 3 };
+enum { PT_BVH_SPHERE = 0, PT_BVH_BOX = 1, PT_BVH_LENS = 2 };
 
 #if defined(__CUDACC__) || defined(__CUDACC_RTC__)
 #define PT_BVH_HD __host__ __device__ __forceinline__
@@ -104,6 +111,54 @@ PT_BVH_HD void pt_bvh_traverse(const float* bvh, float ox, float oy, float oz, f
     float stn[PT_BVH_STACK];
     int sp = 0;
     int cur = 0;
+#if PT_BVH_WHILE_WHILE
+    /* "while-while": every lane first descends to its next leaf (the node code runs with all traversing lanes), then
+     * the leaves are tested together (the primitive code runs with all lanes that found one) */
+    bool done = false;
+    while (!done) {
+        while (cur >= 0) {
+            const PtBvhF4 a = pt_bvh_load4(nodes, 4 * cur), b = pt_bvh_load4(nodes, 4 * cur + 1),
+                          c = pt_bvh_load4(nodes, 4 * cur + 2), d = pt_bvh_load4(nodes, 4 * cur + 3);
+            float n0, f0, n1, f1;
+            pt_bvh_slab(a.x, a.y, a.z, a.w, b.x, b.y, oxl, oyl, ozl, oxh, oyh, ozh, ix, iy, iz, n0, f0);
+            pt_bvh_slab(b.z, b.w, c.x, c.y, c.z, c.w, oxl, oyl, ozl, oxh, oyh, ozh, ix, iy, iz, n1, f1);
+            const bool h0 = (n0 <= f0) && (f0 >= 0.0f) && (n0 <= tBest);
+            const bool h1 = (n1 <= f1) && (f1 >= 0.0f) && (n1 <= tBest);
+            const int r0 = pt_bvh_float_as_int(d.x), r1 = pt_bvh_float_as_int(d.y);
+            if (h0 && h1) {
+                const bool firstIs0 = n0 <= n1;
+                if (sp < PT_BVH_STACK) {
+                    sref[sp] = firstIs0 ? r1 : r0;
+                    stn[sp] = firstIs0 ? n1 : n0;
+                    sp++;
+                }
+                cur = firstIs0 ? r0 : r1;
+            } else if (h0) {
+                cur = r0;
+            } else if (h1) {
+                cur = r1;
+            } else {
+                float tn;
+                do {
+                    if (sp == 0) { done = true; cur = -1; break; }
+                    --sp;
+                    cur = sref[sp];
+                    tn = stn[sp];
+                } while (tn > tBest);
+            }
+        }
+        if (!done) {
+            leaf(~cur);
+            float tn;
+            do {
+                if (sp == 0) { done = true; break; }
+                --sp;
+                cur = sref[sp];
+                tn = stn[sp];
+            } while (tn > tBest);
+        }
+    }
+#else
     for (;;) {
         if (cur >= 0) {
             const PtBvhF4 a = pt_bvh_load4(nodes, 4 * cur), b = pt_bvh_load4(nodes, 4 * cur + 1),
@@ -137,6 +192,7 @@ PT_BVH_HD void pt_bvh_traverse(const float* bvh, float ox, float oy, float oz, f
             tn = stn[sp];
         } while (tn > tBest);
     }
+#endif
 }
 
 #endif /* PT_BVH_H */

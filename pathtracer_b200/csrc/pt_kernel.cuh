@@ -718,12 +718,15 @@ PT_DEV void IntersectionAnalytic(const Ctx& c, const Ray& ray, Hit& h, const boo
         h.lightID = -1.0f;
     }
 #if PT_BVH
-    /* planes (unbounded) in order, then the tree over everything else; the tie rule makes the order irrelevant */
-    const int nSb = PT_N_SPHERES(c), nPb = PT_N_PLANES(c), nBb = PT_N_BOXES(c), nLb = PT_N_LENSES(c), nCb = PT_N_CYCLIDES(c);
+    /* planes (unbounded) in order, then the tree over spheres, boxes and lenses -- the tie rule makes the visiting
+     * order irrelevant -- then the cyclides in order like the reference: they have the highest indices, so the plain
+     * `t < hit.t` is still the right rule, and they cannot live in the tree because the quartic solver reports
+     * spurious roots anywhere along a ray that merely passes the bounding sphere (pt_bvh.cpp). */
+    const int nSb = PT_N_SPHERES(c), nPb = PT_N_PLANES(c), nBb = PT_N_BOXES(c), nLb = PT_N_LENSES(c);
     for (int i = 0; i < nPb; i++) PlaneIntersection(ray, reinterpret_cast<const PtDevPlane*>(sc.pool + PT_OFF_PLANES(sc))[i], nSb + i, h, kShadow);
     const float* bvh = c.ubo + PT_BVH_UBO_OFF;
-    const float* recs = bvh + PT_BVH_HEADER_FLOATS + PT_BVH_NODE_FLOATS * (nSb + nBb + nLb + nCb - 1); /* the pool's copy in global memory */
-    const int offB = PT_OFF_BOXES(sc), offL = PT_OFF_LENSES(sc), offC = PT_OFF_CYCLIDES(sc);
+    const float* recs = bvh + PT_BVH_HEADER_FLOATS + PT_BVH_NODE_FLOATS * (nSb + nBb + nLb - 1); /* the pool's copy in global memory */
+    const int offB = PT_OFF_BOXES(sc), offL = PT_OFF_LENSES(sc);
     pt_bvh_traverse(bvh, ray.origin.x, ray.origin.y, ray.origin.z, ray.dir.x, ray.dir.y, ray.dir.z, h.t, [&](int ref) {
         const int type = ref >> 16, i = ref & 0xffff;
         if (type == PT_BVH_SPHERE) {
@@ -734,7 +737,7 @@ PT_DEV void IntersectionAnalytic(const Ctx& c, const Ray& ray, Hit& h, const boo
                 const PtDevBox o = LoadRecord<PtDevBox>(recs + offB + 20 * i);
                 if (BoundingSphere(ray, o.px, o.py, o.pz, o.bound2)) BoxIntersection(ray, o, nSb + nPb + i, h, kShadow, true);
             }
-        } else if (type == PT_BVH_LENS) {
+        } else {
             if (nLb > 0) {
                 const PtDevLens o = LoadRecord<PtDevLens>(recs + offL + 20 * i);
                 if (BoundingSphere(ray, o.px, o.py, o.pz, o.bound2)) {
@@ -742,13 +745,9 @@ PT_DEV void IntersectionAnalytic(const Ctx& c, const Ray& ray, Hit& h, const boo
                     LensIntersection(ray, o, nSb + nPb + nBb + i, h, isOutside, kShadow, true);
                 }
             }
-        } else {
-            if (nCb > 0) {
-                const PtDevCyclide o = LoadRecord<PtDevCyclide>(recs + offC + 24 * i);
-                if (BoundingSphere(ray, o.px, o.py, o.pz, o.brad)) DupinCyclide(ray, o, nSb + nPb + nBb + nLb + i, h, kShadow, true);
-            }
         }
     });
+    int base = nSb + nPb + nBb + nLb;
 #else
     int base = 0;
     const int nS = PT_N_SPHERES(c);
@@ -776,13 +775,13 @@ PT_DEV void IntersectionAnalytic(const Ctx& c, const Ray& ray, Hit& h, const boo
         LensIntersection(ray, o, base + i, h, isOutside, kShadow);
     }
     base += nL;
+#endif
     const int nC = PT_N_CYCLIDES(c);
     for (int i = 0; i < nC; i++) {
         const PtDevCyclide& o = reinterpret_cast<const PtDevCyclide*>(sc.pool + PT_OFF_CYCLIDES(sc))[i];
         if (!BoundingSphere(ray, o.px, o.py, o.pz, o.brad)) continue;
         DupinCyclide(ray, o, base + i, h, kShadow);
     }
-#endif
 }
 
 /* shader.comp:862-934 / 1121-1216 in one piece (used by the v1 driver) */

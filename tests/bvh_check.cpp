@@ -4,8 +4,9 @@
  * prepares the scene and builds the tree exactly as pt_set_scene does, then shoots rays and compares the closest
  * hit found through pt_bvh_traverse with the in-order brute-force scan -- (t, object index) must be identical bit
  * for bit, ties included.  Spheres use SphereIntersection's arithmetic (shader.comp:289-317; g++ -ffp-contract=off
- * gives the strict kernels' rounding); boxes, lenses and cyclides are stood in for by the sphere BoundingSphere()
- * culls them with, which is what decides whether their intersection routine runs at all.
+ * gives the strict kernels' rounding); boxes and lenses are stood in for by the sphere BoundingSphere() culls them
+ * with, which is what decides whether their intersection routine runs at all (cyclides are not in the tree; the real
+ * box / lens / cyclide routines go through the tree in tests/test_bvh.py's oracle-through-the-tree check).
  *
  * usage: bvh_check <ubo.bin> <n_rays> <seed> <camx> <camy> <camz>     prints "rays N mismatches M visits V visits_near V2 prims K"
  * (leaf tests per ray: all rays / rays that start within the scene's scale)
@@ -66,7 +67,7 @@ int main(int argc, char** argv) {
     const int nPrims = pt_bvh_bounded_prims(&sc);
     const float* nodes = blob.data() + PT_BVH_HEADER_FLOATS;
     const float* recs = nodes + PT_BVH_NODE_FLOATS * (nPrims - 1);
-    if (memcmp(recs, sc.pool, sizeof(float) * sc.offSdfs) != 0) { fprintf(stderr, "record copy differs from the pool\n"); return 1; }
+    if (memcmp(recs, sc.pool, sizeof(float) * sc.offCyclides) != 0) { fprintf(stderr, "record copy differs from the pool\n"); return 1; }
 
     /* every bounded primitive as (centre, culling radius^2, global object index), in the reference's order */
     std::vector<Ball> balls;
@@ -75,12 +76,10 @@ int main(int argc, char** argv) {
     const PtDevSphere* S = reinterpret_cast<const PtDevSphere*>(sc.pool);
     const PtDevBox* B = reinterpret_cast<const PtDevBox*>(sc.pool + sc.offBoxes);
     const PtDevLens* L = reinterpret_cast<const PtDevLens*>(sc.pool + sc.offLenses);
-    const PtDevCyclide* C = reinterpret_cast<const PtDevCyclide*>(sc.pool + sc.offCyclides);
-    std::vector<std::vector<Ball>> byType(4);
+    std::vector<std::vector<Ball>> byType(3);
     for (int i = 0; i < sc.nSpheres; i++) byType[0].push_back({S[i].px, S[i].py, S[i].pz, S[i].r2, typeBase[0] + i});
     for (int i = 0; i < sc.nBoxes; i++) byType[1].push_back({B[i].px, B[i].py, B[i].pz, B[i].bound2, typeBase[1] + i});
     for (int i = 0; i < sc.nLenses; i++) byType[2].push_back({L[i].px, L[i].py, L[i].pz, L[i].bound2, typeBase[2] + i});
-    for (int i = 0; i < sc.nCyclides; i++) byType[3].push_back({C[i].px, C[i].py, C[i].pz, C[i].brad, typeBase[3] + i});
     for (auto& v : byType) balls.insert(balls.end(), v.begin(), v.end());
 
     /* every leaf must appear exactly once */
@@ -91,7 +90,7 @@ int main(int argc, char** argv) {
             memcpy(&ref, nodes + PT_BVH_NODE_FLOATS * n + 12 + k, 4);
             if (ref < 0) {
                 const int type = (~ref) >> 16, idx = (~ref) & 0xffff;
-                if (type < 0 || type > 3 || idx >= (int)byType[type].size()) { fprintf(stderr, "bad leaf ref\n"); return 1; }
+                if (type < 0 || type > 2 || idx >= (int)byType[type].size()) { fprintf(stderr, "bad leaf ref\n"); return 1; }
                 int flat = idx;
                 for (int t = 0; t < type; t++) flat += (int)byType[t].size();
                 seen[flat]++;

@@ -1,8 +1,8 @@
 #!/bin/bash
 # BVH round, second pass: parity with the far-origin inflation, bench lines (with CPU baseline), ncu capture.
 O=gpurun_out/bvh2; mkdir -p $O gpurun_out/jd_bvh
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "bvh or capacity" > $O/pytest_bvh.log 2>&1; echo "pytest rc $?" >> $O/pytest_bvh.log
-tail -4 $O/pytest_bvh.log
+timeout 1500 python -m pytest tests -m gpu -q > $O/pytest_gpu_all.log 2>&1; echo "pytest rc $?" >> $O/pytest_gpu_all.log
+tail -4 $O/pytest_gpu_all.log
 for wl in bvh_spheres169_1080p bvh_mixed74_1080p; do
   timeout 300 python bench.py --workload $wl --steps 16 --warmup 3 > $O/bench_${wl}.json 2> $O/bench_${wl}.err
   PT_NO_UNROLL=1 timeout 300 python bench.py --workload $wl --bvh-min 0 --steps 8 --warmup 3 --no-cpu-baseline > $O/bench_${wl}_scan_rolled.json 2> $O/bench_${wl}_scan_rolled.err
