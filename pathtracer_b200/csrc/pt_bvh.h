@@ -79,12 +79,15 @@ PT_BVH_HD int pt_bvh_float_as_int(float f) {
 #endif
 }
 
-/* ray / box slabs; fminf/fmaxf drop the NaN of 0 * inf (origin on a slab plane, direction parallel to it) */
-PT_BVH_HD void pt_bvh_slab(float lox, float loy, float loz, float hix, float hiy, float hiz, float oxl, float oyl, float ozl,
-                           float oxh, float oyh, float ozh, float ix, float iy, float iz, float& tn, float& tf) {
-    const float ax = (lox - oxl) * ix, bx = (hix - oxh) * ix;
-    const float ay = (loy - oyl) * iy, by = (hiy - oyh) * iy;
-    const float az = (loz - ozl) * iz, bz = (hiz - ozh) * iz;
+/* ray / box slabs, one fused multiply-add per plane: (lo - o) / d = lo * (1/d) - o * (1/d), the second product hoisted
+ * per ray.  1/d is clamped to +-1e25 (pt_bvh_traverse) so that a direction component of 0 yields huge finite products
+ * of the right sign instead of inf - inf.  The rounding differs from the primitives' own arithmetic by ulps; the
+ * padding of the boxes is orders of magnitude larger. */
+PT_BVH_HD void pt_bvh_slab(float lox, float loy, float loz, float hix, float hiy, float hiz, float nxl, float nyl, float nzl,
+                           float nxh, float nyh, float nzh, float ix, float iy, float iz, float& tn, float& tf) {
+    const float ax = fmaf(lox, ix, nxl), bx = fmaf(hix, ix, nxh);
+    const float ay = fmaf(loy, iy, nyl), by = fmaf(hiy, iy, nyh);
+    const float az = fmaf(loz, iz, nzl), bz = fmaf(hiz, iz, nzh);
     tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
     tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
 }
@@ -104,9 +107,11 @@ PT_BVH_HD void pt_bvh_traverse(const float* bvh, float ox, float oy, float oz, f
     const float* nodes = bvh + PT_BVH_HEADER_FLOATS;
     const float cx = ox - hdr.x, cy = oy - hdr.y, cz = oz - hdr.z;
     const float infl = PT_BVH_SQRT_KAPPA * fmaxf(sqrtf(cx * cx + cy * cy + cz * cz) + hdr.w, 0.0f);
-    const float oxl = ox + infl, oyl = oy + infl, ozl = oz + infl; /* lo - (o + e) = (lo - e) - o */
-    const float oxh = ox - infl, oyh = oy - infl, ozh = oz - infl;
-    const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
+    const float ix = fminf(fmaxf(1.0f / dx, -1e25f), 1e25f), iy = fminf(fmaxf(1.0f / dy, -1e25f), 1e25f),
+                iz = fminf(fmaxf(1.0f / dz, -1e25f), 1e25f);
+    /* -(o + e) / d for the lower planes, -(o - e) / d for the upper ones: lo - (o + e) = (lo - e) - o */
+    const float oxl = -(ox + infl) * ix, oyl = -(oy + infl) * iy, ozl = -(oz + infl) * iz;
+    const float oxh = -(ox - infl) * ix, oyh = -(oy - infl) * iy, ozh = -(oz - infl) * iz;
     int sref[PT_BVH_STACK];
     float stn[PT_BVH_STACK];
     int sp = 0;

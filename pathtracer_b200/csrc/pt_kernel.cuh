@@ -28,6 +28,7 @@
  *   v2  (PT_SCHED 1)  four phases over explicit PathState, one phase per warp iteration chosen by ballot,
  *                     lanes refill themselves with their pixel's next sample   default for scenes with SDFs
  *   v2p (PT_SCHED 2)  v2 + a CTA-shared march pool (measured slower: profiles/r01_pool)
+ *   v3  (PT_SCHED 3)  v1's loop bodies in one flat loop with gated path regeneration (PT_REGEN_T)
  * -- and the kernel entry macros.  pt_wavefront.cuh runs the same phases as separate kernels over state in HBM.
  * The kernel is instruction-cache bound (16-byte SASS, 28-45 KB per scene): single call sites and rolled loops
  * are deliberate (profiles/README.md).
@@ -1535,6 +1536,135 @@ __device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const Pt
     if (inRange) StoreTexel(pr, image, gx, gy, outColor);
 }
 
+
+/* ---- driver v3: v1's loop bodies, flattened, with gated path regeneration ----------------------------------------
+ * What v1 loses on the analytic scenes is not the shape of a path but its tail: on scene1 nine lanes in ten are done
+ * after two rays, yet the warp runs bounce 2's shading, shadow ray and the third and fourth intersection for the
+ * one to four lanes still alive -- about half of all executions of the intersection code are that sparse (ncu: 17
+ * of 32 lanes per instruction).  Here the sample loop and the bounce loop are ONE loop: an iteration is one bounce
+ * (TraceRay, shader.comp:1345-1391, verbatim from TracePath above) for every lane with a live path, and the lanes
+ * whose path has ended start their pixel's next sample (Scene() up to TracePath, 1446-1472) as soon as at least
+ * PT_REGEN_T of them are waiting (or nobody is alive), so the stragglers' late bounces ride along with the next
+ * sample's first ones.  Per-lane arithmetic and sample order are v1's: bit-exact in strict mode.  Unlike v2 there is
+ * no phase vote and no explicit hit/shadow state: only v1's live variables, one extra flag and the sample counter. */
+#ifndef PT_REGEN_T
+#define PT_REGEN_T 16
+#endif
+__device__ __forceinline__ void pt_render_body_v3(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
+                                                  float4* __restrict__ image, float* s_tab) {
+    for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int gy = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const bool inRange = (gx < pr.width) && (gy < pr.height);
+
+    Ctx c;
+    c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
+
+    const unsigned xyx = (unsigned)gx;
+    const unsigned xyy = (unsigned)pr.height - (unsigned)gy; /* shader.comp:1510 */
+    const int spf = inRange ? pr.samplesPerFrame : 0;
+    const int pathLength = pr.pathLength;
+
+    V3 outColor = mk3(0.0f, 0.0f, 0.0f);
+    PathState ps; /* only ray, l, radiance, rayradiance, MISBRDFWeight, seed, bounce and pendingFinish are used */
+    PathStateInit(ps);
+    bool alive = false;
+    int k = 0;
+
+    for (;;) {
+        const bool wantNew = !alive && ((k < spf) || ps.pendingFinish);
+        const unsigned bNew = __ballot_sync(0xffffffffu, wantNew);
+        const unsigned bAlive = __ballot_sync(0xffffffffu, alive);
+        if ((bNew | bAlive) == 0u) break;
+        if ((__popc(bNew) >= PT_REGEN_T) || (bAlive == 0u)) { /* warp-uniform */
+            if (wantNew) {
+                if (ps.pendingFinish) { /* Scene()'s tail for the path that ended, shader.comp:1477-1489 */
+                    outColor = outColor + PathColor(c, ps);
+                    ps.pendingFinish = false;
+                }
+                if (k < spf) {
+                    const int next = PhaseNew(c, ps, xyx, xyy, k);
+                    k++;
+                    alive = (next == PT_ST_ISECT); /* pathLength <= 0: PhaseNew left pendingFinish set */
+                }
+            }
+        }
+        if (alive) { /* one iteration of TracePath's loop, shader.comp:1393-1407 */
+            bool goOn = false;
+            Hit h;
+            Intersection(c, ps.ray, h, false);
+            if (h.t < 1e5f) {
+                float temperature, luminosity;
+                GetLightMix(c, h.lightID, temperature, luminosity);
+                if (luminosity > 0.0f) { /* emitter hit terminates the path */
+                    const V4 e = Emit(ps.l, PTK_MAX(temperature, 0.0f), PTK_MAX(luminosity, 0.0f));
+                    ps.radiance = ps.radiance + (e * ps.rayradiance) * ps.MISBRDFWeight;
+                } else {
+                    float peak, sigma, invertf;
+                    GetMaterialMix(c, h.materialID, peak, sigma, invertf);
+                    const V4 brdf = EvaluateBRDF(ps.l, peak, sigma, invertf);
+                    Ray outRay;
+                    outRay.origin = fma3(ps.ray.dir, h.t, ps.ray.origin);
+                    outRay.dir = SampleCosineDirectionHemisphere(h.normal, ps.seed);
+                    const float BRDFpdf = PTK_DIV(dot(outRay.dir, h.normal), PT_PI_F);
+                    if (sc.numLights > 0.0f) { /* SampleLightSource, shader.comp:1298-1343 */
+                        const int randomLight = __float2int_rz(floorf(RandomFloatPCG32(ps.seed) * sc.numLights));
+                        const PtDevLightSlot& ls = sc.lightSlots[randomLight < sc.nLightSlots ? randomLight : sc.nLightSlots - 1];
+                        const V3 toLight = mk3(ls.px - outRay.origin.x, ls.py - outRay.origin.y, ls.pz - outRay.origin.z);
+                        const float invLightDistance = PTK_DIV(1.0f, length(toLight));
+                        const V3 lightDir = toLight * invLightDistance;
+                        const float sinthetaMax = PTK_MIN(ls.boundingRadius * invLightDistance, 1.0f);
+                        const float costhetaMax = PTK_SQRT(1.0f - sinthetaMax * sinthetaMax);
+                        Ray shadowRay;
+                        shadowRay.origin = outRay.origin;
+                        shadowRay.dir = ToWorld(SampleCosineUnitCone(ps.seed, costhetaMax), lightDir);
+                        float lightpdf = sc.invNumLights;
+                        lightpdf *= PTK_DIV(dot(shadowRay.dir, lightDir), PT_PI_F * (1.0f - costhetaMax * costhetaMax));
+                        ps.MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + lightpdf * lightpdf);
+                        const float costheta = dot(shadowRay.dir, h.normal);
+                        const float deathProbability = 1.25f * PTK_MAX(ps.MISBRDFWeight - 0.2f, 0.0f);
+                        if (costheta >= 0.0f) {
+                            if (RandomFloatPCG32(ps.seed) > deathProbability) {
+                                Hit sh;
+                                Intersection(c, shadowRay, sh, true);
+                                if (sh.objectID == ls.objectID) {
+                                    float lt, ll;
+                                    GetLightMix(c, ls.lightID, lt, ll);
+                                    const V4 rr = ps.rayradiance * mulDiv4(brdf, costheta, lightpdf);
+                                    const V4 e = Emit(ps.l, PTK_MAX(lt, 0.0f), PTK_MAX(ll, 0.0f));
+                                    ps.radiance = ps.radiance + (e * rr) * (1.0f - ps.MISBRDFWeight);
+                                }
+                            } else {
+                                ps.MISBRDFWeight = 1.0f;
+                            }
+                        }
+                    } else {
+                        ps.MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + 0.0f * 0.0f);
+                    }
+                    const float costheta = dot(outRay.dir, h.normal);
+                    ps.rayradiance = ps.rayradiance * mulDiv4(brdf, costheta, BRDFpdf);
+                    const float mx = PTK_MAX(ps.rayradiance.x, PTK_MAX(ps.rayradiance.y, PTK_MAX(ps.rayradiance.z, ps.rayradiance.w)));
+                    const float rayProbability = PTK_MIN(PTK_MAX(mx, 0.0f), 0.99f);
+                    if (!(RandomFloatPCG32(ps.seed) > rayProbability)) {
+                        ps.rayradiance = ps.rayradiance * PTK_DIV(1.0f, rayProbability);
+                        ps.ray = outRay;
+                        ps.bounce++;
+                        goOn = ps.bounce < pathLength;
+                    }
+                }
+            }
+            if (!goOn) {
+                alive = false;
+                ps.pendingFinish = true;
+            }
+        }
+    }
+    if (inRange) StoreTexel(pr, image, gx, gy, outColor);
+}
+
 #if PT_HAS_SDF
 /* ---- driver v2p: v2 + a march pool shared by the warps of a CTA --------------------------------------------------
  * In v2 only the lanes of ONE warp that happen to be marching populate the SDF phase (ncu: 7 of 32 on the
@@ -1716,7 +1846,9 @@ __device__ __forceinline__ void pt_render_body_v2p(const PtDevScene& sc, const P
 #endif
 __device__ __forceinline__ void pt_render_body(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
                                                float4* __restrict__ image, float* s_tab) {
-#if PT_SCHED
+#if PT_SCHED == 3
+    pt_render_body_v3(sc, pr, ubo, image, s_tab);
+#elif PT_SCHED
     pt_render_body_v2(sc, pr, ubo, image, s_tab);
 #else
     pt_render_body_v1(sc, pr, ubo, image, s_tab);

@@ -351,6 +351,28 @@ def test_scene_at_the_uniform_block_capacity(ptlib, pipeline, bvh_min):
     assert_bit_equal(got, oracle.Oracle(ubo).render(p, 2, 2), '169 spheres, pipeline %d, bvh_min %d' % (pipeline, bvh_min))
 
 
+# ---- driver v3 (flat loop, gated regeneration): an A/B knob of the run-time compiled kernels ------------------------------
+@pytest.mark.parametrize('name,w,h,spp,spf,pl,regen_t', [
+    ('scene0', 96, 64, 8, 4, 5, 16), ('scene1', 96, 64, 8, 8, 5, 16), ('scene1', 70, 45, 6, 3, 32, 4), ('scene2', 64, 48, 4, 4, 5, 32),
+    ('scene3', 64, 48, 2, 2, 5, 1), ('scene7', 64, 48, 2, 2, 5, 16), ('scene10', 64, 48, 2, 2, 5, 16)])
+def test_v3_driver_strict_bit_exact(ptlib, monkeypatch, name, w, h, spp, spf, pl, regen_t):
+    """PT_SCHED=3: the same per-lane arithmetic in the same sample order as v1, whatever the regeneration threshold
+    (ragged frame sizes included: lanes outside the image never start a path)."""
+    monkeypatch.setenv('PT_SCHED', '3')
+    monkeypatch.setenv('PT_REGEN_T', str(regen_t))
+    sc = ptlib.Scene.load(scene_path(name))
+    ubo = sc.pack_ubo()
+    p = sc.pack_params(1, w, h, spf, pl)
+    r = ptlib.Renderer(device=0, mode=ptlib.MODE_STRICT, jit=2)
+    r.set_scene(ubo, sc.sdf_sources)
+    r.resize(w, h)
+    r.render(p, spp, spf)
+    got = r.read_xyz()
+    r.close()
+    ref = oracle.Oracle(ubo, [s.decode() for s in sc.sdf_sources]).render(p, spp, spf)
+    assert_bit_equal(got, ref, '%s v3 T=%d' % (name, regen_t))
+
+
 # ---- BVH (pt_bvh.h): the same closest-hit search as the reference's scan, section 8f-3 ---------------------------------
 def synthetic_path(name):
     import os
