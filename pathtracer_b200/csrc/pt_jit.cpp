@@ -88,9 +88,16 @@ int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::ve
      * loops), scenes with SDFs with the v2 in-warp scheduler and rolled primitive loops (the kernel is instruction-
      * cache bound); the fast build wants 6 CTAs/SM, the strict one 4. */
     struct Knob { const char* name; int dflt; };
-    const Knob knobs[] = {{"PT_SCHED", sdf_unit.empty() ? 0 : 1}, {"PT_SDF_REPS", 16}, {"PT_FEED_T", 8},
+    /* BVH scenes (profiles/r01_bvh): with boxes / lenses / cyclides among the primitives the in-warp scheduler wins
+     * (2.09 vs 1.61 Gsamples/s on the 74-primitive mix), with spheres only v1 does (3.76 vs 3.58 on 169 spheres).
+     * Scan with many primitives: unrolled loops over baked counts spill (169 spheres: 0.10 vs 0.88 Gsamples/s rolled). */
+    const bool heavy = (opt.counts[2] + opt.counts[3] + opt.counts[4]) > 0;
+    const int n_scanned = opt.counts[0] + opt.counts[1] + opt.counts[2] + opt.counts[3] + opt.counts[4];
+    const int sched = (!sdf_unit.empty() || (opt.bvh && heavy)) ? 1 : 0;
+    const int no_unroll = (!sdf_unit.empty() || (!opt.bvh && n_scanned > 16)) ? 1 : 0;
+    const Knob knobs[] = {{"PT_SCHED", sched}, {"PT_SDF_REPS", 16}, {"PT_FEED_T", 8},
                           {"PT_MIN_BLOCKS", opt.mode == PT_MODE_FAST ? 6 : 4},
-                          {"PT_NO_UNROLL", sdf_unit.empty() ? 0 : 1}, {"PT_STATS", 0},
+                          {"PT_NO_UNROLL", no_unroll}, {"PT_STATS", 0},
                           {"PT_WF_REFILL", 8}, {"PT_POOL_MIN", 24}, {"PT_COOP_NORMALS", 0}, {"PT_BVH_WHILE_WHILE", 0}, {"PT_REGEN_T", 16}};
     for (const Knob& k : knobs) {
         const char* v = getenv(k.name);
