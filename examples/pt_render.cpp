@@ -7,6 +7,7 @@
  *   pt_render --scene scenes/scene0.json --width 512 --height 512 --spp 64 --spf 8 --path-length 5 --shot 1 \
  *             [--fast] [--wavefront] [--jit 0|1|2] [--device 0] [--out render.pfm|render.exr|render.ppm] [--tonemap 3]
  *             [--resume checkpoint.pfm --done-samples N]      continue a run saved with --out checkpoint.pfm
+ *             [--gpus N]      split the samples over the first N GPUs of the box (pt_multi: one NCCL reduce at the end)
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -26,7 +27,7 @@ static int die(const char* what, pt_ctx* ctx) {
 int main(int argc, char** argv) {
     std::string scene_path = "scenes/scene0.json", out_path;
     int width = 1280, height = 720, spp = 1000, spf = 1, path_length = 5, shot = 1, device = 0, tonemap = 3; /* host:30-31,1164-1174 */
-    int fast = 0, jit = -1, wavefront = 0, done = 0;
+    int fast = 0, jit = -1, wavefront = 0, done = 0, gpus = 1;
     std::string resume_path;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -45,6 +46,7 @@ int main(int argc, char** argv) {
         else if (a == "--tonemap") tonemap = atoi(next("--tonemap"));
         else if (a == "--out") out_path = next("--out");
         else if (a == "--jit") jit = atoi(next("--jit"));
+        else if (a == "--gpus") gpus = atoi(next("--gpus"));
         else if (a == "--fast") fast = 1;
         else if (a == "--wavefront") wavefront = 1;
         else if (a == "--resume") resume_path = next("--resume");            /* PFM checkpoint written by --out x.pfm */
@@ -61,6 +63,53 @@ int main(int argc, char** argv) {
     params.tonemap = tonemap;
     std::vector<const char*> sdf;
     for (int i = 0; i < pt_scene_num_sdf(scene); i++) sdf.push_back(pt_scene_sdf_glsl(scene, i));
+
+    auto write_image = [&](const std::vector<float>& img) -> int {
+        const bool ppm = out_path.size() > 4 && out_path.substr(out_path.size() - 4) == ".ppm";
+        const bool exr = out_path.size() > 4 && out_path.substr(out_path.size() - 4) == ".exr";
+        int rc = ppm ? pt_write_ppm(out_path.c_str(), img.data(), width, height, tonemap)
+                     : (exr ? pt_write_exr(out_path.c_str(), img.data(), width, height, 1)
+                            : pt_write_pfm(out_path.c_str(), img.data(), width, height, 0));
+        if (rc != PT_OK) fprintf(stderr, "pt_render: cannot write %s\n", out_path.c_str());
+        return rc;
+    };
+
+    if (gpus > 1) { /* sample-split over devices device .. device + gpus - 1 */
+        std::vector<int> devs;
+        for (int g = 0; g < gpus; g++) devs.push_back(device + g);
+        pt_multi* m = nullptr;
+        if (pt_multi_create(devs.data(), gpus, fast ? PT_MODE_FAST : PT_MODE_STRICT, &m) != PT_OK) {
+            fprintf(stderr, "pt_render: pt_multi_create: %s\n", pt_multi_last_error(nullptr));
+            return 1;
+        }
+        for (int g = 0; g < gpus; g++) {
+            if (jit >= 0) pt_set_jit(pt_multi_ctx(m, g), jit);
+            if (wavefront) pt_set_pipeline(pt_multi_ctx(m, g), PT_PIPE_WAVEFRONT);
+        }
+        auto t0 = std::chrono::steady_clock::now();
+        double secs = 0.0;
+        if (pt_multi_set_scene(m, &ubo, sdf.data(), (int)sdf.size()) != PT_OK || pt_multi_resize(m, width, height) != PT_OK) {
+            fprintf(stderr, "pt_render: %s\n", pt_multi_last_error(m));
+            return 1;
+        }
+        auto t1 = std::chrono::steady_clock::now();
+        if (pt_multi_render(m, &params, 0, spp, spf, &secs) != PT_OK) {
+            fprintf(stderr, "pt_render: %s\n", pt_multi_last_error(m));
+            return 1;
+        }
+        printf("{\"scene\": \"%s\", \"width\": %d, \"height\": %d, \"spp\": %d, \"spf\": %d, \"path_length\": %d, \"mode\": \"%s\", "
+               "\"gpus\": %d, \"compile_s\": %.3f, \"render_s\": %.4f, \"reduce_s\": %.5f, \"msamples_per_s\": %.2f}\n",
+               scene_path.c_str(), width, height, spp, spf, path_length, fast ? "fast" : "strict", gpus,
+               std::chrono::duration<double>(t1 - t0).count(), secs, pt_multi_reduce_seconds(m),
+               (double)width * height * (double)spp / secs / 1e6);
+        if (!out_path.empty()) {
+            std::vector<float> img((size_t)width * height * 4);
+            if (pt_multi_read_xyz(m, img.data(), img.size()) != PT_OK || write_image(img) != PT_OK) return 1;
+        }
+        pt_multi_destroy(m);
+        pt_scene_free(scene);
+        return 0;
+    }
 
     pt_ctx* ctx = nullptr;
     if (pt_create(device, &ctx) != PT_OK) return die("create context", nullptr);
@@ -90,12 +139,7 @@ int main(int argc, char** argv) {
     if (!out_path.empty()) {
         std::vector<float> img((size_t)width * height * 4);
         if (pt_read_xyz(ctx, img.data(), img.size()) != PT_OK) return die("read back", ctx);
-        const bool ppm = out_path.size() > 4 && out_path.substr(out_path.size() - 4) == ".ppm";
-        const bool exr = out_path.size() > 4 && out_path.substr(out_path.size() - 4) == ".exr";
-        int rc = ppm ? pt_write_ppm(out_path.c_str(), img.data(), width, height, tonemap)
-                     : (exr ? pt_write_exr(out_path.c_str(), img.data(), width, height, 1)
-                            : pt_write_pfm(out_path.c_str(), img.data(), width, height, 0));
-        if (rc != PT_OK) { fprintf(stderr, "pt_render: cannot write %s\n", out_path.c_str()); return 1; }
+        if (write_image(img) != PT_OK) return 1;
     }
     pt_destroy(ctx);
     pt_scene_free(scene);

@@ -174,6 +174,26 @@ int pt_scene_pack_params(const pt_scene* scene, int shot, int width, int height,
 int pt_render(pt_ctx* ctx, const pt_params* base, int total_samples, int samples_per_frame);
 int pt_render_resume(pt_ctx* ctx, const pt_params* base, int done_samples, int total_samples, int samples_per_frame);
 
+/* ---- the GPUs of one box from a single host thread (the reference drives one GPU) --------
+ * One pt_ctx per device.  pt_multi_render gives device g the g-th contiguous slice of the sample-index range
+ * (pt_dispatch_sum, issued round-robin: launches are asynchronous), then does the path's one exchange step -- a single
+ * ncclReduce of the fp32 sum images to the first device over NVLink -- and pt_finalize there.  The union of the samples
+ * equals a one-GPU run of the same range; images agree up to fp32 summation order.  libnccl.so.2 is dlopen'ed (env
+ * PT_NCCL_LIB) and only needed for n_devices > 1.  bench.py does the same with one process per GPU. */
+typedef struct pt_multi pt_multi;
+int pt_multi_create(const int* devices, int n_devices, int mode, pt_multi** out);
+void pt_multi_destroy(pt_multi* m);
+const char* pt_multi_last_error(const pt_multi* m); /* m may be NULL: why the last pt_multi_create failed */
+int pt_multi_num_devices(const pt_multi* m);
+pt_ctx* pt_multi_ctx(pt_multi* m, int i);           /* for per-context settings (pt_set_jit, pt_set_bvh ...) */
+int pt_multi_set_scene(pt_multi* m, const pt_ubo* ubo, const char* const* sdf_glsl, int n_sdf);
+int pt_multi_resize(pt_multi* m, int width, int height);
+/* samples first_sample .. first_sample + total_samples - 1 of every pixel; blocks; seconds (optional) = host wall time */
+int pt_multi_render(pt_multi* m, const pt_params* base, int first_sample, int total_samples, int samples_per_dispatch,
+                    double* seconds);
+double pt_multi_reduce_seconds(const pt_multi* m);  /* the ncclReduce of the last pt_multi_render alone */
+int pt_multi_read_xyz(pt_multi* m, float* rgba, size_t n_floats); /* the final image, from the first device */
+
 /* SaveRender + SavePPM (host:3491-3518, 918-933): display transform of shader.frag:31-93, 8-bit P6.
  * pt_write_pfm writes the raw XYZ (or linear sRGB when to_rgb != 0) as a bottom-up PF file. */
 int pt_write_ppm(const char* path, const float* rgba, int width, int height, int tonemap);

@@ -73,6 +73,20 @@ def lib():
         L.pt_set_mode.argtypes = [vp, ci]
         L.pt_set_jit.argtypes = [vp, ci]
         L.pt_set_pipeline.argtypes = [vp, ci]
+        L.pt_multi_create.argtypes = [C.POINTER(ci), ci, ci, C.POINTER(vp)]
+        L.pt_multi_destroy.argtypes = [vp]
+        L.pt_multi_destroy.restype = None
+        L.pt_multi_last_error.argtypes = [vp]
+        L.pt_multi_last_error.restype = C.c_char_p
+        L.pt_multi_num_devices.argtypes = [vp]
+        L.pt_multi_ctx.argtypes = [vp, ci]
+        L.pt_multi_ctx.restype = vp
+        L.pt_multi_set_scene.argtypes = [vp, vp, C.POINTER(C.c_char_p), ci]
+        L.pt_multi_resize.argtypes = [vp, ci, ci]
+        L.pt_multi_render.argtypes = [vp, vp, ci, ci, ci, C.POINTER(C.c_double)]
+        L.pt_multi_reduce_seconds.argtypes = [vp]
+        L.pt_multi_reduce_seconds.restype = C.c_double
+        L.pt_multi_read_xyz.argtypes = [vp, vp, C.c_size_t]
         L.pt_set_bvh.argtypes = [vp, ci]
         L.pt_bvh_active.argtypes = [vp]
         L.pt_set_scene.argtypes = [vp, vp, C.POINTER(C.c_char_p), ci]
@@ -334,3 +348,51 @@ class Renderer:
         d, m = np.empty(n, dtype=np.float32), np.empty(n, dtype=np.float32)
         _check(lib().pt_sdf_eval(self._ctx, _ptr(xyz), n, set1, _ptr(d), _ptr(m)), self._ctx)
         return d, m
+
+
+class MultiRenderer:
+    """pt_multi: the GPUs of one box from a single host thread -- sample-split, one NCCL reduce, finalize on the first
+    device (include/pt_abi.h).  The one-process twin of bench.py's one-rank-per-GPU path."""
+
+    def __init__(self, devices, mode=MODE_STRICT, jit=None):
+        self._m = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        rc = lib().pt_multi_create(arr, len(devices), mode, C.byref(self._m))
+        if rc != 0:
+            raise PtError(rc, (lib().pt_multi_last_error(None) or b'').decode())
+        self.width = self.height = 0
+        if jit is not None:
+            for i in range(len(devices)):
+                _check(lib().pt_set_jit(lib().pt_multi_ctx(self._m, i), jit))
+
+    def _ok(self, rc):
+        if rc != 0:
+            raise PtError(rc, (lib().pt_multi_last_error(self._m) or b'').decode())
+
+    def close(self):
+        if getattr(self, '_m', None) and _lib is not None:
+            _lib.pt_multi_destroy(self._m)
+            self._m = None
+
+    __del__ = close
+
+    def set_scene(self, ubo, sdf_sources=()):
+        ubo = np.ascontiguousarray(ubo, dtype=np.float32)
+        assert ubo.size == UBO_FLOATS
+        self._ok(lib().pt_multi_set_scene(self._m, _ptr(ubo), _c_strings(list(sdf_sources)), len(sdf_sources)))
+
+    def resize(self, width, height):
+        self._ok(lib().pt_multi_resize(self._m, width, height))
+        self.width, self.height = width, height
+
+    def render(self, params, first_sample, total_samples, spf):
+        """Returns (seconds of dispatches + reduce + finalize, seconds of the reduce alone)."""
+        params = np.ascontiguousarray(params)
+        secs = C.c_double(0.0)
+        self._ok(lib().pt_multi_render(self._m, _ptr(params), first_sample, total_samples, spf, C.byref(secs)))
+        return secs.value, lib().pt_multi_reduce_seconds(self._m)
+
+    def read_xyz(self):
+        out = np.empty((self.height, self.width, 4), dtype=np.float32)
+        self._ok(lib().pt_multi_read_xyz(self._m, _ptr(out), out.size))
+        return out

@@ -14,6 +14,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -42,6 +43,12 @@ struct Nvrtc {
 Nvrtc g_nvrtc;
 std::once_flag g_once;
 std::string g_load_error;
+
+/* Process-wide cache of compiled kernels, keyed by the complete translation unit (which spells out the mode, the baked
+ * counts, every tuning knob and the generated SDF code): a cubin is independent of the device it will be loaded on, so
+ * the contexts of a multi-GPU render (pt_multi.cpp) compile each scene once instead of once per GPU. */
+std::mutex g_cache_mu;
+std::map<std::string, std::pair<std::vector<char>, std::string>> g_cubin_cache;
 
 void load_nvrtc() {
     const char* env = getenv("PT_NVRTC_LIB");
@@ -111,6 +118,15 @@ int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::ve
     if (!sdf_unit.empty()) src += "PT_DEFINE_SDF_EVAL_KERNEL(pt_sdf_eval_jit)\n";
     if (opt.wavefront) src += "PT_DEFINE_WAVEFRONT_KERNELS\n";
 
+    if (!getenv("PT_JIT_DUMP")) {
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        auto it = g_cubin_cache.find(src);
+        if (it != g_cubin_cache.end()) {
+            *cubin = it->second.first;
+            *log = it->second.second;
+            return PT_OK;
+        }
+    }
     std::vector<const char*> hdr_names, hdr_texts;
     for (int i = 0; i < pt_embedded_header_count; i++) {
         hdr_names.push_back(pt_embedded_headers[i].name);
@@ -158,5 +174,10 @@ int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::ve
     }
     g_nvrtc.DestroyProgram(&prog);
     *log = plog;
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        if (g_cubin_cache.size() >= 64) g_cubin_cache.clear(); /* bound the memory of a long-lived host process */
+        g_cubin_cache[src] = std::make_pair(*cubin, plog);
+    }
     return PT_OK;
 }

@@ -457,3 +457,48 @@ def test_async_readback_matches_blocking(ptlib, renderer):
     renderer.dispatch(q2)
     renderer.read_wait()
     assert np.array_equal(pinned[0].numpy().view(np.uint32), blocking[0].view(np.uint32))
+
+
+# ---- pt_multi: the GPUs of one box from a single host thread (section 8e, native twin of bench.py's torchrun path) ------
+@pytest.mark.parametrize('name,spp,spf', [('scene1', 16, 4), ('scene10', 6, 4), ('scene0', 4, 4)])
+def test_native_multi_gpu_render(ptlib, renderer, name, spp, spf):
+    """pt_multi over every GPU of the box (one here unless the box has more): sample-split + one ncclReduce + finalize
+    equals the one-context sum over the same sample range -- bit for bit on one device, up to fp32 summation order
+    (1e-5 relative, section 8e) on several."""
+    import torch
+    n = min(torch.cuda.device_count(), 8)
+    w, h = 96, 64
+    sc = ptlib.Scene.load(scene_path(name))
+    ubo = sc.pack_ubo()
+    p = sc.pack_params(1, w, h, spf, 5)
+    renderer.set_mode(0)
+    renderer.set_scene(ubo, sc.sdf_sources)
+    renderer.resize(w, h)
+    renderer.dispatch_sum(p, 100, spp)
+    renderer.finalize(p, spp)
+    single = renderer.read_xyz()
+    for devices in ([0], list(range(n))) if n > 1 else ([0],):
+        m = ptlib.MultiRenderer(devices, mode=0)
+        m.set_scene(ubo, sc.sdf_sources)
+        m.resize(w, h)
+        secs, reduce_s = m.render(p, 100, spp, spf)
+        got = m.read_xyz()
+        m.close()
+        assert secs > 0 and (reduce_s > 0) == (len(devices) > 1)
+        assert (got[..., 3] == 1.0).all()
+        if len(devices) == 1 and spf >= spp:
+            assert_bit_equal(got, single, '%s pt_multi on one device' % name)
+        else:  # several dispatches or devices: the same samples added in another order
+            assert np.allclose(got[..., :3], single[..., :3], rtol=1e-5, atol=1e-7 * float(single[..., :3].max()))
+
+
+def test_native_multi_gpu_errors(ptlib):
+    with pytest.raises(ptlib.PtError):
+        ptlib.MultiRenderer([0, 0])          # NCCL wants distinct devices
+    with pytest.raises(ptlib.PtError):
+        ptlib.MultiRenderer([])
+    m = ptlib.MultiRenderer([0])
+    sc = ptlib.Scene.load(scene_path('scene0'))
+    with pytest.raises(ptlib.PtError):       # no image yet
+        m.render(sc.pack_params(1, 32, 32, 1, 5), 0, 4, 2)
+    m.close()
