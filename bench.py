@@ -48,6 +48,30 @@ def scene_file(name):
     return os.path.join(ROOT, 'scenes', name + '.json')
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner when
+    NCCL_DEBUG=VERSION is set on the box), so file descriptor 1 is pointed at stderr for the duration of the run and
+    the line goes to a saved copy of the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def load_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -216,7 +240,7 @@ def run_reference(args, wl):
         'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -235,6 +259,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-flush', action='store_true')
     args = ap.parse_args()
+    quiet_stdout()
     wl = args.workload
     if args.impl == 'reference':
         return run_reference(args, wl)
@@ -409,7 +434,7 @@ def main():
             line['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': threads, 'kind': 'port', 'sample': desc}
     except Exception as e:  # the baseline legs must never take the measurement down
         line['cpu_baseline_error'] = repr(e)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -131,6 +131,29 @@ int pt_multi_create(const int* devices, int n_devices, int mode, pt_multi** out)
             pt_multi_destroy(m);
             return mfail(nullptr, PT_ERR_CUDA, std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r));
         }
+        /* NCCL sets its transports up lazily, inside the first collective (0.4 s on a 2-GPU box): do that here, on a
+         * scratch buffer, not inside the first pt_multi_render */
+        std::vector<void*> scratch(n_devices, nullptr);
+        for (int g = 0; g < n_devices; g++) {
+            cudaSetDevice(m->devices[g]);
+            cudaMalloc(&scratch[g], 1024);
+            cudaMemsetAsync(scratch[g], 0, 1024, (cudaStream_t)pt_stream_handle(m->ctx[g]));
+        }
+        r = g_nccl.GroupStart();
+        for (int g = 0; g < n_devices && r == 0; g++) {
+            cudaSetDevice(m->devices[g]);
+            r = g_nccl.Reduce(scratch[g], scratch[g], 256, kNcclFloat32, kNcclSum, 0, m->comms[g], (cudaStream_t)pt_stream_handle(m->ctx[g]));
+        }
+        const ncclResult_t r2 = g_nccl.GroupEnd();
+        for (int g = 0; g < n_devices; g++) {
+            pt_sync(m->ctx[g]);
+            cudaSetDevice(m->devices[g]);
+            cudaFree(scratch[g]);
+        }
+        if (r != 0 || r2 != 0) {
+            pt_multi_destroy(m);
+            return mfail(nullptr, PT_ERR_CUDA, std::string("ncclReduce (warm-up): ") + g_nccl.GetErrorString(r != 0 ? r : r2));
+        }
     }
     *out = m;
     return PT_OK;

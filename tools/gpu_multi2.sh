@@ -12,5 +12,5 @@ cat $O/cli_*.json $O/cli_*.err
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 32 --warmup 3 --no-cpu-baseline > $O/bench_cfg2_n2.json 2> $O/bench_cfg2_n2.err
 python - <<'PY'
 import json
-d=json.load(open('gpurun_out/multi2/bench_cfg2_n2.json')); print('bench.py torchrun n=2: %.2f Gs/s reduce %.3f ms'%(d['value']/1e9, d['reduce_ms']))
+t=open('gpurun_out/multi2/bench_cfg2_n2.json').read(); print('stdout lines:', t.count(chr(10))); d=json.loads(t); print('bench.py torchrun n=2: %.2f Gs/s reduce %.3f ms'%(d['value']/1e9, d['reduce_ms']))
 PY
