@@ -1450,6 +1450,12 @@ namespace PT_KERNEL_NS {
 #ifndef PT_COOP_NORMALS
 #define PT_COOP_NORMALS 0 /* measured slower than one lane per ray on every SDF workload: profiles/r01_coop */
 #endif
+#ifndef PT_SDF_MIN
+#define PT_SDF_MIN 0  /* lanes that must be waiting in the SDF phase before it runs while a feeder still has work */
+#endif
+#ifndef PT_SDF_EXIT
+#define PT_SDF_EXIT 0 /* leave the SDF phase early (checked every 4 evaluations) once fewer lanes than this still march */
+#endif
 
 __device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
                                                   float4* __restrict__ image, float* s_tab) {
@@ -1494,9 +1500,14 @@ __device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const Pt
         if (__popc(bIs) >= best) { best = __popc(bIs); phase = PT_ST_ISECT; }
         if (__popc(bSh) >= best) { best = __popc(bSh); phase = PT_ST_SHADE; }
 #if PT_HAS_SDF
-        if (bSdf != 0u && (best < PT_FEED_T || best == 0)) phase = PT_ST_SDF;
+        /* an SDF execution costs an order of magnitude more than a feeder phase whatever its population: with
+         * PT_SDF_MIN > 0 a thin feeder runs first (it may send more lanes marching) unless enough lanes already wait */
+        if (bSdf != 0u && (best == 0 || (best < PT_FEED_T && __popc(bSdf) >= PT_SDF_MIN))) phase = PT_ST_SDF;
 #endif
         PT_STAT(phase, phase == PT_ST_NEW ? bNew : (phase == PT_ST_ISECT ? bIs : (phase == PT_ST_SDF ? bSdf : bSh)));
+#ifdef PT_STATS
+        if (phase == PT_ST_SDF && (threadIdx.x & 31) == 0) atomicAdd(&pt_stats[8 + ((__popc(bSdf) - 1) >> 2)], 1ull); /* population histogram, buckets of 4 */
+#endif
         if (phase == PT_ST_NEW) {
             if (st == PT_ST_NEW) {
                 if (ps.pendingFinish) {
@@ -1524,6 +1535,9 @@ __device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const Pt
 #pragma unroll 1
             for (int rep = 0; rep < PT_SDF_REPS; rep++) {
                 if (st == PT_ST_SDF) st = PhaseSdfEval(c, ps, ms);
+#if PT_SDF_EXIT > 0
+                if ((rep & 3) == 3 && __popc(__ballot_sync(0xffffffffu, st == PT_ST_SDF)) < PT_SDF_EXIT) break;
+#endif
             }
 #endif
             if (st == PT_ST_SHADE) st = PhaseTrivial(ps);

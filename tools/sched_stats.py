@@ -26,4 +26,7 @@ for wl in sys.argv[1:] or ['cfg2_scene1_1080p']:
     for i, n in enumerate(names):
         ex, ln = out[2 * i], out[2 * i + 1]
         print('  %-6s executions %12d (%5.1f%%)  avg lanes %5.2f  per sample-warp %.2f' % (n, ex, 100.0 * ex / max(tot, 1), ln / max(ex, 1), ex / (W * H * 8 / 32)))
+    hist = [out[8 + b] for b in range(8)]
+    if sum(hist):
+        print('  SDF executions by lanes waiting (1-4, 5-8, ... 29-32): ' + ' '.join('%.1f%%' % (100.0 * h / sum(hist)) for h in hist))
     r.close()
