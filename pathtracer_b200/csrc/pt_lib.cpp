@@ -48,7 +48,12 @@ struct pt_ctx {
     bool scene_set = false;
     pt_ubo ubo;
     PtDevScene dev_scene;
-    float* d_ubo = nullptr;   /* flat copy of the uniform block */
+    float* d_ubo = nullptr;   /* flat copy of the uniform block (+ the BVH blob at PT_BVH_UBO_OFF) */
+    /* pinned staging ring for the scene upload: pt_set_scene never synchronises the stream, so a host loop of
+     * set_scene / dispatch / read_xyz_async keeps the GPU busy back to back */
+    float* h_stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+    unsigned stage_next = 0;
     float* d_image = nullptr; /* accumulation image (RGBA32F) */
     bool own_image = false;
     int width = 0, height = 0;
@@ -235,7 +240,11 @@ int pt_create(int device, pt_ctx** out) {
     if (bm && bm[0]) ctx->bvh_min = atoi(bm);
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&ctx->d_ubo, sizeof(float) * (PT_BVH_UBO_OFF + PT_BVH_MAX_FLOATS))) != cudaSuccess) {
+        (e = cudaMalloc((void**)&ctx->d_ubo, sizeof(float) * (PT_BVH_UBO_OFF + PT_BVH_MAX_FLOATS))) != cudaSuccess ||
+        (e = cudaMallocHost((void**)&ctx->h_stage[0], sizeof(float) * (PT_BVH_UBO_OFF + PT_BVH_MAX_FLOATS))) != cudaSuccess ||
+        (e = cudaMallocHost((void**)&ctx->h_stage[1], sizeof(float) * (PT_BVH_UBO_OFF + PT_BVH_MAX_FLOATS))) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_stage[0], cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_stage[1], cudaEventDisableTiming)) != cudaSuccess) {
         int rc = cuda_fail(nullptr, e, "pt_create");
         pt_destroy(ctx);
         return rc;
@@ -257,6 +266,10 @@ void pt_destroy(pt_ctx* ctx) {
     if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
     if (ctx->d_snap) cudaFree(ctx->d_snap);
     if (ctx->d_ubo) cudaFree(ctx->d_ubo);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
+        if (ctx->ev_stage[i]) cudaEventDestroy(ctx->ev_stage[i]);
+    }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -375,11 +388,20 @@ int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, in
     ctx->dev_scene = sc;
     ctx->active_jit = jit;
     ctx->bvh_active = bvh;
-    PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_ubo, &ctx->ubo, sizeof(pt_ubo), cudaMemcpyHostToDevice, ctx->stream));
-    if (bvh)
-        PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_ubo + PT_BVH_UBO_OFF, bvh_blob.data(), bvh_blob.size() * sizeof(float),
-                                     cudaMemcpyHostToDevice, ctx->stream));
-    PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); /* ctx->ubo may be overwritten by the next call */
+    {   /* one asynchronous upload from a pinned slot; the slot is reused two calls later, after its event */
+        const unsigned slot = ctx->stage_next++ & 1u;
+        PT_CUDA(ctx, cudaEventSynchronize(ctx->ev_stage[slot]));
+        float* h = ctx->h_stage[slot];
+        memcpy(h, &ctx->ubo, sizeof(pt_ubo));
+        size_t floats = PT_UBO_FLOATS;
+        if (bvh) {
+            memset(h + PT_UBO_FLOATS, 0, sizeof(float) * (PT_BVH_UBO_OFF - PT_UBO_FLOATS));
+            memcpy(h + PT_BVH_UBO_OFF, bvh_blob.data(), bvh_blob.size() * sizeof(float));
+            floats = PT_BVH_UBO_OFF + bvh_blob.size();
+        }
+        PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_ubo, h, floats * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        PT_CUDA(ctx, cudaEventRecord(ctx->ev_stage[slot], ctx->stream));
+    }
     ctx->scene_set = true;
     ctx->error.clear();
     return PT_OK;
