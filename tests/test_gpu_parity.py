@@ -248,6 +248,60 @@ def test_full_size_properties_cfg2(ptlib, renderer):
     assert np.allclose(s8[..., :3], s44[..., :3], rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize('name,w,h,pl,row_step', [
+    ('scene1', 1920, 1080, 5, 97), ('scene9', 1920, 1080, 5, 131), ('scene10', 1920, 1080, 32, 149),
+    ('scene8', 1920, 1080, 32, 211), ('scene10', 3840, 2160, 5, 307)])
+def test_full_size_rows_bit_exact(ptlib, renderer, name, w, h, pl, row_step):
+    """BASELINE configs 2-5 at their FULL frame sizes, strict mode, 2 spp in two dispatches: a strided sample of rows
+    (the oracle renders only those) must equal the GPU image bit for bit; the whole frame is finite with w == 1."""
+    sc = ptlib.Scene.load(scene_path(name))
+    ubo = sc.pack_ubo()
+    p = sc.pack_params(1, w, h, 1, pl)
+    renderer.set_mode(0)
+    renderer.set_scene(ubo, sc.sdf_sources)
+    renderer.resize(w, h)
+    renderer.render(p, 2, 1)
+    got = renderer.read_xyz()
+    assert np.isfinite(got).all() and (got[..., 3] == 1.0).all() and got[..., 1].mean() > 0
+    o = oracle.Oracle(ubo, [s.decode() for s in sc.sdf_sources])
+    ref = np.zeros((h, w, 4), dtype=np.float32)
+    q = np.array(p, copy=True)
+    for j in (1, 2):
+        q['frame'] = j
+        q['currentSamples'] = j
+        o.dispatch(q, ref, 0, row_step)
+    rows = np.arange(0, h, row_step)
+    assert_bit_equal(np.ascontiguousarray(got[rows]), np.ascontiguousarray(ref[rows]), '%s %dx%d rows 0::%d' % (name, w, h, row_step))
+
+
+@pytest.mark.parametrize('name,w,h,pl', [('scene9', 1920, 1080, 5), ('scene8', 1920, 1080, 32), ('scene10', 3840, 2160, 5)])
+def test_full_size_properties_sdf_configs(ptlib, renderer, name, w, h, pl):
+    """Configs 3-5 at full size, fast mode (the v2 driver): determinism, w == 1, finiteness, linearity of the sum mode,
+    and running mean over two dispatches == finalized sum over the same samples (1e-5, summation order)."""
+    sc = ptlib.Scene.load(scene_path(name))
+    ubo = sc.pack_ubo()
+    p = sc.pack_params(1, w, h, 2, pl)
+    renderer.set_mode(1)
+    renderer.set_jit(2)
+    renderer.set_scene(ubo, sc.sdf_sources)
+    renderer.resize(w, h)
+    renderer.render(p, 4, 2)
+    a = renderer.read_xyz()
+    renderer.clear()
+    renderer.render(p, 4, 2)
+    b = renderer.read_xyz()
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.isfinite(a).all() and (a[..., 3] == 1.0).all() and a[..., 1].mean() > 0
+    renderer.clear()
+    renderer.dispatch_sum(p, 0, 2)
+    renderer.dispatch_sum(p, 2, 2)
+    renderer.finalize(p, 4)
+    s = renderer.read_xyz()
+    scale = float(a[..., :3].max())
+    assert np.allclose(s[..., :3], a[..., :3], rtol=1e-5, atol=1e-6 * scale)
+    renderer.set_jit(1)
+
+
 # ---- the wavefront pipeline (pt_wavefront.cuh): same phases, one kernel each, path state in HBM ------------------------
 
 @pytest.fixture(scope='module')
