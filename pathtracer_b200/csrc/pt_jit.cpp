@@ -101,9 +101,11 @@ int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::ve
     const bool heavy = (opt.counts[2] + opt.counts[3] + opt.counts[4]) > 0;
     const int n_scanned = opt.counts[0] + opt.counts[1] + opt.counts[2] + opt.counts[3] + opt.counts[4];
     const int sched = (!sdf_unit.empty() || (opt.bvh && heavy)) ? 1 : 0;
+    const char* sched_env = getenv("PT_SCHED");
+    const int sched_eff = (sched_env && sched_env[0]) ? atoi(sched_env) : sched;
     const int no_unroll = (!sdf_unit.empty() || (!opt.bvh && n_scanned > 16)) ? 1 : 0;
     const Knob knobs[] = {{"PT_SCHED", sched}, {"PT_SDF_REPS", 16}, {"PT_FEED_T", 8},
-                          {"PT_MIN_BLOCKS", opt.mode == PT_MODE_FAST ? 6 : 4},
+                          {"PT_MIN_BLOCKS", opt.mode == PT_MODE_FAST ? (sched_eff == 4 ? 5 : 6) : 4}, /* v2d: 45 KB of shared memory per CTA */
                           {"PT_NO_UNROLL", no_unroll}, {"PT_STATS", 0},
                           {"PT_WF_REFILL", 8}, {"PT_POOL_MIN", 24}, {"PT_COOP_NORMALS", 0}, {"PT_BVH_WHILE_WHILE", 0}, {"PT_REGEN_T", 16}, {"PT_SDF_MIN", 0}, {"PT_SDF_EXIT", 0}};
     for (const Knob& k : knobs) {

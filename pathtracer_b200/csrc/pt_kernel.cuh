@@ -29,6 +29,8 @@
  *                     lanes refill themselves with their pixel's next sample   default for scenes with SDFs
  *   v2p (PT_SCHED 2)  v2 + a CTA-shared march pool (measured slower: profiles/r01_pool)
  *   v3  (PT_SCHED 3)  v1's loop bodies in one flat loop with gated path regeneration (PT_REGEN_T)
+ *   v2d (PT_SCHED 4)  v2 with two pixels per lane, the idle one parked in shared memory: a lane only waits for the SDF
+ *                     phase when both its paths do
  * -- and the kernel entry macros.  pt_wavefront.cuh runs the same phases as separate kernels over state in HBM.
  * The kernel is instruction-cache bound (16-byte SASS, 28-45 KB per scene): single call sites and rolled loops
  * are deliberate (profiles/README.md).
@@ -1679,6 +1681,158 @@ __device__ __forceinline__ void pt_render_body_v3(const PtDevScene& sc, const Pt
     if (inRange) StoreTexel(pr, image, gx, gy, outColor);
 }
 
+/* ---- driver v2d: v2 with TWO pixels per lane, the idle one parked in shared memory ---------------------------------
+ * v2 cannot fill its phases because a lane is tied to one pixel's sample sequence: a lane whose ray waits in front of
+ * the SDF phase is a lane the feeder phases do not have, so the (expensive) SDF phase runs when the feeders dry up,
+ * with whoever happens to wait -- 1-4 of 32 lanes in 61-73 % of its executions on the fractal scenes
+ * (profiles/r01_sdfsched).  Here every lane owns two pixels (rows gy and gy + 8 of a 16x16 tile).  One path lives in
+ * registers, the other is parked in the lane's own column of shared memory (56 words, no atomics, no queues).  A lane
+ * whose active path has to wait for the SDF phase swaps to its other pixel and keeps feeding; it only counts as waiting
+ * when BOTH its paths wait (the older one is marched first).  So the SDF phase starts with most of the warp in it, and
+ * the feeders lose a lane only when it has nothing else to do.  Per pixel the samples still run in order through the
+ * same phases: bit-exact in strict mode. */
+#define PT_PARK_WORDS 56
+PT_DEV void ParkSwap(float* col, PathState& ps, MarchState& ms, int& st, int& k, V3& outColor) {
+    int w = 0;
+#define PT_SWF(x) { const float t_ = col[w * PT_BLOCK_THREADS]; col[w * PT_BLOCK_THREADS] = (x); (x) = t_; w++; }
+#define PT_SWI(x) { const int t_ = __float_as_int(col[w * PT_BLOCK_THREADS]); col[w * PT_BLOCK_THREADS] = __int_as_float((int)(x)); (x) = t_; w++; }
+    PT_SWF(ps.ray.origin.x) PT_SWF(ps.ray.origin.y) PT_SWF(ps.ray.origin.z)
+    PT_SWF(ps.ray.dir.x) PT_SWF(ps.ray.dir.y) PT_SWF(ps.ray.dir.z)
+    PT_SWF(ps.l.x) PT_SWF(ps.l.y) PT_SWF(ps.l.z) PT_SWF(ps.l.w)
+    PT_SWF(ps.radiance.x) PT_SWF(ps.radiance.y) PT_SWF(ps.radiance.z) PT_SWF(ps.radiance.w)
+    PT_SWF(ps.rayradiance.x) PT_SWF(ps.rayradiance.y) PT_SWF(ps.rayradiance.z) PT_SWF(ps.rayradiance.w)
+    PT_SWF(ps.MISBRDFWeight)
+    PT_SWF(ps.shDir.x) PT_SWF(ps.shDir.y) PT_SWF(ps.shDir.z)
+    PT_SWF(ps.shContrib.x) PT_SWF(ps.shContrib.y) PT_SWF(ps.shContrib.z) PT_SWF(ps.shContrib.w)
+    PT_SWF(ps.h.t) PT_SWF(ps.h.normal.x) PT_SWF(ps.h.normal.y) PT_SWF(ps.h.normal.z) PT_SWF(ps.h.materialID) PT_SWF(ps.h.lightID)
+    PT_SWF(ms.mt) PT_SWF(ms.insT) PT_SWF(ms.omega) PT_SWF(ms.previousRadius) PT_SWF(ms.tMax) PT_SWF(ms.ksign)
+    PT_SWF(ms.probe) PT_SWF(ms.nrm0) PT_SWF(ms.nrm1) PT_SWF(ms.nrm2)
+    PT_SWF(outColor.x) PT_SWF(outColor.y) PT_SWF(outColor.z)
+    { /* seed and set1 are full 32-bit words */
+        unsigned s_ = ps.seed; int si_ = (int)s_; PT_SWI(si_) ps.seed = (unsigned)si_;
+        unsigned m_ = ms.set1; int mi_ = (int)m_; PT_SWI(mi_) ms.set1 = (unsigned)mi_;
+    }
+    int flags = ps.bounce | (ps.isShadow ? (1 << 28) : 0) | (ps.pathAlive ? (1 << 29) : 0) | (ps.pendingFinish ? (1 << 30) : 0);
+    PT_SWI(flags)
+    ps.bounce = flags & ((1 << 28) - 1);
+    ps.isShadow = (flags & (1 << 28)) != 0; ps.pathAlive = (flags & (1 << 29)) != 0; ps.pendingFinish = (flags & (1 << 30)) != 0;
+    PT_SWI(ps.shObj) PT_SWI(ps.h.objectID)
+    PT_SWI(ms.points) PT_SWI(ms.iter) PT_SWI(ms.sub)
+    PT_SWI(st) PT_SWI(k)
+#undef PT_SWF
+#undef PT_SWI
+}
+
+__device__ __forceinline__ void pt_render_body_v2d(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
+                                                   float4* __restrict__ image, float* s_tab, float* s_park) {
+    for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int gy0 = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3); /* the lane's pixels: rows gy0 and gy0 + 8 */
+    float* col = s_park + threadIdx.x;
+
+    Ctx c;
+    c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
+
+    const unsigned xyx = (unsigned)gx;
+    const int spf = pr.samplesPerFrame;
+    const bool inA = (gx < pr.width) && (gy0 < pr.height), inB = (gx < pr.width) && (gy0 + 8 < pr.height);
+
+    PathState ps;
+    MarchState ms;
+    V3 outColor = mk3(0.0f, 0.0f, 0.0f);
+    int k = 0;
+    /* pixel B starts parked: a path in phase NEW (or DONE) carries no other state (k = 0, colour 0, nothing pending) */
+    const int stOther0 = (inB && spf > 0) ? PT_ST_NEW : PT_ST_DONE;
+#pragma unroll 1
+    for (int w = 0; w < PT_PARK_WORDS; w++) col[w * PT_BLOCK_THREADS] = 0.0f;
+    col[(PT_PARK_WORDS - 2) * PT_BLOCK_THREADS] = __int_as_float(stOther0); /* ParkSwap's layout: ..., st, k */
+    int stOther = stOther0; /* register mirror of the parked path's phase */
+    PathStateInit(ps);
+    MarchStateInit(ms);
+    int st = (inA && spf > 0) ? PT_ST_NEW : PT_ST_DONE;
+    int cur = 0; /* which pixel is in registers: 0 = row gy0, 1 = row gy0 + 8 */
+    bool settled = false; /* the active path is the older of two that wait for the SDF phase */
+    V3 colorA = mk3(0.0f, 0.0f, 0.0f), colorB = mk3(0.0f, 0.0f, 0.0f);
+
+    for (;;) {
+        { /* lane-local: keep a runnable path in registers; when both wait for the SDF phase, march the older one */
+            const bool blocked = (st == PT_ST_SDF) || (st == PT_ST_DONE);
+            const bool otherRunnable = (stOther != PT_ST_SDF) && (stOther != PT_ST_DONE);
+            if (st != PT_ST_SDF) settled = false;
+            /* both wait for the SDF phase: bring the one that has waited longer (the parked one) in, once */
+            const bool toOlder = (stOther == PT_ST_SDF) && ((st == PT_ST_DONE) || ((st == PT_ST_SDF) && !settled));
+            const bool wantSwap = (blocked && otherRunnable) || toOlder;
+            if (__ballot_sync(0xffffffffu, wantSwap) != 0u) {
+                if (wantSwap) {
+                    if (st == PT_ST_DONE) { if (cur == 0) colorA = outColor; else colorB = outColor; }
+                    const int mine = st;
+                    ParkSwap(col, ps, ms, st, k, outColor);
+                    stOther = mine;
+                    cur ^= 1;
+                    settled = toOlder;
+                }
+            }
+        }
+        const unsigned xyy = (unsigned)pr.height - (unsigned)(gy0 + 8 * cur); /* shader.comp:1510 */
+        const unsigned bNew = __ballot_sync(0xffffffffu, st == PT_ST_NEW);
+        const unsigned bIs = __ballot_sync(0xffffffffu, st == PT_ST_ISECT);
+        const unsigned bSh = __ballot_sync(0xffffffffu, st == PT_ST_SHADE);
+#if PT_HAS_SDF
+        const unsigned bSdf = __ballot_sync(0xffffffffu, st == PT_ST_SDF);
+#else
+        const unsigned bSdf = 0u;
+#endif
+        if ((bNew | bIs | bSdf | bSh) == 0u) break; /* every lane: active DONE, and then the parked one is DONE too */
+        int phase = PT_ST_NEW, best = __popc(bNew);
+        if (__popc(bIs) >= best) { best = __popc(bIs); phase = PT_ST_ISECT; }
+        if (__popc(bSh) >= best) { best = __popc(bSh); phase = PT_ST_SHADE; }
+#if PT_HAS_SDF
+        if (bSdf != 0u && (best < PT_FEED_T || best == 0)) phase = PT_ST_SDF;
+#endif
+        PT_STAT(phase, phase == PT_ST_NEW ? bNew : (phase == PT_ST_ISECT ? bIs : (phase == PT_ST_SDF ? bSdf : bSh)));
+#ifdef PT_STATS
+        if (phase == PT_ST_SDF && (threadIdx.x & 31) == 0) atomicAdd(&pt_stats[8 + ((__popc(bSdf) - 1) >> 2)], 1ull);
+#endif
+        if (phase == PT_ST_NEW) {
+            if (st == PT_ST_NEW) {
+                if (ps.pendingFinish) {
+                    outColor = outColor + PathColor(c, ps);
+                    ps.pendingFinish = false;
+                }
+                if (k < spf) {
+                    st = PhaseNew(c, ps, xyx, xyy, k);
+                    k++;
+                } else {
+                    st = PT_ST_DONE;
+                }
+            }
+        } else if (phase == PT_ST_ISECT) {
+            if (st == PT_ST_ISECT) {
+                st = PhaseIsect(c, ps, ms);
+                if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
+            }
+        }
+#if PT_HAS_SDF
+        else if (phase == PT_ST_SDF) {
+#pragma unroll 1
+            for (int rep = 0; rep < PT_SDF_REPS; rep++) {
+                if (st == PT_ST_SDF) st = PhaseSdfEval(c, ps, ms);
+            }
+            if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
+        }
+#endif
+        else {
+            if (st == PT_ST_SHADE) st = PhaseShade(c, ps);
+        }
+    }
+    if (cur == 0) colorA = outColor; else colorB = outColor;
+    if (inA) StoreTexel(pr, image, gx, gy0, colorA);
+    if (inB) StoreTexel(pr, image, gx, gy0 + 8, colorB);
+}
+
 #if PT_HAS_SDF
 /* ---- driver v2p: v2 + a march pool shared by the warps of a CTA --------------------------------------------------
  * In v2 only the lanes of ONE warp that happen to be marching populate the SDF phase (ncu: 7 of 32 on the
@@ -1872,7 +2026,18 @@ __device__ __forceinline__ void pt_render_body(const PtDevScene& sc, const PtDev
 } /* namespace PT_KERNEL_NS */
 
 /* the kernel entry point; the name distinguishes the strict / fast / JIT instances */
-#if PT_HAS_SDF && PT_SCHED == 2
+#if PT_SCHED == 4
+#define PT_ROWS_PER_BLOCK 16
+#define PT_DEFINE_RENDER_KERNEL(name)                                                                        \
+    extern "C" __device__ int pt_rows_per_block = 16;                                                        \
+    extern "C" __global__ void __launch_bounds__(PT_BLOCK_THREADS, PT_MIN_BLOCKS)                            \
+    name(const __grid_constant__ PtDevScene sc, const __grid_constant__ PtDevParams pr,                      \
+         const float* __restrict__ ubo, float4* __restrict__ image) {                                        \
+        __shared__ float s_tab[PT_SH_FLOATS];                                                                \
+        __shared__ float s_park[PT_PARK_WORDS * PT_BLOCK_THREADS];                                           \
+        PT_KERNEL_NS::pt_render_body_v2d(sc, pr, ubo, image, s_tab, s_park);                                 \
+    }
+#elif PT_HAS_SDF && PT_SCHED == 2
 #define PT_DEFINE_RENDER_KERNEL(name)                                                                        \
     extern "C" __global__ void __launch_bounds__(PT_BLOCK_THREADS, PT_MIN_BLOCKS)                            \
     name(const __grid_constant__ PtDevScene sc, const __grid_constant__ PtDevParams pr,                      \

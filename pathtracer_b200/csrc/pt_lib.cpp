@@ -27,6 +27,7 @@ struct JitKernel {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kernel = nullptr;
     cudaKernel_t sdf_eval = nullptr; /* only for scenes with SDF snippets */
+    int rows_per_block = 8;          /* image rows one CTA covers: 8, or 16 for the two-pixels-per-lane driver (PT_SCHED=4) */
     /* wavefront pipeline (pt_wavefront.cuh); wf_march only with SDF snippets */
     cudaKernel_t wf_gen = nullptr, wf_isect = nullptr, wf_march = nullptr, wf_shade = nullptr, wf_final = nullptr,
                  wf_ctl = nullptr;
@@ -96,7 +97,8 @@ int launch(pt_ctx* ctx, const PtDevParams& dp) {
         ctx->timing_open = true;
     }
     if (ctx->active_jit) {
-        dim3 grid((unsigned)((dp.width + 15) / 16), (unsigned)((dp.height + 7) / 8), 1), block(128, 1, 1);
+        const int rows = ctx->active_jit->rows_per_block;
+        dim3 grid((unsigned)((dp.width + 15) / 16), (unsigned)((dp.height + rows - 1) / rows), 1), block(128, 1, 1);
         const float* ubo = ctx->d_ubo;
         float* image = ctx->d_image;
         void* args[4] = {(void*)&ctx->dev_scene, (void*)&dp, (void*)&ubo, (void*)&image};
@@ -363,6 +365,15 @@ int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, in
             if (e != cudaSuccess) {
                 cudaLibraryUnload(jk.lib);
                 return cuda_fail(ctx, e, "cudaLibraryGetKernel(pt_render_jit)");
+            }
+            { /* a kernel that covers more than 8 rows per CTA says so */
+                void* dptr = nullptr;
+                size_t bytes = 0;
+                if (cudaLibraryGetGlobal(&dptr, &bytes, jk.lib, "pt_rows_per_block") == cudaSuccess && bytes == sizeof(int)) {
+                    PT_CUDA(ctx, cudaMemcpy(&jk.rows_per_block, dptr, sizeof(int), cudaMemcpyDeviceToHost));
+                } else {
+                    (void)cudaGetLastError();
+                }
             }
             if (n_sdf > 0 && (e = cudaLibraryGetKernel(&jk.sdf_eval, jk.lib, "pt_sdf_eval_jit")) != cudaSuccess) {
                 cudaLibraryUnload(jk.lib);

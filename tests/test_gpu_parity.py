@@ -427,6 +427,27 @@ def test_v3_driver_strict_bit_exact(ptlib, monkeypatch, name, w, h, spp, spf, pl
     assert_bit_equal(got, ref, '%s v3 T=%d' % (name, regen_t))
 
 
+# ---- driver v2d (two pixels per lane, the idle one parked in shared memory) ------------------------------------------------
+@pytest.mark.parametrize('name,w,h,spp,spf,pl,jit', [
+    ('scene9', 96, 64, 4, 2, 5, 2), ('scene10', 70, 45, 3, 3, 32, 2), ('scene8', 64, 48, 2, 2, 5, 1), ('scene7', 64, 40, 2, 1, 5, 2),
+    ('scene1', 96, 72, 6, 3, 5, 2), ('scene0', 33, 17, 4, 4, 5, 2), ('scene3', 64, 48, 2, 2, 5, 1)])
+def test_v2d_driver_strict_bit_exact(ptlib, monkeypatch, name, w, h, spp, spf, pl, jit):
+    """PT_SCHED=4: per pixel the same phases on the same samples in the same order as v2 -- whichever of a lane's two
+    pixels is in registers at any time.  Ragged sizes: rows gy0 + 8 outside the image never start."""
+    monkeypatch.setenv('PT_SCHED', '4')
+    sc = ptlib.Scene.load(scene_path(name))
+    ubo = sc.pack_ubo()
+    p = sc.pack_params(1, w, h, spf, pl)
+    r = ptlib.Renderer(device=0, mode=ptlib.MODE_STRICT, jit=jit)
+    r.set_scene(ubo, sc.sdf_sources)
+    r.resize(w, h)
+    r.render(p, spp, spf)
+    got = r.read_xyz()
+    r.close()
+    ref = oracle.Oracle(ubo, [s.decode() for s in sc.sdf_sources]).render(p, spp, spf)
+    assert_bit_equal(got, ref, '%s v2d' % name)
+
+
 # ---- BVH (pt_bvh.h): the same closest-hit search as the reference's scan, section 8f-3 ---------------------------------
 def synthetic_path(name):
     import os
