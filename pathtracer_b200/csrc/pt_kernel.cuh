@@ -1692,6 +1692,9 @@ __device__ __forceinline__ void pt_render_body_v3(const PtDevScene& sc, const Pt
  * the feeders lose a lane only when it has nothing else to do.  Per pixel the samples still run in order through the
  * same phases: bit-exact in strict mode. */
 #define PT_PARK_WORDS 56
+#ifndef PT_SWAP_MIN
+#define PT_SWAP_MIN 8
+#endif
 PT_DEV void ParkSwap(float* col, PathState& ps, MarchState& ms, int& st, int& k, V3& outColor) {
     int w = 0;
 #define PT_SWF(x) { const float t_ = col[w * PT_BLOCK_THREADS]; col[w * PT_BLOCK_THREADS] = (x); (x) = t_; w++; }
@@ -1765,7 +1768,11 @@ __device__ __forceinline__ void pt_render_body_v2d(const PtDevScene& sc, const P
             /* both wait for the SDF phase: bring the one that has waited longer (the parked one) in, once */
             const bool toOlder = (stOther == PT_ST_SDF) && ((st == PT_ST_DONE) || ((st == PT_ST_SDF) && !settled));
             const bool wantSwap = (blocked && otherRunnable) || toOlder;
-            if (__ballot_sync(0xffffffffu, wantSwap) != 0u) {
+            /* the exchange costs ~250 instructions for the whole warp however many lanes take part: batch it -- wait for
+             * PT_SWAP_MIN candidates unless no lane has anything else to run */
+            const unsigned bWant = __ballot_sync(0xffffffffu, wantSwap);
+            const unsigned bRun = __ballot_sync(0xffffffffu, (st == PT_ST_NEW) || (st == PT_ST_ISECT) || (st == PT_ST_SHADE));
+            if (bWant != 0u && (__popc(bWant) >= PT_SWAP_MIN || bRun == 0u)) {
                 if (wantSwap) {
                     if (st == PT_ST_DONE) { if (cur == 0) colorA = outColor; else colorB = outColor; }
                     const int mine = st;
