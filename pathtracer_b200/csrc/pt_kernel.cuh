@@ -31,6 +31,9 @@
  *   v3  (PT_SCHED 3)  v1's loop bodies in one flat loop with gated path regeneration (PT_REGEN_T)
  *   v2d (PT_SCHED 4)  v2 with two pixels per lane, the idle one parked in shared memory: a lane only waits for the SDF
  *                     phase when both its paths do
+ *   v2s (PT_SCHED 5)  v2 with in-warp sample stealing: the warp's 32 x S samples are a pool of work items, a lane that
+ *                     finishes a path takes the next one whichever pixel it belongs to; per-sample XYZ in shared memory,
+ *                     summed per pixel in sample order at the end of a round
  * -- and the kernel entry macros.  pt_wavefront.cuh runs the same phases as separate kernels over state in HBM.
  * The kernel is instruction-cache bound (16-byte SASS, 28-45 KB per scene): single call sites and rolled loops
  * are deliberate (profiles/README.md).
@@ -534,10 +537,15 @@ PT_DEV float SolveQuarticNearest(float a, float b, float c, float d, float e) {
     return t;
 }
 
-/* shader.comp:633-679 */
-PT_DEV_NOINLINE void DupinCyclide(const Ray& ray, const PtDevCyclide& ob, int objectID, Hit& h, const bool kShadow, const bool kTie = false) {
-    const V3 lo = mulVM(mk3(ray.origin.x - ob.px, ray.origin.y - ob.py, ray.origin.z - ob.pz), ob.m);
-    const V3 ld = mulVM(ray.dir, ob.m);
+/* shader.comp:633-679.  The one out-of-line function of the kernel (the quartic solver is large and rarely reached):
+ * everything goes in and out BY VALUE, in registers.  Passing the caller's Ray / Hit by reference made their address
+ * escape, which parked the whole PathState of the in-warp drivers in local memory (176-byte stack frame, 4 % of all
+ * executed instructions local loads/stores on the scenes with a cyclide).  Returns (t, normal) of an accepted hit --
+ * `t < hT`, or `t == hT` when the caller says a tie goes to this object -- or t = -1 (roots are positive). */
+PT_DEV_NOINLINE float4 DupinCyclideCore(float rox, float roy, float roz, float rdx, float rdy, float rdz, const PtDevCyclide& ob,
+                                        float hT, int tieWins, int wantNormal) {
+    const V3 lo = mulVM(mk3(rox - ob.px, roy - ob.py, roz - ob.pz), ob.m);
+    const V3 ld = mulVM(mk3(rdx, rdy, rdz), ob.m);
     /* .xzy swizzle after the divide by scale */
     const V3 o = mk3(PTK_DIV(lo.x, ob.sx), PTK_DIV(lo.z, ob.sz), PTK_DIV(lo.y, ob.sy));
     const V3 d = mk3(PTK_DIV(ld.x, ob.sx), PTK_DIV(ld.z, ob.sz), PTK_DIV(ld.y, ob.sy));
@@ -557,10 +565,10 @@ PT_DEV_NOINLINE void DupinCyclide(const Ray& ray, const PtDevCyclide& ob, int ob
                      4.0f * C * C * D * D + 8.0f * A * C * D * o.x + 2.0f * BBmDD * dot(o, o) -
                      4.0f * (A * A * o.x * o.x + B * B * o.y * o.y);
     const float t = SolveQuarticNearest(a4, a3, a2, a1, a0);
-    if (CloserHit(t, objectID, h, kTie)) {
-        h.t = t;
-        h.objectID = objectID;
-        if (!kShadow) {
+    float4 r = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
+    if ((t < hT) || (tieWins && (t == hT))) { /* CloserHit */
+        r.x = t;
+        if (wantNormal) {
             const float x = o.x + d.x * t;
             const float y = o.y + d.y * t;
             const float z = o.z + d.z * t;
@@ -569,7 +577,21 @@ PT_DEV_NOINLINE void DupinCyclide(const Ray& ray, const PtDevCyclide& ob, int ob
             n.x = 4.0f * (x * term1 - 2.0f * A * (A * x - C * D));
             n.y = 4.0f * z * term1;
             n.z = 4.0f * y * (term1 - 2.0f * B * B);
-            h.normal = normalize(n);
+            n = normalize(n);
+            r.y = n.x; r.z = n.y; r.w = n.z;
+        }
+    }
+    return r;
+}
+PT_DEV void DupinCyclide(const Ray& ray, const PtDevCyclide& ob, int objectID, Hit& h, const bool kShadow, const bool kTie = false) {
+    const int tieWins = (kTie && (objectID < h.objectID)) ? 1 : 0;
+    const float4 r = DupinCyclideCore(ray.origin.x, ray.origin.y, ray.origin.z, ray.dir.x, ray.dir.y, ray.dir.z, ob, h.t,
+                                      tieWins, kShadow ? 0 : 1);
+    if (r.x >= 0.0f) {
+        h.t = r.x;
+        h.objectID = objectID;
+        if (!kShadow) {
+            h.normal = mk3(r.y, r.z, r.w);
             h.materialID = ob.materialID;
             h.lightID = ob.lightID;
         }
@@ -1553,6 +1575,133 @@ __device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const Pt
 }
 
 
+/* ---- driver v2s (PT_SCHED=5): v2 with in-warp sample stealing ----------------------------------------------------
+ * In v2 a lane owns one pixel and runs that pixel's samples one after the other, so a warp lives as long as its most
+ * expensive pixel: on the SDF scenes a few lanes of a tile march the fractal through all their samples while the
+ * others finished long ago (oracle cost maps, profiles/r01_steal: the mean lane carries 0.35 (menger) / 0.64
+ * (mandelbulb) / 0.72 (terrain) of the work of the busiest lane of its warp at 16 samples per pixel).
+ * Here the warp owns the 32 x S samples of its 8x4 tile as a pool of work items (item = 32 * sample + pixel, so the
+ * first 32 items are v2's initial state and primary rays start coherent); a lane that finishes a path claims the
+ * next unclaimed item, whichever pixel it belongs to (claims happen in the NEW phase, which the warp executes
+ * converged: rank by ballot, no atomics).  A finished sample's XYZ goes to a per-warp table in shared memory
+ * (S x 32 x 3 floats); when the pool is empty and all lanes idle, lane p adds pixel p's S entries IN SAMPLE ORDER --
+ * the same additions in the same order as v1 / v2, so strict mode stays bit-exact -- and the next round of S
+ * samples starts.  Scene() depends only on (pixel, sample index), never on the lane that runs it. */
+#ifndef PT_STEAL_S
+#define PT_STEAL_S 16
+#endif
+#define PT_STEAL_WORDS (3 * PT_STEAL_S * 32) /* per warp */
+static_assert(PT_STEAL_S >= 1 && PT_STEAL_S <= 20, "PT_STEAL_S: the per-sample table must fit the 48 KB of static shared memory next to the uniform block");
+enum { PT_ST_IDLE = 5 };
+
+__device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
+                                                   float4* __restrict__ image, float* s_tab, float* s_colAll) {
+    for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tileX = blockIdx.x * 16 + (warp & 1) * 8, tileY = blockIdx.y * 8 + (warp >> 1) * 4;
+    const int gx = tileX + (lane & 7), gy = tileY + (lane >> 3);
+    const bool inRange = (gx < pr.width) && (gy < pr.height);
+    float* s_col = s_colAll + warp * PT_STEAL_WORDS;
+
+    Ctx c;
+    c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
+
+    const int spf = pr.samplesPerFrame;
+    const bool warpLive = (tileX < pr.width) && (tileY < pr.height) && (spf > 0); /* warp-uniform */
+    int roundBase = 0;                                   /* sample index of the round's first sample */
+    int roundN = spf < PT_STEAL_S ? spf : PT_STEAL_S;    /* samples per pixel in this round */
+    int next = 0;                                        /* first unclaimed item of the round (warp-uniform) */
+    int item = 0;                                        /* the item this lane is working on */
+
+    int st = warpLive ? PT_ST_NEW : PT_ST_DONE;
+    V3 outColor = mk3(0.0f, 0.0f, 0.0f);
+    PathState ps;
+    PathStateInit(ps);
+    MarchState ms;
+    MarchStateInit(ms);
+
+    for (;;) {
+        const unsigned bNew = __ballot_sync(0xffffffffu, st == PT_ST_NEW);
+        const unsigned bIs = __ballot_sync(0xffffffffu, st == PT_ST_ISECT);
+        const unsigned bSh = __ballot_sync(0xffffffffu, st == PT_ST_SHADE);
+#if PT_HAS_SDF
+        const unsigned bSdf = __ballot_sync(0xffffffffu, st == PT_ST_SDF);
+#else
+        const unsigned bSdf = 0u;
+#endif
+        if ((bNew | bIs | bSdf | bSh) == 0u) {
+            if (!warpLive) break;
+            /* end of a round: every item is done.  Lane p sums pixel p's samples in index order. */
+            __syncwarp();
+            if (inRange) {
+#pragma unroll 1
+                for (int kk = 0; kk < roundN; kk++) {
+                    const float* e = s_col + (3 * kk) * 32 + lane;
+                    outColor = outColor + mk3(e[0], e[32], e[64]);
+                }
+            }
+            __syncwarp();
+            roundBase += roundN;
+            if (roundBase >= spf) break;
+            roundN = (spf - roundBase) < PT_STEAL_S ? (spf - roundBase) : PT_STEAL_S;
+            next = 0;
+            st = PT_ST_NEW;
+            continue;
+        }
+        int phase = PT_ST_NEW, best = __popc(bNew);
+        if (__popc(bIs) >= best) { best = __popc(bIs); phase = PT_ST_ISECT; }
+        if (__popc(bSh) >= best) { best = __popc(bSh); phase = PT_ST_SHADE; }
+#if PT_HAS_SDF
+        if (bSdf != 0u && (best == 0 || (best < PT_FEED_T && __popc(bSdf) >= PT_SDF_MIN))) phase = PT_ST_SDF;
+#endif
+        PT_STAT(phase, phase == PT_ST_NEW ? bNew : (phase == PT_ST_ISECT ? bIs : (phase == PT_ST_SDF ? bSdf : bSh)));
+        if (phase == PT_ST_NEW) {
+            if (st == PT_ST_NEW) {
+                if (ps.pendingFinish) { /* the sample this lane just finished: item -> (pixel, sample of the round) */
+                    const V3 col = PathColor(c, ps);
+                    float* e = s_col + (3 * (item >> 5)) * 32 + (item & 31);
+                    e[0] = col.x; e[32] = col.y; e[64] = col.z;
+                    ps.pendingFinish = false;
+                }
+                item = next + __popc(bNew & ((1u << lane) - 1u));
+                if (item < 32 * roundN) {
+                    const int q = item & 31;
+                    const int qx = tileX + (q & 7), qy = tileY + (q >> 3);
+                    if ((qx < pr.width) && (qy < pr.height)) /* else: a pixel beyond the image edge; claim again */
+                        st = PhaseNew(c, ps, (unsigned)qx, (unsigned)pr.height - (unsigned)qy, roundBase + (item >> 5));
+                } else {
+                    st = PT_ST_IDLE;
+                }
+            }
+            next += __popc(bNew);
+        } else if (phase == PT_ST_ISECT) {
+            if (st == PT_ST_ISECT) {
+                st = PhaseIsect(c, ps, ms);
+                if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
+            }
+        }
+#if PT_HAS_SDF
+        else if (phase == PT_ST_SDF) {
+#pragma unroll 1
+            for (int rep = 0; rep < PT_SDF_REPS; rep++) {
+                if (st == PT_ST_SDF) st = PhaseSdfEval(c, ps, ms);
+#if PT_SDF_EXIT > 0
+                if ((rep & 3) == 3 && __popc(__ballot_sync(0xffffffffu, st == PT_ST_SDF)) < PT_SDF_EXIT) break;
+#endif
+            }
+            if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
+        }
+#endif
+        else {
+            if (st == PT_ST_SHADE) st = PhaseShade(c, ps);
+        }
+    }
+    if (inRange) StoreTexel(pr, image, gx, gy, outColor);
+}
+
+
 /* ---- driver v3: v1's loop bodies, flattened, with gated path regeneration ----------------------------------------
  * What v1 loses on the analytic scenes is not the shape of a path but its tail: on scene1 nine lanes in ten are done
  * after two rays, yet the warp runs bounce 2's shading, shadow ray and the third and fourth intersection for the
@@ -2043,6 +2192,15 @@ __device__ __forceinline__ void pt_render_body(const PtDevScene& sc, const PtDev
         __shared__ float s_tab[PT_SH_FLOATS];                                                                \
         __shared__ float s_park[PT_PARK_WORDS * PT_BLOCK_THREADS];                                           \
         PT_KERNEL_NS::pt_render_body_v2d(sc, pr, ubo, image, s_tab, s_park);                                 \
+    }
+#elif PT_SCHED == 5
+#define PT_DEFINE_RENDER_KERNEL(name)                                                                        \
+    extern "C" __global__ void __launch_bounds__(PT_BLOCK_THREADS, PT_MIN_BLOCKS)                            \
+    name(const __grid_constant__ PtDevScene sc, const __grid_constant__ PtDevParams pr,                      \
+         const float* __restrict__ ubo, float4* __restrict__ image) {                                        \
+        __shared__ float s_tab[PT_SH_FLOATS];                                                                \
+        __shared__ float s_col[PT_STEAL_WORDS * (PT_BLOCK_THREADS / 32)];                                    \
+        PT_KERNEL_NS::pt_render_body_v2s(sc, pr, ubo, image, s_tab, s_col);                                  \
     }
 #elif PT_HAS_SDF && PT_SCHED == 2
 #define PT_DEFINE_RENDER_KERNEL(name)                                                                        \

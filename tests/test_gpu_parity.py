@@ -448,6 +448,30 @@ def test_v2d_driver_strict_bit_exact(ptlib, monkeypatch, name, w, h, spp, spf, p
     assert_bit_equal(got, ref, '%s v2d' % name)
 
 
+# ---- driver v2s (in-warp sample stealing: a warp's 32 x S samples are a pool of work items) --------------------------------
+@pytest.mark.parametrize('name,w,h,spp,spf,pl,jit,steal_s', [
+    ('scene9', 96, 64, 4, 2, 5, 2, 16), ('scene10', 70, 45, 6, 3, 32, 2, 2), ('scene8', 64, 48, 2, 2, 5, 1, 16), ('scene7', 64, 40, 2, 1, 5, 2, 8),
+    ('scene1', 96, 72, 40, 20, 5, 2, 16), ('scene0', 33, 17, 12, 12, 5, 2, 8), ('scene3', 64, 48, 2, 2, 5, 1, 16), ('scene10', 64, 48, 18, 18, 5, 2, 16)])
+def test_v2s_driver_strict_bit_exact(ptlib, monkeypatch, name, w, h, spp, spf, pl, jit, steal_s):
+    """PT_SCHED=5: whichever lane runs a sample, Scene() depends only on (pixel, sample index), and each pixel's samples
+    are added in index order at the end of a round -- the oracle's bits.  Covers several rounds per dispatch
+    (spf > PT_STEAL_S, with a short last round), several dispatches, ragged frame sizes (items of pixels beyond the
+    image edge are skipped) and pathLength 32."""
+    monkeypatch.setenv('PT_SCHED', '5')
+    monkeypatch.setenv('PT_STEAL_S', str(steal_s))
+    sc = ptlib.Scene.load(scene_path(name))
+    ubo = sc.pack_ubo()
+    p = sc.pack_params(1, w, h, spf, pl)
+    r = ptlib.Renderer(device=0, mode=ptlib.MODE_STRICT, jit=jit)
+    r.set_scene(ubo, sc.sdf_sources)
+    r.resize(w, h)
+    r.render(p, spp, spf)
+    got = r.read_xyz()
+    r.close()
+    ref = oracle.Oracle(ubo, [s.decode() for s in sc.sdf_sources]).render(p, spp, spf)
+    assert_bit_equal(got, ref, '%s v2s S=%d' % (name, steal_s))
+
+
 # ---- BVH (pt_bvh.h): the same closest-hit search as the reference's scan, section 8f-3 ---------------------------------
 def synthetic_path(name):
     import os
