@@ -1432,6 +1432,39 @@ int oracle_samples(const pt_ubo* ubo, const pt_params* pc, int gx, int gy, int f
     return 0;
 }
 
+#ifdef PT_COUNT
+/* Per-sample cost map (analysis of lane load balance, tests/lane_balance.py): for rows y0..y1-1 and sample indices
+ * 0..n-1 of every pixel, out[((gy - y0) * W + gx) * n + k] = {SDF evaluations, rays traced (path + shadow), shaded
+ * bounces} of that one Scene() call. */
+int oracle_cost_map(const pt_ubo* ubo, const pt_params* pc, int n, unsigned* out, int y0, int y1) {
+    const int W = pc->resolution[0];
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int gy = y0; gy < y1; gy++) {
+        Counters cn;
+        g_cnt = &cn;
+        for (int gx = 0; gx < W; gx++) {
+            pt_params p = *pc;
+            p.samplesPerFrame = 1;
+            for (int k = 0; k < n; k++) {
+                memset(&cn, 0, sizeof cn);
+                p.frame = k + 1; /* uint(frame - spf + 0) == k */
+                const Shader sh = make_shader(ubo, &p);
+                const uint32_t xyx = (uint32_t)gx, xyy = (uint32_t)p.resolution[1] - (uint32_t)gy;
+                const V2 uv = (2.0f * v2((float)xyx, (float)xyy) - v2((float)p.resolution[0], (float)p.resolution[1])) /
+                              (float)p.resolution[1];
+                (void)sh.Scene(xyx, xyy, uv, 0);
+                unsigned* o = out + 3 * (((size_t)(gy - y0) * W + gx) * n + k);
+                o[0] = (unsigned)cn.v[C_SDF_EVAL];
+                o[1] = (unsigned)(cn.v[C_RAYS_PATH] + cn.v[C_RAYS_SHADOW]);
+                o[2] = (unsigned)cn.v[C_BOUNCE];
+            }
+        }
+        g_cnt = nullptr;
+    }
+    return 0;
+}
+#endif
+
 /* Sum mode: image.xyz += sum over sample indices [first, first+n) of Scene(), in index order; w untouched. */
 int oracle_dispatch_sum(const pt_ubo* ubo, const pt_params* pc, int first, int n, float* image) {
     const int W = pc->resolution[0], H = pc->resolution[1];

@@ -105,6 +105,17 @@ class Oracle:
         self.L.oracle_samples(_p(self.ubo), _p(params), gx, gy, first, n, _p(out))
         return out
 
+    def cost_map(self, params, n, y0, y1):
+        """(y1-y0, W, n, 3) uint32: SDF evaluations, rays and shaded bounces of every Scene() call (needs count=True)."""
+        assert self.count
+        self._bind()
+        params = np.ascontiguousarray(params)
+        W = int(np.ravel(params['resolution'])[0])
+        out = np.zeros((y1 - y0, W, n, 3), dtype=np.uint32)
+        self.L.oracle_cost_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        self.L.oracle_cost_map(_p(self.ubo), _p(params), n, _p(out), y0, y1)
+        return out
+
     def dispatch_sum(self, params, first, n, image):
         self._bind()
         params = np.ascontiguousarray(params)

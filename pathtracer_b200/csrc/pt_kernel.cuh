@@ -1590,8 +1590,16 @@ __device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const Pt
 #ifndef PT_STEAL_S
 #define PT_STEAL_S 16
 #endif
+/* PT_STEAL_S == 0 (fast mode only): ONE round with all samplesPerFrame samples of the dispatch in the pool, and a
+ * finished sample is added straight to its pixel's running sum in shared memory (red.shared.add.f32) -- no table,
+ * hence no bound on the pool, at the price of a summation order that follows the schedule instead of the sample
+ * index (the schedule of a warp is a pure function of its inputs, so renders still repeat bit for bit in practice). */
+#if PT_STEAL_S == 0
+#define PT_STEAL_WORDS (3 * 32) /* per warp: the running XYZ sums of the tile's pixels */
+#else
 #define PT_STEAL_WORDS (3 * PT_STEAL_S * 32) /* per warp */
-static_assert(PT_STEAL_S >= 1 && PT_STEAL_S <= 20, "PT_STEAL_S: the per-sample table must fit the 48 KB of static shared memory next to the uniform block");
+#endif
+static_assert(PT_STEAL_S >= 0 && PT_STEAL_S <= 20, "PT_STEAL_S: the per-sample table must fit the 48 KB of static shared memory next to the uniform block");
 enum { PT_ST_IDLE = 5 };
 
 __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
@@ -1611,7 +1619,13 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
     const int spf = pr.samplesPerFrame;
     const bool warpLive = (tileX < pr.width) && (tileY < pr.height) && (spf > 0); /* warp-uniform */
     int roundBase = 0;                                   /* sample index of the round's first sample */
+#if PT_STEAL_S == 0
+    int roundN = spf;
+    s_col[lane] = 0.0f; s_col[32 + lane] = 0.0f; s_col[64 + lane] = 0.0f;
+    __syncwarp();
+#else
     int roundN = spf < PT_STEAL_S ? spf : PT_STEAL_S;    /* samples per pixel in this round */
+#endif
     int next = 0;                                        /* first unclaimed item of the round (warp-uniform) */
     int item = 0;                                        /* the item this lane is working on */
 
@@ -1635,6 +1649,10 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
             if (!warpLive) break;
             /* end of a round: every item is done.  Lane p sums pixel p's samples in index order. */
             __syncwarp();
+#if PT_STEAL_S == 0
+            outColor = mk3(s_col[lane], s_col[32 + lane], s_col[64 + lane]);
+            break;
+#else
             if (inRange) {
 #pragma unroll 1
                 for (int kk = 0; kk < roundN; kk++) {
@@ -1649,6 +1667,7 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
             next = 0;
             st = PT_ST_NEW;
             continue;
+#endif
         }
         int phase = PT_ST_NEW, best = __popc(bNew);
         if (__popc(bIs) >= best) { best = __popc(bIs); phase = PT_ST_ISECT; }
@@ -1661,8 +1680,13 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
             if (st == PT_ST_NEW) {
                 if (ps.pendingFinish) { /* the sample this lane just finished: item -> (pixel, sample of the round) */
                     const V3 col = PathColor(c, ps);
+#if PT_STEAL_S == 0
+                    float* e = s_col + (item & 31);
+                    atomicAdd(e, col.x); atomicAdd(e + 32, col.y); atomicAdd(e + 64, col.z);
+#else
                     float* e = s_col + (3 * (item >> 5)) * 32 + (item & 31);
                     e[0] = col.x; e[32] = col.y; e[64] = col.z;
+#endif
                     ps.pendingFinish = false;
                 }
                 item = next + __popc(bNew & ((1u << lane) - 1u));

@@ -472,6 +472,32 @@ def test_v2s_driver_strict_bit_exact(ptlib, monkeypatch, name, w, h, spp, spf, p
     assert_bit_equal(got, ref, '%s v2s S=%d' % (name, steal_s))
 
 
+@pytest.mark.parametrize('name,w,h,spf,pl', [('scene9', 96, 64, 24, 5), ('scene10', 70, 45, 16, 32), ('scene1', 50, 37, 32, 5), ('scene8', 64, 48, 8, 5)])
+def test_v2s_fast_mode_pools_the_whole_dispatch(ptlib, monkeypatch, name, w, h, spf, pl):
+    """Fast mode, PT_STEAL_S=0: one pool of 32 x samplesPerFrame items per warp, finished samples added to their pixel's
+    sum in shared memory in schedule order.  The samples themselves are those of v2 (same code, same (pixel, index)),
+    so the images differ by fp32 summation order only: relative 1e-5.  Repeated renders give the same bits."""
+    sc = ptlib.Scene.load(scene_path(name))
+    ubo = sc.pack_ubo()
+    p = sc.pack_params(1, w, h, spf, pl)
+
+    def run(sched):
+        monkeypatch.setenv('PT_SCHED', str(sched))
+        r = ptlib.Renderer(device=0, mode=ptlib.MODE_FAST, jit=2)
+        r.set_scene(ubo, sc.sdf_sources)
+        r.resize(w, h)
+        r.render(p, 2 * spf, spf)
+        out = r.read_xyz()
+        r.close()
+        return out
+
+    a, b, b2 = run(1), run(5), run(5)
+    assert np.isfinite(b).all() and (b[..., 3] == 1.0).all()
+    assert np.array_equal(b.view(np.uint32), b2.view(np.uint32))
+    scale = float(a[..., :3].max())
+    assert np.allclose(a[..., :3], b[..., :3], rtol=1e-5, atol=1e-6 * scale), float(np.abs(a - b).max())
+
+
 # ---- BVH (pt_bvh.h): the same closest-hit search as the reference's scan, section 8f-3 ---------------------------------
 def synthetic_path(name):
     import os
