@@ -6,7 +6,7 @@
   python bench.py --impl reference ...                     the reference algorithm on the host cores (CPU oracle)
 
 A "step" is one dispatch of the hot path: --spf samples per pixel over the whole frame of the workload
-(default: BASELINE config 2, scenes/scene1.json at 1920x1080, pathLength 5, camera shot 1; 64 steps x 16 = 1024 spp).
+(default: BASELINE config 2, scenes/scene1.json at 1920x1080, pathLength 5, camera shot 1; 16 steps x 64 = 1024 spp).
 1 sample = one Scene() call (shader.comp:1446-1490): one 4-wavelength hero bundle through the camera lens and the
 whole path.  `value` is device time (CUDA events on the library's stream, inputs resident in HBM, L2 flushed between
 steps); `e2e` is the same metric through the C ABI with host buffers (scene block upload + dispatch + read-back of
@@ -247,11 +247,11 @@ def run_reference(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=64)
+    ap.add_argument('--steps', type=int, default=16)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2_scene1_1080p', choices=sorted(WORKLOADS))
-    ap.add_argument('--spf', type=int, default=16, help='samples per pixel per step (one dispatch)')
+    ap.add_argument('--spf', type=int, default=64, help='samples per pixel per step (one dispatch; the sample-stealing driver pools 32 x spf items per warp)')
     ap.add_argument('--mode', default='fast', choices=['fast', 'strict'])
     ap.add_argument('--jit', type=int, default=2, help='0 static kernels, 1 NVRTC for SDF scenes only, 2 NVRTC scene-specialised')
     ap.add_argument('--pipeline', default='megakernel', choices=['megakernel', 'wavefront'])

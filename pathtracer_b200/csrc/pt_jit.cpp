@@ -100,7 +100,9 @@ int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::ve
      * Scan with many primitives: unrolled loops over baked counts spill (169 spheres: 0.10 vs 0.88 Gsamples/s rolled). */
     const bool heavy = (opt.counts[2] + opt.counts[3] + opt.counts[4]) > 0;
     const int n_scanned = opt.counts[0] + opt.counts[1] + opt.counts[2] + opt.counts[3] + opt.counts[4];
-    const int sched = (!sdf_unit.empty() || (opt.bvh && heavy)) ? 1 : 0;
+    /* v2s, the in-warp scheduler with sample stealing (profiles/r01_steal): +16..40 % over v2 on the SDF workloads, +9 % on
+     * the 74-primitive mix; scenes the reference's scan handles without SDFs stay on v1 (10.85 vs 9.85 Gsamples/s, cfg2). */
+    const int sched = (!sdf_unit.empty() || (opt.bvh && heavy)) ? 5 : 0;
     const char* sched_env = getenv("PT_SCHED");
     const int sched_eff = (sched_env && sched_env[0]) ? atoi(sched_env) : sched;
     const int no_unroll = (!sdf_unit.empty() || (!opt.bvh && n_scanned > 16)) ? 1 : 0;
