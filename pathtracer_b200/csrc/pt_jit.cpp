@@ -104,7 +104,8 @@ int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::ve
      * the 74-primitive mix; scenes the reference's scan handles without SDFs stay on v1 (10.85 vs 9.85 Gsamples/s, cfg2). */
     const int sched = (!sdf_unit.empty() || (opt.bvh && heavy)) ? 5 : 0;
     const char* sched_env = getenv("PT_SCHED");
-    const int sched_eff = (sched_env && sched_env[0]) ? atoi(sched_env) : sched;
+    int sched_eff = (sched_env && sched_env[0]) ? atoi(sched_env) : sched;
+    if (sched_eff == 6 && opt.mode != PT_MODE_FAST) sched_eff = 5; /* v2sp sums in schedule order: strict builds keep v2s' table */
     const int no_unroll = (!sdf_unit.empty() || (!opt.bvh && n_scanned > 16)) ? 1 : 0;
     /* v2s: strict mode needs the per-sample table (sums in sample order); fast mode pools the whole dispatch (0) */
     const char* steal_env = getenv("PT_STEAL_S");
@@ -116,11 +117,12 @@ int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::ve
     const Knob knobs[] = {{"PT_SCHED", sched}, {"PT_SDF_REPS", 16}, {"PT_FEED_T", 8}, {"PT_STEAL_S", -1},
                           {"PT_MIN_BLOCKS", opt.mode == PT_MODE_FAST ? min_blocks_fast : 4},
                           {"PT_NO_UNROLL", no_unroll}, {"PT_STATS", 0},
-                          {"PT_WF_REFILL", 8}, {"PT_POOL_MIN", 24}, {"PT_COOP_NORMALS", 0}, {"PT_BVH_WHILE_WHILE", 0}, {"PT_REGEN_T", 16}, {"PT_SDF_MIN", 0}, {"PT_SDF_EXIT", 0}, {"PT_SWAP_MIN", 8}};
+                          {"PT_WF_REFILL", 8}, {"PT_POOL_MIN", 24}, {"PT_COOP_NORMALS", 0}, {"PT_BVH_WHILE_WHILE", 0}, {"PT_REGEN_T", 16}, {"PT_SDF_MIN", 0}, {"PT_SDF_EXIT", 0}, {"PT_SWAP_MIN", 8}, {"PT_TILE_SLOTS", 4}};
     for (const Knob& k : knobs) {
         const char* v = getenv(k.name);
         const int val = (v && v[0]) ? atoi(v) : k.dflt;
         if (std::string(k.name) == "PT_STATS" && val == 0) continue;
+        if (std::string(k.name) == "PT_SCHED") { src += "#define PT_SCHED " + std::to_string(sched_eff) + "\n"; continue; }
         if (std::string(k.name) == "PT_STEAL_S") { src += "#define PT_STEAL_S " + std::to_string(steal_s) + "\n"; continue; }
         src += std::string("#define ") + k.name + " " + std::to_string(val) + "\n";
     }

@@ -31,6 +31,8 @@
  *   v3  (PT_SCHED 3)  v1's loop bodies in one flat loop with gated path regeneration (PT_REGEN_T)
  *   v2d (PT_SCHED 4)  v2 with two pixels per lane, the idle one parked in shared memory: a lane only waits for the SDF
  *                     phase when both its paths do
+ *   v2sp (PT_SCHED 6) v2s with persistent warps that stream over tiles claimed from a global counter, several tiles in
+ *                     flight per warp (fast mode; strict builds fall back to v2s)
  *   v2s (PT_SCHED 5)  v2 with in-warp sample stealing: the warp's 32 x S samples are a pool of work items, a lane that
  *                     finishes a path takes the next one whichever pixel it belongs to; per-sample XYZ in shared memory,
  *                     summed per pixel in sample order at the end of a round
@@ -1726,6 +1728,177 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
 }
 
 
+/* ---- driver v2sp (PT_SCHED=6, fast mode): v2s with persistent warps streaming over tiles ---------------------------
+ * v2s still drains its pool at the end of every 8x4 tile: the last paths of a tile run alone (an expensive path on the
+ * menger scene is worth a tenth of a whole tile at 64 samples per pixel), and a small samplesPerFrame leaves nothing
+ * to steal.  Here a warp does not belong to a tile.  The grid is persistent (SMs x resident CTAs); a warp claims tiles
+ * from a global counter and keeps up to PT_TILE_SLOTS of them in flight: when the items of the newest tile are all
+ * claimed the lanes that come free open the next tile while the stragglers of the older ones finish.  Per slot the
+ * warp keeps, in shared memory, the tile id, the number of finished items and the running XYZ sums of the tile's 32
+ * pixels (red.shared.add.f32, schedule order: fast mode only -- strict builds use v2s with its per-sample table).  A
+ * tile whose items are all finished is written out (StoreTexel: the reference's Accumulate) by the whole warp and its
+ * slot is recycled.  All bookkeeping happens in the NEW phase, which the warp executes converged (ballots, no locks).
+ * The tile counter lives in the module (pt_tile_ctr[0]); the last warp to leave resets it (pt_tile_ctr[1] counts
+ * leavers), so back-to-back launches on a stream need no host-side reset. */
+#ifndef PT_TILE_SLOTS
+#define PT_TILE_SLOTS 4
+#endif
+#define PT_V2SP_WORDS (PT_TILE_SLOTS * (3 * 32 + 2)) /* per warp: sums, then tile id and finished count per slot */
+
+__device__ __forceinline__ void pt_render_body_v2sp(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
+                                                    float4* __restrict__ image, float* s_tab, float* s_all, unsigned* tileCtr) {
+    for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* s_acc = s_all + warp * PT_V2SP_WORDS;                    /* [slot][channel][pixel] */
+    int* s_tile = reinterpret_cast<int*>(s_acc + PT_TILE_SLOTS * 96); /* [slot]: the tile's pixel origin x0 | y0 << 16, or -1 */
+    int* s_done = s_tile + PT_TILE_SLOTS;                           /* [slot]: finished (or skipped) items */
+    for (int i = lane; i < PT_TILE_SLOTS * 96; i += 32) s_acc[i] = 0.0f;
+    if (lane < PT_TILE_SLOTS) { s_tile[lane] = -1; s_done[lane] = 0; }
+    __syncwarp();
+
+    Ctx c;
+    c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
+
+    const int spf = pr.samplesPerFrame;
+    const int tilesX = (pr.width + 7) >> 3, tilesY = (pr.height + 3) >> 2;
+    const int numTiles = spf > 0 ? tilesX * tilesY : 0;
+    const int total = 32 * spf;      /* items per tile: item = 32 * sample + pixel */
+    int curSlot = -1, next = 0;      /* the slot items are being claimed from (warp-uniform) */
+    bool exhausted = false;          /* the global counter ran past the last tile (warp-uniform) */
+    int item = 0, slot = 0;          /* this lane's current item and the slot of its tile */
+
+    int st = PT_ST_NEW;
+    PathState ps;
+    PathStateInit(ps);
+    MarchState ms;
+    MarchStateInit(ms);
+
+    for (;;) {
+        const unsigned bNew = __ballot_sync(0xffffffffu, st == PT_ST_NEW);
+        const unsigned bIs = __ballot_sync(0xffffffffu, st == PT_ST_ISECT);
+        const unsigned bSh = __ballot_sync(0xffffffffu, st == PT_ST_SHADE);
+#if PT_HAS_SDF
+        const unsigned bSdf = __ballot_sync(0xffffffffu, st == PT_ST_SDF);
+#else
+        const unsigned bSdf = 0u;
+#endif
+        if ((bNew | bIs | bSdf | bSh) == 0u) break; /* every lane idle: no tile left and none in flight */
+        int phase = PT_ST_NEW, best = __popc(bNew);
+        if (__popc(bIs) >= best) { best = __popc(bIs); phase = PT_ST_ISECT; }
+        if (__popc(bSh) >= best) { best = __popc(bSh); phase = PT_ST_SHADE; }
+#if PT_HAS_SDF
+        if (bSdf != 0u && (best == 0 || (best < PT_FEED_T && __popc(bSdf) >= PT_SDF_MIN))) phase = PT_ST_SDF;
+#endif
+        PT_STAT(phase, phase == PT_ST_NEW ? bNew : (phase == PT_ST_ISECT ? bIs : (phase == PT_ST_SDF ? bSdf : bSh)));
+        if (phase == PT_ST_NEW) {
+            /* 1. finished samples -> their pixel's sum; per slot, count them */
+            const bool fin = (st == PT_ST_NEW) && ps.pendingFinish;
+            if (fin) {
+                const V3 col = PathColor(c, ps);
+                float* e = s_acc + slot * 96 + (item & 31);
+                atomicAdd(e, col.x); atomicAdd(e + 32, col.y); atomicAdd(e + 64, col.z);
+                atomicAdd(s_done + slot, 1);
+                ps.pendingFinish = false;
+            }
+            __syncwarp();
+            /* 2. tiles whose items are all finished: write them out, recycle the slot, wake the lanes waiting for one */
+            bool wake = false;
+#pragma unroll 1
+            for (int s = 0; s < PT_TILE_SLOTS; s++) {
+                const int org = s_tile[s];
+                if (org < 0 || s_done[s] != total) continue; /* warp-uniform */
+                const int gx = (org & 0xffff) + (lane & 7), gy = (org >> 16) + (lane >> 3);
+                float* e = s_acc + s * 96 + lane;
+                if (gx < pr.width && gy < pr.height) StoreTexel(pr, image, gx, gy, mk3(e[0], e[32], e[64]));
+                e[0] = 0.0f; e[32] = 0.0f; e[64] = 0.0f;
+                __syncwarp();
+                if (lane == 0) { s_tile[s] = -1; s_done[s] = 0; }
+                __syncwarp();
+                wake = true;
+            }
+            if (wake && st == PT_ST_IDLE) st = PT_ST_NEW;
+            /* 3. claims: rank the lanes that want an item; serve them from the current tile, opening new ones as needed */
+            const bool want = (st == PT_ST_NEW);
+            const unsigned wmask = __ballot_sync(0xffffffffu, want);
+            const int rank = __popc(wmask & ((1u << lane) - 1u));
+            int remaining = __popc(wmask), base = 0;
+            bool got = false;
+#pragma unroll 1
+            while (remaining > 0) {
+                const int avail = curSlot >= 0 ? total - next : 0;
+                const int take = avail < remaining ? avail : remaining;
+                if (want && !got && rank >= base && rank < base + take) {
+                    item = next + (rank - base);
+                    slot = curSlot;
+                    got = true;
+                }
+                next += take; base += take; remaining -= take;
+                if (remaining == 0 || exhausted) break;
+                int freeSlot = -1;
+#pragma unroll 1
+                for (int s = PT_TILE_SLOTS - 1; s >= 0; s--) if (s_tile[s] < 0) freeSlot = s;
+                if (freeSlot < 0) break; /* every slot still has stragglers: the unserved lanes wait */
+                unsigned id = 0u;
+                if (lane == 0) id = atomicAdd(tileCtr, 1u);
+                id = __shfl_sync(0xffffffffu, id, 0);
+                if (id >= (unsigned)numTiles) { exhausted = true; break; }
+                if (lane == 0) { /* the tile's pixel origin, packed: x0 | y0 << 16 */
+                    const int ty = (int)id / tilesX, tx = (int)id - ty * tilesX;
+                    s_tile[freeSlot] = (tx * 8) | ((ty * 4) << 16);
+                    s_done[freeSlot] = 0;
+                }
+                __syncwarp();
+                curSlot = freeSlot;
+                next = 0;
+            }
+            if (want) {
+                if (got) {
+                    const int org = s_tile[slot];
+                    const int q = item & 31;
+                    const int qx = (org & 0xffff) + (q & 7), qy = (org >> 16) + (q >> 3);
+                    if ((qx < pr.width) && (qy < pr.height)) st = PhaseNew(c, ps, (unsigned)qx, (unsigned)pr.height - (unsigned)qy, item >> 5);
+                    else atomicAdd(s_done + slot, 1); /* a pixel beyond the image edge: the item counts as finished, the lane claims again */
+                } else {
+                    st = PT_ST_IDLE;
+                }
+            }
+            __syncwarp();
+        } else if (phase == PT_ST_ISECT) {
+            if (st == PT_ST_ISECT) {
+                st = PhaseIsect(c, ps, ms);
+                if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
+            }
+        }
+#if PT_HAS_SDF
+        else if (phase == PT_ST_SDF) {
+#pragma unroll 1
+            for (int rep = 0; rep < PT_SDF_REPS; rep++) {
+                if (st == PT_ST_SDF) st = PhaseSdfEval(c, ps, ms);
+#if PT_SDF_EXIT > 0
+                if ((rep & 3) == 3 && __popc(__ballot_sync(0xffffffffu, st == PT_ST_SDF)) < PT_SDF_EXIT) break;
+#endif
+            }
+            if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
+        }
+#endif
+        else {
+            if (st == PT_ST_SHADE) st = PhaseShade(c, ps);
+        }
+    }
+    /* the last warp of the grid to leave rearms the tile counter for the next launch */
+    if (lane == 0) {
+        __threadfence();
+        const unsigned leavers = atomicAdd(tileCtr + 1, 1u) + 1u;
+        if (leavers == gridDim.x * gridDim.y * (PT_BLOCK_THREADS / 32)) {
+            tileCtr[0] = 0u;
+            tileCtr[1] = 0u;
+            __threadfence();
+        }
+    }
+}
+
 /* ---- driver v3: v1's loop bodies, flattened, with gated path regeneration ----------------------------------------
  * What v1 loses on the analytic scenes is not the shape of a path but its tail: on scene1 nine lanes in ten are done
  * after two rays, yet the warp runs bounce 2's shading, shadow ray and the third and fourth intersection for the
@@ -2216,6 +2389,17 @@ __device__ __forceinline__ void pt_render_body(const PtDevScene& sc, const PtDev
         __shared__ float s_tab[PT_SH_FLOATS];                                                                \
         __shared__ float s_park[PT_PARK_WORDS * PT_BLOCK_THREADS];                                           \
         PT_KERNEL_NS::pt_render_body_v2d(sc, pr, ubo, image, s_tab, s_park);                                 \
+    }
+#elif PT_SCHED == 6
+#define PT_DEFINE_RENDER_KERNEL(name)                                                                        \
+    extern "C" __device__ int pt_persistent_ctas_per_sm = PT_MIN_BLOCKS;                                     \
+    extern "C" __device__ unsigned pt_tile_ctr[2] = {0u, 0u};                                                \
+    extern "C" __global__ void __launch_bounds__(PT_BLOCK_THREADS, PT_MIN_BLOCKS)                            \
+    name(const __grid_constant__ PtDevScene sc, const __grid_constant__ PtDevParams pr,                      \
+         const float* __restrict__ ubo, float4* __restrict__ image) {                                        \
+        __shared__ float s_tab[PT_SH_FLOATS];                                                                \
+        __shared__ float s_v2sp[PT_V2SP_WORDS * (PT_BLOCK_THREADS / 32)];                                    \
+        PT_KERNEL_NS::pt_render_body_v2sp(sc, pr, ubo, image, s_tab, s_v2sp, pt_tile_ctr);                   \
     }
 #elif PT_SCHED == 5
 #define PT_DEFINE_RENDER_KERNEL(name)                                                                        \

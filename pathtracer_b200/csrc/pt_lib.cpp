@@ -28,6 +28,7 @@ struct JitKernel {
     cudaKernel_t kernel = nullptr;
     cudaKernel_t sdf_eval = nullptr; /* only for scenes with SDF snippets */
     int rows_per_block = 8;          /* image rows one CTA covers: 8, or 16 for the two-pixels-per-lane driver (PT_SCHED=4) */
+    int persistent_ctas_per_sm = 0;  /* > 0: persistent grid of SMs x this many CTAs, tiles claimed from a counter (PT_SCHED=6) */
     /* wavefront pipeline (pt_wavefront.cuh); wf_march only with SDF snippets */
     cudaKernel_t wf_gen = nullptr, wf_isect = nullptr, wf_march = nullptr, wf_shade = nullptr, wf_final = nullptr,
                  wf_ctl = nullptr;
@@ -37,6 +38,7 @@ struct JitKernel {
 
 struct pt_ctx {
     int device = 0;
+    int num_sms = 148;
     cudaStream_t stream = nullptr;
     int mode = PT_MODE_STRICT;
     int jit_policy = 1;      /* 0: never (static kernels only), 1: when the scene has SDFs, 2: always (baked counts) */
@@ -99,6 +101,12 @@ int launch(pt_ctx* ctx, const PtDevParams& dp) {
     if (ctx->active_jit) {
         const int rows = ctx->active_jit->rows_per_block;
         dim3 grid((unsigned)((dp.width + 15) / 16), (unsigned)((dp.height + rows - 1) / rows), 1), block(128, 1, 1);
+        if (ctx->active_jit->persistent_ctas_per_sm > 0) {
+            const long long tiles = (long long)((dp.width + 7) / 8) * ((dp.height + 3) / 4); /* one warp per 8x4 tile at most */
+            long long ctas = (long long)ctx->num_sms * ctx->active_jit->persistent_ctas_per_sm;
+            if (ctas > (tiles + 3) / 4) ctas = (tiles + 3) / 4;
+            grid = dim3((unsigned)(ctas > 0 ? ctas : 1), 1, 1);
+        }
         const float* ubo = ctx->d_ubo;
         float* image = ctx->d_image;
         void* args[4] = {(void*)&ctx->dev_scene, (void*)&dp, (void*)&ubo, (void*)&image};
@@ -236,6 +244,10 @@ int pt_create(int device, pt_ctx** out) {
     if (device < 0 || device >= n) return fail(nullptr, PT_ERR_ARG, "pt_create: device index out of range");
     pt_ctx* ctx = new pt_ctx();
     ctx->device = device;
+    if (cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->num_sms <= 0) {
+        (void)cudaGetLastError();
+        ctx->num_sms = 148;
+    }
     const char* pol = getenv("PT_JIT");
     if (pol && pol[0]) ctx->jit_policy = atoi(pol);
     const char* bm = getenv("PT_BVH_MIN");
@@ -365,6 +377,15 @@ int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, in
             if (e != cudaSuccess) {
                 cudaLibraryUnload(jk.lib);
                 return cuda_fail(ctx, e, "cudaLibraryGetKernel(pt_render_jit)");
+            }
+            { /* a persistent kernel says how many CTAs per SM it is built for */
+                void* dptr = nullptr;
+                size_t bytes = 0;
+                if (cudaLibraryGetGlobal(&dptr, &bytes, jk.lib, "pt_persistent_ctas_per_sm") == cudaSuccess && bytes == sizeof(int)) {
+                    PT_CUDA(ctx, cudaMemcpy(&jk.persistent_ctas_per_sm, dptr, sizeof(int), cudaMemcpyDeviceToHost));
+                } else {
+                    (void)cudaGetLastError();
+                }
             }
             { /* a kernel that covers more than 8 rows per CTA says so */
                 void* dptr = nullptr;

@@ -472,40 +472,58 @@ def test_v2s_driver_strict_bit_exact(ptlib, monkeypatch, name, w, h, spp, spf, p
     assert_bit_equal(got, ref, '%s v2s S=%d' % (name, steal_s))
 
 
-@pytest.mark.parametrize('name,w,h,spf,pl', [('scene9', 96, 64, 24, 5), ('scene10', 70, 45, 16, 32), ('scene1', 50, 37, 32, 5), ('scene8', 64, 48, 8, 5)])
-def test_v2s_fast_mode_pools_the_whole_dispatch(ptlib, monkeypatch, name, w, h, spf, pl):
-    """Fast mode, PT_STEAL_S=0: one pool of 32 x samplesPerFrame items per warp, finished samples added to their pixel's
-    sum in shared memory in schedule order.  Against the table variant of the same driver (PT_STEAL_S=16, sums in sample
-    order) the image differs by fp32 summation order only (relative 1e-5) -- except where the two builds contract a
-    multiply-add differently and a path forks at a threshold, which fast mode permits: at most 1 % of the pixels, and
-    the relRMSE between the two stays far below the Monte-Carlo noise.  Repeated renders give the same bits.  Against
-    v2 (another driver, another compilation) the same statistical statement holds."""
+@pytest.mark.parametrize('sched,name,w,h,spf,pl', [
+    (5, 'scene9', 96, 64, 24, 5), (5, 'scene10', 70, 45, 16, 32), (5, 'scene1', 50, 37, 32, 5), (5, 'scene8', 64, 48, 8, 5),
+    (6, 'scene1', 50, 37, 32, 5), (6, 'scene0', 61, 43, 1, 5), (6, 'scene0', 64, 48, 3, 5), (6, 'scene2', 200, 120, 2, 5),
+    (6, 'scene9', 96, 64, 24, 5), (6, 'scene10', 70, 45, 16, 32), (6, 'scene8', 64, 48, 8, 5)])
+def test_v2s_fast_mode_pools_the_whole_dispatch(ptlib, monkeypatch, sched, name, w, h, spf, pl):
+    """Fast mode.  PT_SCHED=5 with PT_STEAL_S=0: one pool of 32 x samplesPerFrame items per warp, finished samples added to
+    their pixel's sum in shared memory in schedule order.  PT_SCHED=6 (v2sp): persistent warps claim tiles from a global
+    counter and keep several in flight (small samplesPerFrame and ragged frame sizes exercise the slot recycling, the
+    skipped items beyond the image edge and the counter's self-reset between the two dispatches).  Repeated renders
+    give the same bits (5) / the same image up to summation order (6: which warp gets which tile varies from run to
+    run).  Against the table variant of v2s (PT_STEAL_S=16, sums in sample order) on the SAME sample indices:
+      * without SDFs the images agree to fp32 summation order (relative 1e-5) on at least 99 % of the pixels -- the
+        rest are paths that fork where the two compilations contract a multiply-add differently (nvdisasm shows a
+        handful of FFMA vs FMUL+FADD differences between any two builds of the kernel; fast mode permits that);
+      * with SDFs one ulp in a distance moves the hit point, and the numerical normal (central differences, eps 1e-4)
+        amplifies it into another path: there the two builds must be no further apart than two renders of one build
+        with disjoint sample indices (the Monte-Carlo noise), and their mean luminances agree to 1 %."""
     sc = ptlib.Scene.load(scene_path(name))
     ubo = sc.pack_ubo()
     p = sc.pack_params(1, w, h, spf, pl)
+    spp = 2 * spf
 
-    def run(sched, steal):
+    def run(sched, steal, first=0):
         monkeypatch.setenv('PT_SCHED', str(sched))
         monkeypatch.setenv('PT_STEAL_S', str(steal))
         r = ptlib.Renderer(device=0, mode=ptlib.MODE_FAST, jit=2)
         r.set_scene(ubo, sc.sdf_sources)
         r.resize(w, h)
-        r.render(p, 2 * spf, spf)
+        r.dispatch_sum(p, first, spf)
+        r.dispatch_sum(p, first + spf, spf)
+        r.finalize(p, spp)
         out = r.read_xyz()
         r.close()
         return out
 
-    v2, pooled, pooled2, table = run(1, 0), run(5, 0), run(5, 0), run(5, 16)
+    pooled, pooled2, table, table_b = run(sched, 0), run(sched, 0), run(5, 16), run(5, 16, first=1 << 20)
     assert np.isfinite(pooled).all() and (pooled[..., 3] == 1.0).all()
-    assert np.array_equal(pooled.view(np.uint32), pooled2.view(np.uint32))
     scale = float(table[..., :3].max())
-    for other, what in ((table, 'v2s table'), (v2, 'v2')):
-        close = np.isclose(other[..., :3], pooled[..., :3], rtol=1e-5, atol=1e-6 * scale).all(axis=-1)
-        frac = 1.0 - float(close.mean())
-        rr = rel_rmse(pooled, other)
-        print('%s: pooled vs %s: %.4f of the pixels beyond summation-order tolerance, relRMSE %.5f' % (name, what, frac, rr))
-        assert frac <= 0.01 and rr < 0.02, (what, frac, rr)
-    assert abs(float(pooled[..., 1].mean()) / float(table[..., 1].mean()) - 1.0) < 2e-3
+    if sched == 5:
+        assert np.array_equal(pooled.view(np.uint32), pooled2.view(np.uint32))
+    else:
+        assert np.allclose(pooled[..., :3], pooled2[..., :3], rtol=1e-5, atol=1e-6 * scale)
+    close = np.isclose(table[..., :3], pooled[..., :3], rtol=1e-5, atol=1e-6 * scale).all(axis=-1)
+    frac = 1.0 - float(close.mean())
+    diff, noise = rel_rmse(pooled, table), rel_rmse(table_b, table)
+    mean_rel = abs(float(pooled[..., 1].mean()) / float(table[..., 1].mean()) - 1.0)
+    print('%s: pooled vs table: %.4f of the pixels beyond summation-order tolerance, relRMSE %.5f (noise %.5f), mean Y rel diff %.5f'
+          % (name, frac, diff, noise, mean_rel))
+    if not sc.sdf_sources:
+        assert frac <= 0.01
+    assert diff <= 1.1 * noise + 1e-3
+    assert mean_rel < 0.01
 
 
 # ---- BVH (pt_bvh.h): the same closest-hit search as the reference's scan, section 8f-3 ---------------------------------
