@@ -109,15 +109,19 @@ int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::ve
     const int no_unroll = (!sdf_unit.empty() || (!opt.bvh && n_scanned > 16)) ? 1 : 0;
     /* v2s: strict mode needs the per-sample table (sums in sample order); fast mode pools the whole dispatch (0) */
     const char* steal_env = getenv("PT_STEAL_S");
-    const int steal_dflt = opt.mode == PT_MODE_FAST ? 0 : 16;
+    const char* park_env = getenv("PT_MPARK");
+    const int park = (park_env && park_env[0]) ? atoi(park_env) : 0;
+    /* the strict build's table shares the 48 KB of static shared memory with the parking stack */
+    const int steal_dflt = opt.mode == PT_MODE_FAST ? 0 : ((park && !sdf_unit.empty()) ? 8 : 16);
     int steal_s = (steal_env && steal_env[0]) ? atoi(steal_env) : steal_dflt;
-    if (opt.mode != PT_MODE_FAST && steal_s == 0) steal_s = 16;
+    if (opt.mode != PT_MODE_FAST && steal_s == 0) steal_s = steal_dflt;
+    if (opt.mode != PT_MODE_FAST && park && !sdf_unit.empty() && steal_s > 8) steal_s = 8;
     /* shared memory per CTA: v2d 45 KB, v2s 16 KB + 1.5 KB x PT_STEAL_S -> 5 CTAs/SM fit */
     const int min_blocks_fast = (sched_eff == 4 || (sched_eff == 5 && steal_s > 8)) ? 5 : 6;
     const Knob knobs[] = {{"PT_SCHED", sched}, {"PT_SDF_REPS", 16}, {"PT_FEED_T", 8}, {"PT_STEAL_S", -1},
                           {"PT_MIN_BLOCKS", opt.mode == PT_MODE_FAST ? min_blocks_fast : 4},
                           {"PT_NO_UNROLL", no_unroll}, {"PT_STATS", 0},
-                          {"PT_WF_REFILL", 8}, {"PT_POOL_MIN", 24}, {"PT_COOP_NORMALS", 0}, {"PT_BVH_WHILE_WHILE", 0}, {"PT_REGEN_T", 16}, {"PT_SDF_MIN", 0}, {"PT_SDF_EXIT", 0}, {"PT_SWAP_MIN", 8}, {"PT_TILE_SLOTS", 4}};
+                          {"PT_WF_REFILL", 8}, {"PT_POOL_MIN", 24}, {"PT_COOP_NORMALS", 0}, {"PT_BVH_WHILE_WHILE", 0}, {"PT_REGEN_T", 16}, {"PT_SDF_MIN", 0}, {"PT_SDF_EXIT", 0}, {"PT_SWAP_MIN", 8}, {"PT_TILE_SLOTS", 4}, {"PT_MPARK", 0}, {"PT_MPARK_CAP", 24}, {"PT_MPARK_MIN", 12}};
     for (const Knob& k : knobs) {
         const char* v = getenv(k.name);
         const int val = (v && v[0]) ? atoi(v) : k.dflt;

@@ -1604,6 +1604,37 @@ __device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const Pt
 static_assert(PT_STEAL_S >= 0 && PT_STEAL_S <= 20, "PT_STEAL_S: the per-sample table must fit the 48 KB of static shared memory next to the uniform block");
 enum { PT_ST_IDLE = 5 };
 
+/* PT_MPARK (v2s, SDF scenes): rays that must march do not wait in their lane.  At the ISECT -> SDF transition the lane
+ * writes its whole path (40 words: PathState, the march's three live values, the item it belongs to) to a per-warp
+ * stack in shared memory and is free for the next item; in the NEW phase free lanes take parked paths back -- all of
+ * them at once, as soon as PT_MPARK_MIN are waiting (or the pool is empty) -- so the SDF phase starts with a batch of
+ * marching lanes instead of the few whose rays happened to enter a bounding box in the same round, and the feeder
+ * phases no longer carry lanes that only wait for it.  A path is the same arithmetic whichever lane holds it
+ * (strict mode stays bit-exact); a full stack simply leaves the ray marching in its lane as before. */
+#ifndef PT_MPARK
+#define PT_MPARK 0
+#endif
+#ifndef PT_MPARK_CAP
+#define PT_MPARK_CAP 24
+#endif
+#ifndef PT_MPARK_MIN
+#define PT_MPARK_MIN 12
+#endif
+#define PT_MPARK_FIELDS 40
+#if PT_MPARK && PT_HAS_SDF
+#define PT_MPARK_WORDS (PT_MPARK_FIELDS * PT_MPARK_CAP) /* per warp, [field][position]: a batch of lanes hits distinct banks */
+#define PT_MPARK_XFER(X)                                                                                       \
+    X(0, ps.ray.origin.x) X(1, ps.ray.origin.y) X(2, ps.ray.origin.z) X(3, ps.ray.dir.x) X(4, ps.ray.dir.y)    \
+    X(5, ps.ray.dir.z) X(6, ps.l.x) X(7, ps.l.y) X(8, ps.l.z) X(9, ps.l.w) X(10, ps.radiance.x)                \
+    X(11, ps.radiance.y) X(12, ps.radiance.z) X(13, ps.radiance.w) X(14, ps.rayradiance.x)                    \
+    X(15, ps.rayradiance.y) X(16, ps.rayradiance.z) X(17, ps.rayradiance.w) X(18, ps.MISBRDFWeight)           \
+    X(19, ps.shDir.x) X(20, ps.shDir.y) X(21, ps.shDir.z) X(22, ps.shContrib.x) X(23, ps.shContrib.y)          \
+    X(24, ps.shContrib.z) X(25, ps.shContrib.w) X(26, ps.h.t) X(27, ps.h.normal.x) X(28, ps.h.normal.y)        \
+    X(29, ps.h.normal.z) X(30, ps.h.materialID) X(31, ps.h.lightID) X(32, ms.mt) X(33, ms.tMax)
+#else
+#define PT_MPARK_WORDS 0
+#endif
+
 __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
                                                    float4* __restrict__ image, float* s_tab, float* s_colAll) {
     for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
@@ -1613,7 +1644,11 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
     const int tileX = blockIdx.x * 16 + (warp & 1) * 8, tileY = blockIdx.y * 8 + (warp >> 1) * 4;
     const int gx = tileX + (lane & 7), gy = tileY + (lane >> 3);
     const bool inRange = (gx < pr.width) && (gy < pr.height);
-    float* s_col = s_colAll + warp * PT_STEAL_WORDS;
+    float* s_col = s_colAll + warp * (PT_STEAL_WORDS + PT_MPARK_WORDS);
+#if PT_MPARK && PT_HAS_SDF
+    float* s_park = s_col + PT_STEAL_WORDS;
+    int parked = 0;                                      /* paths on the warp's stack (warp-uniform) */
+#endif
 
     Ctx c;
     c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
@@ -1691,7 +1726,36 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
 #endif
                     ps.pendingFinish = false;
                 }
-                item = next + __popc(bNew & ((1u << lane) - 1u));
+            }
+            int rank = __popc(bNew & ((1u << lane) - 1u)), nfree = __popc(bNew);
+#if PT_MPARK && PT_HAS_SDF
+            /* free lanes take parked paths back, the whole batch at once */
+            if (parked > 0 && (parked >= PT_MPARK_MIN || next >= 32 * roundN)) {
+                const int npop = parked < nfree ? parked : nfree;
+                if (st == PT_ST_NEW && rank < npop) {
+                    const float* e = s_park + (parked - 1 - rank);
+#define PT_MPARK_LD(i, f) f = e[(i) * PT_MPARK_CAP];
+                    PT_MPARK_XFER(PT_MPARK_LD)
+#undef PT_MPARK_LD
+                    ps.seed = __float_as_uint(e[34 * PT_MPARK_CAP]);
+                    const unsigned pk = __float_as_uint(e[35 * PT_MPARK_CAP]); /* bounce | isShadow << 30 | pathAlive << 31 */
+                    ps.bounce = (int)(pk & 0x3fffffffu); ps.isShadow = ((pk >> 30) & 1u) != 0u; ps.pathAlive = (pk >> 31) != 0u;
+                    ps.shObj = __float_as_int(e[36 * PT_MPARK_CAP]);
+                    ps.h.objectID = __float_as_int(e[37 * PT_MPARK_CAP]);
+                    ms.set1 = __float_as_uint(e[38 * PT_MPARK_CAP]);
+                    item = __float_as_int(e[39 * PT_MPARK_CAP]);
+                    ms.insT = 0.0f; ms.omega = 1.70f; ms.previousRadius = 0.0f; ms.points = 0; ms.iter = 0;
+                    ms.sub = PT_SUB_SIGN;
+                    st = PT_ST_SDF;
+                }
+                parked -= npop;
+                rank -= npop; /* the lanes served above are no longer NEW */
+                nfree -= npop;
+                __syncwarp();
+            }
+#endif
+            if (st == PT_ST_NEW) {
+                item = next + rank;
                 if (item < 32 * roundN) {
                     const int q = item & 31;
                     const int qx = tileX + (q & 7), qy = tileY + (q >> 3);
@@ -1701,12 +1765,39 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
                     st = PT_ST_IDLE;
                 }
             }
-            next += __popc(bNew);
+            next += nfree;
         } else if (phase == PT_ST_ISECT) {
+            bool entered = false;
             if (st == PT_ST_ISECT) {
                 st = PhaseIsect(c, ps, ms);
                 if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
+                entered = (st == PT_ST_SDF);
             }
+#if PT_MPARK && PT_HAS_SDF
+            /* rays that found an SDF bounding box go to the stack (as many as fit), their lanes are free again */
+            const unsigned bEnt = __ballot_sync(0xffffffffu, entered);
+            if (bEnt != 0u) {
+                const int pos = parked + __popc(bEnt & ((1u << lane) - 1u));
+                if (entered && pos < PT_MPARK_CAP) {
+                    float* e = s_park + pos;
+#define PT_MPARK_ST(i, f) e[(i) * PT_MPARK_CAP] = f;
+                    PT_MPARK_XFER(PT_MPARK_ST)
+#undef PT_MPARK_ST
+                    e[34 * PT_MPARK_CAP] = __uint_as_float(ps.seed);
+                    e[35 * PT_MPARK_CAP] = __uint_as_float((unsigned)ps.bounce | ((unsigned)ps.isShadow << 30) | ((unsigned)ps.pathAlive << 31));
+                    e[36 * PT_MPARK_CAP] = __int_as_float(ps.shObj);
+                    e[37 * PT_MPARK_CAP] = __int_as_float(ps.h.objectID);
+                    e[38 * PT_MPARK_CAP] = __uint_as_float(ms.set1);
+                    e[39 * PT_MPARK_CAP] = __int_as_float(item);
+                    st = PT_ST_NEW; /* nothing pending: the NEW phase hands this lane a parked path or a new item */
+                }
+                const int room = PT_MPARK_CAP - parked, n = __popc(bEnt);
+                parked += n < room ? n : room;
+                __syncwarp();
+            }
+#else
+            (void)entered;
+#endif
         }
 #if PT_HAS_SDF
         else if (phase == PT_ST_SDF) {
@@ -2407,7 +2498,7 @@ __device__ __forceinline__ void pt_render_body(const PtDevScene& sc, const PtDev
     name(const __grid_constant__ PtDevScene sc, const __grid_constant__ PtDevParams pr,                      \
          const float* __restrict__ ubo, float4* __restrict__ image) {                                        \
         __shared__ float s_tab[PT_SH_FLOATS];                                                                \
-        __shared__ float s_col[PT_STEAL_WORDS * (PT_BLOCK_THREADS / 32)];                                    \
+        __shared__ float s_col[(PT_STEAL_WORDS + PT_MPARK_WORDS) * (PT_BLOCK_THREADS / 32)];                 \
         PT_KERNEL_NS::pt_render_body_v2s(sc, pr, ubo, image, s_tab, s_col);                                  \
     }
 #elif PT_HAS_SDF && PT_SCHED == 2
