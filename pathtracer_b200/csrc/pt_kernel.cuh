@@ -1607,7 +1607,7 @@ enum { PT_ST_IDLE = 5 };
 /* PT_MPARK (v2s, SDF scenes): rays that must march do not wait in their lane.  At the ISECT -> SDF transition the lane
  * writes its whole path (40 words: PathState, the march's three live values, the item it belongs to) to a per-warp
  * stack in shared memory and is free for the next item; in the NEW phase free lanes take parked paths back -- all of
- * them at once, as soon as PT_MPARK_MIN are waiting (or the pool is empty) -- so the SDF phase starts with a batch of
+ * them at once, as soon as PT_MPARK_MIN paths wait and as many lanes are free (or the pool is empty) -- so the SDF phase starts with a batch of
  * marching lanes instead of the few whose rays happened to enter a bounding box in the same round, and the feeder
  * phases no longer carry lanes that only wait for it.  A path is the same arithmetic whichever lane holds it
  * (strict mode stays bit-exact); a full stack simply leaves the ray marching in its lane as before. */
@@ -1730,8 +1730,8 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
             int rank = __popc(bNew & ((1u << lane) - 1u)), nfree = __popc(bNew);
 #if PT_MPARK && PT_HAS_SDF
             /* free lanes take parked paths back, the whole batch at once */
-            if (parked > 0 && (parked >= PT_MPARK_MIN || next >= 32 * roundN)) {
-                const int npop = parked < nfree ? parked : nfree;
+            const int npop = parked < nfree ? parked : nfree; /* a batch needs parked paths AND free lanes */
+            if (npop > 0 && (npop >= PT_MPARK_MIN || next >= 32 * roundN)) {
                 if (st == PT_ST_NEW && rank < npop) {
                     const float* e = s_park + (parked - 1 - rank);
 #define PT_MPARK_LD(i, f) f = e[(i) * PT_MPARK_CAP];
