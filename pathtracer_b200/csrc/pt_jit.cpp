@@ -121,7 +121,7 @@ int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::ve
     const Knob knobs[] = {{"PT_SCHED", sched}, {"PT_SDF_REPS", 16}, {"PT_FEED_T", 8}, {"PT_STEAL_S", -1},
                           {"PT_MIN_BLOCKS", opt.mode == PT_MODE_FAST ? min_blocks_fast : 4},
                           {"PT_NO_UNROLL", no_unroll}, {"PT_STATS", 0},
-                          {"PT_WF_REFILL", 8}, {"PT_POOL_MIN", 24}, {"PT_COOP_NORMALS", 0}, {"PT_BVH_WHILE_WHILE", 0}, {"PT_REGEN_T", 16}, {"PT_SDF_MIN", 0}, {"PT_SDF_EXIT", 0}, {"PT_SWAP_MIN", 8}, {"PT_TILE_SLOTS", 4}, {"PT_MPARK", 0}, {"PT_MPARK_CAP", 24}, {"PT_MPARK_MIN", 12}};
+                          {"PT_WF_REFILL", 8}, {"PT_POOL_MIN", 24}, {"PT_COOP_NORMALS", 0}, {"PT_BVH_WHILE_WHILE", 0}, {"PT_REGEN_T", 16}, {"PT_SDF_MIN", 0}, {"PT_SDF_EXIT", 0}, {"PT_SWAP_MIN", 8}, {"PT_TILE_SLOTS", 4}, {"PT_MPARK", 0}, {"PT_MPARK_CAP", 20}, {"PT_MPARK_MIN", 12}};
     for (const Knob& k : knobs) {
         const char* v = getenv(k.name);
         const int val = (v && v[0]) ? atoi(v) : k.dflt;

@@ -1604,23 +1604,25 @@ __device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const Pt
 static_assert(PT_STEAL_S >= 0 && PT_STEAL_S <= 20, "PT_STEAL_S: the per-sample table must fit the 48 KB of static shared memory next to the uniform block");
 enum { PT_ST_IDLE = 5 };
 
-/* PT_MPARK (v2s, SDF scenes): rays that must march do not wait in their lane.  At the ISECT -> SDF transition the lane
- * writes its whole path (40 words: PathState, the march's three live values, the item it belongs to) to a per-warp
- * stack in shared memory and is free for the next item; in the NEW phase free lanes take parked paths back -- all of
- * them at once, as soon as PT_MPARK_MIN paths wait and as many lanes are free (or the pool is empty) -- so the SDF phase starts with a batch of
- * marching lanes instead of the few whose rays happened to enter a bounding box in the same round, and the feeder
- * phases no longer carry lanes that only wait for it.  A path is the same arithmetic whichever lane holds it
- * (strict mode stays bit-exact); a full stack simply leaves the ray marching in its lane as before. */
+/* PT_MPARK (v2s, SDF scenes): rays that march do not wait in a lane.  The march lengths are heavy-tailed (1 .. 512
+ * evaluations), so whatever batch of lanes enters the SDF phase together, its later executions serve the few long
+ * rays only (61-73 % of v2's SDF executions find 1-4 lanes, profiles/r01_sdfsched).  With PT_MPARK a lane whose ray
+ * must march -- after ISECT found a bounding box, and again after every SDF execution that did not finish it -- writes
+ * the whole path (49 words: PathState, MarchState, the item it belongs to) to a per-warp stack in shared memory and is
+ * free for other work; in the NEW phase free lanes take parked paths back, a batch at a time: as soon as
+ * PT_MPARK_MIN paths wait and as many lanes are free (or the pool is empty).  Every SDF execution thus starts with a
+ * batch, and the feeder phases carry no lanes that only wait for it.  A path is the same arithmetic whichever lane
+ * holds it (strict mode stays bit-exact); with a full stack the ray simply stays in its lane as before. */
 #ifndef PT_MPARK
 #define PT_MPARK 0
 #endif
 #ifndef PT_MPARK_CAP
-#define PT_MPARK_CAP 24
+#define PT_MPARK_CAP 20
 #endif
 #ifndef PT_MPARK_MIN
 #define PT_MPARK_MIN 12
 #endif
-#define PT_MPARK_FIELDS 40
+#define PT_MPARK_FIELDS 49
 #if PT_MPARK && PT_HAS_SDF
 #define PT_MPARK_WORDS (PT_MPARK_FIELDS * PT_MPARK_CAP) /* per warp, [field][position]: a batch of lanes hits distinct banks */
 #define PT_MPARK_XFER(X)                                                                                       \
@@ -1630,7 +1632,9 @@ enum { PT_ST_IDLE = 5 };
     X(15, ps.rayradiance.y) X(16, ps.rayradiance.z) X(17, ps.rayradiance.w) X(18, ps.MISBRDFWeight)           \
     X(19, ps.shDir.x) X(20, ps.shDir.y) X(21, ps.shDir.z) X(22, ps.shContrib.x) X(23, ps.shContrib.y)          \
     X(24, ps.shContrib.z) X(25, ps.shContrib.w) X(26, ps.h.t) X(27, ps.h.normal.x) X(28, ps.h.normal.y)        \
-    X(29, ps.h.normal.z) X(30, ps.h.materialID) X(31, ps.h.lightID) X(32, ms.mt) X(33, ms.tMax)
+    X(29, ps.h.normal.z) X(30, ps.h.materialID) X(31, ps.h.lightID) X(32, ms.mt) X(33, ms.tMax)               \
+    X(40, ms.insT) X(41, ms.omega) X(42, ms.previousRadius) X(43, ms.ksign) X(44, ms.probe) X(45, ms.nrm0)     \
+    X(46, ms.nrm1) X(47, ms.nrm2)
 #else
 #define PT_MPARK_WORDS 0
 #endif
@@ -1713,6 +1717,7 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
         if (bSdf != 0u && (best == 0 || (best < PT_FEED_T && __popc(bSdf) >= PT_SDF_MIN))) phase = PT_ST_SDF;
 #endif
         PT_STAT(phase, phase == PT_ST_NEW ? bNew : (phase == PT_ST_ISECT ? bIs : (phase == PT_ST_SDF ? bSdf : bSh)));
+        bool entered = false; /* this lane's ray found an SDF bounding box in this iteration's ISECT phase */
         if (phase == PT_ST_NEW) {
             if (st == PT_ST_NEW) {
                 if (ps.pendingFinish) { /* the sample this lane just finished: item -> (pixel, sample of the round) */
@@ -1744,8 +1749,8 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
                     ps.h.objectID = __float_as_int(e[37 * PT_MPARK_CAP]);
                     ms.set1 = __float_as_uint(e[38 * PT_MPARK_CAP]);
                     item = __float_as_int(e[39 * PT_MPARK_CAP]);
-                    ms.insT = 0.0f; ms.omega = 1.70f; ms.previousRadius = 0.0f; ms.points = 0; ms.iter = 0;
-                    ms.sub = PT_SUB_SIGN;
+                    const unsigned mk = __float_as_uint(e[48 * PT_MPARK_CAP]); /* points | iter << 12 | sub << 24 */
+                    ms.points = (int)(mk & 0xfffu); ms.iter = (int)((mk >> 12) & 0xfffu); ms.sub = (int)(mk >> 24);
                     st = PT_ST_SDF;
                 }
                 parked -= npop;
@@ -1767,35 +1772,12 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
             }
             next += nfree;
         } else if (phase == PT_ST_ISECT) {
-            bool entered = false;
             if (st == PT_ST_ISECT) {
                 st = PhaseIsect(c, ps, ms);
                 if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
                 entered = (st == PT_ST_SDF);
             }
-#if PT_MPARK && PT_HAS_SDF
-            /* rays that found an SDF bounding box go to the stack (as many as fit), their lanes are free again */
-            const unsigned bEnt = __ballot_sync(0xffffffffu, entered);
-            if (bEnt != 0u) {
-                const int pos = parked + __popc(bEnt & ((1u << lane) - 1u));
-                if (entered && pos < PT_MPARK_CAP) {
-                    float* e = s_park + pos;
-#define PT_MPARK_ST(i, f) e[(i) * PT_MPARK_CAP] = f;
-                    PT_MPARK_XFER(PT_MPARK_ST)
-#undef PT_MPARK_ST
-                    e[34 * PT_MPARK_CAP] = __uint_as_float(ps.seed);
-                    e[35 * PT_MPARK_CAP] = __uint_as_float((unsigned)ps.bounce | ((unsigned)ps.isShadow << 30) | ((unsigned)ps.pathAlive << 31));
-                    e[36 * PT_MPARK_CAP] = __int_as_float(ps.shObj);
-                    e[37 * PT_MPARK_CAP] = __int_as_float(ps.h.objectID);
-                    e[38 * PT_MPARK_CAP] = __uint_as_float(ms.set1);
-                    e[39 * PT_MPARK_CAP] = __int_as_float(item);
-                    st = PT_ST_NEW; /* nothing pending: the NEW phase hands this lane a parked path or a new item */
-                }
-                const int room = PT_MPARK_CAP - parked, n = __popc(bEnt);
-                parked += n < room ? n : room;
-                __syncwarp();
-            }
-#else
+#if !(PT_MPARK && PT_HAS_SDF)
             (void)entered;
 #endif
         }
@@ -1814,6 +1796,34 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
         else {
             if (st == PT_ST_SHADE) st = PhaseShade(c, ps);
         }
+#if PT_MPARK && PT_HAS_SDF
+        /* the one parking site: rays that entered a bounding box in this ISECT phase, or that this SDF execution did not
+         * finish, go to the stack (as many as fit); their lanes are free again */
+        if (phase == PT_ST_ISECT || phase == PT_ST_SDF) {
+            const bool doPark = (phase == PT_ST_ISECT) ? entered : (st == PT_ST_SDF);
+            const unsigned bEnt = __ballot_sync(0xffffffffu, doPark);
+            if (bEnt != 0u) {
+                const int pos = parked + __popc(bEnt & ((1u << lane) - 1u));
+                if (doPark && pos < PT_MPARK_CAP) {
+                    float* e = s_park + pos;
+#define PT_MPARK_ST(i, f) e[(i) * PT_MPARK_CAP] = f;
+                    PT_MPARK_XFER(PT_MPARK_ST)
+#undef PT_MPARK_ST
+                    e[34 * PT_MPARK_CAP] = __uint_as_float(ps.seed);
+                    e[35 * PT_MPARK_CAP] = __uint_as_float((unsigned)ps.bounce | ((unsigned)ps.isShadow << 30) | ((unsigned)ps.pathAlive << 31));
+                    e[36 * PT_MPARK_CAP] = __int_as_float(ps.shObj);
+                    e[37 * PT_MPARK_CAP] = __int_as_float(ps.h.objectID);
+                    e[38 * PT_MPARK_CAP] = __uint_as_float(ms.set1);
+                    e[39 * PT_MPARK_CAP] = __int_as_float(item);
+                    e[48 * PT_MPARK_CAP] = __uint_as_float((unsigned)ms.points | ((unsigned)ms.iter << 12) | ((unsigned)ms.sub << 24));
+                    st = PT_ST_NEW; /* nothing pending: the NEW phase hands this lane a parked path or a new item */
+                }
+                const int room = PT_MPARK_CAP - parked, n = __popc(bEnt);
+                parked += n < room ? n : room;
+                __syncwarp();
+            }
+        }
+#endif
     }
     if (inRange) StoreTexel(pr, image, gx, gy, outColor);
 }
