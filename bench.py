@@ -157,14 +157,18 @@ class ClockSampler:
 
 def ncu_traffic(wl):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the workload's kernel, from the committed
-    `ncu --set full` capture of the same bench command (profiles/r01_final/ncu_summary_*.json); None if not captured."""
-    path = os.path.join(ROOT, 'profiles', 'r01_final', 'ncu_summary_%s.json' % wl.split('_')[0])
-    try:
-        with open(path) as f:
-            d = json.load(f)
-        return d['traffic_bytes_per_launch'] if d.get('workload') == wl else None
-    except (OSError, ValueError, KeyError):
-        return None
+    `ncu --set full` capture of the same bench command (profiles/r01_final4/ or r01_final/ncu_summary_*.json; the texel
+    read-modify-write does not depend on the samples per launch); None if not captured."""
+    for sub in ('r01_final4', 'r01_final'):
+        path = os.path.join(ROOT, 'profiles', sub, 'ncu_summary_%s.json' % wl.split('_')[0])
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            if d.get('workload') == wl:
+                return d['traffic_bytes_per_launch']
+        except (OSError, ValueError, KeyError):
+            pass
+    return None
 
 
 def oracle_for(scene_name, count=False, threads=0):
