@@ -99,29 +99,89 @@ def flops_per_sample(cnt, scene_counts, c_sdf, c_mat):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md's clocks line).  The sampler is
-    started before the warm-up (nvidia-smi takes a moment to come up); only rows stamped inside [mark_begin, mark_end]
-    are used."""
+    """SM clock, power and throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).  Polled through
+    NVML in a thread (nvidia_ml_py, every 10 ms: also a 100 ms region gets its samples); if NVML cannot be used the
+    sampler falls back to `nvidia-smi -lms 50` (started before the warm-up: it takes a moment to come up and its
+    rows arrive through a pipe).  Only samples stamped inside [mark_begin, mark_end] are used."""
 
-    def __init__(self, index):
-        self.rows = []
+    REASONS = ((0x8, 'hw_slowdown'), (0x40, 'hw_thermal_slowdown'), (0x20, 'sw_thermal_slowdown'), (0x4, 'sw_power_cap'))
+
+    def __init__(self, index, uuid=None):
+        self.rows = []      # (time, sm_mhz, sm_max_mhz, power_w, [reason names])
         self.proc = None
-        self.index = index
+        self.index = index  # NVML / nvidia-smi index; `uuid` (of the CUDA device) wins when NVML knows it
+        self.uuid = uuid
         self.t0 = self.t1 = None
+        self.source = None
+        self._stop = threading.Event()
+        self._thread = None
 
-    def start(self):
+    # ---- NVML ------------------------------------------------------------------------------------------------
+    def _start_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = None
+        if self.uuid:
+            try:
+                h = nv.nvmlDeviceGetHandleByUUID(('GPU-' + str(self.uuid)).encode())
+            except Exception:
+                h = None
+        if h is None:
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or getattr(nv, 'nvmlDeviceGetCurrentClocksThrottleReasons')
+        float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))  # probe once: raises here, not in the thread
+        int(get_reasons(h))
+
+        def poll():
+            while not self._stop.is_set():
+                try:
+                    sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    mask = int(get_reasons(h))
+                    try:
+                        pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                    except Exception:
+                        pw = None
+                    self.rows.append((time.time(), sm, mx, pw, [n for bit, n in self.REASONS if mask & bit]))
+                except Exception:
+                    pass
+                self._stop.wait(0.01)
+
+        self._thread = threading.Thread(target=poll, daemon=True)
+        self._thread.start()
+        self.source = 'nvml'
+
+    # ---- nvidia-smi ------------------------------------------------------------------------------------------
+    def _start_smi(self):
         q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits',
+                                      '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+
+        def read():
+            for line in self.proc.stdout:
+                r = [t.strip() for t in line.split(',')]
+                try:
+                    reasons = [n for n, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8])
+                               if v.lower().startswith('active')]
+                    self.rows.append((time.time(), float(r[1]), float(r[2]), float(r[3]), reasons))
+                except (ValueError, IndexError):
+                    continue
+
+        self._thread = threading.Thread(target=read, daemon=True)
+        self._thread.start()
+        self.source = 'nvidia-smi'
+
+    def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits',
-                                          '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            self._start_nvml()
+            return
+        except Exception:
+            self.source = None
+        try:
+            self._start_smi()
         except OSError:
             self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), [t.strip() for t in line.split(',')]))
 
     def mark_begin(self):
         self.t0 = time.time()
@@ -137,22 +197,20 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 - 0.05 <= t <= (self.t1 or t) + 0.1]
-        for r in inside or [r for _, r in self.rows[-3:]]:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                power.append(float(r[3]))
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        if not sm:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
-        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm),
-                'samples_in_timed_region': len(inside), 'power_w_max': max(power) if power else None}
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
+        rows = list(self.rows)
+        slack = 0.0 if self.source == 'nvml' else 0.1
+        inside = [r for r in rows if self.t0 is not None and self.t0 - slack / 2 <= r[0] <= (self.t1 or r[0]) + slack]
+        used = inside or rows[-3:]
+        if not used:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0, 'source': self.source}
+        reasons = sorted({n for r in used for n in r[4]})
+        power = [r[3] for r in used if r[3] is not None]
+        return {'sm_mhz': float(np.median([r[1] for r in used])), 'sm_max_mhz': float(max(r[2] for r in used)), 'reasons': reasons,
+                'samples': len(used), 'samples_in_timed_region': len(inside), 'power_w_max': max(power) if power else None,
+                'source': self.source}
 
 
 def ncu_traffic(wl):
@@ -315,7 +373,11 @@ def main():
             with torch.cuda.stream(ext):
                 flush.fill_(rank & 0xFF)
 
-    sampler = ClockSampler(local_rank)
+    try:
+        dev_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        dev_uuid = None
+    sampler = ClockSampler(local_rank, dev_uuid)
     if rank == 0:
         sampler.start()
     for i in range(Wm):

@@ -96,3 +96,49 @@ def test_bench_refuses_to_run_without_gpu():
         pytest.skip('GPU present')
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '1', '--warmup', '0'], capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and 'no CPU fallback' in (r.stderr + r.stdout)
+
+
+def test_bench_clock_sampler_nvml_path_and_fallback(monkeypatch):
+    """bench.py samples SM clock / power / throttle reasons during the timed region through NVML (a fake module here);
+    only samples inside [mark_begin, mark_end] count, reason bits map to the contract's names, and when NVML is
+    unusable the sampler falls back (nvidia-smi; absent in this container: an empty but well-formed result)."""
+    import time
+    import types
+    sys.path.insert(0, ROOT)
+    import bench
+
+    state = {'clock': 1965, 'mask': 0}
+    fake = types.ModuleType('pynvml')
+    fake.NVML_CLOCK_SM = 1
+    fake.nvmlInit = lambda: None
+    fake.nvmlDeviceGetHandleByIndex = lambda i: ('handle', i)
+    fake.nvmlDeviceGetMaxClockInfo = lambda h, k: 1965
+    fake.nvmlDeviceGetClockInfo = lambda h, k: state['clock']
+    fake.nvmlDeviceGetCurrentClocksEventReasons = lambda h: state['mask']
+    fake.nvmlDeviceGetPowerUsage = lambda h: 312800
+    monkeypatch.setitem(sys.modules, 'pynvml', fake)
+    s = bench.ClockSampler(0)
+    s.start()
+    assert s.source == 'nvml'
+    state['clock'], state['mask'] = 1200, 0x8            # before the window: must not be reported
+    time.sleep(0.05)
+    state['clock'], state['mask'] = 1965, 0x4            # sw_power_cap inside the window
+    time.sleep(0.03)
+    s.mark_begin()
+    time.sleep(0.12)
+    s.mark_end()
+    state['clock'], state['mask'] = 1000, 0x40
+    time.sleep(0.03)
+    out = s.stop()
+    assert out['source'] == 'nvml' and out['samples_in_timed_region'] >= 5 and out['samples'] == out['samples_in_timed_region']
+    assert out['sm_mhz'] == 1965.0 and out['sm_max_mhz'] == 1965.0 and out['reasons'] == ['sw_power_cap']
+    assert abs(out['power_w_max'] - 312.8) < 1e-6
+
+    def broken():
+        raise RuntimeError('no driver')
+    fake.nvmlInit = broken
+    s = bench.ClockSampler(0)
+    s.start()
+    s.mark_begin(); s.mark_end()
+    out = s.stop()
+    assert out['source'] in (None, 'nvidia-smi') and 'sm_mhz' in out and 'reasons' in out and 'samples' in out
