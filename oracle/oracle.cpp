@@ -1568,6 +1568,30 @@ void oracle_math_eval(int fn, const float* x, const float* y, float* out, size_t
         }
     }
 }
+/* The samplers on their own (statistical known-answer tests): n draws from one PCG stream.
+ * kind 0 SampleUniformUnitDisk -> (x, y, 0); 1 SampleUniformUnitSphere; 2 SampleCosineDirectionHemisphere(normal n3);
+ * 3 SampleCosineUnitCone(cosThetaMax = param) in the cone's frame; 4 ToWorld(SampleCosineUnitCone(param), n3). */
+void oracle_sample(int kind, unsigned seed, size_t n, float param, const float* n3, float* out) {
+    uint32_t s = seed;
+    const V3 nn = n3 ? v3(n3[0], n3[1], n3[2]) : v3(0.0f, 0.0f, 1.0f);
+    for (size_t i = 0; i < n; i++) {
+        V3 r = v3(0.0f);
+        if (kind == 0) { V2 d = Shader::SampleUniformUnitDisk(s); r = v3(d.x, d.y, 0.0f); }
+        else if (kind == 1) r = Shader::SampleUniformUnitSphere(s);
+        else if (kind == 2) r = Shader::SampleCosineDirectionHemisphere(nn, s);
+        else if (kind == 3) r = Shader::SampleCosineUnitCone(s, param);
+        else r = Shader::ToWorld(Shader::SampleCosineUnitCone(s, param), nn);
+        out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
+    }
+}
+float oracle_cone_pdf(float cosTheta, float cosThetaMax) { return Shader::CosineUnitConePDF(cosTheta, cosThetaMax); }
+float oracle_mis_weight(float pdf1, float pdf2) { return Shader::MISPowerHeuristicsBeta2(pdf1, pdf2); }
+void oracle_orthonormal_basis(const float* n3, float* b6) {
+    V3 b1 = v3(0.0f), b2 = v3(0.0f);
+    Shader::OrthonormalBasis(b1, b2, v3(n3[0], n3[1], n3[2]));
+    b6[0] = b1.x; b6[1] = b1.y; b6[2] = b1.z; b6[3] = b2.x; b6[4] = b2.y; b6[5] = b2.z;
+}
+
 int oracle_num_counters(void) { return C_N; }
 const char* oracle_counter_names(void) {
     return "samples,rays_path,rays_shadow,sphere,sphere_hit,plane,plane_hit,bsphere,box,box_hit,lens,slice_hit,"

@@ -262,3 +262,101 @@ def test_spectral_estimator_normalisation():
         acc += float(emit[0]) * cmf.astype(np.float64) * (330.0 / 440.0) * (1.0 + arcs / 4.0)
     want = acc * 1.0                           # sum over 1 nm bins
     assert np.allclose(got, want, rtol=0.015), (got, want)   # ~2e5 samples: Monte-Carlo error well below 1 %
+
+
+# ---- the samplers against their closed forms ("analytic / statistical") --------------------------------
+def _samples(kind, n, param=0.0, normal=None, seed=12345):
+    import ctypes as C
+    L = oracle.lib()
+    L.oracle_sample.argtypes = [C.c_int, C.c_uint, C.c_size_t, C.c_float, C.c_void_p, C.c_void_p]
+    out = np.zeros((n, 3), dtype=np.float32)
+    nn = None if normal is None else np.ascontiguousarray(normal, dtype=np.float32)
+    L.oracle_sample(kind, seed, n, param, None if nn is None else nn.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out.astype(np.float64)
+
+
+def test_uniform_disk_and_sphere_samplers():
+    """SampleUniformUnitDisk (shader.comp:976-982): inside the unit disk, uniform in area (E[r^2] = 1/2, mean 0).
+    SampleUniformUnitSphere (984-997): unit length, mean 0, E[z^2] = 1/3, z uniform on [-1, 1]."""
+    n = 400000
+    d = _samples(0, n)
+    r2 = (d[:, :2] ** 2).sum(1)
+    assert r2.max() <= 1.0 + 1e-6 and np.all(d[:, 2] == 0.0)
+    assert abs(r2.mean() - 0.5) < 3e-3 and np.abs(d[:, :2].mean(0)).max() < 4e-3
+    s = _samples(1, n)
+    assert np.abs(np.linalg.norm(s, axis=1) - 1.0).max() < 1e-5
+    assert np.abs(s.mean(0)).max() < 4e-3
+    assert np.abs((s ** 2).mean(0) - 1.0 / 3.0).max() < 3e-3
+    hist, _ = np.histogram(s[:, 2], bins=10, range=(-1.0, 1.0))
+    assert np.abs(hist / n - 0.1).max() < 3e-3
+
+
+def test_cosine_hemisphere_sampler_matches_its_pdf():
+    """SampleCosineDirectionHemisphere (999-1003): normalize(n + uniform sphere) is cosine-weighted about n, the pdf
+    CosineDirectionPDF = cos/pi (1005-1010): E[cos] = 2/3, E[cos^2] = 1/2, nothing below the horizon, symmetric about n."""
+    n = 400000
+    nrm = np.array([0.36, -0.48, 0.8])
+    v = _samples(2, n, normal=nrm)
+    c = v @ nrm
+    assert np.abs(np.linalg.norm(v, axis=1) - 1.0).max() < 1e-5
+    assert c.min() > -1e-6
+    assert abs(c.mean() - 2.0 / 3.0) < 2e-3 and abs((c ** 2).mean() - 0.5) < 2e-3
+    tangential = v - np.outer(c, nrm)
+    assert np.abs(tangential.mean(0)).max() < 4e-3
+
+
+@pytest.mark.parametrize('cos_max', [0.95, 0.6, 0.1])
+def test_cosine_cone_sampler_matches_its_pdf(cos_max):
+    """SampleCosineUnitCone (1012-1023) stays inside the cone of half-angle theta_max and is cosine-weighted there:
+    CosineUnitConePDF = cos / (pi sin^2 theta_max) (1025-1028) integrates to 1 over the cone, and the sample mean of
+    cos equals the pdf's E[cos] = (2/3)(1 - cos^3 theta_max) / sin^2 theta_max.  ToWorld (1113-1119) carries the cone
+    onto an arbitrary axis without changing the angles."""
+    import ctypes as C
+    n = 400000
+    v = _samples(3, n, param=cos_max)
+    assert np.abs(np.linalg.norm(v, axis=1) - 1.0).max() < 1e-5
+    assert v[:, 2].min() >= cos_max - 2e-4   # fp32 rounding of the half-angle construction near the rim
+    sin2 = 1.0 - cos_max ** 2
+    want = (2.0 / 3.0) * (1.0 - cos_max ** 3) / sin2
+    assert abs(v[:, 2].mean() - want) < 2e-3
+    assert np.abs(v[:, :2].mean(0)).max() < 4e-3
+    # the pdf integrates to one: midpoint rule over cos in [cos_max, 1] of pdf(cos) * 2 pi
+    L = oracle.lib()
+    L.oracle_cone_pdf.restype = C.c_float
+    L.oracle_cone_pdf.argtypes = [C.c_float, C.c_float]
+    m = 2000
+    cs = cos_max + (np.arange(m) + 0.5) * (1.0 - cos_max) / m
+    integral = sum(L.oracle_cone_pdf(float(c), float(cos_max)) for c in cs) * 2.0 * np.pi * (1.0 - cos_max) / m
+    assert abs(integral - 1.0) < 1e-3
+    # histogram of cos against the pdf
+    hist, edges = np.histogram(v[:, 2], bins=8, range=(cos_max, 1.0))
+    lo, hi = edges[:-1], edges[1:]
+    expect = (hi ** 2 - lo ** 2) / sin2
+    assert np.abs(hist / n - expect).max() < 4e-3
+    axis = np.array([-0.6, 0.0, 0.8])
+    w = _samples(4, n, param=cos_max, normal=axis)
+    assert np.allclose(w @ axis, v[:, 2], atol=2e-6)
+
+
+def test_orthonormal_basis_and_mis_weight():
+    """OrthonormalBasis (1093-1103, Duff et al. without the sign trick, special-cased at n.z < -0.9999999): b1, b2, n
+    orthonormal for random n and at the pole.  MISPowerHeuristicsBeta2 (1293-1296): w(a, b) + w(b, a) = 1."""
+    import ctypes as C
+    L = oracle.lib()
+    L.oracle_orthonormal_basis.argtypes = [C.c_void_p, C.c_void_p]
+    L.oracle_mis_weight.restype = C.c_float
+    L.oracle_mis_weight.argtypes = [C.c_float, C.c_float]
+    rng = np.random.default_rng(5)
+    ns = rng.normal(size=(2000, 3))
+    ns /= np.linalg.norm(ns, axis=1, keepdims=True)
+    ns = np.vstack([ns, [[0.0, 0.0, 1.0], [0.0, 0.0, -1.0], [1.0, 0.0, 0.0]]]).astype(np.float32)
+    for nvec in ns:
+        b = np.zeros(6, dtype=np.float32)
+        L.oracle_orthonormal_basis(np.ascontiguousarray(nvec).ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
+        b1, b2, n64 = b[:3].astype(np.float64), b[3:].astype(np.float64), nvec.astype(np.float64)
+        tol = 2e-3 if nvec[2] < -0.99 else 2e-5   # 1 / (1 + n.z) loses digits towards the south pole
+        assert abs(np.dot(b1, b1) - 1.0) < tol and abs(np.dot(b2, b2) - 1.0) < tol
+        assert abs(np.dot(b1, b2)) < tol and abs(np.dot(b1, n64)) < tol and abs(np.dot(b2, n64)) < tol
+    for a, b in ((0.3, 0.7), (1e-3, 5.0), (2.0, 2.0)):
+        assert abs(L.oracle_mis_weight(a, b) + L.oracle_mis_weight(b, a) - 1.0) < 1e-6
+    assert L.oracle_mis_weight(1.0, 0.0) == 1.0
