@@ -1584,6 +1584,22 @@ void oracle_sample(int kind, unsigned seed, size_t n, float param, const float* 
         out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
     }
 }
+/* TracePath (shader.comp:1393-1407) on its own: the mean radiance of n paths started with the same ray and wavelength
+ * bundle, one PCG stream.  For the closed-form direct-lighting check of tests/test_oracle_kat.py. */
+void oracle_trace_path(const pt_ubo* ubo, const pt_params* pc, const float* o3, const float* d3, const float* l4,
+                       unsigned seed, size_t n, double* mean4) {
+    const Shader sh = make_shader(ubo, pc);
+    uint32_t s = seed;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (size_t i = 0; i < n; i++) {
+        Ray ray;
+        ray.origin = v3(o3[0], o3[1], o3[2]);
+        ray.dir = v3(d3[0], d3[1], d3[2]);
+        const V4 r = sh.TracePath(v4(l4[0], l4[1], l4[2], l4[3]), ray, s);
+        acc[0] += r.x; acc[1] += r.y; acc[2] += r.z; acc[3] += r.w;
+    }
+    for (int k = 0; k < 4; k++) mean4[k] = acc[k] / (double)(n ? n : 1);
+}
 float oracle_cone_pdf(float cosTheta, float cosThetaMax) { return Shader::CosineUnitConePDF(cosTheta, cosThetaMax); }
 float oracle_mis_weight(float pdf1, float pdf2) { return Shader::MISPowerHeuristicsBeta2(pdf1, pdf2); }
 void oracle_orthonormal_basis(const float* n3, float* b6) {

@@ -360,3 +360,41 @@ def test_orthonormal_basis_and_mis_weight():
     for a, b in ((0.3, 0.7), (1e-3, 5.0), (2.0, 2.0)):
         assert abs(L.oracle_mis_weight(a, b) + L.oracle_mis_weight(b, a) - 1.0) < 1e-6
     assert L.oracle_mis_weight(1.0, 0.0) == 1.0
+
+
+@pytest.mark.parametrize('a,h,R', [(0.0, 3.0, 1.0), (2.0, 3.0, 1.0), (4.0, 2.0, 1.0), (1.0, 5.0, 0.5)])
+def test_direct_lighting_matches_the_closed_form(a, h, R):
+    """A Lambertian plane under a spherical black-body emitter, nothing else: the radiance leaving the point x0 = (a, 0, 0)
+    is direct light only, and for a sphere of radius R wholly above the horizon at distance d it is exactly
+        L_o(lambda) = rho(lambda) * L_e(lambda) * (R / d)^2 * cos(theta_c)
+    (irradiance of a uniform sphere: pi L (R/d)^2 cos theta_c; BRDF rho / pi).  TracePath with pathLength 2 combines the
+    light sample (cone towards the emitter's bounding sphere, shader.comp:1298-1343) and the BSDF sample that hits the
+    emitter (1359-1364) by the power heuristic, with Russian roulette on both.  The reference weights each pair of
+    samples with pdfs of two different directions and does not compensate the roulette on the light sample, so it is
+    not exactly unbiased; measured here: within 0.6 % of the closed form (2 M paths per case).  The gate is 2 %: a
+    missing pi, cosine, 1/pdf or a wrong cone would show as tens of percent."""
+    import ctypes as C
+    L = oracle.lib()
+    L.oracle_trace_path.argtypes = [C.c_void_p] * 5 + [C.c_uint, C.c_size_t, C.c_void_p]
+    L.oracle_emit.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+    L.oracle_spd.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p]
+    T, lum = 5500.0, 3.0
+    scene = {'camera': pack.load_scene(scene_path('scene0'))['camera'],
+             'sphere': [{'position': [0, h, 0], 'radius': R, 'materialID': 1, 'lightID': 1}],
+             'plane': [{'position': [0, 0, 0], 'materialID': 1, 'lightID': 0}],
+             'material': [{'reflection': {'peakWavelength': 550.0, 'sigma': 6.0, 'isInvert': False}}],
+             'light': [{'emission': {'temperature': T, 'luminosity': lum}}]}
+    ubo = pack.pack_ubo(scene)
+    p = np.ascontiguousarray(pack.pack_params(scene, 1, 64, 64, 1, 2))
+    o = np.array([a, 1.0, 0.0], dtype=np.float32)
+    d = np.array([0.0, -1.0, 0.0], dtype=np.float32)
+    l4 = np.array([550.0, 500.0, 600.0, 450.0], dtype=np.float32)
+    mean = np.zeros(4, dtype=np.float64)
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
+    L.oracle_trace_path(vp(ubo), vp(p), vp(o), vp(d), vp(l4), 777, 500000, vp(mean))
+    emit, rho = np.zeros(4, dtype=np.float32), np.zeros(4, dtype=np.float32)
+    L.oracle_emit(vp(l4), T, lum, vp(emit))
+    L.oracle_spd(vp(l4), 550.0, 6.0, 0, vp(rho))
+    dist = float(np.hypot(a, h))
+    want = rho.astype(np.float64) * emit.astype(np.float64) * (R / dist) ** 2 * (h / dist)
+    assert np.all(want > 0) and np.all(np.abs(mean / want - 1.0) < 0.02), (mean, want)
