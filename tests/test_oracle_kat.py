@@ -398,3 +398,112 @@ def test_direct_lighting_matches_the_closed_form(a, h, R):
     dist = float(np.hypot(a, h))
     want = rho.astype(np.float64) * emit.astype(np.float64) * (R / dist) ** 2 * (h / dist)
     assert np.all(want > 0) and np.all(np.abs(mean / want - 1.0) < 0.02), (mean, want)
+
+
+def test_sphere_tracing_of_a_unit_sphere_sdf_matches_the_analytic_hit():
+    """SphereTracing (shader.comp:779-860) over `length(p) - 1` in a bounding box: every ray that meets the analytic
+    sphere is reported as a hit and no other; the hit distance is the marched t minus the 1e-3 back-off (853), the march
+    stopping where |sdf| < 1e-4 (a little earlier along grazing rays): analytic t - 6e-3 <= hit <= analytic t - 0.9e-3;
+    the central-difference normal (721-730, eps 1e-4 in fp32) is the radial direction within 5e-3."""
+    src = 'float sdf(in vec3 p) { return length(p) - 1.0; }\nfloat sdfmaterial(in vec3 p) { return 0.0; }\n'
+    ubo = np.zeros(pack.UBO_FLOATS, dtype=np.float32)
+    ubo[5] = 1
+    c = np.array([0.5, 0.25, 4.0])
+    ubo[pack.OFF_SDF:pack.OFF_SDF + 6] = [c[0], c[1], c[2], 2.4, 2.4, 2.4]
+    o = oracle.Oracle(ubo, [src])
+    rng = np.random.default_rng(3)
+    hits = 0
+    for _ in range(600):
+        org = rng.normal(size=3) * 0.3
+        d = c + rng.normal(size=3) * 0.6 - org
+        d /= np.linalg.norm(d)
+        t, out = o.intersect(org.astype(np.float32), d.astype(np.float32))
+        oc = org - c
+        b, cc = float(np.dot(oc, d)), float(np.dot(oc, oc)) - 1.0
+        disc = b * b - cc
+        if disc <= 1e-4:            # a miss or a graze within the march's tolerance: either verdict is acceptable
+            continue
+        ta = -b - np.sqrt(disc)
+        assert t < 1e5, 'missed a sphere the ray crosses'
+        assert -6e-3 <= t - ta <= -0.9e-3, (t, ta)
+        n = org + ta * d - c
+        assert np.abs(out[:3] - n).max() < 5e-3 and out[4] == -1.0
+        hits += 1
+    assert hits > 300
+    t, _ = o.intersect(np.array([0, 0, 0], np.float32), np.array([0, 1, 0], np.float32))
+    assert t == np.float32(1e5)   # past the box: no hit
+
+
+@pytest.mark.parametrize('a,b,c,d,scale', [(2.0, 2.0, 0.0, 0.6, 0.5),            # a torus: a = b = R, c = 0, d = r
+                                           (3.36, -3.17, -1.06, -1.5, 0.25)])    # scene0's cyclide
+def test_dupin_cyclide_hits_match_a_float64_root_finder(a, b, c, d, scale):
+    """DupinCyclide (shader.comp:633-679) + SolveQuartic / SolveCubic (474-541): for rays shot at the surface from
+    outside its bounding sphere, the first crossing of the implicit (x^2+y^2+z^2+b^2-d^2)^2 = 4((ax-cd)^2+(by)^2) -- in
+    the frame after translation, scale and the shader's .xzy swap -- found by sign changes and bisection in float64,
+    agrees with the fp32 closed-form solver within 2e-3 (median error 1e-5), with no false hit and no miss."""
+    pos = np.array([0.0, 1.0, -3.0])
+    scene = {'camera': {}, 'cyclide': [{'position': list(pos), 'rotation': [0, 0, 0], 'scale': [scale] * 3, 'a': a, 'b': b, 'c': c, 'd': d,
+                                        'boundingRadius': abs(a) + abs(d) + abs(c) + 1.0, 'materialID': 1, 'lightID': 0}],
+             'material': [{'reflection': {'peakWavelength': 550, 'sigma': 10, 'isInvert': False}}], 'light': []}
+    o = oracle.Oracle(pack.pack_ubo(scene))
+    rng = np.random.default_rng(1)
+    extent = scale * (abs(a) + abs(d) + abs(c))
+
+    def implicit(p):  # p: (..., 3) world points
+        q = (p - pos) / scale
+        x, y, z = q[..., 0], q[..., 2], q[..., 1]
+        return (x * x + y * y + z * z + b * b - d * d) ** 2 - 4.0 * ((a * x - c * d) ** 2 + (b * y) ** 2)
+
+    hits = errs = 0
+    worst = []
+    for _ in range(160):
+        org = rng.normal(size=3)
+        org = pos + org / np.linalg.norm(org) * extent * 2.0
+        dr = pos + rng.normal(size=3) * scale * abs(a) * 0.7 - org
+        dr /= np.linalg.norm(dr)
+        t, _ = o.intersect(org.astype(np.float32), dr.astype(np.float32))
+        ts = np.linspace(0.0, extent * 4.5, 6001)
+        v = implicit(org + ts[:, None] * dr)
+        idx = np.where(np.sign(v[:-1]) * np.sign(v[1:]) < 0)[0]
+        if len(idx) == 0:
+            if np.abs(v).min() > 1e-3 * np.abs(v).max():   # a clear miss (not a graze between two samples)
+                assert t >= 1e5, 'false hit'
+            continue
+        lo, hi = ts[idx[0]], ts[idx[0] + 1]
+        flo = implicit(org + lo * dr)
+        for _ in range(50):
+            mid = 0.5 * (lo + hi)
+            fm = implicit(org + mid * dr)
+            if np.sign(fm) == np.sign(flo):
+                lo, flo = mid, fm
+            else:
+                hi = mid
+        assert t < 1e5, 'missed the surface'
+        worst.append(abs(t - 0.5 * (lo + hi)))
+        hits += 1
+    assert hits > 50 and max(worst) < 2e-3 and float(np.median(worst)) < 1e-4, (hits, max(worst))
+
+
+def test_lens_caps_match_the_closed_form():
+    """LensIntersection / SphereSliceIntersection (shader.comp:366-448): a converging lens is two caps of spheres of radius
+    2f whose rims (radius R) sit thickness/2 either side of the centre, optical axis = local x.  For a ray parallel to
+    the axis at height y the hit is on the sphere centred 2f behind the cap's vertex: x = x_c - sqrt(4f^2 - y^2); normal
+    radial, flipped towards the ray for hits from inside; beyond the rim and edge-on there is no hit."""
+    f, R, th = 1.0, 1.2, 0.2
+    scene = {'camera': {}, 'lens': [{'position': [5.0, 0.0, 0.0], 'rotation': [0, 0, 0], 'radius': R, 'focalLength': f, 'thickness': th,
+                                     'isConverging': True, 'materialID': 1, 'lightID': 0}],
+             'material': [{'reflection': {'peakWavelength': 550, 'sigma': 10, 'isInvert': False}}], 'light': []}
+    o = oracle.Oracle(pack.pack_ubo(scene))
+    h = 2 * f - np.sqrt(4 * f * f - R * R)            # cap height
+    xc = 5.0 - (h + th / 2) + 2 * f                   # centre of the front cap's sphere
+    for y in (0.0, 0.5, 1.0, 1.19):
+        t, out = o.intersect(np.array([0, y, 0], np.float32), np.array([1, 0, 0], np.float32))
+        x = xc - np.sqrt(4 * f * f - y * y)
+        assert abs(t - x) < 2e-6 and np.allclose(out[:3], [(x - xc) / (2 * f), y / (2 * f), 0.0], atol=1e-6)
+    assert o.intersect(np.array([0, 1.21, 0], np.float32), np.array([1, 0, 0], np.float32))[0] == np.float32(1e5)
+    assert o.intersect(np.array([5, -5, 0], np.float32), np.array([0, 1, 0], np.float32))[0] == np.float32(1e5)
+    xb = 5.0 + (h + th / 2) - 2 * f                    # centre of the back cap's sphere
+    t, out = o.intersect(np.array([10, 0.5, 0], np.float32), np.array([-1, 0, 0], np.float32))
+    assert abs(t - (10 - (xb + np.sqrt(4 - 0.25)))) < 2e-6 and out[0] > 0
+    t, out = o.intersect(np.array([5, 0.5, 0], np.float32), np.array([1, 0, 0], np.float32))   # from between the caps
+    assert abs(t - (xb + np.sqrt(4 - 0.25) - 5)) < 2e-6 and out[0] < 0 and out[1] < 0
