@@ -1600,6 +1600,20 @@ void oracle_trace_path(const pt_ubo* ubo, const pt_params* pc, const float* o3, 
     }
     for (int k = 0; k < 4; k++) mean4[k] = acc[k] / (double)(n ? n : 1);
 }
+/* TracePathLens (shader.comp:1409-1444) for a given ray and hero wavelength; forwardDir as Scene() derives it
+ * (1456-1466).  out9 = origin(3), direction(3) after the two refractions, then forwardDir(3). */
+void oracle_lens_ray(const pt_ubo* ubo, const pt_params* pc, const float* o3, const float* d3, float l_h, float* out6) {
+    const Shader sh = make_shader(ubo, pc);
+    const M3 matrix = Shader::RotationMatrix(v3(pc->cameraAngle[0], pc->cameraAngle[1], 0.0f));
+    const V3 forwardDir = v3(matrix.c[0].z, matrix.c[1].z, matrix.c[2].z);
+    Ray ray;
+    ray.origin = v3(o3[0], o3[1], o3[2]);
+    ray.dir = v3(d3[0], d3[1], d3[2]);
+    sh.TracePathLens(l_h, ray, forwardDir);
+    out6[0] = ray.origin.x; out6[1] = ray.origin.y; out6[2] = ray.origin.z;
+    out6[3] = ray.dir.x; out6[4] = ray.dir.y; out6[5] = ray.dir.z;
+    out6[6] = forwardDir.x; out6[7] = forwardDir.y; out6[8] = forwardDir.z;
+}
 float oracle_cone_pdf(float cosTheta, float cosThetaMax) { return Shader::CosineUnitConePDF(cosTheta, cosThetaMax); }
 float oracle_mis_weight(float pdf1, float pdf2) { return Shader::MISPowerHeuristicsBeta2(pdf1, pdf2); }
 void oracle_orthonormal_basis(const float* n3, float* b6) {
