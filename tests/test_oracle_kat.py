@@ -563,3 +563,48 @@ def test_camera_lens_tracing_matches_float64_physics():
         p2 = p1 + (-b + np.sqrt(b * b - cc)) * d1                       # back cap, from inside
         d2 = refract(d1, -(p2 - c2) / (2 * f), bk7(lam / n))
         assert np.abs(out[:3] - p2).max() < 1e-5 and np.abs(out[3:6] - d2).max() < 1e-5
+
+
+def test_rotated_box_and_its_bounding_sphere_cull_match_a_float64_slab_test():
+    """BoxIntersection (shader.comp:337-364) behind the BoundingSphere cull (263-276, 887-897): for random rays and
+    random rotations the hit distance equals a float64 slab test in the box's frame (local = v * (mX mY mZ), the
+    matrix pinned above) and the normal is the face normal turned back to world space; the cull never rejects a ray
+    the slab test accepts, and rays that miss the box miss."""
+    rng = np.random.default_rng(9)
+    checked = 0
+    for _ in range(12):
+        deg = rng.uniform(-180, 180, 3)
+        size = rng.uniform(0.5, 2.5, 3)
+        pos = rng.uniform(-1, 1, 3) + np.array([0, 0, 6.0])
+        scene = {'camera': {}, 'box': [{'position': list(pos), 'rotation': list(deg), 'size': list(size), 'materialID': 1, 'lightID': 0}],
+                 'material': [{'reflection': {'peakWavelength': 550, 'sigma': 10, 'isInvert': False}}], 'light': []}
+        o = oracle.Oracle(pack.pack_ubo(scene))
+        a = np.deg2rad(np.float32(deg).astype(np.float64))
+        sx, sy, sz, cx, cy, cz = *np.sin(a), *np.cos(a)
+        M = (np.array([[1, 0, 0], [0, cx, sx], [0, -sx, cx]]) @ np.array([[cy, 0, -sy], [0, 1, 0], [sy, 0, cy]]) @
+             np.array([[cz, sz, 0], [-sz, cz, 0], [0, 0, 1]]))
+        pos32, size32 = np.float32(pos).astype(np.float64), np.float32(size).astype(np.float64)
+        for _ in range(60):
+            org = rng.normal(size=3) * 0.5
+            d = pos + rng.normal(size=3) * 1.2 - org
+            d = np.float32(d / np.linalg.norm(d))
+            org = np.float32(org)
+            t, out = o.intersect(org, d)
+            lo, ld = M.T @ (org.astype(np.float64) - pos32), M.T @ d.astype(np.float64)   # v * M == M^T v
+            with np.errstate(divide='ignore'):
+                ta, tb = (-0.5 * size32 - lo) / ld, (0.5 * size32 - lo) / ld
+            t1, t2 = np.minimum(ta, tb).max(), np.maximum(ta, tb).min()
+            if t1 > t2 + 1e-4 or t2 < 1e-3:
+                assert t == np.float32(1e5)
+                continue
+            if t1 > t2 - 1e-4:
+                continue   # a graze: either verdict
+            want = t2 if t1 < 0 else t1
+            assert abs(t - want) < 2e-5 * max(1.0, want), (t, want)
+            q = np.abs((lo + ld * want) / size32)
+            face = int(np.argmax(q))
+            nl = np.zeros(3)
+            nl[face] = -np.sign(ld[face])
+            assert np.allclose(out[:3], M @ nl, atol=2e-5)
+            checked += 1
+    assert checked > 150
