@@ -608,3 +608,66 @@ def test_rotated_box_and_its_bounding_sphere_cull_match_a_float64_slab_test():
             assert np.allclose(out[:3], M @ nl, atol=2e-5)
             checked += 1
     assert checked > 150
+
+
+def test_accumulate_branches_against_their_formulas():
+    """Accumulate (shader.comp:1492-1507).  Static branch: out = ((n - 1) in + out) / n with n = currentSamples / spf
+    (integer division).  Interactive branch (currentSamples == spf and frame > spf, i.e. after a reset while frames keep
+    counting): out = (1 - w) out + w in with w = 2^(-8 / (FPS persistence)).  Both checked against float64 on the
+    oracle's own per-sample values."""
+    o, sc = oracle.from_scene_file(scene_path('scene1'))
+    W, H, spf = 24, 16, 2
+    p = pack.pack_params(sc, 1, W, H, spf, 5)
+    expo = float(np.ravel(p['apertureSize'])[0]) ** 2 * int(np.ravel(p['ISO'])[0])
+
+    def frame_value(first):  # Rendering(): mean of spf Scene() calls times the exposure, for every pixel
+        out = np.zeros((H, W, 3))
+        for y in range(H):
+            for x in range(W):
+                out[y, x] = o.samples(p, x, y, first, spf).astype(np.float64).mean(0) * expo
+        return out
+
+    img = np.zeros((H, W, 4), dtype=np.float32)
+    o.dispatch(p, img)                                   # frame = spf, currentSamples = spf: n = 1
+    f0 = frame_value(0)
+    assert np.allclose(img[..., :3], f0, rtol=2e-6, atol=1e-9)
+    q = p.copy()
+    q['frame'] = 2 * spf
+    q['currentSamples'] = 2 * spf                        # n = 2: running mean of the two frames
+    o.dispatch(q, img)
+    f1 = frame_value(spf)
+    assert np.allclose(img[..., :3], 0.5 * (f0 + f1), rtol=3e-6, atol=1e-9)
+    r = p.copy()
+    r['frame'] = 5 * spf
+    r['currentSamples'] = spf                            # reset while frames keep counting: the EMA branch
+    r['FPS'] = 30.0
+    before = img[..., :3].astype(np.float64)
+    o.dispatch(r, img)
+    f4 = frame_value(4 * spf)
+    w = 2.0 ** (-8.0 / (30.0 * float(np.ravel(r['persistence'])[0])))
+    assert 0.0 < w < 1.0
+    assert np.allclose(img[..., :3], (1.0 - w) * f4 + w * before, rtol=5e-6, atol=1e-9)
+    assert (img[..., 3] == 1.0).all()
+
+
+def test_search_sdf_merges_overlapping_boxes_and_searches_again_after_leaving_them():
+    """SearchSDF (shader.comp:732-777) + the re-search of SphereTracing (826-840).  Three unit-sphere SDFs: boxes A and B
+    overlap along the ray (their intervals merge, both bits set), box C lies beyond a gap.  A ray that crosses A's box
+    beside its sphere must still find B's sphere inside the merged interval; a ray that leaves A's box without a hit must
+    search again and find C; hits are the analytic ones minus the march's 1e-3 back-off."""
+    src = 'float sdf(in vec3 p) { return length(p) - 1.0; }\nfloat sdfmaterial(in vec3 p) { return 0.0; }\n'
+    ubo = np.zeros(pack.UBO_FLOATS, dtype=np.float32)
+    ubo[5] = 3
+    for i, c in enumerate([(0, 0, 4), (0.6, 0, 6.2), (-1.15, 0, 10)]):
+        ubo[pack.OFF_SDF + 6 * i:pack.OFF_SDF + 6 * i + 6] = [c[0], c[1], c[2], 2.4, 2.4, 2.4]
+    o = oracle.Oracle(ubo, [src] * 3)
+    cases = [(1.1, 6.2 - np.sqrt(1 - 0.5 ** 2)),       # through A's box beside sphere A, into sphere B (merged interval)
+             (1.19, 6.2 - np.sqrt(1 - 0.59 ** 2)),
+             (-1.15, 9.0),                              # through A's box, out, across the gap, into sphere C (re-search)
+             (-1.19, 10 - np.sqrt(1 - 0.04 ** 2)),
+             (0.0, 3.0)]                                # sphere A itself
+    for x, want in cases:
+        t, out = o.intersect(np.array([x, 0, 0], np.float32), np.array([0, 0, 1], np.float32))
+        assert -2.5e-3 <= t - want <= -0.9e-3, (x, t, want)
+        assert out[2] < 0 and out[4] == -1.0
+    assert o.intersect(np.array([3.0, 0, 0], np.float32), np.array([0, 0, 1], np.float32))[0] == np.float32(1e5)
