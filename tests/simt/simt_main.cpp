@@ -1,0 +1,81 @@
+/* simt_main.cpp -- TEST INFRASTRUCTURE: the product's megakernel source compiled for the host over cuda_shim.h.
+ * Built per (driver, knobs, SDF unit) by tests/test_simt_emulation.py:
+ *   g++ -std=c++20 -O1 -ffp-contract=off -fno-fast-math -mfma -DPT_SCHED=.. [-DPT_HAS_SDF=1 ..] simt_main.cpp
+ *       ../../pathtracer_b200/csrc/pt_prepare.cpp [sdf_unit.o] -shared -o simt_<tag>.so
+ * simt_dispatch() = pt_dispatch / pt_dispatch_sum of libpt_cuda on the emulated device: the same host-side preparation
+ * (pt_prepare.cpp), the same grid, the kernel entry the JIT would define (PT_DEFINE_RENDER_KERNEL). */
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "cuda_shim.h"
+
+thread_local SimtDim3 threadIdx, blockIdx;
+SimtDim3 gridDim, blockDim;
+thread_local SimtWarp* simt_warp = nullptr;
+thread_local SimtBlock* simt_block = nullptr;
+thread_local unsigned simt_phase = 0;
+
+#if defined(PT_HAS_SDF) && PT_HAS_SDF
+/* the generated SDF unit is a separate object with C linkage on the host (PT_SDF_ENTRY) */
+extern "C" float pt_sdf_dispatch(float px, float py, float pz, unsigned set1);
+extern "C" float pt_sdfmaterial_dispatch(float px, float py, float pz, unsigned set1);
+#endif
+
+#define PT_KERNEL_NS ptk_emu
+#include "pt_internal.h"
+#include "pt_kernel.cuh"
+
+PT_DEFINE_RENDER_KERNEL(pt_render_emu)
+
+extern "C" int simt_sched(void) { return PT_SCHED; }
+
+/* accum_mode 0: pt_dispatch (params carry frame / currentSamples); 2: pt_dispatch_sum(first, n).  image: W*H float4.
+ * persistent_ctas: grid of the tile-streaming driver (PT_SCHED=6); ignored otherwise. */
+extern "C" int simt_dispatch(const pt_ubo* ubo, const pt_params* params, int accum_mode, int first, int n, float* image,
+                             int persistent_ctas) {
+    PtDevScene sc;
+    PtDevParams dp;
+    std::string err;
+    if (pt_prepare_scene(ubo, &sc, &err) != 0) { fprintf(stderr, "simt: %s\n", err.c_str()); return -1; }
+    if (pt_prepare_params(params, accum_mode, first, n, &dp, &err) != 0) { fprintf(stderr, "simt: %s\n", err.c_str()); return -2; }
+#if PT_SCHED == 6
+    gridDim = {(unsigned)(persistent_ctas > 0 ? persistent_ctas : 2), 1u, 1u};
+#elif PT_SCHED == 4
+    gridDim = {(unsigned)((dp.width + 15) / 16), (unsigned)((dp.height + 15) / 16), 1u};
+#else
+    gridDim = {(unsigned)((dp.width + 15) / 16), (unsigned)((dp.height + 7) / 8), 1u};
+#endif
+    blockDim = {PT_BLOCK_THREADS, 1u, 1u};
+    const float* ubo_f = reinterpret_cast<const float*>(ubo);
+    float4* img = reinterpret_cast<float4*>(image);
+    const int nwarps = PT_BLOCK_THREADS / 32;
+    /* One block at a time: `__shared__` arrays are function-local statics here, i.e. one copy for whoever runs.  For the
+     * persistent grid of PT_SCHED=6 this means the first CTA drains the tile counter and the later ones find it
+     * exhausted -- legal for a dynamic scheduler, and the counter's hand-over / self-reset is still exercised. */
+    const unsigned concurrent = 1;
+    for (unsigned b0 = 0; b0 < gridDim.x * gridDim.y; b0 += concurrent) {
+        std::vector<std::thread> threads;
+        std::vector<std::unique_ptr<SimtBlock>> blocks;
+        std::vector<std::unique_ptr<SimtWarp>> warps;
+        for (unsigned b = b0; b < b0 + concurrent && b < gridDim.x * gridDim.y; b++) {
+            blocks.emplace_back(new SimtBlock(PT_BLOCK_THREADS));
+            for (int w = 0; w < nwarps; w++) warps.emplace_back(new SimtWarp());
+            SimtBlock* blk = blocks.back().get();
+            for (int t = 0; t < PT_BLOCK_THREADS; t++) {
+                SimtWarp* wp = warps[warps.size() - nwarps + t / 32].get();
+                threads.emplace_back([=, &sc, &dp]() {
+                    threadIdx = {(unsigned)t, 0u, 0u};
+                    blockIdx = {b % gridDim.x, b / gridDim.x, 0u};
+                    simt_warp = wp;
+                    simt_block = blk;
+                    simt_phase = 0;
+                    pt_render_emu(sc, dp, ubo_f, img);
+                });
+            }
+        }
+        for (auto& th : threads) th.join();
+    }
+    return 0;
+}

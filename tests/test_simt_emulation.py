@@ -1,0 +1,125 @@
+"""The product's kernel source on a host SIMT emulator (tests/simt/cuda_shim.h): driver logic checked WITHOUT a GPU.
+
+pathtracer_b200/csrc/pt_kernel.cuh is compiled, unmodified, for the host: one thread per CUDA thread, barriers for
+__syncthreads / __ballot_sync / __shfl_sync / __syncwarp, statics for shared memory.  In strict mode the arithmetic is
+the oracle's, so every driver -- the nested loops of v1, the in-warp scheduler v2, sample stealing (v2s: table rounds),
+march parking, two pixels per lane (v2d), the flat loop (v3) -- must reproduce the oracle bit for bit, and the
+tile-streaming v2sp up to fp32 summation order.  What this does not cover: the device compiler, fast-math builds, and
+timing -- the `-m gpu` parity tests remain the gate for those.  TEST INFRASTRUCTURE: a checker, not a rendering path."""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, scene_path
+from oracle import oracle, pack, sdf_build
+
+SIMT = os.path.join(ROOT, 'tests', 'simt')
+BUILD = os.path.join(SIMT, '_build')
+CSRC = os.path.join(ROOT, 'pathtracer_b200', 'csrc')
+FLAGS = ['-std=c++20', '-O1', '-fPIC', '-ffp-contract=off', '-fno-fast-math', '-mfma', '-mavx2', '-Wno-unknown-pragmas',
+         '-I' + SIMT, '-I' + os.path.join(ROOT, 'include'), '-I' + CSRC]
+
+
+def build_emulator(ptlib, defines, sdf_sources=(), sdf_raw=None):
+    """g++ the emulated kernel for one (driver, knobs, SDF unit); cached by content."""
+    from pathtracer_b200 import api
+    os.makedirs(BUILD, exist_ok=True)
+    defs = dict(defines)
+    objs = []
+    unit = ''
+    if sdf_sources:
+        unit = api.sdf_translate(list(sdf_sources), sdf_raw)
+        defs['PT_HAS_SDF'] = 1
+    srcs = [os.path.join(SIMT, 'simt_main.cpp'), os.path.join(SIMT, 'cuda_shim.h'), os.path.join(CSRC, 'pt_kernel.cuh'),
+            os.path.join(CSRC, 'pt_prepare.cpp'), os.path.join(CSRC, 'pt_dev_scene.h'), os.path.join(ROOT, 'include', 'pt_math.h')]
+    h = hashlib.sha1((repr(sorted(defs.items())) + unit + ''.join(open(f).read() for f in srcs)).encode()).hexdigest()[:16]
+    so = os.path.join(BUILD, 'simt_%s.so' % h)
+    if not os.path.exists(so):
+        if unit:
+            cpp = os.path.join(BUILD, 'sdf_%s.cpp' % h)
+            open(cpp, 'w').write(unit)
+            obj = cpp[:-4] + '.o'
+            subprocess.run([sdf_build.CXX, *[f for f in sdf_build.CXXFLAGS if f != '-shared'], '-c', '-o', obj, cpp], check=True)
+            objs.append(obj)
+        ph = hashlib.sha1(''.join(open(f).read() for f in srcs[3:]).encode()).hexdigest()[:16]
+        prep = os.path.join(BUILD, 'pt_prepare_%s.o' % ph)   # the product's host-side preparation, compiled once
+        if not os.path.exists(prep):
+            subprocess.run(['g++', *FLAGS, '-c', os.path.join(CSRC, 'pt_prepare.cpp'), '-o', prep + '.tmp.o'], check=True)
+            os.replace(prep + '.tmp.o', prep)
+        cmd = ['g++', *FLAGS, *['-D%s=%s' % kv for kv in sorted(defs.items())], os.path.join(SIMT, 'simt_main.cpp'),
+               prep, *objs, '-shared', '-o', so, '-lpthread']
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+    L = C.CDLL(so)
+    L.simt_dispatch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    return L
+
+
+def emulate(L, ubo, p, spp, spf, ctas=2):
+    """Renderer.render's bookkeeping (host:4042-4048) over the emulated pt_dispatch."""
+    q = np.array(p, copy=True)
+    W, H = int(np.ravel(q['resolution'])[0]), int(np.ravel(q['resolution'])[1])
+    img = np.zeros((H, W, 4), dtype=np.float32)
+    for j in range(1, spp // spf + 1):
+        q['frame'] = j * spf
+        q['currentSamples'] = j * spf
+        q['samplesPerFrame'] = spf
+        qq = np.ascontiguousarray(q)
+        assert L.simt_dispatch(ubo.ctypes.data_as(C.c_void_p), qq.ctypes.data_as(C.c_void_p), 0, 0, 0,
+                               img.ctypes.data_as(C.c_void_p), ctas) == 0
+    return img
+
+
+def scene_inputs(name, w, h, spf, pl):
+    scene = pack.load_scene(scene_path(name))
+    ubo = pack.pack_ubo(scene)
+    src = pack.sdf_sources(scene)
+    return ubo, pack.pack_params(scene, 1, w, h, spf, pl), src, ubo[pack.OFF_SDF:pack.OFF_SDF + 6 * len(src)]
+
+
+DRIVERS = {
+    'v1': {'PT_SCHED': 0}, 'v2': {'PT_SCHED': 1}, 'v3': {'PT_SCHED': 3, 'PT_REGEN_T': 4}, 'v2d': {'PT_SCHED': 4},
+    'v2s_table16': {'PT_SCHED': 5, 'PT_STEAL_S': 16}, 'v2s_table2': {'PT_SCHED': 5, 'PT_STEAL_S': 2},
+    'v2s_park': {'PT_SCHED': 5, 'PT_STEAL_S': 8, 'PT_MPARK': 1, 'PT_MPARK_CAP': 20, 'PT_MPARK_MIN': 4},
+    'v2s_park_tiny_stack': {'PT_SCHED': 5, 'PT_STEAL_S': 3, 'PT_MPARK': 1, 'PT_MPARK_CAP': 2, 'PT_MPARK_MIN': 1},
+}
+
+
+# scenes without SDFs share one build per driver; of the SDF scenes, scene10 (menger, pathLength 32) runs under every
+# driver, scene9 / scene8 under the default driver and the parking variant (each SDF unit is its own build)
+CASES = [(d, 'scene0', 48, 32, 10, 5, 5) for d in sorted(DRIVERS) if 'PT_MPARK' not in DRIVERS[d]]
+CASES += [(d, 'scene1', 50, 37, 3, 3, 5) for d in sorted(DRIVERS) if 'PT_MPARK' not in DRIVERS[d]]
+CASES += [(d, 'scene10', 40, 24, 4, 2, 32) for d in sorted(DRIVERS)]
+CASES += [(d, n, w, h, spp, spf, 5) for d in ('v2s_table16', 'v2s_park') for (n, w, h, spp, spf) in (('scene9', 33, 17, 5, 5), ('scene8', 32, 16, 2, 2))]
+
+
+@pytest.mark.parametrize('driver,name,w,h,spp,spf,pl', CASES)
+def test_emulated_strict_kernel_equals_the_oracle(ptlib, driver, name, w, h, spp, spf, pl):
+    """Every driver, strict arithmetic, ragged frame sizes, several dispatches and (v2s) several rounds per dispatch:
+    the emulated kernel writes the oracle's bits."""
+    ubo, p, src, raw = scene_inputs(name, w, h, spf, pl)
+    L = build_emulator(ptlib, DRIVERS[driver], src, raw)
+    got = emulate(L, ubo, p, spp, spf)
+    ref = oracle.Oracle(ubo, src).render(p, spp, spf)
+    g, r = got.view(np.uint32), ref.view(np.uint32)
+    assert np.array_equal(g, r), '%s on %s: %d floats differ' % (driver, name, int((g != r).sum()))
+
+
+@pytest.mark.parametrize('name,w,h,spp,spf,pl,ctas,slots', [('scene0', 61, 43, 3, 1, 5, 2, 4), ('scene1', 50, 37, 8, 4, 5, 3, 2),
+                                                           ('scene10', 40, 24, 6, 3, 32, 2, 4), ('scene9', 33, 17, 2, 2, 5, 1, 8)])
+def test_emulated_tile_streaming_driver(ptlib, name, w, h, spp, spf, pl, ctas, slots):
+    """v2sp (PT_SCHED=6) adds finished samples to their pixel's sum in schedule order, so it equals the oracle up to fp32
+    summation order (1e-5 relative); here with strict arithmetic, so no path forks: every pixel must agree.  Covers the
+    slot recycling (1 to 4 samples per dispatch, 2 / 4 / 8 slots), items beyond the image edge, several CTAs sharing
+    the tile counter and the counter's self-reset between dispatches."""
+    ubo, p, src, raw = scene_inputs(name, w, h, spf, pl)
+    L = build_emulator(ptlib, {'PT_SCHED': 6, 'PT_TILE_SLOTS': slots}, src, raw)
+    got = emulate(L, ubo, p, spp, spf, ctas)
+    ref = oracle.Oracle(ubo, src).render(p, spp, spf)
+    scale = float(ref[..., :3].max())
+    assert np.allclose(got[..., :3], ref[..., :3], rtol=1e-5, atol=1e-6 * scale)
+    assert (got[..., 3] == 1.0).all()
