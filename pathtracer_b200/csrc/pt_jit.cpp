@@ -117,7 +117,7 @@ int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::ve
     if (opt.mode != PT_MODE_FAST && steal_s == 0) steal_s = steal_dflt;
     if (opt.mode != PT_MODE_FAST && park && !sdf_unit.empty() && steal_s > 8) steal_s = 8;
     /* shared memory per CTA: v2d 45 KB, v2s 16 KB + 1.5 KB x PT_STEAL_S -> 5 CTAs/SM fit */
-    const int min_blocks_fast = (sched_eff == 4 || (sched_eff == 5 && steal_s > 8)) ? 5 : 6;
+    const int min_blocks_fast = (sched_eff == 4 || ((sched_eff == 5 || sched_eff == 7) && steal_s > 8)) ? 5 : 6;
     const Knob knobs[] = {{"PT_SCHED", sched}, {"PT_SDF_REPS", 16}, {"PT_FEED_T", 8}, {"PT_STEAL_S", -1},
                           {"PT_MIN_BLOCKS", opt.mode == PT_MODE_FAST ? min_blocks_fast : 4},
                           {"PT_NO_UNROLL", no_unroll}, {"PT_STATS", 0},

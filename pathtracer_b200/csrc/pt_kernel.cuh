@@ -33,6 +33,7 @@
  *                     phase when both its paths do
  *   v2sp (PT_SCHED 6) v2s with persistent warps that stream over tiles claimed from a global counter, several tiles in
  *                     flight per warp (fast mode; strict builds fall back to v2s)
+ *   v3s (PT_SCHED 7)  v3's flat loop with v2s' sample pool (verified on the host emulator, not yet measured)
  *   v2s (PT_SCHED 5)  v2 with in-warp sample stealing: the warp's 32 x S samples are a pool of work items, a lane that
  *                     finishes a path takes the next one whichever pixel it belongs to; per-sample XYZ in shared memory,
  *                     summed per pixel in sample order at the end of a round
@@ -2000,6 +2001,77 @@ __device__ __forceinline__ void pt_render_body_v2sp(const PtDevScene& sc, const 
     }
 }
 
+/* One iteration of TracePath's loop (shader.comp:1393-1407): TraceRay (1345-1391) with SampleLightSource (1298-1343)
+ * inline, verbatim from TracePath above, on the path held in `ps`.  Returns whether the path goes on.  Shared by the
+ * flat-loop drivers v3 and v3s. */
+PT_DEV bool TraceRayFlat(const Ctx& c, PathState& ps, const int pathLength) {
+    const PtDevScene& sc = *c.sc;
+    bool goOn = false;
+    Hit h;
+    Intersection(c, ps.ray, h, false);
+    if (h.t < 1e5f) {
+        float temperature, luminosity;
+        GetLightMix(c, h.lightID, temperature, luminosity);
+        if (luminosity > 0.0f) { /* emitter hit terminates the path */
+            const V4 e = Emit(ps.l, PTK_MAX(temperature, 0.0f), PTK_MAX(luminosity, 0.0f));
+            ps.radiance = ps.radiance + (e * ps.rayradiance) * ps.MISBRDFWeight;
+        } else {
+            float peak, sigma, invertf;
+            GetMaterialMix(c, h.materialID, peak, sigma, invertf);
+            const V4 brdf = EvaluateBRDF(ps.l, peak, sigma, invertf);
+            Ray outRay;
+            outRay.origin = fma3(ps.ray.dir, h.t, ps.ray.origin);
+            outRay.dir = SampleCosineDirectionHemisphere(h.normal, ps.seed);
+            const float BRDFpdf = PTK_DIV(dot(outRay.dir, h.normal), PT_PI_F);
+            if (sc.numLights > 0.0f) { /* SampleLightSource, shader.comp:1298-1343 */
+                const int randomLight = __float2int_rz(floorf(RandomFloatPCG32(ps.seed) * sc.numLights));
+                const PtDevLightSlot& ls = sc.lightSlots[randomLight < sc.nLightSlots ? randomLight : sc.nLightSlots - 1];
+                const V3 toLight = mk3(ls.px - outRay.origin.x, ls.py - outRay.origin.y, ls.pz - outRay.origin.z);
+                const float invLightDistance = PTK_DIV(1.0f, length(toLight));
+                const V3 lightDir = toLight * invLightDistance;
+                const float sinthetaMax = PTK_MIN(ls.boundingRadius * invLightDistance, 1.0f);
+                const float costhetaMax = PTK_SQRT(1.0f - sinthetaMax * sinthetaMax);
+                Ray shadowRay;
+                shadowRay.origin = outRay.origin;
+                shadowRay.dir = ToWorld(SampleCosineUnitCone(ps.seed, costhetaMax), lightDir);
+                float lightpdf = sc.invNumLights;
+                lightpdf *= PTK_DIV(dot(shadowRay.dir, lightDir), PT_PI_F * (1.0f - costhetaMax * costhetaMax));
+                ps.MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + lightpdf * lightpdf);
+                const float costheta = dot(shadowRay.dir, h.normal);
+                const float deathProbability = 1.25f * PTK_MAX(ps.MISBRDFWeight - 0.2f, 0.0f);
+                if (costheta >= 0.0f) {
+                    if (RandomFloatPCG32(ps.seed) > deathProbability) {
+                        Hit sh;
+                        Intersection(c, shadowRay, sh, true);
+                        if (sh.objectID == ls.objectID) {
+                            float lt, ll;
+                            GetLightMix(c, ls.lightID, lt, ll);
+                            const V4 rr = ps.rayradiance * mulDiv4(brdf, costheta, lightpdf);
+                            const V4 e = Emit(ps.l, PTK_MAX(lt, 0.0f), PTK_MAX(ll, 0.0f));
+                            ps.radiance = ps.radiance + (e * rr) * (1.0f - ps.MISBRDFWeight);
+                        }
+                    } else {
+                        ps.MISBRDFWeight = 1.0f;
+                    }
+                }
+            } else {
+                ps.MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + 0.0f * 0.0f);
+            }
+            const float costheta = dot(outRay.dir, h.normal);
+            ps.rayradiance = ps.rayradiance * mulDiv4(brdf, costheta, BRDFpdf);
+            const float mx = PTK_MAX(ps.rayradiance.x, PTK_MAX(ps.rayradiance.y, PTK_MAX(ps.rayradiance.z, ps.rayradiance.w)));
+            const float rayProbability = PTK_MIN(PTK_MAX(mx, 0.0f), 0.99f);
+            if (!(RandomFloatPCG32(ps.seed) > rayProbability)) {
+                ps.rayradiance = ps.rayradiance * PTK_DIV(1.0f, rayProbability);
+                ps.ray = outRay;
+                ps.bounce++;
+                goOn = ps.bounce < pathLength;
+            }
+        }
+    }
+    return goOn;
+}
+
 /* ---- driver v3: v1's loop bodies, flattened, with gated path regeneration ----------------------------------------
  * What v1 loses on the analytic scenes is not the shape of a path but its tail: on scene1 nine lanes in ten are done
  * after two rays, yet the warp runs bounce 2's shading, shadow ray and the third and fourth intersection for the
@@ -2056,70 +2128,111 @@ __device__ __forceinline__ void pt_render_body_v3(const PtDevScene& sc, const Pt
             }
         }
         if (alive) { /* one iteration of TracePath's loop, shader.comp:1393-1407 */
-            bool goOn = false;
-            Hit h;
-            Intersection(c, ps.ray, h, false);
-            if (h.t < 1e5f) {
-                float temperature, luminosity;
-                GetLightMix(c, h.lightID, temperature, luminosity);
-                if (luminosity > 0.0f) { /* emitter hit terminates the path */
-                    const V4 e = Emit(ps.l, PTK_MAX(temperature, 0.0f), PTK_MAX(luminosity, 0.0f));
-                    ps.radiance = ps.radiance + (e * ps.rayradiance) * ps.MISBRDFWeight;
-                } else {
-                    float peak, sigma, invertf;
-                    GetMaterialMix(c, h.materialID, peak, sigma, invertf);
-                    const V4 brdf = EvaluateBRDF(ps.l, peak, sigma, invertf);
-                    Ray outRay;
-                    outRay.origin = fma3(ps.ray.dir, h.t, ps.ray.origin);
-                    outRay.dir = SampleCosineDirectionHemisphere(h.normal, ps.seed);
-                    const float BRDFpdf = PTK_DIV(dot(outRay.dir, h.normal), PT_PI_F);
-                    if (sc.numLights > 0.0f) { /* SampleLightSource, shader.comp:1298-1343 */
-                        const int randomLight = __float2int_rz(floorf(RandomFloatPCG32(ps.seed) * sc.numLights));
-                        const PtDevLightSlot& ls = sc.lightSlots[randomLight < sc.nLightSlots ? randomLight : sc.nLightSlots - 1];
-                        const V3 toLight = mk3(ls.px - outRay.origin.x, ls.py - outRay.origin.y, ls.pz - outRay.origin.z);
-                        const float invLightDistance = PTK_DIV(1.0f, length(toLight));
-                        const V3 lightDir = toLight * invLightDistance;
-                        const float sinthetaMax = PTK_MIN(ls.boundingRadius * invLightDistance, 1.0f);
-                        const float costhetaMax = PTK_SQRT(1.0f - sinthetaMax * sinthetaMax);
-                        Ray shadowRay;
-                        shadowRay.origin = outRay.origin;
-                        shadowRay.dir = ToWorld(SampleCosineUnitCone(ps.seed, costhetaMax), lightDir);
-                        float lightpdf = sc.invNumLights;
-                        lightpdf *= PTK_DIV(dot(shadowRay.dir, lightDir), PT_PI_F * (1.0f - costhetaMax * costhetaMax));
-                        ps.MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + lightpdf * lightpdf);
-                        const float costheta = dot(shadowRay.dir, h.normal);
-                        const float deathProbability = 1.25f * PTK_MAX(ps.MISBRDFWeight - 0.2f, 0.0f);
-                        if (costheta >= 0.0f) {
-                            if (RandomFloatPCG32(ps.seed) > deathProbability) {
-                                Hit sh;
-                                Intersection(c, shadowRay, sh, true);
-                                if (sh.objectID == ls.objectID) {
-                                    float lt, ll;
-                                    GetLightMix(c, ls.lightID, lt, ll);
-                                    const V4 rr = ps.rayradiance * mulDiv4(brdf, costheta, lightpdf);
-                                    const V4 e = Emit(ps.l, PTK_MAX(lt, 0.0f), PTK_MAX(ll, 0.0f));
-                                    ps.radiance = ps.radiance + (e * rr) * (1.0f - ps.MISBRDFWeight);
-                                }
-                            } else {
-                                ps.MISBRDFWeight = 1.0f;
-                            }
-                        }
-                    } else {
-                        ps.MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + 0.0f * 0.0f);
-                    }
-                    const float costheta = dot(outRay.dir, h.normal);
-                    ps.rayradiance = ps.rayradiance * mulDiv4(brdf, costheta, BRDFpdf);
-                    const float mx = PTK_MAX(ps.rayradiance.x, PTK_MAX(ps.rayradiance.y, PTK_MAX(ps.rayradiance.z, ps.rayradiance.w)));
-                    const float rayProbability = PTK_MIN(PTK_MAX(mx, 0.0f), 0.99f);
-                    if (!(RandomFloatPCG32(ps.seed) > rayProbability)) {
-                        ps.rayradiance = ps.rayradiance * PTK_DIV(1.0f, rayProbability);
-                        ps.ray = outRay;
-                        ps.bounce++;
-                        goOn = ps.bounce < pathLength;
+            const bool goOn = TraceRayFlat(c, ps, pathLength);
+            if (!goOn) {
+                alive = false;
+                ps.pendingFinish = true;
+            }
+        }
+    }
+    if (inRange) StoreTexel(pr, image, gx, gy, outColor);
+}
+
+/* ---- driver v3s (PT_SCHED=7): v3 with in-warp sample stealing ------------------------------------------------------
+ * v3 keeps v1's compact loop bodies (no phase vote, no hit / shadow state) but ties a lane to its pixel's sample
+ * sequence; v2s pools the tile's samples but pays for its phase machine on the scenes without SDFs (cfg2: 9.85 against
+ * v1's 10.96 Gsamples/s).  This is v3's flat loop with v2s' pool: at a regeneration (PT_REGEN_T lanes waiting, or nobody
+ * alive) the waiting lanes deposit their finished sample and claim the next items of the tile's 32 x S pool by ballot
+ * rank, whichever pixel they belong to.  Strict mode: per-sample XYZ table, summed per pixel in sample order at the end
+ * of a round (bit-exact); fast mode (PT_STEAL_S = 0): the whole dispatch is one pool, sums in shared memory.
+ * Verified against the oracle on the host SIMT emulator (tests/test_simt_emulation.py); NOT yet measured on a GPU --
+ * a round-2 candidate for the scenes without SDFs. */
+__device__ __forceinline__ void pt_render_body_v3s(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
+                                                   float4* __restrict__ image, float* s_tab, float* s_colAll) {
+    for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tileX = blockIdx.x * 16 + (warp & 1) * 8, tileY = blockIdx.y * 8 + (warp >> 1) * 4;
+    const int gx = tileX + (lane & 7), gy = tileY + (lane >> 3);
+    const bool inRange = (gx < pr.width) && (gy < pr.height);
+    float* s_col = s_colAll + warp * PT_STEAL_WORDS;
+
+    Ctx c;
+    c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
+
+    const int spf = pr.samplesPerFrame;
+    const int pathLength = pr.pathLength;
+    const bool warpLive = (tileX < pr.width) && (tileY < pr.height) && (spf > 0); /* warp-uniform */
+    int roundBase = 0;
+#if PT_STEAL_S == 0
+    int roundN = warpLive ? spf : 0;
+    s_col[lane] = 0.0f; s_col[32 + lane] = 0.0f; s_col[64 + lane] = 0.0f;
+    __syncwarp();
+#else
+    int roundN = warpLive ? (spf < PT_STEAL_S ? spf : PT_STEAL_S) : 0;
+#endif
+    int next = 0, item = 0;
+
+    V3 outColor = mk3(0.0f, 0.0f, 0.0f);
+    PathState ps; /* only ray, l, radiance, rayradiance, MISBRDFWeight, seed, bounce and pendingFinish are used */
+    PathStateInit(ps);
+    bool alive = false;
+
+    for (;;) {
+        const bool wantNew = !alive && ((next < 32 * roundN) || ps.pendingFinish);
+        const unsigned bNew = __ballot_sync(0xffffffffu, wantNew);
+        const unsigned bAlive = __ballot_sync(0xffffffffu, alive);
+        if ((bNew | bAlive) == 0u) {
+            if (!warpLive) break;
+            /* end of a round: lane p sums pixel p's samples in index order */
+            __syncwarp();
+#if PT_STEAL_S == 0
+            outColor = mk3(s_col[lane], s_col[32 + lane], s_col[64 + lane]);
+            break;
+#else
+            if (inRange) {
+#pragma unroll 1
+                for (int kk = 0; kk < roundN; kk++) {
+                    const float* e = s_col + (3 * kk) * 32 + lane;
+                    outColor = outColor + mk3(e[0], e[32], e[64]);
+                }
+            }
+            __syncwarp();
+            roundBase += roundN;
+            if (roundBase >= spf) break;
+            roundN = (spf - roundBase) < PT_STEAL_S ? (spf - roundBase) : PT_STEAL_S;
+            next = 0;
+            continue;
+#endif
+        }
+        if ((__popc(bNew) >= PT_REGEN_T) || (bAlive == 0u)) { /* warp-uniform */
+            if (wantNew) {
+                if (ps.pendingFinish) { /* Scene()'s tail for the path that ended, shader.comp:1477-1489 */
+                    const V3 col = PathColor(c, ps);
+#if PT_STEAL_S == 0
+                    float* e = s_col + (item & 31);
+                    atomicAdd(e, col.x); atomicAdd(e + 32, col.y); atomicAdd(e + 64, col.z);
+#else
+                    float* e = s_col + (3 * (item >> 5)) * 32 + (item & 31);
+                    e[0] = col.x; e[32] = col.y; e[64] = col.z;
+#endif
+                    ps.pendingFinish = false;
+                }
+                item = next + __popc(bNew & ((1u << lane) - 1u));
+                if (item < 32 * roundN) {
+                    const int q = item & 31;
+                    const int qx = tileX + (q & 7), qy = tileY + (q >> 3);
+                    if ((qx < pr.width) && (qy < pr.height)) { /* else: a pixel beyond the image edge; claim again */
+                        const int nextState = PhaseNew(c, ps, (unsigned)qx, (unsigned)pr.height - (unsigned)qy, roundBase + (item >> 5));
+                        alive = (nextState == PT_ST_ISECT); /* pathLength <= 0: PhaseNew left pendingFinish set */
                     }
                 }
             }
-            if (!goOn) {
+            next += __popc(bNew);
+        }
+        if (alive) { /* one iteration of TracePath's loop, shader.comp:1393-1407 */
+            if (!TraceRayFlat(c, ps, pathLength)) {
                 alive = false;
                 ps.pendingFinish = true;
             }
@@ -2501,6 +2614,15 @@ __device__ __forceinline__ void pt_render_body(const PtDevScene& sc, const PtDev
         __shared__ float s_tab[PT_SH_FLOATS];                                                                \
         __shared__ float s_v2sp[PT_V2SP_WORDS * (PT_BLOCK_THREADS / 32)];                                    \
         PT_KERNEL_NS::pt_render_body_v2sp(sc, pr, ubo, image, s_tab, s_v2sp, pt_tile_ctr);                   \
+    }
+#elif PT_SCHED == 7
+#define PT_DEFINE_RENDER_KERNEL(name)                                                                        \
+    extern "C" __global__ void __launch_bounds__(PT_BLOCK_THREADS, PT_MIN_BLOCKS)                            \
+    name(const __grid_constant__ PtDevScene sc, const __grid_constant__ PtDevParams pr,                      \
+         const float* __restrict__ ubo, float4* __restrict__ image) {                                        \
+        __shared__ float s_tab[PT_SH_FLOATS];                                                                \
+        __shared__ float s_col[PT_STEAL_WORDS * (PT_BLOCK_THREADS / 32)];                                    \
+        PT_KERNEL_NS::pt_render_body_v3s(sc, pr, ubo, image, s_tab, s_col);                                  \
     }
 #elif PT_SCHED == 5
 #define PT_DEFINE_RENDER_KERNEL(name)                                                                        \

@@ -680,3 +680,26 @@ def test_native_multi_gpu_errors(ptlib):
     with pytest.raises(ptlib.PtError):       # no image yet
         m.render(sc.pack_params(1, 32, 32, 1, 5), 0, 4, 2)
     m.close()
+
+
+# ---- driver v3s (v3's flat loop with v2s' sample pool): verified on the host emulator first, here on the device ----------
+@pytest.mark.parametrize('name,w,h,spp,spf,pl,jit,steal_s,regen_t', [
+    ('scene0', 96, 64, 8, 4, 5, 2, 16, 16), ('scene1', 70, 45, 40, 20, 5, 2, 16, 8), ('scene2', 33, 17, 9, 9, 5, 2, 4, 4),
+    ('scene1', 96, 72, 6, 3, 32, 1, 2, 16), ('scene10', 64, 48, 4, 2, 5, 2, 16, 16)])
+def test_v3s_driver_strict_bit_exact(ptlib, monkeypatch, name, w, h, spp, spf, pl, jit, steal_s, regen_t):
+    """PT_SCHED=7: whichever lane runs a sample, Scene() depends only on (pixel, sample index); each pixel's samples are
+    added in index order at the end of a round -- the oracle's bits (several rounds, ragged sizes, pathLength 32)."""
+    monkeypatch.setenv('PT_SCHED', '7')
+    monkeypatch.setenv('PT_STEAL_S', str(steal_s))
+    monkeypatch.setenv('PT_REGEN_T', str(regen_t))
+    sc = ptlib.Scene.load(scene_path(name))
+    ubo = sc.pack_ubo()
+    p = sc.pack_params(1, w, h, spf, pl)
+    r = ptlib.Renderer(device=0, mode=ptlib.MODE_STRICT, jit=jit)
+    r.set_scene(ubo, sc.sdf_sources)
+    r.resize(w, h)
+    r.render(p, spp, spf)
+    got = r.read_xyz()
+    r.close()
+    ref = oracle.Oracle(ubo, [s.decode() for s in sc.sdf_sources]).render(p, spp, spf)
+    assert_bit_equal(got, ref, '%s v3s S=%d T=%d' % (name, steal_s, regen_t))

@@ -136,7 +136,8 @@ def test_nvrtc_builds_the_kernel_with_shipped_snippets(ptlib, name, mode):
     ('scene10', 1, {'PT_SCHED': '5', 'PT_MPARK': '1'}), ('scene10', 1, {'PT_SCHED': '5', 'PT_MPARK': '1', 'PT_MPARK_CAP': '32', 'PT_MIN_BLOCKS': '5'}),
     ('scene10', 0, {'PT_SCHED': '5'}), ('scene10', 0, {'PT_SCHED': '6'}), ('scene10', 0, {'PT_SCHED': '5', 'PT_MPARK': '1'}),
     ('scene9', 1, {}), ('scene8', 1, {'PT_SCHED': '5', 'PT_STEAL_S': '8'}),
-    ('scene1', 1, {'PT_SCHED': '0'}), ('scene1', 1, {'PT_SCHED': '3'}), ('scene1', 1, {'PT_SCHED': '5'}), ('scene1', 1, {'PT_SCHED': '6'})])
+    ('scene1', 1, {'PT_SCHED': '0'}), ('scene1', 1, {'PT_SCHED': '3'}), ('scene1', 1, {'PT_SCHED': '5'}), ('scene1', 1, {'PT_SCHED': '6'}),
+    ('scene1', 1, {'PT_SCHED': '7'}), ('scene1', 0, {'PT_SCHED': '7'}), ('scene10', 1, {'PT_SCHED': '7'})])
 def test_every_driver_of_the_megakernel_builds(ptlib, monkeypatch, name, mode, env):
     """The scene-specialised kernel (jit policy 2) compiles with NVRTC for sm_100a under every driver / knob the A/B
     measurements use (no GPU needed), stays inside the 48 KB of static shared memory and the register budget of its

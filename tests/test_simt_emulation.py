@@ -3,7 +3,8 @@
 pathtracer_b200/csrc/pt_kernel.cuh is compiled, unmodified, for the host: one thread per CUDA thread, barriers for
 __syncthreads / __ballot_sync / __shfl_sync / __syncwarp, statics for shared memory.  In strict mode the arithmetic is
 the oracle's, so every driver -- the nested loops of v1, the in-warp scheduler v2, sample stealing (v2s: table rounds),
-march parking, two pixels per lane (v2d), the flat loop (v3) -- must reproduce the oracle bit for bit, and the
+march parking, two pixels per lane (v2d), the flat loop (v3) and its pooled variant (v3s) -- must reproduce the oracle
+bit for bit, and the
 tile-streaming v2sp up to fp32 summation order.  What this does not cover: the device compiler, fast-math builds, and
 timing -- the `-m gpu` parity tests remain the gate for those.  TEST INFRASTRUCTURE: a checker, not a rendering path."""
 import ctypes as C
@@ -86,6 +87,7 @@ DRIVERS = {
     'v2s_table16': {'PT_SCHED': 5, 'PT_STEAL_S': 16}, 'v2s_table2': {'PT_SCHED': 5, 'PT_STEAL_S': 2},
     'v2s_park': {'PT_SCHED': 5, 'PT_STEAL_S': 8, 'PT_MPARK': 1, 'PT_MPARK_CAP': 20, 'PT_MPARK_MIN': 4},
     'v2s_park_tiny_stack': {'PT_SCHED': 5, 'PT_STEAL_S': 3, 'PT_MPARK': 1, 'PT_MPARK_CAP': 2, 'PT_MPARK_MIN': 1},
+    'v3s_table16': {'PT_SCHED': 7, 'PT_STEAL_S': 16}, 'v3s_table3': {'PT_SCHED': 7, 'PT_STEAL_S': 3, 'PT_REGEN_T': 4},
 }
 
 
@@ -107,6 +109,18 @@ def test_emulated_strict_kernel_equals_the_oracle(ptlib, driver, name, w, h, spp
     ref = oracle.Oracle(ubo, src).render(p, spp, spf)
     g, r = got.view(np.uint32), ref.view(np.uint32)
     assert np.array_equal(g, r), '%s on %s: %d floats differ' % (driver, name, int((g != r).sum()))
+
+
+@pytest.mark.parametrize('name,w,h,spp,spf,pl', [('scene0', 61, 43, 6, 3, 5), ('scene1', 50, 37, 16, 16, 5), ('scene10', 40, 24, 4, 4, 32)])
+def test_emulated_v3s_whole_dispatch_pool(ptlib, name, w, h, spp, spf, pl):
+    """v3s with PT_STEAL_S = 0 (the fast-mode configuration: one pool per dispatch, sums in shared memory in schedule
+    order) under strict arithmetic: equal to the oracle up to fp32 summation order on every pixel."""
+    ubo, p, src, raw = scene_inputs(name, w, h, spf, pl)
+    L = build_emulator(ptlib, {'PT_SCHED': 7, 'PT_STEAL_S': 0, 'PT_REGEN_T': 8}, src, raw)
+    got = emulate(L, ubo, p, spp, spf)
+    ref = oracle.Oracle(ubo, src).render(p, spp, spf)
+    scale = float(ref[..., :3].max())
+    assert np.allclose(got[..., :3], ref[..., :3], rtol=1e-5, atol=1e-6 * scale) and (got[..., 3] == 1.0).all()
 
 
 @pytest.mark.parametrize('name,w,h,spp,spf,pl,ctas,slots', [('scene0', 61, 43, 3, 1, 5, 2, 4), ('scene1', 50, 37, 8, 4, 5, 3, 2),
