@@ -137,3 +137,22 @@ def test_emulated_tile_streaming_driver(ptlib, name, w, h, spp, spf, pl, ctas, s
     scale = float(ref[..., :3].max())
     assert np.allclose(got[..., :3], ref[..., :3], rtol=1e-5, atol=1e-6 * scale)
     assert (got[..., 3] == 1.0).all()
+
+
+EDGE = [('scene0', 5, 3, 1, 1, 5), ('scene1', 17, 9, 33, 33, 5), ('scene1', 8, 4, 2, 2, 0), ('scene2', 31, 7, 34, 17, 2), ('scene0', 16, 8, 1, 1, 100)]
+
+
+@pytest.mark.parametrize('name,w,h,spp,spf,pl', EDGE)
+def test_emulated_drivers_at_the_edges(ptlib, name, w, h, spp, spf, pl):
+    """Frames smaller than a tile, one sample, 33 samples per dispatch (three table rounds, the last of one sample),
+    pathLength 0 (a sample is finished before it starts) and 100: table drivers give the oracle's bits, the pooled ones
+    (v2s / v3s with PT_STEAL_S = 0, v2sp with two slots) its image up to summation order."""
+    ubo, p, src, raw = scene_inputs(name, w, h, spf, pl)
+    ref = oracle.Oracle(ubo, src).render(p, spp, spf)
+    for driver in ('v2s_table16', 'v3s_table3', 'v2', 'v3'):
+        got = emulate(build_emulator(ptlib, DRIVERS[driver], src, raw), ubo, p, spp, spf)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), driver
+    scale = float(ref[..., :3].max()) or 1.0
+    for defs in ({'PT_SCHED': 5, 'PT_STEAL_S': 0}, {'PT_SCHED': 7, 'PT_STEAL_S': 0}, {'PT_SCHED': 6, 'PT_TILE_SLOTS': 2}):
+        got = emulate(build_emulator(ptlib, defs, src, raw), ubo, p, spp, spf, 3)
+        assert np.allclose(got[..., :3], ref[..., :3], rtol=1e-5, atol=1e-6 * scale) and (got[..., 3] == 1.0).all(), defs
