@@ -156,3 +156,26 @@ def test_emulated_drivers_at_the_edges(ptlib, name, w, h, spp, spf, pl):
     for defs in ({'PT_SCHED': 5, 'PT_STEAL_S': 0}, {'PT_SCHED': 7, 'PT_STEAL_S': 0}, {'PT_SCHED': 6, 'PT_TILE_SLOTS': 2}):
         got = emulate(build_emulator(ptlib, defs, src, raw), ubo, p, spp, spf, 3)
         assert np.allclose(got[..., :3], ref[..., :3], rtol=1e-5, atol=1e-6 * scale) and (got[..., 3] == 1.0).all(), defs
+
+
+def baked_counts(ubo, has_sdf):
+    """The defines jit policy 2 adds (pt_jit.cpp): primitive counts as compile-time constants, rolled loops with SDFs."""
+    n = [int(ubo[i]) for i in range(6)]
+    d = {'PT_N_SPHERES_CONST': n[0], 'PT_N_PLANES_CONST': n[1], 'PT_N_BOXES_CONST': n[2], 'PT_N_LENSES_CONST': n[3],
+         'PT_N_CYCLIDES_CONST': n[4], 'PT_N_SDF_CONST': n[5]}
+    if has_sdf:
+        d['PT_NO_UNROLL'] = 1
+    return d
+
+
+@pytest.mark.parametrize('driver,name,w,h,spp,spf,pl', [('v1', 'scene0', 48, 32, 4, 2, 5), ('v3s_table16', 'scene1', 70, 45, 40, 20, 5),
+                                                       ('v2s_table16', 'scene10', 40, 24, 4, 2, 5), ('v3s_table3', 'scene2', 33, 17, 9, 9, 5)])
+def test_emulated_scene_specialised_kernels(ptlib, driver, name, w, h, spp, spf, pl):
+    """jit policy 2 (what bench.py uses): the primitive counts baked in as constants, offsets folded, loops unrolled (or
+    rolled, with SDFs) -- other code from the same source, same bits."""
+    ubo, p, src, raw = scene_inputs(name, w, h, spf, pl)
+    defs = dict(DRIVERS[driver])
+    defs.update(baked_counts(ubo, bool(src)))
+    got = emulate(build_emulator(ptlib, defs, src, raw), ubo, p, spp, spf)
+    ref = oracle.Oracle(ubo, src).render(p, spp, spf)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
