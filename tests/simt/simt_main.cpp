@@ -23,6 +23,10 @@ extern "C" float pt_sdf_dispatch(float px, float py, float pz, unsigned set1);
 extern "C" float pt_sdfmaterial_dispatch(float px, float py, float pz, unsigned set1);
 #endif
 
+#ifdef PT_STATS
+extern "C" { unsigned long long pt_stats[16] = {0ull}; } /* the drivers' scheduling statistics (PT_STAT) */
+#endif
+
 #define PT_KERNEL_NS ptk_emu
 #include "pt_internal.h"
 #include "pt_kernel.cuh"
@@ -33,6 +37,19 @@ extern "C" int simt_sched(void) { return PT_SCHED; }
 
 /* accum_mode 0: pt_dispatch (params carry frame / currentSamples); 2: pt_dispatch_sum(first, n).  image: W*H float4.
  * persistent_ctas: grid of the tile-streaming driver (PT_SCHED=6); ignored otherwise. */
+/* only blocks bx0 <= bx < bx0 + nbx, by0 <= by < by0 + nby of the grid run when nbx > 0 (scheduling statistics of a
+ * full-size frame from a sample of its tiles, tests/simt_stats.py) */
+static int g_bx0 = 0, g_by0 = 0, g_nbx = 0, g_nby = 0;
+extern "C" void simt_select_blocks(int bx0, int by0, int nbx, int nby) { g_bx0 = bx0; g_by0 = by0; g_nbx = nbx; g_nby = nby; }
+extern "C" void simt_stats(unsigned long long* out16, int reset) {
+#ifdef PT_STATS
+    for (int i = 0; i < 16; i++) { out16[i] = pt_stats[i]; if (reset) pt_stats[i] = 0ull; }
+#else
+    for (int i = 0; i < 16; i++) out16[i] = 0ull;
+    (void)reset;
+#endif
+}
+
 extern "C" int simt_dispatch(const pt_ubo* ubo, const pt_params* params, int accum_mode, int first, int n, float* image,
                              int persistent_ctas) {
     PtDevScene sc;
@@ -60,6 +77,10 @@ extern "C" int simt_dispatch(const pt_ubo* ubo, const pt_params* params, int acc
         std::vector<std::unique_ptr<SimtBlock>> blocks;
         std::vector<std::unique_ptr<SimtWarp>> warps;
         for (unsigned b = b0; b < b0 + concurrent && b < gridDim.x * gridDim.y; b++) {
+            if (g_nbx > 0) {
+                const int bx = (int)(b % gridDim.x), by = (int)(b / gridDim.x);
+                if (bx < g_bx0 || bx >= g_bx0 + g_nbx || by < g_by0 || by >= g_by0 + g_nby) continue;
+            }
             blocks.emplace_back(new SimtBlock(PT_BLOCK_THREADS));
             for (int w = 0; w < nwarps; w++) warps.emplace_back(new SimtWarp());
             SimtBlock* blk = blocks.back().get();
