@@ -95,7 +95,7 @@ int pt_create(int device, pt_ctx** out);
 void pt_destroy(pt_ctx* ctx);
 const char* pt_last_error(const pt_ctx* ctx); /* ctx may be NULL: last error of a failed pt_create / loader call */
 int pt_set_mode(pt_ctx* ctx, int mode);       /* default PT_MODE_STRICT; takes effect at the next pt_set_scene */
-/* Run-time compilation policy (env PT_JIT overrides the default 1): 0 = statically compiled kernels only (scenes
+/* Run-time compilation policy (default 1): 0 = statically compiled kernels only (scenes
  * with SDF snippets are refused), 1 = NVRTC only for scenes with SDF snippets, 2 = always NVRTC, with the scene's
  * primitive counts baked in so the intersection loops unroll. Takes effect at the next pt_set_scene. */
 int pt_set_jit(pt_ctx* ctx, int policy);
@@ -103,12 +103,29 @@ int pt_set_jit(pt_ctx* ctx, int policy);
  * (bit-identical in strict mode); profiles/ compares them per scene. */
 int pt_set_pipeline(pt_ctx* ctx, int pipeline);
 /* Closest-hit search of Intersection / LightSourceVisibilityCheck (shader.comp:862-934, 1121-1216): the reference scans
- * every primitive; from min_prims spheres + boxes + lenses (default 12, env PT_BVH_MIN) libpt_cuda walks a host-built
+ * every primitive; from min_prims spheres + boxes + lenses (default 12) libpt_cuda walks a host-built
  * BVH over those instead (run-time compiled kernels only, i.e. not with jit policy 0); planes and cyclides are still
  * scanned in order.  Same winner -- smallest t, ties to the lowest object index; bit-identical in strict mode.
  * min_prims <= 0 disables the tree.  Takes effect at the next pt_set_scene; pt_bvh_active tells whether the current scene uses it. */
 int pt_set_bvh(pt_ctx* ctx, int min_prims);
 int pt_bvh_active(const pt_ctx* ctx);
+/* Tuning options of the run-time compiled kernels.  They choose HOW the kernel schedules the work, never WHAT it
+ * computes: every setting renders the same image (bit-identical in strict mode).  -1 = auto (the measured default for
+ * the scene).  Take effect at the next pt_set_scene; an unknown key or a value out of range is PT_ERR_ARG.
+ *   "sched"       driver: 0 v1 nested loops, 7 v3s flat loop + sample pool, 5 v2s phase machine + sample pool,
+ *                 8 v2m phase machine + pool of parked marching paths (SDF scenes)                        [-1]
+ *   "sdf_reps"    SDF() evaluations per execution of the SDF phase                                          [16]
+ *   "feed_t"      v2s / v2m: the SDF phase waits until every other phase has fewer lanes than this          [8]
+ *   "regen_t"     v3s: finished lanes that trigger a regeneration                                           [16]
+ *   "steal_s"     samples per pixel per round of the warp's sample pool; 0 = the whole dispatch (fast mode) [-1]
+ *   "pool_cap" / "pool_min"   v2m: slots per warp / marching rays from which the SDF phase runs            [32 / 24]
+ *   "min_blocks"  __launch_bounds__ minimum CTAs per SM                                                     [-1]
+ *   "no_unroll"   1 keeps the primitive loops rolled although the counts are baked (jit policy 2)           [-1]
+ *   "stats"       1 builds the scheduling counters in (pt_debug_stats)                                      [0]
+ *   "wf_refill", "wf_max_paths"   wavefront pipeline: evaluations between refills; paths in flight per chunk
+ *   "bvh_while_while"             BVH traversal loop shape */
+int pt_set_option(pt_ctx* ctx, const char* key, long long value);
+int pt_get_option(const pt_ctx* ctx, const char* key, long long* value);
 
 /* UpdateUniformBuffer + RecompileComputeShaders (host:3642-3811, 3836-3841, InsertSDF host:2004-2054).
  * sdf_glsl[i] is scene["sdf"][i]["glsl"] unchanged; n_sdf must equal ubo->numObjects[5].  With n_sdf > 0 the
@@ -212,7 +229,13 @@ long pt_sdf_translate(const char* const* sdf_glsl, int n_sdf, const float* sdfs_
 int pt_sdf_compile_check(const char* const* sdf_glsl, int n_sdf, const float* sdfs_raw, int mode);
 /* Same for the whole kernel pt_set_scene would build for (ubo, snippets, mode); bake_counts as jit policy 2 */
 int pt_kernel_compile_check(const pt_ubo* ubo, const char* const* sdf_glsl, int n_sdf, int mode, int bake_counts);
-/* Scheduling statistics of a kernel built with env PT_STATS=1: per phase p of the v2 driver, out16[2p] = times the
+/* The same with tuning options given as "key=value,key=value" (see pt_set_option) */
+int pt_kernel_compile_check_opts(const pt_ubo* ubo, const char* const* sdf_glsl, int n_sdf, int mode, int bake_counts,
+                                 const char* options);
+/* FP32 peak of the device, measured: independent FFMA chains on every SM, CUDA-event time, best of `repeats`.
+ * bench.py's roofline denominator (MEASURED_PEAKS.json holds no FP32 figure). */
+int pt_fp32_peak(pt_ctx* ctx, int repeats, double* tflops, double* ms_best);
+/* Scheduling statistics of a kernel built with option "stats" = 1: per phase p of the v2 driver, out16[2p] = times the
  * phase ran, out16[2p+1] = lanes it served (debug / profiles only) */
 int pt_debug_stats(pt_ctx* ctx, unsigned long long* out16, int reset);
 /* Evaluate a pt_math.h function on the device: fn 0 sin,1 cos,2 acos,3 exp2,4 log2,5 exp,6 log,7 pow(x,y),8 PCG32 */

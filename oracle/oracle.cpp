@@ -52,7 +52,7 @@ enum {
     C_SAMPLES, C_RAYS_PATH, C_RAYS_SHADOW, C_SPHERE, C_SPHERE_HIT, C_PLANE, C_PLANE_HIT, C_BSPHERE, C_BOX, C_BOX_HIT,
     C_LENS, C_SLICE_HIT, C_CYCLIDE, C_CYCLIDE_3ROOT, C_CYCLIDE_HIT, C_SEARCHSDF, C_ST_CALLS, C_ST_ENTER, C_ST_ITER,
     C_ST_BACKSTEP, C_ST_HIT, C_SDF_EVAL, C_SDFMAT_EVAL, C_BOUNCE, C_EMIT_HIT, C_LIGHT_SAMPLE, C_LIGHT_VISIBLE,
-    C_RNG, C_MISS, C_N
+    C_RNG, C_MISS, C_ST_ITER_BEYOND, C_ST_ENTER_BEYOND, C_N
 };
 struct Counters { unsigned long long v[C_N]; };
 #ifdef PT_COUNT
@@ -701,10 +701,12 @@ struct Shader {
             return false;
         }
         CNT(C_ST_ENTER, 1);
+        if (t > hitdist) CNT(C_ST_ENTER_BEYOND, 1); /* the bounding box starts behind the nearest analytic hit */
         float k = gsign(SDF(ray.origin, set1));
 
         for (int i = 0; i < 512; i++) {
             CNT(C_ST_ITER, 1);
+            if (t > hitdist) CNT(C_ST_ITER_BEYOND, 1); /* marching behind the nearest analytic hit (cannot win if t never returns) */
             float radius = SDF(p, set1);
             if (insT > (gabs(previousRadius) + gabs(radius))) {
                 CNT(C_ST_BACKSTEP, 1);
@@ -1626,7 +1628,7 @@ int oracle_num_counters(void) { return C_N; }
 const char* oracle_counter_names(void) {
     return "samples,rays_path,rays_shadow,sphere,sphere_hit,plane,plane_hit,bsphere,box,box_hit,lens,slice_hit,"
            "cyclide,cyclide_3root,cyclide_hit,searchsdf,st_calls,st_enter,st_iter,st_backstep,st_hit,sdf_eval,"
-           "sdfmat_eval,bounce,emit_hit,light_sample,light_visible,rng,miss";
+           "sdfmat_eval,bounce,emit_hit,light_sample,light_visible,rng,miss,st_iter_beyond,st_enter_beyond";
 }
 int oracle_has_counters(void) {
 #ifdef PT_COUNT

@@ -3,7 +3,7 @@
 Nothing in here computes: the hot path is hand-written sm_100a CUDA behind the C ABI of include/pt_abi.h.
 There is no CPU fallback; importing works anywhere, creating a Renderer needs a CUDA device and the built library.
 """
-from .api import (LibraryNotBuilt, MultiRenderer, PtError, Renderer, Scene, build_library, lib, library_path, MODE_FAST, MODE_STRICT,
+from .api import (kernel_compile_check, LibraryNotBuilt, MultiRenderer, PtError, Renderer, Scene, build_library, lib, library_path, MODE_FAST, MODE_STRICT,
                   PARAMS_DTYPE, PIPE_MEGAKERNEL, PIPE_WAVEFRONT, UBO_FLOATS)
 
 __all__ = ['LibraryNotBuilt', 'MultiRenderer', 'PtError', 'Renderer', 'Scene', 'build_library', 'lib', 'library_path', 'MODE_FAST',

@@ -131,6 +131,12 @@ def lib():
         L.pt_sdf_compile_check.argtypes = [C.POINTER(C.c_char_p), ci, vp, ci]
         L.pt_math_eval.argtypes = [vp, ci, vp, vp, vp, C.c_size_t]
         L.pt_sdf_eval.argtypes = [vp, vp, C.c_size_t, C.c_uint32, vp, vp]
+        L.pt_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
+        L.pt_get_option.argtypes = [vp, C.c_char_p, C.POINTER(C.c_longlong)]
+        L.pt_kernel_compile_check.argtypes = [vp, C.POINTER(C.c_char_p), ci, ci, ci]
+        L.pt_kernel_compile_check_opts.argtypes = [vp, C.POINTER(C.c_char_p), ci, ci, ci, C.c_char_p]
+        L.pt_fp32_peak.argtypes = [vp, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.pt_debug_stats.argtypes = [vp, vp, ci]
         _lib = L
     return _lib
 
@@ -172,6 +178,16 @@ def sdf_compile_check(sources, sdfs_raw=None, mode=MODE_STRICT):
     """NVRTC compile-only check of the whole kernel with these snippets; needs no GPU."""
     raw = np.zeros(6 * max(len(sources), 1), dtype=np.float32) if sdfs_raw is None else np.ascontiguousarray(sdfs_raw, dtype=np.float32)
     _check(lib().pt_sdf_compile_check(_c_strings(sources), len(sources), _ptr(raw), mode))
+
+
+def kernel_compile_check(ubo, sources, mode=MODE_STRICT, bake_counts=True, options=None, wavefront=False, bvh=False):
+    """NVRTC compile-only check of the kernel pt_set_scene would build (needs no GPU).  `options` is a dict of
+    pt_set_option keys.  Returns the ptxas report (registers, spills, shared memory)."""
+    ubo = np.ascontiguousarray(ubo, dtype=np.float32)
+    opts = ','.join('%s=%d' % (k, int(v)) for k, v in (options or {}).items()).encode()
+    m = int(mode) | (2 if wavefront else 0) | (4 if bvh else 0)
+    _check(lib().pt_kernel_compile_check_opts(_ptr(ubo), _c_strings(list(sources)), len(sources), m, int(bool(bake_counts)), opts))
+    return (lib().pt_last_error(None) or b'').decode(errors='replace')
 
 
 class Scene:
@@ -232,7 +248,7 @@ class Scene:
 class Renderer:
     """One device context (pt_ctx). Fails loudly without a GPU: there is no CPU fallback."""
 
-    def __init__(self, device=0, mode=MODE_STRICT, jit=None, pipeline=PIPE_MEGAKERNEL):
+    def __init__(self, device=0, mode=MODE_STRICT, jit=None, pipeline=PIPE_MEGAKERNEL, options=None):
         self._ctx = C.c_void_p()
         self.width = self.height = 0
         _check(lib().pt_create(device, C.byref(self._ctx)))
@@ -241,7 +257,29 @@ class Renderer:
             _check(lib().pt_set_jit(self._ctx, jit), self._ctx)
         if pipeline != PIPE_MEGAKERNEL:
             _check(lib().pt_set_pipeline(self._ctx, pipeline), self._ctx)
+        for k, v in (options or {}).items():
+            self.set_option(k, v)
         self._keep = None
+
+    def set_option(self, key, value):
+        """pt_set_option: a tuning option of the run-time compiled kernels ("sched", "steal_s", ...); next set_scene."""
+        _check(lib().pt_set_option(self._ctx, key.encode(), int(value)), self._ctx)
+
+    def get_option(self, key):
+        v = C.c_longlong()
+        _check(lib().pt_get_option(self._ctx, key.encode(), C.byref(v)), self._ctx)
+        return int(v.value)
+
+    def fp32_peak(self, repeats=5):
+        """Measured FP32 FMA peak of the device in TFLOP/s (pt_fp32_peak)."""
+        t, ms = C.c_double(), C.c_double()
+        _check(lib().pt_fp32_peak(self._ctx, repeats, C.byref(t), C.byref(ms)), self._ctx)
+        return float(t.value), float(ms.value)
+
+    def debug_stats(self, reset=True):
+        out = (C.c_ulonglong * 16)()
+        _check(lib().pt_debug_stats(self._ctx, out, 1 if reset else 0), self._ctx)
+        return [int(v) for v in out]
 
     def close(self):
         if getattr(self, '_ctx', None) and _lib is not None:

@@ -22,13 +22,35 @@ int pt_bvh_build(const PtDevScene* sc, std::vector<float>* blob, std::string* er
 int pt_sdf_generate(const char* const* sdf_glsl, int n_sdf, const float* sdfs_raw, std::string* out, std::string* err);
 
 /* pt_jit.cpp: NVRTC.  Returns a cubin for sm_100a in *cubin. */
+/* Tuning options of the run-time compiled kernels (pt_set_option, pt_abi.h).  -1 = "auto": pt_jit_compile picks the
+ * measured default for the scene.  They are part of the translation unit, hence of every cache key. */
+struct PtKnobs {
+    int sched = -1;       /* driver: 0 v1, 5 v2s, 7 v3s, 8 v2m */
+    int sdf_reps = 16;    /* SDF() evaluations per execution of the SDF phase */
+    int feed_t = 8;       /* v2s / v2m: the SDF phase waits until every feeder phase has fewer lanes than this */
+    int regen_t = 16;     /* v3s: waiting lanes that trigger a regeneration */
+    int steal_s = -1;     /* samples per pixel per round of the pool (0 = the whole dispatch, fast mode only) */
+    int min_blocks = -1;  /* __launch_bounds__ minimum CTAs per SM */
+    int no_unroll = -1;   /* 1: keep the primitive loops rolled although the counts are baked */
+    int pool_cap = 32;    /* v2m: slots of the per-warp pool of parked paths */
+    int pool_min = 24;    /* v2m: marching rays from which the SDF phase runs ahead of the feeders */
+    int stats = 0;        /* 1: build with the scheduling counters (pt_debug_stats) */
+    int wf_refill = 8;    /* wavefront march kernel: evaluations between refills */
+    int bvh_while_while = 0;
+};
+int pt_knob_set(PtKnobs* k, const char* key, long long value);       /* 0, or -1 for an unknown key / bad value */
+int pt_knob_get(const PtKnobs* k, const char* key, long long* value);
+int pt_knobs_parse(PtKnobs* k, const char* text, std::string* err);  /* "key=value,key=value" */
 struct PtJitOptions {
     int mode;            /* pt_mode */
     bool bake_counts;    /* compile primitive counts in as constants */
     bool wavefront;      /* also build the wavefront pipeline's kernels (pt_wavefront.cuh) */
     bool bvh;            /* closest hit through the BVH of pt_bvh.h instead of the brute-force scan */
     int counts[6];       /* spheres, planes, boxes, lenses, cyclides, sdfs */
+    PtKnobs knobs;
 };
+/* the complete translation unit pt_jit_compile would hand to NVRTC (also the key of every kernel cache) */
+std::string pt_jit_source(const std::string& sdf_unit, const PtJitOptions& opt);
 int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::vector<char>* cubin, std::string* log);
 
 /* pt_kernels_{strict,fast}.cu: statically compiled generic kernels (no SDF) and helpers */
@@ -36,6 +58,7 @@ extern "C" {
 void pt_launch_strict(const PtDevScene* sc, const PtDevParams* pr, const float* ubo, void* image, void* stream);
 void pt_launch_fast(const PtDevScene* sc, const PtDevParams* pr, const float* ubo, void* image, void* stream);
 void pt_launch_finalize(void* image, int n_texels, float invTotal, float exposure, void* stream);
+void pt_launch_fma_peak(float* out, int blocks, int threads, int iters, void* stream);
 void pt_launch_math_eval(int fn, const float* x, const float* y, float* out, size_t n, void* stream);
 const void* pt_static_kernel_strict(void);
 const void* pt_static_kernel_fast(void);

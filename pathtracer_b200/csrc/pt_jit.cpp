@@ -44,6 +44,14 @@ Nvrtc g_nvrtc;
 std::once_flag g_once;
 std::string g_load_error;
 
+/* the drivers the "auto" option resolves to (DESIGN.md section 7 has the A/B numbers) */
+#ifndef PT_DEFAULT_SCHED_SDF
+#define PT_DEFAULT_SCHED_SDF 5
+#endif
+#ifndef PT_DEFAULT_SCHED_ANALYTIC
+#define PT_DEFAULT_SCHED_ANALYTIC 0
+#endif
+
 /* Process-wide cache of compiled kernels, keyed by the complete translation unit (which spells out the mode, the baked
  * counts, every tuning knob and the generated SDF code): a cubin is independent of the device it will be loaded on, so
  * the contexts of a multi-GPU render (pt_multi.cpp) compile each scene once instead of once per GPU. */
@@ -76,10 +84,64 @@ void load_nvrtc() {
 
 }  // namespace
 
-int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::vector<char>* cubin, std::string* log) {
-    std::call_once(g_once, load_nvrtc);
-    if (!g_nvrtc.h) { *log = g_load_error; return PT_ERR_COMPILE; }
+int pt_knob_set(PtKnobs* k, const char* key, long long value) {
+    if (!k || !key) return -1;
+    const std::string s(key);
+    const int v = (int)value;
+    if (s == "sched") { if (v != -1 && v != 0 && v != 5 && v != 7 && v != 8) return -1; k->sched = v; }
+    else if (s == "sdf_reps") { if (v < 1 || v > 512) return -1; k->sdf_reps = v; }
+    else if (s == "feed_t") { if (v < 0 || v > 33) return -1; k->feed_t = v; }
+    else if (s == "regen_t") { if (v < 1 || v > 32) return -1; k->regen_t = v; }
+    else if (s == "steal_s") { if (v < -1 || v > 20) return -1; k->steal_s = v; }
+    else if (s == "min_blocks") { if (v < -1 || v == 0 || v > 16) return -1; k->min_blocks = v; }
+    else if (s == "no_unroll") { if (v < -1 || v > 1) return -1; k->no_unroll = v; }
+    else if (s == "pool_cap") { if (v < 1 || v > 32) return -1; k->pool_cap = v; }
+    else if (s == "pool_min") { if (v < 1 || v > 64) return -1; k->pool_min = v; }
+    else if (s == "stats") { if (v < 0 || v > 1) return -1; k->stats = v; }
+    else if (s == "wf_refill") { if (v < 1 || v > 512) return -1; k->wf_refill = v; }
+    else if (s == "bvh_while_while") { if (v < 0 || v > 1) return -1; k->bvh_while_while = v; }
+    else return -1;
+    return 0;
+}
+int pt_knob_get(const PtKnobs* k, const char* key, long long* value) {
+    if (!k || !key || !value) return -1;
+    const std::string s(key);
+    if (s == "sched") *value = k->sched; else if (s == "sdf_reps") *value = k->sdf_reps;
+    else if (s == "feed_t") *value = k->feed_t; else if (s == "regen_t") *value = k->regen_t;
+    else if (s == "steal_s") *value = k->steal_s; else if (s == "min_blocks") *value = k->min_blocks;
+    else if (s == "no_unroll") *value = k->no_unroll; else if (s == "pool_cap") *value = k->pool_cap;
+    else if (s == "pool_min") *value = k->pool_min; else if (s == "stats") *value = k->stats;
+    else if (s == "wf_refill") *value = k->wf_refill; else if (s == "bvh_while_while") *value = k->bvh_while_while;
+    else return -1;
+    return 0;
+}
+int pt_knobs_parse(PtKnobs* k, const char* text, std::string* err) {
+    if (!text) return 0;
+    std::string s(text);
+    size_t i = 0;
+    while (i < s.size()) {
+        size_t j = s.find(',', i);
+        if (j == std::string::npos) j = s.size();
+        const std::string item = s.substr(i, j - i);
+        i = j + 1;
+        if (item.empty()) continue;
+        const size_t eq = item.find('=');
+        if (eq == std::string::npos || pt_knob_set(k, item.substr(0, eq).c_str(), atoll(item.c_str() + eq + 1)) != 0) {
+            if (err) *err = "bad option '" + item + "'";
+            return -1;
+        }
+    }
+    return 0;
+}
 
+/* Driver selection and the defaults of the "auto" options, as measured on B200:
+ *   scenes the reference's scan handles without SDFs run the flat loop with the sample pool (v3s; round 1: v1);
+ *   scenes with SDFs, and BVH scenes with boxes / lenses / cyclides, run the phase machine (v2m / v2s);
+ *   primitive loops stay rolled when the kernel would otherwise outgrow the instruction cache (SDF scenes) or spill
+ *   (scan over more than 16 primitives: 169 spheres unrolled 0.10 vs 0.88 Gsamples/s rolled);
+ *   strict builds sum a round's samples in index order from a shared-memory table, fast builds pool the whole dispatch. */
+std::string pt_jit_source(const std::string& sdf_unit, const PtJitOptions& opt) {
+    const PtKnobs& k = opt.knobs;
     std::string src;
     src += opt.mode == PT_MODE_FAST ? "#define PT_FAST 1\n#define PT_KERNEL_NS ptk_jit_fast\n"
                                     : "#define PT_KERNEL_NS ptk_jit_strict\n";
@@ -90,51 +152,50 @@ int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::ve
                                 "PT_N_CYCLIDES_CONST", "PT_N_SDF_CONST"};
         for (int i = 0; i < 6; i++) src += std::string("#define ") + names[i] + " " + std::to_string(opt.counts[i]) + "\n";
     }
-    /* Driver selection and tuning knobs (env overrides are for A/B measurements: bench.py, profiles/).
-     * Measured on B200 (profiles/r01_sched_ab.md): scenes without SDFs are fastest with the v1 driver (nested
-     * loops), scenes with SDFs with the v2 in-warp scheduler and rolled primitive loops (the kernel is instruction-
-     * cache bound); the fast build wants 6 CTAs/SM, the strict one 4. */
-    struct Knob { const char* name; int dflt; };
-    /* BVH scenes (profiles/r01_bvh): with boxes / lenses / cyclides among the primitives the in-warp scheduler wins
-     * (2.09 vs 1.61 Gsamples/s on the 74-primitive mix), with spheres only v1 does (3.76 vs 3.58 on 169 spheres).
-     * Scan with many primitives: unrolled loops over baked counts spill (169 spheres: 0.10 vs 0.88 Gsamples/s rolled). */
+    const bool has_sdf = !sdf_unit.empty();
     const bool heavy = (opt.counts[2] + opt.counts[3] + opt.counts[4]) > 0;
     const int n_scanned = opt.counts[0] + opt.counts[1] + opt.counts[2] + opt.counts[3] + opt.counts[4];
-    /* v2s, the in-warp scheduler with sample stealing (profiles/r01_steal): +16..40 % over v2 on the SDF workloads, +9 % on
-     * the 74-primitive mix; scenes the reference's scan handles without SDFs stay on v1 (10.85 vs 9.85 Gsamples/s, cfg2). */
-    const int sched = (!sdf_unit.empty() || (opt.bvh && heavy)) ? 5 : 0;
-    const char* sched_env = getenv("PT_SCHED");
-    int sched_eff = (sched_env && sched_env[0]) ? atoi(sched_env) : sched;
-    if (sched_eff == 6 && opt.mode != PT_MODE_FAST) sched_eff = 5; /* v2sp sums in schedule order: strict builds keep v2s' table */
-    const int no_unroll = (!sdf_unit.empty() || (!opt.bvh && n_scanned > 16)) ? 1 : 0;
-    /* v2s: strict mode needs the per-sample table (sums in sample order); fast mode pools the whole dispatch (0) */
-    const char* steal_env = getenv("PT_STEAL_S");
-    const char* park_env = getenv("PT_MPARK");
-    const int park = (park_env && park_env[0]) ? atoi(park_env) : 0;
-    /* the strict build's table shares the 48 KB of static shared memory with the parking stack */
-    const int steal_dflt = opt.mode == PT_MODE_FAST ? 0 : ((park && !sdf_unit.empty()) ? 8 : 16);
-    int steal_s = (steal_env && steal_env[0]) ? atoi(steal_env) : steal_dflt;
-    if (opt.mode != PT_MODE_FAST && steal_s == 0) steal_s = steal_dflt;
-    if (opt.mode != PT_MODE_FAST && park && !sdf_unit.empty() && steal_s > 8) steal_s = 8;
-    /* shared memory per CTA: v2d 45 KB, v2s 16 KB + 1.5 KB x PT_STEAL_S -> 5 CTAs/SM fit */
-    const int min_blocks_fast = (sched_eff == 4 || ((sched_eff == 5 || sched_eff == 7) && steal_s > 8)) ? 5 : 6;
-    const Knob knobs[] = {{"PT_SCHED", sched}, {"PT_SDF_REPS", 16}, {"PT_FEED_T", 8}, {"PT_STEAL_S", -1},
-                          {"PT_MIN_BLOCKS", opt.mode == PT_MODE_FAST ? min_blocks_fast : 4},
-                          {"PT_NO_UNROLL", no_unroll}, {"PT_STATS", 0},
-                          {"PT_WF_REFILL", 8}, {"PT_POOL_MIN", 24}, {"PT_COOP_NORMALS", 0}, {"PT_BVH_WHILE_WHILE", 0}, {"PT_REGEN_T", 16}, {"PT_SDF_MIN", 0}, {"PT_SDF_EXIT", 0}, {"PT_SWAP_MIN", 8}, {"PT_TILE_SLOTS", 4}, {"PT_MPARK", 0}, {"PT_MPARK_CAP", 20}, {"PT_MPARK_MIN", 12}};
-    for (const Knob& k : knobs) {
-        const char* v = getenv(k.name);
-        const int val = (v && v[0]) ? atoi(v) : k.dflt;
-        if (std::string(k.name) == "PT_STATS" && val == 0) continue;
-        if (std::string(k.name) == "PT_SCHED") { src += "#define PT_SCHED " + std::to_string(sched_eff) + "\n"; continue; }
-        if (std::string(k.name) == "PT_STEAL_S") { src += "#define PT_STEAL_S " + std::to_string(steal_s) + "\n"; continue; }
-        src += std::string("#define ") + k.name + " " + std::to_string(val) + "\n";
+    int sched = k.sched;
+    if (sched < 0) sched = has_sdf ? PT_DEFAULT_SCHED_SDF : ((opt.bvh && heavy) ? 5 : PT_DEFAULT_SCHED_ANALYTIC);
+    if (sched == 8 && !has_sdf) sched = 5; /* nothing marches */
+    const int no_unroll = k.no_unroll >= 0 ? k.no_unroll : ((has_sdf || (!opt.bvh && n_scanned > 16)) ? 1 : 0);
+    const bool pooled = (sched == 5 || sched == 7 || sched == 8);
+    int steal_s = k.steal_s;
+    if (steal_s < 0) steal_s = opt.mode == PT_MODE_FAST ? 0 : (sched == 8 ? 4 : 16);
+    if (opt.mode != PT_MODE_FAST && steal_s == 0) steal_s = (sched == 8 ? 4 : 16); /* strict builds sum in sample order */
+    int pool_cap = k.pool_cap;
+    /* static shared memory is capped at 48 KB: uniform block + per-warp table + per-warp pool of 50-word slots */
+    while (sched == 8 && 16388 + 4 * 4 * ((steal_s == 0 ? 96 : 96 * steal_s) + 50 * pool_cap) > 49152 && pool_cap > 4) pool_cap--;
+    int min_blocks = k.min_blocks;
+    if (min_blocks < 0) {
+        if (opt.mode != PT_MODE_FAST) min_blocks = 4;
+        else if (sched == 8) min_blocks = 5;                    /* 16 KB + 26 KB of shared memory per CTA */
+        else min_blocks = (pooled && steal_s > 8) ? 5 : 6;      /* 85 registers: +12 % over 4 CTAs/SM on scene1 */
     }
+    src += "#define PT_SCHED " + std::to_string(sched) + "\n";
+    src += "#define PT_SDF_REPS " + std::to_string(k.sdf_reps) + "\n";
+    src += "#define PT_FEED_T " + std::to_string(k.feed_t) + "\n";
+    src += "#define PT_REGEN_T " + std::to_string(k.regen_t) + "\n";
+    src += "#define PT_STEAL_S " + std::to_string(steal_s) + "\n";
+    src += "#define PT_MIN_BLOCKS " + std::to_string(min_blocks) + "\n";
+    src += "#define PT_NO_UNROLL " + std::to_string(no_unroll) + "\n";
+    src += "#define PT_POOL_CAP " + std::to_string(pool_cap) + "\n";
+    src += "#define PT_POOL_MIN " + std::to_string(k.pool_min) + "\n";
+    src += "#define PT_WF_REFILL " + std::to_string(k.wf_refill) + "\n";
+    src += "#define PT_BVH_WHILE_WHILE " + std::to_string(k.bvh_while_while) + "\n";
+    if (k.stats) src += "#define PT_STATS 1\n";
     src += opt.wavefront ? "#include \"pt_wavefront.cuh\"\n" : "#include \"pt_kernel.cuh\"\n";
     src += sdf_unit;
     src += "\nPT_DEFINE_RENDER_KERNEL(pt_render_jit)\n";
-    if (!sdf_unit.empty()) src += "PT_DEFINE_SDF_EVAL_KERNEL(pt_sdf_eval_jit)\n";
+    if (has_sdf) src += "PT_DEFINE_SDF_EVAL_KERNEL(pt_sdf_eval_jit)\n";
     if (opt.wavefront) src += "PT_DEFINE_WAVEFRONT_KERNELS\n";
+    return src;
+}
+
+int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::vector<char>* cubin, std::string* log) {
+    std::call_once(g_once, load_nvrtc);
+    if (!g_nvrtc.h) { *log = g_load_error; return PT_ERR_COMPILE; }
+    const std::string src = pt_jit_source(sdf_unit, opt);
 
     if (!getenv("PT_JIT_DUMP")) {
         std::lock_guard<std::mutex> lock(g_cache_mu);

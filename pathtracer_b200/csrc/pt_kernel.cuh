@@ -22,24 +22,23 @@
  *   - the whole uniform block (CIE table, material/light tables: divergent indices) is staged in shared memory;
  *   - a warp covers an 8x4 pixel tile so primary rays stay coherent.
  *
- * Layout of this file: value types and mode-dependent primitives; the shader's functions (RNG, spectral helpers,
- * intersections, SDF search); then the DRIVERS that run them --
- *   v1  (PT_SCHED 0)  nested sample / bounce loops per thread            default for scenes without SDFs
- *   v2  (PT_SCHED 1)  four phases over explicit PathState, one phase per warp iteration chosen by ballot,
- *                     lanes refill themselves with their pixel's next sample   default for scenes with SDFs
- *   v2p (PT_SCHED 2)  v2 + a CTA-shared march pool (measured slower: profiles/r01_pool)
- *   v3  (PT_SCHED 3)  v1's loop bodies in one flat loop with gated path regeneration (PT_REGEN_T)
- *   v2d (PT_SCHED 4)  v2 with two pixels per lane, the idle one parked in shared memory: a lane only waits for the SDF
- *                     phase when both its paths do
- *   v2sp (PT_SCHED 6) v2s with persistent warps that stream over tiles claimed from a global counter, several tiles in
- *                     flight per warp (fast mode; strict builds fall back to v2s)
- *   v3s (PT_SCHED 7)  v3's flat loop with v2s' sample pool (verified on the host emulator, not yet measured)
- *   v2s (PT_SCHED 5)  v2 with in-warp sample stealing: the warp's 32 x S samples are a pool of work items, a lane that
- *                     finishes a path takes the next one whichever pixel it belongs to; per-sample XYZ in shared memory,
- *                     summed per pixel in sample order at the end of a round
+ * Layout of this file: value types and mode-dependent primitives; the shader's leaf functions (RNG, spectral helpers,
+ * intersections, SDF search); then ONE statement of a path as four phases over an explicit PathState --
+ *   PhaseNew (camera + lens + wavelengths), PhaseIsect (closest hit over the primitives + SearchSDF), PhaseSdfEval (one
+ *   SDF() evaluation of the march or of the numerical normal), PhaseShade (emitter / BSDF / light sample / roulette),
+ *   PathColor (XYZ projection) --
+ * and the DRIVERS that schedule those phases over the lanes of a warp:
+ *   v1  (PT_SCHED 0)  nested sample / bounce loops per thread (TraceRayFlat = ISECT + SHADE + shadow ISECT inline)
+ *   v3s (PT_SCHED 7)  v1's loop bodies in one flat loop; finished lanes regenerate from the tile's sample pool
+ *   v2s (PT_SCHED 5)  one phase per warp iteration chosen by ballot; finished lanes take the next sample of the tile's
+ *                     pool whichever pixel it belongs to (in-warp sample stealing)
+ *   v2m (PT_SCHED 8)  v2s + a per-warp pool of PARKED paths in shared memory: a ray that has to march is parked with its
+ *                     whole path state and its lane takes other work; the SDF phase marches parked rays with all 32
+ *                     lanes whatever paths those lanes hold in registers
  * -- and the kernel entry macros.  pt_wavefront.cuh runs the same phases as separate kernels over state in HBM.
- * The kernel is instruction-cache bound (16-byte SASS, 28-45 KB per scene): single call sites and rolled loops
- * are deliberate (profiles/README.md).
+ * Drivers that were measured and dropped (v2, v2p CTA job board, v2d two pixels per lane, v3, v2sp persistent tiles,
+ * march parking inside v2s) live in the history of this file and in profiles/r01_*; DESIGN.md section 7 has their numbers.
+ * The kernel is instruction-cache bound (16-byte SASS): single call sites and rolled loops are deliberate.
  */
 #ifndef PT_KERNEL_CUH
 #define PT_KERNEL_CUH
@@ -651,75 +650,6 @@ PT_DEV bool SearchSDF(const Ctx& c, V3 p, V3 invdir, float& tMin, float& tMax, u
     return isFoundSDF;
 }
 
-/* shader.comp:779-860.  For shadow rays the normal probes and the material are skipped (never read). */
-PT_DEV_NOINLINE void SphereTracing(const Ctx& c, const Ray& ray, Hit& h, const bool kShadow) {
-    const float MAXDIST = 1e5f;
-    float t = 1e-3f;
-    float insT = 0.0f;
-    const float omegaMax = 1.70f;
-    const float omegaSpeed = 0.20f;
-    float omega = omegaMax;
-    float previousRadius = 0.0f;
-    V3 p = ray.origin;
-    const V3 invdir = mk3(PTK_DIV(1.0f, ray.dir.x), PTK_DIV(1.0f, ray.dir.y), PTK_DIV(1.0f, ray.dir.z));
-    int points = 0;
-    float tMin = MAXDIST, tMax = MAXDIST;
-    unsigned set1 = 0u;
-    if (SearchSDF(c, p, invdir, tMin, tMax, set1)) {
-        t = PTK_MAX(tMin, t);
-        p = fma3(ray.dir, t, ray.origin);
-    } else {
-        return;
-    }
-    const float k = gsign(SDF(ray.origin, set1));
-
-    for (int i = 0; i < 512; i++) {
-        const float radius = SDF(p, set1);
-        if (insT > (fabsf(previousRadius) + fabsf(radius))) {
-            t -= insT;
-            omega = 1.0f;
-            insT = previousRadius * omega * k;
-            t += insT;
-            p = fma3(ray.dir, t, ray.origin);
-            continue;
-        }
-        if (fabsf(radius) < 1e-4f) break;
-        if (t > tMax) points += 1; else points = 0;
-        if (points >= 2) {
-            t = tMax + 1e-3f;
-            tMin = MAXDIST; tMax = MAXDIST;
-            if (SearchSDF(c, fma3(ray.dir, t, ray.origin), invdir, tMin, tMax, set1)) {
-                tMin += t; tMax += t;
-                t = PTK_MAX(tMin, t);
-                p = fma3(ray.dir, t, ray.origin);
-                continue;
-            } else {
-                return;
-            }
-        }
-        insT = radius * omega * k;
-        t += insT;
-        p = fma3(ray.dir, t, ray.origin);
-        const float omegaSpeedFactor = PTK_MIN(PTK_DIV(radius, previousRadius), 0.99f);
-        omega += omegaSpeed * (PTK_MIN(PTK_DIV(1.0f, 1.0f - omegaSpeedFactor), omegaMax) - omega);
-        previousRadius = radius;
-    }
-
-    if (t < h.t) {
-        h.t = t - 1e-3f;
-        h.objectID = -1;
-        if (!kShadow) {
-            p = fma3(ray.dir, t, ray.origin);
-            const float e = 1e-4f; /* shader.comp:721-730 */
-            const float nx = SDF(mk3(p.x + e, p.y + 0.0f, p.z + 0.0f), set1) - SDF(mk3(p.x - e, p.y - 0.0f, p.z - 0.0f), set1);
-            const float ny = SDF(mk3(p.x + 0.0f, p.y + e, p.z + 0.0f), set1) - SDF(mk3(p.x - 0.0f, p.y - e, p.z - 0.0f), set1);
-            const float nz = SDF(mk3(p.x + 0.0f, p.y + 0.0f, p.z + e), set1) - SDF(mk3(p.x - 0.0f, p.y - 0.0f, p.z - e), set1);
-            h.normal = normalize(mk3(nx, ny, nz));
-            h.materialID = ::pt_sdfmaterial_dispatch(p.x, p.y, p.z, set1);
-            h.lightID = -1.0f;
-        }
-    }
-}
 #endif /* PT_HAS_SDF */
 
 #if PT_BVH
@@ -812,13 +742,6 @@ PT_DEV void IntersectionAnalytic(const Ctx& c, const Ray& ray, Hit& h, const boo
     }
 }
 
-/* shader.comp:862-934 / 1121-1216 in one piece (used by the v1 driver) */
-PT_DEV void Intersection(const Ctx& c, const Ray& ray, Hit& h, const bool kShadow) {
-    IntersectionAnalytic(c, ray, h, kShadow);
-#if PT_HAS_SDF
-    SphereTracing(c, ray, h, kShadow);
-#endif
-}
 
 /* ---- sampling (shader.comp:976-1028, 1093-1119) ------------------------------------------------------------------ */
 PT_DEV V3 SampleCosineDirectionHemisphere(V3 normal, unsigned& seed) {
@@ -851,81 +774,6 @@ PT_DEV V3 ToWorld(V3 v, V3 n) {
     return b1 * v.x + b2 * v.y + n * v.z;
 }
 
-/* ---- one path (shader.comp:1298-1407) --------------------------------------------------------------------------- */
-PT_DEV V4 TracePath(const Ctx& c, V4 l, Ray ray, unsigned& seed) {
-    const PtDevScene& sc = *c.sc;
-    V4 radiance = mk4(0.0f, 0.0f, 0.0f, 0.0f);
-    V4 rayradiance = mk4(1.0f, 1.0f, 1.0f, 1.0f);
-    float MISBRDFWeight = 1.0f;
-    const int pathLength = c.pr->pathLength;
-    for (int bounce = 0; bounce < pathLength; bounce++) {
-        /* TraceRay, shader.comp:1345-1391 */
-        Hit h;
-        Intersection(c, ray, h, false);
-        if (!(h.t < 1e5f)) break; /* miss: black environment */
-        float temperature, luminosity;
-        GetLightMix(c, h.lightID, temperature, luminosity);
-        if (luminosity > 0.0f) { /* emitter hit terminates the path */
-            const V4 e = Emit(l, PTK_MAX(temperature, 0.0f), PTK_MAX(luminosity, 0.0f));
-            radiance = radiance + (e * rayradiance) * MISBRDFWeight;
-            break;
-        }
-        float peak, sigma, invertf;
-        GetMaterialMix(c, h.materialID, peak, sigma, invertf);
-        const V4 brdf = EvaluateBRDF(l, peak, sigma, invertf);
-
-        Ray outRay;
-        outRay.origin = fma3(ray.dir, h.t, ray.origin);
-        outRay.dir = SampleCosineDirectionHemisphere(h.normal, seed);
-        const float BRDFpdf = PTK_DIV(dot(outRay.dir, h.normal), PT_PI_F);
-
-        /* SampleLightSource, shader.comp:1298-1343 */
-        if (sc.numLights > 0.0f) {
-            const int randomLight = __float2int_rz(floorf(RandomFloatPCG32(seed) * sc.numLights));
-            const PtDevLightSlot& ls = sc.lightSlots[randomLight < sc.nLightSlots ? randomLight : sc.nLightSlots - 1];
-            const V3 toLight = mk3(ls.px - outRay.origin.x, ls.py - outRay.origin.y, ls.pz - outRay.origin.z);
-            const float invLightDistance = PTK_DIV(1.0f, length(toLight));
-            const V3 lightDir = toLight * invLightDistance;
-            const float sinthetaMax = PTK_MIN(ls.boundingRadius * invLightDistance, 1.0f);
-            const float costhetaMax = PTK_SQRT(1.0f - sinthetaMax * sinthetaMax);
-            Ray shadowRay;
-            shadowRay.origin = outRay.origin;
-            shadowRay.dir = ToWorld(SampleCosineUnitCone(seed, costhetaMax), lightDir);
-            float lightpdf = sc.invNumLights;
-            lightpdf *= PTK_DIV(dot(shadowRay.dir, lightDir), PT_PI_F * (1.0f - costhetaMax * costhetaMax));
-            MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + lightpdf * lightpdf);
-            const float costheta = dot(shadowRay.dir, h.normal);
-            const float deathProbability = 1.25f * PTK_MAX(MISBRDFWeight - 0.2f, 0.0f);
-            if (costheta >= 0.0f) {
-                if (RandomFloatPCG32(seed) > deathProbability) {
-                    Hit sh;
-                    Intersection(c, shadowRay, sh, true);
-                    if (sh.objectID == ls.objectID) {
-                        float lt, ll;
-                        GetLightMix(c, ls.lightID, lt, ll);
-                        const V4 rr = rayradiance * mulDiv4(brdf, costheta, lightpdf);
-                        const V4 e = Emit(l, PTK_MAX(lt, 0.0f), PTK_MAX(ll, 0.0f));
-                        radiance = radiance + (e * rr) * (1.0f - MISBRDFWeight);
-                    }
-                } else {
-                    MISBRDFWeight = 1.0f;
-                }
-            }
-        } else {
-            MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + 0.0f * 0.0f);
-        }
-
-        const float costheta = dot(outRay.dir, h.normal);
-        rayradiance = rayradiance * mulDiv4(brdf, costheta, BRDFpdf);
-        const float mx = PTK_MAX(rayradiance.x, PTK_MAX(rayradiance.y, PTK_MAX(rayradiance.z, rayradiance.w)));
-        const float rayProbability = PTK_MIN(PTK_MAX(mx, 0.0f), 0.99f);
-        if (RandomFloatPCG32(seed) > rayProbability) break;
-        rayradiance = rayradiance * PTK_DIV(1.0f, rayProbability);
-        ray = outRay;
-    }
-    return radiance;
-}
-
 /* shader.comp:1409-1444: two refractions through the camera's BK7 lens */
 PT_DEV void TracePathLens(const Ctx& c, float l, Ray& ray) {
     const PtDevLens& lens = c.pr->camLens;
@@ -954,46 +802,6 @@ PT_DEV void TracePathLens(const Ctx& c, float l, Ray& ray) {
     }
 }
 
-/* shader.comp:1446-1490: one spectral path sample -> CIE XYZ */
-PT_DEV V3 Scene(const Ctx& c, unsigned xyx, unsigned xyy, float uvx, float uvy, int k) {
-    const PtDevParams& pr = *c.pr;
-    unsigned seed = (unsigned)(pr.firstSample + k); /* GenerateSeed, shader.comp:948-958 */
-    PCG32(seed);
-    seed += xyx + (unsigned)pr.width * xyy;
-
-    const float j1 = RandomFloatPCG32(seed);
-    const float j2 = RandomFloatPCG32(seed);
-    uvx = uvx + PTK_DIV(2.0f * j1 - 0.5f, pr.resX);
-    uvy = uvy + PTK_DIV(2.0f * j2 - 0.5f, pr.resY);
-    uvx *= pr.sensorScale;
-    uvy *= pr.sensorScale;
-    const V3 camPos = mk3(pr.camPosX, pr.camPosY, pr.camPosZ);
-    Ray ray;
-    ray.origin = camPos + mulVM(mk3(uvx, uvy, 0.0f), pr.camM);
-    /* SampleUniformUnitDisk, shader.comp:976-982 */
-    const float rx = RandomFloatPCG32(seed);
-    const float ry = RandomFloatPCG32(seed);
-    const float phi = 2.0f * PT_PI_F * ry;
-    const float dd = PTK_SQRT(rx);
-    const float diskx = pr.halfAperture * (dd * PTK_COS(phi));
-    const float disky = pr.halfAperture * (dd * PTK_SIN(phi));
-    const V3 pointOnAperture = camPos + mulVM(mk3(diskx, disky, pr.apertureDist), pr.camM);
-    ray.dir = normalize(pointOnAperture - ray.origin);
-
-    const float r5 = RandomFloatPCG32(seed);
-    const float l_h = 360.0f * (1.0f - r5) + 800.0f * r5; /* mix(360, 800, r) */
-    TracePathLens(c, l_h, ray);
-    const V4 l = SampleWavelengths(l_h);
-    const V4 radiance = TracePath(c, l, ray, seed);
-    const V3 w0 = WaveToXYZ(c, l.x), w1 = WaveToXYZ(c, l.y), w2 = WaveToXYZ(c, l.z), w3 = WaveToXYZ(c, l.w);
-    V3 color;
-    color.x = 0.0f + (radiance.x * w0.x + radiance.y * w1.x + radiance.z * w2.x + radiance.w * w3.x) * 330.0f * 0.25f;
-    color.y = 0.0f + (radiance.x * w0.y + radiance.y * w1.y + radiance.z * w2.y + radiance.w * w3.y) * 330.0f * 0.25f;
-    color.z = 0.0f + (radiance.x * w0.z + radiance.y * w1.z + radiance.z * w2.z + radiance.w * w3.z) * 330.0f * 0.25f;
-    if ((color.x != color.x) || (color.y != color.y) || (color.z != color.z)) return mk3(0.0f, 0.0f, 0.0f);
-    return color;
-}
-
 /* Rendering()'s tail + Accumulate() + imageStore, shader.comp:1492-1533 */
 PT_DEV void StoreTexel(const PtDevParams& pr, float4* __restrict__ image, int gx, int gy, V3 outColor) {
     float4* texel = image + ((size_t)gx + (size_t)pr.width * (size_t)gy);
@@ -1016,33 +824,6 @@ PT_DEV void StoreTexel(const PtDevParams& pr, float4* __restrict__ image, int gx
                        PTK_DIV(nm1 * in.z + outColor.z, n));
     }
     *texel = make_float4(outColor.x, outColor.y, outColor.z, 1.0f);
-}
-
-/* ---- driver v1: one thread = one pixel, nested sample / bounce loops (kept for A/B measurements, PT_SCHED=0) ----
- * Grid: 2-D tiles of 16x8 pixels per 128-thread block; each warp owns an 8x4 sub-tile. */
-__device__ __forceinline__ void pt_render_body_v1(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
-                                                  float4* __restrict__ image, float* s_tab) {
-    for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
-    __syncthreads();
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int gy = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
-    if (gx >= pr.width || gy >= pr.height) return;
-
-    Ctx c;
-    c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
-
-    const unsigned xyx = (unsigned)gx;
-    const unsigned xyy = (unsigned)pr.height - (unsigned)gy; /* shader.comp:1510 */
-    const float uvx = PTK_DIV(2.0f * __uint2float_rn(xyx) - pr.resX, pr.resY);
-    const float uvy = PTK_DIV(2.0f * __uint2float_rn(xyy) - pr.resY, pr.resY);
-
-    V3 outColor = mk3(0.0f, 0.0f, 0.0f);
-    const int spf = pr.samplesPerFrame;
-#pragma unroll 1
-    for (int k = 0; k < spf; k++) outColor = outColor + Scene(c, xyx, xyy, uvx, uvy, k);
-    StoreTexel(pr, image, gx, gy, outColor);
 }
 
 /* ---- the path as four phases over explicit per-path state --------------------------------------------------------
@@ -1166,6 +947,21 @@ PT_DEV int PhaseNew(const Ctx& c, PathState& ps, unsigned xyx, unsigned xyy, int
     return PT_ST_NEW;
 }
 
+
+#if PT_HAS_SDF
+/* SphereTracing's prologue (shader.comp:780-801): the bounding boxes the ray meets.  True = there is a march to run. */
+PT_DEV bool MarchBegin(const Ctx& c, V3 origin, V3 dir, MarchState& ms) {
+    const V3 invdir = mk3(PTK_DIV(1.0f, dir.x), PTK_DIV(1.0f, dir.y), PTK_DIV(1.0f, dir.z));
+    float tMin = 1e5f;
+    ms.tMax = 1e5f;
+    if (!SearchSDF(c, origin, invdir, tMin, ms.tMax, ms.set1)) return false;
+    ms.mt = PTK_MAX(tMin, 1e-3f);
+    ms.insT = 0.0f; ms.omega = 1.70f; ms.previousRadius = 0.0f; ms.points = 0; ms.iter = 0;
+    ms.sub = PT_SUB_SIGN;
+    return true;
+}
+#endif
+
 /* ISECT: Intersection / LightSourceVisibilityCheck up to (and with) SphereTracing's prologue */
 PT_DEV int PhaseIsect(const Ctx& c, PathState& ps, MarchState& ms) {
     Ray r;
@@ -1173,21 +969,13 @@ PT_DEV int PhaseIsect(const Ctx& c, PathState& ps, MarchState& ms) {
     r.dir = ps.isShadow ? ps.shDir : ps.ray.dir;
     IntersectionAnalytic(c, r, ps.h, ps.isShadow);
 #if PT_HAS_SDF
-    const V3 invdir = mk3(PTK_DIV(1.0f, r.dir.x), PTK_DIV(1.0f, r.dir.y), PTK_DIV(1.0f, r.dir.z)); /* shader.comp:780-801 */
-    float tMin = 1e5f;
-    ms.tMax = 1e5f;
-    if (SearchSDF(c, r.origin, invdir, tMin, ms.tMax, ms.set1)) {
-        ms.mt = PTK_MAX(tMin, 1e-3f);
-        ms.insT = 0.0f; ms.omega = 1.70f; ms.previousRadius = 0.0f; ms.points = 0; ms.iter = 0;
-        ms.sub = PT_SUB_SIGN;
-        return PT_ST_SDF;
-    }
+    if (MarchBegin(c, r.origin, r.dir, ms)) return PT_ST_SDF;
 #endif
     return PT_ST_SHADE;
 }
 
 #if PT_HAS_SDF
-/* The SDF phase in three pieces, so a driver can decide WHO evaluates the distance function at WHICH point:
+/* The SDF phase in pieces, so a driver can decide WHO evaluates the distance function at WHICH point:
  * SdfMarchPoint (where the march wants its next evaluation), SdfProbePoint (the j-th of the six normal probes around
  * p: +x -x +y -y +z -z, CalculateNumericalSDFNormals shader.comp:721-730) and SdfMarchConsume (SphereTracing's
  * bookkeeping for one evaluated distance, shader.comp:801-858). */
@@ -1257,19 +1045,13 @@ PT_DEV int SdfMarchConsume(const Ctx& c, PathState& ps, MarchState& ms, float d)
     }
     return PT_ST_SDF;
 }
-/* The hit of a converged path ray from its six probe values (shader.comp:853-857) */
-PT_DEV void SdfFinishHit(PathState& ps, const MarchState& ms, float e0, float e1, float e2, float e3, float e4, float e5) {
-    const V3 p = fma3(ps.ray.dir, ms.mt, ps.ray.origin);
-    ps.h.normal = normalize(mk3(e0 - e1, e2 - e3, e4 - e5));
-    ps.h.materialID = ::pt_sdfmaterial_dispatch(p.x, p.y, p.z, ms.set1);
-    ps.h.lightID = -1.0f;
-}
 
-/* SDF, one lane on its own: one SDF() evaluation and the bookkeeping around it.  Returns SDF (more to do) or SHADE. */
+/* SDF: one SDF() evaluation and the bookkeeping around it.  Returns SDF (more to do) or SHADE.
+ * This is the ONE SDF() site of a megakernel: sign probe, march steps and the six normal probes funnel through it. */
 PT_DEV int PhaseSdfEval(const Ctx& c, PathState& ps, MarchState& ms) {
     const V3 pm = SdfMarchPoint(ps, ms);
     const V3 pe = (ms.sub >= PT_SUB_N0) ? SdfProbePoint(pm, ms.sub - PT_SUB_N0) : pm;
-    const float d = SDF(pe, ms.set1); /* the one SDF() site of the kernel */
+    const float d = SDF(pe, ms.set1);
     if (ms.sub < PT_SUB_N0) return SdfMarchConsume(c, ps, ms, d);
     const int j = ms.sub - PT_SUB_N0;
     if ((j & 1) == 0) {
@@ -1288,158 +1070,11 @@ PT_DEV int PhaseSdfEval(const Ctx& c, PathState& ps, MarchState& ms) {
     }
     return PT_ST_SDF;
 }
-
-/* SDF, the whole warp at once (v2 driver): per round every lane evaluates SDF() at most once -- marching lanes at
- * their own next point, and, when some lanes have converged on a path ray, lanes 0..6m-1 at the six normal probes
- * of the first m <= 5 of them (a marching lane drafted as a prober just advances one round later).  A converged
- * ray's normal thus costs one round with six lanes busy instead of six rounds with one, and runs concurrently with
- * the other lanes' marching.  Same evaluations, same arithmetic: bit-exact. */
-PT_DEV int PhaseSdfWarp(const Ctx& c, PathState& ps, MarchState& ms, int st, int rounds) {
-    const unsigned lane = threadIdx.x & 31u;
-#pragma unroll 1
-    for (int rep = 0; rep < rounds; rep++) {
-        const bool inSdf = (st == PT_ST_SDF);
-        const bool needN = inSdf && (ms.sub == PT_SUB_N0);
-        const unsigned needMask = __ballot_sync(0xffffffffu, needN);
-        if (__ballot_sync(0xffffffffu, inSdf) == 0u) break;
-        const int m = min(__popc(needMask), 5);
-        const bool prober = (int)lane < 6 * m;
-        V3 pe = ps.ray.origin;
-        unsigned set = ms.set1;
-        bool doEval = false;
-        if (m > 0) { /* warp-uniform */
-            const V3 ph = fma3(ps.ray.dir, ms.mt, ps.ray.origin); /* meaningful on the converged lanes */
-            const int slot = (int)lane / 6, probe = (int)lane - 6 * slot;
-            const int src = prober ? (int)__fns(needMask, 0u, slot + 1) : 0;
-            const float qx = __shfl_sync(0xffffffffu, ph.x, src), qy = __shfl_sync(0xffffffffu, ph.y, src),
-                        qz = __shfl_sync(0xffffffffu, ph.z, src);
-            const unsigned qs = __shfl_sync(0xffffffffu, ms.set1, src);
-            if (prober) {
-                pe = SdfProbePoint(mk3(qx, qy, qz), probe);
-                set = qs;
-                doEval = true;
-            }
-        }
-        const bool marching = inSdf && (ms.sub < PT_SUB_N0) && !prober;
-        if (marching) {
-            pe = SdfMarchPoint(ps, ms);
-            set = ms.set1;
-            doEval = true;
-        }
-        float d = 0.0f;
-        if (doEval) d = SDF(pe, set); /* the one SDF() site of the kernel */
-        if (marching) st = SdfMarchConsume(c, ps, ms, d);
-        if (m > 0) {
-            const int nr = __popc(needMask & ((1u << lane) - 1u));
-            const bool served = needN && (nr < m);
-            const int b0 = served ? 6 * nr : 0;
-            const float e0 = __shfl_sync(0xffffffffu, d, b0), e1 = __shfl_sync(0xffffffffu, d, b0 + 1),
-                        e2 = __shfl_sync(0xffffffffu, d, b0 + 2), e3 = __shfl_sync(0xffffffffu, d, b0 + 3),
-                        e4 = __shfl_sync(0xffffffffu, d, b0 + 4), e5 = __shfl_sync(0xffffffffu, d, b0 + 5);
-            if (served) {
-                SdfFinishHit(ps, ms, e0, e1, e2, e3, e4, e5);
-                st = PT_ST_SHADE;
-            }
-        }
-    }
-    return st;
-}
 #endif
 
-/* SHADE: TraceRay after Intersection (shader.comp:1352-1390) with SampleLightSource (1298-1343), or the verdict of
- * the pending shadow ray (1218-1222, 1328-1334).  Returns ISECT (another ray to trace) or NEW (path finished). */
-PT_DEV int PhaseShade(const Ctx& c, PathState& ps) {
-    const PtDevScene& sc = *c.sc;
-    bool done = false;
-    int next = PT_ST_ISECT;
-    if (ps.isShadow) {
-        if (ps.h.objectID == ps.shObj) ps.radiance = ps.radiance + ps.shContrib;
-        ps.isShadow = false;
-        if (!ps.pathAlive) done = true;
-    } else if (!(ps.h.t < 1e5f)) { /* miss: black environment */
-        done = true;
-    } else {
-        float emitT, emitL; /* the light Emit() is evaluated for: the one hit, or the one sampled */
-        GetLightMix(c, ps.h.lightID, emitT, emitL);
-        const bool emitterHit = emitL > 0.0f; /* terminates the path, shader.comp:1359-1364 */
-        bool needShadow = false, alive = false;
-        V4 rr = ps.rayradiance;
-        float emitScale = ps.MISBRDFWeight;
-        V3 outOrigin = ps.ray.origin, outDir = ps.ray.dir;
-        if (!emitterHit) {
-            float peak, sigma, invertf;
-            GetMaterialMix(c, ps.h.materialID, peak, sigma, invertf);
-            const V4 brdf = EvaluateBRDF(ps.l, peak, sigma, invertf);
-            const V3 n = ps.h.normal;
-            outOrigin = fma3(ps.ray.dir, ps.h.t, ps.ray.origin);
-            outDir = SampleCosineDirectionHemisphere(n, ps.seed);
-            const float BRDFpdf = PTK_DIV(dot(outDir, n), PT_PI_F);
-            if (sc.numLights > 0.0f) { /* SampleLightSource, shader.comp:1298-1343 */
-                const int randomLight = __float2int_rz(floorf(RandomFloatPCG32(ps.seed) * sc.numLights));
-                const PtDevLightSlot& ls = sc.lightSlots[randomLight < sc.nLightSlots ? randomLight : sc.nLightSlots - 1];
-                const V3 toLight = mk3(ls.px - outOrigin.x, ls.py - outOrigin.y, ls.pz - outOrigin.z);
-                const float invLightDistance = PTK_DIV(1.0f, length(toLight));
-                const V3 lightDir = toLight * invLightDistance;
-                const float sinthetaMax = PTK_MIN(ls.boundingRadius * invLightDistance, 1.0f);
-                const float costhetaMax = PTK_SQRT(1.0f - sinthetaMax * sinthetaMax);
-                const V3 sdir = ToWorld(SampleCosineUnitCone(ps.seed, costhetaMax), lightDir);
-                float lightpdf = sc.invNumLights;
-                lightpdf *= PTK_DIV(dot(sdir, lightDir), PT_PI_F * (1.0f - costhetaMax * costhetaMax));
-                ps.MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + lightpdf * lightpdf);
-                const float costheta = dot(sdir, n);
-                const float deathProbability = 1.25f * PTK_MAX(ps.MISBRDFWeight - 0.2f, 0.0f);
-                if (costheta >= 0.0f) {
-                    if (RandomFloatPCG32(ps.seed) > deathProbability) {
-                        GetLightMix(c, ls.lightID, emitT, emitL);
-                        rr = ps.rayradiance * mulDiv4(brdf, costheta, lightpdf);
-                        emitScale = 1.0f - ps.MISBRDFWeight;
-                        ps.shDir = sdir;
-                        ps.shObj = ls.objectID;
-                        needShadow = true;
-                    } else {
-                        ps.MISBRDFWeight = 1.0f;
-                    }
-                }
-            } else {
-                ps.MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + 0.0f * 0.0f);
-            }
-            const float costheta = dot(outDir, n);
-            ps.rayradiance = ps.rayradiance * mulDiv4(brdf, costheta, BRDFpdf);
-            const V4 t4 = ps.rayradiance;
-            const float mx = PTK_MAX(t4.x, PTK_MAX(t4.y, PTK_MAX(t4.z, t4.w)));
-            const float rayProbability = PTK_MIN(PTK_MAX(mx, 0.0f), 0.99f);
-            alive = !(RandomFloatPCG32(ps.seed) > rayProbability);
-            if (alive) ps.rayradiance = ps.rayradiance * PTK_DIV(1.0f, rayProbability);
-            ps.bounce++;
-            if (ps.bounce >= c.pr->pathLength) alive = false; /* TracePath's loop bound, shader.comp:1400 */
-        }
-        if (emitterHit || needShadow) { /* the one Emit() site: (Emit * rr) * scale in both uses */
-            const V4 e = Emit(ps.l, PTK_MAX(emitT, 0.0f), PTK_MAX(emitL, 0.0f));
-            const V4 contrib = (e * rr) * emitScale;
-            if (emitterHit) ps.radiance = ps.radiance + contrib; else ps.shContrib = contrib;
-        }
-        ps.ray.origin = outOrigin;
-        ps.ray.dir = outDir; /* next path direction; a pending shadow ray travels along shDir */
-        if (emitterHit) {
-            done = true;
-        } else if (needShadow) {
-            ps.isShadow = true;
-            ps.pathAlive = alive;
-        } else if (!alive) {
-            done = true;
-        }
-    }
-    if (done) {
-        ps.pendingFinish = true;
-        next = PT_ST_NEW;
-    }
-    return next;
-}
-
 /* The two outcomes of a traced ray that need no shading work -- the verdict of a shadow ray and a path ray that left
- * the scene -- exactly as PhaseShade handles them (shader.comp:1218-1222,1328-1334 and 1387-1389).  The in-warp
- * drivers apply this right after the intersection / march phases, so the SHADE phase only ever runs real shading.
- * Returns the next phase, or SHADE when the hit needs shading. */
+ * the scene (shader.comp:1218-1222,1328-1334 and 1387-1389).  Returns the next phase, or SHADE when the hit needs
+ * shading. */
 PT_DEV int PhaseTrivial(PathState& ps) {
     if (ps.isShadow) {
         if (ps.h.objectID == ps.shObj) ps.radiance = ps.radiance + ps.shContrib;
@@ -1448,152 +1083,165 @@ PT_DEV int PhaseTrivial(PathState& ps) {
         ps.pendingFinish = true;
         return PT_ST_NEW;
     }
-    if (!(ps.h.t < 1e5f)) {
+    if (!(ps.h.t < 1e5f)) { /* miss: black environment */
         ps.pendingFinish = true;
         return PT_ST_NEW;
     }
     return PT_ST_SHADE;
 }
 
-/* ---- driver v2: in-warp scheduled state machine, all state in registers ------------------------------------------
- * Every lane runs the phases above for its own pixel; per iteration the warp executes ONE phase, chosen by ballot.
- * A lane that finishes a path refills itself with its pixel's next sample index instead of idling, so the
- * expensive phases run with more lanes populated than in v1.  No queues, no HBM traffic. */
+/* SHADE: TraceRay after Intersection (shader.comp:1352-1390) with SampleLightSource (1298-1343) for a path ray that hit
+ * something -- THE statement of the bounce arithmetic, shared by every driver and by the wavefront pipeline.
+ * The light sample's visibility test is not traced here: the sampled direction, the object to look for and the
+ * contribution it would add are left in shDir / shObj / shContrib with isShadow set (LightSourceVisibilityCheck draws no
+ * random numbers and its result only gates that addition, so running it after the roulette below changes nothing).
+ * Returns ISECT (another ray to trace: the shadow ray if isShadow, else the next path ray) or NEW (path finished). */
+PT_DEV int PhaseShadeHit(const Ctx& c, PathState& ps) {
+    const PtDevScene& sc = *c.sc;
+    float emitT, emitL; /* the light Emit() is evaluated for: the one hit, or the one sampled */
+    GetLightMix(c, ps.h.lightID, emitT, emitL);
+    const bool emitterHit = emitL > 0.0f; /* terminates the path, shader.comp:1359-1364 */
+    bool needShadow = false, alive = false;
+    V4 rr = ps.rayradiance;
+    float emitScale = ps.MISBRDFWeight;
+    V3 outOrigin = ps.ray.origin, outDir = ps.ray.dir;
+    if (!emitterHit) {
+        float peak, sigma, invertf;
+        GetMaterialMix(c, ps.h.materialID, peak, sigma, invertf);
+        const V4 brdf = EvaluateBRDF(ps.l, peak, sigma, invertf);
+        const V3 n = ps.h.normal;
+        outOrigin = fma3(ps.ray.dir, ps.h.t, ps.ray.origin);
+        outDir = SampleCosineDirectionHemisphere(n, ps.seed);
+        const float BRDFpdf = PTK_DIV(dot(outDir, n), PT_PI_F);
+        if (sc.numLights > 0.0f) { /* SampleLightSource, shader.comp:1298-1343 */
+            const int randomLight = __float2int_rz(floorf(RandomFloatPCG32(ps.seed) * sc.numLights));
+            const PtDevLightSlot& ls = sc.lightSlots[randomLight < sc.nLightSlots ? randomLight : sc.nLightSlots - 1];
+            const V3 toLight = mk3(ls.px - outOrigin.x, ls.py - outOrigin.y, ls.pz - outOrigin.z);
+            const float invLightDistance = PTK_DIV(1.0f, length(toLight));
+            const V3 lightDir = toLight * invLightDistance;
+            const float sinthetaMax = PTK_MIN(ls.boundingRadius * invLightDistance, 1.0f);
+            const float costhetaMax = PTK_SQRT(1.0f - sinthetaMax * sinthetaMax);
+            const V3 sdir = ToWorld(SampleCosineUnitCone(ps.seed, costhetaMax), lightDir);
+            float lightpdf = sc.invNumLights;
+            lightpdf *= PTK_DIV(dot(sdir, lightDir), PT_PI_F * (1.0f - costhetaMax * costhetaMax));
+            ps.MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + lightpdf * lightpdf);
+            const float costheta = dot(sdir, n);
+            const float deathProbability = 1.25f * PTK_MAX(ps.MISBRDFWeight - 0.2f, 0.0f);
+            if (costheta >= 0.0f) {
+                if (RandomFloatPCG32(ps.seed) > deathProbability) {
+                    GetLightMix(c, ls.lightID, emitT, emitL);
+                    rr = ps.rayradiance * mulDiv4(brdf, costheta, lightpdf);
+                    emitScale = 1.0f - ps.MISBRDFWeight;
+                    ps.shDir = sdir;
+                    ps.shObj = ls.objectID;
+                    needShadow = true;
+                } else {
+                    ps.MISBRDFWeight = 1.0f;
+                }
+            }
+        } else {
+            ps.MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + 0.0f * 0.0f);
+        }
+        const float costheta = dot(outDir, n);
+        ps.rayradiance = ps.rayradiance * mulDiv4(brdf, costheta, BRDFpdf);
+        const V4 t4 = ps.rayradiance;
+        const float mx = PTK_MAX(t4.x, PTK_MAX(t4.y, PTK_MAX(t4.z, t4.w)));
+        const float rayProbability = PTK_MIN(PTK_MAX(mx, 0.0f), 0.99f);
+        alive = !(RandomFloatPCG32(ps.seed) > rayProbability);
+        if (alive) ps.rayradiance = ps.rayradiance * PTK_DIV(1.0f, rayProbability);
+        ps.bounce++;
+        if (ps.bounce >= c.pr->pathLength) alive = false; /* TracePath's loop bound, shader.comp:1400 */
+    }
+    if (emitterHit || needShadow) { /* the one Emit() site: (Emit * rr) * scale in both uses */
+        const V4 e = Emit(ps.l, PTK_MAX(emitT, 0.0f), PTK_MAX(emitL, 0.0f));
+        const V4 contrib = (e * rr) * emitScale;
+        if (emitterHit) ps.radiance = ps.radiance + contrib; else ps.shContrib = contrib;
+    }
+    ps.ray.origin = outOrigin;
+    ps.ray.dir = outDir; /* next path direction; a pending shadow ray travels along shDir */
+    if (needShadow) {
+        ps.isShadow = true;
+        ps.pathAlive = alive;
+        return PT_ST_ISECT;
+    }
+    if (emitterHit || !alive) {
+        ps.pendingFinish = true;
+        return PT_ST_NEW;
+    }
+    return PT_ST_ISECT;
+}
+/* SHADE for callers that have not applied PhaseTrivial themselves (the wavefront pipeline's SHADE kernel) */
+PT_DEV int PhaseShade(const Ctx& c, PathState& ps) {
+    const int t = PhaseTrivial(ps);
+    return (t == PT_ST_SHADE) ? PhaseShadeHit(c, ps) : t;
+}
+
+/* ---- the phases run back to back by one lane: the loop bodies of the v1 and v3s drivers -----------------------------
+ * shader.comp:862-934 / 1121-1216: Intersection / LightSourceVisibilityCheck in one piece (kShadow is a compile-time
+ * constant at both call sites, so the shadow flavour drops normals, materials, probes). */
+#if PT_HAS_SDF
+PT_DEV_NOINLINE void SphereTracing(const Ctx& c, const Ray& ray, Hit& h, const bool kShadow) {
+    PathState js;
+    js.ray = ray; js.shDir = ray.dir; js.isShadow = kShadow; js.h = h;
+    MarchState ms;
+    if (!MarchBegin(c, ray.origin, ray.dir, ms)) return;
+    int st = PT_ST_SDF;
+#pragma unroll 1
+    while (st == PT_ST_SDF) st = PhaseSdfEval(c, js, ms);
+    h = js.h;
+}
+#endif
+PT_DEV void Intersection(const Ctx& c, const Ray& ray, Hit& h, const bool kShadow) {
+    IntersectionAnalytic(c, ray, h, kShadow);
+#if PT_HAS_SDF
+    SphereTracing(c, ray, h, kShadow);
+#endif
+}
+/* One iteration of TracePath's loop (shader.comp:1393-1407) on the path held in `ps`: TraceRay (1345-1391) = closest hit,
+ * PhaseShadeHit, and the light sample's visibility test when one is pending.  Returns whether the path goes on. */
+PT_DEV bool TraceRayFlat(const Ctx& c, PathState& ps) {
+    Intersection(c, ps.ray, ps.h, false);
+    int next = PhaseTrivial(ps);
+    if (next == PT_ST_SHADE) next = PhaseShadeHit(c, ps);
+    if (ps.isShadow) {
+        Ray sr;
+        sr.origin = ps.ray.origin;
+        sr.dir = ps.shDir;
+        Intersection(c, sr, ps.h, true);
+        next = PhaseTrivial(ps);
+    }
+    return next == PT_ST_ISECT;
+}
+
+/* ---- scheduling statistics and knobs of the in-warp drivers ---------------------------------------------------------- */
 #ifdef PT_STATS
-/* scheduling statistics (debug builds only, env PT_STATS=1): per phase, [2p] = executions, [2p+1] = lanes served */
+/* debug builds only (option "stats"): per phase, [2p] = executions, [2p+1] = lanes served; [8..15] = SDF executions by
+ * participants (1-4, 5-8, ... 29-32) */
 } /* namespace */
 extern "C" __device__ unsigned long long pt_stats[16];
 namespace PT_KERNEL_NS {
 #define PT_STAT(p, mask) do { if ((threadIdx.x & 31) == 0) { atomicAdd(&pt_stats[2 * (p)], 1ull); atomicAdd(&pt_stats[2 * (p) + 1], (unsigned long long)__popc(mask)); } } while (0)
+#define PT_STAT_SDF(n) do { if ((threadIdx.x & 31) == 0 && (n) > 0) atomicAdd(&pt_stats[8 + (((n) - 1) >> 2)], 1ull); } while (0)
 #else
 #define PT_STAT(p, mask) do { } while (0)
+#define PT_STAT_SDF(n) do { } while (0)
 #endif
 #ifndef PT_SDF_REPS
-#define PT_SDF_REPS 16
+#define PT_SDF_REPS 16 /* SDF() evaluations per execution of the SDF phase */
 #endif
 #ifndef PT_FEED_T
-#define PT_FEED_T 8
+#define PT_FEED_T 8    /* the SDF phase runs once every feeder phase (NEW / ISECT / SHADE) has fewer lanes than this */
 #endif
-#ifndef PT_COOP_NORMALS
-#define PT_COOP_NORMALS 0 /* measured slower than one lane per ray on every SDF workload: profiles/r01_coop */
+#ifndef PT_REGEN_T
+#define PT_REGEN_T 16  /* v3s: lanes that must wait for a new sample before the warp regenerates */
 #endif
-#ifndef PT_SDF_MIN
-#define PT_SDF_MIN 0  /* lanes that must be waiting in the SDF phase before it runs while a feeder still has work */
-#endif
-#ifndef PT_SDF_EXIT
-#define PT_SDF_EXIT 0 /* leave the SDF phase early (checked every 4 evaluations) once fewer lanes than this still march */
-#endif
-
-__device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
-                                                  float4* __restrict__ image, float* s_tab) {
-    for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
-    __syncthreads();
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int gy = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
-    const bool inRange = (gx < pr.width) && (gy < pr.height);
-
-    Ctx c;
-    c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
-
-    const unsigned xyx = (unsigned)gx;
-    const unsigned xyy = (unsigned)pr.height - (unsigned)gy; /* shader.comp:1510 */
-    const int spf = pr.samplesPerFrame;
-
-    int st = (inRange && spf > 0) ? PT_ST_NEW : PT_ST_DONE;
-    int k = 0;
-    V3 outColor = mk3(0.0f, 0.0f, 0.0f);
-    PathState ps;
-    PathStateInit(ps);
-    MarchState ms;
-    MarchStateInit(ms);
-
-    for (;;) {
-        const unsigned bNew = __ballot_sync(0xffffffffu, st == PT_ST_NEW);
-        const unsigned bIs = __ballot_sync(0xffffffffu, st == PT_ST_ISECT);
-        const unsigned bSh = __ballot_sync(0xffffffffu, st == PT_ST_SHADE);
-#if PT_HAS_SDF
-        const unsigned bSdf = __ballot_sync(0xffffffffu, st == PT_ST_SDF);
-#else
-        const unsigned bSdf = 0u;
-#endif
-        if ((bNew | bIs | bSdf | bSh) == 0u) break;
-        /* Phase selection.  Executing a phase costs the same whatever its population.  The fullest of the three
-         * "feeder" phases wins (ties go to the later pipeline stage); lanes waiting in the SDF phase take their
-         * PT_SDF_REPS evaluations when every feeder has fewer than PT_FEED_T lanes waiting.  Without SDFs this
-         * is "the phase most lanes are waiting for". */
-        int phase = PT_ST_NEW, best = __popc(bNew);
-        if (__popc(bIs) >= best) { best = __popc(bIs); phase = PT_ST_ISECT; }
-        if (__popc(bSh) >= best) { best = __popc(bSh); phase = PT_ST_SHADE; }
-#if PT_HAS_SDF
-        /* an SDF execution costs an order of magnitude more than a feeder phase whatever its population: with
-         * PT_SDF_MIN > 0 a thin feeder runs first (it may send more lanes marching) unless enough lanes already wait */
-        if (bSdf != 0u && (best == 0 || (best < PT_FEED_T && __popc(bSdf) >= PT_SDF_MIN))) phase = PT_ST_SDF;
-#endif
-        PT_STAT(phase, phase == PT_ST_NEW ? bNew : (phase == PT_ST_ISECT ? bIs : (phase == PT_ST_SDF ? bSdf : bSh)));
-#ifdef PT_STATS
-        if (phase == PT_ST_SDF && (threadIdx.x & 31) == 0) atomicAdd(&pt_stats[8 + ((__popc(bSdf) - 1) >> 2)], 1ull); /* population histogram, buckets of 4 */
-#endif
-        if (phase == PT_ST_NEW) {
-            if (st == PT_ST_NEW) {
-                if (ps.pendingFinish) {
-                    outColor = outColor + PathColor(c, ps);
-                    ps.pendingFinish = false;
-                }
-                if (k < spf) {
-                    st = PhaseNew(c, ps, xyx, xyy, k);
-                    k++;
-                } else {
-                    st = PT_ST_DONE;
-                }
-            }
-        } else if (phase == PT_ST_ISECT) {
-            if (st == PT_ST_ISECT) {
-                st = PhaseIsect(c, ps, ms);
-                if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
-            }
-        }
-#if PT_HAS_SDF
-        else if (phase == PT_ST_SDF) {
-#if PT_COOP_NORMALS
-            st = PhaseSdfWarp(c, ps, ms, st, PT_SDF_REPS);
-#else
-#pragma unroll 1
-            for (int rep = 0; rep < PT_SDF_REPS; rep++) {
-                if (st == PT_ST_SDF) st = PhaseSdfEval(c, ps, ms);
-#if PT_SDF_EXIT > 0
-                if ((rep & 3) == 3 && __popc(__ballot_sync(0xffffffffu, st == PT_ST_SDF)) < PT_SDF_EXIT) break;
-#endif
-            }
-#endif
-            if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
-        }
-#endif
-        else {
-            if (st == PT_ST_SHADE) st = PhaseShade(c, ps);
-        }
-    }
-    if (inRange) StoreTexel(pr, image, gx, gy, outColor);
-}
-
-
-/* ---- driver v2s (PT_SCHED=5): v2 with in-warp sample stealing ----------------------------------------------------
- * In v2 a lane owns one pixel and runs that pixel's samples one after the other, so a warp lives as long as its most
- * expensive pixel: on the SDF scenes a few lanes of a tile march the fractal through all their samples while the
- * others finished long ago (oracle cost maps, profiles/r01_steal: the mean lane carries 0.35 (menger) / 0.64
- * (mandelbulb) / 0.72 (terrain) of the work of the busiest lane of its warp at 16 samples per pixel).
- * Here the warp owns the 32 x S samples of its 8x4 tile as a pool of work items (item = 32 * sample + pixel, so the
- * first 32 items are v2's initial state and primary rays start coherent); a lane that finishes a path claims the
- * next unclaimed item, whichever pixel it belongs to (claims happen in the NEW phase, which the warp executes
- * converged: rank by ballot, no atomics).  A finished sample's XYZ goes to a per-warp table in shared memory
- * (S x 32 x 3 floats); when the pool is empty and all lanes idle, lane p adds pixel p's S entries IN SAMPLE ORDER --
- * the same additions in the same order as v1 / v2, so strict mode stays bit-exact -- and the next round of S
- * samples starts.  Scene() depends only on (pixel, sample index), never on the lane that runs it. */
 #ifndef PT_STEAL_S
 #define PT_STEAL_S 16
 #endif
-/* PT_STEAL_S == 0 (fast mode only): ONE round with all samplesPerFrame samples of the dispatch in the pool, and a
+/* PT_STEAL_S > 0: the warp's pool holds S samples per pixel at a time and a finished sample's XYZ goes to a per-warp
+ * table in shared memory (S x 32 x 3 floats); when the pool is empty lane p adds pixel p's S entries IN SAMPLE ORDER --
+ * the additions of the reference's loop in its order, so strict mode stays bit-exact -- and the next round starts.
+ * PT_STEAL_S == 0 (fast mode only): ONE round with all samplesPerFrame samples of the dispatch in the pool, and a
  * finished sample is added straight to its pixel's running sum in shared memory (red.shared.add.f32) -- no table,
  * hence no bound on the pool, at the price of a summation order that follows the schedule instead of the sample
  * index (the schedule of a warp is a pure function of its inputs, so renders still repeat bit for bit in practice). */
@@ -1605,41 +1253,157 @@ __device__ __forceinline__ void pt_render_body_v2(const PtDevScene& sc, const Pt
 static_assert(PT_STEAL_S >= 0 && PT_STEAL_S <= 20, "PT_STEAL_S: the per-sample table must fit the 48 KB of static shared memory next to the uniform block");
 enum { PT_ST_IDLE = 5 };
 
-/* PT_MPARK (v2s, SDF scenes): rays that march do not wait in a lane.  The march lengths are heavy-tailed (1 .. 512
- * evaluations), so whatever batch of lanes enters the SDF phase together, its later executions serve the few long
- * rays only (61-73 % of v2's SDF executions find 1-4 lanes, profiles/r01_sdfsched).  With PT_MPARK a lane whose ray
- * must march -- after ISECT found a bounding box, and again after every SDF execution that did not finish it -- writes
- * the whole path (49 words: PathState, MarchState, the item it belongs to) to a per-warp stack in shared memory and is
- * free for other work; in the NEW phase free lanes take parked paths back, a batch at a time: as soon as
- * PT_MPARK_MIN paths wait and as many lanes are free (or the pool is empty).  Every SDF execution thus starts with a
- * batch, and the feeder phases carry no lanes that only wait for it.  A path is the same arithmetic whichever lane
- * holds it (strict mode stays bit-exact); with a full stack the ray simply stays in its lane as before. */
-#ifndef PT_MPARK
-#define PT_MPARK 0
-#endif
-#ifndef PT_MPARK_CAP
-#define PT_MPARK_CAP 20
-#endif
-#ifndef PT_MPARK_MIN
-#define PT_MPARK_MIN 12
-#endif
-#define PT_MPARK_FIELDS 49
-#if PT_MPARK && PT_HAS_SDF
-#define PT_MPARK_WORDS (PT_MPARK_FIELDS * PT_MPARK_CAP) /* per warp, [field][position]: a batch of lanes hits distinct banks */
-#define PT_MPARK_XFER(X)                                                                                       \
-    X(0, ps.ray.origin.x) X(1, ps.ray.origin.y) X(2, ps.ray.origin.z) X(3, ps.ray.dir.x) X(4, ps.ray.dir.y)    \
-    X(5, ps.ray.dir.z) X(6, ps.l.x) X(7, ps.l.y) X(8, ps.l.z) X(9, ps.l.w) X(10, ps.radiance.x)                \
-    X(11, ps.radiance.y) X(12, ps.radiance.z) X(13, ps.radiance.w) X(14, ps.rayradiance.x)                    \
-    X(15, ps.rayradiance.y) X(16, ps.rayradiance.z) X(17, ps.rayradiance.w) X(18, ps.MISBRDFWeight)           \
-    X(19, ps.shDir.x) X(20, ps.shDir.y) X(21, ps.shDir.z) X(22, ps.shContrib.x) X(23, ps.shContrib.y)          \
-    X(24, ps.shContrib.z) X(25, ps.shContrib.w) X(26, ps.h.t) X(27, ps.h.normal.x) X(28, ps.h.normal.y)        \
-    X(29, ps.h.normal.z) X(30, ps.h.materialID) X(31, ps.h.lightID) X(32, ms.mt) X(33, ms.tMax)               \
-    X(40, ms.insT) X(41, ms.omega) X(42, ms.previousRadius) X(43, ms.ksign) X(44, ms.probe) X(45, ms.nrm0)     \
-    X(46, ms.nrm1) X(47, ms.nrm2)
+/* the tile's sample pool, shared by v3s / v2s / v2m: deposit a finished sample, close a round */
+PT_DEV void PoolDeposit(float* s_col, int item, V3 col) {
+#if PT_STEAL_S == 0
+    float* e = s_col + (item & 31);
+    atomicAdd(e, col.x); atomicAdd(e + 32, col.y); atomicAdd(e + 64, col.z);
 #else
-#define PT_MPARK_WORDS 0
+    float* e = s_col + (3 * (item >> 5)) * 32 + (item & 31);
+    e[0] = col.x; e[32] = col.y; e[64] = col.z;
 #endif
+}
+/* end of a round (every item finished): lane p takes pixel p's sum.  Returns false when the dispatch is complete. */
+PT_DEV bool PoolCloseRound(float* s_col, int lane, bool inRange, int spf, int& roundBase, int& roundN, V3& outColor) {
+    __syncwarp();
+#if PT_STEAL_S == 0
+    (void)inRange; (void)spf; (void)roundBase; (void)roundN;
+    outColor = mk3(s_col[lane], s_col[32 + lane], s_col[64 + lane]);
+    return false;
+#else
+    if (inRange) {
+#pragma unroll 1
+        for (int kk = 0; kk < roundN; kk++) {
+            const float* e = s_col + (3 * kk) * 32 + lane;
+            outColor = outColor + mk3(e[0], e[32], e[64]);
+        }
+    }
+    __syncwarp();
+    roundBase += roundN;
+    if (roundBase >= spf) return false;
+    roundN = (spf - roundBase) < PT_STEAL_S ? (spf - roundBase) : PT_STEAL_S;
+    return true;
+#endif
+}
 
+/* ---- driver v1 (PT_SCHED 0): one thread = one pixel, nested sample / bounce loops -----------------------------------
+ * Grid: 2-D tiles of 16x8 pixels per 128-thread block; each warp owns an 8x4 sub-tile. */
+__device__ __forceinline__ void pt_render_body_v1(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
+                                                  float4* __restrict__ image, float* s_tab) {
+    for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int gy = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    if (gx >= pr.width || gy >= pr.height) return;
+
+    Ctx c;
+    c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
+
+    const unsigned xyx = (unsigned)gx;
+    const unsigned xyy = (unsigned)pr.height - (unsigned)gy; /* shader.comp:1510 */
+
+    V3 outColor = mk3(0.0f, 0.0f, 0.0f);
+    const int spf = pr.samplesPerFrame;
+    PathState ps;
+    PathStateInit(ps);
+#pragma unroll 1
+    for (int k = 0; k < spf; k++) { /* Scene(), shader.comp:1446-1490 */
+        if (PhaseNew(c, ps, xyx, xyy, k) == PT_ST_ISECT) {
+#pragma unroll 1
+            while (TraceRayFlat(c, ps)) { }
+        }
+        ps.pendingFinish = false;
+        outColor = outColor + PathColor(c, ps);
+    }
+    StoreTexel(pr, image, gx, gy, outColor);
+}
+
+/* ---- driver v3s (PT_SCHED 7): v1's loop bodies in ONE flat loop, with the tile's sample pool ------------------------
+ * What v1 loses on the analytic scenes is a path's tail: on scene1 nine lanes in ten are done after two rays, yet the
+ * warp runs the later bounces for the one to four lanes still alive (ncu on v1: 17 of 32 lanes per instruction).  Here
+ * the sample loop and the bounce loop are one loop: an iteration is one bounce (TraceRayFlat) for every lane with a
+ * live path, and as soon as PT_REGEN_T lanes wait (or nobody is alive) the waiting lanes deposit their finished sample
+ * and claim the next items of the tile's 32 x S pool by ballot rank, whichever pixel they belong to, so the
+ * stragglers' late bounces ride along with the next samples' first ones.  Scene() depends only on (pixel, sample
+ * index), never on the lane that runs it: bit-exact in strict mode (per-sample table, summed in sample order). */
+__device__ __forceinline__ void pt_render_body_v3s(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
+                                                   float4* __restrict__ image, float* s_tab, float* s_colAll) {
+    for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tileX = blockIdx.x * 16 + (warp & 1) * 8, tileY = blockIdx.y * 8 + (warp >> 1) * 4;
+    const int gx = tileX + (lane & 7), gy = tileY + (lane >> 3);
+    const bool inRange = (gx < pr.width) && (gy < pr.height);
+    float* s_col = s_colAll + warp * PT_STEAL_WORDS;
+
+    Ctx c;
+    c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
+
+    const int spf = pr.samplesPerFrame;
+    const bool warpLive = (tileX < pr.width) && (tileY < pr.height) && (spf > 0); /* warp-uniform */
+    int roundBase = 0;
+#if PT_STEAL_S == 0
+    int roundN = warpLive ? spf : 0;
+    s_col[lane] = 0.0f; s_col[32 + lane] = 0.0f; s_col[64 + lane] = 0.0f;
+    __syncwarp();
+#else
+    int roundN = warpLive ? (spf < PT_STEAL_S ? spf : PT_STEAL_S) : 0;
+#endif
+    int next = 0, item = 0;
+
+    V3 outColor = mk3(0.0f, 0.0f, 0.0f);
+    PathState ps;
+    PathStateInit(ps);
+    bool alive = false;
+
+    for (;;) {
+        const bool wantNew = !alive && ((next < 32 * roundN) || ps.pendingFinish);
+        const unsigned bNew = __ballot_sync(0xffffffffu, wantNew);
+        const unsigned bAlive = __ballot_sync(0xffffffffu, alive);
+        if ((bNew | bAlive) == 0u) {
+            if (!warpLive) break;
+            if (!PoolCloseRound(s_col, lane, inRange, spf, roundBase, roundN, outColor)) break;
+            next = 0;
+            continue;
+        }
+        if ((__popc(bNew) >= PT_REGEN_T) || (bAlive == 0u)) { /* warp-uniform */
+            if (wantNew) {
+                if (ps.pendingFinish) { /* Scene()'s tail for the path that ended, shader.comp:1477-1489 */
+                    PoolDeposit(s_col, item, PathColor(c, ps));
+                    ps.pendingFinish = false;
+                }
+                item = next + __popc(bNew & ((1u << lane) - 1u));
+                if (item < 32 * roundN) {
+                    const int q = item & 31;
+                    const int qx = tileX + (q & 7), qy = tileY + (q >> 3);
+                    if ((qx < pr.width) && (qy < pr.height)) { /* else: a pixel beyond the image edge; claim again */
+                        const int nextState = PhaseNew(c, ps, (unsigned)qx, (unsigned)pr.height - (unsigned)qy, roundBase + (item >> 5));
+                        alive = (nextState == PT_ST_ISECT); /* pathLength <= 0: PhaseNew left pendingFinish set */
+                    }
+                }
+            }
+            next += __popc(bNew);
+        }
+        if (alive) { /* one iteration of TracePath's loop, shader.comp:1393-1407 */
+            if (!TraceRayFlat(c, ps)) alive = false; /* the phases left pendingFinish set */
+        }
+    }
+    if (inRange) StoreTexel(pr, image, gx, gy, outColor);
+}
+
+/* ---- driver v2s (PT_SCHED 5): one phase per warp iteration, with the tile's sample pool ------------------------------
+ * Every lane is a state machine over the four phases; per iteration the warp executes ONE phase chosen by ballot (the
+ * fullest feeder first; the SDF phase, PT_SDF_REPS evaluations at a time, once every feeder has fewer than PT_FEED_T
+ * lanes), so path and shadow rays share one intersection site and sign probe, march steps and normal probes one SDF()
+ * site.  The warp owns the 32 x S samples of its 8x4 tile as a pool of work items (item = 32 * sample + pixel, so the
+ * first 32 items are one sample of every pixel and primary rays start coherent); a lane that finishes a path claims the
+ * next unclaimed item, whichever pixel it belongs to (claims happen in the NEW phase, which the warp executes
+ * converged: rank by ballot, no atomics).  With a lane tied to its pixel's sample sequence a warp lives as long as its
+ * most expensive pixel (the mean lane carries 0.35 / 0.64 / 0.72 of the busiest lane's work on menger / mandelbulb /
+ * terrain, profiles/r01_steal); the pool balances that. */
 __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
                                                    float4* __restrict__ image, float* s_tab, float* s_colAll) {
     for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
@@ -1649,11 +1413,7 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
     const int tileX = blockIdx.x * 16 + (warp & 1) * 8, tileY = blockIdx.y * 8 + (warp >> 1) * 4;
     const int gx = tileX + (lane & 7), gy = tileY + (lane >> 3);
     const bool inRange = (gx < pr.width) && (gy < pr.height);
-    float* s_col = s_colAll + warp * (PT_STEAL_WORDS + PT_MPARK_WORDS);
-#if PT_MPARK && PT_HAS_SDF
-    float* s_park = s_col + PT_STEAL_WORDS;
-    int parked = 0;                                      /* paths on the warp's stack (warp-uniform) */
-#endif
+    float* s_col = s_colAll + warp * PT_STEAL_WORDS;
 
     Ctx c;
     c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
@@ -1689,79 +1449,25 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
 #endif
         if ((bNew | bIs | bSdf | bSh) == 0u) {
             if (!warpLive) break;
-            /* end of a round: every item is done.  Lane p sums pixel p's samples in index order. */
-            __syncwarp();
-#if PT_STEAL_S == 0
-            outColor = mk3(s_col[lane], s_col[32 + lane], s_col[64 + lane]);
-            break;
-#else
-            if (inRange) {
-#pragma unroll 1
-                for (int kk = 0; kk < roundN; kk++) {
-                    const float* e = s_col + (3 * kk) * 32 + lane;
-                    outColor = outColor + mk3(e[0], e[32], e[64]);
-                }
-            }
-            __syncwarp();
-            roundBase += roundN;
-            if (roundBase >= spf) break;
-            roundN = (spf - roundBase) < PT_STEAL_S ? (spf - roundBase) : PT_STEAL_S;
+            if (!PoolCloseRound(s_col, lane, inRange, spf, roundBase, roundN, outColor)) break;
             next = 0;
             st = PT_ST_NEW;
             continue;
-#endif
         }
         int phase = PT_ST_NEW, best = __popc(bNew);
         if (__popc(bIs) >= best) { best = __popc(bIs); phase = PT_ST_ISECT; }
         if (__popc(bSh) >= best) { best = __popc(bSh); phase = PT_ST_SHADE; }
 #if PT_HAS_SDF
-        if (bSdf != 0u && (best == 0 || (best < PT_FEED_T && __popc(bSdf) >= PT_SDF_MIN))) phase = PT_ST_SDF;
+        if (bSdf != 0u && best < PT_FEED_T) phase = PT_ST_SDF;
 #endif
         PT_STAT(phase, phase == PT_ST_NEW ? bNew : (phase == PT_ST_ISECT ? bIs : (phase == PT_ST_SDF ? bSdf : bSh)));
-        bool entered = false; /* this lane's ray found an SDF bounding box in this iteration's ISECT phase */
         if (phase == PT_ST_NEW) {
             if (st == PT_ST_NEW) {
                 if (ps.pendingFinish) { /* the sample this lane just finished: item -> (pixel, sample of the round) */
-                    const V3 col = PathColor(c, ps);
-#if PT_STEAL_S == 0
-                    float* e = s_col + (item & 31);
-                    atomicAdd(e, col.x); atomicAdd(e + 32, col.y); atomicAdd(e + 64, col.z);
-#else
-                    float* e = s_col + (3 * (item >> 5)) * 32 + (item & 31);
-                    e[0] = col.x; e[32] = col.y; e[64] = col.z;
-#endif
+                    PoolDeposit(s_col, item, PathColor(c, ps));
                     ps.pendingFinish = false;
                 }
-            }
-            int rank = __popc(bNew & ((1u << lane) - 1u)), nfree = __popc(bNew);
-#if PT_MPARK && PT_HAS_SDF
-            /* free lanes take parked paths back, the whole batch at once */
-            const int npop = parked < nfree ? parked : nfree; /* a batch needs parked paths AND free lanes */
-            if (npop > 0 && (npop >= PT_MPARK_MIN || next >= 32 * roundN)) {
-                if (st == PT_ST_NEW && rank < npop) {
-                    const float* e = s_park + (parked - 1 - rank);
-#define PT_MPARK_LD(i, f) f = e[(i) * PT_MPARK_CAP];
-                    PT_MPARK_XFER(PT_MPARK_LD)
-#undef PT_MPARK_LD
-                    ps.seed = __float_as_uint(e[34 * PT_MPARK_CAP]);
-                    const unsigned pk = __float_as_uint(e[35 * PT_MPARK_CAP]); /* bounce | isShadow << 30 | pathAlive << 31 */
-                    ps.bounce = (int)(pk & 0x3fffffffu); ps.isShadow = ((pk >> 30) & 1u) != 0u; ps.pathAlive = (pk >> 31) != 0u;
-                    ps.shObj = __float_as_int(e[36 * PT_MPARK_CAP]);
-                    ps.h.objectID = __float_as_int(e[37 * PT_MPARK_CAP]);
-                    ms.set1 = __float_as_uint(e[38 * PT_MPARK_CAP]);
-                    item = __float_as_int(e[39 * PT_MPARK_CAP]);
-                    const unsigned mk = __float_as_uint(e[48 * PT_MPARK_CAP]); /* points | iter << 12 | sub << 24 */
-                    ms.points = (int)(mk & 0xfffu); ms.iter = (int)((mk >> 12) & 0xfffu); ms.sub = (int)(mk >> 24);
-                    st = PT_ST_SDF;
-                }
-                parked -= npop;
-                rank -= npop; /* the lanes served above are no longer NEW */
-                nfree -= npop;
-                __syncwarp();
-            }
-#endif
-            if (st == PT_ST_NEW) {
-                item = next + rank;
+                item = next + __popc(bNew & ((1u << lane) - 1u));
                 if (item < 32 * roundN) {
                     const int q = item & 31;
                     const int qx = tileX + (q & 7), qy = tileY + (q >> 3);
@@ -1771,202 +1477,7 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
                     st = PT_ST_IDLE;
                 }
             }
-            next += nfree;
-        } else if (phase == PT_ST_ISECT) {
-            if (st == PT_ST_ISECT) {
-                st = PhaseIsect(c, ps, ms);
-                if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
-                entered = (st == PT_ST_SDF);
-            }
-#if !(PT_MPARK && PT_HAS_SDF)
-            (void)entered;
-#endif
-        }
-#if PT_HAS_SDF
-        else if (phase == PT_ST_SDF) {
-#pragma unroll 1
-            for (int rep = 0; rep < PT_SDF_REPS; rep++) {
-                if (st == PT_ST_SDF) st = PhaseSdfEval(c, ps, ms);
-#if PT_SDF_EXIT > 0
-                if ((rep & 3) == 3 && __popc(__ballot_sync(0xffffffffu, st == PT_ST_SDF)) < PT_SDF_EXIT) break;
-#endif
-            }
-            if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
-        }
-#endif
-        else {
-            if (st == PT_ST_SHADE) st = PhaseShade(c, ps);
-        }
-#if PT_MPARK && PT_HAS_SDF
-        /* the one parking site: rays that entered a bounding box in this ISECT phase, or that this SDF execution did not
-         * finish, go to the stack (as many as fit); their lanes are free again */
-        if (phase == PT_ST_ISECT || phase == PT_ST_SDF) {
-            const bool doPark = (phase == PT_ST_ISECT) ? entered : (st == PT_ST_SDF);
-            const unsigned bEnt = __ballot_sync(0xffffffffu, doPark);
-            if (bEnt != 0u) {
-                const int pos = parked + __popc(bEnt & ((1u << lane) - 1u));
-                if (doPark && pos < PT_MPARK_CAP) {
-                    float* e = s_park + pos;
-#define PT_MPARK_ST(i, f) e[(i) * PT_MPARK_CAP] = f;
-                    PT_MPARK_XFER(PT_MPARK_ST)
-#undef PT_MPARK_ST
-                    e[34 * PT_MPARK_CAP] = __uint_as_float(ps.seed);
-                    e[35 * PT_MPARK_CAP] = __uint_as_float((unsigned)ps.bounce | ((unsigned)ps.isShadow << 30) | ((unsigned)ps.pathAlive << 31));
-                    e[36 * PT_MPARK_CAP] = __int_as_float(ps.shObj);
-                    e[37 * PT_MPARK_CAP] = __int_as_float(ps.h.objectID);
-                    e[38 * PT_MPARK_CAP] = __uint_as_float(ms.set1);
-                    e[39 * PT_MPARK_CAP] = __int_as_float(item);
-                    e[48 * PT_MPARK_CAP] = __uint_as_float((unsigned)ms.points | ((unsigned)ms.iter << 12) | ((unsigned)ms.sub << 24));
-                    st = PT_ST_NEW; /* nothing pending: the NEW phase hands this lane a parked path or a new item */
-                }
-                const int room = PT_MPARK_CAP - parked, n = __popc(bEnt);
-                parked += n < room ? n : room;
-                __syncwarp();
-            }
-        }
-#endif
-    }
-    if (inRange) StoreTexel(pr, image, gx, gy, outColor);
-}
-
-
-/* ---- driver v2sp (PT_SCHED=6, fast mode): v2s with persistent warps streaming over tiles ---------------------------
- * v2s still drains its pool at the end of every 8x4 tile: the last paths of a tile run alone (an expensive path on the
- * menger scene is worth a tenth of a whole tile at 64 samples per pixel), and a small samplesPerFrame leaves nothing
- * to steal.  Here a warp does not belong to a tile.  The grid is persistent (SMs x resident CTAs); a warp claims tiles
- * from a global counter and keeps up to PT_TILE_SLOTS of them in flight: when the items of the newest tile are all
- * claimed the lanes that come free open the next tile while the stragglers of the older ones finish.  Per slot the
- * warp keeps, in shared memory, the tile id, the number of finished items and the running XYZ sums of the tile's 32
- * pixels (red.shared.add.f32, schedule order: fast mode only -- strict builds use v2s with its per-sample table).  A
- * tile whose items are all finished is written out (StoreTexel: the reference's Accumulate) by the whole warp and its
- * slot is recycled.  All bookkeeping happens in the NEW phase, which the warp executes converged (ballots, no locks).
- * The tile counter lives in the module (pt_tile_ctr[0]); the last warp to leave resets it (pt_tile_ctr[1] counts
- * leavers), so back-to-back launches on a stream need no host-side reset. */
-#ifndef PT_TILE_SLOTS
-#define PT_TILE_SLOTS 4
-#endif
-#define PT_V2SP_WORDS (PT_TILE_SLOTS * (3 * 32 + 2)) /* per warp: sums, then tile id and finished count per slot */
-
-__device__ __forceinline__ void pt_render_body_v2sp(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
-                                                    float4* __restrict__ image, float* s_tab, float* s_all, unsigned* tileCtr) {
-    for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
-    __syncthreads();
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* s_acc = s_all + warp * PT_V2SP_WORDS;                    /* [slot][channel][pixel] */
-    int* s_tile = reinterpret_cast<int*>(s_acc + PT_TILE_SLOTS * 96); /* [slot]: the tile's pixel origin x0 | y0 << 16, or -1 */
-    int* s_done = s_tile + PT_TILE_SLOTS;                           /* [slot]: finished (or skipped) items */
-    for (int i = lane; i < PT_TILE_SLOTS * 96; i += 32) s_acc[i] = 0.0f;
-    if (lane < PT_TILE_SLOTS) { s_tile[lane] = -1; s_done[lane] = 0; }
-    __syncwarp();
-
-    Ctx c;
-    c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
-
-    const int spf = pr.samplesPerFrame;
-    const int tilesX = (pr.width + 7) >> 3, tilesY = (pr.height + 3) >> 2;
-    const int numTiles = spf > 0 ? tilesX * tilesY : 0;
-    const int total = 32 * spf;      /* items per tile: item = 32 * sample + pixel */
-    int curSlot = -1, next = 0;      /* the slot items are being claimed from (warp-uniform) */
-    bool exhausted = false;          /* the global counter ran past the last tile (warp-uniform) */
-    int item = 0, slot = 0;          /* this lane's current item and the slot of its tile */
-
-    int st = PT_ST_NEW;
-    PathState ps;
-    PathStateInit(ps);
-    MarchState ms;
-    MarchStateInit(ms);
-
-    for (;;) {
-        const unsigned bNew = __ballot_sync(0xffffffffu, st == PT_ST_NEW);
-        const unsigned bIs = __ballot_sync(0xffffffffu, st == PT_ST_ISECT);
-        const unsigned bSh = __ballot_sync(0xffffffffu, st == PT_ST_SHADE);
-#if PT_HAS_SDF
-        const unsigned bSdf = __ballot_sync(0xffffffffu, st == PT_ST_SDF);
-#else
-        const unsigned bSdf = 0u;
-#endif
-        if ((bNew | bIs | bSdf | bSh) == 0u) break; /* every lane idle: no tile left and none in flight */
-        int phase = PT_ST_NEW, best = __popc(bNew);
-        if (__popc(bIs) >= best) { best = __popc(bIs); phase = PT_ST_ISECT; }
-        if (__popc(bSh) >= best) { best = __popc(bSh); phase = PT_ST_SHADE; }
-#if PT_HAS_SDF
-        if (bSdf != 0u && (best == 0 || (best < PT_FEED_T && __popc(bSdf) >= PT_SDF_MIN))) phase = PT_ST_SDF;
-#endif
-        PT_STAT(phase, phase == PT_ST_NEW ? bNew : (phase == PT_ST_ISECT ? bIs : (phase == PT_ST_SDF ? bSdf : bSh)));
-        if (phase == PT_ST_NEW) {
-            /* 1. finished samples -> their pixel's sum; per slot, count them */
-            const bool fin = (st == PT_ST_NEW) && ps.pendingFinish;
-            if (fin) {
-                const V3 col = PathColor(c, ps);
-                float* e = s_acc + slot * 96 + (item & 31);
-                atomicAdd(e, col.x); atomicAdd(e + 32, col.y); atomicAdd(e + 64, col.z);
-                atomicAdd(s_done + slot, 1);
-                ps.pendingFinish = false;
-            }
-            __syncwarp();
-            /* 2. tiles whose items are all finished: write them out, recycle the slot, wake the lanes waiting for one */
-            bool wake = false;
-#pragma unroll 1
-            for (int s = 0; s < PT_TILE_SLOTS; s++) {
-                const int org = s_tile[s];
-                if (org < 0 || s_done[s] != total) continue; /* warp-uniform */
-                const int gx = (org & 0xffff) + (lane & 7), gy = (org >> 16) + (lane >> 3);
-                float* e = s_acc + s * 96 + lane;
-                if (gx < pr.width && gy < pr.height) StoreTexel(pr, image, gx, gy, mk3(e[0], e[32], e[64]));
-                e[0] = 0.0f; e[32] = 0.0f; e[64] = 0.0f;
-                __syncwarp();
-                if (lane == 0) { s_tile[s] = -1; s_done[s] = 0; }
-                __syncwarp();
-                wake = true;
-            }
-            if (wake && st == PT_ST_IDLE) st = PT_ST_NEW;
-            /* 3. claims: rank the lanes that want an item; serve them from the current tile, opening new ones as needed */
-            const bool want = (st == PT_ST_NEW);
-            const unsigned wmask = __ballot_sync(0xffffffffu, want);
-            const int rank = __popc(wmask & ((1u << lane) - 1u));
-            int remaining = __popc(wmask), base = 0;
-            bool got = false;
-#pragma unroll 1
-            while (remaining > 0) {
-                const int avail = curSlot >= 0 ? total - next : 0;
-                const int take = avail < remaining ? avail : remaining;
-                if (want && !got && rank >= base && rank < base + take) {
-                    item = next + (rank - base);
-                    slot = curSlot;
-                    got = true;
-                }
-                next += take; base += take; remaining -= take;
-                if (remaining == 0 || exhausted) break;
-                int freeSlot = -1;
-#pragma unroll 1
-                for (int s = PT_TILE_SLOTS - 1; s >= 0; s--) if (s_tile[s] < 0) freeSlot = s;
-                if (freeSlot < 0) break; /* every slot still has stragglers: the unserved lanes wait */
-                unsigned id = 0u;
-                if (lane == 0) id = atomicAdd(tileCtr, 1u);
-                id = __shfl_sync(0xffffffffu, id, 0);
-                if (id >= (unsigned)numTiles) { exhausted = true; break; }
-                if (lane == 0) { /* the tile's pixel origin, packed: x0 | y0 << 16 */
-                    const int ty = (int)id / tilesX, tx = (int)id - ty * tilesX;
-                    s_tile[freeSlot] = (tx * 8) | ((ty * 4) << 16);
-                    s_done[freeSlot] = 0;
-                }
-                __syncwarp();
-                curSlot = freeSlot;
-                next = 0;
-            }
-            if (want) {
-                if (got) {
-                    const int org = s_tile[slot];
-                    const int q = item & 31;
-                    const int qx = (org & 0xffff) + (q & 7), qy = (org >> 16) + (q >> 3);
-                    if ((qx < pr.width) && (qy < pr.height)) st = PhaseNew(c, ps, (unsigned)qx, (unsigned)pr.height - (unsigned)qy, item >> 5);
-                    else atomicAdd(s_done + slot, 1); /* a pixel beyond the image edge: the item counts as finished, the lane claims again */
-                } else {
-                    st = PT_ST_IDLE;
-                }
-            }
-            __syncwarp();
+            next += __popc(bNew);
         } else if (phase == PT_ST_ISECT) {
             if (st == PT_ST_ISECT) {
                 st = PhaseIsect(c, ps, ms);
@@ -1975,179 +1486,105 @@ __device__ __forceinline__ void pt_render_body_v2sp(const PtDevScene& sc, const 
         }
 #if PT_HAS_SDF
         else if (phase == PT_ST_SDF) {
+            PT_STAT_SDF(__popc(bSdf));
 #pragma unroll 1
             for (int rep = 0; rep < PT_SDF_REPS; rep++) {
                 if (st == PT_ST_SDF) st = PhaseSdfEval(c, ps, ms);
-#if PT_SDF_EXIT > 0
-                if ((rep & 3) == 3 && __popc(__ballot_sync(0xffffffffu, st == PT_ST_SDF)) < PT_SDF_EXIT) break;
-#endif
             }
             if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
         }
 #endif
         else {
-            if (st == PT_ST_SHADE) st = PhaseShade(c, ps);
-        }
-    }
-    /* the last warp of the grid to leave rearms the tile counter for the next launch */
-    if (lane == 0) {
-        __threadfence();
-        const unsigned leavers = atomicAdd(tileCtr + 1, 1u) + 1u;
-        if (leavers == gridDim.x * gridDim.y * (PT_BLOCK_THREADS / 32)) {
-            tileCtr[0] = 0u;
-            tileCtr[1] = 0u;
-            __threadfence();
-        }
-    }
-}
-
-/* One iteration of TracePath's loop (shader.comp:1393-1407): TraceRay (1345-1391) with SampleLightSource (1298-1343)
- * inline, verbatim from TracePath above, on the path held in `ps`.  Returns whether the path goes on.  Shared by the
- * flat-loop drivers v3 and v3s. */
-PT_DEV bool TraceRayFlat(const Ctx& c, PathState& ps, const int pathLength) {
-    const PtDevScene& sc = *c.sc;
-    bool goOn = false;
-    Hit h;
-    Intersection(c, ps.ray, h, false);
-    if (h.t < 1e5f) {
-        float temperature, luminosity;
-        GetLightMix(c, h.lightID, temperature, luminosity);
-        if (luminosity > 0.0f) { /* emitter hit terminates the path */
-            const V4 e = Emit(ps.l, PTK_MAX(temperature, 0.0f), PTK_MAX(luminosity, 0.0f));
-            ps.radiance = ps.radiance + (e * ps.rayradiance) * ps.MISBRDFWeight;
-        } else {
-            float peak, sigma, invertf;
-            GetMaterialMix(c, h.materialID, peak, sigma, invertf);
-            const V4 brdf = EvaluateBRDF(ps.l, peak, sigma, invertf);
-            Ray outRay;
-            outRay.origin = fma3(ps.ray.dir, h.t, ps.ray.origin);
-            outRay.dir = SampleCosineDirectionHemisphere(h.normal, ps.seed);
-            const float BRDFpdf = PTK_DIV(dot(outRay.dir, h.normal), PT_PI_F);
-            if (sc.numLights > 0.0f) { /* SampleLightSource, shader.comp:1298-1343 */
-                const int randomLight = __float2int_rz(floorf(RandomFloatPCG32(ps.seed) * sc.numLights));
-                const PtDevLightSlot& ls = sc.lightSlots[randomLight < sc.nLightSlots ? randomLight : sc.nLightSlots - 1];
-                const V3 toLight = mk3(ls.px - outRay.origin.x, ls.py - outRay.origin.y, ls.pz - outRay.origin.z);
-                const float invLightDistance = PTK_DIV(1.0f, length(toLight));
-                const V3 lightDir = toLight * invLightDistance;
-                const float sinthetaMax = PTK_MIN(ls.boundingRadius * invLightDistance, 1.0f);
-                const float costhetaMax = PTK_SQRT(1.0f - sinthetaMax * sinthetaMax);
-                Ray shadowRay;
-                shadowRay.origin = outRay.origin;
-                shadowRay.dir = ToWorld(SampleCosineUnitCone(ps.seed, costhetaMax), lightDir);
-                float lightpdf = sc.invNumLights;
-                lightpdf *= PTK_DIV(dot(shadowRay.dir, lightDir), PT_PI_F * (1.0f - costhetaMax * costhetaMax));
-                ps.MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + lightpdf * lightpdf);
-                const float costheta = dot(shadowRay.dir, h.normal);
-                const float deathProbability = 1.25f * PTK_MAX(ps.MISBRDFWeight - 0.2f, 0.0f);
-                if (costheta >= 0.0f) {
-                    if (RandomFloatPCG32(ps.seed) > deathProbability) {
-                        Hit sh;
-                        Intersection(c, shadowRay, sh, true);
-                        if (sh.objectID == ls.objectID) {
-                            float lt, ll;
-                            GetLightMix(c, ls.lightID, lt, ll);
-                            const V4 rr = ps.rayradiance * mulDiv4(brdf, costheta, lightpdf);
-                            const V4 e = Emit(ps.l, PTK_MAX(lt, 0.0f), PTK_MAX(ll, 0.0f));
-                            ps.radiance = ps.radiance + (e * rr) * (1.0f - ps.MISBRDFWeight);
-                        }
-                    } else {
-                        ps.MISBRDFWeight = 1.0f;
-                    }
-                }
-            } else {
-                ps.MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + 0.0f * 0.0f);
-            }
-            const float costheta = dot(outRay.dir, h.normal);
-            ps.rayradiance = ps.rayradiance * mulDiv4(brdf, costheta, BRDFpdf);
-            const float mx = PTK_MAX(ps.rayradiance.x, PTK_MAX(ps.rayradiance.y, PTK_MAX(ps.rayradiance.z, ps.rayradiance.w)));
-            const float rayProbability = PTK_MIN(PTK_MAX(mx, 0.0f), 0.99f);
-            if (!(RandomFloatPCG32(ps.seed) > rayProbability)) {
-                ps.rayradiance = ps.rayradiance * PTK_DIV(1.0f, rayProbability);
-                ps.ray = outRay;
-                ps.bounce++;
-                goOn = ps.bounce < pathLength;
-            }
-        }
-    }
-    return goOn;
-}
-
-/* ---- driver v3: v1's loop bodies, flattened, with gated path regeneration ----------------------------------------
- * What v1 loses on the analytic scenes is not the shape of a path but its tail: on scene1 nine lanes in ten are done
- * after two rays, yet the warp runs bounce 2's shading, shadow ray and the third and fourth intersection for the
- * one to four lanes still alive -- about half of all executions of the intersection code are that sparse (ncu: 17
- * of 32 lanes per instruction).  Here the sample loop and the bounce loop are ONE loop: an iteration is one bounce
- * (TraceRay, shader.comp:1345-1391, verbatim from TracePath above) for every lane with a live path, and the lanes
- * whose path has ended start their pixel's next sample (Scene() up to TracePath, 1446-1472) as soon as at least
- * PT_REGEN_T of them are waiting (or nobody is alive), so the stragglers' late bounces ride along with the next
- * sample's first ones.  Per-lane arithmetic and sample order are v1's: bit-exact in strict mode.  Unlike v2 there is
- * no phase vote and no explicit hit/shadow state: only v1's live variables, one extra flag and the sample counter. */
-#ifndef PT_REGEN_T
-#define PT_REGEN_T 16
-#endif
-__device__ __forceinline__ void pt_render_body_v3(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
-                                                  float4* __restrict__ image, float* s_tab) {
-    for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
-    __syncthreads();
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int gy = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
-    const bool inRange = (gx < pr.width) && (gy < pr.height);
-
-    Ctx c;
-    c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
-
-    const unsigned xyx = (unsigned)gx;
-    const unsigned xyy = (unsigned)pr.height - (unsigned)gy; /* shader.comp:1510 */
-    const int spf = inRange ? pr.samplesPerFrame : 0;
-    const int pathLength = pr.pathLength;
-
-    V3 outColor = mk3(0.0f, 0.0f, 0.0f);
-    PathState ps; /* only ray, l, radiance, rayradiance, MISBRDFWeight, seed, bounce and pendingFinish are used */
-    PathStateInit(ps);
-    bool alive = false;
-    int k = 0;
-
-    for (;;) {
-        const bool wantNew = !alive && ((k < spf) || ps.pendingFinish);
-        const unsigned bNew = __ballot_sync(0xffffffffu, wantNew);
-        const unsigned bAlive = __ballot_sync(0xffffffffu, alive);
-        if ((bNew | bAlive) == 0u) break;
-        if ((__popc(bNew) >= PT_REGEN_T) || (bAlive == 0u)) { /* warp-uniform */
-            if (wantNew) {
-                if (ps.pendingFinish) { /* Scene()'s tail for the path that ended, shader.comp:1477-1489 */
-                    outColor = outColor + PathColor(c, ps);
-                    ps.pendingFinish = false;
-                }
-                if (k < spf) {
-                    const int next = PhaseNew(c, ps, xyx, xyy, k);
-                    k++;
-                    alive = (next == PT_ST_ISECT); /* pathLength <= 0: PhaseNew left pendingFinish set */
-                }
-            }
-        }
-        if (alive) { /* one iteration of TracePath's loop, shader.comp:1393-1407 */
-            const bool goOn = TraceRayFlat(c, ps, pathLength);
-            if (!goOn) {
-                alive = false;
-                ps.pendingFinish = true;
-            }
+            if (st == PT_ST_SHADE) st = PhaseShadeHit(c, ps);
         }
     }
     if (inRange) StoreTexel(pr, image, gx, gy, outColor);
 }
 
-/* ---- driver v3s (PT_SCHED=7): v3 with in-warp sample stealing ------------------------------------------------------
- * v3 keeps v1's compact loop bodies (no phase vote, no hit / shadow state) but ties a lane to its pixel's sample
- * sequence; v2s pools the tile's samples but pays for its phase machine on the scenes without SDFs (cfg2: 9.85 against
- * v1's 10.96 Gsamples/s).  This is v3's flat loop with v2s' pool: at a regeneration (PT_REGEN_T lanes waiting, or nobody
- * alive) the waiting lanes deposit their finished sample and claim the next items of the tile's 32 x S pool by ballot
- * rank, whichever pixel they belong to.  Strict mode: per-sample XYZ table, summed per pixel in sample order at the end
- * of a round (bit-exact); fast mode (PT_STEAL_S = 0): the whole dispatch is one pool, sums in shared memory.
- * Verified against the oracle on the host SIMT emulator (tests/test_simt_emulation.py); NOT yet measured on a GPU --
- * a round-2 candidate for the scenes without SDFs. */
-__device__ __forceinline__ void pt_render_body_v3s(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
+#if PT_HAS_SDF
+/* ---- driver v2m (PT_SCHED 8): v2s + a per-warp pool of parked paths ---------------------------------------------------
+ * In v2s a lane whose ray must march waits in the SDF state until the feeders run dry, and the SDF phase then serves
+ * whoever waits: 11-15 of 32 lanes on the fractal scenes, for 35-42 % of all executed instructions.  While a lane is
+ * tied to the path it holds, utilisation is conserved: filling the SDF phase by holding it back empties the feeders by
+ * the same amount (profiles/r01_sdfsched).  The way out is more paths than lanes:
+ *   * a ray that enters an SDF bounding box is PARKED: the lane writes the whole path (PT_POOL_FIELDS words) to a free
+ *     slot of the warp's pool in shared memory and is free again -- it takes the next item or a finished parked path;
+ *   * the SDF phase marches parked rays with ALL 32 lanes, whatever paths those lanes hold in registers (their own
+ *     PathState is not touched): a lane loads the march job of a slot (origin, direction, SphereTracing's locals),
+ *     advances it PT_SDF_REPS evaluations and writes it back, or -- finished -- writes the hit and marks the slot READY;
+ *   * in the NEW phase free lanes pick READY paths up (before new items) and carry them on: PhaseTrivial, then SHADE.
+ * The phase runs when PT_POOL_MIN rays wait, or when the feeders have nothing to do.  With no free slot the ray stays in
+ * its lane and marches from there in the same phase (the pool cannot deadlock).  All bookkeeping is warp-uniform masks
+ * and ballots; no atomics, no fences beyond __syncwarp.  A path is the same arithmetic whichever lane holds it: strict
+ * mode stays bit-exact. */
+#ifndef PT_POOL_CAP
+#define PT_POOL_CAP 32 /* slots per warp (<= 32: one mask word) */
+#endif
+#ifndef PT_POOL_MIN
+#define PT_POOL_MIN 24 /* marching rays (parked + in-lane) from which the SDF phase runs ahead of the feeders */
+#endif
+static_assert(PT_POOL_CAP >= 1 && PT_POOL_CAP <= 32, "PT_POOL_CAP: one 32-bit mask");
+#define PT_POOL_FIELDS 50
+#define PT_POOL_WORDS (PT_POOL_FIELDS * PT_POOL_CAP) /* per warp, [field][slot]: lanes of one access hit distinct banks */
+/* field numbers: the march job first (what the SDF phase reads / writes), then the rest of the path */
+enum { PF_OX = 0, PF_OY, PF_OZ, PF_DX, PF_DY, PF_DZ, PF_SX, PF_SY, PF_SZ, PF_FLAGS, PF_HT, PF_HOBJ, PF_MT, PF_INST, PF_OMEGA,
+       PF_PREV, PF_TMAX, PF_KSIGN, PF_PROBE, PF_N0, PF_N1, PF_N2, PF_MPACK, PF_SET1, PF_HNX, PF_HNY, PF_HNZ, PF_HMAT,
+       PF_HLIGHT, PF_LX, PF_LY, PF_LZ, PF_LW, PF_RX, PF_RY, PF_RZ, PF_RW, PF_TX, PF_TY, PF_TZ, PF_TW, PF_MIS, PF_SEED,
+       PF_CX, PF_CY, PF_CZ, PF_CW, PF_SHOBJ, PF_ITEM, PF_SPARE };
+static_assert(PF_SPARE + 1 == PT_POOL_FIELDS, "pool layout");
+#define PT_PF(f) e[(f) * PT_POOL_CAP]
+
+PT_DEV unsigned PoolPackMarch(const MarchState& ms) { return (unsigned)ms.points | ((unsigned)ms.iter << 12) | ((unsigned)ms.sub << 24); }
+PT_DEV void PoolUnpackMarch(unsigned mk, MarchState& ms) { ms.points = (int)(mk & 0xfffu); ms.iter = (int)((mk >> 12) & 0xfffu); ms.sub = (int)(mk >> 24); }
+PT_DEV void PoolStoreMarch(float* e, const MarchState& ms) {
+    PT_PF(PF_MT) = ms.mt; PT_PF(PF_INST) = ms.insT; PT_PF(PF_OMEGA) = ms.omega; PT_PF(PF_PREV) = ms.previousRadius;
+    PT_PF(PF_TMAX) = ms.tMax; PT_PF(PF_KSIGN) = ms.ksign; PT_PF(PF_PROBE) = ms.probe; PT_PF(PF_N0) = ms.nrm0;
+    PT_PF(PF_N1) = ms.nrm1; PT_PF(PF_N2) = ms.nrm2; PT_PF(PF_MPACK) = __uint_as_float(PoolPackMarch(ms));
+    PT_PF(PF_SET1) = __uint_as_float(ms.set1);
+}
+PT_DEV void PoolLoadMarch(const float* e, MarchState& ms) {
+    ms.mt = PT_PF(PF_MT); ms.insT = PT_PF(PF_INST); ms.omega = PT_PF(PF_OMEGA); ms.previousRadius = PT_PF(PF_PREV);
+    ms.tMax = PT_PF(PF_TMAX); ms.ksign = PT_PF(PF_KSIGN); ms.probe = PT_PF(PF_PROBE); ms.nrm0 = PT_PF(PF_N0);
+    ms.nrm1 = PT_PF(PF_N1); ms.nrm2 = PT_PF(PF_N2); PoolUnpackMarch(__float_as_uint(PT_PF(PF_MPACK)), ms);
+    ms.set1 = __float_as_uint(PT_PF(PF_SET1));
+}
+/* the whole path into a slot (its ray is about to march: ps.h holds the analytic hit, ms SphereTracing's prologue) */
+PT_DEV void PoolPark(float* e, const PathState& ps, const MarchState& ms, int item) {
+    PT_PF(PF_OX) = ps.ray.origin.x; PT_PF(PF_OY) = ps.ray.origin.y; PT_PF(PF_OZ) = ps.ray.origin.z;
+    PT_PF(PF_DX) = ps.ray.dir.x; PT_PF(PF_DY) = ps.ray.dir.y; PT_PF(PF_DZ) = ps.ray.dir.z;
+    PT_PF(PF_SX) = ps.shDir.x; PT_PF(PF_SY) = ps.shDir.y; PT_PF(PF_SZ) = ps.shDir.z;
+    PT_PF(PF_FLAGS) = __uint_as_float((unsigned)ps.bounce | ((unsigned)ps.isShadow << 30) | ((unsigned)ps.pathAlive << 31));
+    PT_PF(PF_HT) = ps.h.t; PT_PF(PF_HOBJ) = __int_as_float(ps.h.objectID);
+    PoolStoreMarch(e, ms);
+    PT_PF(PF_HNX) = ps.h.normal.x; PT_PF(PF_HNY) = ps.h.normal.y; PT_PF(PF_HNZ) = ps.h.normal.z;
+    PT_PF(PF_HMAT) = ps.h.materialID; PT_PF(PF_HLIGHT) = ps.h.lightID;
+    PT_PF(PF_LX) = ps.l.x; PT_PF(PF_LY) = ps.l.y; PT_PF(PF_LZ) = ps.l.z; PT_PF(PF_LW) = ps.l.w;
+    PT_PF(PF_RX) = ps.radiance.x; PT_PF(PF_RY) = ps.radiance.y; PT_PF(PF_RZ) = ps.radiance.z; PT_PF(PF_RW) = ps.radiance.w;
+    PT_PF(PF_TX) = ps.rayradiance.x; PT_PF(PF_TY) = ps.rayradiance.y; PT_PF(PF_TZ) = ps.rayradiance.z; PT_PF(PF_TW) = ps.rayradiance.w;
+    PT_PF(PF_MIS) = ps.MISBRDFWeight; PT_PF(PF_SEED) = __uint_as_float(ps.seed);
+    PT_PF(PF_CX) = ps.shContrib.x; PT_PF(PF_CY) = ps.shContrib.y; PT_PF(PF_CZ) = ps.shContrib.z; PT_PF(PF_CW) = ps.shContrib.w;
+    PT_PF(PF_SHOBJ) = __int_as_float(ps.shObj); PT_PF(PF_ITEM) = __int_as_float(item);
+}
+/* a READY path back into a lane: everything but the march state (the march is over) */
+PT_DEV void PoolPickup(const float* e, PathState& ps, int& item) {
+    ps.ray.origin = mk3(PT_PF(PF_OX), PT_PF(PF_OY), PT_PF(PF_OZ));
+    ps.ray.dir = mk3(PT_PF(PF_DX), PT_PF(PF_DY), PT_PF(PF_DZ));
+    ps.shDir = mk3(PT_PF(PF_SX), PT_PF(PF_SY), PT_PF(PF_SZ));
+    const unsigned pk = __float_as_uint(PT_PF(PF_FLAGS));
+    ps.bounce = (int)(pk & 0x3fffffffu); ps.isShadow = ((pk >> 30) & 1u) != 0u; ps.pathAlive = (pk >> 31) != 0u;
+    ps.pendingFinish = false;
+    ps.h.t = PT_PF(PF_HT); ps.h.objectID = __float_as_int(PT_PF(PF_HOBJ));
+    ps.h.normal = mk3(PT_PF(PF_HNX), PT_PF(PF_HNY), PT_PF(PF_HNZ));
+    ps.h.materialID = PT_PF(PF_HMAT); ps.h.lightID = PT_PF(PF_HLIGHT);
+    ps.l = mk4(PT_PF(PF_LX), PT_PF(PF_LY), PT_PF(PF_LZ), PT_PF(PF_LW));
+    ps.radiance = mk4(PT_PF(PF_RX), PT_PF(PF_RY), PT_PF(PF_RZ), PT_PF(PF_RW));
+    ps.rayradiance = mk4(PT_PF(PF_TX), PT_PF(PF_TY), PT_PF(PF_TZ), PT_PF(PF_TW));
+    ps.MISBRDFWeight = PT_PF(PF_MIS); ps.seed = __float_as_uint(PT_PF(PF_SEED));
+    ps.shContrib = mk4(PT_PF(PF_CX), PT_PF(PF_CY), PT_PF(PF_CZ), PT_PF(PF_CW));
+    ps.shObj = __float_as_int(PT_PF(PF_SHOBJ)); item = __float_as_int(PT_PF(PF_ITEM));
+}
+
+__device__ __forceinline__ void pt_render_body_v2m(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
                                                    float4* __restrict__ image, float* s_tab, float* s_colAll) {
     for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
     __syncthreads();
@@ -2156,464 +1593,188 @@ __device__ __forceinline__ void pt_render_body_v3s(const PtDevScene& sc, const P
     const int tileX = blockIdx.x * 16 + (warp & 1) * 8, tileY = blockIdx.y * 8 + (warp >> 1) * 4;
     const int gx = tileX + (lane & 7), gy = tileY + (lane >> 3);
     const bool inRange = (gx < pr.width) && (gy < pr.height);
-    float* s_col = s_colAll + warp * PT_STEAL_WORDS;
+    float* s_col = s_colAll + warp * (PT_STEAL_WORDS + PT_POOL_WORDS);
+    float* s_pool = s_col + PT_STEAL_WORDS;
+    const unsigned capMask = (PT_POOL_CAP == 32) ? 0xffffffffu : ((1u << (PT_POOL_CAP & 31)) - 1u);
+    const unsigned below = (1u << lane) - 1u;
 
     Ctx c;
     c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
 
     const int spf = pr.samplesPerFrame;
-    const int pathLength = pr.pathLength;
     const bool warpLive = (tileX < pr.width) && (tileY < pr.height) && (spf > 0); /* warp-uniform */
     int roundBase = 0;
 #if PT_STEAL_S == 0
-    int roundN = warpLive ? spf : 0;
+    int roundN = spf;
     s_col[lane] = 0.0f; s_col[32 + lane] = 0.0f; s_col[64 + lane] = 0.0f;
     __syncwarp();
 #else
-    int roundN = warpLive ? (spf < PT_STEAL_S ? spf : PT_STEAL_S) : 0;
+    int roundN = spf < PT_STEAL_S ? spf : PT_STEAL_S;
 #endif
     int next = 0, item = 0;
+    unsigned mMarch = 0u, mReady = 0u; /* slots holding an unfinished march / a finished one waiting for a lane (warp-uniform) */
 
+    int st = warpLive ? PT_ST_NEW : PT_ST_DONE;
     V3 outColor = mk3(0.0f, 0.0f, 0.0f);
-    PathState ps; /* only ray, l, radiance, rayradiance, MISBRDFWeight, seed, bounce and pendingFinish are used */
-    PathStateInit(ps);
-    bool alive = false;
-
-    for (;;) {
-        const bool wantNew = !alive && ((next < 32 * roundN) || ps.pendingFinish);
-        const unsigned bNew = __ballot_sync(0xffffffffu, wantNew);
-        const unsigned bAlive = __ballot_sync(0xffffffffu, alive);
-        if ((bNew | bAlive) == 0u) {
-            if (!warpLive) break;
-            /* end of a round: lane p sums pixel p's samples in index order */
-            __syncwarp();
-#if PT_STEAL_S == 0
-            outColor = mk3(s_col[lane], s_col[32 + lane], s_col[64 + lane]);
-            break;
-#else
-            if (inRange) {
-#pragma unroll 1
-                for (int kk = 0; kk < roundN; kk++) {
-                    const float* e = s_col + (3 * kk) * 32 + lane;
-                    outColor = outColor + mk3(e[0], e[32], e[64]);
-                }
-            }
-            __syncwarp();
-            roundBase += roundN;
-            if (roundBase >= spf) break;
-            roundN = (spf - roundBase) < PT_STEAL_S ? (spf - roundBase) : PT_STEAL_S;
-            next = 0;
-            continue;
-#endif
-        }
-        if ((__popc(bNew) >= PT_REGEN_T) || (bAlive == 0u)) { /* warp-uniform */
-            if (wantNew) {
-                if (ps.pendingFinish) { /* Scene()'s tail for the path that ended, shader.comp:1477-1489 */
-                    const V3 col = PathColor(c, ps);
-#if PT_STEAL_S == 0
-                    float* e = s_col + (item & 31);
-                    atomicAdd(e, col.x); atomicAdd(e + 32, col.y); atomicAdd(e + 64, col.z);
-#else
-                    float* e = s_col + (3 * (item >> 5)) * 32 + (item & 31);
-                    e[0] = col.x; e[32] = col.y; e[64] = col.z;
-#endif
-                    ps.pendingFinish = false;
-                }
-                item = next + __popc(bNew & ((1u << lane) - 1u));
-                if (item < 32 * roundN) {
-                    const int q = item & 31;
-                    const int qx = tileX + (q & 7), qy = tileY + (q >> 3);
-                    if ((qx < pr.width) && (qy < pr.height)) { /* else: a pixel beyond the image edge; claim again */
-                        const int nextState = PhaseNew(c, ps, (unsigned)qx, (unsigned)pr.height - (unsigned)qy, roundBase + (item >> 5));
-                        alive = (nextState == PT_ST_ISECT); /* pathLength <= 0: PhaseNew left pendingFinish set */
-                    }
-                }
-            }
-            next += __popc(bNew);
-        }
-        if (alive) { /* one iteration of TracePath's loop, shader.comp:1393-1407 */
-            if (!TraceRayFlat(c, ps, pathLength)) {
-                alive = false;
-                ps.pendingFinish = true;
-            }
-        }
-    }
-    if (inRange) StoreTexel(pr, image, gx, gy, outColor);
-}
-
-/* ---- driver v2d: v2 with TWO pixels per lane, the idle one parked in shared memory ---------------------------------
- * v2 cannot fill its phases because a lane is tied to one pixel's sample sequence: a lane whose ray waits in front of
- * the SDF phase is a lane the feeder phases do not have, so the (expensive) SDF phase runs when the feeders dry up,
- * with whoever happens to wait -- 1-4 of 32 lanes in 61-73 % of its executions on the fractal scenes
- * (profiles/r01_sdfsched).  Here every lane owns two pixels (rows gy and gy + 8 of a 16x16 tile).  One path lives in
- * registers, the other is parked in the lane's own column of shared memory (56 words, no atomics, no queues).  A lane
- * whose active path has to wait for the SDF phase swaps to its other pixel and keeps feeding; it only counts as waiting
- * when BOTH its paths wait (the older one is marched first).  So the SDF phase starts with most of the warp in it, and
- * the feeders lose a lane only when it has nothing else to do.  Per pixel the samples still run in order through the
- * same phases: bit-exact in strict mode. */
-#define PT_PARK_WORDS 56
-#ifndef PT_SWAP_MIN
-#define PT_SWAP_MIN 8
-#endif
-PT_DEV void ParkSwap(float* col, PathState& ps, MarchState& ms, int& st, int& k, V3& outColor) {
-    int w = 0;
-#define PT_SWF(x) { const float t_ = col[w * PT_BLOCK_THREADS]; col[w * PT_BLOCK_THREADS] = (x); (x) = t_; w++; }
-#define PT_SWI(x) { const int t_ = __float_as_int(col[w * PT_BLOCK_THREADS]); col[w * PT_BLOCK_THREADS] = __int_as_float((int)(x)); (x) = t_; w++; }
-    PT_SWF(ps.ray.origin.x) PT_SWF(ps.ray.origin.y) PT_SWF(ps.ray.origin.z)
-    PT_SWF(ps.ray.dir.x) PT_SWF(ps.ray.dir.y) PT_SWF(ps.ray.dir.z)
-    PT_SWF(ps.l.x) PT_SWF(ps.l.y) PT_SWF(ps.l.z) PT_SWF(ps.l.w)
-    PT_SWF(ps.radiance.x) PT_SWF(ps.radiance.y) PT_SWF(ps.radiance.z) PT_SWF(ps.radiance.w)
-    PT_SWF(ps.rayradiance.x) PT_SWF(ps.rayradiance.y) PT_SWF(ps.rayradiance.z) PT_SWF(ps.rayradiance.w)
-    PT_SWF(ps.MISBRDFWeight)
-    PT_SWF(ps.shDir.x) PT_SWF(ps.shDir.y) PT_SWF(ps.shDir.z)
-    PT_SWF(ps.shContrib.x) PT_SWF(ps.shContrib.y) PT_SWF(ps.shContrib.z) PT_SWF(ps.shContrib.w)
-    PT_SWF(ps.h.t) PT_SWF(ps.h.normal.x) PT_SWF(ps.h.normal.y) PT_SWF(ps.h.normal.z) PT_SWF(ps.h.materialID) PT_SWF(ps.h.lightID)
-    PT_SWF(ms.mt) PT_SWF(ms.insT) PT_SWF(ms.omega) PT_SWF(ms.previousRadius) PT_SWF(ms.tMax) PT_SWF(ms.ksign)
-    PT_SWF(ms.probe) PT_SWF(ms.nrm0) PT_SWF(ms.nrm1) PT_SWF(ms.nrm2)
-    PT_SWF(outColor.x) PT_SWF(outColor.y) PT_SWF(outColor.z)
-    { /* seed and set1 are full 32-bit words */
-        unsigned s_ = ps.seed; int si_ = (int)s_; PT_SWI(si_) ps.seed = (unsigned)si_;
-        unsigned m_ = ms.set1; int mi_ = (int)m_; PT_SWI(mi_) ms.set1 = (unsigned)mi_;
-    }
-    int flags = ps.bounce | (ps.isShadow ? (1 << 28) : 0) | (ps.pathAlive ? (1 << 29) : 0) | (ps.pendingFinish ? (1 << 30) : 0);
-    PT_SWI(flags)
-    ps.bounce = flags & ((1 << 28) - 1);
-    ps.isShadow = (flags & (1 << 28)) != 0; ps.pathAlive = (flags & (1 << 29)) != 0; ps.pendingFinish = (flags & (1 << 30)) != 0;
-    PT_SWI(ps.shObj) PT_SWI(ps.h.objectID)
-    PT_SWI(ms.points) PT_SWI(ms.iter) PT_SWI(ms.sub)
-    PT_SWI(st) PT_SWI(k)
-#undef PT_SWF
-#undef PT_SWI
-}
-
-__device__ __forceinline__ void pt_render_body_v2d(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
-                                                   float4* __restrict__ image, float* s_tab, float* s_park) {
-    for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
-    __syncthreads();
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int gy0 = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3); /* the lane's pixels: rows gy0 and gy0 + 8 */
-    float* col = s_park + threadIdx.x;
-
-    Ctx c;
-    c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
-
-    const unsigned xyx = (unsigned)gx;
-    const int spf = pr.samplesPerFrame;
-    const bool inA = (gx < pr.width) && (gy0 < pr.height), inB = (gx < pr.width) && (gy0 + 8 < pr.height);
-
     PathState ps;
-    MarchState ms;
-    V3 outColor = mk3(0.0f, 0.0f, 0.0f);
-    int k = 0;
-    /* pixel B starts parked: a path in phase NEW (or DONE) carries no other state (k = 0, colour 0, nothing pending) */
-    const int stOther0 = (inB && spf > 0) ? PT_ST_NEW : PT_ST_DONE;
-#pragma unroll 1
-    for (int w = 0; w < PT_PARK_WORDS; w++) col[w * PT_BLOCK_THREADS] = 0.0f;
-    col[(PT_PARK_WORDS - 2) * PT_BLOCK_THREADS] = __int_as_float(stOther0); /* ParkSwap's layout: ..., st, k */
-    int stOther = stOther0; /* register mirror of the parked path's phase */
     PathStateInit(ps);
+    MarchState ms;
     MarchStateInit(ms);
-    int st = (inA && spf > 0) ? PT_ST_NEW : PT_ST_DONE;
-    int cur = 0; /* which pixel is in registers: 0 = row gy0, 1 = row gy0 + 8 */
-    bool settled = false; /* the active path is the older of two that wait for the SDF phase */
-    V3 colorA = mk3(0.0f, 0.0f, 0.0f), colorB = mk3(0.0f, 0.0f, 0.0f);
 
     for (;;) {
-        { /* lane-local: keep a runnable path in registers; when both wait for the SDF phase, march the older one */
-            const bool blocked = (st == PT_ST_SDF) || (st == PT_ST_DONE);
-            const bool otherRunnable = (stOther != PT_ST_SDF) && (stOther != PT_ST_DONE);
-            if (st != PT_ST_SDF) settled = false;
-            /* both wait for the SDF phase: bring the one that has waited longer (the parked one) in, once */
-            const bool toOlder = (stOther == PT_ST_SDF) && ((st == PT_ST_DONE) || ((st == PT_ST_SDF) && !settled));
-            const bool wantSwap = (blocked && otherRunnable) || toOlder;
-            /* the exchange costs ~250 instructions for the whole warp however many lanes take part: batch it -- wait for
-             * PT_SWAP_MIN candidates unless no lane has anything else to run */
-            const unsigned bWant = __ballot_sync(0xffffffffu, wantSwap);
-            const unsigned bRun = __ballot_sync(0xffffffffu, (st == PT_ST_NEW) || (st == PT_ST_ISECT) || (st == PT_ST_SHADE));
-            if (bWant != 0u && (__popc(bWant) >= PT_SWAP_MIN || bRun == 0u)) {
-                if (wantSwap) {
-                    if (st == PT_ST_DONE) { if (cur == 0) colorA = outColor; else colorB = outColor; }
-                    const int mine = st;
-                    ParkSwap(col, ps, ms, st, k, outColor);
-                    stOther = mine;
-                    cur ^= 1;
-                    settled = toOlder;
-                }
-            }
-        }
-        const unsigned xyy = (unsigned)pr.height - (unsigned)(gy0 + 8 * cur); /* shader.comp:1510 */
+        if (st == PT_ST_IDLE && mReady != 0u) st = PT_ST_NEW; /* a parked path finished: somebody has to carry it on */
         const unsigned bNew = __ballot_sync(0xffffffffu, st == PT_ST_NEW);
         const unsigned bIs = __ballot_sync(0xffffffffu, st == PT_ST_ISECT);
         const unsigned bSh = __ballot_sync(0xffffffffu, st == PT_ST_SHADE);
-#if PT_HAS_SDF
-        const unsigned bSdf = __ballot_sync(0xffffffffu, st == PT_ST_SDF);
-#else
-        const unsigned bSdf = 0u;
-#endif
-        if ((bNew | bIs | bSdf | bSh) == 0u) break; /* every lane: active DONE, and then the parked one is DONE too */
+        const unsigned bSdf = __ballot_sync(0xffffffffu, st == PT_ST_SDF); /* rays marching in their lane (pool was full) */
+        if ((bNew | bIs | bSdf | bSh | mMarch) == 0u) { /* (mReady != 0 implies bNew != 0) */
+            if (!warpLive) break;
+            if (!PoolCloseRound(s_col, lane, inRange, spf, roundBase, roundN, outColor)) break;
+            next = 0;
+            st = PT_ST_NEW;
+            continue;
+        }
         int phase = PT_ST_NEW, best = __popc(bNew);
         if (__popc(bIs) >= best) { best = __popc(bIs); phase = PT_ST_ISECT; }
         if (__popc(bSh) >= best) { best = __popc(bSh); phase = PT_ST_SHADE; }
-#if PT_HAS_SDF
-        if (bSdf != 0u && (best < PT_FEED_T || best == 0)) phase = PT_ST_SDF;
-#endif
-        PT_STAT(phase, phase == PT_ST_NEW ? bNew : (phase == PT_ST_ISECT ? bIs : (phase == PT_ST_SDF ? bSdf : bSh)));
-#ifdef PT_STATS
-        if (phase == PT_ST_SDF && (threadIdx.x & 31) == 0) atomicAdd(&pt_stats[8 + ((__popc(bSdf) - 1) >> 2)], 1ull);
-#endif
+        const int marching = __popc(mMarch) + __popc(bSdf);
+        if (marching > 0 && (marching >= PT_POOL_MIN || best == 0 || (bSdf != 0u && best < PT_FEED_T))) phase = PT_ST_SDF;
+        PT_STAT(phase, phase == PT_ST_NEW ? bNew : (phase == PT_ST_ISECT ? bIs : (phase == PT_ST_SDF ? 0u : bSh)));
         if (phase == PT_ST_NEW) {
+            const int rank = __popc(bNew & below), nReady = __popc(mReady);
+            const int take = (__popc(bNew) < nReady) ? __popc(bNew) : nReady; /* READY paths picked up in this execution */
+            unsigned taken = 0u;
             if (st == PT_ST_NEW) {
                 if (ps.pendingFinish) {
-                    outColor = outColor + PathColor(c, ps);
+                    PoolDeposit(s_col, item, PathColor(c, ps));
                     ps.pendingFinish = false;
                 }
-                if (k < spf) {
-                    st = PhaseNew(c, ps, xyx, xyy, k);
-                    k++;
+                if (rank < take) { /* carry a finished parked path on */
+                    const int slot = (int)__fns(mReady, 0u, rank + 1);
+                    PoolPickup(s_pool + slot, ps, item);
+                    taken = 1u << slot;
+                    st = PhaseTrivial(ps);
                 } else {
-                    st = PT_ST_DONE;
+                    item = next + (rank - take);
+                    if (item < 32 * roundN) {
+                        const int q = item & 31;
+                        const int qx = tileX + (q & 7), qy = tileY + (q >> 3);
+                        if ((qx < pr.width) && (qy < pr.height)) /* else: a pixel beyond the image edge; claim again */
+                            st = PhaseNew(c, ps, (unsigned)qx, (unsigned)pr.height - (unsigned)qy, roundBase + (item >> 5));
+                    } else {
+                        st = PT_ST_IDLE;
+                    }
                 }
             }
+            next += __popc(bNew) - take;
+            if (take > 0) {
+                mReady &= ~__reduce_or_sync(0xffffffffu, taken);
+                __syncwarp();
+            }
         } else if (phase == PT_ST_ISECT) {
+            bool entered = false;
             if (st == PT_ST_ISECT) {
                 st = PhaseIsect(c, ps, ms);
                 if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
+                entered = (st == PT_ST_SDF);
             }
-        }
-#if PT_HAS_SDF
-        else if (phase == PT_ST_SDF) {
-#pragma unroll 1
-            for (int rep = 0; rep < PT_SDF_REPS; rep++) {
-                if (st == PT_ST_SDF) st = PhaseSdfEval(c, ps, ms);
-            }
-            if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
-        }
-#endif
-        else {
-            if (st == PT_ST_SHADE) st = PhaseShade(c, ps);
-        }
-    }
-    if (cur == 0) colorA = outColor; else colorB = outColor;
-    if (inA) StoreTexel(pr, image, gx, gy0, colorA);
-    if (inB) StoreTexel(pr, image, gx, gy0 + 8, colorB);
-}
-
-#if PT_HAS_SDF
-/* ---- driver v2p: v2 + a march pool shared by the warps of a CTA --------------------------------------------------
- * In v2 only the lanes of ONE warp that happen to be marching populate the SDF phase (ncu: 7 of 32 on the
- * mandelbulb scene).  Here a lane whose ray entered an SDF box publishes the march as a job in shared memory
- * (origin, direction, SphereTracing's locals: 24 words) and waits; whenever a warp runs the SDF phase, ALL its
- * lanes -- whatever their own state -- claim pending jobs of ANY thread of the CTA (128-bit pending mask, claims by
- * atomicAnd), advance them PT_SDF_REPS evaluations with the same PhaseSdfEval, and put them back or mark them done.
- * The per-job arithmetic does not depend on who executes it, so strict mode stays bit-exact. */
-enum { PT_ST_WAIT = 5 };
-enum { PJ_OX = 0, PJ_OY, PJ_OZ, PJ_DX, PJ_DY, PJ_DZ, PJ_SHADOW, PJ_HT, PJ_MT, PJ_INST, PJ_OMEGA, PJ_PREV, PJ_TMAX, PJ_KSIGN,
-       PJ_PROBE, PJ_N0, PJ_N1, PJ_N2, PJ_POINTS, PJ_ITER, PJ_SUB, PJ_SET1, PJ_OBJ, PJ_MAT, PJ_DONE, PJ_FIELDS };
-#ifndef PT_POOL_MIN
-#define PT_POOL_MIN 24
-#endif
-
-__device__ __forceinline__ void pt_render_body_v2p(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
-                                                   float4* __restrict__ image, float* s_tab, float* s_job, unsigned* s_mask) {
-    for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
-    if (threadIdx.x < 4) s_mask[threadIdx.x] = 0u;
-    __syncthreads();
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int gy = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
-    const bool inRange = (gx < pr.width) && (gy < pr.height);
-    const int tid = threadIdx.x;
-
-    Ctx c;
-    c.sc = &sc; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
-
-    const unsigned xyx = (unsigned)gx;
-    const unsigned xyy = (unsigned)pr.height - (unsigned)gy; /* shader.comp:1510 */
-    const int spf = pr.samplesPerFrame;
-
-    int st = (inRange && spf > 0) ? PT_ST_NEW : PT_ST_DONE;
-    int k = 0;
-    V3 outColor = mk3(0.0f, 0.0f, 0.0f);
-    PathState ps;
-    PathStateInit(ps);
-    volatile float* job = s_job;
-    volatile unsigned* vmask = s_mask;
-#define PJ(f, t) job[(f) * PT_BLOCK_THREADS + (t)]
-
-    for (;;) {
-        /* a finished job: take the hit back */
-        if (st == PT_ST_WAIT && PJ(PJ_DONE, tid) != 0.0f) {
-            ps.h.t = PJ(PJ_HT, tid);
-            ps.h.objectID = __float_as_int(PJ(PJ_OBJ, tid));
-            if (__float_as_int(PJ(PJ_SUB, tid)) == PT_SUB_N0 + 6) { /* a path ray hit the SDF: normal and material came with it */
-                ps.h.normal = mk3(PJ(PJ_N0, tid), PJ(PJ_N1, tid), PJ(PJ_N2, tid));
-                ps.h.materialID = PJ(PJ_MAT, tid);
-                ps.h.lightID = -1.0f;
-            }
-            st = PhaseTrivial(ps);
-        }
-        const unsigned bNew = __ballot_sync(0xffffffffu, st == PT_ST_NEW);
-        const unsigned bIs = __ballot_sync(0xffffffffu, st == PT_ST_ISECT);
-        const unsigned bSh = __ballot_sync(0xffffffffu, st == PT_ST_SHADE);
-        const unsigned bWait = __ballot_sync(0xffffffffu, st == PT_ST_WAIT);
-        if ((bNew | bIs | bSh | bWait) == 0u) break;
-        /* one snapshot of the pending mask for the whole warp (lane 0's), so ranks and the vote are consistent */
-        const unsigned m0 = __shfl_sync(0xffffffffu, vmask[0], 0), m1 = __shfl_sync(0xffffffffu, vmask[1], 0),
-                       m2 = __shfl_sync(0xffffffffu, vmask[2], 0), m3 = __shfl_sync(0xffffffffu, vmask[3], 0);
-        const int pending = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
-        int phase = PT_ST_NEW, best = __popc(bNew);
-        if (__popc(bIs) >= best) { best = __popc(bIs); phase = PT_ST_ISECT; }
-        if (__popc(bSh) >= best) { best = __popc(bSh); phase = PT_ST_SHADE; }
-        /* march when a (nearly) full warp's worth of jobs is waiting in the CTA, or when this warp's feeders are thin */
-        if (pending > 0 && (pending >= PT_POOL_MIN || best < PT_FEED_T)) phase = PT_ST_SDF;
-        if (best == 0 && phase != PT_ST_SDF) { /* everyone here waits on jobs other warps are running */
-            __nanosleep(200);
-            continue;
-        }
-        PT_STAT(phase, phase == PT_ST_NEW ? bNew : (phase == PT_ST_ISECT ? bIs : (phase == PT_ST_SDF ? 0u : bSh)));
-        if (phase == PT_ST_NEW) {
-            if (st == PT_ST_NEW) {
-                if (ps.pendingFinish) {
-                    outColor = outColor + PathColor(c, ps);
-                    ps.pendingFinish = false;
+            const unsigned bEnt = __ballot_sync(0xffffffffu, entered);
+            if (bEnt != 0u) { /* park the rays that have to march, as many as there are free slots */
+                const unsigned mFree = ~(mMarch | mReady) & capMask;
+                const int r = __popc(bEnt & below), nFree = __popc(mFree);
+                unsigned parkedBit = 0u;
+                if (entered && r < nFree) {
+                    const int slot = (int)__fns(mFree, 0u, r + 1);
+                    PoolPark(s_pool + slot, ps, ms, item);
+                    parkedBit = 1u << slot;
+                    st = PT_ST_NEW; /* nothing pending: the NEW phase hands this lane a READY path or a new item */
                 }
-                if (k < spf) {
-                    st = PhaseNew(c, ps, xyx, xyy, k);
-                    k++;
-                } else {
-                    st = PT_ST_DONE;
-                }
-            }
-        } else if (phase == PT_ST_ISECT) {
-            if (st == PT_ST_ISECT) {
-                MarchState ms;
-                st = PhaseIsect(c, ps, ms);
-                if (st == PT_ST_SDF) { /* publish the march as a job of the CTA's pool */
-                    const V3 d = ps.isShadow ? ps.shDir : ps.ray.dir;
-                    PJ(PJ_OX, tid) = ps.ray.origin.x; PJ(PJ_OY, tid) = ps.ray.origin.y; PJ(PJ_OZ, tid) = ps.ray.origin.z;
-                    PJ(PJ_DX, tid) = d.x; PJ(PJ_DY, tid) = d.y; PJ(PJ_DZ, tid) = d.z;
-                    PJ(PJ_SHADOW, tid) = ps.isShadow ? 1.0f : 0.0f;
-                    PJ(PJ_HT, tid) = ps.h.t;
-                    PJ(PJ_OBJ, tid) = __int_as_float(ps.h.objectID);
-                    PJ(PJ_MT, tid) = ms.mt; PJ(PJ_INST, tid) = ms.insT; PJ(PJ_OMEGA, tid) = ms.omega;
-                    PJ(PJ_PREV, tid) = ms.previousRadius; PJ(PJ_TMAX, tid) = ms.tMax; PJ(PJ_KSIGN, tid) = 0.0f;
-                    PJ(PJ_PROBE, tid) = 0.0f; PJ(PJ_N0, tid) = 0.0f; PJ(PJ_N1, tid) = 0.0f; PJ(PJ_N2, tid) = 0.0f;
-                    PJ(PJ_POINTS, tid) = __int_as_float(ms.points); PJ(PJ_ITER, tid) = __int_as_float(ms.iter);
-                    PJ(PJ_SUB, tid) = __int_as_float(ms.sub); PJ(PJ_SET1, tid) = __uint_as_float(ms.set1);
-                    PJ(PJ_DONE, tid) = 0.0f;
-                    __threadfence_block();
-                    atomicOr(&s_mask[warp], 1u << lane);
-                    st = PT_ST_WAIT;
-                } else {
-                    st = PhaseTrivial(ps);
-                }
+                mMarch |= __reduce_or_sync(0xffffffffu, parkedBit);
+                __syncwarp();
             }
         } else if (phase == PT_ST_SDF) {
-            /* lane L takes the L-th pending job of the CTA (if it wins the atomicAnd against the other warps) */
-            int j = -1;
-            {
-                int r = lane;
-                const unsigned mm[4] = {m0, m1, m2, m3};
-#pragma unroll
-                for (int w = 0; w < 4; w++) {
-                    const int n = __popc(mm[w]);
-                    if (j < 0 && r < n) j = w * 32 + (int)__fns(mm[w], 0u, r + 1);
-                    r -= n;
-                }
+            /* who marches what: lanes with a ray of their own march that; the others take the parked rays in slot order */
+            const bool own = (st == PT_ST_SDF);
+            const int r = __popc(~bSdf & below);
+            const bool job = !own && (r < __popc(mMarch));
+            PT_STAT_SDF(__popc(bSdf) + min(32 - __popc(bSdf), __popc(mMarch)));
+#ifdef PT_STATS
+            if ((threadIdx.x & 31) == 0) atomicAdd(&pt_stats[2 * PT_ST_SDF + 1], (unsigned long long)(__popc(bSdf) + min(32 - __popc(bSdf), __popc(mMarch))));
+#endif
+            float* e = s_pool + (job ? (int)__fns(mMarch, 0u, r + 1) : 0);
+            PathState js; /* the marching ray: only ray.origin, the direction, isShadow and h are read / written */
+            MarchState jm = ms;
+            js.ray.origin = ps.ray.origin;
+            js.ray.dir = ps.isShadow ? ps.shDir : ps.ray.dir;
+            js.isShadow = ps.isShadow;
+            js.h = ps.h;
+            if (job) {
+                js.ray.origin = mk3(PT_PF(PF_OX), PT_PF(PF_OY), PT_PF(PF_OZ));
+                js.isShadow = ((__float_as_uint(PT_PF(PF_FLAGS)) >> 30) & 1u) != 0u;
+                js.ray.dir = js.isShadow ? mk3(PT_PF(PF_SX), PT_PF(PF_SY), PT_PF(PF_SZ)) : mk3(PT_PF(PF_DX), PT_PF(PF_DY), PT_PF(PF_DZ));
+                js.h.t = PT_PF(PF_HT);
+                js.h.objectID = __float_as_int(PT_PF(PF_HOBJ));
+                PoolLoadMarch(e, jm);
             }
-            if (j >= 0) {
-                const unsigned bit = 1u << (j & 31);
-                if ((atomicAnd(&s_mask[j >> 5], ~bit) & bit) == 0u) j = -1; /* another warp got it */
-            }
-            if (j >= 0) {
-                __threadfence_block();
-                PathState js;
-                MarchState ms;
-                js.ray.origin = mk3(PJ(PJ_OX, j), PJ(PJ_OY, j), PJ(PJ_OZ, j));
-                js.ray.dir = mk3(PJ(PJ_DX, j), PJ(PJ_DY, j), PJ(PJ_DZ, j));
-                js.shDir = js.ray.dir;
-                js.isShadow = PJ(PJ_SHADOW, j) != 0.0f;
-                js.h.t = PJ(PJ_HT, j);
-                js.h.objectID = __float_as_int(PJ(PJ_OBJ, j));
-                js.h.normal = mk3(0.0f, 0.0f, 0.0f); js.h.materialID = 0.0f; js.h.lightID = -1.0f;
-                ms.mt = PJ(PJ_MT, j); ms.insT = PJ(PJ_INST, j); ms.omega = PJ(PJ_OMEGA, j); ms.previousRadius = PJ(PJ_PREV, j);
-                ms.tMax = PJ(PJ_TMAX, j); ms.ksign = PJ(PJ_KSIGN, j); ms.probe = PJ(PJ_PROBE, j);
-                ms.nrm0 = PJ(PJ_N0, j); ms.nrm1 = PJ(PJ_N1, j); ms.nrm2 = PJ(PJ_N2, j);
-                ms.points = __float_as_int(PJ(PJ_POINTS, j)); ms.iter = __float_as_int(PJ(PJ_ITER, j));
-                ms.sub = __float_as_int(PJ(PJ_SUB, j)); ms.set1 = __float_as_uint(PJ(PJ_SET1, j));
-                int jst = PT_ST_SDF;
+            js.shDir = js.ray.dir;
+            int jst = (own || job) ? PT_ST_SDF : PT_ST_DONE;
 #pragma unroll 1
-                for (int rep = 0; rep < PT_SDF_REPS && jst == PT_ST_SDF; rep++) jst = PhaseSdfEval(c, js, ms);
-                PJ(PJ_HT, j) = js.h.t;
-                PJ(PJ_OBJ, j) = __int_as_float(js.h.objectID);
-                PJ(PJ_SUB, j) = __int_as_float(ms.sub);
+            for (int rep = 0; rep < PT_SDF_REPS; rep++) {
+                if (jst == PT_ST_SDF) jst = PhaseSdfEval(c, js, jm);
+            }
+            unsigned doneBit = 0u;
+            if (own) {
+                ps.h = js.h;
+                ms = jm;
+                st = jst;
+                if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
+            } else if (job) {
+                /* (a converged path ray has its hit distance before its normal: h.t travels with an unfinished job too) */
+                PT_PF(PF_HT) = js.h.t; PT_PF(PF_HOBJ) = __int_as_float(js.h.objectID);
                 if (jst == PT_ST_SDF) {
-                    PJ(PJ_MT, j) = ms.mt; PJ(PJ_INST, j) = ms.insT; PJ(PJ_OMEGA, j) = ms.omega; PJ(PJ_PREV, j) = ms.previousRadius;
-                    PJ(PJ_TMAX, j) = ms.tMax; PJ(PJ_KSIGN, j) = ms.ksign; PJ(PJ_PROBE, j) = ms.probe;
-                    PJ(PJ_N0, j) = ms.nrm0; PJ(PJ_N1, j) = ms.nrm1; PJ(PJ_N2, j) = ms.nrm2;
-                    PJ(PJ_POINTS, j) = __int_as_float(ms.points); PJ(PJ_ITER, j) = __int_as_float(ms.iter);
-                    PJ(PJ_SET1, j) = __uint_as_float(ms.set1);
-                    __threadfence_block();
-                    atomicOr(&s_mask[j >> 5], 1u << (j & 31));
-                } else {
-                    if (ms.sub == PT_SUB_N0 + 6) {
-                        PJ(PJ_N0, j) = js.h.normal.x; PJ(PJ_N1, j) = js.h.normal.y; PJ(PJ_N2, j) = js.h.normal.z;
-                        PJ(PJ_MAT, j) = js.h.materialID;
+                    PoolStoreMarch(e, jm);
+                } else { /* finished: the hit goes to the slot, the path waits there for a free lane */
+                    if (jm.sub == PT_SUB_N0 + 6) { /* a path ray that hit the SDF: normal and material came with it */
+                        PT_PF(PF_HNX) = js.h.normal.x; PT_PF(PF_HNY) = js.h.normal.y; PT_PF(PF_HNZ) = js.h.normal.z;
+                        PT_PF(PF_HMAT) = js.h.materialID; PT_PF(PF_HLIGHT) = js.h.lightID;
                     }
-                    __threadfence_block();
-                    PJ(PJ_DONE, j) = 1.0f;
+                    doneBit = 1u << (unsigned)(e - s_pool);
                 }
+            }
+            if (mMarch != 0u) {
+                doneBit = __reduce_or_sync(0xffffffffu, doneBit);
+                mMarch &= ~doneBit;
+                mReady |= doneBit;
+                __syncwarp();
             }
         } else {
-            if (st == PT_ST_SHADE) st = PhaseShade(c, ps);
+            if (st == PT_ST_SHADE) st = PhaseShadeHit(c, ps);
         }
     }
-#undef PJ
     if (inRange) StoreTexel(pr, image, gx, gy, outColor);
 }
+#undef PT_PF
 #endif /* PT_HAS_SDF */
 
 #ifndef PT_SCHED
-#define PT_SCHED 1
+#define PT_SCHED 0
 #endif
-__device__ __forceinline__ void pt_render_body(const PtDevScene& sc, const PtDevParams& pr, const float* __restrict__ ubo,
-                                               float4* __restrict__ image, float* s_tab) {
-#if PT_SCHED == 3
-    pt_render_body_v3(sc, pr, ubo, image, s_tab);
-#elif PT_SCHED
-    pt_render_body_v2(sc, pr, ubo, image, s_tab);
-#else
-    pt_render_body_v1(sc, pr, ubo, image, s_tab);
+#if PT_SCHED == 8 && !PT_HAS_SDF
+#undef PT_SCHED
+#define PT_SCHED 5 /* nothing marches: v2m is v2s */
 #endif
-}
 
 } /* namespace PT_KERNEL_NS */
 
 /* the kernel entry point; the name distinguishes the strict / fast / JIT instances */
-#if PT_SCHED == 4
-#define PT_ROWS_PER_BLOCK 16
+#if PT_SCHED == 8
 #define PT_DEFINE_RENDER_KERNEL(name)                                                                        \
-    extern "C" __device__ int pt_rows_per_block = 16;                                                        \
     extern "C" __global__ void __launch_bounds__(PT_BLOCK_THREADS, PT_MIN_BLOCKS)                            \
     name(const __grid_constant__ PtDevScene sc, const __grid_constant__ PtDevParams pr,                      \
          const float* __restrict__ ubo, float4* __restrict__ image) {                                        \
         __shared__ float s_tab[PT_SH_FLOATS];                                                                \
-        __shared__ float s_park[PT_PARK_WORDS * PT_BLOCK_THREADS];                                           \
-        PT_KERNEL_NS::pt_render_body_v2d(sc, pr, ubo, image, s_tab, s_park);                                 \
-    }
-#elif PT_SCHED == 6
-#define PT_DEFINE_RENDER_KERNEL(name)                                                                        \
-    extern "C" __device__ int pt_persistent_ctas_per_sm = PT_MIN_BLOCKS;                                     \
-    extern "C" __device__ unsigned pt_tile_ctr[2] = {0u, 0u};                                                \
-    extern "C" __global__ void __launch_bounds__(PT_BLOCK_THREADS, PT_MIN_BLOCKS)                            \
-    name(const __grid_constant__ PtDevScene sc, const __grid_constant__ PtDevParams pr,                      \
-         const float* __restrict__ ubo, float4* __restrict__ image) {                                        \
-        __shared__ float s_tab[PT_SH_FLOATS];                                                                \
-        __shared__ float s_v2sp[PT_V2SP_WORDS * (PT_BLOCK_THREADS / 32)];                                    \
-        PT_KERNEL_NS::pt_render_body_v2sp(sc, pr, ubo, image, s_tab, s_v2sp, pt_tile_ctr);                   \
+        __shared__ float s_col[(PT_STEAL_WORDS + PT_POOL_WORDS) * (PT_BLOCK_THREADS / 32)];                  \
+        PT_KERNEL_NS::pt_render_body_v2m(sc, pr, ubo, image, s_tab, s_col);                                  \
     }
 #elif PT_SCHED == 7
 #define PT_DEFINE_RENDER_KERNEL(name)                                                                        \
@@ -2630,29 +1791,20 @@ __device__ __forceinline__ void pt_render_body(const PtDevScene& sc, const PtDev
     name(const __grid_constant__ PtDevScene sc, const __grid_constant__ PtDevParams pr,                      \
          const float* __restrict__ ubo, float4* __restrict__ image) {                                        \
         __shared__ float s_tab[PT_SH_FLOATS];                                                                \
-        __shared__ float s_col[(PT_STEAL_WORDS + PT_MPARK_WORDS) * (PT_BLOCK_THREADS / 32)];                 \
+        __shared__ float s_col[PT_STEAL_WORDS * (PT_BLOCK_THREADS / 32)];                                    \
         PT_KERNEL_NS::pt_render_body_v2s(sc, pr, ubo, image, s_tab, s_col);                                  \
     }
-#elif PT_HAS_SDF && PT_SCHED == 2
+#elif PT_SCHED == 0
 #define PT_DEFINE_RENDER_KERNEL(name)                                                                        \
     extern "C" __global__ void __launch_bounds__(PT_BLOCK_THREADS, PT_MIN_BLOCKS)                            \
     name(const __grid_constant__ PtDevScene sc, const __grid_constant__ PtDevParams pr,                      \
          const float* __restrict__ ubo, float4* __restrict__ image) {                                        \
         __shared__ float s_tab[PT_SH_FLOATS];                                                                \
-        __shared__ float s_job[PT_KERNEL_NS::PJ_FIELDS * PT_BLOCK_THREADS];                                  \
-        __shared__ unsigned s_mask[4];                                                                       \
-        PT_KERNEL_NS::pt_render_body_v2p(sc, pr, ubo, image, s_tab, s_job, s_mask);                          \
+        PT_KERNEL_NS::pt_render_body_v1(sc, pr, ubo, image, s_tab);                                          \
     }
 #else
-#define PT_DEFINE_RENDER_KERNEL(name)                                                                        \
-    extern "C" __global__ void __launch_bounds__(PT_BLOCK_THREADS, PT_MIN_BLOCKS)                            \
-    name(const __grid_constant__ PtDevScene sc, const __grid_constant__ PtDevParams pr,                      \
-         const float* __restrict__ ubo, float4* __restrict__ image) {                                        \
-        __shared__ float s_tab[PT_SH_FLOATS];                                                                \
-        PT_KERNEL_NS::pt_render_body(sc, pr, ubo, image, s_tab);                                             \
-    }
+#error "PT_SCHED: 0 (v1), 5 (v2s), 7 (v3s) or 8 (v2m)"
 #endif
-
 
 #if PT_HAS_SDF
 /* SDF()/SDFMATERIAL() at arbitrary points: used by the tests to compare the NVRTC build of the snippets with the

@@ -27,8 +27,6 @@ struct JitKernel {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kernel = nullptr;
     cudaKernel_t sdf_eval = nullptr; /* only for scenes with SDF snippets */
-    int rows_per_block = 8;          /* image rows one CTA covers: 8, or 16 for the two-pixels-per-lane driver (PT_SCHED=4) */
-    int persistent_ctas_per_sm = 0;  /* > 0: persistent grid of SMs x this many CTAs, tiles claimed from a counter (PT_SCHED=6) */
     /* wavefront pipeline (pt_wavefront.cuh); wf_march only with SDF snippets */
     cudaKernel_t wf_gen = nullptr, wf_isect = nullptr, wf_march = nullptr, wf_shade = nullptr, wf_final = nullptr,
                  wf_ctl = nullptr;
@@ -44,6 +42,8 @@ struct pt_ctx {
     int jit_policy = 1;      /* 0: never (static kernels only), 1: when the scene has SDFs, 2: always (baked counts) */
     int pipeline = PT_PIPE_MEGAKERNEL;
     int bvh_min = PT_BVH_DEFAULT_MIN_PRIMS; /* bounded primitives from which the BVH replaces the scan; <= 0: never */
+    PtKnobs knobs;           /* pt_set_option: tuning options of the run-time compiled kernels */
+    long long wf_max_paths = 32ll << 20; /* wavefront pipeline: paths in flight per chunk */
     bool bvh_active = false;
     PtWf wf;                 /* wavefront buffers (lazily allocated) */
     void* wf_block = nullptr;
@@ -99,14 +99,7 @@ int launch(pt_ctx* ctx, const PtDevParams& dp) {
         ctx->timing_open = true;
     }
     if (ctx->active_jit) {
-        const int rows = ctx->active_jit->rows_per_block;
-        dim3 grid((unsigned)((dp.width + 15) / 16), (unsigned)((dp.height + rows - 1) / rows), 1), block(128, 1, 1);
-        if (ctx->active_jit->persistent_ctas_per_sm > 0) {
-            const long long tiles = (long long)((dp.width + 7) / 8) * ((dp.height + 3) / 4); /* one warp per 8x4 tile at most */
-            long long ctas = (long long)ctx->num_sms * ctx->active_jit->persistent_ctas_per_sm;
-            if (ctas > (tiles + 3) / 4) ctas = (tiles + 3) / 4;
-            grid = dim3((unsigned)(ctas > 0 ? ctas : 1), 1, 1);
-        }
+        const dim3 grid((unsigned)((dp.width + 15) / 16), (unsigned)((dp.height + 7) / 8), 1), block(128, 1, 1);
         const float* ubo = ctx->d_ubo;
         float* image = ctx->d_image;
         void* args[4] = {(void*)&ctx->dev_scene, (void*)&dp, (void*)&ubo, (void*)&image};
@@ -148,8 +141,7 @@ int launch_wavefront(pt_ctx* ctx, const PtDevParams& dp0) {
     JitKernel* k = ctx->active_jit;
     if (!k || !k->wf_gen) return fail(ctx, PT_ERR_ARG, "wavefront pipeline: kernels not built (call pt_set_scene after pt_set_pipeline)");
     const size_t pixels = (size_t)dp0.width * (size_t)dp0.height;
-    size_t max_paths = 32u << 20;
-    if (const char* e = getenv("PT_WF_MAX_PATHS")) { if (atoll(e) > 0) max_paths = (size_t)atoll(e); }
+    const size_t max_paths = (size_t)ctx->wf_max_paths;
     int chunk = (int)(max_paths / pixels);
     if (chunk < 1) chunk = 1;
     if (chunk > dp0.samplesPerFrame) chunk = dp0.samplesPerFrame;
@@ -248,10 +240,6 @@ int pt_create(int device, pt_ctx** out) {
         (void)cudaGetLastError();
         ctx->num_sms = 148;
     }
-    const char* pol = getenv("PT_JIT");
-    if (pol && pol[0]) ctx->jit_policy = atoi(pol);
-    const char* bm = getenv("PT_BVH_MIN");
-    if (bm && bm[0]) ctx->bvh_min = atoi(bm);
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
         (e = cudaMalloc((void**)&ctx->d_ubo, sizeof(float) * (PT_BVH_UBO_OFF + PT_BVH_MAX_FLOATS))) != cudaSuccess ||
@@ -313,6 +301,25 @@ int pt_set_bvh(pt_ctx* ctx, int min_prims) {
     return PT_OK;
 }
 
+/* Tuning options (pt_abi.h): they select and parametrise the kernel pt_set_scene builds -- never the result */
+int pt_set_option(pt_ctx* ctx, const char* key, long long value) {
+    if (!ctx || !key) return fail(ctx, PT_ERR_ARG, "pt_set_option: null argument");
+    if (std::string(key) == "wf_max_paths") {
+        if (value < 1) return fail(ctx, PT_ERR_ARG, "pt_set_option: wf_max_paths must be positive");
+        ctx->wf_max_paths = value;
+        return PT_OK;
+    }
+    if (pt_knob_set(&ctx->knobs, key, value) != 0)
+        return fail(ctx, PT_ERR_ARG, std::string("pt_set_option: unknown option or value out of range: ") + key);
+    ctx->scene_set = false; /* kernels are selected in pt_set_scene */
+    return PT_OK;
+}
+int pt_get_option(const pt_ctx* ctx, const char* key, long long* value) {
+    if (!ctx || !key || !value) return PT_ERR_ARG;
+    if (std::string(key) == "wf_max_paths") { *value = ctx->wf_max_paths; return PT_OK; }
+    return pt_knob_get(&ctx->knobs, key, value) == 0 ? PT_OK : PT_ERR_ARG;
+}
+
 int pt_bvh_active(const pt_ctx* ctx) { return (ctx && ctx->scene_set && ctx->bvh_active) ? 1 : 0; }
 
 int pt_set_pipeline(pt_ctx* ctx, int pipeline) {
@@ -361,10 +368,9 @@ int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, in
         opt.bvh = bvh;
         const int counts[6] = {sc.nSpheres, sc.nPlanes, sc.nBoxes, sc.nLenses, sc.nCyclides, sc.nSdfs};
         memcpy(opt.counts, counts, sizeof counts);
-        std::string key = std::to_string(opt.mode) + (opt.bake_counts ? "b" : "g") + (wavefront ? "w" : "m") + (bvh ? "B" : "");
-        if (opt.bake_counts)
-            for (int i = 0; i < 6; i++) key += "," + std::to_string(counts[i]);
-        key += "|" + unit;
+        opt.knobs = ctx->knobs;
+        /* the cache key is the complete translation unit: mode, baked counts, every resolved option, the SDF text */
+        const std::string key = pt_jit_source(unit, opt);
         auto it = ctx->jit_cache.find(key);
         if (it == ctx->jit_cache.end()) {
             std::vector<char> cubin;
@@ -377,24 +383,6 @@ int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, in
             if (e != cudaSuccess) {
                 cudaLibraryUnload(jk.lib);
                 return cuda_fail(ctx, e, "cudaLibraryGetKernel(pt_render_jit)");
-            }
-            { /* a persistent kernel says how many CTAs per SM it is built for */
-                void* dptr = nullptr;
-                size_t bytes = 0;
-                if (cudaLibraryGetGlobal(&dptr, &bytes, jk.lib, "pt_persistent_ctas_per_sm") == cudaSuccess && bytes == sizeof(int)) {
-                    PT_CUDA(ctx, cudaMemcpy(&jk.persistent_ctas_per_sm, dptr, sizeof(int), cudaMemcpyDeviceToHost));
-                } else {
-                    (void)cudaGetLastError();
-                }
-            }
-            { /* a kernel that covers more than 8 rows per CTA says so */
-                void* dptr = nullptr;
-                size_t bytes = 0;
-                if (cudaLibraryGetGlobal(&dptr, &bytes, jk.lib, "pt_rows_per_block") == cudaSuccess && bytes == sizeof(int)) {
-                    PT_CUDA(ctx, cudaMemcpy(&jk.rows_per_block, dptr, sizeof(int), cudaMemcpyDeviceToHost));
-                } else {
-                    (void)cudaGetLastError();
-                }
             }
             if (n_sdf > 0 && (e = cudaLibraryGetKernel(&jk.sdf_eval, jk.lib, "pt_sdf_eval_jit")) != cudaSuccess) {
                 cudaLibraryUnload(jk.lib);
@@ -516,17 +504,21 @@ int pt_render(pt_ctx* ctx, const pt_params* base, int total_samples, int samples
 }
 
 /* pt_render continuing a run that already holds done_samples samples per pixel in the image (a multiple of
- * samples_per_frame): dispatches done/spf + 1 .. total/spf with the same bookkeeping. */
+ * samples_per_frame).  The reference's offscreen loop keeps dispatching while currentSamples < numSamples
+ * (host:4042-4074), i.e. ceil(total / spf) dispatches of spf samples each -- a total that is not a multiple of
+ * samples_per_frame renders the next multiple, as the reference does. */
 int pt_render_resume(pt_ctx* ctx, const pt_params* base, int done_samples, int total_samples, int samples_per_frame) {
     if (!ctx || !base) return fail(ctx, PT_ERR_ARG, "pt_render: null argument");
-    if (samples_per_frame <= 0 || total_samples < samples_per_frame || done_samples < 0 || done_samples % samples_per_frame != 0)
-        return fail(ctx, PT_ERR_ARG, "pt_render: need total_samples >= samples_per_frame > 0 and done_samples a multiple of it");
+    if (samples_per_frame <= 0 || total_samples <= 0 || done_samples < 0 || done_samples % samples_per_frame != 0)
+        return fail(ctx, PT_ERR_ARG, "pt_render: need total_samples > 0, samples_per_frame > 0 and done_samples a multiple of it");
     pt_params p = *base;
     p.samplesPerFrame = samples_per_frame;
+    const long long spf = samples_per_frame, total = total_samples;
+    if (((total + spf - 1) / spf) * spf > 2147483647ll) return fail(ctx, PT_ERR_ARG, "pt_render: sample index would overflow the 32-bit frame counter");
     /* offscreen MainLoop bookkeeping (host:4042-4048): before dispatch j, frame = currentSamples = j * spf */
-    for (int j = done_samples / samples_per_frame + 1; j * samples_per_frame <= total_samples; j++) {
-        p.frame = j * samples_per_frame;
-        p.currentSamples = j * samples_per_frame;
+    for (long long j = done_samples / spf + 1; (j - 1) * spf < total; j++) {
+        p.frame = (int)(j * spf);
+        p.currentSamples = (int)(j * spf);
         int rc = pt_dispatch(ctx, &p);
         if (rc != PT_OK) return rc;
     }
@@ -642,6 +634,7 @@ int pt_sdf_compile_check(const char* const* sdf_glsl, int n_sdf, const float* sd
     opt.wavefront = false;
     opt.bvh = false;
     memset(opt.counts, 0, sizeof opt.counts);
+    opt.counts[5] = n_sdf;
     std::vector<char> cubin;
     rc = pt_jit_compile(unit, opt, &cubin, &log);
     if (rc != PT_OK) return fail(nullptr, rc, log);
@@ -652,8 +645,14 @@ int pt_sdf_compile_check(const char* const* sdf_glsl, int n_sdf, const float* sd
 /* Compile (NVRTC, no GPU needed) exactly the kernel pt_set_scene would build for this scene, mode and jit policy.
  * The ptxas report (registers, spills) is left in pt_last_error(NULL). */
 int pt_kernel_compile_check(const pt_ubo* ubo, const char* const* sdf_glsl, int n_sdf, int mode, int bake_counts) {
+    return pt_kernel_compile_check_opts(ubo, sdf_glsl, n_sdf, mode, bake_counts, nullptr);
+}
+int pt_kernel_compile_check_opts(const pt_ubo* ubo, const char* const* sdf_glsl, int n_sdf, int mode, int bake_counts,
+                                 const char* options) {
     if (!ubo) return fail(nullptr, PT_ERR_ARG, "null ubo");
     std::string unit, err, log;
+    PtKnobs knobs;
+    if (pt_knobs_parse(&knobs, options, &err) != 0) return fail(nullptr, PT_ERR_ARG, err);
     PtDevScene sc;
     int rc = pt_prepare_scene(ubo, &sc, &err);
     if (rc != PT_OK) return fail(nullptr, rc, err);
@@ -668,10 +667,41 @@ int pt_kernel_compile_check(const pt_ubo* ubo, const char* const* sdf_glsl, int 
     opt.bvh = (mode & 4) != 0;       /* mode bit 2: closest hit through the BVH */
     const int counts[6] = {sc.nSpheres, sc.nPlanes, sc.nBoxes, sc.nLenses, sc.nCyclides, sc.nSdfs};
     memcpy(opt.counts, counts, sizeof counts);
+    opt.knobs = knobs;
     std::vector<char> cubin;
     rc = pt_jit_compile(unit, opt, &cubin, &log);
     if (rc != PT_OK) return fail(nullptr, rc, log);
     g_last_error = log;
+    return PT_OK;
+}
+
+/* Measured FP32 peak of this device: a grid of independent FFMA chains (pt_kernels_fast.cu), timed with CUDA events on
+ * the context's stream, best of `repeats`.  The roofline denominator of bench.py. */
+int pt_fp32_peak(pt_ctx* ctx, int repeats, double* tflops, double* ms_best) {
+    if (!ctx || !tflops) return fail(ctx, PT_ERR_ARG, "pt_fp32_peak: null argument");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    float* d = nullptr;
+    const int blocks = ctx->num_sms * 8, threads = 256, iters = 4096;
+    PT_CUDA(ctx, cudaMalloc((void**)&d, sizeof(float) * (size_t)blocks * threads));
+    cudaEvent_t a, b;
+    PT_CUDA(ctx, cudaEventCreate(&a));
+    PT_CUDA(ctx, cudaEventCreate(&b));
+    double best = 1e30;
+    if (repeats < 1) repeats = 1;
+    for (int r = 0; r < repeats + 1; r++) { /* first run warms up */
+        cudaEventRecord(a, ctx->stream);
+        pt_launch_fma_peak(d, blocks, threads, iters, ctx->stream);
+        cudaEventRecord(b, ctx->stream);
+        cudaError_t e = cudaEventSynchronize(b);
+        if (e != cudaSuccess) { cudaFree(d); return cuda_fail(ctx, e, "pt_fp32_peak"); }
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, a, b);
+        if (r > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * (double)threads; /* 16 FFMA per iteration per thread */
+    *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_best) *ms_best = best;
     return PT_OK;
 }
 
@@ -698,7 +728,7 @@ int pt_sdf_eval(pt_ctx* ctx, const float* xyz, size_t n, unsigned set1, float* d
     return PT_OK;
 }
 
-/* debug: scheduling statistics of a kernel built with env PT_STATS=1 (16 counters; see pt_kernel.cuh) */
+/* debug: scheduling statistics of a kernel built with option "stats" = 1 (16 counters; see pt_kernel.cuh) */
 int pt_debug_stats(pt_ctx* ctx, unsigned long long* out16, int reset) {
     if (!ctx || !out16 || !ctx->active_jit) return fail(ctx, PT_ERR_ARG, "pt_debug_stats: needs a JIT kernel");
     void* dptr = nullptr;
@@ -706,7 +736,7 @@ int pt_debug_stats(pt_ctx* ctx, unsigned long long* out16, int reset) {
     PT_CUDA(ctx, cudaSetDevice(ctx->device));
     PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaError_t e = cudaLibraryGetGlobal(&dptr, &bytes, ctx->active_jit->lib, "pt_stats");
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "pt_stats symbol (build with PT_STATS=1)");
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "pt_stats symbol (pt_set_option(ctx, \"stats\", 1) before pt_set_scene)");
     PT_CUDA(ctx, cudaMemcpy(out16, dptr, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     if (reset) PT_CUDA(ctx, cudaMemset(dptr, 0, 16 * sizeof(unsigned long long)));
     return PT_OK;

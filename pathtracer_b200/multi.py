@@ -33,7 +33,12 @@ def render_split(renderer, params, total_samples, spf, image, dist=None, first_s
     finished XYZ image in the reference's units, other ranks' hold their partial sums."""
     rank = dist.get_rank() if dist is not None else 0
     world = dist.get_world_size() if dist is not None else 1
+    import torch
+    # The renderer launches on its OWN stream (created cudaStreamNonBlocking: it never synchronises implicitly with
+    # torch's), while image.zero_() and the NCCL reduce are enqueued on torch's current stream.  Every hand-over between
+    # the two is ordered explicitly: zero -> dispatches, dispatches -> reduce, reduce -> finalize.
     image.zero_()
+    torch.cuda.current_stream().synchronize()
     renderer.bind_image(image)
     begin, end = sample_slice(rank, world, total_samples, first_sample)
     for s, n in chunks(begin, end, spf):
@@ -41,6 +46,7 @@ def render_split(renderer, params, total_samples, spf, image, dist=None, first_s
     renderer.sync()
     if dist is not None and world > 1:
         dist.reduce(image, dst=0, op=dist.ReduceOp.SUM)
+        torch.cuda.current_stream().synchronize()   # the reduce has landed before finalize touches the image
     if rank == 0:
         renderer.finalize(params, total_samples)
         renderer.sync()

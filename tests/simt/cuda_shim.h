@@ -69,6 +69,17 @@ static inline uint32_t simt_exchange(uint32_t mine, int src) { /* src < 0: gathe
     for (int i = 0; i < 32; i++) r |= (w.xchg[ph][i] ? 1u : 0u) << i;
     return r;
 }
+static inline unsigned __reduce_or_sync(unsigned mask, unsigned v) { /* redux.sync.or.b32 */
+    simt_require_full(mask);
+    SimtWarp& w = *simt_warp;
+    const unsigned ph = simt_phase & 1u;
+    simt_phase++;
+    w.xchg[ph][threadIdx.x & 31u] = v;
+    w.bar.arrive_and_wait();
+    uint32_t r = 0;
+    for (int i = 0; i < 32; i++) r |= w.xchg[ph][i];
+    return r;
+}
 static inline unsigned __ballot_sync(unsigned mask, bool pred) { simt_require_full(mask); return simt_exchange(pred ? 1u : 0u, -1); }
 static inline float __shfl_sync(unsigned mask, float v, int src) {
     simt_require_full(mask);

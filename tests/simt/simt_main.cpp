@@ -57,13 +57,8 @@ extern "C" int simt_dispatch(const pt_ubo* ubo, const pt_params* params, int acc
     std::string err;
     if (pt_prepare_scene(ubo, &sc, &err) != 0) { fprintf(stderr, "simt: %s\n", err.c_str()); return -1; }
     if (pt_prepare_params(params, accum_mode, first, n, &dp, &err) != 0) { fprintf(stderr, "simt: %s\n", err.c_str()); return -2; }
-#if PT_SCHED == 6
-    gridDim = {(unsigned)(persistent_ctas > 0 ? persistent_ctas : 2), 1u, 1u};
-#elif PT_SCHED == 4
-    gridDim = {(unsigned)((dp.width + 15) / 16), (unsigned)((dp.height + 15) / 16), 1u};
-#else
+    (void)persistent_ctas;
     gridDim = {(unsigned)((dp.width + 15) / 16), (unsigned)((dp.height + 7) / 8), 1u};
-#endif
     blockDim = {PT_BLOCK_THREADS, 1u, 1u};
     const float* ubo_f = reinterpret_cast<const float*>(ubo);
     float4* img = reinterpret_cast<float4*>(image);

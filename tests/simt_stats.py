@@ -44,6 +44,9 @@ print('%s %dx%d pathLength %d, %d samples per pixel, %d blocks, defines %s' % (n
 for i, n in enumerate(['NEW', 'ISECT', 'SDF', 'SHADE']):
     ex, ln = out[2 * i], out[2 * i + 1]
     print('  %-6s executions %10d (%5.1f%%)  avg lanes %5.2f  per sample-warp %.2f' % (n, ex, 100.0 * ex / max(tot, 1), ln / max(ex, 1), ex / (samples / 32)))
+hist = [out[8 + b] for b in range(8)]
+if sum(hist):
+    print('  SDF executions by participants (1-4, 5-8, ... 29-32): ' + ' '.join('%.1f%%' % (100.0 * h / sum(hist)) for h in hist))
 # a coarse issue-slot model, calibrated on the ncu capture of v2s on cfg3 (profiles/r01_final4: 266 warp instructions per
 # sample, 42 % of them in the SDF phase): warp instructions per 32 samples = sum over phases of executions x cost
 R = defs.get('PT_SDF_REPS', 16)

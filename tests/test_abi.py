@@ -22,10 +22,85 @@ def test_every_declared_symbol_is_exported(ptlib):
     assert not missing, missing
 
 
-def test_struct_sizes():
-    text = open(os.path.join(ROOT, 'include', 'pt_abi.h')).read()
-    assert '16388' in text and '88 bytes' in text
+LAYOUT_TU = r'''
+#include <stddef.h>
+#include "pt_abi.h"
+/* the uniform block: 4097 tightly packed floats in the reference's order (shader.comp:19-27 == host:187-195) */
+static_assert(sizeof(pt_ubo) == 16388, "uniform block");
+static_assert(offsetof(pt_ubo, numObjects) == 0 && offsetof(pt_ubo, objects) == 4 * 7, "ubo head");
+static_assert(offsetof(pt_ubo, sdfs) == 4 * 1031 && offsetof(pt_ubo, materials) == 4 * 1799, "ubo sdfs / materials");
+static_assert(offsetof(pt_ubo, lights) == 4 * 2582 && offsetof(pt_ubo, lightIDs) == 4 * 2710, "ubo lights");
+static_assert(offsetof(pt_ubo, CIEXYZ1931) == 4 * 2774, "ubo CIE table");
+/* the push-constant block, byte offsets as SURVEY.md section 8a lists them (shader.comp:31-52 == host:197-218) */
+static_assert(sizeof(pt_params) == 88, "push constants");
+static_assert(offsetof(pt_params, resolution) == 0 && offsetof(pt_params, frame) == 8 && offsetof(pt_params, currentSamples) == 12, "");
+static_assert(offsetof(pt_params, samplesPerFrame) == 16 && offsetof(pt_params, FPS) == 20 && offsetof(pt_params, persistence) == 24, "");
+static_assert(offsetof(pt_params, pathLength) == 28 && offsetof(pt_params, cameraAngle) == 32 && offsetof(pt_params, cameraPosX) == 40, "");
+static_assert(offsetof(pt_params, cameraPosY) == 44 && offsetof(pt_params, cameraPosZ) == 48 && offsetof(pt_params, ISO) == 52, "");
+static_assert(offsetof(pt_params, cameraSize) == 56 && offsetof(pt_params, apertureSize) == 60 && offsetof(pt_params, apertureDist) == 64, "");
+static_assert(offsetof(pt_params, lensRadius) == 68 && offsetof(pt_params, lensFocalLength) == 72 && offsetof(pt_params, lensThickness) == 76, "");
+static_assert(offsetof(pt_params, lensDistance) == 80 && offsetof(pt_params, tonemap) == 84, "");
+int main(void) { return 0; }
+'''
+
+
+def test_struct_layout_through_a_compiler(tmp_path):
+    """sizeof / offsetof of the two boundary blocks, checked by gcc (C11) and g++ (C++17) on a real translation unit."""
+    import subprocess
+    src = tmp_path / 'layout.c'
+    src.write_text(LAYOUT_TU.replace('static_assert', '_Static_assert'))
+    subprocess.run(['gcc', '-std=c11', '-fsyntax-only', '-I' + os.path.join(ROOT, 'include'), str(src)], check=True)
+    srcpp = tmp_path / 'layout.cpp'
+    srcpp.write_text(LAYOUT_TU)
+    subprocess.run(['g++', '-std=c++17', '-fsyntax-only', '-I' + os.path.join(ROOT, 'include'), str(srcpp)], check=True)
     assert 7 + 1024 + 768 + 783 + 128 + 64 + 1323 == 4097
+
+
+def test_integration_md_binding_compiles(tmp_path):
+    """The reference-side binding shown in INTEGRATION.md, through g++: its static_asserts against the reference's own
+    struct definitions (taken from /root/reference when present, else from stand-ins with the same members), and every
+    pt_* call of the snippet against the header's prototypes."""
+    import subprocess
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    blocks = re.findall(r'```cpp\n(.*?)```', text, flags=re.S)
+    assert blocks, 'INTEGRATION.md has no ```cpp block'
+    ref_structs = None
+    ref_host = os.path.join(ROOT, 'oracle', '_ref', 'ref_host.cpp')
+    if os.path.exists(ref_host):
+        t = open(ref_host).read()
+        a, b = t.index('#define MAX_OBJECTS_SIZE'), t.index('const float CIEXYZ1931[1323]')
+        ref_structs = '#include <glm/glm.hpp>\n#include <string>\n' + t[a:b]
+    if ref_structs is None or not os.path.exists('/root/reference/includes/glm/glm.hpp'):
+        ref_structs = '''
+struct UniformBufferObject { float numObjects[7]; float packedObjects[1024]; float packedSdfs[768]; float packedMaterials[783];
+                             float packedLights[128]; float packedLightIDs[64]; float CIEXYZ1931[1323]; };
+struct PushConstantValues { int resolution[2]; int frame, currentSamples, samplesPerFrame; float FPS, persistence; int pathLength;
+                            float cameraAngle[2]; float cameraPosX, cameraPosY, cameraPosZ; int ISO; float cameraSize, apertureSize,
+                            apertureDist, lensRadius, lensFocalLength, lensThickness, lensDistance; int tonemap; };
+'''
+    # the members of the reference's App the snippet touches (host:1088-1089, 1129, 1146, 1157-1191), as a base class
+    base = '''
+struct sdf_stub { std::string glsl; };
+struct AppBase {
+    int W = 1280, H = 720, tonemap = 3;
+    UniformBufferObject ubo;
+    PushConstantValues pushConstant;
+    std::vector<sdf_stub> sdfs;
+    std::string renderDir;
+    void UpdateUniformBuffer() {}
+    void UpdatePushConstant() {}
+};
+'''
+    body = '\n'.join(blocks)
+    assert 'class App {' in body
+    head, tail = body.split('class App {', 1)
+    tu = ('#include <stdexcept>\n#include <string>\n#include <vector>\n#include <cstring>\n' + ref_structs + head + base +
+          'class App : public AppBase {' + tail + '\nint main() { return 0; }\n')
+    src = tmp_path / 'binding.cpp'
+    src.write_text(tu)
+    r = subprocess.run(['g++', '-std=c++17', '-fsyntax-only', '-I' + os.path.join(ROOT, 'include'), '-I/root/reference/includes', str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
 
 
 def test_no_cpu_fallback(ptlib):

@@ -320,10 +320,10 @@ def test_wavefront_strict_bit_exact(ptlib, wf_renderer, name, w, h, spp, spf, pl
     assert_bit_equal(got, ref, 'wavefront %s' % name)
 
 
-def test_wavefront_chunking_and_sum_mode(ptlib, wf_renderer, monkeypatch):
-    """Several chunks of samples per dispatch (PT_WF_MAX_PATHS caps the paths in flight) keep the per-pixel sums in
+def test_wavefront_chunking_and_sum_mode(ptlib, wf_renderer):
+    """Several chunks of samples per dispatch (option wf_max_paths caps the paths in flight) keep the per-pixel sums in
     sample-index order: still bit-exact; and the raw-sum mode used by the multi-GPU split works through it too."""
-    monkeypatch.setenv('PT_WF_MAX_PATHS', str(96 * 64 * 3))
+    wf_renderer.set_option('wf_max_paths', 96 * 64 * 3)
     got, ubo, p, src = gpu_render(ptlib, wf_renderer, 'scene0', 96, 64, 8, 8)
     ref = oracle.Oracle(ubo, src).render(p, 8, 8)
     assert_bit_equal(got, ref, 'wavefront chunked')
@@ -333,6 +333,7 @@ def test_wavefront_chunking_and_sum_mode(ptlib, wf_renderer, monkeypatch):
     refs = np.zeros_like(ref)
     oracle.Oracle(ubo, src).dispatch_sum(p, 5, 7, refs)
     assert_bit_equal(s[..., :3].copy(), refs[..., :3].copy(), 'wavefront sum mode')
+    wf_renderer.set_option('wf_max_paths', 32 << 20)
 
 
 def test_wavefront_matches_megakernel_fast_mode(ptlib, renderer, wf_renderer):
@@ -405,150 +406,179 @@ def test_scene_at_the_uniform_block_capacity(ptlib, pipeline, bvh_min):
     assert_bit_equal(got, oracle.Oracle(ubo).render(p, 2, 2), '169 spheres, pipeline %d, bvh_min %d' % (pipeline, bvh_min))
 
 
-# ---- driver v3 (flat loop, gated regeneration): an A/B knob of the run-time compiled kernels ------------------------------
-@pytest.mark.parametrize('name,w,h,spp,spf,pl,regen_t', [
-    ('scene0', 96, 64, 8, 4, 5, 16), ('scene1', 96, 64, 8, 8, 5, 16), ('scene1', 70, 45, 6, 3, 32, 4), ('scene2', 64, 48, 4, 4, 5, 32),
-    ('scene3', 64, 48, 2, 2, 5, 1), ('scene7', 64, 48, 2, 2, 5, 16), ('scene10', 64, 48, 2, 2, 5, 16)])
-def test_v3_driver_strict_bit_exact(ptlib, monkeypatch, name, w, h, spp, spf, pl, regen_t):
-    """PT_SCHED=3: the same per-lane arithmetic in the same sample order as v1, whatever the regeneration threshold
-    (ragged frame sizes included: lanes outside the image never start a path)."""
-    monkeypatch.setenv('PT_SCHED', '3')
-    monkeypatch.setenv('PT_REGEN_T', str(regen_t))
+# ---- the drivers of the megakernel (pt_set_option "sched"): same paths, same sums, whatever the schedule ------------------
+DRIVER_CASES = [
+    # v1: nested loops
+    ({'sched': 0}, 'scene0', 96, 64, 8, 4, 5, 2), ({'sched': 0}, 'scene10', 64, 48, 2, 2, 5, 2), ({'sched': 0}, 'scene1', 70, 45, 6, 3, 32, 1),
+    # v3s: flat loop + sample pool (table rounds, ragged sizes, regeneration thresholds)
+    ({'sched': 7, 'steal_s': 16, 'regen_t': 16}, 'scene0', 96, 64, 8, 4, 5, 2), ({'sched': 7, 'steal_s': 16, 'regen_t': 8}, 'scene1', 70, 45, 40, 20, 5, 2),
+    ({'sched': 7, 'steal_s': 4, 'regen_t': 4}, 'scene2', 33, 17, 9, 9, 5, 2), ({'sched': 7, 'steal_s': 2, 'regen_t': 16}, 'scene1', 96, 72, 6, 3, 32, 1),
+    ({'sched': 7, 'steal_s': 16, 'regen_t': 32}, 'scene10', 64, 48, 4, 2, 5, 2), ({'sched': 7, 'steal_s': 16, 'regen_t': 1}, 'scene3', 64, 48, 2, 2, 5, 1),
+    # v2s: phase machine + sample pool
+    ({'sched': 5, 'steal_s': 16}, 'scene9', 96, 64, 4, 2, 5, 2), ({'sched': 5, 'steal_s': 2}, 'scene10', 70, 45, 6, 3, 32, 2),
+    ({'sched': 5, 'steal_s': 16}, 'scene8', 64, 48, 2, 2, 5, 1), ({'sched': 5, 'steal_s': 8}, 'scene7', 64, 40, 2, 1, 5, 2),
+    ({'sched': 5, 'steal_s': 16}, 'scene1', 96, 72, 40, 20, 5, 2), ({'sched': 5, 'steal_s': 8}, 'scene0', 33, 17, 12, 12, 5, 2),
+    ({'sched': 5, 'steal_s': 16}, 'scene3', 64, 48, 2, 2, 5, 1), ({'sched': 5, 'steal_s': 16}, 'scene10', 64, 48, 18, 18, 5, 2),
+    # v2m: phase machine + pool of parked marching paths (default, tiny, never-full-enough and greedy pools)
+    ({'sched': 8}, 'scene9', 96, 64, 4, 2, 5, 2), ({'sched': 8}, 'scene10', 70, 45, 6, 3, 32, 2), ({'sched': 8}, 'scene8', 64, 48, 4, 4, 5, 1),
+    ({'sched': 8, 'pool_cap': 3, 'pool_min': 1, 'steal_s': 3}, 'scene8', 50, 37, 10, 10, 32, 2), ({'sched': 8, 'pool_min': 64}, 'scene7', 64, 40, 2, 1, 5, 2),
+    ({'sched': 8, 'pool_cap': 8, 'pool_min': 8, 'sdf_reps': 3}, 'scene3', 64, 48, 12, 12, 5, 1), ({'sched': 8, 'steal_s': 4}, 'scene10', 64, 48, 18, 18, 5, 2),
+    ({'sched': 8}, 'scene1', 96, 72, 6, 3, 5, 2),   # no SDF: v2m is v2s
+]
+
+
+def render_with(ptlib, options, name, w, h, spp, spf, pl, mode, jit, first=None):
     sc = ptlib.Scene.load(scene_path(name))
     ubo = sc.pack_ubo()
     p = sc.pack_params(1, w, h, spf, pl)
-    r = ptlib.Renderer(device=0, mode=ptlib.MODE_STRICT, jit=2)
+    r = ptlib.Renderer(device=0, mode=mode, jit=jit, options=options)
     r.set_scene(ubo, sc.sdf_sources)
     r.resize(w, h)
-    r.render(p, spp, spf)
+    if first is None:
+        r.render(p, spp, spf)
+    else:
+        for j in range(spp // spf):
+            r.dispatch_sum(p, first + j * spf, spf)
+        r.finalize(p, spp)
     got = r.read_xyz()
     r.close()
-    ref = oracle.Oracle(ubo, [s.decode() for s in sc.sdf_sources]).render(p, spp, spf)
-    assert_bit_equal(got, ref, '%s v3 T=%d' % (name, regen_t))
+    return got, ubo, p, [s.decode() for s in sc.sdf_sources]
 
 
-# ---- driver v2d (two pixels per lane, the idle one parked in shared memory) ------------------------------------------------
-@pytest.mark.parametrize('name,w,h,spp,spf,pl,jit', [
-    ('scene9', 96, 64, 4, 2, 5, 2), ('scene10', 70, 45, 3, 3, 32, 2), ('scene8', 64, 48, 2, 2, 5, 1), ('scene7', 64, 40, 2, 1, 5, 2),
-    ('scene1', 96, 72, 6, 3, 5, 2), ('scene0', 33, 17, 4, 4, 5, 2), ('scene3', 64, 48, 2, 2, 5, 1)])
-def test_v2d_driver_strict_bit_exact(ptlib, monkeypatch, name, w, h, spp, spf, pl, jit):
-    """PT_SCHED=4: per pixel the same phases on the same samples in the same order as v2 -- whichever of a lane's two
-    pixels is in registers at any time.  Ragged sizes: rows gy0 + 8 outside the image never start."""
-    monkeypatch.setenv('PT_SCHED', '4')
-    sc = ptlib.Scene.load(scene_path(name))
-    ubo = sc.pack_ubo()
-    p = sc.pack_params(1, w, h, spf, pl)
-    r = ptlib.Renderer(device=0, mode=ptlib.MODE_STRICT, jit=jit)
-    r.set_scene(ubo, sc.sdf_sources)
-    r.resize(w, h)
-    r.render(p, spp, spf)
-    got = r.read_xyz()
-    r.close()
-    ref = oracle.Oracle(ubo, [s.decode() for s in sc.sdf_sources]).render(p, spp, spf)
-    assert_bit_equal(got, ref, '%s v2d' % name)
+@pytest.mark.parametrize('options,name,w,h,spp,spf,pl,jit', DRIVER_CASES)
+def test_driver_strict_bit_exact(ptlib, options, name, w, h, spp, spf, pl, jit):
+    """Whichever lane runs a sample and however the warp schedules its phases, Scene() depends only on (pixel, sample
+    index), and each pixel's samples are added in index order: every driver writes the oracle's bits.  Covers several
+    rounds per dispatch (spf > steal_s, with a short last round), several dispatches, ragged frame sizes (items of
+    pixels beyond the image edge are skipped), pathLength 32, and for v2m pools that overflow (the ray then marches in
+    its lane), never reach their threshold, or run the SDF phase for every single ray."""
+    got, ubo, p, src = render_with(ptlib, options, name, w, h, spp, spf, pl, ptlib.MODE_STRICT, jit)
+    ref = oracle.Oracle(ubo, src).render(p, spp, spf)
+    assert_bit_equal(got, ref, '%s %r' % (name, options))
 
 
-# ---- driver v2s (in-warp sample stealing: a warp's 32 x S samples are a pool of work items) --------------------------------
-@pytest.mark.parametrize('name,w,h,spp,spf,pl,jit,steal_s', [
-    ('scene9', 96, 64, 4, 2, 5, 2, 16), ('scene10', 70, 45, 6, 3, 32, 2, 2), ('scene8', 64, 48, 2, 2, 5, 1, 16), ('scene7', 64, 40, 2, 1, 5, 2, 8),
-    ('scene1', 96, 72, 40, 20, 5, 2, 16), ('scene0', 33, 17, 12, 12, 5, 2, 8), ('scene3', 64, 48, 2, 2, 5, 1, 16), ('scene10', 64, 48, 18, 18, 5, 2, 16)])
-def test_v2s_driver_strict_bit_exact(ptlib, monkeypatch, name, w, h, spp, spf, pl, jit, steal_s):
-    """PT_SCHED=5: whichever lane runs a sample, Scene() depends only on (pixel, sample index), and each pixel's samples
-    are added in index order at the end of a round -- the oracle's bits.  Covers several rounds per dispatch
-    (spf > PT_STEAL_S, with a short last round), several dispatches, ragged frame sizes (items of pixels beyond the
-    image edge are skipped) and pathLength 32."""
-    monkeypatch.setenv('PT_SCHED', '5')
-    monkeypatch.setenv('PT_STEAL_S', str(steal_s))
-    sc = ptlib.Scene.load(scene_path(name))
-    ubo = sc.pack_ubo()
-    p = sc.pack_params(1, w, h, spf, pl)
-    r = ptlib.Renderer(device=0, mode=ptlib.MODE_STRICT, jit=jit)
-    r.set_scene(ubo, sc.sdf_sources)
-    r.resize(w, h)
-    r.render(p, spp, spf)
-    got = r.read_xyz()
-    r.close()
-    ref = oracle.Oracle(ubo, [s.decode() for s in sc.sdf_sources]).render(p, spp, spf)
-    assert_bit_equal(got, ref, '%s v2s S=%d' % (name, steal_s))
-
-
-@pytest.mark.parametrize('name,w,h,spp,spf,pl,jit,cap,pmin', [
-    ('scene9', 96, 64, 4, 2, 5, 2, 24, 12), ('scene10', 70, 45, 6, 3, 32, 2, 24, 4), ('scene8', 64, 48, 4, 4, 5, 1, 24, 12),
-    ('scene8', 50, 37, 10, 10, 32, 2, 3, 1), ('scene7', 64, 40, 2, 1, 5, 2, 24, 12), ('scene3', 64, 48, 12, 12, 5, 1, 8, 8)])
-def test_v2s_march_parking_strict_bit_exact(ptlib, monkeypatch, name, w, h, spp, spf, pl, jit, cap, pmin):
-    """PT_MPARK=1: rays that must march are parked on the warp's stack in shared memory and taken back in batches by
-    whichever lanes are free.  A path is the same arithmetic whichever lane holds it: the oracle's bits, also with a
-    stack that overflows (cap 3: the ray then marches in its lane), several rounds per dispatch (the strict table holds
-    8 samples next to the stack) and pathLength 32."""
-    monkeypatch.setenv('PT_SCHED', '5')
-    monkeypatch.setenv('PT_MPARK', '1')
-    monkeypatch.setenv('PT_MPARK_CAP', str(cap))
-    monkeypatch.setenv('PT_MPARK_MIN', str(pmin))
-    sc = ptlib.Scene.load(scene_path(name))
-    ubo = sc.pack_ubo()
-    p = sc.pack_params(1, w, h, spf, pl)
-    r = ptlib.Renderer(device=0, mode=ptlib.MODE_STRICT, jit=jit)
-    r.set_scene(ubo, sc.sdf_sources)
-    r.resize(w, h)
-    r.render(p, spp, spf)
-    got = r.read_xyz()
-    r.close()
-    ref = oracle.Oracle(ubo, [s.decode() for s in sc.sdf_sources]).render(p, spp, spf)
-    assert_bit_equal(got, ref, '%s v2s + march parking (cap %d, min %d)' % (name, cap, pmin))
+def test_option_errors(ptlib, renderer):
+    with pytest.raises(ptlib.PtError):
+        renderer.set_option('no_such_option', 1)
+    with pytest.raises(ptlib.PtError):
+        renderer.set_option('sched', 3)      # a driver that no longer exists
+    renderer.set_option('sdf_reps', 8)
+    assert renderer.get_option('sdf_reps') == 8
+    renderer.set_option('sdf_reps', 16)
 
 
 @pytest.mark.parametrize('sched,name,w,h,spf,pl', [
     (5, 'scene9', 96, 64, 24, 5), (5, 'scene10', 70, 45, 16, 32), (5, 'scene1', 50, 37, 32, 5), (5, 'scene8', 64, 48, 8, 5),
-    (6, 'scene1', 50, 37, 32, 5), (6, 'scene0', 61, 43, 1, 5), (6, 'scene0', 64, 48, 3, 5), (6, 'scene2', 200, 120, 2, 5),
-    (6, 'scene9', 96, 64, 24, 5), (6, 'scene10', 70, 45, 16, 32), (6, 'scene8', 64, 48, 8, 5)])
-def test_v2s_fast_mode_pools_the_whole_dispatch(ptlib, monkeypatch, sched, name, w, h, spf, pl):
-    """Fast mode.  PT_SCHED=5 with PT_STEAL_S=0: one pool of 32 x samplesPerFrame items per warp, finished samples added to
-    their pixel's sum in shared memory in schedule order.  PT_SCHED=6 (v2sp): persistent warps claim tiles from a global
-    counter and keep several in flight (small samplesPerFrame and ragged frame sizes exercise the slot recycling, the
-    skipped items beyond the image edge and the counter's self-reset between the two dispatches).  Repeated renders
-    give the same bits (5) / the same image up to summation order (6: which warp gets which tile varies from run to
-    run).  Against the table variant of v2s (PT_STEAL_S=16, sums in sample order) on the SAME sample indices:
+    (7, 'scene1', 50, 37, 32, 5), (7, 'scene0', 61, 43, 3, 5), (7, 'scene2', 200, 120, 2, 5),
+    (8, 'scene9', 96, 64, 24, 5), (8, 'scene10', 70, 45, 16, 32), (8, 'scene8', 64, 48, 8, 5), (8, 'scene3', 64, 48, 12, 5)])
+def test_fast_mode_pools_the_whole_dispatch(ptlib, sched, name, w, h, spf, pl):
+    """Fast mode, steal_s = 0 (what the fast builds default to): one pool of 32 x samplesPerFrame items per warp, finished
+    samples added to their pixel's sum in shared memory in schedule order.  Repeated renders give the same bits (the
+    schedule of a warp is a pure function of its inputs).  Against the table variant of v2s (steal_s = 16, sums in
+    sample order) on the SAME sample indices:
       * without SDFs the images agree to fp32 summation order (relative 1e-5) on at least 97 % of the pixels -- the
         rest are paths that fork where the two compilations contract a multiply-add differently (nvdisasm shows a
         handful of FFMA vs FMUL+FADD differences between any two builds of the kernel; fast mode permits that);
       * with SDFs one ulp in a distance moves the hit point, and the numerical normal (central differences, eps 1e-4)
         amplifies it into another path: there the two builds must be no further apart than two renders of one build
         with disjoint sample indices (the Monte-Carlo noise), and their mean luminances agree to 1 %."""
-    sc = ptlib.Scene.load(scene_path(name))
-    ubo = sc.pack_ubo()
-    p = sc.pack_params(1, w, h, spf, pl)
     spp = 2 * spf
 
-    def run(sched, steal, first=0):
-        monkeypatch.setenv('PT_SCHED', str(sched))
-        monkeypatch.setenv('PT_STEAL_S', str(steal))
-        r = ptlib.Renderer(device=0, mode=ptlib.MODE_FAST, jit=2)
-        r.set_scene(ubo, sc.sdf_sources)
-        r.resize(w, h)
-        r.dispatch_sum(p, first, spf)
-        r.dispatch_sum(p, first + spf, spf)
-        r.finalize(p, spp)
-        out = r.read_xyz()
-        r.close()
-        return out
+    def run(options, first=0):
+        return render_with(ptlib, options, name, w, h, spp, spf, pl, ptlib.MODE_FAST, 2, first=first)[0]
 
-    pooled, pooled2, table, table_b = run(sched, 0), run(sched, 0), run(5, 16), run(5, 16, first=1 << 20)
+    pooled, pooled2 = run({'sched': sched, 'steal_s': 0}), run({'sched': sched, 'steal_s': 0})
+    table, table_b = run({'sched': 5, 'steal_s': 16}), run({'sched': 5, 'steal_s': 16}, first=1 << 20)
     assert np.isfinite(pooled).all() and (pooled[..., 3] == 1.0).all()
     scale = float(table[..., :3].max())
-    if sched == 5:
-        assert np.array_equal(pooled.view(np.uint32), pooled2.view(np.uint32))
-    else:
-        assert np.allclose(pooled[..., :3], pooled2[..., :3], rtol=1e-5, atol=1e-6 * scale)
+    assert np.array_equal(pooled.view(np.uint32), pooled2.view(np.uint32))
     close = np.isclose(table[..., :3], pooled[..., :3], rtol=1e-5, atol=1e-6 * scale).all(axis=-1)
     frac = 1.0 - float(close.mean())
     diff, noise = rel_rmse(pooled, table), rel_rmse(table_b, table)
     mean_rel = abs(float(pooled[..., 1].mean()) / float(table[..., 1].mean()) - 1.0)
-    print('%s: pooled vs table: %.4f of the pixels beyond summation-order tolerance, relRMSE %.5f (noise %.5f), mean Y rel diff %.5f'
-          % (name, frac, diff, noise, mean_rel))
-    if not sc.sdf_sources:
+    print('%s sched %d: pooled vs table: %.4f of the pixels beyond summation-order tolerance, relRMSE %.5f (noise %.5f), mean Y rel diff %.5f'
+          % (name, sched, frac, diff, noise, mean_rel))
+    if name in ('scene0', 'scene1', 'scene2'):
         assert frac <= 0.03
     assert diff <= 1.1 * noise + 1e-3
     assert mean_rel < 0.01
+
+
+# ---- fast mode is what gets benchmarked: gate it for BIAS, not only for noise ------------------------------------------
+def _mean_and_sigma(ptlib, mode, name, w, h, spp, spf, pl, first, options=None):
+    """Per-channel image means of a render and the standard error of those means, estimated from the spread of the
+    per-dispatch image means (each dispatch is an independent estimate with spf samples per pixel)."""
+    sc = ptlib.Scene.load(scene_path(name))
+    ubo = sc.pack_ubo()
+    p = sc.pack_params(1, w, h, spf, pl)
+    r = ptlib.Renderer(device=0, mode=mode, jit=2, options=options or {})
+    r.set_scene(ubo, sc.sdf_sources)
+    r.resize(w, h)
+    means = []
+    for j in range(spp // spf):
+        r.clear()
+        r.dispatch_sum(p, first + j * spf, spf)
+        r.finalize(p, spf)
+        means.append(r.read_xyz()[..., :3].astype(np.float64).mean(axis=(0, 1)))
+    r.close()
+    means = np.array(means)
+    return means.mean(axis=0), means.std(axis=0, ddof=1) / np.sqrt(len(means))
+
+
+@pytest.mark.parametrize('name,pl', [('scene0', 5), ('scene1', 5), ('scene9', 5), ('scene10', 5), ('scene8', 5), ('scene10', 32)])
+def test_fast_mode_is_unbiased_against_strict(ptlib, name, pl):
+    """96x64 at 4096 spp, disjoint sample indices, jit policy 2 and the default driver -- the configuration bench.py
+    times.  The per-channel image means of the fast build (MUFU sin/cos/ex2/lg2, rcp.approx, fma contraction, the
+    rewritten Emit / SpectralPowerDistribution algebra of shader.comp:1030-1055) must agree with the strict build's
+    within 3 sigma of the measured Monte-Carlo error of the difference AND within 0.5 %."""
+    w, h, spp, spf = 96, 64, 4096, 256
+    ms, ss = _mean_and_sigma(ptlib, ptlib.MODE_STRICT, name, w, h, spp, spf, pl, 0)
+    mf, sf = _mean_and_sigma(ptlib, ptlib.MODE_FAST, name, w, h, spp, spf, pl, 1 << 20)
+    sigma = np.sqrt(ss ** 2 + sf ** 2)
+    z = np.abs(mf - ms) / sigma
+    rel = np.abs(mf / ms - 1.0)
+    print('%s pl %d: strict mean XYZ %s, fast %s, |diff|/sigma %s, rel diff %s' % (name, pl, ms, mf, np.round(z, 2), np.round(rel, 5)))
+    assert (z < 3.0).all() or (rel < 0.001).all(), (z, rel)
+    assert (rel < 0.005).all(), rel
+
+
+@pytest.mark.parametrize('name', ['scene0', 'scene1', 'scene9', 'scene10', 'scene8'])
+def test_converged_gate(ptlib, name):
+    """SURVEY section 8d's converged gate at reduced size: relRMSE against a STRICT 16384-spp reference with disjoint
+    sample indices -- fast at 256 spp must be within 5 % of strict at 256 spp.  A biased fast build would stall above."""
+    w, h = 64, 48
+    ref = render_with(ptlib, {}, name, w, h, 16384, 256, 5, ptlib.MODE_STRICT, 2, first=1 << 20)[0]
+    strict = render_with(ptlib, {}, name, w, h, 256, 64, 5, ptlib.MODE_STRICT, 2, first=0)[0]
+    fast = render_with(ptlib, {}, name, w, h, 256, 64, 5, ptlib.MODE_FAST, 2, first=0)[0]
+    es, ef = rel_rmse(strict, ref), rel_rmse(fast, ref)
+    print('%s: relRMSE vs strict 16k-spp reference: strict %.4f, fast %.4f' % (name, es, ef))
+    assert ef <= 1.05 * es + 1e-3
+
+
+# ---- the CUDA path against the reference's own shader source (oracle/_ref, prebuilt: it travels with the repo) -----------
+@pytest.mark.parametrize('name', ['scene0', 'scene1', 'scene9', 'scene10', 'scene8'])
+def test_cuda_against_the_reference_shader(ptlib, renderer, name):
+    """Strict CUDA kernel vs src/shader.comp compiled for the CPU over glm (oracle/ref_build.py), same sample indices:
+    the images differ only by the paths that fork on ulp-level differences of two legal float realisations (libm vs
+    pt_math.h, v * inversesqrt vs v / length) -- a small fraction of the Monte-Carlo floor."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip('oracle/_ref was not prebuilt and /root/reference is absent')
+    w, h, spp, spf = 48, 32, 32, 8
+    got, ubo, p, src = gpu_render(ptlib, renderer, name, w, h, spp, spf)
+    rs = ref.RefScene(scene_path(name))
+    theirs = rs.render(w, h, spp, spf)
+    other = oracle.Oracle(ubo, src)
+    q = np.array(p, copy=True)
+    b = np.zeros((h, w, 4), np.float32)
+    for j in range(1, spp // spf + 1):
+        q['frame'] = (1 << 20) + j * spf
+        q['currentSamples'] = j * spf
+        other.dispatch(q, b)
+    floor, d = rel_rmse(b, got), rel_rmse(got, theirs)
+    print('%s: relRMSE(CUDA strict, reference shader) %.4f, Monte-Carlo floor %.4f' % (name, d, floor))
+    assert d < 0.25 * floor
+    assert abs(float(got[..., 1].mean()) / float(theirs[..., 1].mean()) - 1) < 0.01
 
 
 # ---- BVH (pt_bvh.h): the same closest-hit search as the reference's scan, section 8f-3 ---------------------------------
@@ -680,26 +710,3 @@ def test_native_multi_gpu_errors(ptlib):
     with pytest.raises(ptlib.PtError):       # no image yet
         m.render(sc.pack_params(1, 32, 32, 1, 5), 0, 4, 2)
     m.close()
-
-
-# ---- driver v3s (v3's flat loop with v2s' sample pool): verified on the host emulator first, here on the device ----------
-@pytest.mark.parametrize('name,w,h,spp,spf,pl,jit,steal_s,regen_t', [
-    ('scene0', 96, 64, 8, 4, 5, 2, 16, 16), ('scene1', 70, 45, 40, 20, 5, 2, 16, 8), ('scene2', 33, 17, 9, 9, 5, 2, 4, 4),
-    ('scene1', 96, 72, 6, 3, 32, 1, 2, 16), ('scene10', 64, 48, 4, 2, 5, 2, 16, 16)])
-def test_v3s_driver_strict_bit_exact(ptlib, monkeypatch, name, w, h, spp, spf, pl, jit, steal_s, regen_t):
-    """PT_SCHED=7: whichever lane runs a sample, Scene() depends only on (pixel, sample index); each pixel's samples are
-    added in index order at the end of a round -- the oracle's bits (several rounds, ragged sizes, pathLength 32)."""
-    monkeypatch.setenv('PT_SCHED', '7')
-    monkeypatch.setenv('PT_STEAL_S', str(steal_s))
-    monkeypatch.setenv('PT_REGEN_T', str(regen_t))
-    sc = ptlib.Scene.load(scene_path(name))
-    ubo = sc.pack_ubo()
-    p = sc.pack_params(1, w, h, spf, pl)
-    r = ptlib.Renderer(device=0, mode=ptlib.MODE_STRICT, jit=jit)
-    r.set_scene(ubo, sc.sdf_sources)
-    r.resize(w, h)
-    r.render(p, spp, spf)
-    got = r.read_xyz()
-    r.close()
-    ref = oracle.Oracle(ubo, [s.decode() for s in sc.sdf_sources]).render(p, spp, spf)
-    assert_bit_equal(got, ref, '%s v3s S=%d T=%d' % (name, steal_s, regen_t))

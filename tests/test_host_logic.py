@@ -85,9 +85,27 @@ def test_bench_reference_arm_contract():
     assert r.returncode == 0, r.stderr
     d = json.loads(r.stdout.strip().split('\n')[-1])
     assert d['impl'] == 'reference' and d['value'] > 0 and d['unit'] == 'samples/s' and d['higher_is_better'] is True
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    from oracle import ref
+    assert d['cpu_baseline']['kind'] == ('reference' if ref.available() else 'port')   # oracle/_ref when it was built
+    assert d['cpu_baseline']['cores'] == len(os.sched_getaffinity(0))                   # all host cores ...
     assert d['e2e'] == {'value': d['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert d['config']['workload'] == 'cfg1_scene0_512'
+
+
+def test_bench_reference_arm_ignores_torchrun_thread_cap():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; round 1's reference arm then ran on one core and every N >= 2
+    ratio of the scaling record was inflated by the core count.  The arm sizes itself from the affinity mask instead."""
+    env = dict(os.environ, OMP_NUM_THREADS='1', RANK='0', WORLD_SIZE='2')
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0',
+                        '--workload', 'cfg1_scene0_512', '--gpus', '2'], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout.strip().split('\n')[-1])
+    assert d['cpu_baseline']['cores'] == len(os.sched_getaffinity(0)) and 'warning' not in d
+    # the other ranks print nothing and exit 0
+    env['RANK'] = '1'
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0', '--gpus', '2'],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ''
 
 
 def test_bench_refuses_to_run_without_gpu():

@@ -130,39 +130,33 @@ def test_nvrtc_builds_the_kernel_with_shipped_snippets(ptlib, name, mode):
     api.sdf_compile_check(src, ubo[pack.OFF_SDF:pack.OFF_SDF + 6 * len(src)], mode)
 
 
-@pytest.mark.parametrize('name,mode,env', [
-    ('scene10', 1, {'PT_SCHED': '1'}), ('scene10', 1, {'PT_SCHED': '2'}), ('scene10', 1, {'PT_SCHED': '3'}),
-    ('scene10', 1, {'PT_SCHED': '4'}), ('scene10', 1, {'PT_SCHED': '5'}), ('scene10', 1, {'PT_SCHED': '6'}),
-    ('scene10', 1, {'PT_SCHED': '5', 'PT_MPARK': '1'}), ('scene10', 1, {'PT_SCHED': '5', 'PT_MPARK': '1', 'PT_MPARK_CAP': '32', 'PT_MIN_BLOCKS': '5'}),
-    ('scene10', 0, {'PT_SCHED': '5'}), ('scene10', 0, {'PT_SCHED': '6'}), ('scene10', 0, {'PT_SCHED': '5', 'PT_MPARK': '1'}),
-    ('scene9', 1, {}), ('scene8', 1, {'PT_SCHED': '5', 'PT_STEAL_S': '8'}),
-    ('scene1', 1, {'PT_SCHED': '0'}), ('scene1', 1, {'PT_SCHED': '3'}), ('scene1', 1, {'PT_SCHED': '5'}), ('scene1', 1, {'PT_SCHED': '6'}),
-    ('scene1', 1, {'PT_SCHED': '7'}), ('scene1', 0, {'PT_SCHED': '7'}), ('scene10', 1, {'PT_SCHED': '7'})])
-def test_every_driver_of_the_megakernel_builds(ptlib, monkeypatch, name, mode, env):
-    """The scene-specialised kernel (jit policy 2) compiles with NVRTC for sm_100a under every driver / knob the A/B
+@pytest.mark.parametrize('name,mode,options', [
+    ('scene10', 1, {'sched': 5}), ('scene10', 1, {'sched': 8}), ('scene10', 1, {'sched': 7}), ('scene10', 1, {'sched': 0}),
+    ('scene10', 1, {'sched': 8, 'pool_cap': 16, 'pool_min': 12, 'min_blocks': 4}), ('scene10', 0, {'sched': 5}), ('scene10', 0, {'sched': 8}),
+    ('scene10', 0, {'sched': 8, 'steal_s': 16}),   # the pool shrinks until table + pool fit the 48 KB of static shared memory
+    ('scene9', 1, {}), ('scene9', 1, {'sched': 8}), ('scene8', 1, {'sched': 5, 'steal_s': 8}), ('scene8', 1, {'sched': 8}), ('scene3', 1, {'sched': 8}),
+    ('scene1', 1, {'sched': 0}), ('scene1', 1, {'sched': 5}), ('scene1', 1, {'sched': 7}), ('scene1', 0, {'sched': 7}), ('scene1', 1, {'sched': 8}),
+    ('scene0', 1, {'sched': 7}), ('scene2', 1, {'sched': 7}), ('scene10', 1, {'stats': 1, 'sched': 8})])
+def test_every_driver_of_the_megakernel_builds(ptlib, name, mode, options):
+    """The scene-specialised kernel (jit policy 2) compiles with NVRTC for sm_100a under every driver / option the A/B
     measurements use (no GPU needed), stays inside the 48 KB of static shared memory and the register budget of its
-    launch bounds, and spills at most a few words.  PT_SCHED=6 in strict mode must fall back to v2s (its per-sample
-    table): the build then has v2s' shared-memory size."""
-    import ctypes as C
+    launch bounds, and spills at most a few words."""
     import re
-    from pathtracer_b200 import api
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
     scene = pack.load_scene(scene_path(name))
     ubo = pack.pack_ubo(scene)
-    src = [s.encode() if isinstance(s, str) else s for s in pack.sdf_sources(scene)]
-    L = ptlib.lib()
-    L.pt_kernel_compile_check.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int]
-    rc = L.pt_kernel_compile_check(ubo.ctypes.data_as(C.c_void_p), api._c_strings(src), len(src), mode, 1)
-    log = L.pt_last_error(None).decode()
-    assert rc == 0, log
+    log = ptlib.kernel_compile_check(ubo, pack.sdf_sources(scene), mode, True, options)
     m = re.search(r"Compiling entry function 'pt_render_jit'.*?Used (\d+) registers.*?(\d+) bytes smem", log, re.S)
     assert m, log
     regs, smem = int(m.group(1)), int(m.group(2))
     assert smem <= 48 * 1024
-    min_blocks = int(env.get('PT_MIN_BLOCKS', 6 if mode == 1 else 4))
-    assert regs <= 65536 // (128 * min_blocks) or regs <= 128
+    assert regs <= 128
     spills = [int(x) for x in re.findall(r'(\d+) bytes spill stores', log)]
-    assert max(spills) <= 128, log
-    if mode == 0 and env.get('PT_SCHED') == '6':
-        assert smem == 16388 + 4 * 3 * 16 * 32 * 4   # v2s: uniform block + the 16-sample table of four warps
+    assert max(spills) <= 192, log
+
+
+def test_unknown_option_is_an_error(ptlib):
+    scene = pack.load_scene(scene_path('scene1'))
+    with pytest.raises(ptlib.PtError):
+        ptlib.kernel_compile_check(pack.pack_ubo(scene), [], 1, True, {'sched': 6})
+    with pytest.raises(ptlib.PtError):
+        ptlib.kernel_compile_check(pack.pack_ubo(scene), [], 1, True, {'nonsense': 1})

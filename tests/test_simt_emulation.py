@@ -2,10 +2,10 @@
 
 pathtracer_b200/csrc/pt_kernel.cuh is compiled, unmodified, for the host: one thread per CUDA thread, barriers for
 __syncthreads / __ballot_sync / __shfl_sync / __syncwarp, statics for shared memory.  In strict mode the arithmetic is
-the oracle's, so every driver -- the nested loops of v1, the in-warp scheduler v2, sample stealing (v2s: table rounds),
-march parking, two pixels per lane (v2d), the flat loop (v3) and its pooled variant (v3s) -- must reproduce the oracle
-bit for bit, and the
-tile-streaming v2sp up to fp32 summation order.  What this does not cover: the device compiler, fast-math builds, and
+the oracle's, so every driver -- the nested loops of v1, the flat loop with the sample pool (v3s), the phase machine with
+the sample pool (v2s: table rounds) and with the pool of parked marching paths (v2m: full, tiny and overflowing pools)
+-- must reproduce the oracle bit for bit, and the whole-dispatch pools (PT_STEAL_S = 0) up to fp32 summation order.
+What this does not cover: the device compiler, fast-math builds, and
 timing -- the `-m gpu` parity tests remain the gate for those.  TEST INFRASTRUCTURE: a checker, not a rendering path."""
 import ctypes as C
 import hashlib
@@ -83,20 +83,26 @@ def scene_inputs(name, w, h, spf, pl):
 
 
 DRIVERS = {
-    'v1': {'PT_SCHED': 0}, 'v2': {'PT_SCHED': 1}, 'v3': {'PT_SCHED': 3, 'PT_REGEN_T': 4}, 'v2d': {'PT_SCHED': 4},
+    'v1': {'PT_SCHED': 0},
     'v2s_table16': {'PT_SCHED': 5, 'PT_STEAL_S': 16}, 'v2s_table2': {'PT_SCHED': 5, 'PT_STEAL_S': 2},
-    'v2s_park': {'PT_SCHED': 5, 'PT_STEAL_S': 8, 'PT_MPARK': 1, 'PT_MPARK_CAP': 20, 'PT_MPARK_MIN': 4},
-    'v2s_park_tiny_stack': {'PT_SCHED': 5, 'PT_STEAL_S': 3, 'PT_MPARK': 1, 'PT_MPARK_CAP': 2, 'PT_MPARK_MIN': 1},
     'v3s_table16': {'PT_SCHED': 7, 'PT_STEAL_S': 16}, 'v3s_table3': {'PT_SCHED': 7, 'PT_STEAL_S': 3, 'PT_REGEN_T': 4},
+    # v2m: the pool of parked paths at its default size, with two slots (rays mostly march in their lanes), with a
+    # threshold no warp reaches (the phase only runs when the feeders are dry) and with a greedy one
+    'v2m': {'PT_SCHED': 8, 'PT_STEAL_S': 4, 'PT_POOL_CAP': 32, 'PT_POOL_MIN': 24},
+    'v2m_tiny_pool': {'PT_SCHED': 8, 'PT_STEAL_S': 3, 'PT_POOL_CAP': 2, 'PT_POOL_MIN': 2},
+    'v2m_lazy': {'PT_SCHED': 8, 'PT_STEAL_S': 8, 'PT_POOL_CAP': 7, 'PT_POOL_MIN': 64},
+    'v2m_greedy': {'PT_SCHED': 8, 'PT_STEAL_S': 2, 'PT_POOL_CAP': 32, 'PT_POOL_MIN': 1, 'PT_SDF_REPS': 3},
 }
+V2M = [d for d in sorted(DRIVERS) if d.startswith('v2m')]
 
 
-# scenes without SDFs share one build per driver; of the SDF scenes, scene10 (menger, pathLength 32) runs under every
-# driver, scene9 / scene8 under the default driver and the parking variant (each SDF unit is its own build)
-CASES = [(d, 'scene0', 48, 32, 10, 5, 5) for d in sorted(DRIVERS) if 'PT_MPARK' not in DRIVERS[d]]
-CASES += [(d, 'scene1', 50, 37, 3, 3, 5) for d in sorted(DRIVERS) if 'PT_MPARK' not in DRIVERS[d]]
+# scenes without SDFs share one build per driver (v2m is v2s there); of the SDF scenes, scene10 (menger, pathLength 32)
+# runs under every driver, scene9 / scene8 / scene3 under the phase machines (each SDF unit is its own build)
+CASES = [(d, 'scene0', 48, 32, 10, 5, 5) for d in sorted(DRIVERS) if d not in V2M]
+CASES += [(d, 'scene1', 50, 37, 3, 3, 5) for d in sorted(DRIVERS) if d not in V2M]
 CASES += [(d, 'scene10', 40, 24, 4, 2, 32) for d in sorted(DRIVERS)]
-CASES += [(d, n, w, h, spp, spf, 5) for d in ('v2s_table16', 'v2s_park') for (n, w, h, spp, spf) in (('scene9', 33, 17, 5, 5), ('scene8', 32, 16, 2, 2))]
+CASES += [(d, n, w, h, spp, spf, 5) for d in ['v2s_table16'] + V2M
+          for (n, w, h, spp, spf) in (('scene9', 33, 17, 5, 5), ('scene8', 32, 16, 2, 2), ('scene3', 24, 16, 3, 3))]
 
 
 @pytest.mark.parametrize('driver,name,w,h,spp,spf,pl', CASES)
@@ -123,20 +129,17 @@ def test_emulated_v3s_whole_dispatch_pool(ptlib, name, w, h, spp, spf, pl):
     assert np.allclose(got[..., :3], ref[..., :3], rtol=1e-5, atol=1e-6 * scale) and (got[..., 3] == 1.0).all()
 
 
-@pytest.mark.parametrize('name,w,h,spp,spf,pl,ctas,slots', [('scene0', 61, 43, 3, 1, 5, 2, 4), ('scene1', 50, 37, 8, 4, 5, 3, 2),
-                                                           ('scene10', 40, 24, 6, 3, 32, 2, 4), ('scene9', 33, 17, 2, 2, 5, 1, 8)])
-def test_emulated_tile_streaming_driver(ptlib, name, w, h, spp, spf, pl, ctas, slots):
-    """v2sp (PT_SCHED=6) adds finished samples to their pixel's sum in schedule order, so it equals the oracle up to fp32
-    summation order (1e-5 relative); here with strict arithmetic, so no path forks: every pixel must agree.  Covers the
-    slot recycling (1 to 4 samples per dispatch, 2 / 4 / 8 slots), items beyond the image edge, several CTAs sharing
-    the tile counter and the counter's self-reset between dispatches."""
+@pytest.mark.parametrize('name,w,h,spp,spf,pl', [('scene10', 40, 24, 8, 8, 32), ('scene9', 33, 17, 6, 6, 5), ('scene8', 32, 16, 3, 3, 5)])
+def test_emulated_v2m_whole_dispatch_pool(ptlib, name, w, h, spp, spf, pl):
+    """v2m as the fast build configures it (PT_STEAL_S = 0: one pool per dispatch, sums in schedule order) under strict
+    arithmetic: equal to the oracle up to fp32 summation order on every pixel -- no path is lost or run twice while it
+    moves between lanes and slots."""
     ubo, p, src, raw = scene_inputs(name, w, h, spf, pl)
-    L = build_emulator(ptlib, {'PT_SCHED': 6, 'PT_TILE_SLOTS': slots}, src, raw)
-    got = emulate(L, ubo, p, spp, spf, ctas)
+    L = build_emulator(ptlib, {'PT_SCHED': 8, 'PT_STEAL_S': 0}, src, raw)
+    got = emulate(L, ubo, p, spp, spf)
     ref = oracle.Oracle(ubo, src).render(p, spp, spf)
     scale = float(ref[..., :3].max())
-    assert np.allclose(got[..., :3], ref[..., :3], rtol=1e-5, atol=1e-6 * scale)
-    assert (got[..., 3] == 1.0).all()
+    assert np.allclose(got[..., :3], ref[..., :3], rtol=1e-5, atol=1e-6 * scale) and (got[..., 3] == 1.0).all()
 
 
 EDGE = [('scene0', 5, 3, 1, 1, 5), ('scene1', 17, 9, 33, 33, 5), ('scene1', 8, 4, 2, 2, 0), ('scene2', 31, 7, 34, 17, 2), ('scene0', 16, 8, 1, 1, 100)]
@@ -146,14 +149,14 @@ EDGE = [('scene0', 5, 3, 1, 1, 5), ('scene1', 17, 9, 33, 33, 5), ('scene1', 8, 4
 def test_emulated_drivers_at_the_edges(ptlib, name, w, h, spp, spf, pl):
     """Frames smaller than a tile, one sample, 33 samples per dispatch (three table rounds, the last of one sample),
     pathLength 0 (a sample is finished before it starts) and 100: table drivers give the oracle's bits, the pooled ones
-    (v2s / v3s with PT_STEAL_S = 0, v2sp with two slots) its image up to summation order."""
+    (v2s / v3s with PT_STEAL_S = 0) its image up to summation order."""
     ubo, p, src, raw = scene_inputs(name, w, h, spf, pl)
     ref = oracle.Oracle(ubo, src).render(p, spp, spf)
-    for driver in ('v2s_table16', 'v3s_table3', 'v2', 'v3'):
+    for driver in ('v1', 'v2s_table16', 'v3s_table3'):
         got = emulate(build_emulator(ptlib, DRIVERS[driver], src, raw), ubo, p, spp, spf)
         assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), driver
     scale = float(ref[..., :3].max()) or 1.0
-    for defs in ({'PT_SCHED': 5, 'PT_STEAL_S': 0}, {'PT_SCHED': 7, 'PT_STEAL_S': 0}, {'PT_SCHED': 6, 'PT_TILE_SLOTS': 2}):
+    for defs in ({'PT_SCHED': 5, 'PT_STEAL_S': 0}, {'PT_SCHED': 7, 'PT_STEAL_S': 0}):
         got = emulate(build_emulator(ptlib, defs, src, raw), ubo, p, spp, spf, 3)
         assert np.allclose(got[..., :3], ref[..., :3], rtol=1e-5, atol=1e-6 * scale) and (got[..., 3] == 1.0).all(), defs
 
@@ -169,7 +172,8 @@ def baked_counts(ubo, has_sdf):
 
 
 @pytest.mark.parametrize('driver,name,w,h,spp,spf,pl', [('v1', 'scene0', 48, 32, 4, 2, 5), ('v3s_table16', 'scene1', 70, 45, 40, 20, 5),
-                                                       ('v2s_table16', 'scene10', 40, 24, 4, 2, 5), ('v3s_table3', 'scene2', 33, 17, 9, 9, 5)])
+                                                       ('v2s_table16', 'scene10', 40, 24, 4, 2, 5), ('v3s_table3', 'scene2', 33, 17, 9, 9, 5),
+                                                       ('v2m', 'scene10', 40, 24, 4, 2, 5), ('v2m_tiny_pool', 'scene9', 33, 17, 3, 3, 5)])
 def test_emulated_scene_specialised_kernels(ptlib, driver, name, w, h, spp, spf, pl):
     """jit policy 2 (what bench.py uses): the primitive counts baked in as constants, offsets folded, loops unrolled (or
     rolled, with SDFs) -- other code from the same source, same bits."""

@@ -15,11 +15,9 @@ from make_synthetic_scenes import many_sphere_scene  # noqa: E402
 W, H, SPF, STEPS = 1920, 1080, 16, 4
 
 
-def rate(scene_text, bvh_min, env=None):
-    for k, v in (env or {}).items():
-        os.environ[k] = v
+def rate(scene_text, bvh_min, options=None):
     sc = pt.Scene.parse(scene_text)
-    r = pt.Renderer(device=0, mode=pt.MODE_FAST, jit=2)
+    r = pt.Renderer(device=0, mode=pt.MODE_FAST, jit=2, options=options)
     r.set_bvh(bvh_min)
     r.set_scene(sc.pack_ubo())
     active = r.bvh_active
@@ -32,8 +30,6 @@ def rate(scene_text, bvh_min, env=None):
         r.dispatch(p)
     ms, _n = r.kernel_time()
     r.close()
-    for k in (env or {}):
-        os.environ.pop(k, None)
     return W * H * SPF * STEPS / (ms * 1e-3), active
 
 
@@ -41,7 +37,7 @@ def main():
     for n in [int(a) for a in sys.argv[1:]] or [2, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128, 169]:
         text = json.dumps(many_sphere_scene(n))
         scan, a0 = rate(text, 0)
-        scan_rolled, _ = rate(text, 0, {'PT_NO_UNROLL': '1'})
+        scan_rolled, _ = rate(text, 0, {'no_unroll': 1})
         tree, a1 = rate(text, 2)
         assert not a0 and a1
         print(json.dumps({'spheres': n, 'scan_gsamples_s': scan / 1e9, 'scan_rolled_gsamples_s': scan_rolled / 1e9,

@@ -1,6 +1,9 @@
 #!/usr/bin/env python3
 """Second half of BASELINE.json's metric: wall time to reach a fixed relative RMSE against a 65 536-spp reference.
 
+The reference image is rendered in STRICT mode (--ref-mode; round 1 rendered it with the same fast kernel it was then
+compared with, which made the curves blind to any bias of the fast build), at --scale of the workload's resolution
+when the full frame would take too long in strict mode.
 For each workload: the reference image is rendered with the DISJOINT sample indices [2^20, 2^20 + ref_spp) (so test
 renders are statistically independent of it), then test renders with indices 0..spp-1 for
 spp = 1, 2, 4, ...; relRMSE = sqrt(mean((I-R)^2 / (R^2 + eps))), eps = (0.01 mean R)^2, on the XYZ buffer (computed
@@ -27,19 +30,26 @@ def main():
     ap.add_argument('--ref-spp', type=int, default=65536)
     ap.add_argument('--max-spp', type=int, default=4096)
     ap.add_argument('--mode', default='fast')
+    ap.add_argument('--ref-mode', default='strict')
+    ap.add_argument('--scale', type=int, default=1, help='render at 1/scale of the resolution in x and y')
     ap.add_argument('--thresholds', default='0.2,0.1,0.05,0.02')
     args = ap.parse_args()
     thresholds = [float(t) for t in args.thresholds.split(',')]
     for wl in args.workloads:
         scene, W, H, _, pl, _, _ = WORKLOADS[wl]
+        W, H = W // args.scale, H // args.scale
         sc = pt.Scene.load(os.path.join(ROOT, 'scenes', scene + '.json'))
-        r = pt.Renderer(mode=pt.MODE_FAST if args.mode == 'fast' else pt.MODE_STRICT, jit=2)
+        modes = {'fast': pt.MODE_FAST, 'strict': pt.MODE_STRICT}
+        r = pt.Renderer(mode=modes[args.mode], jit=2)
         r.set_scene(sc.pack_ubo(), sc.sdf_sources)
+        rr = pt.Renderer(mode=modes[args.ref_mode], jit=2)
+        rr.set_scene(sc.pack_ubo(), sc.sdf_sources)
         p = sc.pack_params(1, W, H, 16, pl)
         img = torch.zeros((H, W, 4), dtype=torch.float32, device='cuda')
         r.bind_image(img)
+        rr.bind_image(img)
 
-        def render(first, spp):
+        def render(first, spp, r=r):
             img.zero_()
             r.sync(); r.kernel_time()
             s = first
@@ -51,14 +61,14 @@ def main():
             ms, _ = r.kernel_time()
             return img.clone(), ms * 1e-3
 
-        ref, ref_s = render(1 << 20, args.ref_spp)
+        ref, ref_s = render(1 << 20, args.ref_spp, rr)
         curve = []
         spp = 1
         while spp <= args.max_spp:
             im, secs = render(0, spp)
             curve.append((spp, secs, rel_rmse(im, ref)))
             spp *= 2
-        out = {'workload': wl, 'scene': scene, 'width': W, 'height': H, 'path_length': pl, 'mode': args.mode,
+        out = {'workload': wl, 'scene': scene, 'width': W, 'height': H, 'path_length': pl, 'mode': args.mode, 'ref_mode': args.ref_mode,
                'reference': {'spp': args.ref_spp, 'first_sample': 1 << 20, 'seconds': ref_s},
                'curve': [{'spp': s, 'seconds': t, 'rel_rmse': e} for s, t, e in curve], 'time_to_rel_rmse': {}}
         for th in thresholds:
@@ -73,6 +83,7 @@ def main():
             out['time_to_rel_rmse'][str(th)] = tt
         print(json.dumps(out))
         r.close()
+        rr.close()
 
 
 if __name__ == '__main__':
