@@ -173,6 +173,41 @@ PT_HD float pt_log2(float x) {
     return pt_fma(s, p, (float)e);
 }
 
+/* ---- asin / atan / atan2 / tan (not used by shader.comp or the shipped snippets; third-party SDF code uses them) ------ */
+PT_HD float pt_asin(float x) {
+    float a = pt_abs(x);
+    if (!(a <= 1.0f)) return pt_u2f(0x7fc00000u);
+    if (a <= 0.5f) return pt__asin_poly(x);
+    float s = pt_sqrt(pt_mul(pt_sub(1.0f, a), 0.5f)); /* asin(a) = pi/2 - 2 asin(sqrt((1-a)/2)) */
+    float t = pt_sub(PT_PIO2_F, pt_mul(2.0f, pt__asin_poly(s)));
+    return (x < 0.0f) ? -t : t;
+}
+/* atan: Cephes' single-precision scheme -- reduce to |r| <= tan(pi/8) (r = -1/a above tan(3pi/8), (a-1)/(a+1) above
+ * tan(pi/8)), then r + r^3 P(r^2) with its four published coefficients; <= 2 ulp */
+PT_HD float pt_atan(float x) {
+    if (!(x == x)) return x;
+    float a = pt_abs(x), base = 0.0f, r = a;
+    if (a > 2.414213562373095f) { base = PT_PIO2_F; r = pt_div(-1.0f, a); }
+    else if (a > 0.4142135623730950f) { base = 7.853981853e-01f; r = pt_div(pt_sub(a, 1.0f), pt_add(a, 1.0f)); }
+    float z = pt_mul(r, r);
+    float p = pt_fma(z, 8.05374449538e-2f, -1.38776856032e-1f);
+    p = pt_fma(z, p, 1.99777106478e-1f);
+    p = pt_fma(z, p, -3.33329491539e-1f);
+    float y = pt_add(base, pt_fma(pt_mul(p, z), r, r));
+    return (x < 0.0f) ? -y : y;
+}
+/* GLSL atan(y, x): the angle of (x, y) in (-pi, pi]; atan(0, 0) is undefined in GLSL, 0 here */
+PT_HD float pt_atan2(float y, float x) {
+    if (!(x == x) || !(y == y)) return pt_u2f(0x7fc00000u);
+    if (x == 0.0f) return (y > 0.0f) ? PT_PIO2_F : ((y < 0.0f) ? -PT_PIO2_F : 0.0f);
+    float t = pt_atan(pt_div(y, x));
+    if (x > 0.0f) return t;
+    return (y < 0.0f) ? pt_sub(t, PT_PI_F) : pt_add(t, PT_PI_F);
+}
+PT_HD float pt_sin(float x);
+PT_HD float pt_cos(float x);
+PT_HD float pt_tan(float x) { return pt_div(pt_sin(x), pt_cos(x)); }
+
 /* ---- the GLSL transcendental set, per App. F --------------------------------------------------------------- */
 PT_HD float pt_exp(float x) { return pt_exp2(pt_mul(x, 1.442695022e+00f)); }
 PT_HD float pt_log(float x) { return pt_mul(pt_log2(x), 6.931471825e-01f); }

@@ -270,6 +270,23 @@ def _strip_comments(s):
     return re.sub(r'//[^\n]*', '', s)
 
 
+def _array_constructors(s):
+    """GLSL `float[3](a, b, c)` / `vec2[](u, v)` -> C++ braced initialisers"""
+    out, i = [], 0
+    rx = re.compile(r'\b(?:float|int|uint|bool|[iub]?vec[234]|mat[234])\s*\[\s*\d*\s*\]\s*\(')
+    while True:
+        m = rx.search(s, i)
+        if not m:
+            out.append(s[i:])
+            return ''.join(out)
+        depth, j = 1, m.end()
+        while depth and j < len(s):
+            depth += {'(': 1, ')': -1}.get(s[j], 0)
+            j += 1
+        out.append(s[i:m.start()] + '{' + _array_constructors(s[m.end():j - 1]) + '}')
+        i = j
+
+
 def _swizzle_stores(s):
     """`v.xy = E;` / `v.zw -= E;` -> swz_store<..>(v, E): glm's function-style swizzles are rvalues only."""
     def repl(m):
@@ -279,6 +296,18 @@ def _swizzle_stores(s):
             rhs = '%s.%s %s (%s)' % (var, sw, op[0], rhs)
         return 'swz_store%d<%s>(%s, %s);' % (len(sw), idx, var, rhs)
     return re.sub(r'\b(\w+)\.([xyzw]{2,4})\s*(=|[-+*/]=)(?!=)\s*([^;]+);', repl, s)
+
+
+def _xyzw_spelling(s):
+    """rgba / stpq swizzles spelled as xyzw (glm's function-style swizzles exist for all three; one spelling keeps the
+    store rewrite simple)"""
+    def repl(m):
+        w = m.group(1)
+        for alphabet in ('rgba', 'stpq'):
+            if all(c in alphabet for c in w):
+                return '.' + ''.join('xyzw'[alphabet.index(c)] for c in w)
+        return m.group(0)
+    return re.sub(r'\.([rgbastpq]{1,4})\b(?!\s*\()', repl, s)
 
 
 def _split_args(text):
@@ -378,6 +407,12 @@ def translate_shader(glsl):
     mats = set(re.findall(r'\bmat[234]\s+(\w+)\s*[=;,)]', s))
     if mats:
         s = re.sub(r'\b([\w.]+)\s*\*=\s*(%s)\s*;' % '|'.join(sorted(mats)), r'\1 = \1 * \2;', s)
+    s = _array_constructors(s)
+    # rgba / stpq spellings occur in SDF snippets only; the shader's own structs have members named a, b, c, d
+    a, b = s.find('vec2 smin('), s.find('float SDF(')
+    if 0 <= a < b:
+        a = s.index('}', a) + 1
+        s = s[:a] + _xyzw_spelling(s[a:b]) + s[b:]
     s = _swizzle_stores(s)
     s = re.sub(r'\.([xyzw]{2,4})\b(?!\s*\()', r'.\1()', s)
     s, n = re.subn(r'\bvoid\s+main\s*\(\s*\)', 'void shader_main()', s)

@@ -5,7 +5,8 @@ GLSL -> C++ rewrite needed to compile the snippets with g++ against include/pt_g
   * first "sdf" substring -> SDF{i+1}, then first "sdfmaterial" -> SDF{i+1}MATERIAL      (host:2015-2017)
   * dispatcher lines, SDF 1 first, the material line before the distance line            (host:2046-2051)
   * float literals get an `f` suffix, `in` qualifiers vanish, `out/inout T x` -> `T& x`, multi-letter swizzles
-    become swizzle calls.
+    become swizzle calls (`.sw3<0,2,1>()` reads, `.lsw2<0,2>()` in front of an assignment operator), array
+    constructors `T[n](..)` become braced initialisers; `#define` lines go through as they are.
 The product has its own C++ front-end (pathtracer_b200/csrc/pt_sdf_front.cpp); tests compare both on random points.
 """
 import hashlib
@@ -35,10 +36,40 @@ def translate_snippet(glsl, number):
     s = re.sub(r'//[^\n]*', '', s)
     s = re.sub(r'/\*.*?\*/', '', s, flags=re.S)
     s = _FLOAT.sub(lambda m: m.group(1) + 'f', s)
-    s = re.sub(r'\b(?:const\s+)?in\s+(?=(?:float|int|uint|bool|vec[234]|mat3)\b)', '', s)
-    s = re.sub(r'\b(?:inout|out)\s+(float|int|uint|bool|vec[234]|mat3)\s+', r'\1& ', s)
-    s = re.sub(r'\.([xyzw]{2,4})\b(?!\s*\()', r'.\1()', s)
+    s = re.sub(r'\b(?:const\s+)?in\s+(?=(?:float|int|uint|bool|vec[234]|mat[234])\b)', '', s)
+    s = re.sub(r'\b(?:inout|out)\s+(float|int|uint|bool|vec[234]|mat[234])\s+', r'\1& ', s)
+    s = _array_constructors(s)
+
+    def swz(m):
+        letters = m.group(1)
+        for alphabet in ('xyzw', 'rgba', 'stpq'):
+            if all(c in alphabet for c in letters):
+                idx = ','.join(str(alphabet.index(c)) for c in letters)
+                break
+        else:
+            return m.group(0)
+        kind = 'lsw' if m.group(2) else 'sw'
+        return '.%s%d<%s>()%s' % (kind, len(letters), idx, m.group(2) or '')
+    s = re.sub(r'\.([xyzwrgbastpq]{2,4})\b(?!\s*\()(\s*(?:[-+*/]=|=(?!=)))?', swz, s)
+    s = re.sub(r'\.([rgbastpq])\b(?!\s*\()', lambda m: '.' + 'xyzwxyzw'['rgbastpq'.index(m.group(1))], s)
     return s
+
+
+def _array_constructors(s):
+    """`float[3](a, b, c)` / `vec2[](u, v)` -> `{a, b, c}` (matching parenthesis found by depth counting)"""
+    out, i = [], 0
+    rx = re.compile(r'\b(?:float|int|uint|bool|vec[234]|mat[234])\s*\[\s*\d*\s*\]\s*\(')
+    while True:
+        m = rx.search(s, i)
+        if not m:
+            out.append(s[i:])
+            return ''.join(out)
+        depth, j = 1, m.end()
+        while depth and j < len(s):
+            depth += {'(': 1, ')': -1}.get(s[j], 0)
+            j += 1
+        out.append(s[i:m.start()] + '{' + _array_constructors(s[m.end():j - 1]) + '}')
+        i = j
 
 
 PRELUDE = r'''

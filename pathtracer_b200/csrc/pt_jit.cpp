@@ -49,7 +49,7 @@ std::string g_load_error;
 #define PT_DEFAULT_SCHED_SDF 5
 #endif
 #ifndef PT_DEFAULT_SCHED_ANALYTIC
-#define PT_DEFAULT_SCHED_ANALYTIC 0
+#define PT_DEFAULT_SCHED_ANALYTIC 7 /* v3s: 10.73 vs v1's 9.96 Gsamples/s on cfg2, 8.10 vs 7.62 on cfg1 (profiles/r02_gpu1) */
 #endif
 
 /* Process-wide cache of compiled kernels, keyed by the complete translation unit (which spells out the mode, the baked

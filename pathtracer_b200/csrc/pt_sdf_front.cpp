@@ -12,14 +12,24 @@
  * text against include/pt_glsl.h:
  *   * float literals get an `f` suffix (GLSL literals are 32-bit; unsuffixed C++ literals would be double)
  *   * parameter qualifiers: `in T x` -> `T x`, `out T x` / `inout T x` -> `T& x`; precision qualifiers vanish
- *   * multi-component swizzles `.xzy` -> `.xzy()` (rgba / stpq spellings are mapped to xyzw)
+ *   * multi-component swizzles: reads `.xzy` -> `.sw3<0,2,1>()`, writes `v.xz = e` / `v.xz *= m` -> `.lsw2<0,2>() = e`
+ *     (an lvalue proxy of pt_glsl.h); rgba / stpq spellings are mapped to xyzw
+ *   * array constructors `float[3](a, b, c)` / `vec2[](..)` -> braced initialisers
+ *   * `#define` / `#undef` / `#if*` lines pass through (every macro a snippet defines is #undef'ed after the snippets, so
+ *     it cannot reach the kernel text that follows); `#include`, `#pragma`, `#line`, `#error`, `#extension` are refused
  *   * comments are dropped.
  * Snippet text is otherwise passed through unchanged: mandelbulb / menger / blob / terrain load as shipped.
+ *
+ * Scene files are data, and in the reference their snippets were sandboxed GLSL.  Here the text ends up in a CUDA C++
+ * translation unit inside the host process's context, so everything GLSL does not have is refused before NVRTC sees it:
+ * pointers and references (unary `*` / `&`, `->`, `T*`), `::`, casts, `asm`, string / character literals, C++ keywords,
+ * and identifiers that reach into CUDA, libc or this library (`__*`, `cuda*`, `atomic*`, `threadIdx`, `printf`, `pt_*` ..).
  */
 #include <stdio.h>
 #include <string.h>
 
 #include <string>
+#include <vector>
 
 #include "pt_internal.h"
 
@@ -30,7 +40,7 @@ bool is_ident(char c) { return is_ident_start(c) || (c >= '0' && c <= '9'); }
 bool is_digit(char c) { return c >= '0' && c <= '9'; }
 
 bool is_type_name(const std::string& w) {
-    static const char* k[] = {"float", "int", "uint", "bool", "vec2", "vec3", "vec4", "mat3", nullptr};
+    static const char* k[] = {"float", "int", "uint", "bool", "vec2", "vec3", "vec4", "mat2", "mat3", "mat4", "void", nullptr};
     for (int i = 0; k[i]; i++)
         if (w == k[i]) return true;
     return false;
@@ -62,12 +72,33 @@ bool swizzle_letters(const std::string& w, std::string* mapped) {
     return false;
 }
 
-/* token-level GLSL -> C++/CUDA rewrite of one snippet */
-bool rewrite(const std::string& in, std::string* out, std::string* err) {
+/* words GLSL does not have (or reserves) and identifiers that would reach outside the snippet's sandbox */
+bool forbidden_word(const std::string& w) {
+    static const char* k[] = {"asm", "reinterpret_cast", "static_cast", "const_cast", "dynamic_cast", "new", "delete", "goto", "extern",
+                              "volatile", "typedef", "using", "namespace", "template", "typename", "class", "union", "enum", "sizeof",
+                              "alignof", "decltype", "auto", "operator", "this", "throw", "try", "catch", "friend", "virtual", "public",
+                              "private", "protected", "mutable", "register", "static", "inline", "constexpr", "nullptr", "char", "short",
+                              "long", "double", "unsigned", "signed", "printf", "malloc", "free", "assert", "memcpy", "memset", "threadIdx",
+                              "blockIdx", "blockDim", "gridDim", "warpSize", "clock", "clock64", "sdfs_raw", "ptglsl", nullptr};
+    for (int i = 0; k[i]; i++)
+        if (w == k[i]) return true;
+    if (w.size() >= 2 && w[0] == '_' && w[1] == '_') return true;
+    static const char* pre[] = {"cuda", "atomic", "pt_", "PT_", "ptk", "nvrtc", nullptr};
+    for (int i = 0; pre[i]; i++)
+        if (w.compare(0, strlen(pre[i]), pre[i]) == 0) return true;
+    return false;
+}
+
+/* token-level GLSL -> C++/CUDA rewrite of one snippet; macro names it #defines are appended to *macros */
+bool rewrite(const std::string& in, std::string* out, std::string* err, std::vector<std::string>* macros) {
     const std::string& s = in;
     std::string o;
     size_t i = 0;
     const size_t n = s.size();
+    /* last significant token: 'v' a value (identifier, literal, `)` or `]`), 't' a type name, 'o' anything after which an
+     * operand is expected.  A `*` or `&` where an operand is expected, or right after a type name, is a pointer. */
+    char last = 'o';
+    std::vector<char> closers; /* what each open `(` closes with: `)` or, for an array constructor, `}` */
     while (i < n) {
         const char c = s[i];
         if (c == '/' && i + 1 < n && s[i + 1] == '/') { /* line comment */
@@ -83,7 +114,34 @@ bool rewrite(const std::string& in, std::string* out, std::string* err) {
             i = e + 2;
             continue;
         }
-        if (c == '#') { *err = "preprocessor directives are not supported in SDF snippets"; return false; }
+        if (c == '#') { /* preprocessor: #define / #undef / conditionals pass through; the body is rewritten like any text */
+            size_t j = i + 1;
+            while (j < n && (s[j] == ' ' || s[j] == '\t')) j++;
+            size_t e = j;
+            while (e < n && is_ident(s[e])) e++;
+            const std::string d = s.substr(j, e - j);
+            if (!(d == "define" || d == "undef" || d == "if" || d == "ifdef" || d == "ifndef" || d == "else" || d == "elif" || d == "endif")) {
+                *err = "preprocessor directive #" + d + " is not supported in SDF snippets";
+                return false;
+            }
+            if (d == "define") {
+                const std::string name = peek_ident(s, e);
+                if (name.empty() || forbidden_word(name) || is_type_name(name)) { *err = "bad macro name in #define " + name; return false; }
+                macros->push_back(name);
+            }
+            o.push_back('#');
+            o += d;
+            i = e;
+            last = 'o';
+            continue;
+        }
+        if (c == '"' || c == '\'') { *err = "string and character literals are not GLSL"; return false; }
+        if (c == ':' && i + 1 < n && s[i + 1] == ':') { *err = "'::' is not GLSL"; return false; }
+        if (c == '-' && i + 1 < n && s[i + 1] == '>') { *err = "'->' is not GLSL"; return false; }
+        if ((c == '*' || c == '&') && !(i + 1 < n && s[i + 1] == '=') && !(c == '&' && i + 1 < n && s[i + 1] == '&') &&
+            !(c == '&' && i > 0 && s[i - 1] == '&')) {
+            if (last != 'v') { *err = std::string("unary '") + c + "' (pointers / references) is not GLSL"; return false; }
+        }
         if (is_digit(c) || (c == '.' && i + 1 < n && is_digit(s[i + 1]))) { /* numeric literal */
             size_t j = i;
             bool is_float = false, is_hex = false;
@@ -117,6 +175,7 @@ bool rewrite(const std::string& in, std::string* out, std::string* err) {
                 j++;
             }
             i = j;
+            last = 'v';
             continue;
         }
         if (is_ident_start(c)) {
@@ -124,6 +183,26 @@ bool rewrite(const std::string& in, std::string* out, std::string* err) {
             while (j < n && is_ident(s[j])) j++;
             const std::string w = s.substr(i, j - i);
             if (w == "highp" || w == "mediump" || w == "lowp") { i = j; continue; }
+            if (forbidden_word(w)) { *err = "'" + w + "' is not available to SDF snippets"; return false; }
+            if (is_type_name(w)) { /* array constructor: T[n]( .. ) or T[]( .. )  ->  { .. } */
+                size_t k = j;
+                while (k < n && (s[k] == ' ' || s[k] == '\t')) k++;
+                if (k < n && s[k] == '[') {
+                    size_t q = k + 1;
+                    while (q < n && (is_digit(s[q]) || s[q] == ' ')) q++;
+                    if (q < n && s[q] == ']') {
+                        size_t r = q + 1;
+                        while (r < n && (s[r] == ' ' || s[r] == '\t')) r++;
+                        if (r < n && s[r] == '(') {
+                            o.push_back('{');
+                            closers.push_back('}');
+                            i = r + 1;
+                            last = 'o';
+                            continue;
+                        }
+                    }
+                }
+            }
             if (w == "in" || w == "out" || w == "inout") {
                 const std::string next = peek_ident(s, j);
                 if (is_type_name(next)) {
@@ -139,6 +218,7 @@ bool rewrite(const std::string& in, std::string* out, std::string* err) {
             }
             o += w;
             i = j;
+            last = is_type_name(w) ? 't' : ((w == "return" || w == "else" || w == "const" || w == "in" || w == "out" || w == "inout") ? 'o' : 'v');
             continue;
         }
         if (c == '.' && i + 1 < n && is_ident_start(s[i + 1])) { /* member access: maybe a swizzle */
@@ -150,9 +230,20 @@ bool rewrite(const std::string& in, std::string* out, std::string* err) {
             while (k < n && (s[k] == ' ' || s[k] == '\t')) k++;
             const bool is_call = (k < n && s[k] == '(');
             if (!is_call && swizzle_letters(w, &mapped)) {
-                o.push_back('.');
-                o += mapped;
-                o += "()";
+                /* `.xz = e`, `.xz += e` ... write through the lvalue proxy; every other use reads a value */
+                bool lvalue = false;
+                if (k < n) {
+                    if (s[k] == '=' && !(k + 1 < n && s[k + 1] == '=')) lvalue = true;
+                    if ((s[k] == '+' || s[k] == '-' || s[k] == '*' || s[k] == '/') && k + 1 < n && s[k + 1] == '=') lvalue = true;
+                }
+                o += lvalue ? ".lsw" : ".sw";
+                o += std::to_string(mapped.size());
+                o.push_back('<');
+                for (size_t q = 0; q < mapped.size(); q++) {
+                    if (q) o.push_back(',');
+                    o.push_back((char)('0' + (strchr("xyzw", mapped[q]) - "xyzw")));
+                }
+                o += ">()";
             } else if (!is_call && w.size() == 1 && strchr("rgbastpq", w[0])) {
                 const char* sets[2] = {"rgba", "stpq"};
                 char m = w[0];
@@ -167,8 +258,22 @@ bool rewrite(const std::string& in, std::string* out, std::string* err) {
                 o += w;
             }
             i = j;
+            last = 'v';
             continue;
         }
+        if (c == '(') { closers.push_back(')'); o.push_back('('); i++; last = 'o'; continue; }
+        if (c == ')') {
+            const char cl = closers.empty() ? ')' : closers.back();
+            if (!closers.empty()) closers.pop_back();
+            o.push_back(cl);
+            i++;
+            last = 'v';
+            continue;
+        }
+        if (c == ']') last = 'v';
+        else if (c == '+' && i + 1 < n && s[i + 1] == '+') { o += "++"; i += 2; continue; } /* x++ / ++x leave `last` as it is */
+        else if (c == '-' && i + 1 < n && s[i + 1] == '-') { o += "--"; i += 2; continue; }
+        else if (c != ' ' && c != '\t' && c != '\n' && c != '\r') last = 'o';
         o.push_back(c);
         i++;
     }
@@ -233,6 +338,7 @@ int pt_sdf_generate(const char* const* sdf_glsl, int n_sdf, const float* sdfs_ra
     }
     o += "};\n";
     o += kHelpers;
+    std::vector<std::string> macros;
     for (int i = 0; i < n_sdf; i++) {
         if (!sdf_glsl || !sdf_glsl[i]) { *err = "null SDF snippet"; return PT_ERR_ARG; }
         std::string src(sdf_glsl[i]);
@@ -250,11 +356,12 @@ int pt_sdf_generate(const char* const* sdf_glsl, int n_sdf, const float* sdfs_ra
         if (p == std::string::npos) { *err = "SDF snippet " + std::to_string(i + 1) + " defines no sdfmaterial()"; return PT_ERR_COMPILE; }
         t.replace(p, 11, name + "MATERIAL");
         std::string r;
-        if (!rewrite(t, &r, err)) return PT_ERR_COMPILE;
+        if (!rewrite(t, &r, err, &macros)) { *err = "SDF snippet " + std::to_string(i + 1) + ": " + *err; return PT_ERR_COMPILE; }
         o += "/* ---- snippet " + std::to_string(i + 1) + " ---- */\n";
         o += r;
         o += "\n";
     }
+    for (const std::string& m : macros) o += "#undef " + m + "\n"; /* a snippet's macros end with the snippets */
     std::string sdf_lines, mat_lines;
     for (int i = 0; i < n_sdf; i++) {
         const std::string code = std::to_string(1u << (i % 32)) + "u";

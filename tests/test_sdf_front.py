@@ -107,7 +107,7 @@ def test_rewrite_rules(ptlib):
     text = api.sdf_translate([src.replace('// a comment with sdf in it would break the reference too\n', '')])
     assert 'vec3& q' in text and 'float& w' in text and 'float s' in text and ' in ' not in text.split('snippet 1')[1]
     assert '2.f' in text and '1e-3f' in text and '.5f' in text and '1.5f' in text and '1.0e+0f' in text and '+ 3;' in text
-    assert 'p.zyx()' in text and 'p.xz()' in text
+    assert 'p.sw3<2,1,0>()' in text and 'p.sw2<0,2>()' in text and 'q.lsw2<0,1>() = q.sw2<1,0>()' in text
 
 
 def test_errors_are_reported(ptlib):

@@ -1,0 +1,123 @@
+"""The SDF hook beyond the four shipped snippets: swizzle assignment, mat2/3/4, atan / asin / tan, #define, array
+constructors -- ten third-party-style snippets (tests/sdf_snippets/*.glsl) must load unchanged.  No GPU needed:
+  * the product's front end (pt_sdf_front.cpp) output compiles with NVRTC in both modes and with g++;
+  * the g++ build is bit-equal to the oracle's independent translation (oracle/sdf_build.py) of the same text;
+  * both agree with the REFERENCE's own pipeline -- InsertSDF splices the snippet into src/shader.comp, which is then
+    compiled over the vendored glm (oracle/_ref) -- to float tolerance: this pins the semantics of pt_glsl.h's matrices
+    (column-major constructors, v * M vs M * v), swizzle stores and atan(y, x) to glm's, not to our reading of GLSL;
+  * what GLSL does not have is refused before NVRTC sees it (scene files are data, not code)."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, scene_path
+from oracle import oracle, pack
+from test_sdf_front import build_product_unit
+
+SNIPPETS = sorted(os.path.basename(f)[:-5] for f in glob.glob(os.path.join(ROOT, 'tests', 'sdf_snippets', '*.glsl')))
+POS, SIZE = [0.2, 1.0, -0.1], [2.5, 2.5, 2.5]
+
+
+def snippet(name):
+    # scene files store their snippets with CRLF line ends (the reference's InsertSDF only works on those)
+    return open(os.path.join(ROOT, 'tests', 'sdf_snippets', name + '.glsl')).read().replace('\n', '\r\n')
+
+
+def scene_with(name, tmp_path):
+    sc = pack.load_scene(scene_path('scene10'))
+    sc['sdf'] = [{'position': POS, 'boundingSize': SIZE, 'glsl': snippet(name)}]
+    path = os.path.join(str(tmp_path), name + '.json')
+    json.dump(sc, open(path, 'w'))
+    return path, sc
+
+
+def test_there_are_ten():
+    assert len(SNIPPETS) >= 10
+
+
+@pytest.mark.parametrize('name', SNIPPETS)
+def test_snippet_loads_unchanged(ptlib, name, tmp_path):
+    from pathtracer_b200 import api
+    path, sc = scene_with(name, tmp_path)
+    ubo = pack.pack_ubo(sc)
+    src = [snippet(name)]
+    raw = ubo[pack.OFF_SDF:pack.OFF_SDF + 6]
+    # NVRTC: the SDF unit alone in both modes, and the whole scene-specialised kernel in fast mode
+    api.sdf_compile_check(src, raw, ptlib.MODE_STRICT)
+    api.sdf_compile_check(src, raw, ptlib.MODE_FAST)
+    ptlib.kernel_compile_check(ubo, src, ptlib.MODE_FAST, True)
+    # g++ build of the same text vs the oracle's own translator: same bits
+    L, text = build_product_unit(ptlib, src, raw)
+    rng = np.random.default_rng(1)
+    pts = (np.array(POS) + (rng.random((3000, 3)) - 0.5) * np.array(SIZE)).astype(np.float32)
+    d = np.array([L.pt_sdf_dispatch(*map(float, p), 1) for p in pts], dtype=np.float32)
+    m = np.array([L.pt_sdfmaterial_dispatch(*map(float, p), 1) for p in pts], dtype=np.float32)
+    do, mo = oracle.Oracle(ubo, src).sdf_eval(pts)
+    assert np.isfinite(d).all()
+    assert np.array_equal(d.view(np.uint32), do.view(np.uint32)) and np.array_equal(m.view(np.uint32), mo.view(np.uint32))
+    # the reference's own pipeline: InsertSDF + shader.comp over glm
+    from oracle import ref
+    if not ref.available():
+        pytest.skip('no /root/reference and no prebuilt oracle/_ref')
+    from oracle import ref_build
+    if not ref_build.have_reference() and not os.path.exists(ref_build.shader_so(src)):
+        pytest.skip('oracle/_ref object for this snippet was not prebuilt')
+    rs = ref.RefScene(path)
+    assert np.array_equal(rs.ubo().view(np.uint32), ubo.view(np.uint32))
+    dt, mt = rs.shader().sdf_eval(rs.ubo(), pts)
+    assert np.abs(d - dt).max() <= 2e-5 * max(1.0, float(np.abs(dt).max())), float(np.abs(d - dt).max())
+    assert (np.abs(m - mt) < 1e-4).mean() > 0.999
+
+
+def test_widened_rewrite_rules(ptlib):
+    from pathtracer_b200 import api
+    src = ('#define K 0.5\n'
+           'float sdf(in vec3 p) { p.xz *= mat2(1.0, 0.0, 0.0, 1.0); p.yx = p.xy; vec2 q = p.zy; float a[2] = float[2](K, 2.0);\n'
+           '  if (p.x == q.x) p.zyx += 1.0; return a[0] + length(p.rgb) + q.s; }\n'
+           'float sdfmaterial(in vec3 p) { return 0.0; }\n')
+    text = api.sdf_translate([src]).split('snippet 1')[1]
+    assert 'p.lsw2<0,2>() *= mat2(' in text and 'p.lsw2<1,0>() = p.sw2<0,1>()' in text and 'vec2 q = p.sw2<2,1>()' in text
+    assert 'float a[2] = {K, 2.0f}' in text and 'p.lsw3<2,1,0>() += 1.0f' in text and 'p.x == q.x' in text
+    assert 'p.sw3<0,1,2>()' in text and 'q.x;' in text and '#define K 0.5f' in text and '#undef K' in text
+
+
+@pytest.mark.parametrize('bad,why', [
+    ('float sdf(in vec3 p) { float* q = 0; return 0.0; }', "unary '*'"),
+    ('float sdf(in vec3 p) { return *(&p.x); }', 'unary'),
+    ('float sdf(in vec3 p) { vec3& r = p; return r.x; }', "unary '&'"),
+    ('float sdf(in vec3 p) { asm("trap;"); return 0.0; }', 'asm'),
+    ('#include "/etc/passwd"\nfloat sdf(in vec3 p) { return 0.0; }', '#include'),
+    ('#pragma unroll\nfloat sdf(in vec3 p) { return 0.0; }', '#pragma'),
+    ('float sdf(in vec3 p) { return ptk_jit_fast::x; }', 'ptk_jit_fast'),
+    ('float sdf(in vec3 p) { return p->x; }', '->'),
+    ('float sdf(in vec3 p) { atomicAdd(0, 1); return 0.0; }', 'atomicAdd'),
+    ('float sdf(in vec3 p) { return float(threadIdx.x); }', 'threadIdx'),
+    ('float sdf(in vec3 p) { return __sinf(p.x); }', '__sinf'),
+    ('float sdf(in vec3 p) { return reinterpret_cast<float&>(p); }', 'reinterpret_cast'),
+    ('float sdf(in vec3 p) { printf("x"); return 0.0; }', 'printf'),
+    ('float sdf(in vec3 p) { return sizeof(p); }', 'sizeof'),
+    ('float sdf(in vec3 p) { double d = 1.0; return 0.0; }', 'double'),
+    ("float sdf(in vec3 p) { return float('a'); }", 'literals'),
+    ('#define pt_sdf_dispatch 1\nfloat sdf(in vec3 p) { return 0.0; }', 'macro name'),
+])
+def test_non_glsl_is_refused_before_nvrtc(ptlib, bad, why):
+    """Scene files are data.  In the reference their snippets were sandboxed GLSL; here the text reaches a CUDA C++
+    translation unit inside the host's context, so pointers, casts, asm, file inclusion and identifiers that reach
+    into CUDA / libc / this library are refused by the front end with PT_ERR_COMPILE."""
+    from pathtracer_b200 import api
+    with pytest.raises(ptlib.PtError) as e:
+        api.sdf_translate([bad + '\nfloat sdfmaterial(in vec3 p) { return 0.0; }'])
+    assert e.value.code == -2, str(e.value)
+    assert why.split()[0].strip("'") in str(e.value) or why in str(e.value), str(e.value)
+
+
+def test_legitimate_operators_are_not_refused(ptlib):
+    from pathtracer_b200 import api
+    ok = ('float sdf(in vec3 p) { int m = 3 & 1; bool b = (p.x > 0.0) && (p.y < 1.0); float s = -p.x * -p.y; s *= 2.0;\n'
+          '  float t = (p.z) * (s); t = p[0] * p[1]; for (int i = 0; i < 3; i++) { t += p[i] * float(m); } return b ? s * t : -s; }\n'
+          'float sdfmaterial(in vec3 p) { return 0.0; }')
+    api.sdf_translate([ok])
+    api.sdf_compile_check([ok], None, ptlib.MODE_STRICT)
