@@ -31,7 +31,8 @@ extern "C" {
 #define PT_MAX_LIGHTS_SIZE 128     /* host:42  / shader.comp:14 */
 #define PT_MAX_LIGHTIDS_SIZE 64    /* host:43  / shader.comp:15 */
 #define PT_CIE_SIZE 1323           /* 441 rows x 3, 360..800 nm (host:400-842) */
-#define PT_MAX_SDF_SNIPPETS 32     /* only set1 of the four 32-bit masks is ever filled (shader.comp:734-738) */
+#define PT_MAX_SDF_SNIPPETS 128    /* sdfs[768] / 6 floats; four 32-bit masks set1..set4 (shader.comp:12, 706).  The reference
+                                      only fills set1, i.e. 32 usable SDFs (734-738); libpt_cuda fills all four */
 
 /* == UniformBufferObject (host:187-195) == `ubo` block (shader.comp:19-27); counts and ids are stored as floats */
 typedef struct pt_ubo {
@@ -121,6 +122,7 @@ int pt_bvh_active(const pt_ctx* ctx);
  *   "pool_cap" / "pool_min"   v2m: slots per warp / marching rays from which the SDF phase runs            [32 / 24]
  *   "min_blocks"  __launch_bounds__ minimum CTAs per SM                                                     [-1]
  *   "no_unroll"   1 keeps the primitive loops rolled although the counts are baked (jit policy 2)           [-1]
+ *   "sin_poly_every"  fast mode: every k-th sin( of the SDF snippets runs on the FMA pipe instead of MUFU     [0]
  *   "stats"       1 builds the scheduling counters in (pt_debug_stats)                                      [0]
  *   "wf_refill", "wf_max_paths"   wavefront pipeline: evaluations between refills; paths in flight per chunk
  *   "bvh_while_while"             BVH traversal loop shape */
@@ -242,6 +244,7 @@ int pt_debug_stats(pt_ctx* ctx, unsigned long long* out16, int reset);
 int pt_math_eval(pt_ctx* ctx, int fn, const float* x, const float* y, float* out, size_t n);
 /* Evaluate SDF()/SDFMATERIAL() of the current scene at n points (xyz triples); set1 mask as given */
 int pt_sdf_eval(pt_ctx* ctx, const float* xyz, size_t n, unsigned set1, float* dist, float* material);
+int pt_sdf_eval4(pt_ctx* ctx, const float* xyz, size_t n, const unsigned sets[4], float* dist, float* material);
 const char* pt_version(void);
 
 #ifdef __cplusplus

@@ -230,6 +230,30 @@ PT_HD float tanh(float x) { float a = exp(x), b = exp(-x); return (a - b) / (a +
 PT_HD int clamp(int x, int lo, int hi) { return min(max(x, lo), hi); }
 PT_HD float mix(float x, float y, bool a) { return a ? y : x; }
 
+/* sin on the FMA pipe (fast device builds): MUFU.SIN issues at 1/8 of the FP32 rate, so a snippet made of sines -- the
+ * terrain's 22 per evaluation -- is bound by the XU pipe while the FMA pipe idles.  PT_SIN_SITE(n, x) is what the front
+ * end emits for the n-th `sin(` of a snippet; every PT_SIN_POLY_EVERY-th site (option "sin_poly_every", 0 = none) takes
+ * this polynomial instead: x in turns, nearest integer subtracted with the 1.5 * 2^23 trick, then t P(t^2) on
+ * [-1/2, 1/2] (six terms, max abs error 7e-7 -- __sinf's own is 5e-7 near 0 and grows with |x|).  Strict builds and the
+ * CPU never see it: there every site is pt_sin. */
+#if defined(PT_FAST) && defined(__CUDA_ARCH__) && defined(PT_SIN_POLY_EVERY) && PT_SIN_POLY_EVERY > 0
+PT_HD float sin_fma(float x) {
+    float t = x * 0.15915494309189535f;
+    const float r = (t + 12582912.0f) - 12582912.0f;
+    t = t - r;
+    const float z = t * t;
+    float p = fmaf(z, -12.27126693725586f, 41.20539855957031f);
+    p = fmaf(z, p, -76.5801010131836f);
+    p = fmaf(z, p, 81.59618377685547f);
+    p = fmaf(z, p, -41.34142303466797f);
+    p = fmaf(z, p, 6.283182621002197f);
+    return p * t;
+}
+#define PT_SIN_SITE(n, x) ((((n) % PT_SIN_POLY_EVERY) == 0) ? sin_fma(x) : sin(x))
+#else
+#define PT_SIN_SITE(n, x) sin(x)
+#endif
+
 /* ---- componentwise lifting ---------------------------------------------------------------------------------- */
 #define PT_V_UN(f)                                                          \
     PT_HD vec2 f(const vec2& a) { return vec2(f(a.x), f(a.y)); }            \
@@ -237,6 +261,9 @@ PT_HD float mix(float x, float y, bool a) { return a ? y : x; }
     PT_HD vec4 f(const vec4& a) { return vec4(f(a.x), f(a.y), f(a.z), f(a.w)); }
 PT_V_UN(sin) PT_V_UN(cos) PT_V_UN(acos) PT_V_UN(exp) PT_V_UN(exp2) PT_V_UN(log) PT_V_UN(log2) PT_V_UN(sqrt)
 PT_V_UN(inversesqrt) PT_V_UN(abs) PT_V_UN(floor) PT_V_UN(ceil) PT_V_UN(fract) PT_V_UN(sign)
+#if defined(PT_FAST) && defined(__CUDA_ARCH__) && defined(PT_SIN_POLY_EVERY) && PT_SIN_POLY_EVERY > 0
+PT_V_UN(sin_fma)
+#endif
 PT_V_UN(tan) PT_V_UN(asin) PT_V_UN(atan) PT_V_UN(radians) PT_V_UN(degrees) PT_V_UN(trunc) PT_V_UN(round) PT_V_UN(sinh) PT_V_UN(cosh) PT_V_UN(tanh)
 #undef PT_V_UN
 

@@ -168,7 +168,16 @@ inline V3 operator*(const M3& M, V3 v) { return M.c[0] * v.x + M.c[1] * v.y + M.
 /* ------------------------------------------------------------------------------------------------------------
  * shader state: the uniform block, the push constants, the injected SDF dispatchers
  * ---------------------------------------------------------------------------------------------------------- */
-typedef float (*sdf_dispatch_fn)(const float* sdfs, float px, float py, float pz, unsigned set1);
+/* which SDFs a ray's bounding-box search found: bit i % 32 of word i / 32 -- the four masks set1..set4 the shader declares
+ * (shader.comp:706-719, 732-738).  The reference only ever fills set1 ("Program To Use set2, set3, set4 Not Yet
+ * Written", its `1 << uint(i)` is undefined from i = 32 on); filling the other three the way InsertSDF's generated
+ * dispatcher lines already read them (host:2012, 2029: set<i/32 + 1> & 2^(i % 32)) is the extension of SURVEY 8f-3.
+ * With at most 32 SDFs only w[0] is ever non-zero and everything is the reference's arithmetic. */
+struct SdfSet { unsigned w[4]; };
+inline SdfSet sdfset(unsigned a = 0u, unsigned b = 0u, unsigned c = 0u, unsigned d = 0u) { SdfSet s = {{a, b, c, d}}; return s; }
+inline SdfSet sdfset_bit(int i) { SdfSet s = sdfset(); if (i >= 0 && i < 128) s.w[i >> 5] = 1u << (unsigned)(i & 31); return s; }
+inline void sdfset_add(SdfSet& s, int i) { if (i >= 0 && i < 128) s.w[i >> 5] += 1u << (unsigned)(i & 31); }
+typedef float (*sdf_dispatch_fn)(const float* sdfs, float px, float py, float pz, unsigned set1, unsigned set2, unsigned set3, unsigned set4);
 
 const float MAXDIST = 1e5f;                                   /* shader.comp:8 */
 const float PI = 3.141592653589792623810034526344f;           /* shader.comp:9  (rounds to 0x40490FDB) */
@@ -615,19 +624,19 @@ struct Shader {
     }
 
     /* shader.comp:706-719: the dispatchers InsertSDF (host:2004-2054) generates; built by oracle/sdf_build.py */
-    float SDF(V3 p, unsigned set1) const {
+    float SDF(V3 p, const SdfSet& set1) const {
         CNT(C_SDF_EVAL, 1);
         if (!sdf_fn) return MAXDIST;
-        return sdf_fn(ubo + OFF_SDF, p.x, p.y, p.z, set1);
+        return sdf_fn(ubo + OFF_SDF, p.x, p.y, p.z, set1.w[0], set1.w[1], set1.w[2], set1.w[3]);
     }
-    float SDFMATERIAL(V3 p, unsigned set1) const {
+    float SDFMATERIAL(V3 p, const SdfSet& set1) const {
         CNT(C_SDFMAT_EVAL, 1);
         if (!sdfmat_fn) return 0.0f;
-        return sdfmat_fn(ubo + OFF_SDF, p.x, p.y, p.z, set1);
+        return sdfmat_fn(ubo + OFF_SDF, p.x, p.y, p.z, set1.w[0], set1.w[1], set1.w[2], set1.w[3]);
     }
 
     /* shader.comp:721-730 */
-    V3 CalculateNumericalSDFNormals(V3 p, unsigned set1) const {
+    V3 CalculateNumericalSDFNormals(V3 p, const SdfSet& set1) const {
         float epsilon = 1e-4f;
         V3 hx = v3(epsilon, 0.0f, 0.0f), hy = v3(0.0f, epsilon, 0.0f), hz = v3(0.0f, 0.0f, epsilon);
         float nx = SDF(p + hx, set1) - SDF(p - hx, set1);
@@ -636,11 +645,11 @@ struct Shader {
         return normalize(v3(nx, ny, nz));
     }
 
-    /* shader.comp:732-777; set2..set4 are never filled by the reference */
-    bool SearchSDF(V3 p, V3 invdir, V2& tMinMax, unsigned& set1) const {
+    /* shader.comp:732-777 (set1 here = the four masks; see SdfSet) */
+    bool SearchSDF(V3 p, V3 invdir, V2& tMinMax, SdfSet& set1) const {
         CNT(C_SEARCHSDF, 1);
         bool isFoundSDF = false;
-        set1 = 0;
+        set1 = sdfset();
         for (int i = 0; (float)i < numObjects(5); i++) {
             Box boundingBox;
             Sdf sdf;
@@ -649,19 +658,18 @@ struct Shader {
             boundingBox.size = sdf.size;
             V2 boxMinMax = RayIntersectAABB(p, invdir, boundingBox);
             if ((boxMinMax.x > boxMinMax.y) || (boxMinMax.y < 0.0f)) continue;
-            unsigned bit = (i < 32) ? (1u << (unsigned)i) : 0u; /* `1 << uint(i)` is undefined for i >= 32 */
             if (boxMinMax.x < tMinMax.x) {
                 isFoundSDF = true;
                 if (boxMinMax.y < tMinMax.x) {
                     tMinMax = boxMinMax;
-                    set1 = bit;
+                    set1 = sdfset_bit(i);
                 } else {
                     if (boxMinMax.y < tMinMax.y) {
                         tMinMax.x = boxMinMax.x;
-                        set1 += bit;
+                        sdfset_add(set1, i);
                     } else {
                         tMinMax = boxMinMax;
-                        set1 += bit;
+                        sdfset_add(set1, i);
                     }
                 }
             } else {
@@ -669,9 +677,9 @@ struct Shader {
                     isFoundSDF = true;
                     if (boxMinMax.y > tMinMax.y) {
                         tMinMax.y = boxMinMax.y;
-                        set1 += bit;
+                        sdfset_add(set1, i);
                     } else {
-                        set1 += bit;
+                        sdfset_add(set1, i);
                     }
                 }
             }
@@ -693,7 +701,7 @@ struct Shader {
         V3 invdir = 1.0f / ray.dir;
         int points = 0;
         V2 tMinMax = v2(MAXDIST, MAXDIST);
-        unsigned set1 = 0;
+        SdfSet set1 = sdfset();
         if (SearchSDF(p, invdir, tMinMax, set1)) {
             t = gmax(tMinMax.x, t);
             p = vfma(ray.dir, v3(t), ray.origin);
@@ -1338,8 +1346,8 @@ int oracle_load_sdf(const char* so_path) {
     if (!so_path || !so_path[0]) return 0;
     g_sdf_handle = dlopen(so_path, RTLD_NOW | RTLD_LOCAL);
     if (!g_sdf_handle) { fprintf(stderr, "oracle_load_sdf: %s\n", dlerror()); return -1; }
-    g_sdf_fn = (sdf_dispatch_fn)dlsym(g_sdf_handle, "oracle_SDF");
-    g_sdfmat_fn = (sdf_dispatch_fn)dlsym(g_sdf_handle, "oracle_SDFMATERIAL");
+    g_sdf_fn = (sdf_dispatch_fn)dlsym(g_sdf_handle, "oracle_SDF4");
+    g_sdfmat_fn = (sdf_dispatch_fn)dlsym(g_sdf_handle, "oracle_SDFMATERIAL4");
     return (g_sdf_fn && g_sdfmat_fn) ? 0 : -2;
 }
 
@@ -1545,9 +1553,15 @@ void oracle_solve_quartic(const float* coef5, float* roots4, int* real4) {
     Shader::SolveQuartic(coef5[0], coef5[1], coef5[2], coef5[3], coef5[4], r, isReal);
     for (int i = 0; i < 4; i++) { roots4[i] = r[i]; real4[i] = isReal[i]; }
 }
-void oracle_sdf_eval(const pt_ubo* ubo, const float* xyz, size_t n, unsigned set1, float* dist, float* material) {
+void oracle_sdf_eval4(const pt_ubo* ubo, const float* xyz, size_t n, const unsigned* sets4, float* dist, float* material);
+void oracle_sdf_eval(const pt_ubo* ubo, const float* xyz, size_t n, unsigned set1_word, float* dist, float* material) {
+    const unsigned sets[4] = {set1_word, 0u, 0u, 0u};
+    oracle_sdf_eval4(ubo, xyz, n, sets, dist, material);
+}
+void oracle_sdf_eval4(const pt_ubo* ubo, const float* xyz, size_t n, const unsigned* sets4, float* dist, float* material) {
     pt_params pc; memset(&pc, 0, sizeof pc);
     Shader s = make_shader(ubo, &pc);
+    const SdfSet set1 = sdfset(sets4[0], sets4[1], sets4[2], sets4[3]);
     for (size_t i = 0; i < n; i++) {
         V3 p = v3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
         if (dist) dist[i] = s.SDF(p, set1);

@@ -34,6 +34,7 @@ def lib(count=False, bvh=False):
         L.oracle_emit.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p]
         L.oracle_spd.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p]
         L.oracle_sdf_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.oracle_sdf_eval4.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_math_eval.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.oracle_dispatch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_dispatch_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -122,12 +123,16 @@ class Oracle:
         self.L.oracle_dispatch_sum(_p(self.ubo), _p(params), first, n, _p(image))
 
     def sdf_eval(self, xyz, set1=1):
+        """SDF() / SDFMATERIAL() at the points; set1 is the first mask word, or a sequence of up to four words."""
         self._bind()
         xyz = np.ascontiguousarray(xyz, dtype=np.float32)
         n = xyz.shape[0]
         d = np.zeros(n, dtype=np.float32)
         m = np.zeros(n, dtype=np.float32)
-        self.L.oracle_sdf_eval(_p(self.ubo), _p(xyz), n, set1, _p(d), _p(m))
+        words = np.zeros(4, dtype=np.uint32)
+        w = np.atleast_1d(np.asarray(set1, dtype=np.uint64))
+        words[:len(w)] = w
+        self.L.oracle_sdf_eval4(_p(self.ubo), _p(xyz), n, _p(words), _p(d), _p(m))
         return d, m
 
     def intersect(self, origin, direction):

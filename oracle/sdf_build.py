@@ -39,6 +39,8 @@ def translate_snippet(glsl, number):
     s = re.sub(r'\b(?:const\s+)?in\s+(?=(?:float|int|uint|bool|vec[234]|mat[234])\b)', '', s)
     s = re.sub(r'\b(?:inout|out)\s+(float|int|uint|bool|vec[234]|mat[234])\s+', r'\1& ', s)
     s = _array_constructors(s)
+    # (the product's front end numbers its sin( sites for the fast build's FMA-pipe option; on the CPU and in strict
+    # builds every site is sin(), so the oracle's translation leaves them alone)
 
     def swz(m):
         letters = m.group(1)
@@ -106,37 +108,40 @@ def generate(sources):
     sdf_lines, mat_lines = [], []
     for i in range(len(sources)):
         code = 1 << (i % 32)
-        if i >= 32:
-            continue  # set2..set4 are never filled (shader.comp:734-738)
+        word = i // 32 + 1          # InsertSDF: "(set" + ((i - i % 32) / 32 + 1) + " & " + 2^(i % 32)  (host:2012, 2029-2033)
+        if word > 4:
+            raise ValueError('more than 128 SDFs')
         pos = '(p - vec3(sdfs[%d], sdfs[%d], sdfs[%d]))' % (6 * i, 6 * i + 1, 6 * i + 2)
-        cond = 'if ((set1 & %du) == %du) ' % (code, code)
+        cond = 'if ((set%d & %du) == %du) ' % (word, code, code)
         sdf_line = cond + 'sdf = min(sdf, SDF%d%s);' % (i + 1, pos)
         mat_line = cond + 'sdfmaterial = minMaterial(sdf, SDF%d%s, sdfmaterial, SDF%dMATERIAL%s);' % (i + 1, pos, i + 1, pos)
         sdf_lines.append(sdf_line)
         mat_lines += [mat_line, sdf_line]
     out.append('''
 /* shader.comp:706-711 */
-inline float SDF(vec3 p, uint set1) {
+inline float SDF(vec3 p, uint set1, uint set2, uint set3, uint set4) {
     float sdf = MAXDIST;
     %s
     return sdf;
 }
 /* shader.comp:713-719 */
-inline float SDFMATERIAL(vec3 p, uint set1) {
+inline float SDFMATERIAL(vec3 p, uint set1, uint set2, uint set3, uint set4) {
     float sdf = MAXDIST;
     float sdfmaterial = 0.0f;
     %s
     return sdfmaterial;
 }
 } // namespace ptglsl
-extern "C" float oracle_SDF(const float* s, float x, float y, float z, unsigned set1) {
+extern "C" float oracle_SDF4(const float* s, float x, float y, float z, unsigned set1, unsigned set2, unsigned set3, unsigned set4) {
     ptglsl::sdfs = s;
-    return ptglsl::SDF(ptglsl::vec3(x, y, z), set1);
+    return ptglsl::SDF(ptglsl::vec3(x, y, z), set1, set2, set3, set4);
 }
-extern "C" float oracle_SDFMATERIAL(const float* s, float x, float y, float z, unsigned set1) {
+extern "C" float oracle_SDFMATERIAL4(const float* s, float x, float y, float z, unsigned set1, unsigned set2, unsigned set3, unsigned set4) {
     ptglsl::sdfs = s;
-    return ptglsl::SDFMATERIAL(ptglsl::vec3(x, y, z), set1);
+    return ptglsl::SDFMATERIAL(ptglsl::vec3(x, y, z), set1, set2, set3, set4);
 }
+extern "C" float oracle_SDF(const float* s, float x, float y, float z, unsigned set1) { return oracle_SDF4(s, x, y, z, set1, 0u, 0u, 0u); }
+extern "C" float oracle_SDFMATERIAL(const float* s, float x, float y, float z, unsigned set1) { return oracle_SDFMATERIAL4(s, x, y, z, set1, 0u, 0u, 0u); }
 ''' % ('\n    '.join(sdf_lines), '\n    '.join(mat_lines)))
     return '\n'.join(out)
 

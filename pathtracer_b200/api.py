@@ -131,6 +131,7 @@ def lib():
         L.pt_sdf_compile_check.argtypes = [C.POINTER(C.c_char_p), ci, vp, ci]
         L.pt_math_eval.argtypes = [vp, ci, vp, vp, vp, C.c_size_t]
         L.pt_sdf_eval.argtypes = [vp, vp, C.c_size_t, C.c_uint32, vp, vp]
+        L.pt_sdf_eval4.argtypes = [vp, vp, C.c_size_t, vp, vp, vp]
         L.pt_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
         L.pt_get_option.argtypes = [vp, C.c_char_p, C.POINTER(C.c_longlong)]
         L.pt_kernel_compile_check.argtypes = [vp, C.POINTER(C.c_char_p), ci, ci, ci]
@@ -381,10 +382,14 @@ class Renderer:
         return out
 
     def sdf_eval(self, xyz, set1=1):
+        """SDF() / SDFMATERIAL() of the current scene at the points; set1 = the first mask word or up to four words."""
         xyz = np.ascontiguousarray(xyz, dtype=np.float32)
         n = xyz.shape[0]
         d, m = np.empty(n, dtype=np.float32), np.empty(n, dtype=np.float32)
-        _check(lib().pt_sdf_eval(self._ctx, _ptr(xyz), n, set1, _ptr(d), _ptr(m)), self._ctx)
+        words = np.zeros(4, dtype=np.uint32)
+        w = np.atleast_1d(np.asarray(set1, dtype=np.uint64))
+        words[:len(w)] = w
+        _check(lib().pt_sdf_eval4(self._ctx, _ptr(xyz), n, _ptr(words), _ptr(d), _ptr(m)), self._ctx)
         return d, m
 
 

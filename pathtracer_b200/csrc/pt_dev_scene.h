@@ -15,10 +15,10 @@
 #define PT_DEV_SCENE_H
 
 /* Capacity = whatever fits the reference's uniform block (1024 object floats, 768 SDF floats: host:39-40), i.e. up to
- * 170 spheres / 204 planes / 93 boxes / 85 lenses / 64 cyclides; only the first 32 SDFs are usable (set1 mask).
+ * 170 spheres / 204 planes / 93 boxes / 85 lenses / 64 cyclides, and 128 SDFs (sdfs[768]; four 32-bit masks).
  * The records of all types sit back to back in one pool, in the shader's type order; the worst case for the pool is
  * a scene made of boxes only (20 pool floats per 11 uniform-block floats). */
-#define PT_DEV_MAX_SDFS 32
+#define PT_DEV_MAX_SDFS 128
 #define PT_DEV_POOL_FLOATS (((1024 / 11) * 20) + 24 + PT_DEV_MAX_SDFS * 8)
 #define PT_DEV_MAX_LIGHT_SLOTS 65 /* lightIDs[0..numLights] inclusive: r == 1.0 reads one past */
 

@@ -100,6 +100,7 @@ int pt_knob_set(PtKnobs* k, const char* key, long long value) {
     else if (s == "stats") { if (v < 0 || v > 1) return -1; k->stats = v; }
     else if (s == "wf_refill") { if (v < 1 || v > 512) return -1; k->wf_refill = v; }
     else if (s == "bvh_while_while") { if (v < 0 || v > 1) return -1; k->bvh_while_while = v; }
+    else if (s == "sin_poly_every") { if (v < 0 || v > 64) return -1; k->sin_poly_every = v; }
     else return -1;
     return 0;
 }
@@ -112,6 +113,7 @@ int pt_knob_get(const PtKnobs* k, const char* key, long long* value) {
     else if (s == "no_unroll") *value = k->no_unroll; else if (s == "pool_cap") *value = k->pool_cap;
     else if (s == "pool_min") *value = k->pool_min; else if (s == "stats") *value = k->stats;
     else if (s == "wf_refill") *value = k->wf_refill; else if (s == "bvh_while_while") *value = k->bvh_while_while;
+    else if (s == "sin_poly_every") *value = k->sin_poly_every;
     else return -1;
     return 0;
 }
@@ -158,6 +160,8 @@ std::string pt_jit_source(const std::string& sdf_unit, const PtJitOptions& opt) 
     int sched = k.sched;
     if (sched < 0) sched = has_sdf ? PT_DEFAULT_SCHED_SDF : ((opt.bvh && heavy) ? 5 : PT_DEFAULT_SCHED_ANALYTIC);
     if (sched == 8 && !has_sdf) sched = 5; /* nothing marches */
+    const int sdf_words = opt.counts[5] > 0 ? (opt.counts[5] + 31) / 32 : 1;
+    if (sched == 8 && sdf_words > 1) sched = 5; /* the pool parks one mask word per path */
     const int no_unroll = k.no_unroll >= 0 ? k.no_unroll : ((has_sdf || (!opt.bvh && n_scanned > 16)) ? 1 : 0);
     const bool pooled = (sched == 5 || sched == 7 || sched == 8);
     int steal_s = k.steal_s;
@@ -173,6 +177,7 @@ std::string pt_jit_source(const std::string& sdf_unit, const PtJitOptions& opt) 
         else min_blocks = (pooled && steal_s > 8) ? 5 : 6;      /* 85 registers: +12 % over 4 CTAs/SM on scene1 */
     }
     src += "#define PT_SCHED " + std::to_string(sched) + "\n";
+    if (sdf_words > 1) src += "#define PT_SDF_WORDS " + std::to_string(sdf_words) + "\n";
     src += "#define PT_SDF_REPS " + std::to_string(k.sdf_reps) + "\n";
     src += "#define PT_FEED_T " + std::to_string(k.feed_t) + "\n";
     src += "#define PT_REGEN_T " + std::to_string(k.regen_t) + "\n";
@@ -184,6 +189,7 @@ std::string pt_jit_source(const std::string& sdf_unit, const PtJitOptions& opt) 
     src += "#define PT_WF_REFILL " + std::to_string(k.wf_refill) + "\n";
     src += "#define PT_BVH_WHILE_WHILE " + std::to_string(k.bvh_while_while) + "\n";
     if (k.stats) src += "#define PT_STATS 1\n";
+    if (k.sin_poly_every > 0 && opt.mode == PT_MODE_FAST) src += "#define PT_SIN_POLY_EVERY " + std::to_string(k.sin_poly_every) + "\n";
     src += opt.wavefront ? "#include \"pt_wavefront.cuh\"\n" : "#include \"pt_kernel.cuh\"\n";
     src += sdf_unit;
     src += "\nPT_DEFINE_RENDER_KERNEL(pt_render_jit)\n";

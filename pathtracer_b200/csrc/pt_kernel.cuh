@@ -127,8 +127,8 @@ static __device__ __forceinline__ float ptk_rsqrt(float x) { float r; asm("rsqrt
 
 #if PT_HAS_SDF
 /* provided by the generated translation unit (pt_sdf_front.cpp): the dispatchers InsertSDF builds (host:2004-2054) */
-__device__ float pt_sdf_dispatch(float px, float py, float pz, unsigned set1);
-__device__ float pt_sdfmaterial_dispatch(float px, float py, float pz, unsigned set1);
+__device__ float pt_sdf_dispatch(float px, float py, float pz, unsigned set1, unsigned set2, unsigned set3, unsigned set4);
+__device__ float pt_sdfmaterial_dispatch(float px, float py, float pz, unsigned set1, unsigned set2, unsigned set3, unsigned set4);
 #endif
 
 namespace PT_KERNEL_NS {
@@ -600,9 +600,30 @@ PT_DEV void DupinCyclide(const Ray& ray, const PtDevCyclide& ob, int objectID, H
     }
 }
 
+/* Which SDFs the bounding-box search found: bit i % 32 of word i / 32 -- the shader's four masks set1..set4
+ * (shader.comp:706-719).  The reference fills set1 only (732-738: "Program To Use set2, set3, set4 Not Yet Written"),
+ * which caps it at 32 SDFs; the other words are filled here the way InsertSDF's dispatcher lines already read them
+ * (host:2012: set<i/32 + 1> & 2^(i % 32)) -- SURVEY 8f-3.  PT_SDF_WORDS = ceil(n_sdf / 32) is baked in by the JIT: with
+ * at most 32 SDFs (every shipped scene) the set is one register and the arithmetic is the reference's. */
+#ifndef PT_SDF_WORDS
+#define PT_SDF_WORDS 1
+#endif
+struct SdfSet { unsigned w[PT_SDF_WORDS]; };
+PT_DEV void SdfSetClear(SdfSet& s) {
+#pragma unroll
+    for (int k = 0; k < PT_SDF_WORDS; k++) s.w[k] = 0u;
+}
+PT_DEV void SdfSetAdd(SdfSet& s, int i) { /* set += 1 << i */
+    const unsigned bit = 1u << (unsigned)(i & 31);
+#pragma unroll
+    for (int k = 0; k < PT_SDF_WORDS; k++)
+        if ((i >> 5) == k) s.w[k] += bit;
+}
+#define PT_SDF_SET_ARGS(s) (s).w[0], (PT_SDF_WORDS > 1 ? (s).w[PT_SDF_WORDS > 1 ? 1 : 0] : 0u), \
+                           (PT_SDF_WORDS > 2 ? (s).w[PT_SDF_WORDS > 2 ? 2 : 0] : 0u), (PT_SDF_WORDS > 3 ? (s).w[PT_SDF_WORDS > 3 ? 3 : 0] : 0u)
 /* ---- SDF sphere tracing (shader.comp:704-860) ------------------------------------------------------------------ */
 #if PT_HAS_SDF
-PT_DEV float SDF(V3 p, unsigned set1) { return ::pt_sdf_dispatch(p.x, p.y, p.z, set1); }
+PT_DEV float SDF(V3 p, const SdfSet& set1) { return ::pt_sdf_dispatch(p.x, p.y, p.z, PT_SDF_SET_ARGS(set1)); }
 
 /* shader.comp:278-287 with box = SDF bounding box */
 PT_DEV void RayIntersectAABB(V3 origin, V3 invdir, const PtDevSdf& s, float& t1, float& t2) {
@@ -616,34 +637,33 @@ PT_DEV void RayIntersectAABB(V3 origin, V3 invdir, const PtDevSdf& s, float& t1,
 }
 
 /* shader.comp:732-777 */
-PT_DEV bool SearchSDF(const Ctx& c, V3 p, V3 invdir, float& tMin, float& tMax, unsigned& set1) {
+PT_DEV bool SearchSDF(const Ctx& c, V3 p, V3 invdir, float& tMin, float& tMax, SdfSet& set1) {
     bool isFoundSDF = false;
-    set1 = 0u;
+    SdfSetClear(set1);
     const int n = PT_N_SDF(c);
     for (int i = 0; i < n; i++) {
         float bx, by;
         RayIntersectAABB(p, invdir, reinterpret_cast<const PtDevSdf*>(c.sc->pool + PT_OFF_SDFS(*c.sc))[i], bx, by);
         if ((bx > by) || (by < 0.0f)) continue;
-        const unsigned bit = 1u << (unsigned)i;
         if (bx < tMin) {
             isFoundSDF = true;
             if (by < tMin) {
                 tMin = bx; tMax = by;
-                set1 = bit;
+                SdfSetClear(set1); SdfSetAdd(set1, i);
             } else {
                 if (by < tMax) {
                     tMin = bx;
-                    set1 += bit;
+                    SdfSetAdd(set1, i);
                 } else {
                     tMin = bx; tMax = by;
-                    set1 += bit;
+                    SdfSetAdd(set1, i);
                 }
             }
         } else {
             if (bx < tMax) {
                 isFoundSDF = true;
                 if (by > tMax) tMax = by;
-                set1 += bit;
+                SdfSetAdd(set1, i);
             }
         }
     }
@@ -866,7 +886,7 @@ struct MarchState {     /* SphereTracing's locals, shader.comp:780-794 */
     float mt, insT, omega, previousRadius, tMax, ksign;
     float probe, nrm0, nrm1, nrm2;
     int points, iter, sub;
-    unsigned set1;
+    SdfSet set1;
 };
 
 PT_DEV void PathStateInit(PathState& ps) {
@@ -881,7 +901,7 @@ PT_DEV void PathStateInit(PathState& ps) {
 PT_DEV void MarchStateInit(MarchState& ms) {
     ms.mt = 0.0f; ms.insT = 0.0f; ms.omega = 1.7f; ms.previousRadius = 0.0f; ms.tMax = 1e5f; ms.ksign = 0.0f;
     ms.probe = 0.0f; ms.nrm0 = 0.0f; ms.nrm1 = 0.0f; ms.nrm2 = 0.0f;
-    ms.points = 0; ms.iter = 0; ms.sub = PT_SUB_SIGN; ms.set1 = 0u;
+    ms.points = 0; ms.iter = 0; ms.sub = PT_SUB_SIGN; SdfSetClear(ms.set1);
 }
 
 /* Scene()'s tail, shader.comp:1477-1489: radiance -> XYZ, NaNs dropped.  The four table look-ups run through one
@@ -1064,7 +1084,7 @@ PT_DEV int PhaseSdfEval(const Ctx& c, PathState& ps, MarchState& ms) {
     if (j == 5) {
         const V3 p = fma3(ps.ray.dir, ms.mt, ps.ray.origin);
         ps.h.normal = normalize(mk3(ms.nrm0, ms.nrm1, ms.nrm2));
-        ps.h.materialID = ::pt_sdfmaterial_dispatch(p.x, p.y, p.z, ms.set1);
+        ps.h.materialID = ::pt_sdfmaterial_dispatch(p.x, p.y, p.z, PT_SDF_SET_ARGS(ms.set1));
         ps.h.lightID = -1.0f;
         return PT_ST_SHADE;
     }
@@ -1540,13 +1560,13 @@ PT_DEV void PoolStoreMarch(float* e, const MarchState& ms) {
     PT_PF(PF_MT) = ms.mt; PT_PF(PF_INST) = ms.insT; PT_PF(PF_OMEGA) = ms.omega; PT_PF(PF_PREV) = ms.previousRadius;
     PT_PF(PF_TMAX) = ms.tMax; PT_PF(PF_KSIGN) = ms.ksign; PT_PF(PF_PROBE) = ms.probe; PT_PF(PF_N0) = ms.nrm0;
     PT_PF(PF_N1) = ms.nrm1; PT_PF(PF_N2) = ms.nrm2; PT_PF(PF_MPACK) = __uint_as_float(PoolPackMarch(ms));
-    PT_PF(PF_SET1) = __uint_as_float(ms.set1);
+    PT_PF(PF_SET1) = __uint_as_float(ms.set1.w[0]);
 }
 PT_DEV void PoolLoadMarch(const float* e, MarchState& ms) {
     ms.mt = PT_PF(PF_MT); ms.insT = PT_PF(PF_INST); ms.omega = PT_PF(PF_OMEGA); ms.previousRadius = PT_PF(PF_PREV);
     ms.tMax = PT_PF(PF_TMAX); ms.ksign = PT_PF(PF_KSIGN); ms.probe = PT_PF(PF_PROBE); ms.nrm0 = PT_PF(PF_N0);
     ms.nrm1 = PT_PF(PF_N1); ms.nrm2 = PT_PF(PF_N2); PoolUnpackMarch(__float_as_uint(PT_PF(PF_MPACK)), ms);
-    ms.set1 = __float_as_uint(PT_PF(PF_SET1));
+    ms.set1.w[0] = __float_as_uint(PT_PF(PF_SET1));
 }
 /* the whole path into a slot (its ray is about to march: ps.h holds the analytic hit, ms SphereTracing's prologue) */
 PT_DEV void PoolPark(float* e, const PathState& ps, const MarchState& ms, int item) {
@@ -1759,6 +1779,9 @@ __device__ __forceinline__ void pt_render_body_v2m(const PtDevScene& sc, const P
 #ifndef PT_SCHED
 #define PT_SCHED 0
 #endif
+#if PT_SCHED == 8 && PT_HAS_SDF && PT_SDF_WORDS > 1
+#error "v2m parks one mask word per path: more than 32 SDFs need the v2s driver (pt_jit.cpp selects it)"
+#endif
 #if PT_SCHED == 8 && !PT_HAS_SDF
 #undef PT_SCHED
 #define PT_SCHED 5 /* nothing marches: v2m is v2s */
@@ -1811,12 +1834,13 @@ __device__ __forceinline__ void pt_render_body_v2m(const PtDevScene& sc, const P
  * CPU oracle's g++ build bit for bit (pt_sdf_eval) */
 #define PT_DEFINE_SDF_EVAL_KERNEL(name)                                                                      \
     extern "C" __global__ void name(const float* __restrict__ xyz, unsigned long long n, unsigned set1,      \
+                                    unsigned set2, unsigned set3, unsigned set4,                             \
                                     float* __restrict__ dist, float* __restrict__ material) {                \
         const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;              \
         if (i >= n) return;                                                                                  \
         const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];                                  \
-        if (dist) dist[i] = ::pt_sdf_dispatch(x, y, z, set1);                                                  \
-        if (material) material[i] = ::pt_sdfmaterial_dispatch(x, y, z, set1);                                  \
+        if (dist) dist[i] = ::pt_sdf_dispatch(x, y, z, set1, set2, set3, set4);                                            \
+        if (material) material[i] = ::pt_sdfmaterial_dispatch(x, y, z, set1, set2, set3, set4);                            \
     }
 #endif
 

@@ -706,7 +706,11 @@ int pt_fp32_peak(pt_ctx* ctx, int repeats, double* tflops, double* ms_best) {
 }
 
 int pt_sdf_eval(pt_ctx* ctx, const float* xyz, size_t n, unsigned set1, float* dist, float* material) {
-    if (!ctx || !xyz || n == 0) return fail(ctx, PT_ERR_ARG, "pt_sdf_eval: bad argument");
+    const unsigned sets[4] = {set1, 0u, 0u, 0u};
+    return pt_sdf_eval4(ctx, xyz, n, sets, dist, material);
+}
+int pt_sdf_eval4(pt_ctx* ctx, const float* xyz, size_t n, const unsigned sets[4], float* dist, float* material) {
+    if (!ctx || !xyz || !sets || n == 0) return fail(ctx, PT_ERR_ARG, "pt_sdf_eval: bad argument");
     if (!ctx->scene_set || !ctx->active_jit || !ctx->active_jit->sdf_eval)
         return fail(ctx, PT_ERR_ARG, "pt_sdf_eval: the current scene has no SDF snippets");
     PT_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -717,7 +721,8 @@ int pt_sdf_eval(pt_ctx* ctx, const float* xyz, size_t n, unsigned set1, float* d
     cudaMemcpyAsync(dx, xyz, n * 12, cudaMemcpyHostToDevice, ctx->stream);
     unsigned long long nn = n;
     const float* a0 = dx;
-    void* args[5] = {(void*)&a0, (void*)&nn, (void*)&set1, (void*)&dd, (void*)&dm};
+    unsigned s0 = sets[0], s1 = sets[1], s2 = sets[2], s3 = sets[3];
+    void* args[8] = {(void*)&a0, (void*)&nn, (void*)&s0, (void*)&s1, (void*)&s2, (void*)&s3, (void*)&dd, (void*)&dm};
     cudaError_t e = cudaLaunchKernel((const void*)ctx->active_jit->sdf_eval, dim3((unsigned)((n + 127) / 128)), dim3(128), args,
                                      0, ctx->stream);
     if (e == cudaSuccess && dist) e = cudaMemcpyAsync(dist, dd, n * 4, cudaMemcpyDeviceToHost, ctx->stream);

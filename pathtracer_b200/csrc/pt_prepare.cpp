@@ -82,7 +82,7 @@ int pt_prepare_scene(const pt_ubo* ubo, PtDevScene* sc, std::string* err) {
     /* anything the reference's 1024-float objects[] can describe fits the pool; counts that overrun the arrays
      * (a hand-made ubo) are refused rather than read out of bounds */
     if (6L * nS + 5L * nP + 11L * nB + 12L * nL + 16L * nC > PT_MAX_OBJECTS_SIZE || nSdf > PT_DEV_MAX_SDFS) {
-        if (err) *err = "numObjects[] describes more objects than the uniform block holds (or more than 32 SDFs)";
+        if (err) *err = "numObjects[] describes more objects than the uniform block holds (or more than 128 SDFs)";
         return PT_ERR_ARG;
     }
     sc->nSpheres = nS; sc->nPlanes = nP; sc->nBoxes = nB; sc->nLenses = nL; sc->nCyclides = nC; sc->nSdfs = nSdf;

@@ -90,7 +90,7 @@ bool forbidden_word(const std::string& w) {
 }
 
 /* token-level GLSL -> C++/CUDA rewrite of one snippet; macro names it #defines are appended to *macros */
-bool rewrite(const std::string& in, std::string* out, std::string* err, std::vector<std::string>* macros) {
+bool rewrite(const std::string& in, std::string* out, std::string* err, std::vector<std::string>* macros, int* sin_sites) {
     const std::string& s = in;
     std::string o;
     size_t i = 0;
@@ -216,6 +216,17 @@ bool rewrite(const std::string& in, std::string* out, std::string* err, std::vec
                     continue;
                 }
             }
+            if (w == "sin" && !(i > 0 && s[i - 1] == '.')) { /* the n-th sin( of the unit: PT_SIN_SITE(n, ..) (pt_glsl.h) */
+                size_t k = j;
+                while (k < n && (s[k] == ' ' || s[k] == '\t')) k++;
+                if (k < n && s[k] == '(') {
+                    o += "PT_SIN_SITE(" + std::to_string((*sin_sites)++) + ", ";
+                    closers.push_back(')');
+                    i = k + 1;
+                    last = 'o';
+                    continue;
+                }
+            }
             o += w;
             i = j;
             last = is_type_name(w) ? 't' : ((w == "return" || w == "else" || w == "const" || w == "in" || w == "out" || w == "inout") ? 'o' : 'v');
@@ -318,7 +329,7 @@ PT_SDF_FN vec2 smin(vec2 x, vec2 y) {
 
 int pt_sdf_generate(const char* const* sdf_glsl, int n_sdf, const float* sdfs_raw, std::string* out, std::string* err) {
     if (n_sdf < 0 || n_sdf > PT_MAX_SDF_SNIPPETS) {
-        *err = "at most 32 SDFs are usable (only set1 of the four masks is ever filled: shader.comp:734-738)";
+        *err = "at most 128 SDFs fit the uniform block's sdfs[768] and the shader's four 32-bit masks (shader.comp:12, 706)";
         return PT_ERR_ARG;
     }
     std::string o;
@@ -339,6 +350,7 @@ int pt_sdf_generate(const char* const* sdf_glsl, int n_sdf, const float* sdfs_ra
     o += "};\n";
     o += kHelpers;
     std::vector<std::string> macros;
+    int sin_sites = 0;
     for (int i = 0; i < n_sdf; i++) {
         if (!sdf_glsl || !sdf_glsl[i]) { *err = "null SDF snippet"; return PT_ERR_ARG; }
         std::string src(sdf_glsl[i]);
@@ -356,7 +368,7 @@ int pt_sdf_generate(const char* const* sdf_glsl, int n_sdf, const float* sdfs_ra
         if (p == std::string::npos) { *err = "SDF snippet " + std::to_string(i + 1) + " defines no sdfmaterial()"; return PT_ERR_COMPILE; }
         t.replace(p, 11, name + "MATERIAL");
         std::string r;
-        if (!rewrite(t, &r, err, &macros)) { *err = "SDF snippet " + std::to_string(i + 1) + ": " + *err; return PT_ERR_COMPILE; }
+        if (!rewrite(t, &r, err, &macros, &sin_sites)) { *err = "SDF snippet " + std::to_string(i + 1) + ": " + *err; return PT_ERR_COMPILE; }
         o += "/* ---- snippet " + std::to_string(i + 1) + " ---- */\n";
         o += r;
         o += "\n";
@@ -368,22 +380,23 @@ int pt_sdf_generate(const char* const* sdf_glsl, int n_sdf, const float* sdfs_ra
         const std::string num = std::to_string(i + 1);
         const std::string pos = "(p - vec3(sdfs[" + std::to_string(6 * i) + "], sdfs[" + std::to_string(6 * i + 1) +
                                 "], sdfs[" + std::to_string(6 * i + 2) + "]))";
-        const std::string cond = "    if ((set1 & " + code + ") == " + code + ") ";
+        /* InsertSDF: "(set" + ((i - i % 32) / 32 + 1) + " & " + 2^(i % 32) + ") == ..." (host:2012, 2029-2033) */
+        const std::string cond = "    if ((set" + std::to_string(i / 32 + 1) + " & " + code + ") == " + code + ") ";
         const std::string sdf_line = cond + "sdf = min(sdf, SDF" + num + pos + ");\n";
         const std::string mat_line = cond + "sdfmaterial = minMaterial(sdf, SDF" + num + pos + ", sdfmaterial, SDF" + num +
                                      "MATERIAL" + pos + ");\n";
         sdf_lines += sdf_line;
         mat_lines += mat_line + sdf_line;
     }
-    o += "/* shader.comp:706-711 */\nPT_SDF_FN float SDF(vec3 p, uint set1) {\n    float sdf = MAXDIST;\n" + sdf_lines +
+    o += "/* shader.comp:706-711 */\nPT_SDF_FN float SDF(vec3 p, uint set1, uint set2, uint set3, uint set4) {\n    float sdf = MAXDIST;\n" + sdf_lines +
          "    return sdf;\n}\n";
-    o += "/* shader.comp:713-719 */\nPT_SDF_FN float SDFMATERIAL(vec3 p, uint set1) {\n    float sdf = MAXDIST;\n"
-         "    float sdfmaterial = 0.0f;\n" + mat_lines + "    (void)sdf;\n    return sdfmaterial;\n}\n";
+    o += "/* shader.comp:713-719 */\nPT_SDF_FN float SDFMATERIAL(vec3 p, uint set1, uint set2, uint set3, uint set4) {\n    float sdf = MAXDIST;\n"
+         "    float sdfmaterial = 0.0f;\n" + mat_lines + "    (void)sdf; (void)set1; (void)set2; (void)set3; (void)set4;\n    return sdfmaterial;\n}\n";
     o += "} /* namespace ptglsl */\n";
-    o += "PT_SDF_ENTRY float pt_sdf_dispatch(float px, float py, float pz, unsigned set1) {\n"
-         "    return ptglsl::SDF(ptglsl::vec3(px, py, pz), set1);\n}\n";
-    o += "PT_SDF_ENTRY float pt_sdfmaterial_dispatch(float px, float py, float pz, unsigned set1) {\n"
-         "    return ptglsl::SDFMATERIAL(ptglsl::vec3(px, py, pz), set1);\n}\n";
+    o += "PT_SDF_ENTRY float pt_sdf_dispatch(float px, float py, float pz, unsigned set1, unsigned set2, unsigned set3, unsigned set4) {\n"
+         "    return ptglsl::SDF(ptglsl::vec3(px, py, pz), set1, set2, set3, set4);\n}\n";
+    o += "PT_SDF_ENTRY float pt_sdfmaterial_dispatch(float px, float py, float pz, unsigned set1, unsigned set2, unsigned set3, unsigned set4) {\n"
+         "    return ptglsl::SDFMATERIAL(ptglsl::vec3(px, py, pz), set1, set2, set3, set4);\n}\n";
     *out = o;
     return PT_OK;
 }

@@ -19,8 +19,8 @@ thread_local unsigned simt_phase = 0;
 
 #if defined(PT_HAS_SDF) && PT_HAS_SDF
 /* the generated SDF unit is a separate object with C linkage on the host (PT_SDF_ENTRY) */
-extern "C" float pt_sdf_dispatch(float px, float py, float pz, unsigned set1);
-extern "C" float pt_sdfmaterial_dispatch(float px, float py, float pz, unsigned set1);
+extern "C" float pt_sdf_dispatch(float px, float py, float pz, unsigned set1, unsigned set2, unsigned set3, unsigned set4);
+extern "C" float pt_sdfmaterial_dispatch(float px, float py, float pz, unsigned set1, unsigned set2, unsigned set3, unsigned set4);
 #endif
 
 #ifdef PT_STATS

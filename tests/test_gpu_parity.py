@@ -505,6 +505,39 @@ def test_driver_strict_bit_exact(ptlib, options, name, w, h, spp, spf, pl, jit):
     assert_bit_equal(got, ref, '%s %r' % (name, options))
 
 
+@pytest.mark.parametrize('options,mode', [({'sched': 5}, 0), ({'sched': 0}, 0), ({'sched': 8}, 0), ({}, 1)])
+def test_more_than_32_sdfs(ptlib, options, mode):
+    """scenes_synthetic/sdf40.json: 40 SDFs, so the bounding-box search fills the shader's second mask as well (the
+    reference stops at 32: shader.comp:732-738).  Strict builds write the oracle's bits under every driver (v2m falls back
+    to v2s: its pool parks one mask word); the fast build agrees statistically."""
+    import os
+    from conftest import ROOT
+    path = os.path.join(ROOT, 'scenes_synthetic', 'sdf40.json')
+    sc = ptlib.Scene.load(path)
+    ubo = sc.pack_ubo()
+    w, h, spp, spf = 96, 64, 4 if mode == 0 else 64, 2 if mode == 0 else 32
+    p = sc.pack_params(1, w, h, spf, 5)
+    r = ptlib.Renderer(device=0, mode=mode, jit=2, options=options)
+    r.set_scene(ubo, sc.sdf_sources)
+    r.resize(w, h)
+    r.render(p, spp, spf)
+    got = r.read_xyz()
+    src = [s.decode() for s in sc.sdf_sources]
+    o = oracle.Oracle(ubo, src)
+    ref = o.render(p, spp, spf)
+    if mode == 0:
+        assert_bit_equal(got, ref, 'sdf40 %r' % options)
+        pts = (np.array([0.0, 1.0, 0.0]) + (np.random.default_rng(4).random((50000, 3)) - 0.5) * np.array([3.6, 2.2, 1.0])).astype(np.float32)
+        for words in ((0xFFFFFFFF, 0xFF), (0, 0x81), (1 << 31, 1)):
+            d, m = r.sdf_eval(pts, words)
+            d_ref, m_ref = o.sdf_eval(pts, words)
+            assert np.array_equal(d.view(np.uint32), d_ref.view(np.uint32)) and np.array_equal(m.view(np.uint32), m_ref.view(np.uint32))
+    else:
+        assert np.isfinite(got).all()
+        assert abs(float(got[..., 1].mean()) / float(ref[..., 1].mean()) - 1.0) < 0.02
+    r.close()
+
+
 def test_option_errors(ptlib, renderer):
     with pytest.raises(ptlib.PtError):
         renderer.set_option('no_such_option', 1)

@@ -25,11 +25,20 @@ def build_product_unit(ptlib, sources, raw):
         cpp = so[:-3] + '.cpp'
         open(cpp, 'w').write(text)
         subprocess.run([sdf_build.CXX, *sdf_build.CXXFLAGS, '-o', so, cpp], check=True)
-    L = C.CDLL(so)
-    for f in (L.pt_sdf_dispatch, L.pt_sdfmaterial_dispatch):
+    lib = C.CDLL(so)
+    for f in (lib.pt_sdf_dispatch, lib.pt_sdfmaterial_dispatch):
         f.restype = C.c_float
-        f.argtypes = [C.c_float, C.c_float, C.c_float, C.c_uint32]
-    return L, text
+        f.argtypes = [C.c_float, C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+
+    class Unit:  # the dispatchers take the shader's four masks; the tests below mostly use the first
+        @staticmethod
+        def pt_sdf_dispatch(x, y, z, set1, set2=0, set3=0, set4=0):
+            return lib.pt_sdf_dispatch(x, y, z, set1, set2, set3, set4)
+
+        @staticmethod
+        def pt_sdfmaterial_dispatch(x, y, z, set1, set2=0, set3=0, set4=0):
+            return lib.pt_sdfmaterial_dispatch(x, y, z, set1, set2, set3, set4)
+    return Unit, text
 
 
 @pytest.mark.parametrize('name', SDF_SCENES)
@@ -94,6 +103,32 @@ def test_two_sdfs_dispatch_order_and_masks(ptlib):
         d = np.array([L.pt_sdf_dispatch(*map(float, p), mask) for p in pts], dtype=np.float32)
         m = np.array([L.pt_sdfmaterial_dispatch(*map(float, p), mask) for p in pts], dtype=np.float32)
         assert np.array_equal(d.view(np.uint32), d_ref.view(np.uint32)) and np.array_equal(m, m_ref)
+
+
+def test_more_than_32_sdfs_use_the_other_masks(ptlib):
+    """InsertSDF's dispatcher line for SDF i reads mask set<i/32 + 1>, bit i % 32 (host:2012, 2029-2033); the front end
+    and the oracle's translator both reproduce that for up to 128 snippets, and 129 are refused."""
+    from pathtracer_b200 import api
+    n = 70
+    srcs = ['float sdf(in vec3 p) { return length(p) - %.2f; }\nfloat sdfmaterial(in vec3 p) { return %d.0; }\n' % (0.1 + 0.01 * i, i % 5) for i in range(n)]
+    raw = np.zeros(6 * n, dtype=np.float32)
+    for i in range(n):
+        raw[6 * i:6 * i + 6] = [0.3 * i, 0.0, 0.0, 1.0, 1.0, 1.0]
+    L, text = build_product_unit(ptlib, srcs, raw)
+    assert 'if ((set2 & 1u) == 1u) sdf = min(sdf, SDF33(' in text and 'if ((set3 & 32u) == 32u) sdf = min(sdf, SDF70(' in text
+    ubo = np.zeros(pack.UBO_FLOATS, dtype=np.float32)
+    ubo[5] = n
+    ubo[pack.OFF_SDF:pack.OFF_SDF + 6 * n] = raw
+    o = oracle.Oracle(ubo, srcs)
+    pts = (np.random.default_rng(2).random((200, 3)).astype(np.float32)) * np.array([21.0, 1.0, 1.0], dtype=np.float32)
+    for words in ((1, 0, 0, 0), (0, 1, 0, 0), (0, 0, 32, 0), (0xFFFFFFFF, 0xFFFFFFFF, 0x3F, 0), (0, 0x80000000, 1, 0)):
+        d_ref, m_ref = o.sdf_eval(pts, words)
+        d = np.array([L.pt_sdf_dispatch(*map(float, q), *words) for q in pts], dtype=np.float32)
+        m = np.array([L.pt_sdfmaterial_dispatch(*map(float, q), *words) for q in pts], dtype=np.float32)
+        assert np.array_equal(d.view(np.uint32), d_ref.view(np.uint32)) and np.array_equal(m, m_ref)
+    assert abs(L.pt_sdf_dispatch(9.6, 0.0, 0.0, 0, 1, 0, 0) + 0.42) < 1e-6      # SDF 33 sits at x = 9.6, radius 0.42
+    with pytest.raises(ptlib.PtError):
+        api.sdf_translate(srcs[:1] * 129, np.zeros(6 * 129, dtype=np.float32))
 
 
 def test_rewrite_rules(ptlib):

@@ -76,7 +76,8 @@ def emulate(L, ubo, p, spp, spf, ctas=2):
 
 
 def scene_inputs(name, w, h, spf, pl):
-    scene = pack.load_scene(scene_path(name))
+    path = scene_path(name) if not name.startswith('synthetic/') else os.path.join(ROOT, 'scenes_synthetic', name.split('/', 1)[1] + '.json')
+    scene = pack.load_scene(path)
     ubo = pack.pack_ubo(scene)
     src = pack.sdf_sources(scene)
     return ubo, pack.pack_params(scene, 1, w, h, spf, pl), src, ubo[pack.OFF_SDF:pack.OFF_SDF + 6 * len(src)]
@@ -159,6 +160,26 @@ def test_emulated_drivers_at_the_edges(ptlib, name, w, h, spp, spf, pl):
     for defs in ({'PT_SCHED': 5, 'PT_STEAL_S': 0}, {'PT_SCHED': 7, 'PT_STEAL_S': 0}):
         got = emulate(build_emulator(ptlib, defs, src, raw), ubo, p, spp, spf, 3)
         assert np.allclose(got[..., :3], ref[..., :3], rtol=1e-5, atol=1e-6 * scale) and (got[..., 3] == 1.0).all(), defs
+
+
+@pytest.mark.parametrize('driver', ['v1', 'v2s_table2', 'v3s_table3'])
+def test_emulated_more_than_32_sdfs(ptlib, driver):
+    """40 SDFs (scenes_synthetic/sdf40.json): the bounding-box search fills set2 as well as set1 (the reference declares
+    set1..set4 and its generated dispatcher lines read them, but SearchSDF only ever writes set1: shader.comp:732-738).
+    Kernel (PT_SDF_WORDS = 2) and oracle agree bit for bit; SDFs 33..40 really are in the image."""
+    ubo, p, src, raw = scene_inputs('synthetic/sdf40', 40, 24, 2, 5)
+    assert len(src) == 40
+    defs = dict(DRIVERS[driver])
+    defs['PT_SDF_WORDS'] = 2
+    got = emulate(build_emulator(ptlib, defs, src, raw), ubo, p, 2, 2)
+    o = oracle.Oracle(ubo, src)
+    ref = o.render(p, 2, 2)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # the same scene with the last eight SDFs removed renders differently: they are reachable
+    ubo32 = ubo.copy()
+    ubo32[5] = 32
+    ref32 = oracle.Oracle(ubo32, src[:32]).render(p, 2, 2)
+    assert not np.array_equal(ref32.view(np.uint32), ref.view(np.uint32))
 
 
 def baked_counts(ubo, has_sdf):
