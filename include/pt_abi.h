@@ -115,7 +115,7 @@ int pt_bvh_active(const pt_ctx* ctx);
  * the scene).  Take effect at the next pt_set_scene; an unknown key or a value out of range is PT_ERR_ARG.
  *   "sched"       driver: 0 v1 nested loops, 7 v3s flat loop + sample pool, 5 v2s phase machine + sample pool,
  *                 8 v2m phase machine + pool of parked marching paths (SDF scenes)                        [-1]
- *   "sdf_reps"    SDF() evaluations per execution of the SDF phase                                          [16]
+ *   "sdf_reps"    SDF() evaluations per execution of the SDF phase                                          [8]
  *   "feed_t"      v2s / v2m: the SDF phase waits until every other phase has fewer lanes than this          [8]
  *   "regen_t"     v3s: finished lanes that trigger a regeneration                                           [16]
  *   "steal_s"     samples per pixel per round of the warp's sample pool; 0 = the whole dispatch (fast mode) [-1]

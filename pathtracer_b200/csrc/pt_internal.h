@@ -26,7 +26,7 @@ int pt_sdf_generate(const char* const* sdf_glsl, int n_sdf, const float* sdfs_ra
  * measured default for the scene.  They are part of the translation unit, hence of every cache key. */
 struct PtKnobs {
     int sched = -1;       /* driver: 0 v1, 5 v2s, 7 v3s, 8 v2m */
-    int sdf_reps = 16;    /* SDF() evaluations per execution of the SDF phase */
+    int sdf_reps = 8;     /* SDF() evaluations per execution of the SDF phase (8 vs 16: +1..2 % on cfg3/4a/5, profiles/r02_gpu3-4) */
     int feed_t = 8;       /* v2s / v2m: the SDF phase waits until every feeder phase has fewer lanes than this */
     int regen_t = 16;     /* v3s: waiting lanes that trigger a regeneration */
     int steal_s = -1;     /* samples per pixel per round of the pool (0 = the whole dispatch, fast mode only) */

@@ -877,8 +877,9 @@ struct PathState {
     bool pathAlive;     /* whether the path continues after the pending shadow ray */
     bool pendingFinish; /* a finished path whose radiance is still to be projected to XYZ */
     V3 shDir;
-    V4 shContrib;       /* added to radiance iff the shadow ray sees object shObj */
+    V4 shContrib;       /* added to radiance iff the shadow ray sees object shObj (kDeferEmit: the factor Emit() is scaled by) */
     int shObj;
+    float shScale, shT, shL; /* kDeferEmit only: (Emit(l, shT, shL) * shContrib) * shScale is the contribution */
     Hit h;
 };
 
@@ -895,7 +896,7 @@ PT_DEV void PathStateInit(PathState& ps) {
     ps.ray.origin = z3; ps.ray.dir = z3; ps.l = z4; ps.radiance = z4; ps.rayradiance = z4;
     ps.MISBRDFWeight = 1.0f; ps.seed = 0u; ps.bounce = 0;
     ps.isShadow = false; ps.pathAlive = false; ps.pendingFinish = false;
-    ps.shDir = z3; ps.shContrib = z4; ps.shObj = 0;
+    ps.shDir = z3; ps.shContrib = z4; ps.shObj = 0; ps.shScale = 0.0f; ps.shT = 0.0f; ps.shL = 0.0f;
     ps.h.t = 1e5f; ps.h.normal = z3; ps.h.materialID = 0.0f; ps.h.lightID = -1.0f; ps.h.objectID = -1;
 }
 PT_DEV void MarchStateInit(MarchState& ms) {
@@ -910,7 +911,11 @@ PT_DEV void MarchStateInit(MarchState& ms) {
 PT_DEV V3 PathColor(const Ctx& c, const PathState& ps) {
     V4 l = ps.l, r = ps.radiance;
     V3 sum = mk3(0.0f, 0.0f, 0.0f);
+#if PT_HAS_SDF /* rolled where the kernel outgrows the instruction cache; unrolled (no rotations) where it does not */
 #pragma unroll 1
+#else
+#pragma unroll
+#endif
     for (int i = 0; i < 4; i++) {
         const V3 w = WaveToXYZ(c, l.x);
         sum = (i == 0) ? mk3(r.x * w.x, r.x * w.y, r.x * w.z) : mk3(sum.x + r.x * w.x, sum.y + r.x * w.y, sum.z + r.x * w.z);
@@ -1116,7 +1121,8 @@ PT_DEV int PhaseTrivial(PathState& ps) {
  * contribution it would add are left in shDir / shObj / shContrib with isShadow set (LightSourceVisibilityCheck draws no
  * random numbers and its result only gates that addition, so running it after the roulette below changes nothing).
  * Returns ISECT (another ray to trace: the shadow ray if isShadow, else the next path ray) or NEW (path finished). */
-PT_DEV int PhaseShadeHit(const Ctx& c, PathState& ps) {
+template <bool kDeferEmit>
+PT_DEV int PhaseShadeHitT(const Ctx& c, PathState& ps) {
     const PtDevScene& sc = *c.sc;
     float emitT, emitL; /* the light Emit() is evaluated for: the one hit, or the one sampled */
     GetLightMix(c, ps.h.lightID, emitT, emitL);
@@ -1172,7 +1178,11 @@ PT_DEV int PhaseShadeHit(const Ctx& c, PathState& ps) {
         ps.bounce++;
         if (ps.bounce >= c.pr->pathLength) alive = false; /* TracePath's loop bound, shader.comp:1400 */
     }
-    if (emitterHit || needShadow) { /* the one Emit() site: (Emit * rr) * scale in both uses */
+    if (kDeferEmit && needShadow) {
+        /* the drivers that trace the shadow ray right away (TraceRayFlat) evaluate Emit() only if the light is seen:
+         * most light samples are occluded or face away.  Same products in the same order: (Emit * rr) * scale. */
+        ps.shContrib = rr; ps.shScale = emitScale; ps.shT = emitT; ps.shL = emitL;
+    } else if (emitterHit || needShadow) { /* the one Emit() site: (Emit * rr) * scale in both uses */
         const V4 e = Emit(ps.l, PTK_MAX(emitT, 0.0f), PTK_MAX(emitL, 0.0f));
         const V4 contrib = (e * rr) * emitScale;
         if (emitterHit) ps.radiance = ps.radiance + contrib; else ps.shContrib = contrib;
@@ -1190,6 +1200,7 @@ PT_DEV int PhaseShadeHit(const Ctx& c, PathState& ps) {
     }
     return PT_ST_ISECT;
 }
+PT_DEV int PhaseShadeHit(const Ctx& c, PathState& ps) { return PhaseShadeHitT<false>(c, ps); }
 /* SHADE for callers that have not applied PhaseTrivial themselves (the wavefront pipeline's SHADE kernel) */
 PT_DEV int PhaseShade(const Ctx& c, PathState& ps) {
     const int t = PhaseTrivial(ps);
@@ -1222,13 +1233,23 @@ PT_DEV void Intersection(const Ctx& c, const Ray& ray, Hit& h, const bool kShado
 PT_DEV bool TraceRayFlat(const Ctx& c, PathState& ps) {
     Intersection(c, ps.ray, ps.h, false);
     int next = PhaseTrivial(ps);
-    if (next == PT_ST_SHADE) next = PhaseShadeHit(c, ps);
-    if (ps.isShadow) {
+    if (next == PT_ST_SHADE) next = PhaseShadeHitT<true>(c, ps);
+    if (ps.isShadow) { /* the light sample's visibility test, shader.comp:1121-1223, 1328-1334 */
         Ray sr;
         sr.origin = ps.ray.origin;
         sr.dir = ps.shDir;
         Intersection(c, sr, ps.h, true);
-        next = PhaseTrivial(ps);
+        if (ps.h.objectID == ps.shObj) {
+            const V4 e = Emit(ps.l, PTK_MAX(ps.shT, 0.0f), PTK_MAX(ps.shL, 0.0f));
+            ps.radiance = ps.radiance + (e * ps.shContrib) * ps.shScale;
+        }
+        ps.isShadow = false;
+        if (ps.pathAlive) {
+            next = PT_ST_ISECT;
+        } else {
+            ps.pendingFinish = true;
+            next = PT_ST_NEW;
+        }
     }
     return next == PT_ST_ISECT;
 }
