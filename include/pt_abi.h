@@ -122,6 +122,7 @@ int pt_bvh_active(const pt_ctx* ctx);
  *   "pool_cap" / "pool_min"   v2m: slots per warp / marching rays from which the SDF phase runs            [32 / 24]
  *   "min_blocks"  __launch_bounds__ minimum CTAs per SM                                                     [-1]
  *   "no_unroll"   1 keeps the primitive loops rolled although the counts are baked (jit policy 2)           [-1]
+ *   "heavy_min"   v2s: > 0 runs the box / lens / cyclide tests as a phase of their own once so many lanes wait   [-1]
  *   "sin_poly_every"  fast mode: every k-th sin( of the SDF snippets runs on the FMA pipe instead of MUFU     [0]
  *   "stats"       1 builds the scheduling counters in (pt_debug_stats)                                      [0]
  *   "wf_refill", "wf_max_paths"   wavefront pipeline: evaluations between refills; paths in flight per chunk

@@ -37,6 +37,7 @@ struct PtKnobs {
     int stats = 0;        /* 1: build with the scheduling counters (pt_debug_stats) */
     int wf_refill = 8;    /* wavefront march kernel: evaluations between refills */
     int bvh_while_while = 0;
+    int heavy_min = -1;   /* v2s: lanes that must wait before the box / lens / cyclide tests run as a phase of their own (0: inline) */
     int sin_poly_every = 0; /* fast mode: every k-th sin( of the SDF snippets is evaluated on the FMA pipe (0: none) */
 };
 int pt_knob_set(PtKnobs* k, const char* key, long long value);       /* 0, or -1 for an unknown key / bad value */

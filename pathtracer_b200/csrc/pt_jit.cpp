@@ -48,6 +48,9 @@ std::string g_load_error;
 #ifndef PT_DEFAULT_SCHED_SDF
 #define PT_DEFAULT_SCHED_SDF 5
 #endif
+#ifndef PT_DEFAULT_HEAVY_MIN
+#define PT_DEFAULT_HEAVY_MIN 0
+#endif
 #ifndef PT_DEFAULT_SCHED_ANALYTIC
 #define PT_DEFAULT_SCHED_ANALYTIC 7 /* v3s: 10.73 vs v1's 9.96 Gsamples/s on cfg2, 8.10 vs 7.62 on cfg1 (profiles/r02_gpu1) */
 #endif
@@ -101,6 +104,7 @@ int pt_knob_set(PtKnobs* k, const char* key, long long value) {
     else if (s == "wf_refill") { if (v < 1 || v > 512) return -1; k->wf_refill = v; }
     else if (s == "bvh_while_while") { if (v < 0 || v > 1) return -1; k->bvh_while_while = v; }
     else if (s == "sin_poly_every") { if (v < 0 || v > 64) return -1; k->sin_poly_every = v; }
+    else if (s == "heavy_min") { if (v < -1 || v > 32) return -1; k->heavy_min = v; }
     else return -1;
     return 0;
 }
@@ -113,7 +117,7 @@ int pt_knob_get(const PtKnobs* k, const char* key, long long* value) {
     else if (s == "no_unroll") *value = k->no_unroll; else if (s == "pool_cap") *value = k->pool_cap;
     else if (s == "pool_min") *value = k->pool_min; else if (s == "stats") *value = k->stats;
     else if (s == "wf_refill") *value = k->wf_refill; else if (s == "bvh_while_while") *value = k->bvh_while_while;
-    else if (s == "sin_poly_every") *value = k->sin_poly_every;
+    else if (s == "sin_poly_every") *value = k->sin_poly_every; else if (s == "heavy_min") *value = k->heavy_min;
     else return -1;
     return 0;
 }
@@ -188,6 +192,12 @@ std::string pt_jit_source(const std::string& sdf_unit, const PtJitOptions& opt) 
     src += "#define PT_POOL_MIN " + std::to_string(k.pool_min) + "\n";
     src += "#define PT_WF_REFILL " + std::to_string(k.wf_refill) + "\n";
     src += "#define PT_BVH_WHILE_WHILE " + std::to_string(k.bvh_while_while) + "\n";
+    {   /* the heavy phase needs the scan (no BVH), at most 32 boxes + lenses + cyclides, and the phase machine */
+        int heavy_min = k.heavy_min < 0 ? PT_DEFAULT_HEAVY_MIN : k.heavy_min;
+        const int n_heavy = opt.counts[2] + opt.counts[3] + opt.counts[4];
+        if (sched != 5 || opt.bvh || n_heavy == 0 || n_heavy > 32 || !opt.bake_counts) heavy_min = 0;
+        src += "#define PT_HEAVY_MIN " + std::to_string(heavy_min) + "\n";
+    }
     if (k.stats) src += "#define PT_STATS 1\n";
     if (k.sin_poly_every > 0 && opt.mode == PT_MODE_FAST) src += "#define PT_SIN_POLY_EVERY " + std::to_string(k.sin_poly_every) + "\n";
     src += opt.wavefront ? "#include \"pt_wavefront.cuh\"\n" : "#include \"pt_kernel.cuh\"\n";

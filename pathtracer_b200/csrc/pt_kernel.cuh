@@ -763,6 +763,70 @@ PT_DEV void IntersectionAnalytic(const Ctx& c, const Ray& ray, Hit& h, const boo
 }
 
 
+#if !PT_BVH
+/* The scan in two halves, for the drivers that run the heavy tests as a phase of their own (v2s, option heavy_min):
+ * IntersectLight = spheres and planes, and for boxes / lenses / cyclides only the bounding-sphere cull -- whoever passes
+ * is a bit in the returned candidate mask (bit = position among the boxes, lenses, cyclides in scan order; at most 32,
+ * pt_jit.cpp keeps the option off beyond that);  IntersectHeavy = the full tests of the candidates, in the same order.
+ * Light then Heavy is IntersectionAnalytic's scan operation for operation: spheres and planes come first in the
+ * reference's order anyway (shader.comp:866-924), so `t < hit.t` sees the same sequence of hits. */
+PT_DEV unsigned IntersectLight(const Ctx& c, const Ray& ray, Hit& h, const bool kShadow) {
+    const PtDevScene& sc = *c.sc;
+    h.t = 1e5f;
+    h.objectID = -1;
+    if (!kShadow) {
+        h.normal = mk3(0.0f, 0.0f, 0.0f);
+        h.materialID = 0.0f;
+        h.lightID = -1.0f;
+    }
+    int base = 0;
+    const int nS = PT_N_SPHERES(c);
+    PT_UNROLL_PRIMS
+    for (int i = 0; i < nS; i++) SphereIntersection(ray, reinterpret_cast<const PtDevSphere*>(sc.pool)[i], base + i, h, kShadow);
+    base += nS;
+    const int nP = PT_N_PLANES(c);
+    PT_UNROLL_PRIMS
+    for (int i = 0; i < nP; i++) PlaneIntersection(ray, reinterpret_cast<const PtDevPlane*>(sc.pool + PT_OFF_PLANES(sc))[i], base + i, h, kShadow);
+    unsigned cand = 0u;
+    int bit = 0;
+    const int nB = PT_N_BOXES(c), nL = PT_N_LENSES(c), nC = PT_N_CYCLIDES(c);
+    for (int i = 0; i < nB; i++, bit++) {
+        const PtDevBox& o = reinterpret_cast<const PtDevBox*>(sc.pool + PT_OFF_BOXES(sc))[i];
+        if (BoundingSphere(ray, o.px, o.py, o.pz, o.bound2)) cand |= 1u << bit;
+    }
+    for (int i = 0; i < nL; i++, bit++) {
+        const PtDevLens& o = reinterpret_cast<const PtDevLens*>(sc.pool + PT_OFF_LENSES(sc))[i];
+        if (BoundingSphere(ray, o.px, o.py, o.pz, o.bound2)) cand |= 1u << bit;
+    }
+    for (int i = 0; i < nC; i++, bit++) {
+        const PtDevCyclide& o = reinterpret_cast<const PtDevCyclide*>(sc.pool + PT_OFF_CYCLIDES(sc))[i];
+        if (BoundingSphere(ray, o.px, o.py, o.pz, o.brad)) cand |= 1u << bit;
+    }
+    return cand;
+}
+PT_DEV void IntersectHeavy(const Ctx& c, const Ray& ray, Hit& h, const bool kShadow, unsigned cand) {
+    const PtDevScene& sc = *c.sc;
+    const int nB = PT_N_BOXES(c), nL = PT_N_LENSES(c), nC = PT_N_CYCLIDES(c);
+    int base = PT_N_SPHERES(c) + PT_N_PLANES(c), bit = 0;
+    for (int i = 0; i < nB; i++, bit++) {
+        if (((cand >> bit) & 1u) == 0u) continue;
+        BoxIntersection(ray, reinterpret_cast<const PtDevBox*>(sc.pool + PT_OFF_BOXES(sc))[i], base + i, h, kShadow);
+    }
+    base += nB;
+    for (int i = 0; i < nL; i++, bit++) {
+        if (((cand >> bit) & 1u) == 0u) continue;
+        int isOutside = 1;
+        LensIntersection(ray, reinterpret_cast<const PtDevLens*>(sc.pool + PT_OFF_LENSES(sc))[i], base + i, h, isOutside, kShadow);
+    }
+    base += nL;
+    for (int i = 0; i < nC; i++, bit++) {
+        if (((cand >> bit) & 1u) == 0u) continue;
+        DupinCyclide(ray, reinterpret_cast<const PtDevCyclide*>(sc.pool + PT_OFF_CYCLIDES(sc))[i], base + i, h, kShadow);
+    }
+}
+#endif
+
+
 /* ---- sampling (shader.comp:976-1028, 1093-1119) ------------------------------------------------------------------ */
 PT_DEV V3 SampleCosineDirectionHemisphere(V3 normal, unsigned& seed) {
     const float rx = RandomFloatPCG32(seed);
@@ -998,6 +1062,27 @@ PT_DEV int PhaseIsect(const Ctx& c, PathState& ps, MarchState& ms) {
 #endif
     return PT_ST_SHADE;
 }
+
+#if !PT_BVH
+/* ISECT in two phases (option heavy_min): the light half returns the phase that follows the intersection (SDF / SHADE)
+ * and the candidates of the heavy half; ms.points / ms.iter carry them while the lane waits for the HEAVY phase */
+PT_DEV int PhaseIsectLight(const Ctx& c, PathState& ps, MarchState& ms, unsigned& cand) {
+    Ray r;
+    r.origin = ps.ray.origin;
+    r.dir = ps.isShadow ? ps.shDir : ps.ray.dir;
+    cand = IntersectLight(c, r, ps.h, ps.isShadow);
+#if PT_HAS_SDF
+    if (MarchBegin(c, r.origin, r.dir, ms)) return PT_ST_SDF;
+#endif
+    return PT_ST_SHADE;
+}
+PT_DEV void PhaseHeavy(const Ctx& c, PathState& ps, unsigned cand) {
+    Ray r;
+    r.origin = ps.ray.origin;
+    r.dir = ps.isShadow ? ps.shDir : ps.ray.dir;
+    IntersectHeavy(c, r, ps.h, ps.isShadow, cand);
+}
+#endif
 
 #if PT_HAS_SDF
 /* The SDF phase in pieces, so a driver can decide WHO evaluates the distance function at WHICH point:
@@ -1292,7 +1377,15 @@ namespace PT_KERNEL_NS {
 #define PT_STEAL_WORDS (3 * PT_STEAL_S * 32) /* per warp */
 #endif
 static_assert(PT_STEAL_S >= 0 && PT_STEAL_S <= 20, "PT_STEAL_S: the per-sample table must fit the 48 KB of static shared memory next to the uniform block");
-enum { PT_ST_IDLE = 5 };
+enum { PT_ST_IDLE = 5, PT_ST_HEAVY = 6 };
+#ifndef PT_HEAVY_MIN
+#define PT_HEAVY_MIN 0 /* v2s: > 0 runs the box / lens / cyclide tests as a phase of their own, once this many lanes wait for it
+                          (or the feeders run dry): fewer, fuller executions of the kernel's coldest 450 instructions */
+#endif
+#if PT_BVH
+#undef PT_HEAVY_MIN
+#define PT_HEAVY_MIN 0
+#endif
 
 /* the tile's sample pool, shared by v3s / v2s / v2m: deposit a finished sample, close a round */
 PT_DEV void PoolDeposit(float* s_col, int item, V3 col) {
@@ -1488,7 +1581,12 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
 #else
         const unsigned bSdf = 0u;
 #endif
-        if ((bNew | bIs | bSdf | bSh) == 0u) {
+#if PT_HEAVY_MIN > 0
+        const unsigned bHv = __ballot_sync(0xffffffffu, st == PT_ST_HEAVY);
+#else
+        const unsigned bHv = 0u;
+#endif
+        if ((bNew | bIs | bSdf | bSh | bHv) == 0u) {
             if (!warpLive) break;
             if (!PoolCloseRound(s_col, lane, inRange, spf, roundBase, roundN, outColor)) break;
             next = 0;
@@ -1501,7 +1599,10 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
 #if PT_HAS_SDF
         if (bSdf != 0u && best < PT_FEED_T) phase = PT_ST_SDF;
 #endif
-        PT_STAT(phase, phase == PT_ST_NEW ? bNew : (phase == PT_ST_ISECT ? bIs : (phase == PT_ST_SDF ? bSdf : bSh)));
+#if PT_HEAVY_MIN > 0
+        if (bHv != 0u && (__popc(bHv) >= PT_HEAVY_MIN || best < PT_FEED_T)) phase = PT_ST_HEAVY;
+#endif
+        PT_STAT(phase == PT_ST_HEAVY ? PT_ST_ISECT : phase, phase == PT_ST_NEW ? bNew : (phase == PT_ST_ISECT ? bIs : (phase == PT_ST_SDF ? bSdf : bSh)));
         if (phase == PT_ST_NEW) {
             if (st == PT_ST_NEW) {
                 if (ps.pendingFinish) { /* the sample this lane just finished: item -> (pixel, sample of the round) */
@@ -1521,10 +1622,33 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
             next += __popc(bNew);
         } else if (phase == PT_ST_ISECT) {
             if (st == PT_ST_ISECT) {
+#if PT_HEAVY_MIN > 0
+                unsigned cand;
+                st = PhaseIsectLight(c, ps, ms, cand);
+                if (cand != 0u) { /* wait for the HEAVY phase; what follows it and who is to be tested ride in ms */
+                    ms.iter = (st == PT_ST_SDF) ? 0 : -1;
+                    ms.points = (int)cand;
+                    st = PT_ST_HEAVY;
+                } else if (st == PT_ST_SHADE) {
+                    st = PhaseTrivial(ps);
+                }
+#else
                 st = PhaseIsect(c, ps, ms);
+                if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
+#endif
+            }
+        }
+#if PT_HEAVY_MIN > 0
+        else if (phase == PT_ST_HEAVY) {
+            if (st == PT_ST_HEAVY) {
+                PhaseHeavy(c, ps, (unsigned)ms.points);
+                st = (ms.iter == 0) ? PT_ST_SDF : PT_ST_SHADE;
+                ms.points = 0;
+                ms.iter = 0;
                 if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
             }
         }
+#endif
 #if PT_HAS_SDF
         else if (phase == PT_ST_SDF) {
             PT_STAT_SDF(__popc(bSdf));

@@ -89,6 +89,8 @@ DRIVERS = {
     'v3s_table16': {'PT_SCHED': 7, 'PT_STEAL_S': 16}, 'v3s_table3': {'PT_SCHED': 7, 'PT_STEAL_S': 3, 'PT_REGEN_T': 4},
     # v2m: the pool of parked paths at its default size, with two slots (rays mostly march in their lanes), with a
     # threshold no warp reaches (the phase only runs when the feeders are dry) and with a greedy one
+    # v2s with the box / lens / cyclide tests as a phase of their own (immediately / once eight lanes wait)
+    'v2s_heavy1': {'PT_SCHED': 5, 'PT_STEAL_S': 16, 'PT_HEAVY_MIN': 1}, 'v2s_heavy8': {'PT_SCHED': 5, 'PT_STEAL_S': 4, 'PT_HEAVY_MIN': 8},
     'v2m': {'PT_SCHED': 8, 'PT_STEAL_S': 4, 'PT_POOL_CAP': 32, 'PT_POOL_MIN': 24},
     'v2m_tiny_pool': {'PT_SCHED': 8, 'PT_STEAL_S': 3, 'PT_POOL_CAP': 2, 'PT_POOL_MIN': 2},
     'v2m_lazy': {'PT_SCHED': 8, 'PT_STEAL_S': 8, 'PT_POOL_CAP': 7, 'PT_POOL_MIN': 64},
@@ -102,7 +104,7 @@ V2M = [d for d in sorted(DRIVERS) if d.startswith('v2m')]
 CASES = [(d, 'scene0', 48, 32, 10, 5, 5) for d in sorted(DRIVERS) if d not in V2M]
 CASES += [(d, 'scene1', 50, 37, 3, 3, 5) for d in sorted(DRIVERS) if d not in V2M]
 CASES += [(d, 'scene10', 40, 24, 4, 2, 32) for d in sorted(DRIVERS)]
-CASES += [(d, n, w, h, spp, spf, 5) for d in ['v2s_table16'] + V2M
+CASES += [(d, n, w, h, spp, spf, 5) for d in ['v2s_table16', 'v2s_heavy8'] + V2M
           for (n, w, h, spp, spf) in (('scene9', 33, 17, 5, 5), ('scene8', 32, 16, 2, 2), ('scene3', 24, 16, 3, 3))]
 
 
