@@ -8,6 +8,7 @@
  *             [--fast] [--wavefront] [--jit 0|1|2] [--device 0] [--out render.pfm|render.exr|render.ppm] [--tonemap 3]
  *             [--resume checkpoint.pfm --done-samples N]      continue a run saved with --out checkpoint.pfm
  *             [--gpus N]      split the samples over the first N GPUs of the box (pt_multi: one NCCL reduce at the end)
+ *             [--opt key=value]  a tuning option of the kernels (pt_set_option: sched, sdf_reps, ...); repeatable
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -29,6 +30,7 @@ int main(int argc, char** argv) {
     int width = 1280, height = 720, spp = 1000, spf = 1, path_length = 5, shot = 1, device = 0, tonemap = 3; /* host:30-31,1164-1174 */
     int fast = 0, jit = -1, wavefront = 0, done = 0, gpus = 1;
     std::string resume_path;
+    std::vector<std::pair<std::string, long long>> opts;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&](const char* name) -> const char* {
@@ -52,6 +54,12 @@ int main(int argc, char** argv) {
         else if (a == "--resume") resume_path = next("--resume");            /* PFM checkpoint written by --out x.pfm */
         else if (a == "--done-samples") done = atoi(next("--done-samples"));   /* samples per pixel already in it */
         else if (a == "--strict") fast = 0;
+        else if (a == "--opt") {
+            const std::string kv = next("--opt");
+            const size_t eq = kv.find('=');
+            if (eq == std::string::npos) { fprintf(stderr, "pt_render: --opt wants key=value\n"); return 2; }
+            opts.emplace_back(kv.substr(0, eq), atoll(kv.c_str() + eq + 1));
+        }
         else { fprintf(stderr, "pt_render: unknown flag %s\n", a.c_str()); return 2; }
     }
     pt_scene* scene = nullptr;
@@ -84,6 +92,8 @@ int main(int argc, char** argv) {
         }
         for (int g = 0; g < gpus; g++) {
             if (jit >= 0) pt_set_jit(pt_multi_ctx(m, g), jit);
+            for (auto& o : opts)
+                if (pt_set_option(pt_multi_ctx(m, g), o.first.c_str(), o.second) != PT_OK) return die("option", pt_multi_ctx(m, g));
             if (wavefront) pt_set_pipeline(pt_multi_ctx(m, g), PT_PIPE_WAVEFRONT);
         }
         auto t0 = std::chrono::steady_clock::now();
@@ -115,6 +125,8 @@ int main(int argc, char** argv) {
     if (pt_create(device, &ctx) != PT_OK) return die("create context", nullptr);
     pt_set_mode(ctx, fast ? PT_MODE_FAST : PT_MODE_STRICT);
     if (jit >= 0) pt_set_jit(ctx, jit);
+    for (auto& o : opts)
+        if (pt_set_option(ctx, o.first.c_str(), o.second) != PT_OK) return die("option", ctx);
     if (wavefront) pt_set_pipeline(ctx, PT_PIPE_WAVEFRONT);
     auto t0 = std::chrono::steady_clock::now();
     if (pt_set_scene(ctx, &ubo, sdf.data(), (int)sdf.size()) != PT_OK) return die("set scene", ctx);
