@@ -522,19 +522,17 @@ PT_DEV float SolveQuarticNearest(float a, float b, float c, float d, float e) {
     const float invsubq2div = invs2subp - q2divsqrt;
     const float bdiv4a = 0.25f * inva * b;
     const float a4 = 4.0f * a, b3 = 3.0f * b, c2 = 2.0f * c;
-    if (invaddq2div >= 0.0f) {
-        const float sq = PTK_SQRT(invaddq2div);
-        const float r0 = QuarticNewton(a, b, c, d, e, a4, b3, c2, 0.5f * (-sqrts2subp + 1.0f * sq) - bdiv4a);
-        const float r1 = QuarticNewton(a, b, c, d, e, a4, b3, c2, 0.5f * (-sqrts2subp + -1.0f * sq) - bdiv4a);
-        if ((r0 < t) && (r0 > 0.0f)) t = r0;
-        if ((r1 < t) && (r1 > 0.0f)) t = r1;
-    }
-    if (invsubq2div >= 0.0f) {
-        const float sq = PTK_SQRT(invsubq2div);
-        const float r2 = QuarticNewton(a, b, c, d, e, a4, b3, c2, 0.5f * (sqrts2subp + 1.0f * sq) - bdiv4a);
-        const float r3 = QuarticNewton(a, b, c, d, e, a4, b3, c2, 0.5f * (sqrts2subp + -1.0f * sq) - bdiv4a);
-        if ((r2 < t) && (r2 > 0.0f)) t = r2;
-        if ((r3 < t) && (r3 > 0.0f)) t = r3;
+    /* the four candidates 0.5 * (-+sqrts2subp +- sq) - bdiv4a in the shader's order (r0..r3), through ONE copy of the
+     * Newton step (instruction-cache footprint): the signs enter as factors of +-1, which is exact */
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        const float inv = (k < 2) ? invaddq2div : invsubq2div;
+        if (inv >= 0.0f) {
+            const float sq = PTK_SQRT(inv);
+            const float s1 = (k < 2) ? -1.0f : 1.0f, s2 = (k & 1) ? -1.0f : 1.0f;
+            const float rk = QuarticNewton(a, b, c, d, e, a4, b3, c2, 0.5f * (s1 * sqrts2subp + s2 * sq) - bdiv4a);
+            if ((rk < t) && (rk > 0.0f)) t = rk;
+        }
     }
     return t;
 }
@@ -1634,7 +1632,6 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
                 }
 #else
                 st = PhaseIsect(c, ps, ms);
-                if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
 #endif
             }
         }
@@ -1656,11 +1653,16 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
             for (int rep = 0; rep < PT_SDF_REPS; rep++) {
                 if (st == PT_ST_SDF) st = PhaseSdfEval(c, ps, ms);
             }
-            if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
         }
 #endif
         else {
             if (st == PT_ST_SHADE) st = PhaseShadeHit(c, ps);
+        }
+        /* A traced ray's verdict, at ONE site for the ISECT and SDF phases (instruction-cache footprint).  PhaseTrivial
+         * leaves a lane that already waits for SHADE untouched (it is not a shadow ray and it hit something), so it
+         * may see those lanes again. */
+        if (phase == PT_ST_ISECT || phase == PT_ST_SDF) {
+            if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
         }
     }
     if (inRange) StoreTexel(pr, image, gx, gy, outColor);
