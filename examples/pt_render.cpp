@@ -69,6 +69,10 @@ int main(int argc, char** argv) {
     if (pt_scene_pack_ubo(scene, &ubo) != PT_OK) return die("pack ubo", nullptr);
     if (pt_scene_pack_params(scene, shot, width, height, spf, path_length, &params) != PT_OK) return die("pack params", nullptr);
     params.tonemap = tonemap;
+    /* surface extensions of the scene file ("bsdf" keys on materials; none in the reference's scenes) */
+    pt_surface_ext surface_ext[PT_MAX_SURFACE_EXT];
+    const int n_surface_ext = pt_scene_surface_ext(scene, surface_ext, PT_MAX_SURFACE_EXT);
+    if (n_surface_ext < 0) return die("surface extensions", nullptr);
     std::vector<const char*> sdf;
     for (int i = 0; i < pt_scene_num_sdf(scene); i++) sdf.push_back(pt_scene_sdf_glsl(scene, i));
 
@@ -98,7 +102,8 @@ int main(int argc, char** argv) {
         }
         auto t0 = std::chrono::steady_clock::now();
         double secs = 0.0;
-        if (pt_multi_set_scene(m, &ubo, sdf.data(), (int)sdf.size()) != PT_OK || pt_multi_resize(m, width, height) != PT_OK) {
+        if (pt_multi_set_surface_ext(m, surface_ext, n_surface_ext) != PT_OK ||
+            pt_multi_set_scene(m, &ubo, sdf.data(), (int)sdf.size()) != PT_OK || pt_multi_resize(m, width, height) != PT_OK) {
             fprintf(stderr, "pt_render: %s\n", pt_multi_last_error(m));
             return 1;
         }
@@ -129,6 +134,7 @@ int main(int argc, char** argv) {
         if (pt_set_option(ctx, o.first.c_str(), o.second) != PT_OK) return die("option", ctx);
     if (wavefront) pt_set_pipeline(ctx, PT_PIPE_WAVEFRONT);
     auto t0 = std::chrono::steady_clock::now();
+    if (pt_set_surface_ext(ctx, surface_ext, n_surface_ext) != PT_OK) return die("surface extensions", ctx);
     if (pt_set_scene(ctx, &ubo, sdf.data(), (int)sdf.size()) != PT_OK) return die("set scene", ctx);
     auto t1 = std::chrono::steady_clock::now();
     if (pt_resize(ctx, width, height) != PT_OK) return die("resize", ctx);

@@ -89,6 +89,23 @@ typedef enum pt_pipeline {
                                queues compacted by warp ballot (pt_wavefront.cuh); same results */
 } pt_pipeline;
 
+/* Surface extensions.  NOT reference behaviour: every surface of shader.comp is the Lambertian of lines
+ * 1075-1091, and the reference's TODO.md:2 lists "Specular, Glossy Materials, Etc" as future work.  Off unless the
+ * host asks: with no table set (the default) results are the reference's, bit for bit in strict mode. */
+typedef enum pt_bsdf {
+    PT_BSDF_REFERENCE = 0,  /* the reference's Lambertian with the material's spectrum */
+    PT_BSDF_MIRROR = 1,     /* perfect reflection, tinted by the material's spectrum */
+    PT_BSDF_GLOSSY = 2,     /* GGX conductor: alpha = roughness^2, Schlick Fresnel with F0 = the material's spectrum */
+    PT_BSDF_DIELECTRIC = 3  /* smooth glass: exact Fresnel, refraction at `ior` (0: BK7 at the hero wavelength) */
+} pt_bsdf;
+typedef struct pt_surface_ext {
+    int32_t bsdf;     /* pt_bsdf */
+    float roughness;  /* PT_BSDF_GLOSSY */
+    float ior;        /* PT_BSDF_DIELECTRIC */
+    float pad;
+} pt_surface_ext;
+#define PT_MAX_SURFACE_EXT 64
+
 typedef struct pt_ctx pt_ctx;
 
 /* ---- device context (replaces InitVulkan + CreateComputePipeline, host:2424-2455, 2056-2092) ---------------- */
@@ -134,6 +151,9 @@ int pt_get_option(const pt_ctx* ctx, const char* key, long long* value);
  * sdf_glsl[i] is scene["sdf"][i]["glsl"] unchanged; n_sdf must equal ubo->numObjects[5].  With n_sdf > 0 the
  * kernel is rebuilt by NVRTC with the snippets translated against include/pt_glsl.h. */
 int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, int n_sdf);
+/* table[i] extends material i (0-based, the order of the scene file's "material" array) for the NEXT pt_set_scene;
+ * n = 0 (the default) restores the reference's shading.  Needs the run-time compiled kernel (pt_set_jit != 0). */
+int pt_set_surface_ext(pt_ctx* ctx, const pt_surface_ext* table, int n);
 
 /* CreateTexelBuffer (host:2250-2269): library-owned W*H RGBA32F accumulation image, zero-filled */
 int pt_resize(pt_ctx* ctx, int width, int height);
@@ -184,6 +204,10 @@ long pt_scene_to_json(const pt_scene* scene, char* out, size_t cap);
 int pt_scene_save_json(const pt_scene* scene, const char* path);
 /* UpdateUniformBuffer (host:3642-3811) incl. the CIE table copy of CreateUniformBuffer (host:2230-2248) */
 int pt_scene_pack_ubo(const pt_scene* scene, pt_ubo* ubo);
+/* The optional material keys "bsdf" ("mirror" | "glossy" | "dielectric"), "roughness", "ior" of the scene file (an
+ * extension of the reference's schema; absent in every shipped scene).  Writes up to `max` entries and returns how many
+ * to hand to pt_set_surface_ext: 0 when no material carries a "bsdf" key. */
+int pt_scene_surface_ext(const pt_scene* scene, pt_surface_ext* out, int max);
 /* UpdatePushConstant (host:3813-3834) for camera shot `shot` (1-based, host:1170); the per-dispatch fields are
  * set to the first offscreen dispatch: frame = currentSamples = samples_per_frame (host:4042-4048). */
 int pt_scene_pack_params(const pt_scene* scene, int shot, int width, int height, int samples_per_frame,
@@ -206,6 +230,7 @@ void pt_multi_destroy(pt_multi* m);
 const char* pt_multi_last_error(const pt_multi* m); /* m may be NULL: why the last pt_multi_create failed */
 int pt_multi_num_devices(const pt_multi* m);
 pt_ctx* pt_multi_ctx(pt_multi* m, int i);           /* for per-context settings (pt_set_jit, pt_set_bvh ...) */
+int pt_multi_set_surface_ext(pt_multi* m, const pt_surface_ext* table, int n); /* before pt_multi_set_scene */
 int pt_multi_set_scene(pt_multi* m, const pt_ubo* ubo, const char* const* sdf_glsl, int n_sdf);
 int pt_multi_resize(pt_multi* m, int width, int height);
 /* samples first_sample .. first_sample + total_samples - 1 of every pixel; blocks; seconds (optional) = host wall time */

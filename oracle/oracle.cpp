@@ -43,6 +43,15 @@
 static std::vector<float> g_bvh_blob;
 #endif
 
+#include <vector>
+/* Surface extensions (include/pt_abi.h pt_surface_ext): NOT reference behaviour -- shader.comp has one
+ * surface model, the Lambertian of lines 1075-1091, and the reference's TODO.md:2 lists specular / glossy materials as
+ * future work.  PARITY UNPINNED for everything reached through this table: the reference holds nothing to check it
+ * against.  What follows is this oracle's own statement of the definitions in DESIGN.md section 4 (the CUDA code states
+ * them a second time; the two are compared bit for bit), and tests/test_surface_ext.py holds it to the physics:
+ * reflection and Snell's law, Fresnel limits, energy bounds.  With an empty table (the default) none of it is reached. */
+static std::vector<pt_surface_ext> g_surface_ext;
+
 namespace {
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -824,14 +833,15 @@ struct Shader {
 #endif
 
     /* shader.comp:862-934 */
-    float Intersection(const Ray& ray, V3& normal, float& materialID, float& lightID) const {
+    float Intersection(const Ray& ray, V3& normal, float& materialID, float& lightID, bool* sdfHit = nullptr) const {
         CNT(C_RAYS_PATH, 1);
 #ifdef PT_ORACLE_BVH
         if (!g_bvh_blob.empty()) {
             float hd = MAXDIST;
             int objectID = -1;
             ClosestAnalyticBvh(ray, hd, normal, materialID, lightID, objectID);
-            SphereTracing(ray, hd, normal, materialID, lightID);
+            const bool viaSdf = SphereTracing(ray, hd, normal, materialID, lightID);
+            if (sdfHit) *sdfHit = viaSdf;
             return hd;
         }
 #endif
@@ -871,7 +881,8 @@ struct Shader {
             DupinCyclide(ray, object, hitdist, normal, materialID, lightID);
         }
         offset += 16 * pt_f2i(numObjects(4));
-        SphereTracing(ray, hitdist, normal, materialID, lightID);
+        const bool viaSdf = SphereTracing(ray, hitdist, normal, materialID, lightID);
+        if (sdfHit) *sdfHit = viaSdf; /* surface extensions only: the hit point then lies 1e-3 in front of the surface */
         return hitdist;
     }
 
@@ -1125,9 +1136,92 @@ struct Shader {
         return pdf1 * pdf1 / (pdf1 * pdf1 + pdf2 * pdf2);
     }
 
-    /* shader.comp:1298-1343 */
+    /* ---- surface extensions (not in shader.comp; see the note at g_surface_ext) ---------------------------------- */
+    struct GlossyLobe { V3 i; float a2; V4 R; };
+    static const pt_surface_ext* SurfaceExtOf(float materialID) {
+        const int m = pt_f2i(pt_floor(materialID));
+        if (m < 0 || m >= (int)g_surface_ext.size() || g_surface_ext[(size_t)m].bsdf == PT_BSDF_REFERENCE) return nullptr;
+        return &g_surface_ext[(size_t)m];
+    }
+    static V3 Reflect(V3 I, V3 N) { float d = 2.0f * dot(N, I); return v3(I.x - d * N.x, I.y - d * N.y, I.z - d * N.z); }
+    static float GgxD(float nh, float a2) {
+        float q = nh * nh * (a2 - 1.0f) + 1.0f;
+        return a2 / (PI * (q * q));
+    }
+    static float GgxG1(float nv, float a2) { return (2.0f * nv) / (nv + gsqrt(a2 + (1.0f - a2) * (nv * nv))); }
+    static V4 SchlickF(V4 f0, float ih) {
+        float m = gclamp(1.0f - ih, 0.0f, 1.0f);
+        float m2 = m * m;
+        float m5 = m2 * m2 * m;
+        return f0 + (1.0f - f0) * m5;
+    }
+    static float GgxAlpha2(float roughness) {
+        float a = roughness * roughness;
+        return gmax(a * a, 1e-8f);
+    }
+    static V4 GgxEval(V3 i, V3 o, V3 n, float a2, V4 f0) {
+        float ni = dot(n, i), no = dot(n, o);
+        if (!(ni > 0.0f) || !(no > 0.0f)) return v4(0.0f);
+        V3 h = normalize(i + o);
+        float nh = dot(n, h), ih = dot(i, h);
+        float k = (GgxD(nh, a2) * (GgxG1(ni, a2) * GgxG1(no, a2))) / (4.0f * ni * no);
+        return SchlickF(f0, ih) * k;
+    }
+    /* one scattering event: next direction, throughput factor f cos / pdf, lobe pdf (0: delta), path dies */
+    static void SurfaceExtSample(const pt_surface_ext& ext, V3 d, V3 n, V4 R, V4 l, uint32_t& seed, bool& inside, V3& outDir,
+                                 V4& weight, float& pdf, bool& dead) {
+        pdf = 0.0f;
+        dead = false;
+        weight = R;
+        if (ext.bsdf == PT_BSDF_MIRROR) {
+            outDir = Reflect(d, n);
+        } else if (ext.bsdf == PT_BSDF_GLOSSY) {
+            float a2 = GgxAlpha2(ext.roughness);
+            float u1 = RandomFloatPCG32(seed);
+            float u2 = RandomFloatPCG32(seed);
+            float cos2 = (1.0f - u1) / (1.0f + (a2 - 1.0f) * u1);
+            float cosT = gsqrt(cos2);
+            float sinT = gsqrt(gmax(1.0f - cos2, 0.0f));
+            float phi = 2.0f * PI * u2;
+            V3 h = ToWorld(v3(gcos(phi) * sinT, gsin(phi) * sinT, cosT), n);
+            outDir = Reflect(d, h);
+            V3 i = -d;
+            float ni = dot(n, i), no = dot(n, outDir), nh = dot(n, h), ih = dot(i, h);
+            if (!(no > 0.0f) || !(ih > 0.0f) || !(ni > 0.0f)) {
+                dead = true;
+                weight = v4(0.0f);
+            } else {
+                pdf = (GgxD(nh, a2) * nh) / (4.0f * ih);
+                weight = SchlickF(R, ih) * (((GgxG1(ni, a2) * GgxG1(no, a2)) * ih) / (ni * nh));
+            }
+        } else { /* PT_BSDF_DIELECTRIC */
+            float ng = (ext.ior > 0.0f) ? ext.ior : RefractiveIndexBK7Glass(l.w);
+            float n1 = inside ? ng : 1.0f, n2 = inside ? 1.0f : ng;
+            float eta = n1 / n2;
+            float cosi = -dot(d, n);
+            float sin2t = eta * eta * (1.0f - cosi * cosi);
+            float F = 1.0f, cost = 0.0f;
+            if (sin2t < 1.0f) {
+                cost = gsqrt(1.0f - sin2t);
+                float rs = (n1 * cosi - n2 * cost) / (n1 * cosi + n2 * cost);
+                float rp = (n2 * cosi - n1 * cost) / (n2 * cosi + n1 * cost);
+                F = 0.5f * (rs * rs + rp * rp);
+            }
+            float u = RandomFloatPCG32(seed);
+            if (u < F) {
+                outDir = Reflect(d, n);
+                weight = v4(1.0f);
+            } else {
+                float k = eta * cosi - cost;
+                outDir = normalize(v3(eta * d.x + k * n.x, eta * d.y + k * n.y, eta * d.z + k * n.z));
+                inside = !inside;
+            }
+        }
+    }
+
+    /* shader.comp:1298-1343 (glossy: not in the reference -- the light sample is weighted with the extension's lobe) */
     V4 SampleLightSource(V4 l, V4 rayradiance, Ray outRay, V3 normal, const Material& mat, uint32_t& seed,
-                         float BRDFpdf, float& MISBRDFWeight) const {
+                         float BRDFpdf, float& MISBRDFWeight, const GlossyLobe* glossy = nullptr) const {
         float boundingRadius = 0.0f;
         V3 lightPos = v3(0.0f);
         float lightIDOut = -1.0f;
@@ -1153,7 +1247,8 @@ struct Shader {
                         CNT(C_LIGHT_VISIBLE, 1);
                         Light lt;
                         GetLightMix(lt, lightIDOut);
-                        rayradiance = rayradiance * (EvaluateBRDF(l, mat) * costheta / lightpdf);
+                        V4 f = glossy ? GgxEval(glossy->i, outRay.dir, normal, glossy->a2, glossy->R) : EvaluateBRDF(l, mat);
+                        rayradiance = rayradiance * (f * costheta / lightpdf);
                         return Emit(l, lt) * rayradiance * (1.0f - MISBRDFWeight);
                     }
                 } else {
@@ -1167,12 +1262,13 @@ struct Shader {
     }
 
     /* shader.comp:1345-1391 */
-    V4 TraceRay(V4 l, V4& rayradiance, Ray& inRay, uint32_t& seed, float& MISBRDFWeight, bool& isTerminate) const {
+    V4 TraceRay(V4 l, V4& rayradiance, Ray& inRay, uint32_t& seed, float& MISBRDFWeight, bool& isTerminate, bool& inside) const {
         V4 radiance = v4(0.0f);
         V3 normal = v3(0.0f);
         float materialID = 0.0f;
         float lightID = -1.0f;
-        float hitdist = Intersection(inRay, normal, materialID, lightID);
+        bool sdfHit = false;
+        float hitdist = Intersection(inRay, normal, materialID, lightID, &sdfHit);
         Material mat;
         Light lt;
         GetMaterialMix(mat, materialID);
@@ -1187,6 +1283,36 @@ struct Shader {
             }
             CNT(C_BOUNCE, 1);
             outRay.origin = vfma(inRay.dir, v3(hitdist), inRay.origin);
+            if (const pt_surface_ext* ext = SurfaceExtOf(materialID)) { /* not reference behaviour: surface extensions */
+                V3 nf = (dot(inRay.dir, normal) > 0.0f) ? -normal : normal;
+                V4 R = EvaluateBRDF(l, mat) * PI;
+                V4 weight = v4(0.0f);
+                float pdf = 0.0f;
+                bool dead = false;
+                SurfaceExtSample(*ext, inRay.dir, nf, R, l, seed, inside, outRay.dir, weight, pdf, dead);
+                /* The next ray starts off the surface, on the side it leaves to: the reference's primitives reject hits
+                 * nearer than 1e-4 and its Lambertian never sends a ray INTO a surface; a refracted ray that starts on a
+                 * sphere sees its near root at +-1 ulp and, when it comes out positive, misses the far side as well.
+                 * SDF hits already sit 1e-3 in front of their surface (shader.comp:853), so they step further. */
+                float side = (dot(outRay.dir, nf) > 0.0f) ? 1.0f : -1.0f;
+                float eps = side * (sdfHit ? 2e-3f : 2e-4f);
+                outRay.origin = v3(outRay.origin.x + nf.x * eps, outRay.origin.y + nf.y * eps, outRay.origin.z + nf.z * eps);
+                if (ext->bsdf == PT_BSDF_GLOSSY && !dead && numObjects(6) > 0.0f) {
+                    GlossyLobe lobe = {-inRay.dir, GgxAlpha2(ext->roughness), R};
+                    radiance = SampleLightSource(l, rayradiance, outRay, nf, mat, seed, pdf, MISBRDFWeight, &lobe);
+                } else {
+                    MISBRDFWeight = 1.0f;
+                }
+                rayradiance = rayradiance * weight;
+                float p = gclamp(gmax(rayradiance.x, gmax(rayradiance.y, gmax(rayradiance.z, rayradiance.w))), 0.0f, 0.99f);
+                if ((RandomFloatPCG32(seed) > p) || dead) {
+                    isTerminate = true;
+                    return radiance;
+                }
+                rayradiance = rayradiance * (1.0f / p);
+                inRay = outRay;
+                return radiance;
+            }
             outRay.dir = SampleBRDF(normal, seed);
             float BRDFpdf = BRDFPDF(outRay.dir, normal);
             radiance = SampleLightSource(l, rayradiance, outRay, normal, mat, seed, BRDFpdf, MISBRDFWeight);
@@ -1213,8 +1339,9 @@ struct Shader {
         V4 rayradiance = v4(1.0f);
         float MISBRDFWeight = 1.0f;
         bool isTerminate = false;
+        bool inside = false; /* surface extensions only: inside a dielectric */
         for (int i = 0; i < pc.pathLength; i++) {
-            radiance = radiance + TraceRay(l, rayradiance, ray, seed, MISBRDFWeight, isTerminate);
+            radiance = radiance + TraceRay(l, rayradiance, ray, seed, MISBRDFWeight, isTerminate, inside);
             if (isTerminate) break;
         }
         return radiance;
@@ -1364,6 +1491,13 @@ int oracle_bvh_build(const pt_ubo* ubo) {
     return (int)g_bvh_blob.size();
 }
 #endif
+
+/* surface extensions (pt_set_surface_ext's twin): n = 0 restores the reference's shading.  Process-global. */
+int oracle_set_surface_ext(const pt_surface_ext* table, int n) {
+    if (n < 0 || n > PT_MAX_SURFACE_EXT || (n > 0 && !table)) return -1;
+    g_surface_ext.assign(table, table + n);
+    return 0;
+}
 
 void oracle_set_threads(int n) { g_threads = n; }
 int oracle_max_threads(void) {
@@ -1527,6 +1661,22 @@ void oracle_emit(const float* l4, float temperature, float luminosity, float* ou
 void oracle_spd(const float* l4, float peak, float sigma, int invert, float* out4) {
     V4 v = Shader::SpectralPowerDistribution(v4(l4[0], l4[1], l4[2], l4[3]), peak, sigma, invert);
     out4[0] = v.x; out4[1] = v.y; out4[2] = v.z; out4[3] = v.w;
+}
+/* surface extensions, one scattering event (tests/test_surface_ext.py): d, n unit vectors with dot(d, n) <= 0.
+ * Returns 1 when the path dies; seed and inside are updated in place; out = dir xyz, weight xyzw, pdf */
+int oracle_surface_ext_sample(const pt_surface_ext* ext, const float* d3, const float* n3, const float* R4, const float* l4,
+                              uint32_t* seed, int* inside, float* out8) {
+    V3 o = v3(0.0f); V4 w = v4(0.0f); float pdf = 0.0f; bool dead = false, in = *inside != 0;
+    Shader::SurfaceExtSample(*ext, v3(d3[0], d3[1], d3[2]), v3(n3[0], n3[1], n3[2]), v4(R4[0], R4[1], R4[2], R4[3]),
+                             v4(l4[0], l4[1], l4[2], l4[3]), *seed, in, o, w, pdf, dead);
+    *inside = in ? 1 : 0;
+    out8[0] = o.x; out8[1] = o.y; out8[2] = o.z; out8[3] = w.x; out8[4] = w.y; out8[5] = w.z; out8[6] = w.w; out8[7] = pdf;
+    return dead ? 1 : 0;
+}
+void oracle_ggx_eval(const float* i3, const float* o3, const float* n3, float roughness, const float* f04, float* out4) {
+    V4 f = Shader::GgxEval(v3(i3[0], i3[1], i3[2]), v3(o3[0], o3[1], o3[2]), v3(n3[0], n3[1], n3[2]), Shader::GgxAlpha2(roughness),
+                           v4(f04[0], f04[1], f04[2], f04[3]));
+    out4[0] = f.x; out4[1] = f.y; out4[2] = f.z; out4[3] = f.w;
 }
 void oracle_rotation_matrix(const float* deg3, float* m9) { /* column-major like GLSL */
     M3 m = Shader::RotationMatrix(v3(deg3[0], deg3[1], deg3[2]));

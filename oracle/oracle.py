@@ -41,6 +41,7 @@ def lib(count=False, bvh=False):
         L.oracle_samples.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.oracle_dispatch_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.oracle_load_sdf.argtypes = [C.c_char_p]
+        L.oracle_set_surface_ext.argtypes = [C.c_void_p, C.c_int]
         if bvh:
             L.oracle_bvh_build.argtypes = [C.c_void_p]
         _libs[name] = L
@@ -54,7 +55,7 @@ def _p(a):
 class Oracle:
     """One scene bound to the CPU oracle. `ubo` float32[4097], `sdf_sources` list of GLSL strings."""
 
-    def __init__(self, ubo, sdf_sources=(), count=False, threads=0, bvh=False):
+    def __init__(self, ubo, sdf_sources=(), count=False, threads=0, bvh=False, surface_ext=None):
         """bvh=True: liboracle_bvh.so, the checker that routes the closest-hit search through the PRODUCT's BVH
         (pt_bvh.cpp) with the oracle's primitives at the leaves; must render what the plain oracle renders."""
         self.L = lib(count, bvh)
@@ -64,8 +65,12 @@ class Oracle:
         assert self.ubo.size == pack.UBO_FLOATS
         self.sdf_so = sdf_build.build(list(sdf_sources))
         self.threads = threads
+        # surface extensions (pt_surface_ext table; NOT reference behaviour, parity unpinned): None = the reference's shading
+        self.surface_ext = np.ascontiguousarray(surface_ext if surface_ext is not None else [], dtype=pack.SURFACE_EXT_DTYPE)
 
     def _bind(self):
+        if self.L.oracle_set_surface_ext(_p(self.surface_ext) if self.surface_ext.size else None, int(self.surface_ext.size)) != 0:
+            raise RuntimeError('oracle: bad surface extension table')
         if self.L.oracle_load_sdf(self.sdf_so.encode()) != 0:
             raise RuntimeError('oracle: cannot load SDF dispatchers %s' % self.sdf_so)
         self.L.oracle_set_threads(int(self.threads))
@@ -155,4 +160,4 @@ def math_eval(fn, x, y=None):
 
 def from_scene_file(path, count=False, threads=0):
     scene = pack.load_scene(path)
-    return Oracle(pack.pack_ubo(scene), pack.sdf_sources(scene), count=count, threads=threads), scene
+    return Oracle(pack.pack_ubo(scene), pack.sdf_sources(scene), count=count, threads=threads, surface_ext=pack.surface_ext(scene)), scene

@@ -124,5 +124,22 @@ def pack_params(scene, shot=1, width=512, height=512, spf=1, path_length=5, disp
     return p
 
 
+SURFACE_EXT_DTYPE = np.dtype([('bsdf', '<i4'), ('roughness', '<f4'), ('ior', '<f4'), ('pad', '<f4')])  # pt_surface_ext
+
+
+def surface_ext(scene):
+    """The optional material keys "bsdf" / "roughness" / "ior" (an extension of the reference's schema; no
+    shipped scene has them) as a pt_surface_ext table: entry i extends material i; empty when no material has a "bsdf"."""
+    names = {'reference': 0, 'diffuse': 0, 'mirror': 1, 'glossy': 2, 'dielectric': 3}
+    mats = scene.get('material', [])
+    n = max([i + 1 for i, m in enumerate(mats) if names[m.get('bsdf', 'reference')] != 0], default=0)
+    t = np.zeros(n, dtype=SURFACE_EXT_DTYPE)
+    for i in range(n):
+        t[i]['bsdf'] = names[mats[i].get('bsdf', 'reference')]
+        t[i]['roughness'] = mats[i].get('roughness', 0.0)
+        t[i]['ior'] = mats[i].get('ior', 0.0)
+    return t
+
+
 def sdf_sources(scene):
     return [s['glsl'] for s in scene.get('sdf', [])]

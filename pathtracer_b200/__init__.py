@@ -4,7 +4,9 @@ Nothing in here computes: the hot path is hand-written sm_100a CUDA behind the C
 There is no CPU fallback; importing works anywhere, creating a Renderer needs a CUDA device and the built library.
 """
 from .api import (kernel_compile_check, LibraryNotBuilt, MultiRenderer, PtError, Renderer, Scene, build_library, lib, library_path, MODE_FAST, MODE_STRICT,
-                  PARAMS_DTYPE, PIPE_MEGAKERNEL, PIPE_WAVEFRONT, UBO_FLOATS)
+                  PARAMS_DTYPE, PIPE_MEGAKERNEL, PIPE_WAVEFRONT, UBO_FLOATS, SURFACE_EXT_DTYPE, BSDF_REFERENCE, BSDF_MIRROR,
+                  BSDF_GLOSSY, BSDF_DIELECTRIC)
 
 __all__ = ['LibraryNotBuilt', 'MultiRenderer', 'PtError', 'Renderer', 'Scene', 'build_library', 'lib', 'library_path', 'MODE_FAST',
-           'MODE_STRICT', 'PARAMS_DTYPE', 'PIPE_MEGAKERNEL', 'PIPE_WAVEFRONT', 'UBO_FLOATS']
+           'MODE_STRICT', 'PARAMS_DTYPE', 'PIPE_MEGAKERNEL', 'PIPE_WAVEFRONT', 'UBO_FLOATS', 'SURFACE_EXT_DTYPE', 'BSDF_REFERENCE',
+           'BSDF_MIRROR', 'BSDF_GLOSSY', 'BSDF_DIELECTRIC', 'kernel_compile_check']

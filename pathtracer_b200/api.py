@@ -28,6 +28,10 @@ PARAMS_DTYPE = np.dtype([
     ('apertureSize', '<f4'), ('apertureDist', '<f4'), ('lensRadius', '<f4'), ('lensFocalLength', '<f4'),
     ('lensThickness', '<f4'), ('lensDistance', '<f4'), ('tonemap', '<i4')])
 assert PARAMS_DTYPE.itemsize == 88
+# pt_surface_ext (pt_abi.h): the surface extensions of SURVEY 8f-4 -- not reference behaviour, off by default
+SURFACE_EXT_DTYPE = np.dtype([('bsdf', '<i4'), ('roughness', '<f4'), ('ior', '<f4'), ('pad', '<f4')])
+BSDF_REFERENCE, BSDF_MIRROR, BSDF_GLOSSY, BSDF_DIELECTRIC = 0, 1, 2, 3
+MAX_SURFACE_EXT = 64
 
 
 class PtError(RuntimeError):
@@ -90,6 +94,9 @@ def lib():
         L.pt_set_bvh.argtypes = [vp, ci]
         L.pt_bvh_active.argtypes = [vp]
         L.pt_set_scene.argtypes = [vp, vp, C.POINTER(C.c_char_p), ci]
+        L.pt_set_surface_ext.argtypes = [vp, vp, ci]
+        L.pt_multi_set_surface_ext.argtypes = [vp, vp, ci]
+        L.pt_scene_surface_ext.argtypes = [vp, vp, ci]
         L.pt_resize.argtypes = [vp, ci, ci]
         L.pt_bind_image.argtypes = [vp, vp, ci, ci]
         L.pt_clear.argtypes = [vp]
@@ -181,12 +188,13 @@ def sdf_compile_check(sources, sdfs_raw=None, mode=MODE_STRICT):
     _check(lib().pt_sdf_compile_check(_c_strings(sources), len(sources), _ptr(raw), mode))
 
 
-def kernel_compile_check(ubo, sources, mode=MODE_STRICT, bake_counts=True, options=None, wavefront=False, bvh=False):
+def kernel_compile_check(ubo, sources, mode=MODE_STRICT, bake_counts=True, options=None, wavefront=False, bvh=False,
+                         surface_ext=False):
     """NVRTC compile-only check of the kernel pt_set_scene would build (needs no GPU).  `options` is a dict of
     pt_set_option keys.  Returns the ptxas report (registers, spills, shared memory)."""
     ubo = np.ascontiguousarray(ubo, dtype=np.float32)
     opts = ','.join('%s=%d' % (k, int(v)) for k, v in (options or {}).items()).encode()
-    m = int(mode) | (2 if wavefront else 0) | (4 if bvh else 0)
+    m = int(mode) | (2 if wavefront else 0) | (4 if bvh else 0) | (8 if surface_ext else 0)
     _check(lib().pt_kernel_compile_check_opts(_ptr(ubo), _c_strings(list(sources)), len(sources), m, int(bool(bake_counts)), opts))
     return (lib().pt_last_error(None) or b'').decode(errors='replace')
 
@@ -239,6 +247,13 @@ class Scene:
         ubo = np.zeros(UBO_FLOATS, dtype=np.float32)
         _check(lib().pt_scene_pack_ubo(self._h, _ptr(ubo)))
         return ubo
+
+    def surface_ext(self):
+        """The materials' optional "bsdf" / "roughness" / "ior" keys as a pt_surface_ext table (empty: none set)."""
+        t = np.zeros(MAX_SURFACE_EXT, dtype=SURFACE_EXT_DTYPE)
+        n = lib().pt_scene_surface_ext(self._h, _ptr(t), MAX_SURFACE_EXT)
+        _check(min(n, 0))
+        return t[:n].copy()
 
     def pack_params(self, shot=1, width=1280, height=720, spf=1, path_length=5):
         p = np.zeros((), dtype=PARAMS_DTYPE)
@@ -306,6 +321,12 @@ class Renderer:
     @property
     def bvh_active(self):
         return bool(lib().pt_bvh_active(self._ctx))
+
+    def set_surface_ext(self, table=None):
+        """pt_set_surface_ext: table = SURFACE_EXT_DTYPE array (entry i extends material i), None / empty = reference
+        shading.  Takes effect at the next set_scene."""
+        t = np.ascontiguousarray(table if table is not None else [], dtype=SURFACE_EXT_DTYPE)
+        _check(lib().pt_set_surface_ext(self._ctx, _ptr(t) if t.size else None, int(t.size)), self._ctx)
 
     def set_scene(self, ubo, sdf_sources=()):
         ubo = np.ascontiguousarray(ubo, dtype=np.float32)
@@ -418,6 +439,10 @@ class MultiRenderer:
             self._m = None
 
     __del__ = close
+
+    def set_surface_ext(self, table=None):
+        t = np.ascontiguousarray(table if table is not None else [], dtype=SURFACE_EXT_DTYPE)
+        self._ok(lib().pt_multi_set_surface_ext(self._m, _ptr(t) if t.size else None, int(t.size)))
 
     def set_scene(self, ubo, sdf_sources=()):
         ubo = np.ascontiguousarray(ubo, dtype=np.float32)

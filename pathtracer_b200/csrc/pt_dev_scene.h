@@ -77,15 +77,28 @@ typedef struct PtDevLightSlot { /* what SampleRandomLightSource (shader.comp:122
     float pad[2];
 } PtDevLightSlot;
 
+/* Surface extension of one material (mirror / glossy / dielectric surfaces -- NOT in the reference, whose
+ * every surface is the Lambertian of shader.comp:1075-1091; pt_set_surface_ext, pt_abi.h).  Entry i extends material i
+ * (0-based, the scene file's order = floor(materialID) in the kernel). */
+#define PT_DEV_MAX_SURFACE_EXT 64
+typedef struct PtDevSurfaceExt {
+    int bsdf;            /* pt_bsdf: 0 the reference's Lambertian, 1 mirror, 2 glossy (GGX conductor), 3 dielectric */
+    float roughness;     /* glossy: GGX alpha = roughness^2 */
+    float ior;           /* dielectric: index of refraction; 0 = BK7 Sellmeier at the hero wavelength (shader.comp:1064-1073) */
+    float pad;
+} PtDevSurfaceExt;
+
 typedef struct PtDevScene {
     int nSpheres, nPlanes, nBoxes, nLenses, nCyclides, nSdfs, nLightSlots;
     float numLights;     /* numObjects[6] as the float the shader multiplies with */
     float invNumLights;  /* 1.0 / numObjects[6] (shader.comp:1289) */
     /* offsets (in floats) of each type's records inside pool; spheres start at 0 */
     int offPlanes, offBoxes, offLenses, offCyclides, offSdfs;
-    int pad0[2];
+    int nSurfaceExt;     /* 0: every surface is the reference's (the kernels are then built without the extension code) */
+    int pad0;
     float pool[PT_DEV_POOL_FLOATS]; /* PtDevSphere[], PtDevPlane[], PtDevBox[], PtDevLens[], PtDevCyclide[], PtDevSdf[] */
     PtDevLightSlot lightSlots[PT_DEV_MAX_LIGHT_SLOTS];
+    PtDevSurfaceExt surfaceExt[PT_DEV_MAX_SURFACE_EXT];
 } PtDevScene;
 
 /* Per-dispatch constants: the push constants (shader.comp:31-52) plus what Scene()/TracePathLens() derive from them */

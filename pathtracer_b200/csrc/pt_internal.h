@@ -11,6 +11,7 @@
 
 /* pt_prepare.cpp */
 int pt_prepare_scene(const pt_ubo* ubo, PtDevScene* sc, std::string* err);
+bool pt_prepare_surface_ext(const pt_surface_ext* table, int n, PtDevScene* sc);
 int pt_prepare_params(const pt_params* p, int accum_mode, int first_sample, int n_samples, PtDevParams* d,
                       std::string* err);
 
@@ -49,6 +50,7 @@ struct PtJitOptions {
     bool wavefront;      /* also build the wavefront pipeline's kernels (pt_wavefront.cuh) */
     bool bvh;            /* closest hit through the BVH of pt_bvh.h instead of the brute-force scan */
     int counts[6];       /* spheres, planes, boxes, lenses, cyclides, sdfs */
+    bool surface_ext = false; /* the scene carries surface extensions (pt_set_surface_ext): build the kernel with them */
     PtKnobs knobs;
 };
 /* the complete translation unit pt_jit_compile would hand to NVRTC (also the key of every kernel cache) */

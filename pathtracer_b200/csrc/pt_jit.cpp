@@ -153,6 +153,7 @@ std::string pt_jit_source(const std::string& sdf_unit, const PtJitOptions& opt) 
                                     : "#define PT_KERNEL_NS ptk_jit_strict\n";
     if (!sdf_unit.empty()) src += "#define PT_HAS_SDF 1\n";
     if (opt.bvh) src += "#define PT_BVH 1\n";
+    if (opt.surface_ext) src += "#define PT_EXT_BSDF 1\n";
     if (opt.bake_counts) {
         const char* names[6] = {"PT_N_SPHERES_CONST", "PT_N_PLANES_CONST", "PT_N_BOXES_CONST", "PT_N_LENSES_CONST",
                                 "PT_N_CYCLIDES_CONST", "PT_N_SDF_CONST"};

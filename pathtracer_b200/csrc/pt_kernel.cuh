@@ -61,6 +61,9 @@
 #ifndef PT_HAS_SDF
 #define PT_HAS_SDF 0
 #endif
+#ifndef PT_EXT_BSDF
+#define PT_EXT_BSDF 0 /* 1: the scene carries surface extensions (pt_set_surface_ext); 0 = the reference's shading, untouched */
+#endif
 
 #define PT_DEV __device__ __forceinline__
 #define PT_DEV_NOINLINE __device__ __noinline__
@@ -938,6 +941,7 @@ struct PathState {
     bool isShadow;      /* the ray being traced is the shadow ray (origin = ray.origin, direction = shDir) */
     bool pathAlive;     /* whether the path continues after the pending shadow ray */
     bool pendingFinish; /* a finished path whose radiance is still to be projected to XYZ */
+    bool inside;        /* PT_EXT_BSDF: the path is inside a dielectric (toggled by every refraction); else always false */
     V3 shDir;
     V4 shContrib;       /* added to radiance iff the shadow ray sees object shObj (kDeferEmit: the factor Emit() is scaled by) */
     int shObj;
@@ -957,7 +961,7 @@ PT_DEV void PathStateInit(PathState& ps) {
     const V4 z4 = mk4(0.0f, 0.0f, 0.0f, 0.0f);
     ps.ray.origin = z3; ps.ray.dir = z3; ps.l = z4; ps.radiance = z4; ps.rayradiance = z4;
     ps.MISBRDFWeight = 1.0f; ps.seed = 0u; ps.bounce = 0;
-    ps.isShadow = false; ps.pathAlive = false; ps.pendingFinish = false;
+    ps.isShadow = false; ps.pathAlive = false; ps.pendingFinish = false; ps.inside = false;
     ps.shDir = z3; ps.shContrib = z4; ps.shObj = 0; ps.shScale = 0.0f; ps.shT = 0.0f; ps.shL = 0.0f;
     ps.h.t = 1e5f; ps.h.normal = z3; ps.h.materialID = 0.0f; ps.h.lightID = -1.0f; ps.h.objectID = -1;
 }
@@ -1029,6 +1033,7 @@ PT_DEV int PhaseNew(const Ctx& c, PathState& ps, unsigned xyx, unsigned xyy, int
     ps.MISBRDFWeight = 1.0f;
     ps.bounce = 0;
     ps.isShadow = false;
+    ps.inside = false;
     if (pr.pathLength > 0) return PT_ST_ISECT;
     ps.pendingFinish = true;
     return PT_ST_NEW;
@@ -1198,6 +1203,109 @@ PT_DEV int PhaseTrivial(PathState& ps) {
     return PT_ST_SHADE;
 }
 
+#if PT_EXT_BSDF
+/* ---- surface extensions --------------------------------------------------------------------------------
+ * NOT reference behaviour: shader.comp shades every surface as a Lambertian (1075-1091) and its TODO.md:2 lists
+ * "Specular, Glossy Materials, Etc" as future work, so nothing here can be parity-checked against the reference.  The
+ * checker is oracle/oracle.cpp's own statement of the same definitions plus the physical
+ * invariants of tests/test_surface_ext.py.  A scene without extensions compiles none of this.
+ *   mirror      o = reflect(d, n); throughput *= R(lambda); no light sampling (delta lobe)
+ *   glossy      GGX conductor, alpha = roughness^2, Schlick Fresnel with F0 = R(lambda), Smith G1*G1; the half vector is
+ *               drawn from D(h)(n.h); light sampling + the reference's MIS weighting with this lobe's pdf
+ *   dielectric  exact unpolarised Fresnel at eta = n1/n2 (n = ior, or BK7 at the hero wavelength l.w like the camera
+ *               lens: the bundle follows the hero's direction); reflect with probability F, else refract and tint by
+ *               R(lambda); `inside` toggles at every refraction
+ * R(lambda) = EvaluateBRDF * PI = the material's spectrum; n is turned to face the incoming ray first. */
+PT_DEV PtDevSurfaceExt SurfaceExtOf(const Ctx& c, float materialID) {
+    PtDevSurfaceExt e;
+    e.bsdf = 0; e.roughness = 0.0f; e.ior = 0.0f; e.pad = 0.0f;
+    const int m = __float2int_rz(floorf(materialID));
+    if (m >= 0 && m < c.sc->nSurfaceExt) e = c.sc->surfaceExt[m];
+    return e;
+}
+PT_DEV V3 Reflect3(V3 I, V3 N) { /* GLSL 4.50 8.5: I - 2 dot(N, I) N */
+    const float d = 2.0f * dot(N, I);
+    return mk3(I.x - d * N.x, I.y - d * N.y, I.z - d * N.z);
+}
+PT_DEV float GgxD(float nh, float a2) {
+    const float q = nh * nh * (a2 - 1.0f) + 1.0f;
+    return PTK_DIV(a2, PT_PI_F * (q * q));
+}
+PT_DEV float GgxG1(float nv, float a2) { return PTK_DIV(2.0f * nv, nv + PTK_SQRT(a2 + (1.0f - a2) * (nv * nv))); }
+PT_DEV V4 SchlickF(V4 f0, float ih) {
+    const float m = PTK_MIN(PTK_MAX(1.0f - ih, 0.0f), 1.0f);
+    const float m2 = m * m;
+    const float m5 = m2 * m2 * m;
+    return mk4(f0.x + (1.0f - f0.x) * m5, f0.y + (1.0f - f0.y) * m5, f0.z + (1.0f - f0.z) * m5, f0.w + (1.0f - f0.w) * m5);
+}
+PT_DEV float GgxAlpha2(float roughness) {
+    const float a = roughness * roughness;
+    return PTK_MAX(a * a, 1e-8f);
+}
+/* the GGX lobe f(i, o) without the cosine; i = -ray direction, all three on the side of n */
+PT_DEV V4 GgxEval(V3 i, V3 o, V3 n, float a2, V4 f0) {
+    const float ni = dot(n, i), no = dot(n, o);
+    if (!(ni > 0.0f) || !(no > 0.0f)) return mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    const V3 h = normalize(i + o);
+    const float nh = dot(n, h), ih = dot(i, h);
+    const float k = PTK_DIV(GgxD(nh, a2) * (GgxG1(ni, a2) * GgxG1(no, a2)), 4.0f * ni * no);
+    return SchlickF(f0, ih) * k;
+}
+/* One scattering event of an extended surface.  In: ray direction d, facing normal n (dot(d, n) <= 0), spectrum R.
+ * Out: the next direction, the throughput factor f cos / pdf, the lobe's pdf for the MIS weight (0 for the delta lobes),
+ * whether the path dies here (sampled below the surface).  Draws: mirror none, glossy 2, dielectric 1. */
+PT_DEV void SurfaceExtSample(const PtDevSurfaceExt& ext, V3 d, V3 n, V4 R, V4 l, unsigned& seed, bool& inside, V3& outDir, V4& weight,
+                             float& pdf, bool& dead) {
+    pdf = 0.0f;
+    dead = false;
+    weight = R;
+    if (ext.bsdf == 1) {
+        outDir = Reflect3(d, n);
+    } else if (ext.bsdf == 2) {
+        const float a2 = GgxAlpha2(ext.roughness);
+        const float u1 = RandomFloatPCG32(seed);
+        const float u2 = RandomFloatPCG32(seed);
+        const float cos2 = PTK_DIV(1.0f - u1, 1.0f + (a2 - 1.0f) * u1);
+        const float cosT = PTK_SQRT(cos2);
+        const float sinT = PTK_SQRT(PTK_MAX(1.0f - cos2, 0.0f));
+        const float phi = 2.0f * PT_PI_F * u2;
+        const V3 h = ToWorld(mk3(PTK_COS(phi) * sinT, PTK_SIN(phi) * sinT, cosT), n);
+        outDir = Reflect3(d, h);
+        const V3 i = -d;
+        const float ni = dot(n, i), no = dot(n, outDir), nh = dot(n, h), ih = dot(i, h);
+        if (!(no > 0.0f) || !(ih > 0.0f) || !(ni > 0.0f)) {
+            dead = true;
+            weight = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+        } else {
+            pdf = PTK_DIV(GgxD(nh, a2) * nh, 4.0f * ih);
+            weight = SchlickF(R, ih) * PTK_DIV((GgxG1(ni, a2) * GgxG1(no, a2)) * ih, ni * nh);
+        }
+    } else {
+        const float ng = (ext.ior > 0.0f) ? ext.ior : RefractiveIndexBK7Glass(l.w);
+        const float n1 = inside ? ng : 1.0f, n2 = inside ? 1.0f : ng;
+        const float eta = PTK_DIV(n1, n2);
+        const float cosi = -dot(d, n);
+        const float sin2t = eta * eta * (1.0f - cosi * cosi);
+        float F = 1.0f, cost = 0.0f;
+        if (sin2t < 1.0f) {
+            cost = PTK_SQRT(1.0f - sin2t);
+            const float rs = PTK_DIV(n1 * cosi - n2 * cost, n1 * cosi + n2 * cost);
+            const float rp = PTK_DIV(n2 * cosi - n1 * cost, n2 * cosi + n1 * cost);
+            F = 0.5f * (rs * rs + rp * rp);
+        }
+        const float u = RandomFloatPCG32(seed);
+        if (u < F) {
+            outDir = Reflect3(d, n);
+            weight = mk4(1.0f, 1.0f, 1.0f, 1.0f);
+        } else {
+            const float k = eta * cosi - cost;
+            outDir = normalize(mk3(eta * d.x + k * n.x, eta * d.y + k * n.y, eta * d.z + k * n.z));
+            inside = !inside;
+        }
+    }
+}
+#endif /* PT_EXT_BSDF */
+
 /* SHADE: TraceRay after Intersection (shader.comp:1352-1390) with SampleLightSource (1298-1343) for a path ray that hit
  * something -- THE statement of the bounce arithmetic, shared by every driver and by the wavefront pipeline.
  * The light sample's visibility test is not traced here: the sampled direction, the object to look for and the
@@ -1218,11 +1326,31 @@ PT_DEV int PhaseShadeHitT(const Ctx& c, PathState& ps) {
         float peak, sigma, invertf;
         GetMaterialMix(c, ps.h.materialID, peak, sigma, invertf);
         const V4 brdf = EvaluateBRDF(ps.l, peak, sigma, invertf);
-        const V3 n = ps.h.normal;
+        V3 n = ps.h.normal;
         outOrigin = fma3(ps.ray.dir, ps.h.t, ps.ray.origin);
-        outDir = SampleCosineDirectionHemisphere(n, ps.seed);
-        const float BRDFpdf = PTK_DIV(dot(outDir, n), PT_PI_F);
-        if (sc.numLights > 0.0f) { /* SampleLightSource, shader.comp:1298-1343 */
+        float BRDFpdf;
+        bool sampleLights = sc.numLights > 0.0f;
+#if PT_EXT_BSDF
+        const PtDevSurfaceExt ext = SurfaceExtOf(c, ps.h.materialID);
+        const V4 spectrum = brdf * PT_PI_F; /* R(lambda) */
+        V4 extWeight = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+        bool extDead = false;
+        if (ext.bsdf != 0) {
+            if (dot(ps.ray.dir, n) > 0.0f) n = -n; /* cyclide and SDF normals are not turned towards the ray */
+            SurfaceExtSample(ext, ps.ray.dir, n, spectrum, ps.l, ps.seed, ps.inside, outDir, extWeight, BRDFpdf, extDead);
+            /* the next ray starts off the surface, on the side it leaves to (the reference's primitives reject hits nearer
+             * than 1e-4 and never see a ray that starts on a surface and goes INTO it; SDF hits sit 1e-3 in front) */
+            const float side = (dot(outDir, n) > 0.0f) ? 1.0f : -1.0f;
+            const float eps = side * ((ps.h.objectID < 0) ? 2e-3f : 2e-4f);
+            outOrigin = mk3(outOrigin.x + n.x * eps, outOrigin.y + n.y * eps, outOrigin.z + n.z * eps);
+            sampleLights = sampleLights && (ext.bsdf == 2) && !extDead; /* delta lobes: nothing to connect */
+        } else
+#endif
+        {
+            outDir = SampleCosineDirectionHemisphere(n, ps.seed);
+            BRDFpdf = PTK_DIV(dot(outDir, n), PT_PI_F);
+        }
+        if (sampleLights) { /* SampleLightSource, shader.comp:1298-1343 */
             const int randomLight = __float2int_rz(floorf(RandomFloatPCG32(ps.seed) * sc.numLights));
             const PtDevLightSlot& ls = sc.lightSlots[randomLight < sc.nLightSlots ? randomLight : sc.nLightSlots - 1];
             const V3 toLight = mk3(ls.px - outOrigin.x, ls.py - outOrigin.y, ls.pz - outOrigin.z);
@@ -1239,7 +1367,12 @@ PT_DEV int PhaseShadeHitT(const Ctx& c, PathState& ps) {
             if (costheta >= 0.0f) {
                 if (RandomFloatPCG32(ps.seed) > deathProbability) {
                     GetLightMix(c, ls.lightID, emitT, emitL);
-                    rr = ps.rayradiance * mulDiv4(brdf, costheta, lightpdf);
+#if PT_EXT_BSDF
+                    const V4 fLight = (ext.bsdf == 2) ? GgxEval(-ps.ray.dir, sdir, n, GgxAlpha2(ext.roughness), spectrum) : brdf;
+#else
+                    const V4 fLight = brdf;
+#endif
+                    rr = ps.rayradiance * mulDiv4(fLight, costheta, lightpdf);
                     emitScale = 1.0f - ps.MISBRDFWeight;
                     ps.shDir = sdir;
                     ps.shObj = ls.objectID;
@@ -1249,15 +1382,29 @@ PT_DEV int PhaseShadeHitT(const Ctx& c, PathState& ps) {
                 }
             }
         } else {
+#if PT_EXT_BSDF
+            if (ext.bsdf != 0) ps.MISBRDFWeight = 1.0f; /* the next emitter hit counts in full */
+            else
+#endif
             ps.MISBRDFWeight = PTK_DIV(BRDFpdf * BRDFpdf, BRDFpdf * BRDFpdf + 0.0f * 0.0f);
         }
-        const float costheta = dot(outDir, n);
-        ps.rayradiance = ps.rayradiance * mulDiv4(brdf, costheta, BRDFpdf);
+#if PT_EXT_BSDF
+        if (ext.bsdf != 0) {
+            ps.rayradiance = ps.rayradiance * extWeight;
+        } else
+#endif
+        {
+            const float costheta = dot(outDir, n);
+            ps.rayradiance = ps.rayradiance * mulDiv4(brdf, costheta, BRDFpdf);
+        }
         const V4 t4 = ps.rayradiance;
         const float mx = PTK_MAX(t4.x, PTK_MAX(t4.y, PTK_MAX(t4.z, t4.w)));
         const float rayProbability = PTK_MIN(PTK_MAX(mx, 0.0f), 0.99f);
         alive = !(RandomFloatPCG32(ps.seed) > rayProbability);
         if (alive) ps.rayradiance = ps.rayradiance * PTK_DIV(1.0f, rayProbability);
+#if PT_EXT_BSDF
+        if (extDead) alive = false;
+#endif
         ps.bounce++;
         if (ps.bounce >= c.pr->pathLength) alive = false; /* TracePath's loop bound, shader.comp:1400 */
     }
@@ -1601,6 +1748,7 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
         if (bHv != 0u && (__popc(bHv) >= PT_HEAVY_MIN || best < PT_FEED_T)) phase = PT_ST_HEAVY;
 #endif
         PT_STAT(phase == PT_ST_HEAVY ? PT_ST_ISECT : phase, phase == PT_ST_NEW ? bNew : (phase == PT_ST_ISECT ? bIs : (phase == PT_ST_SDF ? bSdf : bSh)));
+        const bool ran = (st == phase) && (phase == PT_ST_ISECT || phase == PT_ST_SDF);
         if (phase == PT_ST_NEW) {
             if (st == PT_ST_NEW) {
                 if (ps.pendingFinish) { /* the sample this lane just finished: item -> (pixel, sample of the round) */
@@ -1658,12 +1806,9 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
         else {
             if (st == PT_ST_SHADE) st = PhaseShadeHit(c, ps);
         }
-        /* A traced ray's verdict, at ONE site for the ISECT and SDF phases (instruction-cache footprint).  PhaseTrivial
-         * leaves a lane that already waits for SHADE untouched (it is not a shadow ray and it hit something), so it
-         * may see those lanes again. */
-        if (phase == PT_ST_ISECT || phase == PT_ST_SDF) {
-            if (st == PT_ST_SHADE) st = PhaseTrivial(ps);
-        }
+        /* A traced ray's verdict, at ONE site for the ISECT and SDF phases (instruction-cache footprint): only lanes
+         * that took part in this phase can have arrived at SHADE just now. */
+        if (ran && st == PT_ST_SHADE) st = PhaseTrivial(ps);
     }
     if (inRange) StoreTexel(pr, image, gx, gy, outColor);
 }
@@ -1720,7 +1865,7 @@ PT_DEV void PoolPark(float* e, const PathState& ps, const MarchState& ms, int it
     PT_PF(PF_OX) = ps.ray.origin.x; PT_PF(PF_OY) = ps.ray.origin.y; PT_PF(PF_OZ) = ps.ray.origin.z;
     PT_PF(PF_DX) = ps.ray.dir.x; PT_PF(PF_DY) = ps.ray.dir.y; PT_PF(PF_DZ) = ps.ray.dir.z;
     PT_PF(PF_SX) = ps.shDir.x; PT_PF(PF_SY) = ps.shDir.y; PT_PF(PF_SZ) = ps.shDir.z;
-    PT_PF(PF_FLAGS) = __uint_as_float((unsigned)ps.bounce | ((unsigned)ps.isShadow << 30) | ((unsigned)ps.pathAlive << 31));
+    PT_PF(PF_FLAGS) = __uint_as_float((unsigned)ps.bounce | ((unsigned)ps.inside << 29) | ((unsigned)ps.isShadow << 30) | ((unsigned)ps.pathAlive << 31));
     PT_PF(PF_HT) = ps.h.t; PT_PF(PF_HOBJ) = __int_as_float(ps.h.objectID);
     PoolStoreMarch(e, ms);
     PT_PF(PF_HNX) = ps.h.normal.x; PT_PF(PF_HNY) = ps.h.normal.y; PT_PF(PF_HNZ) = ps.h.normal.z;
@@ -1738,7 +1883,7 @@ PT_DEV void PoolPickup(const float* e, PathState& ps, int& item) {
     ps.ray.dir = mk3(PT_PF(PF_DX), PT_PF(PF_DY), PT_PF(PF_DZ));
     ps.shDir = mk3(PT_PF(PF_SX), PT_PF(PF_SY), PT_PF(PF_SZ));
     const unsigned pk = __float_as_uint(PT_PF(PF_FLAGS));
-    ps.bounce = (int)(pk & 0x3fffffffu); ps.isShadow = ((pk >> 30) & 1u) != 0u; ps.pathAlive = (pk >> 31) != 0u;
+    ps.bounce = (int)(pk & 0x1fffffffu); ps.inside = ((pk >> 29) & 1u) != 0u; ps.isShadow = ((pk >> 30) & 1u) != 0u; ps.pathAlive = (pk >> 31) != 0u;
     ps.pendingFinish = false;
     ps.h.t = PT_PF(PF_HT); ps.h.objectID = __float_as_int(PT_PF(PF_HOBJ));
     ps.h.normal = mk3(PT_PF(PF_HNX), PT_PF(PF_HNY), PT_PF(PF_HNZ));

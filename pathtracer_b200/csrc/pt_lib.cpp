@@ -43,6 +43,7 @@ struct pt_ctx {
     int pipeline = PT_PIPE_MEGAKERNEL;
     int bvh_min = PT_BVH_DEFAULT_MIN_PRIMS; /* bounded primitives from which the BVH replaces the scan; <= 0: never */
     PtKnobs knobs;           /* pt_set_option: tuning options of the run-time compiled kernels */
+    std::vector<pt_surface_ext> surface_ext; /* pt_set_surface_ext: applied by the next pt_set_scene */
     long long wf_max_paths = 32ll << 20; /* wavefront pipeline: paths in flight per chunk */
     bool bvh_active = false;
     PtWf wf;                 /* wavefront buffers (lazily allocated) */
@@ -330,6 +331,24 @@ int pt_set_pipeline(pt_ctx* ctx, int pipeline) {
     return PT_OK;
 }
 
+static_assert(PT_MAX_SURFACE_EXT == PT_DEV_MAX_SURFACE_EXT, "pt_abi.h and pt_dev_scene.h disagree");
+int pt_set_surface_ext(pt_ctx* ctx, const pt_surface_ext* table, int n) {
+    if (!ctx || n < 0 || (n > 0 && !table)) return fail(ctx, PT_ERR_ARG, "pt_set_surface_ext: bad argument");
+    if (n > PT_MAX_SURFACE_EXT)
+        return fail(ctx, PT_ERR_ARG, "pt_set_surface_ext: at most " + std::to_string(PT_MAX_SURFACE_EXT) + " materials can carry an extension");
+    for (int i = 0; i < n; i++) {
+        const pt_surface_ext& e = table[i];
+        if (e.bsdf < PT_BSDF_REFERENCE || e.bsdf > PT_BSDF_DIELECTRIC)
+            return fail(ctx, PT_ERR_ARG, "pt_set_surface_ext: entry " + std::to_string(i) + ": unknown bsdf " + std::to_string(e.bsdf));
+        if (e.bsdf == PT_BSDF_GLOSSY && !(e.roughness >= 0.0f && e.roughness <= 1.0f))
+            return fail(ctx, PT_ERR_ARG, "pt_set_surface_ext: entry " + std::to_string(i) + ": roughness must be in [0, 1]");
+        if (e.bsdf == PT_BSDF_DIELECTRIC && !(e.ior == 0.0f || (e.ior >= 1.0f && e.ior <= 4.0f)))
+            return fail(ctx, PT_ERR_ARG, "pt_set_surface_ext: entry " + std::to_string(i) + ": ior must be 0 (BK7) or in [1, 4]");
+    }
+    ctx->surface_ext.assign(table, table + n);
+    return PT_OK;
+}
+
 int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, int n_sdf) {
     if (!ctx || !ubo) return fail(ctx, PT_ERR_ARG, "pt_set_scene: null argument");
     PT_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -340,6 +359,10 @@ int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, in
     if (n_sdf != sc.nSdfs)
         return fail(ctx, PT_ERR_ARG, "pt_set_scene: n_sdf (" + std::to_string(n_sdf) + ") != ubo.numObjects[5] (" +
                                          std::to_string(sc.nSdfs) + ")");
+    /* surface extensions (not reference behaviour; empty table = the reference's shading, kernels built without them) */
+    const bool surface_ext = pt_prepare_surface_ext(ctx->surface_ext.data(), (int)ctx->surface_ext.size(), &sc);
+    if (surface_ext && ctx->jit_policy == 0)
+        return fail(ctx, PT_ERR_COMPILE, "surface extensions need the run-time compiled kernel (pt_set_jit(ctx, 0) set)");
     JitKernel* jit = nullptr;
     const bool wavefront = ctx->pipeline == PT_PIPE_WAVEFRONT;
     /* enough bounded primitives for the tree to beat the scan (run-time compiled kernels only) */
@@ -352,7 +375,7 @@ int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, in
         if (rc != PT_OK) return fail(ctx, rc, err);
         if (bvh_blob.size() > (size_t)PT_BVH_MAX_FLOATS) return fail(ctx, PT_ERR_ARG, "BVH blob larger than its device buffer");
     }
-    const bool want_jit = (n_sdf > 0) || ctx->jit_policy == 2 || wavefront || bvh;
+    const bool want_jit = (n_sdf > 0) || ctx->jit_policy == 2 || wavefront || bvh || surface_ext;
     if ((n_sdf > 0 || wavefront) && ctx->jit_policy == 0)
         return fail(ctx, PT_ERR_COMPILE, "scenes with SDF snippets and the wavefront pipeline need run-time compilation (PT_JIT=0 set)");
     if (want_jit) {
@@ -366,6 +389,7 @@ int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, in
         opt.bake_counts = (ctx->jit_policy == 2);
         opt.wavefront = wavefront;
         opt.bvh = bvh;
+        opt.surface_ext = surface_ext;
         const int counts[6] = {sc.nSpheres, sc.nPlanes, sc.nBoxes, sc.nLenses, sc.nCyclides, sc.nSdfs};
         memcpy(opt.counts, counts, sizeof counts);
         opt.knobs = ctx->knobs;
@@ -665,6 +689,7 @@ int pt_kernel_compile_check_opts(const pt_ubo* ubo, const char* const* sdf_glsl,
     opt.bake_counts = bake_counts != 0;
     opt.wavefront = (mode & 2) != 0; /* mode bit 1: also build the wavefront kernels */
     opt.bvh = (mode & 4) != 0;       /* mode bit 2: closest hit through the BVH */
+    opt.surface_ext = (mode & 8) != 0; /* mode bit 3: with the surface extensions (pt_set_surface_ext) */
     const int counts[6] = {sc.nSpheres, sc.nPlanes, sc.nBoxes, sc.nLenses, sc.nCyclides, sc.nSdfs};
     memcpy(opt.counts, counts, sizeof counts);
     opt.knobs = knobs;

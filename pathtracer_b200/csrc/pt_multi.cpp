@@ -162,6 +162,15 @@ int pt_multi_create(const int* devices, int n_devices, int mode, pt_multi** out)
 int pt_multi_num_devices(const pt_multi* m) { return m ? (int)m->ctx.size() : 0; }
 pt_ctx* pt_multi_ctx(pt_multi* m, int i) { return (m && i >= 0 && i < (int)m->ctx.size()) ? m->ctx[i] : nullptr; }
 
+int pt_multi_set_surface_ext(pt_multi* m, const pt_surface_ext* table, int n) {
+    if (!m) return PT_ERR_ARG;
+    for (size_t g = 0; g < m->ctx.size(); g++) {
+        int rc = from_ctx(m, (int)g, pt_set_surface_ext(m->ctx[g], table, n));
+        if (rc != PT_OK) return rc;
+    }
+    return PT_OK;
+}
+
 /* per-context settings (pt_set_jit, pt_set_pipeline, pt_set_bvh) go through pt_multi_ctx before this call */
 int pt_multi_set_scene(pt_multi* m, const pt_ubo* ubo, const char* const* sdf_glsl, int n_sdf) {
     if (!m || !ubo) return mfail(m, PT_ERR_ARG, "pt_multi_set_scene: null argument");

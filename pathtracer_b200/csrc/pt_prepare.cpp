@@ -71,6 +71,21 @@ void prepare_lens(float px, float py, float pz, float rx, float ry, float rz, fl
 
 }  // namespace
 
+/* The surface extension table of pt_set_surface_ext into the scene the kernels read.  Returns whether any entry leaves
+ * the reference's shading (only then is the kernel built with the extension code). */
+bool pt_prepare_surface_ext(const pt_surface_ext* table, int n, PtDevScene* sc) {
+    bool any = false;
+    sc->nSurfaceExt = 0;
+    memset(sc->surfaceExt, 0, sizeof sc->surfaceExt);
+    for (int i = 0; i < n && i < PT_DEV_MAX_SURFACE_EXT; i++) {
+        sc->surfaceExt[i].bsdf = table[i].bsdf;
+        sc->surfaceExt[i].roughness = table[i].roughness;
+        sc->surfaceExt[i].ior = table[i].ior;
+        if (table[i].bsdf != PT_BSDF_REFERENCE) { any = true; sc->nSurfaceExt = i + 1; }
+    }
+    return any;
+}
+
 int pt_prepare_scene(const pt_ubo* ubo, PtDevScene* sc, std::string* err) {
     memset(sc, 0, sizeof *sc);
     Flat F = {reinterpret_cast<const float*>(ubo)};

@@ -30,7 +30,7 @@ struct Box { float pos[3], rotation[3], size[3]; int materialID, lightID; };
 struct Lens { float pos[3], rotation[3]; float radius, focalLength, thickness; bool isConverging; int materialID, lightID; };
 struct Cyclide { float pos[3], rotation[3], scale[3]; float a, b, c, d, brad; int materialID, lightID; };
 struct Sdf { float pos[3], size[3]; std::string glsl; };
-struct Material { float reflection[3]; };
+struct Material { float reflection[3]; int bsdf = 0; float roughness = 0.0f, ior = 0.0f; /* surface extension (pt_abi.h), absent in the reference's schema */ };
 struct Light { float emission[2]; };
 struct CameraShot { float pos[3]; float angle[2]; };
 struct Camera { int ISO; float size, apertureSize, apertureDist, lensRadius, lensFocalLength, lensThickness, lensDistance; };
@@ -155,6 +155,22 @@ int pt_scene_parse_json(const char* text, pt_scene** out) {
         s->materials[k].reflection[0] = f(r["peakWavelength"]);
         s->materials[k].reflection[1] = f(r["sigma"]);
         s->materials[k].reflection[2] = r["isInvert"].truthy() ? 1.0f : 0.0f;
+        if (const PtJson* b = mt.at(k).find("bsdf")) { /* extension of the schema; the reference ignores unknown keys */
+            const std::string& n = b->str;
+            int id = -1;
+            if (n == "reference" || n == "diffuse") id = PT_BSDF_REFERENCE;
+            else if (n == "mirror") id = PT_BSDF_MIRROR;
+            else if (n == "glossy") id = PT_BSDF_GLOSSY;
+            else if (n == "dielectric") id = PT_BSDF_DIELECTRIC;
+            if (b->type != PtJson::String || id < 0) {
+                g_error = "scene JSON: material " + std::to_string(k) + ": \"bsdf\" must be \"reference\", \"mirror\", \"glossy\" or \"dielectric\"";
+                delete s;
+                return PT_ERR_IO;
+            }
+            s->materials[k].bsdf = id;
+            if (const PtJson* v = mt.at(k).find("roughness")) s->materials[k].roughness = f(*v);
+            if (const PtJson* v = mt.at(k).find("ior")) s->materials[k].ior = f(*v);
+        }
     }
     const PtJson& lt = j["light"]; /* host:2717-2721 */
     s->lights.resize(lt.size());
@@ -309,6 +325,15 @@ long pt_scene_to_json(const pt_scene* s, char* out, size_t cap) {
             r.obj.emplace_back("sigma", num(v.reflection[1]));
             r.obj.emplace_back("isInvert", boolean(v.reflection[2] != 0.0f));
             o.obj.emplace_back("reflection", r);
+            if (v.bsdf != PT_BSDF_REFERENCE) {
+                static const char* const names[4] = {"reference", "mirror", "glossy", "dielectric"};
+                PtJson b;
+                b.type = PtJson::String;
+                b.str = names[v.bsdf];
+                o.obj.emplace_back("bsdf", b);
+                if (v.bsdf == PT_BSDF_GLOSSY) o.obj.emplace_back("roughness", num(v.roughness));
+                if (v.bsdf == PT_BSDF_DIELECTRIC) o.obj.emplace_back("ior", num(v.ior));
+            }
             a.arr.push_back(o);
         }
         root.obj.emplace_back("material", a);
@@ -343,6 +368,21 @@ int pt_scene_save_json(const pt_scene* s, const char* path) {
     if (!fp) { g_error = std::string("cannot write ") + path; return PT_ERR_IO; }
     const bool ok = fwrite(buf.data(), 1, (size_t)n - 1, fp) == (size_t)n - 1;
     return (fclose(fp) == 0 && ok) ? PT_OK : PT_ERR_IO;
+}
+
+int pt_scene_surface_ext(const pt_scene* s, pt_surface_ext* out, int max) {
+    if (!s || (max > 0 && !out)) { g_error = "pt_scene_surface_ext: null argument"; return PT_ERR_ARG; }
+    int n = 0;
+    for (size_t k = 0; k < s->materials.size(); k++)
+        if (s->materials[k].bsdf != PT_BSDF_REFERENCE) n = (int)k + 1;
+    if (n > PT_MAX_SURFACE_EXT) { g_error = "scene: only the first " + std::to_string(PT_MAX_SURFACE_EXT) + " materials can carry a \"bsdf\""; return PT_ERR_ARG; }
+    for (int k = 0; k < n && k < max; k++) {
+        out[k].bsdf = s->materials[k].bsdf;
+        out[k].roughness = s->materials[k].roughness;
+        out[k].ior = s->materials[k].ior;
+        out[k].pad = 0.0f;
+    }
+    return n;
 }
 
 int pt_scene_pack_ubo(const pt_scene* s, pt_ubo* ubo) { /* host:3642-3811 */

@@ -12,7 +12,7 @@
  *   wl   [P] float4  the wavelength bundle                 rad   [P] float4  radiance
  *   thr  [P] float4  rayradiance (throughput)              shD   [P] float4  shadow dir xyz, shObj (int bits)
  *   shC  [P] float4  pending light contribution            hit0  [P] float4  t, normal xyz
- *   hit1 [P] float4  materialID, lightID, objectID bits    misc  [P] uint2   seed, bounce | isShadow<<30 | pathAlive<<31
+ *   hit1 [P] float4  materialID, lightID, objectID bits    misc  [P] uint2   seed, bounce | inside<<29 | isShadow<<30 | pathAlive<<31
  *   col  [P] float4  XYZ of the finished path              acc   [nPix] float4 per-pixel sum, added in sample order
  * Queues hold path indices; pushes are warp-aggregated (ballot + popc prefix, one atomicAdd per warp).
  * Per bounce depth:  ISECT(qA) -> MARCH(qM) -> SHADE(qA: -> qS shadow rays, qB next depth, or finished)
@@ -58,10 +58,12 @@ PT_DEV void StageTable(const float* __restrict__ ubo, float* s_tab) {
 }
 
 PT_DEV unsigned PackMisc(const PathState& ps) {
-    return ((unsigned)ps.bounce & 0x3fffffffu) | (ps.isShadow ? 0x40000000u : 0u) | (ps.pathAlive ? 0x80000000u : 0u);
+    return ((unsigned)ps.bounce & 0x1fffffffu) | (ps.inside ? 0x20000000u : 0u) | (ps.isShadow ? 0x40000000u : 0u) |
+           (ps.pathAlive ? 0x80000000u : 0u);
 }
 PT_DEV void UnpackMisc(unsigned v, PathState& ps) {
-    ps.bounce = (int)(v & 0x3fffffffu);
+    ps.bounce = (int)(v & 0x1fffffffu);
+    ps.inside = (v & 0x20000000u) != 0u;
     ps.isShadow = (v & 0x40000000u) != 0u;
     ps.pathAlive = (v & 0x80000000u) != 0u;
 }

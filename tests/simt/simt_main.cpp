@@ -50,6 +50,10 @@ extern "C" void simt_stats(unsigned long long* out16, int reset) {
 #endif
 }
 
+/* pt_set_surface_ext of the emulated device (surface extensions; the kernel must be built with -DPT_EXT_BSDF=1) */
+static std::vector<pt_surface_ext> g_surface_ext;
+extern "C" void simt_set_surface_ext(const pt_surface_ext* table, int n) { g_surface_ext.assign(table, table + (n > 0 ? n : 0)); }
+
 extern "C" int simt_dispatch(const pt_ubo* ubo, const pt_params* params, int accum_mode, int first, int n, float* image,
                              int persistent_ctas) {
     PtDevScene sc;
@@ -57,6 +61,10 @@ extern "C" int simt_dispatch(const pt_ubo* ubo, const pt_params* params, int acc
     std::string err;
     if (pt_prepare_scene(ubo, &sc, &err) != 0) { fprintf(stderr, "simt: %s\n", err.c_str()); return -1; }
     if (pt_prepare_params(params, accum_mode, first, n, &dp, &err) != 0) { fprintf(stderr, "simt: %s\n", err.c_str()); return -2; }
+    if (pt_prepare_surface_ext(g_surface_ext.data(), (int)g_surface_ext.size(), &sc) && !PT_EXT_BSDF) {
+        fprintf(stderr, "simt: surface extensions set but the kernel was built without PT_EXT_BSDF\n");
+        return -3;
+    }
     (void)persistent_ctas;
     gridDim = {(unsigned)((dp.width + 15) / 16), (unsigned)((dp.height + 7) / 8), 1u};
     blockDim = {PT_BLOCK_THREADS, 1u, 1u};
