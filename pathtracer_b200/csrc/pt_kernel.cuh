@@ -1883,7 +1883,7 @@ PT_DEV void PoolPickup(const float* e, PathState& ps, int& item) {
     ps.ray.dir = mk3(PT_PF(PF_DX), PT_PF(PF_DY), PT_PF(PF_DZ));
     ps.shDir = mk3(PT_PF(PF_SX), PT_PF(PF_SY), PT_PF(PF_SZ));
     const unsigned pk = __float_as_uint(PT_PF(PF_FLAGS));
-    ps.bounce = (int)(pk & 0x1fffffffu); ps.inside = ((pk >> 29) & 1u) != 0u; ps.isShadow = ((pk >> 30) & 1u) != 0u; ps.pathAlive = (pk >> 31) != 0u;
+    ps.bounce = (int)(pk & 0x1fffffffu); ps.inside = PT_EXT_BSDF ? (((pk >> 29) & 1u) != 0u) : false; ps.isShadow = ((pk >> 30) & 1u) != 0u; ps.pathAlive = (pk >> 31) != 0u;
     ps.pendingFinish = false;
     ps.h.t = PT_PF(PF_HT); ps.h.objectID = __float_as_int(PT_PF(PF_HOBJ));
     ps.h.normal = mk3(PT_PF(PF_HNX), PT_PF(PF_HNY), PT_PF(PF_HNZ));

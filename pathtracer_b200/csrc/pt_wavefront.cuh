@@ -63,7 +63,7 @@ PT_DEV unsigned PackMisc(const PathState& ps) {
 }
 PT_DEV void UnpackMisc(unsigned v, PathState& ps) {
     ps.bounce = (int)(v & 0x1fffffffu);
-    ps.inside = (v & 0x20000000u) != 0u;
+    ps.inside = PT_EXT_BSDF ? ((v & 0x20000000u) != 0u) : false; /* only the surface extensions ever set it */
     ps.isShadow = (v & 0x40000000u) != 0u;
     ps.pathAlive = (v & 0x80000000u) != 0u;
 }
