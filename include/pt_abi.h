@@ -142,7 +142,8 @@ int pt_bvh_active(const pt_ctx* ctx);
  *   "heavy_min"   v2s: > 0 runs the box / lens / cyclide tests as a phase of their own once so many lanes wait   [-1]
  *   "sin_poly_every"  fast mode: every k-th sin( of the SDF snippets runs on the FMA pipe instead of MUFU     [0]
  *   "stats"       1 builds the scheduling counters in (pt_debug_stats)                                      [0]
- *   "wf_refill", "wf_max_paths"   wavefront pipeline: evaluations between refills; paths in flight per chunk
+ *   "wf_refill", "wf_max_paths"   wavefront pipeline: evaluations between refills; paths in flight per chunk (a chunk is
+ *                                 a band of consecutive pixels x some samples; 0 = auto: 4 Mi without SDFs, 32 Mi with)
  *   "bvh_while_while"             BVH traversal loop shape */
 int pt_set_option(pt_ctx* ctx, const char* key, long long value);
 int pt_get_option(const pt_ctx* ctx, const char* key, long long* value);

@@ -136,11 +136,12 @@ typedef struct PtWf {
     PT_WF_PTR(uint2) misc;
     PT_WF_PTR(unsigned) qA; PT_WF_PTR(unsigned) qB; PT_WF_PTR(unsigned) qS; PT_WF_PTR(unsigned) qM;
     PT_WF_PTR(unsigned) cnt;  /* [0] nA  [1] nB  [2] nS  [3] nM  [4] march head */
-    unsigned P, nPix;        /* paths in flight (pixels x samples of the chunk), pixels */
+    unsigned P, nPix;        /* paths in flight (pixels x samples of the chunk), pixels of the chunk's band */
     int chunkBase;           /* k of the chunk's first sample (sample index = firstSample + k) */
     int chunkSamples;
     int lastChunk;
-    int pad;
+    unsigned pixBase;        /* first pixel (row-major index) of the chunk's band: chunks tile the frame so that the path
+                                state of one chunk stays resident in L2 */
 } PtWf;
 
 /* raw tables the kernel indexes with computed ids; a copy of the tail of the uniform block in global memory:

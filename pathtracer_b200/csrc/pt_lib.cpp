@@ -44,7 +44,8 @@ struct pt_ctx {
     int bvh_min = PT_BVH_DEFAULT_MIN_PRIMS; /* bounded primitives from which the BVH replaces the scan; <= 0: never */
     PtKnobs knobs;           /* pt_set_option: tuning options of the run-time compiled kernels */
     std::vector<pt_surface_ext> surface_ext; /* pt_set_surface_ext: applied by the next pt_set_scene */
-    long long wf_max_paths = 32ll << 20; /* wavefront pipeline: paths in flight per chunk */
+    long long wf_max_paths = 0; /* wavefront pipeline: paths in flight per chunk; 0 = auto (4 Mi without SDFs, 32 Mi with:
+                                   profiles/r02_wf_l2) */
     bool bvh_active = false;
     PtWf wf;                 /* wavefront buffers (lazily allocated) */
     void* wf_block = nullptr;
@@ -142,11 +143,15 @@ int launch_wavefront(pt_ctx* ctx, const PtDevParams& dp0) {
     JitKernel* k = ctx->active_jit;
     if (!k || !k->wf_gen) return fail(ctx, PT_ERR_ARG, "wavefront pipeline: kernels not built (call pt_set_scene after pt_set_pipeline)");
     const size_t pixels = (size_t)dp0.width * (size_t)dp0.height;
-    const size_t max_paths = (size_t)ctx->wf_max_paths;
-    int chunk = (int)(max_paths / pixels);
+    /* A chunk = a band of consecutive pixels x some samples, at most wf_max_paths paths: the frame is tiled so that the
+     * ~190 B of state per path of one chunk can stay in the 126 MB L2 between the kernels of a bounce. */
+    const size_t max_paths = ctx->wf_max_paths > 0 ? (size_t)ctx->wf_max_paths
+                                                   : (ctx->dev_scene.nSdfs > 0 ? (size_t)32 << 20 : (size_t)4 << 20);
+    const size_t band = pixels < max_paths ? pixels : max_paths; /* pixels per chunk */
+    int chunk = (int)(max_paths / band);                          /* samples per chunk */
     if (chunk < 1) chunk = 1;
     if (chunk > dp0.samplesPerFrame) chunk = dp0.samplesPerFrame;
-    int rc = wf_alloc(ctx, pixels * (size_t)chunk, pixels);
+    int rc = wf_alloc(ctx, band * (size_t)chunk, band);
     if (rc != PT_OK) return rc;
     if (!ctx->timing_open) {
         PT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
@@ -159,7 +164,6 @@ int launch_wavefront(pt_ctx* ctx, const PtDevParams& dp0) {
     float* image = ctx->d_image;
     PtDevParams dp = dp0;
     PtWf w = ctx->wf;
-    w.nPix = (unsigned)pixels;
     const bool has_sdf = ctx->dev_scene.nSdfs > 0;
     auto run = [&](cudaKernel_t kern, const dim3& g, int which, int identity, int nargs) -> cudaError_t {
         void* args[7] = {(void*)&ctx->dev_scene, (void*)&dp, (void*)&ubo, (void*)&w, (void*)&which, (void*)&identity, nullptr};
@@ -171,9 +175,12 @@ int launch_wavefront(pt_ctx* ctx, const PtDevParams& dp0) {
         void* args[2] = {(void*)&w, (void*)&op};
         return cudaLaunchKernel((const void*)k->wf_ctl, one, dim3(32, 1, 1), args, 0, ctx->stream);
     };
+    for (size_t pix0 = 0; pix0 < pixels; pix0 += band)
     for (int base = 0; base < dp0.samplesPerFrame; base += chunk) {
         const int ns = (dp0.samplesPerFrame - base < chunk) ? dp0.samplesPerFrame - base : chunk;
-        w.P = (unsigned)(pixels * (size_t)ns);
+        w.pixBase = (unsigned)pix0;
+        w.nPix = (unsigned)((pixels - pix0 < band) ? pixels - pix0 : band);
+        w.P = (unsigned)((size_t)w.nPix * (size_t)ns);
         w.chunkBase = base;
         w.chunkSamples = ns;
         w.lastChunk = (base + ns >= dp0.samplesPerFrame) ? 1 : 0;
@@ -306,7 +313,7 @@ int pt_set_bvh(pt_ctx* ctx, int min_prims) {
 int pt_set_option(pt_ctx* ctx, const char* key, long long value) {
     if (!ctx || !key) return fail(ctx, PT_ERR_ARG, "pt_set_option: null argument");
     if (std::string(key) == "wf_max_paths") {
-        if (value < 1) return fail(ctx, PT_ERR_ARG, "pt_set_option: wf_max_paths must be positive");
+        if (value < 0) return fail(ctx, PT_ERR_ARG, "pt_set_option: wf_max_paths must be positive (or 0 = auto)");
         ctx->wf_max_paths = value;
         return PT_OK;
     }

@@ -7,7 +7,8 @@
  * is HBM traffic for the state (SoA, one float4 per field group so a warp reads 512 contiguous bytes per field)
  * and more launches; pt_kernel.cuh's megakernel pays neither.  profiles/ holds the measured comparison.
  *
- * Layout (P paths in flight = pixels x samples of the chunk; path p belongs to pixel p % nPix, sample p / nPix):
+ * Layout (P paths in flight = pixels x samples of the chunk; path p belongs to pixel pixBase + p % nPix of the frame and
+ * to sample chunkBase + p / nPix; a chunk is a band of nPix consecutive pixels x some samples, sized by wf_max_paths):
  *   rayO [P] float4  ray origin xyz, MISBRDFWeight         rayD  [P] float4  ray dir xyz (next path direction)
  *   wl   [P] float4  the wavelength bundle                 rad   [P] float4  radiance
  *   thr  [P] float4  rayradiance (throughput)              shD   [P] float4  shadow dir xyz, shObj (int bits)
@@ -96,7 +97,7 @@ PT_DEV void LoadHit(const PtWf& w, unsigned p, Hit& h) {
 PT_DEV void WfGen(const Ctx& c, const PtWf& w) {
     const PtDevParams& pr = *c.pr;
     for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < w.P; p += gridDim.x * blockDim.x) {
-        const unsigned pix = p % w.nPix, s = p / w.nPix;
+        const unsigned pix = w.pixBase + p % w.nPix, s = p / w.nPix;
         unsigned xyx, xyy;
         PixelOf(pr, pix, xyx, xyy);
         PathState ps;
@@ -266,7 +267,8 @@ PT_DEV void WfFinal(const PtDevParams& pr, const PtWf& w, float4* __restrict__ i
             outColor = outColor + mk3(cc.x, cc.y, cc.z);
         }
         if (w.lastChunk) {
-            StoreTexel(pr, image, (int)(pix % (unsigned)pr.width), (int)(pix / (unsigned)pr.width), outColor);
+            const unsigned g = w.pixBase + pix; /* pix counts inside the chunk's band of the frame */
+            StoreTexel(pr, image, (int)(g % (unsigned)pr.width), (int)(g / (unsigned)pr.width), outColor);
         } else {
             w.acc[pix] = make_float4(outColor.x, outColor.y, outColor.z, 0.0f);
         }

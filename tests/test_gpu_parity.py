@@ -381,7 +381,14 @@ def test_wavefront_chunking_and_sum_mode(ptlib, wf_renderer):
     refs = np.zeros_like(ref)
     oracle.Oracle(ubo, src).dispatch_sum(p, 5, 7, refs)
     assert_bit_equal(s[..., :3].copy(), refs[..., :3].copy(), 'wavefront sum mode')
-    wf_renderer.set_option('wf_max_paths', 32 << 20)
+    # fewer paths in flight than the frame has pixels: the frame is tiled into bands of consecutive pixels (the last one
+    # ragged: 96 * 64 = 6144 = 6 * 1000 + 144), each band runs all its samples before the next starts
+    for cap in (1000, 96 * 64 - 1, 2500):
+        wf_renderer.set_option('wf_max_paths', cap)
+        for name, spp, spf in (('scene0', 6, 3), ('scene10', 2, 2)):
+            got, ubo, p, src = gpu_render(ptlib, wf_renderer, name, 96, 64, spp, spf)
+            assert_bit_equal(got, oracle.Oracle(ubo, src).render(p, spp, spf), 'wavefront tiled %d %s' % (cap, name))
+    wf_renderer.set_option('wf_max_paths', 0)
 
 
 def test_wavefront_matches_megakernel_fast_mode(ptlib, renderer, wf_renderer):
