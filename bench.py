@@ -601,12 +601,16 @@ def roofline_for(m, peaks, peak_kind, fp32_peak, clocks, args):
         'bound': 'fp32', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
         'traffic': traffic, 'traffic_source': traffic_src,
         'kernel': 'pt_render_jit' if args.jit == 2 or m['has_sdf'] else 'pt_render_' + args.mode,
+        # option "pregen" (auto for scenes with a cyclide): a step is pt_gen_jit (camera rays, 32-byte records) + pt_render_jit;
+        # `achieved` divides by the device time of BOTH, the records add 64 B per sample (written once, read once) to the HBM side
+        'kernels_per_step': m['launches'] / max(m['K'], 1),
         'flops_per_sample_algorithmic': F, 'flops_counting_rule': 'SURVEY.md App. D v1 (source-level, as written in shader.comp)',
         'peak_basis': ('measured in this run: pt_fp32_peak, 16 independent FFMA chains per thread on every SM, CUDA events' if fp32_peak else
                        'derived: 148 SM x 128 FP32 lanes x 2 x %s sm_max_mhz (%s)' % (peaks.get('sm_max_mhz', 1965.0), peak_kind)),
         'peak_derived_at_max_clock': derived_max, 'frac_of_derived_peak': achieved / derived_max,
         'hbm': {'achieved_gbs': m['W'] * m['H'] * 32 / (m['dev_ms'] / m['K'] * 1e-3) / 1e9, 'peak_gbs': peaks.get('hbm_gbs'),
-                'algorithmic_bytes_per_launch': m['W'] * m['H'] * 32},
+                'algorithmic_bytes_per_launch': m['W'] * m['H'] * 32,
+                'pregen_record_bytes_per_step': (m['W'] * m['H'] * args.spf * 64) if m['launches'] > m['K'] else 0},
         'oracle_counters_per_sample': {k: v / max(cnt['samples'], 1) for k, v in cnt.items()},
     }
 

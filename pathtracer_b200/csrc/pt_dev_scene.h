@@ -101,6 +101,13 @@ typedef struct PtDevScene {
     PtDevSurfaceExt surfaceExt[PT_DEV_MAX_SURFACE_EXT];
 } PtDevScene;
 
+/* Pointer types are spelled out on the device and opaque on the host (same layout). */
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__) || defined(PT_CUDA_SHIM_H) /* the device, or tests/simt */
+#define PT_WF_PTR(T) T*
+#else
+#define PT_WF_PTR(T) void*
+#endif
+
 /* Per-dispatch constants: the push constants (shader.comp:31-52) plus what Scene()/TracePathLens() derive from them */
 typedef struct PtDevParams {
     int width, height;
@@ -120,15 +127,17 @@ typedef struct PtDevParams {
     float apertureDist;
     float camM[9];         /* RotationMatrix(vec3(cameraAngle, 0)), column-major */
     PtDevLens camLens;     /* TracePathLens' lens object (shader.comp:1411-1418) */
+    /* Camera rays generated ahead of the megakernel (option "pregen", pt_kernel.cuh pt_gen_body): two planes of
+     * genCount float4 each -- (origin.xyz, dir.x) and (dir.y, dir.z, hero wavelength, seed bits) -- one record per
+     * (warp tile, sample of the dispatch, pixel of the tile): record = (tile * samplesPerFrame + k) * 32 + pixel. */
+    PT_WF_PTR(float4) gen;
+    unsigned long long genCount;
+    int blockY0;           /* first CTA row (8 pixel rows each) of this launch: a dispatch whose records outgrow the scratch
+                              buffer runs as several bands of CTA rows */
+    int pad1;
 } PtDevParams;
 
-/* Wavefront pipeline (pt_wavefront.cuh): device buffers of the path state, SoA.  Pointer types are spelled out on the
- * device and opaque on the host (same layout). */
-#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
-#define PT_WF_PTR(T) T*
-#else
-#define PT_WF_PTR(T) void*
-#endif
+/* Wavefront pipeline (pt_wavefront.cuh): device buffers of the path state, SoA. */
 typedef struct PtWf {
     PT_WF_PTR(float4) rayO; PT_WF_PTR(float4) rayD; PT_WF_PTR(float4) wl; PT_WF_PTR(float4) rad; PT_WF_PTR(float4) thr;
     PT_WF_PTR(float4) shD; PT_WF_PTR(float4) shC; PT_WF_PTR(float4) hit0; PT_WF_PTR(float4) hit1; PT_WF_PTR(float4) col;

@@ -105,6 +105,7 @@ int pt_knob_set(PtKnobs* k, const char* key, long long value) {
     else if (s == "bvh_while_while") { if (v < 0 || v > 1) return -1; k->bvh_while_while = v; }
     else if (s == "sin_poly_every") { if (v < 0 || v > 64) return -1; k->sin_poly_every = v; }
     else if (s == "heavy_min") { if (v < -1 || v > 32) return -1; k->heavy_min = v; }
+    else if (s == "pregen") { if (v < -1 || v > 1) return -1; k->pregen = v; }
     else return -1;
     return 0;
 }
@@ -118,6 +119,7 @@ int pt_knob_get(const PtKnobs* k, const char* key, long long* value) {
     else if (s == "pool_min") *value = k->pool_min; else if (s == "stats") *value = k->stats;
     else if (s == "wf_refill") *value = k->wf_refill; else if (s == "bvh_while_while") *value = k->bvh_while_while;
     else if (s == "sin_poly_every") *value = k->sin_poly_every; else if (s == "heavy_min") *value = k->heavy_min;
+    else if (s == "pregen") *value = k->pregen;
     else return -1;
     return 0;
 }
@@ -199,15 +201,25 @@ std::string pt_jit_source(const std::string& sdf_unit, const PtJitOptions& opt) 
         if (sched != 5 || opt.bvh || n_heavy == 0 || n_heavy > 32 || !opt.bake_counts) heavy_min = 0;
         src += "#define PT_HEAVY_MIN " + std::to_string(heavy_min) + "\n";
     }
+    /* camera rays from records (pt_gen_body): the pooled megakernel drivers only */
+    /* auto: scenes with a cyclide -- their kernel is 39-41 KB of SASS with the camera inline and 35-36 KB without, i.e.
+     * the generation kernel buys the instruction cache (cfg5 3.93 -> 4.26, cfg1 8.17 -> 8.86, cfg3 3.49 -> 3.61 Gsamples/s);
+     * where the kernel fits anyway the records' 64 B per sample of memory traffic eat the gain (cfg2 11.49 -> 11.41, cfg4b
+     * 1.058 -> 1.050): profiles/r02_pregen */
+    const bool pregen = !opt.wavefront && (sched == 5 || sched == 7) && (k.pregen < 0 ? opt.counts[4] > 0 : k.pregen != 0);
+    if (pregen) src += "#define PT_PREGEN 1\n";
     if (k.stats) src += "#define PT_STATS 1\n";
     if (k.sin_poly_every > 0 && opt.mode == PT_MODE_FAST) src += "#define PT_SIN_POLY_EVERY " + std::to_string(k.sin_poly_every) + "\n";
     src += opt.wavefront ? "#include \"pt_wavefront.cuh\"\n" : "#include \"pt_kernel.cuh\"\n";
     src += sdf_unit;
     src += "\nPT_DEFINE_RENDER_KERNEL(pt_render_jit)\n";
+    if (pregen) src += "PT_DEFINE_GEN_KERNEL(pt_gen_jit)\n";
     if (has_sdf) src += "PT_DEFINE_SDF_EVAL_KERNEL(pt_sdf_eval_jit)\n";
     if (opt.wavefront) src += "PT_DEFINE_WAVEFRONT_KERNELS\n";
     return src;
 }
+
+bool pt_jit_uses_pregen(const std::string& source) { return source.find("#define PT_PREGEN 1\n") != std::string::npos; }
 
 int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::vector<char>* cubin, std::string* log) {
     std::call_once(g_once, load_nvrtc);

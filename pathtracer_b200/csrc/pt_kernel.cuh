@@ -996,9 +996,13 @@ PT_DEV V3 PathColor(const Ctx& c, const PathState& ps) {
     return color;
 }
 
-/* NEW: Scene() up to TracePath, shader.comp:1446-1472, for sample index pr.firstSample + k of pixel (xyx, xyy).
+/* NEW: Scene() up to TracePath, shader.comp:1446-1472, for sample index pr.firstSample + k of pixel (xyx, xyy), in two
+ * halves.  PhaseNewCamera is everything that depends on (pixel, sample index) alone -- seed, sensor jitter, aperture
+ * sample, hero wavelength, the two refractions through the camera lens: 350 instructions every lane executes identically.
+ * The pooled drivers can take its result from a record a generation kernel wrote beforehand (PT_PREGEN, pt_gen_body):
+ * there all 32 lanes are busy, here only the lanes that happen to start a sample.  PhaseNewFinish resets the path.
  * Returns the next phase (ISECT, or NEW again with pendingFinish when pathLength <= 0). */
-PT_DEV int PhaseNew(const Ctx& c, PathState& ps, unsigned xyx, unsigned xyy, int k) {
+PT_DEV void PhaseNewCamera(const Ctx& c, unsigned xyx, unsigned xyy, int k, Ray& ray, float& l_h, unsigned& seedOut) {
     const PtDevParams& pr = *c.pr;
     const V3 camPos = mk3(pr.camPosX, pr.camPosY, pr.camPosZ);
     const float uvx0 = PTK_DIV(2.0f * __uint2float_rn(xyx) - pr.resX, pr.resY); /* shader.comp:1511 */
@@ -1012,7 +1016,6 @@ PT_DEV int PhaseNew(const Ctx& c, PathState& ps, unsigned xyx, unsigned xyy, int
     float uvy = uvy0 + PTK_DIV(2.0f * j2 - 0.5f, pr.resY);
     uvx *= pr.sensorScale;
     uvy *= pr.sensorScale;
-    Ray ray;
     ray.origin = camPos + mulVM(mk3(uvx, uvy, 0.0f), pr.camM);
     const float rx = RandomFloatPCG32(seed); /* SampleUniformUnitDisk, shader.comp:976-982 */
     const float ry = RandomFloatPCG32(seed);
@@ -1023,8 +1026,11 @@ PT_DEV int PhaseNew(const Ctx& c, PathState& ps, unsigned xyx, unsigned xyy, int
     const V3 pointOnAperture = camPos + mulVM(mk3(diskx, disky, pr.apertureDist), pr.camM);
     ray.dir = normalize(pointOnAperture - ray.origin);
     const float r5 = RandomFloatPCG32(seed);
-    const float l_h = 360.0f * (1.0f - r5) + 800.0f * r5; /* mix(360, 800, r) */
+    l_h = 360.0f * (1.0f - r5) + 800.0f * r5; /* mix(360, 800, r) */
     TracePathLens(c, l_h, ray);
+    seedOut = seed;
+}
+PT_DEV int PhaseNewFinish(const Ctx& c, PathState& ps, const Ray& ray, float l_h, unsigned seed) {
     ps.ray = ray;
     ps.l = SampleWavelengths(l_h);
     ps.seed = seed;
@@ -1034,10 +1040,55 @@ PT_DEV int PhaseNew(const Ctx& c, PathState& ps, unsigned xyx, unsigned xyy, int
     ps.bounce = 0;
     ps.isShadow = false;
     ps.inside = false;
-    if (pr.pathLength > 0) return PT_ST_ISECT;
+    if (c.pr->pathLength > 0) return PT_ST_ISECT;
     ps.pendingFinish = true;
     return PT_ST_NEW;
 }
+PT_DEV int PhaseNew(const Ctx& c, PathState& ps, unsigned xyx, unsigned xyy, int k) {
+    Ray ray;
+    float l_h;
+    unsigned seed;
+    PhaseNewCamera(c, xyx, xyy, k, ray, l_h, seed);
+    return PhaseNewFinish(c, ps, ray, l_h, seed);
+}
+
+#ifndef PT_PREGEN
+#define PT_PREGEN 0 /* 1: the pooled drivers (v2s, v3s) read PhaseNewCamera's result from pr.gen instead of computing it */
+#endif
+/* Generation kernel of PT_PREGEN: the launch geometry of the render kernel (one warp = one 8x4 tile), lane p computes
+ * the camera rays of pixel p of its tile for every sample of the dispatch -- no divergence, no table, 30 registers.
+ * Record layout: PtDevParams::gen.  32 B per sample written once and read once: at 12 Gsamples/s 0.8 TB/s of the 7.7. */
+__device__ __forceinline__ void pt_gen_body(const PtDevParams& pr, float4* __restrict__ gen) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tileX = blockIdx.x * 16 + (warp & 1) * 8, tileY = ((int)blockIdx.y + pr.blockY0) * 8 + (warp >> 1) * 4;
+    const int qx = tileX + (lane & 7), qy = tileY + (lane >> 3);
+    if (qx >= pr.width || qy >= pr.height) return;
+    Ctx c;
+    c.sc = nullptr; c.pr = &pr; c.ubo = nullptr; c.s_tab = nullptr;
+    const unsigned long long tile = ((unsigned long long)blockIdx.y * gridDim.x + blockIdx.x) * (PT_BLOCK_THREADS / 32) + (unsigned)warp;
+    float4* a = gen + tile * 32ull * (unsigned long long)pr.samplesPerFrame + (unsigned)lane;
+    float4* b = a + pr.genCount;
+#pragma unroll 1
+    for (int k = 0; k < pr.samplesPerFrame; k++) {
+        Ray ray;
+        float l_h;
+        unsigned seed;
+        PhaseNewCamera(c, (unsigned)qx, (unsigned)pr.height - (unsigned)qy, k, ray, l_h, seed);
+        a[32 * k] = make_float4(ray.origin.x, ray.origin.y, ray.origin.z, ray.dir.x);
+        b[32 * k] = make_float4(ray.dir.y, ray.dir.z, l_h, __uint_as_float(seed));
+    }
+}
+#if PT_PREGEN
+/* NEW for item (sample k of the dispatch, pixel q of the warp's tile) from its record */
+PT_DEV int PhaseNewFromRecord(const Ctx& c, PathState& ps, unsigned long long tileRecord0, int k, int q) {
+    const float4* a = c.pr->gen + tileRecord0 + 32ull * (unsigned)k + (unsigned)q;
+    const float4 A = __ldg(a), B = __ldg(a + c.pr->genCount);
+    Ray ray;
+    ray.origin = mk3(A.x, A.y, A.z);
+    ray.dir = mk3(A.w, B.x, B.y);
+    return PhaseNewFinish(c, ps, ray, B.z, __float_as_uint(B.w));
+}
+#endif
 
 
 #if PT_HAS_SDF
@@ -1574,7 +1625,7 @@ __device__ __forceinline__ void pt_render_body_v1(const PtDevScene& sc, const Pt
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const int gy = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const int gy = ((int)blockIdx.y + pr.blockY0) * 8 + (warp >> 1) * 4 + (lane >> 3);
     if (gx >= pr.width || gy >= pr.height) return;
 
     Ctx c;
@@ -1613,7 +1664,11 @@ __device__ __forceinline__ void pt_render_body_v3s(const PtDevScene& sc, const P
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tileX = blockIdx.x * 16 + (warp & 1) * 8, tileY = blockIdx.y * 8 + (warp >> 1) * 4;
+    const int tileX = blockIdx.x * 16 + (warp & 1) * 8, tileY = ((int)blockIdx.y + pr.blockY0) * 8 + (warp >> 1) * 4;
+#if PT_PREGEN
+    const unsigned long long tileRecord0 = (((unsigned long long)blockIdx.y * gridDim.x + blockIdx.x) * (PT_BLOCK_THREADS / 32) + (unsigned)warp) *
+                                           32ull * (unsigned long long)pr.samplesPerFrame;
+#endif
     const int gx = tileX + (lane & 7), gy = tileY + (lane >> 3);
     const bool inRange = (gx < pr.width) && (gy < pr.height);
     float* s_col = s_colAll + warp * PT_STEAL_WORDS;
@@ -1659,7 +1714,11 @@ __device__ __forceinline__ void pt_render_body_v3s(const PtDevScene& sc, const P
                     const int q = item & 31;
                     const int qx = tileX + (q & 7), qy = tileY + (q >> 3);
                     if ((qx < pr.width) && (qy < pr.height)) { /* else: a pixel beyond the image edge; claim again */
+#if PT_PREGEN
+                        const int nextState = PhaseNewFromRecord(c, ps, tileRecord0, roundBase + (item >> 5), q);
+#else
                         const int nextState = PhaseNew(c, ps, (unsigned)qx, (unsigned)pr.height - (unsigned)qy, roundBase + (item >> 5));
+#endif
                         alive = (nextState == PT_ST_ISECT); /* pathLength <= 0: PhaseNew left pendingFinish set */
                     }
                 }
@@ -1689,7 +1748,11 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tileX = blockIdx.x * 16 + (warp & 1) * 8, tileY = blockIdx.y * 8 + (warp >> 1) * 4;
+    const int tileX = blockIdx.x * 16 + (warp & 1) * 8, tileY = ((int)blockIdx.y + pr.blockY0) * 8 + (warp >> 1) * 4;
+#if PT_PREGEN
+    const unsigned long long tileRecord0 = (((unsigned long long)blockIdx.y * gridDim.x + blockIdx.x) * (PT_BLOCK_THREADS / 32) + (unsigned)warp) *
+                                           32ull * (unsigned long long)pr.samplesPerFrame;
+#endif
     const int gx = tileX + (lane & 7), gy = tileY + (lane >> 3);
     const bool inRange = (gx < pr.width) && (gy < pr.height);
     float* s_col = s_colAll + warp * PT_STEAL_WORDS;
@@ -1759,8 +1822,13 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
                 if (item < 32 * roundN) {
                     const int q = item & 31;
                     const int qx = tileX + (q & 7), qy = tileY + (q >> 3);
-                    if ((qx < pr.width) && (qy < pr.height)) /* else: a pixel beyond the image edge; claim again */
+                    if ((qx < pr.width) && (qy < pr.height)) { /* else: a pixel beyond the image edge; claim again */
+#if PT_PREGEN
+                        st = PhaseNewFromRecord(c, ps, tileRecord0, roundBase + (item >> 5), q);
+#else
                         st = PhaseNew(c, ps, (unsigned)qx, (unsigned)pr.height - (unsigned)qy, roundBase + (item >> 5));
+#endif
+                    }
                 } else {
                     st = PT_ST_IDLE;
                 }
@@ -1902,7 +1970,7 @@ __device__ __forceinline__ void pt_render_body_v2m(const PtDevScene& sc, const P
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tileX = blockIdx.x * 16 + (warp & 1) * 8, tileY = blockIdx.y * 8 + (warp >> 1) * 4;
+    const int tileX = blockIdx.x * 16 + (warp & 1) * 8, tileY = ((int)blockIdx.y + pr.blockY0) * 8 + (warp >> 1) * 4;
     const int gx = tileX + (lane & 7), gy = tileY + (lane >> 3);
     const bool inRange = (gx < pr.width) && (gy < pr.height);
     float* s_col = s_colAll + warp * (PT_STEAL_WORDS + PT_POOL_WORDS);
@@ -2120,6 +2188,11 @@ __device__ __forceinline__ void pt_render_body_v2m(const PtDevScene& sc, const P
 #else
 #error "PT_SCHED: 0 (v1), 5 (v2s), 7 (v3s) or 8 (v2m)"
 #endif
+
+/* the generation kernel of option "pregen" (same grid and block as the render kernel) */
+#define PT_DEFINE_GEN_KERNEL(name)                                                                           \
+    extern "C" __global__ void __launch_bounds__(PT_BLOCK_THREADS)                                           \
+    name(const __grid_constant__ PtDevParams pr, float4* __restrict__ gen) { PT_KERNEL_NS::pt_gen_body(pr, gen); }
 
 #if PT_HAS_SDF
 /* SDF()/SDFMATERIAL() at arbitrary points: used by the tests to compare the NVRTC build of the snippets with the

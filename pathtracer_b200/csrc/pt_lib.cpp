@@ -27,6 +27,7 @@ struct JitKernel {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kernel = nullptr;
     cudaKernel_t sdf_eval = nullptr; /* only for scenes with SDF snippets */
+    cudaKernel_t gen = nullptr;      /* option "pregen": the camera-ray generation kernel (pt_gen_body) */
     /* wavefront pipeline (pt_wavefront.cuh); wf_march only with SDF snippets */
     cudaKernel_t wf_gen = nullptr, wf_isect = nullptr, wf_march = nullptr, wf_shade = nullptr, wf_final = nullptr,
                  wf_ctl = nullptr;
@@ -44,6 +45,10 @@ struct pt_ctx {
     int bvh_min = PT_BVH_DEFAULT_MIN_PRIMS; /* bounded primitives from which the BVH replaces the scan; <= 0: never */
     PtKnobs knobs;           /* pt_set_option: tuning options of the run-time compiled kernels */
     std::vector<pt_surface_ext> surface_ext; /* pt_set_surface_ext: applied by the next pt_set_scene */
+    long long pregen_max_mb = 24576; /* option "pregen": largest record buffer; a dispatch that needs more runs in bands of CTA rows */
+    float4* d_gen = nullptr;
+    size_t gen_bytes = 0;
+    bool gen_clamped = false; /* the buffer is smaller than asked for because memory was short */
     long long wf_max_paths = 0; /* wavefront pipeline: paths in flight per chunk; 0 = auto (4 Mi without SDFs, 32 Mi with:
                                    profiles/r02_wf_l2) */
     bool bvh_active = false;
@@ -100,7 +105,45 @@ int launch(pt_ctx* ctx, const PtDevParams& dp) {
         PT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
         ctx->timing_open = true;
     }
-    if (ctx->active_jit) {
+    if (ctx->active_jit && ctx->active_jit->gen) {
+        /* option "pregen": the generation kernel writes one 32-byte record per sample of the launch, the render kernel reads
+         * them.  Both run on the same grid; a dispatch whose records outgrow the buffer runs as bands of CTA rows. */
+        const unsigned gx = (unsigned)((dp.width + 15) / 16), gy = (unsigned)((dp.height + 7) / 8);
+        const size_t per_row = (size_t)gx * 4u * 32u * (size_t)dp.samplesPerFrame; /* records of one CTA row */
+        size_t rows = ((size_t)ctx->pregen_max_mb << 20) / (per_row * 32u);
+        if (rows < 1) rows = 1;
+        if (rows > gy) rows = gy;
+        const size_t have_rows = ctx->gen_bytes / (per_row * 32u);
+        if (have_rows < rows && !(ctx->gen_clamped && have_rows >= 1)) { /* grow (rarely): only now ask how much memory is free */
+            const size_t want_rows = rows;
+            size_t free_b = 0, total_b = 0;
+            if (ctx->d_gen) { PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_gen); ctx->d_gen = nullptr; ctx->gen_bytes = 0; }
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && rows * per_row * 32u > free_b / 2) rows = (free_b / 2) / (per_row * 32u);
+            if (rows < 1) rows = 1;
+            PT_CUDA(ctx, cudaMalloc((void**)&ctx->d_gen, rows * per_row * 32u));
+            ctx->gen_bytes = rows * per_row * 32u;
+            ctx->gen_clamped = rows < want_rows; /* do not try again at every dispatch */
+        }
+        if (rows > ctx->gen_bytes / (per_row * 32u)) rows = ctx->gen_bytes / (per_row * 32u);
+        const float* ubo = ctx->d_ubo;
+        float* image = ctx->d_image;
+        const dim3 block(128, 1, 1);
+        for (unsigned y0 = 0; y0 < gy; y0 += (unsigned)rows) {
+            const unsigned ny = (gy - y0 < (unsigned)rows) ? gy - y0 : (unsigned)rows;
+            PtDevParams band = dp;
+            band.gen = ctx->d_gen;
+            band.genCount = (unsigned long long)ny * per_row;
+            band.blockY0 = (int)y0;
+            const dim3 grid(gx, ny, 1);
+            float4* gen = ctx->d_gen;
+            void* gargs[2] = {(void*)&band, (void*)&gen};
+            PT_CUDA(ctx, cudaLaunchKernel((const void*)ctx->active_jit->gen, grid, block, gargs, 0, ctx->stream));
+            void* args[4] = {(void*)&ctx->dev_scene, (void*)&band, (void*)&ubo, (void*)&image};
+            PT_CUDA(ctx, cudaLaunchKernel((const void*)ctx->active_jit->kernel, grid, block, args, 0, ctx->stream));
+            ctx->launches += 2;
+        }
+        ctx->launches--; /* the render kernel of the last band is counted below */
+    } else if (ctx->active_jit) {
         const dim3 grid((unsigned)((dp.width + 15) / 16), (unsigned)((dp.height + 7) / 8), 1), block(128, 1, 1);
         const float* ubo = ctx->d_ubo;
         float* image = ctx->d_image;
@@ -271,6 +314,7 @@ void pt_destroy(pt_ctx* ctx) {
         if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
     if (ctx->own_image && ctx->d_image) cudaFree(ctx->d_image);
     if (ctx->wf_block) cudaFree(ctx->wf_block);
+    if (ctx->d_gen) cudaFree(ctx->d_gen);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->ev_snap) cudaEventDestroy(ctx->ev_snap);
     if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
@@ -312,6 +356,11 @@ int pt_set_bvh(pt_ctx* ctx, int min_prims) {
 /* Tuning options (pt_abi.h): they select and parametrise the kernel pt_set_scene builds -- never the result */
 int pt_set_option(pt_ctx* ctx, const char* key, long long value) {
     if (!ctx || !key) return fail(ctx, PT_ERR_ARG, "pt_set_option: null argument");
+    if (std::string(key) == "pregen_max_mb") {
+        if (value < 1) return fail(ctx, PT_ERR_ARG, "pt_set_option: pregen_max_mb must be positive");
+        ctx->pregen_max_mb = value;
+        return PT_OK;
+    }
     if (std::string(key) == "wf_max_paths") {
         if (value < 0) return fail(ctx, PT_ERR_ARG, "pt_set_option: wf_max_paths must be positive (or 0 = auto)");
         ctx->wf_max_paths = value;
@@ -325,6 +374,7 @@ int pt_set_option(pt_ctx* ctx, const char* key, long long value) {
 int pt_get_option(const pt_ctx* ctx, const char* key, long long* value) {
     if (!ctx || !key || !value) return PT_ERR_ARG;
     if (std::string(key) == "wf_max_paths") { *value = ctx->wf_max_paths; return PT_OK; }
+    if (std::string(key) == "pregen_max_mb") { *value = ctx->pregen_max_mb; return PT_OK; }
     return pt_knob_get(&ctx->knobs, key, value) == 0 ? PT_OK : PT_ERR_ARG;
 }
 
@@ -418,6 +468,10 @@ int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, in
             if (n_sdf > 0 && (e = cudaLibraryGetKernel(&jk.sdf_eval, jk.lib, "pt_sdf_eval_jit")) != cudaSuccess) {
                 cudaLibraryUnload(jk.lib);
                 return cuda_fail(ctx, e, "cudaLibraryGetKernel(pt_sdf_eval_jit)");
+            }
+            if (pt_jit_uses_pregen(key) && (e = cudaLibraryGetKernel(&jk.gen, jk.lib, "pt_gen_jit")) != cudaSuccess) {
+                cudaLibraryUnload(jk.lib);
+                return cuda_fail(ctx, e, "cudaLibraryGetKernel(pt_gen_jit)");
             }
             if (wavefront) {
                 struct { const char* name; cudaKernel_t* k; bool need; } wk[] = {

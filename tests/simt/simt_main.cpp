@@ -32,6 +32,9 @@ extern "C" { unsigned long long pt_stats[16] = {0ull}; } /* the drivers' schedul
 #include "pt_kernel.cuh"
 
 PT_DEFINE_RENDER_KERNEL(pt_render_emu)
+#if PT_PREGEN
+PT_DEFINE_GEN_KERNEL(pt_gen_emu)
+#endif
 
 extern "C" int simt_sched(void) { return PT_SCHED; }
 
@@ -65,9 +68,26 @@ extern "C" int simt_dispatch(const pt_ubo* ubo, const pt_params* params, int acc
         fprintf(stderr, "simt: surface extensions set but the kernel was built without PT_EXT_BSDF\n");
         return -3;
     }
-    (void)persistent_ctas;
     gridDim = {(unsigned)((dp.width + 15) / 16), (unsigned)((dp.height + 7) / 8), 1u};
     blockDim = {PT_BLOCK_THREADS, 1u, 1u};
+#if PT_PREGEN
+    /* option "pregen" as pt_lib.cpp's launch() runs it: the generation kernel's records, then the render kernel, band by
+     * band of CTA rows (persistent_ctas = rows per band here; 0 = the whole frame at once).  Every block runs its
+     * generation part and then its render part: a block only reads the records of its own warps' tiles. */
+    const unsigned gy_all = gridDim.y;
+    const unsigned rows = (persistent_ctas > 0 && (unsigned)persistent_ctas < gy_all) ? (unsigned)persistent_ctas : gy_all;
+    const size_t per_row = (size_t)gridDim.x * 4u * 32u * (size_t)dp.samplesPerFrame;
+    std::vector<float4> gen(2 * rows * per_row);
+    for (unsigned y0 = 0; y0 < gy_all; y0 += rows) {
+    const unsigned ny = (gy_all - y0 < rows) ? gy_all - y0 : rows;
+    gridDim.y = ny;
+    dp.gen = gen.data();
+    dp.genCount = (unsigned long long)ny * per_row;
+    dp.blockY0 = (int)y0;
+    for (auto& g : gen) g = make_float4(NAN, NAN, NAN, NAN); /* a record nobody wrote would poison the image */
+#else
+    (void)persistent_ctas;
+#endif
     const float* ubo_f = reinterpret_cast<const float*>(ubo);
     float4* img = reinterpret_cast<float4*>(image);
     const int nwarps = PT_BLOCK_THREADS / 32;
@@ -95,11 +115,18 @@ extern "C" int simt_dispatch(const pt_ubo* ubo, const pt_params* params, int acc
                     simt_warp = wp;
                     simt_block = blk;
                     simt_phase = 0;
+#if PT_PREGEN
+                    pt_gen_emu(dp, dp.gen);
+                    __syncthreads();
+#endif
                     pt_render_emu(sc, dp, ubo_f, img);
                 });
             }
         }
         for (auto& th : threads) th.join();
     }
+#if PT_PREGEN
+    }
+#endif
     return 0;
 }

@@ -171,7 +171,8 @@ def test_nvrtc_builds_the_kernel_with_shipped_snippets(ptlib, name, mode):
     ('scene10', 0, {'sched': 8, 'steal_s': 16}),   # the pool shrinks until table + pool fit the 48 KB of static shared memory
     ('scene9', 1, {}), ('scene9', 1, {'sched': 8}), ('scene8', 1, {'sched': 5, 'steal_s': 8}), ('scene8', 1, {'sched': 8}), ('scene3', 1, {'sched': 8}),
     ('scene1', 1, {'sched': 0}), ('scene1', 1, {'sched': 5}), ('scene1', 1, {'sched': 7}), ('scene1', 0, {'sched': 7}), ('scene1', 1, {'sched': 8}),
-    ('scene0', 1, {'sched': 7}), ('scene2', 1, {'sched': 7}), ('scene10', 1, {'stats': 1, 'sched': 8})])
+    ('scene0', 1, {'sched': 7}), ('scene2', 1, {'sched': 7}), ('scene10', 1, {'stats': 1, 'sched': 8}),
+    ('scene10', 1, {'sched': 5, 'pregen': 1}), ('scene10', 0, {'sched': 5, 'pregen': 1}), ('scene1', 1, {'sched': 7, 'pregen': 1}), ('scene8', 1, {'pregen': 1})])
 def test_every_driver_of_the_megakernel_builds(ptlib, name, mode, options):
     """The scene-specialised kernel (jit policy 2) compiles with NVRTC for sm_100a under every driver / option the A/B
     measurements use (no GPU needed), stays inside the 48 KB of static shared memory and the register budget of its
@@ -187,6 +188,22 @@ def test_every_driver_of_the_megakernel_builds(ptlib, name, mode, options):
     assert regs <= 128
     spills = [int(x) for x in re.findall(r'(\d+) bytes spill stores', log)]
     assert max(spills) <= 192, log
+
+
+def test_generation_kernel_is_built_where_it_pays(ptlib):
+    """Option pregen, auto: scenes with a cyclide (their kernel outgrows the instruction cache with the camera inline) get
+    the generation kernel pt_gen_jit next to the render kernel, which then is some 260 instructions shorter; the others,
+    and the drivers that do not pool samples, do not -- unless asked."""
+    import re
+
+    def entries(name, options):
+        scene = pack.load_scene(scene_path(name))
+        log = ptlib.kernel_compile_check(pack.pack_ubo(scene), pack.sdf_sources(scene), 1, True, options)
+        return set(re.findall(r"Compiling entry function '(\w+)'", log))
+    assert 'pt_gen_jit' in entries('scene10', {}) and 'pt_gen_jit' in entries('scene0', {}) and 'pt_gen_jit' in entries('scene9', {})
+    assert 'pt_gen_jit' not in entries('scene1', {}) and 'pt_gen_jit' not in entries('scene8', {})
+    assert 'pt_gen_jit' in entries('scene1', {'pregen': 1}) and 'pt_gen_jit' not in entries('scene10', {'pregen': 0})
+    assert 'pt_gen_jit' not in entries('scene10', {'sched': 0, 'pregen': 1}) and 'pt_gen_jit' not in entries('scene10', {'sched': 8, 'pregen': 1})
 
 
 def test_unknown_option_is_an_error(ptlib):
