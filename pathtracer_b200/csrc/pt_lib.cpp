@@ -45,10 +45,13 @@ struct pt_ctx {
     int bvh_min = PT_BVH_DEFAULT_MIN_PRIMS; /* bounded primitives from which the BVH replaces the scan; <= 0: never */
     PtKnobs knobs;           /* pt_set_option: tuning options of the run-time compiled kernels */
     std::vector<pt_surface_ext> surface_ext; /* pt_set_surface_ext: applied by the next pt_set_scene */
-    long long pregen_max_mb = 24576; /* option "pregen": largest record buffer; a dispatch that needs more runs in bands of CTA rows */
+    long long pregen_max_mb = 4096;  /* option "pregen": record buffer of one band; a dispatch that needs more runs as bands of
+                                        CTA rows over two such buffers */
     float4* d_gen = nullptr;
     size_t gen_bytes = 0;
     bool gen_clamped = false; /* the buffer is smaller than asked for because memory was short */
+    cudaStream_t gen_stream = nullptr; /* second stream of a banded pregen dispatch */
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     long long wf_max_paths = 0; /* wavefront pipeline: paths in flight per chunk; 0 = auto (4 Mi without SDFs, 32 Mi with:
                                    profiles/r02_wf_l2) */
     bool bvh_active = false;
@@ -106,41 +109,74 @@ int launch(pt_ctx* ctx, const PtDevParams& dp) {
         ctx->timing_open = true;
     }
     if (ctx->active_jit && ctx->active_jit->gen) {
-        /* option "pregen": the generation kernel writes one 32-byte record per sample of the launch, the render kernel reads
-         * them.  Both run on the same grid; a dispatch whose records outgrow the buffer runs as bands of CTA rows. */
+        /* option "pregen": the generation kernel writes one 32-byte record per sample, the render kernel reads them; both
+         * run on the same grid.  A dispatch whose records outgrow pregen_max_mb runs as bands of CTA rows, alternating
+         * between two record buffers and two streams: band k + 1 is generated while band k renders and its render
+         * kernel fills the SMs that band k's last wave leaves idle (bands write disjoint texels).  Band k + 2 reuses
+         * band k's buffer in band k's stream, so stream order is all the synchronisation the buffers need; the second
+         * stream is forked from and joined to the context's stream with events around the dispatch. */
         const unsigned gx = (unsigned)((dp.width + 15) / 16), gy = (unsigned)((dp.height + 7) / 8);
         const size_t per_row = (size_t)gx * 4u * 32u * (size_t)dp.samplesPerFrame; /* records of one CTA row */
         size_t rows = ((size_t)ctx->pregen_max_mb << 20) / (per_row * 32u);
         if (rows < 1) rows = 1;
         if (rows > gy) rows = gy;
-        const size_t have_rows = ctx->gen_bytes / (per_row * 32u);
+        const size_t nbuf_want = rows < gy ? 2 : 1;
+        const size_t have_rows = ctx->gen_bytes / (per_row * 32u * nbuf_want);
         if (have_rows < rows && !(ctx->gen_clamped && have_rows >= 1)) { /* grow (rarely): only now ask how much memory is free */
             const size_t want_rows = rows;
             size_t free_b = 0, total_b = 0;
-            if (ctx->d_gen) { PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_gen); ctx->d_gen = nullptr; ctx->gen_bytes = 0; }
-            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && rows * per_row * 32u > free_b / 2) rows = (free_b / 2) / (per_row * 32u);
+            if (ctx->d_gen) {
+                PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                if (ctx->gen_stream) PT_CUDA(ctx, cudaStreamSynchronize(ctx->gen_stream));
+                cudaFree(ctx->d_gen);
+                ctx->d_gen = nullptr;
+                ctx->gen_bytes = 0;
+            }
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && nbuf_want * rows * per_row * 32u > free_b / 2)
+                rows = (free_b / 2) / (per_row * 32u * 2u);
             if (rows < 1) rows = 1;
-            PT_CUDA(ctx, cudaMalloc((void**)&ctx->d_gen, rows * per_row * 32u));
-            ctx->gen_bytes = rows * per_row * 32u;
+            const size_t nbuf = rows < gy ? 2 : 1;
+            PT_CUDA(ctx, cudaMalloc((void**)&ctx->d_gen, nbuf * rows * per_row * 32u));
+            ctx->gen_bytes = nbuf * rows * per_row * 32u;
             ctx->gen_clamped = rows < want_rows; /* do not try again at every dispatch */
         }
-        if (rows > ctx->gen_bytes / (per_row * 32u)) rows = ctx->gen_bytes / (per_row * 32u);
+        {   /* what the buffer we have allows */
+            const size_t nbuf = rows < gy ? 2 : 1;
+            if (rows * nbuf > ctx->gen_bytes / (per_row * 32u)) rows = ctx->gen_bytes / (per_row * 32u * 2u);
+            if (rows < 1) rows = 1; /* cannot happen: the buffer holds at least one row per stream */
+        }
+        const bool two = rows < gy;
+        if (two && !ctx->gen_stream) {
+            PT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->gen_stream, cudaStreamNonBlocking));
+            PT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            PT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        }
+        if (two) { /* fork: everything queued on the context's stream so far (scene upload, earlier dispatches, clears) comes first */
+            PT_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+            PT_CUDA(ctx, cudaStreamWaitEvent(ctx->gen_stream, ctx->ev_fork, 0));
+        }
         const float* ubo = ctx->d_ubo;
         float* image = ctx->d_image;
         const dim3 block(128, 1, 1);
-        for (unsigned y0 = 0; y0 < gy; y0 += (unsigned)rows) {
+        unsigned k = 0;
+        for (unsigned y0 = 0; y0 < gy; y0 += (unsigned)rows, k++) {
             const unsigned ny = (gy - y0 < (unsigned)rows) ? gy - y0 : (unsigned)rows;
+            cudaStream_t st = (k & 1u) ? ctx->gen_stream : ctx->stream;
             PtDevParams band = dp;
-            band.gen = ctx->d_gen;
+            band.gen = ctx->d_gen + (size_t)(k & 1u) * rows * per_row * 2u; /* two float4 per record: the odd bands' buffer follows the even ones' */
             band.genCount = (unsigned long long)ny * per_row;
             band.blockY0 = (int)y0;
             const dim3 grid(gx, ny, 1);
-            float4* gen = ctx->d_gen;
+            float4* gen = ctx->d_gen + (size_t)(k & 1u) * rows * per_row * 2u;
             void* gargs[2] = {(void*)&band, (void*)&gen};
-            PT_CUDA(ctx, cudaLaunchKernel((const void*)ctx->active_jit->gen, grid, block, gargs, 0, ctx->stream));
+            PT_CUDA(ctx, cudaLaunchKernel((const void*)ctx->active_jit->gen, grid, block, gargs, 0, st));
             void* args[4] = {(void*)&ctx->dev_scene, (void*)&band, (void*)&ubo, (void*)&image};
-            PT_CUDA(ctx, cudaLaunchKernel((const void*)ctx->active_jit->kernel, grid, block, args, 0, ctx->stream));
+            PT_CUDA(ctx, cudaLaunchKernel((const void*)ctx->active_jit->kernel, grid, block, args, 0, st));
             ctx->launches += 2;
+        }
+        if (two) { /* join */
+            PT_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->gen_stream));
+            PT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
         }
         ctx->launches--; /* the render kernel of the last band is counted below */
     } else if (ctx->active_jit) {
@@ -314,7 +350,10 @@ void pt_destroy(pt_ctx* ctx) {
         if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
     if (ctx->own_image && ctx->d_image) cudaFree(ctx->d_image);
     if (ctx->wf_block) cudaFree(ctx->wf_block);
+    if (ctx->gen_stream) { cudaStreamSynchronize(ctx->gen_stream); cudaStreamDestroy(ctx->gen_stream); }
     if (ctx->d_gen) cudaFree(ctx->d_gen);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->ev_snap) cudaEventDestroy(ctx->ev_snap);
     if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
