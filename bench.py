@@ -221,9 +221,10 @@ class ClockSampler:
 
 def ncu_traffic(wl):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the workload's kernel, from the committed
-    `ncu --set full` capture of the same bench command (profiles/<round>/ncu_summary_<cfg>.json; the texel
-    read-modify-write does not depend on the samples per launch).  Returns (bytes or None, the file it came from)."""
-    for sub in ('r02_final', 'r02_gpu1', 'r01_final4', 'r01_final'):
+    `ncu --set full` capture of the same bench command at 64 samples per step (profiles/<round>/ncu_summary_<cfg>.json):
+    the texel read-modify-write plus, with option pregen, the 32-byte records the render kernel reads.  Returns (bytes or
+    None, the file it came from)."""
+    for sub in ('r02_final2', 'r02_final', 'r02_gpu1', 'r01_final4', 'r01_final'):
         path = os.path.join(ROOT, 'profiles', sub, 'ncu_summary_%s.json' % wl.split('_')[0])
         try:
             with open(path) as f:
@@ -608,9 +609,9 @@ def roofline_for(m, peaks, peak_kind, fp32_peak, clocks, args):
         'peak_basis': ('measured in this run: pt_fp32_peak, 16 independent FFMA chains per thread on every SM, CUDA events' if fp32_peak else
                        'derived: 148 SM x 128 FP32 lanes x 2 x %s sm_max_mhz (%s)' % (peaks.get('sm_max_mhz', 1965.0), peak_kind)),
         'peak_derived_at_max_clock': derived_max, 'frac_of_derived_peak': achieved / derived_max,
-        'hbm': {'achieved_gbs': m['W'] * m['H'] * 32 / (m['dev_ms'] / m['K'] * 1e-3) / 1e9, 'peak_gbs': peaks.get('hbm_gbs'),
-                'algorithmic_bytes_per_launch': m['W'] * m['H'] * 32,
-                'pregen_record_bytes_per_step': (m['W'] * m['H'] * args.spf * 64) if m['launches'] > m['K'] else 0},
+        'hbm': (lambda rec: {'achieved_gbs': (m['W'] * m['H'] * 32 + rec) / (m['dev_ms'] / m['K'] * 1e-3) / 1e9, 'peak_gbs': peaks.get('hbm_gbs'),
+                             'algorithmic_bytes_per_launch': m['W'] * m['H'] * 32 + rec,
+                             'of_which_pregen_records': rec})((m['W'] * m['H'] * args.spf * 64) if m['launches'] > m['K'] else 0),
         'oracle_counters_per_sample': {k: v / max(cnt['samples'], 1) for k, v in cnt.items()},
     }
 
