@@ -131,10 +131,11 @@ typedef struct PtDevParams {
      * genCount float4 each -- (origin.xyz, dir.x) and (dir.y, dir.z, hero wavelength, seed bits) -- one record per
      * (warp tile, sample of the dispatch, pixel of the tile): record = (tile * samplesPerFrame + k) * 32 + pixel. */
     PT_WF_PTR(float4) gen;
+    PT_WF_PTR(float4) rad; /* option "resolve": genCount float4, the radiance bundle of every finished sample (same index) */
     unsigned long long genCount;
     int blockY0;           /* first CTA row (8 pixel rows each) of this launch: a dispatch whose records outgrow the scratch
                               buffer runs as several bands of CTA rows */
-    int pad1;
+    int pad1[3];
 } PtDevParams;
 
 /* Wavefront pipeline (pt_wavefront.cuh): device buffers of the path state, SoA. */

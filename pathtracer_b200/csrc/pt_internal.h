@@ -41,6 +41,7 @@ struct PtKnobs {
     int heavy_min = -1;   /* v2s: lanes that must wait before the box / lens / cyclide tests run as a phase of their own (0: inline) */
     int sin_poly_every = 0; /* fast mode: every k-th sin( of the SDF snippets is evaluated on the FMA pipe (0: none) */
     int pregen = -1;      /* v2s / v3s: camera rays from a generation kernel's records instead of inline (-1: auto) */
+    int resolve = -1;     /* with pregen: radiance -> XYZ and the per-pixel sum in a resolve kernel (-1: auto = with pregen) */
 };
 int pt_knob_set(PtKnobs* k, const char* key, long long value);       /* 0, or -1 for an unknown key / bad value */
 int pt_knob_get(const PtKnobs* k, const char* key, long long* value);
@@ -57,6 +58,7 @@ struct PtJitOptions {
 /* the complete translation unit pt_jit_compile would hand to NVRTC (also the key of every kernel cache) */
 std::string pt_jit_source(const std::string& sdf_unit, const PtJitOptions& opt);
 bool pt_jit_uses_pregen(const std::string& source); /* whether that translation unit reads its camera rays from records */
+bool pt_jit_uses_resolve(const std::string& source); /* ... and leaves XYZ projection and summation to the resolve kernel */
 int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::vector<char>* cubin, std::string* log);
 
 /* pt_kernels_{strict,fast}.cu: statically compiled generic kernels (no SDF) and helpers */

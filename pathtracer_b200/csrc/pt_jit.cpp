@@ -51,6 +51,9 @@ std::string g_load_error;
 #ifndef PT_DEFAULT_HEAVY_MIN
 #define PT_DEFAULT_HEAVY_MIN 0
 #endif
+#ifndef PT_DEFAULT_RESOLVE
+#define PT_DEFAULT_RESOLVE 0 /* until measured */
+#endif
 #ifndef PT_DEFAULT_SCHED_ANALYTIC
 #define PT_DEFAULT_SCHED_ANALYTIC 7 /* v3s: 10.73 vs v1's 9.96 Gsamples/s on cfg2, 8.10 vs 7.62 on cfg1 (profiles/r02_gpu1) */
 #endif
@@ -106,6 +109,7 @@ int pt_knob_set(PtKnobs* k, const char* key, long long value) {
     else if (s == "sin_poly_every") { if (v < 0 || v > 64) return -1; k->sin_poly_every = v; }
     else if (s == "heavy_min") { if (v < -1 || v > 32) return -1; k->heavy_min = v; }
     else if (s == "pregen") { if (v < -1 || v > 1) return -1; k->pregen = v; }
+    else if (s == "resolve") { if (v < -1 || v > 1) return -1; k->resolve = v; }
     else return -1;
     return 0;
 }
@@ -120,6 +124,7 @@ int pt_knob_get(const PtKnobs* k, const char* key, long long* value) {
     else if (s == "wf_refill") *value = k->wf_refill; else if (s == "bvh_while_while") *value = k->bvh_while_while;
     else if (s == "sin_poly_every") *value = k->sin_poly_every; else if (s == "heavy_min") *value = k->heavy_min;
     else if (s == "pregen") *value = k->pregen;
+    else if (s == "resolve") *value = k->resolve;
     else return -1;
     return 0;
 }
@@ -170,10 +175,18 @@ std::string pt_jit_source(const std::string& sdf_unit, const PtJitOptions& opt) 
     const int sdf_words = opt.counts[5] > 0 ? (opt.counts[5] + 31) / 32 : 1;
     if (sched == 8 && sdf_words > 1) sched = 5; /* the pool parks one mask word per path */
     const int no_unroll = k.no_unroll >= 0 ? k.no_unroll : ((has_sdf || (!opt.bvh && n_scanned > 16)) ? 1 : 0);
+    /* camera rays from records (pt_gen_body): the pooled megakernel drivers only */
+    /* auto: scenes with a cyclide -- their kernel is 39-41 KB of SASS with the camera inline and 35-36 KB without, i.e.
+     * the generation kernel buys the instruction cache (cfg5 3.93 -> 4.26, cfg1 8.17 -> 8.86, cfg3 3.49 -> 3.61 Gsamples/s);
+     * where the kernel fits anyway the records' 64 B per sample of memory traffic eat the gain (cfg2 11.49 -> 11.41, cfg4b
+     * 1.058 -> 1.050): profiles/r02_pregen */
+    const bool pregen = !opt.wavefront && (sched == 5 || sched == 7) && (k.pregen < 0 ? opt.counts[4] > 0 : k.pregen != 0);
+    const bool resolve = pregen && (k.resolve < 0 ? PT_DEFAULT_RESOLVE != 0 : k.resolve != 0);
     const bool pooled = (sched == 5 || sched == 7 || sched == 8);
     int steal_s = k.steal_s;
     if (steal_s < 0) steal_s = opt.mode == PT_MODE_FAST ? 0 : (sched == 8 ? 4 : 16);
     if (opt.mode != PT_MODE_FAST && steal_s == 0) steal_s = (sched == 8 ? 4 : 16); /* strict builds sum in sample order */
+    if (resolve) steal_s = 0; /* the resolve kernel sums in sample order in every mode: one round, no table, no shared sums */
     int pool_cap = k.pool_cap;
     /* static shared memory is capped at 48 KB: uniform block + per-warp table + per-warp pool of 50-word slots */
     while (sched == 8 && 16388 + 4 * 4 * ((steal_s == 0 ? 96 : 96 * steal_s) + 50 * pool_cap) > 49152 && pool_cap > 4) pool_cap--;
@@ -201,24 +214,21 @@ std::string pt_jit_source(const std::string& sdf_unit, const PtJitOptions& opt) 
         if (sched != 5 || opt.bvh || n_heavy == 0 || n_heavy > 32 || !opt.bake_counts) heavy_min = 0;
         src += "#define PT_HEAVY_MIN " + std::to_string(heavy_min) + "\n";
     }
-    /* camera rays from records (pt_gen_body): the pooled megakernel drivers only */
-    /* auto: scenes with a cyclide -- their kernel is 39-41 KB of SASS with the camera inline and 35-36 KB without, i.e.
-     * the generation kernel buys the instruction cache (cfg5 3.93 -> 4.26, cfg1 8.17 -> 8.86, cfg3 3.49 -> 3.61 Gsamples/s);
-     * where the kernel fits anyway the records' 64 B per sample of memory traffic eat the gain (cfg2 11.49 -> 11.41, cfg4b
-     * 1.058 -> 1.050): profiles/r02_pregen */
-    const bool pregen = !opt.wavefront && (sched == 5 || sched == 7) && (k.pregen < 0 ? opt.counts[4] > 0 : k.pregen != 0);
     if (pregen) src += "#define PT_PREGEN 1\n";
+    if (resolve) src += "#define PT_RESOLVE 1\n";
     if (k.stats) src += "#define PT_STATS 1\n";
     if (k.sin_poly_every > 0 && opt.mode == PT_MODE_FAST) src += "#define PT_SIN_POLY_EVERY " + std::to_string(k.sin_poly_every) + "\n";
     src += opt.wavefront ? "#include \"pt_wavefront.cuh\"\n" : "#include \"pt_kernel.cuh\"\n";
     src += sdf_unit;
     src += "\nPT_DEFINE_RENDER_KERNEL(pt_render_jit)\n";
     if (pregen) src += "PT_DEFINE_GEN_KERNEL(pt_gen_jit)\n";
+    if (resolve) src += "PT_DEFINE_RESOLVE_KERNEL(pt_resolve_jit)\n";
     if (has_sdf) src += "PT_DEFINE_SDF_EVAL_KERNEL(pt_sdf_eval_jit)\n";
     if (opt.wavefront) src += "PT_DEFINE_WAVEFRONT_KERNELS\n";
     return src;
 }
 
+bool pt_jit_uses_resolve(const std::string& source) { return source.find("#define PT_RESOLVE 1\n") != std::string::npos; }
 bool pt_jit_uses_pregen(const std::string& source) { return source.find("#define PT_PREGEN 1\n") != std::string::npos; }
 
 int pt_jit_compile(const std::string& sdf_unit, const PtJitOptions& opt, std::vector<char>* cubin, std::string* log) {

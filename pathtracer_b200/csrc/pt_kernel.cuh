@@ -974,8 +974,7 @@ PT_DEV void MarchStateInit(MarchState& ms) {
 /* Scene()'s tail, shader.comp:1477-1489: radiance -> XYZ, NaNs dropped.  The four table look-ups run through one
  * rolled loop body (instruction-cache footprint); the sum keeps the shader's order
  * ((rad.x*W(l.x) + rad.y*W(l.y)) + rad.z*W(l.z)) + rad.w*W(l.w), the first product initialising it. */
-PT_DEV V3 PathColor(const Ctx& c, const PathState& ps) {
-    V4 l = ps.l, r = ps.radiance;
+PT_DEV V3 PathColorOf(const Ctx& c, V4 l, V4 r) {
     V3 sum = mk3(0.0f, 0.0f, 0.0f);
 #if PT_HAS_SDF /* rolled where the kernel outgrows the instruction cache; unrolled (no rotations) where it does not */
 #pragma unroll 1
@@ -995,6 +994,7 @@ PT_DEV V3 PathColor(const Ctx& c, const PathState& ps) {
     if ((color.x != color.x) || (color.y != color.y) || (color.z != color.z)) color = mk3(0.0f, 0.0f, 0.0f);
     return color;
 }
+PT_DEV V3 PathColor(const Ctx& c, const PathState& ps) { return PathColorOf(c, ps.l, ps.radiance); }
 
 /* NEW: Scene() up to TracePath, shader.comp:1446-1472, for sample index pr.firstSample + k of pixel (xyx, xyy), in two
  * halves.  PhaseNewCamera is everything that depends on (pixel, sample index) alone -- seed, sensor jitter, aperture
@@ -1078,6 +1078,42 @@ __device__ __forceinline__ void pt_gen_body(const PtDevParams& pr, float4* __res
         b[32 * k] = make_float4(ray.dir.y, ray.dir.z, l_h, __uint_as_float(seed));
     }
 }
+#ifndef PT_RESOLVE
+#define PT_RESOLVE 0 /* 1 (with PT_PREGEN): finished samples leave their radiance bundle in pr.rad; pt_resolve_body projects and sums */
+#endif
+/* Resolve kernel of PT_RESOLVE: Scene()'s tail (radiance -> XYZ, shader.comp:1477-1489) and Rendering()'s sum over the
+ * samples (1492-1533) for pixel p of the warp's tile, in SAMPLE ORDER -- so the image does not depend on the schedule in
+ * any mode -- with all lanes busy, where the render kernel ran the four table look-ups for whichever lanes had just
+ * finished a path (17 of 32 on cfg5, 8 % of its instructions).  The wavelength bundle is rebuilt from the hero
+ * wavelength of the generation record. */
+__device__ __forceinline__ void pt_resolve_body(const PtDevParams& pr, const float* __restrict__ ubo, float4* __restrict__ image,
+                                                float* s_tab) {
+    for (int i = threadIdx.x; i < PT_SH_FLOATS; i += PT_BLOCK_THREADS) s_tab[i] = __ldg(ubo + PT_SH_BASE + i);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gx = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int gy = ((int)blockIdx.y + pr.blockY0) * 8 + (warp >> 1) * 4 + (lane >> 3);
+    if (gx >= pr.width || gy >= pr.height) return;
+    Ctx c;
+    c.sc = nullptr; c.pr = &pr; c.ubo = ubo; c.s_tab = s_tab;
+    const unsigned long long tile = ((unsigned long long)blockIdx.y * gridDim.x + blockIdx.x) * (PT_BLOCK_THREADS / 32) + (unsigned)warp;
+    const unsigned long long r0 = tile * 32ull * (unsigned long long)pr.samplesPerFrame + (unsigned)lane;
+    const float4* rad = pr.rad + r0;
+    const float4* rec = pr.gen + pr.genCount + r0; /* (dir.y, dir.z, hero wavelength, seed) */
+    V3 outColor = mk3(0.0f, 0.0f, 0.0f);
+#pragma unroll 1
+    for (int k = 0; k < pr.samplesPerFrame; k++) {
+        const float4 R = __ldg(rad + 32 * k);
+        const float l_h = __ldg(rec + 32 * k).z;
+        outColor = outColor + PathColorOf(c, SampleWavelengths(l_h), mk4(R.x, R.y, R.z, R.w));
+    }
+    StoreTexel(pr, image, gx, gy, outColor);
+}
+#if PT_RESOLVE
+PT_DEV void ResolveDeposit(const PtDevParams& pr, unsigned long long tileRecord0, int k, int q, V4 radiance) {
+    pr.rad[tileRecord0 + 32ull * (unsigned)k + (unsigned)q] = make_float4(radiance.x, radiance.y, radiance.z, radiance.w);
+}
+#endif
 #if PT_PREGEN
 /* NEW for item (sample k of the dispatch, pixel q of the warp's tile) from its record */
 PT_DEV int PhaseNewFromRecord(const Ctx& c, PathState& ps, unsigned long long tileRecord0, int k, int q) {
@@ -1706,7 +1742,11 @@ __device__ __forceinline__ void pt_render_body_v3s(const PtDevScene& sc, const P
         if ((__popc(bNew) >= PT_REGEN_T) || (bAlive == 0u)) { /* warp-uniform */
             if (wantNew) {
                 if (ps.pendingFinish) { /* Scene()'s tail for the path that ended, shader.comp:1477-1489 */
+#if PT_RESOLVE
+                    ResolveDeposit(pr, tileRecord0, roundBase + (item >> 5), item & 31, ps.radiance);
+#else
                     PoolDeposit(s_col, item, PathColor(c, ps));
+#endif
                     ps.pendingFinish = false;
                 }
                 item = next + __popc(bNew & ((1u << lane) - 1u));
@@ -1729,7 +1769,11 @@ __device__ __forceinline__ void pt_render_body_v3s(const PtDevScene& sc, const P
             if (!TraceRayFlat(c, ps)) alive = false; /* the phases left pendingFinish set */
         }
     }
+#if PT_RESOLVE
+    (void)inRange; (void)outColor; (void)image; (void)gx; (void)gy; /* pt_resolve_body writes the texels */
+#else
     if (inRange) StoreTexel(pr, image, gx, gy, outColor);
+#endif
 }
 
 /* ---- driver v2s (PT_SCHED 5): one phase per warp iteration, with the tile's sample pool ------------------------------
@@ -1815,7 +1859,11 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
         if (phase == PT_ST_NEW) {
             if (st == PT_ST_NEW) {
                 if (ps.pendingFinish) { /* the sample this lane just finished: item -> (pixel, sample of the round) */
+#if PT_RESOLVE
+                    ResolveDeposit(pr, tileRecord0, roundBase + (item >> 5), item & 31, ps.radiance);
+#else
                     PoolDeposit(s_col, item, PathColor(c, ps));
+#endif
                     ps.pendingFinish = false;
                 }
                 item = next + __popc(bNew & ((1u << lane) - 1u));
@@ -1878,7 +1926,11 @@ __device__ __forceinline__ void pt_render_body_v2s(const PtDevScene& sc, const P
          * that took part in this phase can have arrived at SHADE just now. */
         if (ran && st == PT_ST_SHADE) st = PhaseTrivial(ps);
     }
+#if PT_RESOLVE
+    (void)inRange; (void)outColor; (void)image; (void)gx; (void)gy; /* pt_resolve_body writes the texels */
+#else
     if (inRange) StoreTexel(pr, image, gx, gy, outColor);
+#endif
 }
 
 #if PT_HAS_SDF
@@ -2193,6 +2245,14 @@ __device__ __forceinline__ void pt_render_body_v2m(const PtDevScene& sc, const P
 #define PT_DEFINE_GEN_KERNEL(name)                                                                           \
     extern "C" __global__ void __launch_bounds__(PT_BLOCK_THREADS)                                           \
     name(const __grid_constant__ PtDevParams pr, float4* __restrict__ gen) { PT_KERNEL_NS::pt_gen_body(pr, gen); }
+
+/* the resolve kernel of option "resolve" (same grid and block again) */
+#define PT_DEFINE_RESOLVE_KERNEL(name)                                                                       \
+    extern "C" __global__ void __launch_bounds__(PT_BLOCK_THREADS)                                           \
+    name(const __grid_constant__ PtDevParams pr, const float* __restrict__ ubo, float4* __restrict__ image) { \
+        __shared__ float s_tab[PT_SH_FLOATS];                                                                \
+        PT_KERNEL_NS::pt_resolve_body(pr, ubo, image, s_tab);                                                \
+    }
 
 #if PT_HAS_SDF
 /* SDF()/SDFMATERIAL() at arbitrary points: used by the tests to compare the NVRTC build of the snippets with the

@@ -28,6 +28,7 @@ struct JitKernel {
     cudaKernel_t kernel = nullptr;
     cudaKernel_t sdf_eval = nullptr; /* only for scenes with SDF snippets */
     cudaKernel_t gen = nullptr;      /* option "pregen": the camera-ray generation kernel (pt_gen_body) */
+    cudaKernel_t resolve = nullptr;  /* option "resolve": radiance -> XYZ and the per-pixel sums (pt_resolve_body) */
     /* wavefront pipeline (pt_wavefront.cuh); wf_march only with SDF snippets */
     cudaKernel_t wf_gen = nullptr, wf_isect = nullptr, wf_march = nullptr, wf_shade = nullptr, wf_final = nullptr,
                  wf_ctl = nullptr;
@@ -117,11 +118,12 @@ int launch(pt_ctx* ctx, const PtDevParams& dp) {
          * stream is forked from and joined to the context's stream with events around the dispatch. */
         const unsigned gx = (unsigned)((dp.width + 15) / 16), gy = (unsigned)((dp.height + 7) / 8);
         const size_t per_row = (size_t)gx * 4u * 32u * (size_t)dp.samplesPerFrame; /* records of one CTA row */
-        size_t rows = ((size_t)ctx->pregen_max_mb << 20) / (per_row * 32u);
+        const size_t rec_bytes = ctx->active_jit->resolve ? 48u : 32u;             /* + the radiance bundle of option "resolve" */
+        size_t rows = ((size_t)ctx->pregen_max_mb << 20) / (per_row * rec_bytes);
         if (rows < 1) rows = 1;
         if (rows > gy) rows = gy;
         const size_t nbuf_want = rows < gy ? 2 : 1;
-        const size_t have_rows = ctx->gen_bytes / (per_row * 32u * nbuf_want);
+        const size_t have_rows = ctx->gen_bytes / (per_row * rec_bytes * nbuf_want);
         if (have_rows < rows && !(ctx->gen_clamped && have_rows >= 1)) { /* grow (rarely): only now ask how much memory is free */
             const size_t want_rows = rows;
             size_t free_b = 0, total_b = 0;
@@ -132,17 +134,17 @@ int launch(pt_ctx* ctx, const PtDevParams& dp) {
                 ctx->d_gen = nullptr;
                 ctx->gen_bytes = 0;
             }
-            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && nbuf_want * rows * per_row * 32u > free_b / 2)
-                rows = (free_b / 2) / (per_row * 32u * 2u);
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && nbuf_want * rows * per_row * rec_bytes > free_b / 2)
+                rows = (free_b / 2) / (per_row * rec_bytes * 2u);
             if (rows < 1) rows = 1;
             const size_t nbuf = rows < gy ? 2 : 1;
-            PT_CUDA(ctx, cudaMalloc((void**)&ctx->d_gen, nbuf * rows * per_row * 32u));
-            ctx->gen_bytes = nbuf * rows * per_row * 32u;
+            PT_CUDA(ctx, cudaMalloc((void**)&ctx->d_gen, nbuf * rows * per_row * rec_bytes));
+            ctx->gen_bytes = nbuf * rows * per_row * rec_bytes;
             ctx->gen_clamped = rows < want_rows; /* do not try again at every dispatch */
         }
         {   /* what the buffer we have allows */
             const size_t nbuf = rows < gy ? 2 : 1;
-            if (rows * nbuf > ctx->gen_bytes / (per_row * 32u)) rows = ctx->gen_bytes / (per_row * 32u * 2u);
+            if (rows * nbuf > ctx->gen_bytes / (per_row * rec_bytes)) rows = ctx->gen_bytes / (per_row * rec_bytes * 2u);
             if (rows < 1) rows = 1; /* cannot happen: the buffer holds at least one row per stream */
         }
         const bool two = rows < gy;
@@ -163,16 +165,23 @@ int launch(pt_ctx* ctx, const PtDevParams& dp) {
             const unsigned ny = (gy - y0 < (unsigned)rows) ? gy - y0 : (unsigned)rows;
             cudaStream_t st = (k & 1u) ? ctx->gen_stream : ctx->stream;
             PtDevParams band = dp;
-            band.gen = ctx->d_gen + (size_t)(k & 1u) * rows * per_row * 2u; /* two float4 per record: the odd bands' buffer follows the even ones' */
+            float4* buf = ctx->d_gen + (size_t)(k & 1u) * rows * per_row * (rec_bytes / 16u); /* the odd bands' buffer follows the even ones' */
+            band.gen = buf;                         /* two planes of genCount float4 */
+            band.rad = buf + 2u * (size_t)ny * per_row; /* one more for option "resolve" */
             band.genCount = (unsigned long long)ny * per_row;
             band.blockY0 = (int)y0;
             const dim3 grid(gx, ny, 1);
-            float4* gen = ctx->d_gen + (size_t)(k & 1u) * rows * per_row * 2u;
+            float4* gen = buf;
             void* gargs[2] = {(void*)&band, (void*)&gen};
             PT_CUDA(ctx, cudaLaunchKernel((const void*)ctx->active_jit->gen, grid, block, gargs, 0, st));
             void* args[4] = {(void*)&ctx->dev_scene, (void*)&band, (void*)&ubo, (void*)&image};
             PT_CUDA(ctx, cudaLaunchKernel((const void*)ctx->active_jit->kernel, grid, block, args, 0, st));
             ctx->launches += 2;
+            if (ctx->active_jit->resolve) {
+                void* rargs[3] = {(void*)&band, (void*)&ubo, (void*)&image};
+                PT_CUDA(ctx, cudaLaunchKernel((const void*)ctx->active_jit->resolve, grid, block, rargs, 0, st));
+                ctx->launches++;
+            }
         }
         if (two) { /* join */
             PT_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->gen_stream));
@@ -511,6 +520,10 @@ int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, in
             if (pt_jit_uses_pregen(key) && (e = cudaLibraryGetKernel(&jk.gen, jk.lib, "pt_gen_jit")) != cudaSuccess) {
                 cudaLibraryUnload(jk.lib);
                 return cuda_fail(ctx, e, "cudaLibraryGetKernel(pt_gen_jit)");
+            }
+            if (pt_jit_uses_resolve(key) && (e = cudaLibraryGetKernel(&jk.resolve, jk.lib, "pt_resolve_jit")) != cudaSuccess) {
+                cudaLibraryUnload(jk.lib);
+                return cuda_fail(ctx, e, "cudaLibraryGetKernel(pt_resolve_jit)");
             }
             if (wavefront) {
                 struct { const char* name; cudaKernel_t* k; bool need; } wk[] = {

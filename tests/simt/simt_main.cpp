@@ -35,6 +35,9 @@ PT_DEFINE_RENDER_KERNEL(pt_render_emu)
 #if PT_PREGEN
 PT_DEFINE_GEN_KERNEL(pt_gen_emu)
 #endif
+#if PT_RESOLVE
+PT_DEFINE_RESOLVE_KERNEL(pt_resolve_emu)
+#endif
 
 extern "C" int simt_sched(void) { return PT_SCHED; }
 
@@ -77,12 +80,13 @@ extern "C" int simt_dispatch(const pt_ubo* ubo, const pt_params* params, int acc
     const unsigned gy_all = gridDim.y;
     const unsigned rows = (persistent_ctas > 0 && (unsigned)persistent_ctas < gy_all) ? (unsigned)persistent_ctas : gy_all;
     const size_t per_row = (size_t)gridDim.x * 4u * 32u * (size_t)dp.samplesPerFrame;
-    std::vector<float4> gen(2 * rows * per_row);
+    std::vector<float4> gen(3 * rows * per_row); /* two planes of records + the radiance bundles of PT_RESOLVE */
     for (unsigned y0 = 0; y0 < gy_all; y0 += rows) {
     const unsigned ny = (gy_all - y0 < rows) ? gy_all - y0 : rows;
     gridDim.y = ny;
     dp.gen = gen.data();
     dp.genCount = (unsigned long long)ny * per_row;
+    dp.rad = gen.data() + 2 * dp.genCount;
     dp.blockY0 = (int)y0;
     for (auto& g : gen) g = make_float4(NAN, NAN, NAN, NAN); /* a record nobody wrote would poison the image */
 #else
@@ -120,6 +124,10 @@ extern "C" int simt_dispatch(const pt_ubo* ubo, const pt_params* params, int acc
                     __syncthreads();
 #endif
                     pt_render_emu(sc, dp, ubo_f, img);
+#if PT_RESOLVE
+                    __syncthreads();
+                    pt_resolve_emu(dp, ubo_f, img);
+#endif
                 });
             }
         }

@@ -478,6 +478,9 @@ DRIVER_CASES = [
     ({'sched': 5, 'steal_s': 16, 'pregen': 1}, 'scene10', 70, 45, 6, 3, 32, 2), ({'sched': 7, 'steal_s': 16, 'pregen': 1}, 'scene1', 96, 72, 40, 20, 5, 2),
     ({'sched': 5, 'steal_s': 4, 'pregen': 1, 'pregen_max_mb': 1}, 'scene9', 200, 120, 16, 8, 5, 2), ({'sched': 7, 'pregen': 1, 'pregen_max_mb': 1}, 'scene0', 333, 99, 12, 12, 5, 2),
     ({'sched': 5, 'pregen': 1}, 'scene1', 33, 17, 9, 9, 5, 1),
+    # ... and the XYZ projection + per-pixel sums in the resolve kernel (option resolve), whole frame and in bands
+    ({'sched': 5, 'pregen': 1, 'resolve': 1}, 'scene10', 70, 45, 6, 3, 32, 2), ({'sched': 7, 'pregen': 1, 'resolve': 1}, 'scene1', 96, 72, 40, 20, 5, 2),
+    ({'sched': 5, 'resolve': 1, 'pregen_max_mb': 1}, 'scene9', 200, 120, 16, 8, 5, 2), ({'sched': 7, 'resolve': 1, 'pregen_max_mb': 1}, 'scene0', 333, 99, 12, 12, 5, 2),
     # v2m: phase machine + pool of parked marching paths (default, tiny, never-full-enough and greedy pools)
     ({'sched': 8}, 'scene9', 96, 64, 4, 2, 5, 2), ({'sched': 8}, 'scene10', 70, 45, 6, 3, 32, 2), ({'sched': 8}, 'scene8', 64, 48, 4, 4, 5, 1),
     ({'sched': 8, 'pool_cap': 3, 'pool_min': 1, 'steal_s': 3}, 'scene8', 50, 37, 10, 10, 32, 2), ({'sched': 8, 'pool_min': 64}, 'scene7', 64, 40, 2, 1, 5, 2),

@@ -93,6 +93,8 @@ DRIVERS = {
     'v2s_heavy1': {'PT_SCHED': 5, 'PT_STEAL_S': 16, 'PT_HEAVY_MIN': 1}, 'v2s_heavy8': {'PT_SCHED': 5, 'PT_STEAL_S': 4, 'PT_HEAVY_MIN': 8},
     # camera rays from the generation kernel's records (option pregen), in bands of two CTA rows (emulate()'s ctas)
     'v2s_pregen': {'PT_SCHED': 5, 'PT_STEAL_S': 16, 'PT_PREGEN': 1}, 'v3s_pregen': {'PT_SCHED': 7, 'PT_STEAL_S': 3, 'PT_REGEN_T': 4, 'PT_PREGEN': 1},
+    # ... and radiance -> XYZ plus the per-pixel sums in the resolve kernel (option resolve): one round, no table, sample order
+    'v2s_resolve': {'PT_SCHED': 5, 'PT_STEAL_S': 0, 'PT_PREGEN': 1, 'PT_RESOLVE': 1}, 'v3s_resolve': {'PT_SCHED': 7, 'PT_STEAL_S': 0, 'PT_REGEN_T': 4, 'PT_PREGEN': 1, 'PT_RESOLVE': 1},
     'v2m': {'PT_SCHED': 8, 'PT_STEAL_S': 4, 'PT_POOL_CAP': 32, 'PT_POOL_MIN': 24},
     'v2m_tiny_pool': {'PT_SCHED': 8, 'PT_STEAL_S': 3, 'PT_POOL_CAP': 2, 'PT_POOL_MIN': 2},
     'v2m_lazy': {'PT_SCHED': 8, 'PT_STEAL_S': 8, 'PT_POOL_CAP': 7, 'PT_POOL_MIN': 64},
@@ -157,7 +159,7 @@ def test_emulated_drivers_at_the_edges(ptlib, name, w, h, spp, spf, pl):
     (v2s / v3s with PT_STEAL_S = 0) its image up to summation order."""
     ubo, p, src, raw = scene_inputs(name, w, h, spf, pl)
     ref = oracle.Oracle(ubo, src).render(p, spp, spf)
-    for driver in ('v1', 'v2s_table16', 'v3s_table3', 'v2s_pregen', 'v3s_pregen'):
+    for driver in ('v1', 'v2s_table16', 'v3s_table3', 'v2s_pregen', 'v3s_pregen', 'v2s_resolve', 'v3s_resolve'):
         got = emulate(build_emulator(ptlib, DRIVERS[driver], src, raw), ubo, p, spp, spf)
         assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), driver
     scale = float(ref[..., :3].max()) or 1.0
