@@ -35,7 +35,12 @@
  *   v2m (PT_SCHED 8)  v2s + a per-warp pool of PARKED paths in shared memory: a ray that has to march is parked with its
  *                     whole path state and its lane takes other work; the SDF phase marches parked rays with all 32
  *                     lanes whatever paths those lanes hold in registers
- * -- and the kernel entry macros.  pt_wavefront.cuh runs the same phases as separate kernels over state in HBM.
+ * -- two small kernels that take the coherent ends of Scene() out of the pooled drivers' hot loop (options pregen /
+ * resolve): pt_gen_body computes PhaseNew's camera half for every sample of a dispatch into 32-byte records with all
+ * lanes busy, pt_resolve_body projects stored radiance bundles to XYZ and sums them per pixel in sample order --
+ * and the kernel entry macros.  pt_wavefront.cuh runs the same phases as separate kernels over state in HBM.
+ * Surface extensions (PT_EXT_BSDF: mirror / glossy / dielectric lobes; NOT reference behaviour) are compiled in only for
+ * scenes that ask for them (pt_set_surface_ext).
  * Drivers that were measured and dropped (v2, v2p CTA job board, v2d two pixels per lane, v3, v2sp persistent tiles,
  * march parking inside v2s) live in the history of this file and in profiles/r01_*; DESIGN.md section 7 has their numbers.
  * The kernel is instruction-cache bound (16-byte SASS): single call sites and rolled loops are deliberate.
