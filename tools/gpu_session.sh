@@ -11,7 +11,8 @@
 #   launches         ncu launch list (gpu__time_duration) of the default bench command
 #   ncu:<workload>[:<opts>]   ncu --set full of the workload's render kernel + summary json + per-function profile
 #   stats:<workload>[:<opts>] scheduling statistics of the in-warp drivers
-#   sanitizer:<tool> compute-sanitizer --tool <memcheck|racecheck|initcheck> over a small parity subset, one run per driver
+#   sanitizer:<tool>[:<opts>] compute-sanitizer --tool <memcheck|racecheck|initcheck> over a small parity subset, one run per
+#                    driver and per generation / resolve kernel configuration (or only for the comma separated <opts>)
 #   wavefront        ncu of the wavefront pipeline's kernels on cfg3 (queue traffic, L2 hit rate, sectors per request)
 #   rmse             tools/rmse_vs_time.py with a strict reference at 1/4 resolution
 O=gpurun_out/$1; shift; mkdir -p $O
@@ -50,9 +51,10 @@ PY
          cub=$(ls $O/jd_$a/*.cubin 2>/dev/null | head -1); [ -n "$cub" ] && python tools/ncu_by_line.py $O/ncu_$tag.ncu-rep $cub pt_render_jit > $O/by_function_$tag.txt 2>&1
          rm -f $O/ncu_$tag.ncu-rep.tmp; head -c 1200 $O/ncu_summary_$tag.json;;
     stats) python tools/sched_stats.py $a $(echo $b | tr ',' ' ') > $O/stats_${a}_$(echo $b | tr ',=' '__').txt 2>&1; cat $O/stats_${a}_*.txt | tail -8;;
-    sanitizer) for drv in "sched=0" "sched=7" "sched=5" "sched=8"; do
-                 PT_TEST_OPTIONS=$drv timeout 1500 compute-sanitizer --tool $a --error-exitcode 1 python tools/sanitizer_subset.py $drv > $O/sanitizer_${a}_${drv/=/_}.log 2>&1
-                 echo "sanitizer $a $drv rc=$?" | tee -a $O/sanitizer_summary.txt; grep -E "ERROR SUMMARY|RACECHECK SUMMARY" $O/sanitizer_${a}_${drv/=/_}.log | tail -1 | tee -a $O/sanitizer_summary.txt
+    sanitizer) for drv in ${b:-"sched=0" "sched=7" "sched=5" "sched=8" "sched=5,pregen=1,resolve=1,pregen_max_mb=1" "sched=7,pregen=1,pregen_max_mb=1"}; do
+                 tag=$(echo $drv | tr ',=' '__')
+                 timeout 1500 compute-sanitizer --tool $a --error-exitcode 1 python tools/sanitizer_subset.py $(echo $drv | tr ',' ' ') > $O/sanitizer_${a}_$tag.log 2>&1
+                 echo "sanitizer $a $drv rc=$?" | tee -a $O/sanitizer_summary.txt; grep -E "ERROR SUMMARY|RACECHECK SUMMARY" $O/sanitizer_${a}_$tag.log | tail -1 | tee -a $O/sanitizer_summary.txt
                done;;
     wavefront) timeout 900 ncu --set full --clock-control none -k regex:pt_wf_ -s 40 -c 24 -f -o $O/ncu_wavefront python bench.py --workload cfg3_scene9_mandelbulb_1080p --pipeline wavefront --no-per-workload --no-cpu-baseline --no-rmse --steps 1 --warmup 3 --spf 16 > $O/ncu_wavefront.log 2>&1
                ncu -i $O/ncu_wavefront.ncu-rep --page raw --csv > $O/ncu_wavefront_raw.csv 2>/dev/null

@@ -16,6 +16,8 @@ from oracle import oracle  # noqa: E402
 opts = {k: int(v) for k, v in (a.split('=', 1) for a in sys.argv[1:] if '=' in a)}
 wavefront = 'wavefront' in sys.argv[1:]
 CASES = [('scene0', 40, 24, 4, 2, 5), ('scene1', 33, 17, 6, 3, 5), ('scene10', 40, 24, 4, 2, 5), ('scene9', 33, 17, 2, 2, 5), ('scene8', 32, 16, 2, 2, 5)]
+if opts.get('pregen_max_mb'):  # a frame whose records outgrow 1 MiB: eight bands over two buffers and two streams
+    CASES.append(('scene0', 200, 64, 16, 16, 5))
 bad = 0
 for mode in (pt.MODE_STRICT, pt.MODE_FAST):
     for name, w, h, spp, spf, pl in CASES:
