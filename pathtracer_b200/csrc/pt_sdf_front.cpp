@@ -136,6 +136,14 @@ bool rewrite(const std::string& in, std::string* out, std::string* err, std::vec
             continue;
         }
         if (c == '"' || c == '\'') { *err = "string and character literals are not GLSL"; return false; }
+        /* what would let a snippet assemble a refused identifier behind this filter's back: line splicing (and universal
+         * character names), the digraph spelling of # / ## (token pasting), and bytes outside GLSL's character set */
+        if (c == '\\') { *err = "'\\' (line continuation) is not accepted in SDF snippets"; return false; }
+        if (c == '%' && i + 1 < n && s[i + 1] == ':') { *err = "the digraph '%:' is not GLSL"; return false; }
+        if (c == '$' || c == '@' || c == '`' || (unsigned char)c >= 0x80 || ((unsigned char)c < 0x20 && c != '\n' && c != '\r' && c != '\t')) {
+            *err = "character outside GLSL's character set in SDF snippet";
+            return false;
+        }
         if (c == ':' && i + 1 < n && s[i + 1] == ':') { *err = "'::' is not GLSL"; return false; }
         if (c == '-' && i + 1 < n && s[i + 1] == '>') { *err = "'->' is not GLSL"; return false; }
         if ((c == '*' || c == '&') && !(i + 1 < n && s[i + 1] == '=') && !(c == '&' && i + 1 < n && s[i + 1] == '&') &&
