@@ -111,3 +111,35 @@ def test_capacity_is_the_uniform_block(ptlib):
     bad = pack.pack_ubo(base)
     bad[0] = 400.0   # a hand-made block claiming more spheres than objects[] holds
     assert L.pt_kernel_compile_check(bad.ctypes.data_as(C.c_void_p), api._c_strings([]), 0, 1, 0) == -1
+
+
+def test_loader_survives_mutated_scene_files(ptlib):
+    """Scene files come from outside: byte flips, truncations, deleted chunks and absurd nesting of a shipped scene are
+    either parsed (and then pack, save and report their extensions without incident) or refused with PT_ERR_IO /
+    PT_ERR_ARG -- the loader never crashes the host (the reference throws from nlohmann::json, host:893-908)."""
+    import random
+    rnd = random.Random(7)
+    base = open(scene_path('scene10')).read()
+    parsed = refused = 0
+    for it in range(800):
+        s = list(base)
+        mode = it % 4
+        if mode == 0:
+            for _ in range(rnd.randint(1, 8)):
+                s[rnd.randrange(len(s))] = chr(rnd.choice([0x20, 0x22, 0x2c, 0x5b, 0x5d, 0x7b, 0x7d, 0x30, 0x2d, 0x65, 0x2e, 0x5c, 0x0a, 0x01, 0xe9]))
+        elif mode == 1:
+            s = s[:rnd.randrange(len(s))]
+        elif mode == 2:
+            i = rnd.randrange(len(s))
+            del s[i:i + rnd.randint(1, 200)]
+        else:
+            i = rnd.randrange(len(s))
+            s[i:i] = list(rnd.choice(['[', '{"a":']) * rnd.randint(1, 5000))
+        try:
+            sc = ptlib.Scene.parse(''.join(s))
+            sc.pack_ubo(), sc.to_json(), sc.surface_ext(), sc.pack_params(1, 64, 64, 1, 5)
+            parsed += 1
+        except ptlib.PtError as e:
+            assert e.code in (-1, -4), e
+            refused += 1
+    assert parsed > 50 and refused > 300, (parsed, refused)
