@@ -138,7 +138,13 @@ int launch(pt_ctx* ctx, const PtDevParams& dp) {
                 rows = (free_b / 2) / (per_row * rec_bytes * 2u);
             if (rows < 1) rows = 1;
             const size_t nbuf = rows < gy ? 2 : 1;
-            PT_CUDA(ctx, cudaMalloc((void**)&ctx->d_gen, nbuf * rows * per_row * rec_bytes));
+            if (cudaMalloc((void**)&ctx->d_gen, nbuf * rows * per_row * rec_bytes) != cudaSuccess) {
+                (void)cudaGetLastError();
+                ctx->d_gen = nullptr;
+                return fail(ctx, PT_ERR_CUDA, "no memory for the camera-ray records of one row of tiles (" +
+                                                  std::to_string((nbuf * rows * per_row * rec_bytes) >> 20) +
+                                                  " MiB): dispatch fewer samples at a time or pt_set_option(ctx, \"pregen\", 0)");
+            }
             ctx->gen_bytes = nbuf * rows * per_row * rec_bytes;
             ctx->gen_clamped = rows < want_rows; /* do not try again at every dispatch */
         }
