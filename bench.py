@@ -68,7 +68,11 @@ def quiet_stdout():
         os.dup2(2, 1)
 
 
+_T_PROCESS = time.perf_counter()
+
+
 def emit(line):
+    line.setdefault('wall_s_process', round(time.perf_counter() - _T_PROCESS, 2))  # everything: imports, JIT, CPU legs, parity
     data = (json.dumps(line) + '\n').encode()
     if _REAL_STDOUT is None:
         sys.stdout.write(data.decode())
