@@ -41,6 +41,7 @@ struct PtKnobs {
     int heavy_min = -1;   /* v2s: lanes that must wait before the box / lens / cyclide tests run as a phase of their own (0: inline) */
     int sin_poly_every = 0; /* fast mode: every k-th sin( of the SDF snippets is evaluated on the FMA pipe (0: none) */
     int pregen = -1;      /* v2s / v3s: camera rays from a generation kernel's records instead of inline (-1: auto) */
+    int pathcolor_unroll = -1; /* SDF builds: PathColor's four CIE look-ups unrolled (-1: auto = with pregen) */
     int resolve = -1;     /* with pregen: radiance -> XYZ and the per-pixel sum in a resolve kernel (-1: auto = with pregen) */
 };
 int pt_knob_set(PtKnobs* k, const char* key, long long value);       /* 0, or -1 for an unknown key / bad value */

@@ -66,6 +66,9 @@
 #ifndef PT_HAS_SDF
 #define PT_HAS_SDF 0
 #endif
+#ifndef PT_PATHCOLOR_UNROLL
+#define PT_PATHCOLOR_UNROLL 0 /* experiment: PathColor's four table look-ups unrolled also in SDF builds */
+#endif
 #ifndef PT_EXT_BSDF
 #define PT_EXT_BSDF 0 /* 1: the scene carries surface extensions (pt_set_surface_ext); 0 = the reference's shading, untouched */
 #endif
@@ -948,6 +951,9 @@ struct PathState {
     bool pendingFinish; /* a finished path whose radiance is still to be projected to XYZ */
     bool inside;        /* PT_EXT_BSDF: the path is inside a dielectric (toggled by every refraction); else always false */
     V3 shDir;
+    V3 traceDir;        /* direction of the ray being traced: shDir while a shadow ray is pending, else ray.dir.  The phases that
+                           serve both kinds of ray read this instead of selecting (three FSEL per intersection and per SDF
+                           evaluation, on the half-rate ALU pipe); drivers that never read it pay nothing (dead stores) */
     V4 shContrib;       /* added to radiance iff the shadow ray sees object shObj (kDeferEmit: the factor Emit() is scaled by) */
     int shObj;
     float shScale, shT, shL; /* kDeferEmit only: (Emit(l, shT, shL) * shContrib) * shScale is the contribution */
@@ -967,7 +973,7 @@ PT_DEV void PathStateInit(PathState& ps) {
     ps.ray.origin = z3; ps.ray.dir = z3; ps.l = z4; ps.radiance = z4; ps.rayradiance = z4;
     ps.MISBRDFWeight = 1.0f; ps.seed = 0u; ps.bounce = 0;
     ps.isShadow = false; ps.pathAlive = false; ps.pendingFinish = false; ps.inside = false;
-    ps.shDir = z3; ps.shContrib = z4; ps.shObj = 0; ps.shScale = 0.0f; ps.shT = 0.0f; ps.shL = 0.0f;
+    ps.shDir = z3; ps.traceDir = z3; ps.shContrib = z4; ps.shObj = 0; ps.shScale = 0.0f; ps.shT = 0.0f; ps.shL = 0.0f;
     ps.h.t = 1e5f; ps.h.normal = z3; ps.h.materialID = 0.0f; ps.h.lightID = -1.0f; ps.h.objectID = -1;
 }
 PT_DEV void MarchStateInit(MarchState& ms) {
@@ -981,7 +987,7 @@ PT_DEV void MarchStateInit(MarchState& ms) {
  * ((rad.x*W(l.x) + rad.y*W(l.y)) + rad.z*W(l.z)) + rad.w*W(l.w), the first product initialising it. */
 PT_DEV V3 PathColorOf(const Ctx& c, V4 l, V4 r) {
     V3 sum = mk3(0.0f, 0.0f, 0.0f);
-#if PT_HAS_SDF /* rolled where the kernel outgrows the instruction cache; unrolled (no rotations) where it does not */
+#if PT_HAS_SDF && !PT_PATHCOLOR_UNROLL /* rolled where the kernel outgrows the instruction cache; unrolled (no rotations) where it does not */
 #pragma unroll 1
 #else
 #pragma unroll
@@ -1037,6 +1043,7 @@ PT_DEV void PhaseNewCamera(const Ctx& c, unsigned xyx, unsigned xyy, int k, Ray&
 }
 PT_DEV int PhaseNewFinish(const Ctx& c, PathState& ps, const Ray& ray, float l_h, unsigned seed) {
     ps.ray = ray;
+    ps.traceDir = ray.dir;
     ps.l = SampleWavelengths(l_h);
     ps.seed = seed;
     ps.radiance = mk4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -1150,7 +1157,7 @@ PT_DEV bool MarchBegin(const Ctx& c, V3 origin, V3 dir, MarchState& ms) {
 PT_DEV int PhaseIsect(const Ctx& c, PathState& ps, MarchState& ms) {
     Ray r;
     r.origin = ps.ray.origin;
-    r.dir = ps.isShadow ? ps.shDir : ps.ray.dir;
+    r.dir = ps.traceDir;
     IntersectionAnalytic(c, r, ps.h, ps.isShadow);
 #if PT_HAS_SDF
     if (MarchBegin(c, r.origin, r.dir, ms)) return PT_ST_SDF;
@@ -1164,7 +1171,7 @@ PT_DEV int PhaseIsect(const Ctx& c, PathState& ps, MarchState& ms) {
 PT_DEV int PhaseIsectLight(const Ctx& c, PathState& ps, MarchState& ms, unsigned& cand) {
     Ray r;
     r.origin = ps.ray.origin;
-    r.dir = ps.isShadow ? ps.shDir : ps.ray.dir;
+    r.dir = ps.traceDir;
     cand = IntersectLight(c, r, ps.h, ps.isShadow);
 #if PT_HAS_SDF
     if (MarchBegin(c, r.origin, r.dir, ms)) return PT_ST_SDF;
@@ -1174,7 +1181,7 @@ PT_DEV int PhaseIsectLight(const Ctx& c, PathState& ps, MarchState& ms, unsigned
 PT_DEV void PhaseHeavy(const Ctx& c, PathState& ps, unsigned cand) {
     Ray r;
     r.origin = ps.ray.origin;
-    r.dir = ps.isShadow ? ps.shDir : ps.ray.dir;
+    r.dir = ps.traceDir;
     IntersectHeavy(c, r, ps.h, ps.isShadow, cand);
 }
 #endif
@@ -1186,7 +1193,7 @@ PT_DEV void PhaseHeavy(const Ctx& c, PathState& ps, unsigned cand) {
  * bookkeeping for one evaluated distance, shader.comp:801-858). */
 PT_DEV V3 SdfMarchPoint(const PathState& ps, const MarchState& ms) {
     if (ms.sub == PT_SUB_SIGN) return ps.ray.origin; /* k = sign(SDF(ray.origin)), shader.comp:801 */
-    return fma3(ps.isShadow ? ps.shDir : ps.ray.dir, ms.mt, ps.ray.origin);
+    return fma3(ps.traceDir, ms.mt, ps.ray.origin);
 }
 PT_DEV V3 SdfProbePoint(V3 p, int j) {
     const int axis = j >> 1;
@@ -1202,7 +1209,7 @@ PT_DEV int SdfMarchConsume(const Ctx& c, PathState& ps, MarchState& ms, float d)
         return PT_ST_SDF;
     }
     /* one iteration of the loop at shader.comp:803-849 */
-    const V3 dir = ps.isShadow ? ps.shDir : ps.ray.dir;
+    const V3 dir = ps.traceDir;
     const float radius = d;
     bool finished = false, nohit = false;
     if (ms.insT > (fabsf(ms.previousRadius) + fabsf(radius))) {
@@ -1284,6 +1291,7 @@ PT_DEV int PhaseTrivial(PathState& ps) {
     if (ps.isShadow) {
         if (ps.h.objectID == ps.shObj) ps.radiance = ps.radiance + ps.shContrib;
         ps.isShadow = false;
+        ps.traceDir = ps.ray.dir; /* the path ray that was waiting behind the shadow ray */
         if (ps.pathAlive) return PT_ST_ISECT;
         ps.pendingFinish = true;
         return PT_ST_NEW;
@@ -1511,6 +1519,7 @@ PT_DEV int PhaseShadeHitT(const Ctx& c, PathState& ps) {
     }
     ps.ray.origin = outOrigin;
     ps.ray.dir = outDir; /* next path direction; a pending shadow ray travels along shDir */
+    ps.traceDir = needShadow ? ps.shDir : outDir;
     if (needShadow) {
         ps.isShadow = true;
         ps.pathAlive = alive;
@@ -1535,7 +1544,7 @@ PT_DEV int PhaseShade(const Ctx& c, PathState& ps) {
 #if PT_HAS_SDF
 PT_DEV_NOINLINE void SphereTracing(const Ctx& c, const Ray& ray, Hit& h, const bool kShadow) {
     PathState js;
-    js.ray = ray; js.shDir = ray.dir; js.isShadow = kShadow; js.h = h;
+    js.ray = ray; js.shDir = ray.dir; js.traceDir = ray.dir; js.isShadow = kShadow; js.h = h;
     MarchState ms;
     if (!MarchBegin(c, ray.origin, ray.dir, ms)) return;
     int st = PT_ST_SDF;
@@ -2007,6 +2016,7 @@ PT_DEV void PoolPickup(const float* e, PathState& ps, int& item) {
     ps.ray.origin = mk3(PT_PF(PF_OX), PT_PF(PF_OY), PT_PF(PF_OZ));
     ps.ray.dir = mk3(PT_PF(PF_DX), PT_PF(PF_DY), PT_PF(PF_DZ));
     ps.shDir = mk3(PT_PF(PF_SX), PT_PF(PF_SY), PT_PF(PF_SZ));
+    ps.traceDir = ps.ray.dir; /* a READY path goes through PhaseTrivial / SHADE, which set it, before anything reads it */
     const unsigned pk = __float_as_uint(PT_PF(PF_FLAGS));
     ps.bounce = (int)(pk & 0x1fffffffu); ps.inside = PT_EXT_BSDF ? (((pk >> 29) & 1u) != 0u) : false; ps.isShadow = ((pk >> 30) & 1u) != 0u; ps.pathAlive = (pk >> 31) != 0u;
     ps.pendingFinish = false;
@@ -2154,6 +2164,7 @@ __device__ __forceinline__ void pt_render_body_v2m(const PtDevScene& sc, const P
                 PoolLoadMarch(e, jm);
             }
             js.shDir = js.ray.dir;
+            js.traceDir = js.ray.dir;
             int jst = (own || job) ? PT_ST_SDF : PT_ST_DONE;
 #pragma unroll 1
             for (int rep = 0; rep < PT_SDF_REPS; rep++) {

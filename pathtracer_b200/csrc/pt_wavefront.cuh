@@ -78,9 +78,11 @@ PT_DEV void LoadRay(const PtWf& w, unsigned p, PathState& ps) {
     if (ps.isShadow) {
         const float4 d = w.shD[p];
         ps.shDir = mk3(d.x, d.y, d.z);
+        ps.traceDir = ps.shDir;
     } else {
         const float4 d = w.rayD[p];
         ps.ray.dir = mk3(d.x, d.y, d.z);
+        ps.traceDir = ps.ray.dir;
     }
 }
 PT_DEV void StoreHit(const PtWf& w, unsigned p, const Hit& h) {
