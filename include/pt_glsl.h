@@ -41,7 +41,10 @@
  * ALU pipe.  Differs from GLSL's (y < x) ? y : x only when an operand is NaN (IEEE minNum / maxNum return the other one) */
 #define PT_FN_MIN(x, y) fminf(x, y)
 #define PT_FN_MAX(x, y) fmaxf(x, y)
+/* x - y * floor(x / y) as one FFMA after the floor (with y = 2 the compiler otherwise emits t + t and two FADDs) */
+#define PT_FN_MOD(x, y) fmaf(-(y), floorf((x) / (y)), (x))
 #else
+#define PT_FN_MOD(x, y) ((x) - (y) * pt_floor((x) / (y)))
 #define PT_FN_MIN(x, y) (((y) < (x)) ? (y) : (x))
 #define PT_FN_MAX(x, y) (((x) < (y)) ? (y) : (x))
 #define PT_FN_SIN(x) pt_sin(x)
@@ -221,7 +224,7 @@ PT_HD int max(int x, int y) { return (x < y) ? y : x; }
 PT_HD float clamp(float x, float lo, float hi) { return min(max(x, lo), hi); }
 PT_HD float mix(float x, float y, float a) { return x * (1.0f - a) + y * a; }
 PT_HD float step(float e, float x) { return (x < e) ? 0.0f : 1.0f; }
-PT_HD float mod(float x, float y) { return x - y * pt_floor(x / y); }
+PT_HD float mod(float x, float y) { return PT_FN_MOD(x, y); } /* GLSL 4.50 8.3: x - y * floor(x / y) */
 PT_HD float smoothstep(float e0, float e1, float x) {
     float t = clamp((x - e0) / (e1 - e0), 0.0f, 1.0f);
     return t * t * (3.0f - 2.0f * t);
