@@ -1998,7 +1998,7 @@ PT_DEV void PoolLoadMarch(const float* e, MarchState& ms) {
 PT_DEV void PoolPark(float* e, const PathState& ps, const MarchState& ms, int item) {
     PT_PF(PF_OX) = ps.ray.origin.x; PT_PF(PF_OY) = ps.ray.origin.y; PT_PF(PF_OZ) = ps.ray.origin.z;
     PT_PF(PF_DX) = ps.ray.dir.x; PT_PF(PF_DY) = ps.ray.dir.y; PT_PF(PF_DZ) = ps.ray.dir.z;
-    PT_PF(PF_SX) = ps.shDir.x; PT_PF(PF_SY) = ps.shDir.y; PT_PF(PF_SZ) = ps.shDir.z;
+    PT_PF(PF_SX) = ps.traceDir.x; PT_PF(PF_SY) = ps.traceDir.y; PT_PF(PF_SZ) = ps.traceDir.z; /* the marching ray's direction */
     PT_PF(PF_FLAGS) = __uint_as_float((unsigned)ps.bounce | ((unsigned)ps.inside << 29) | ((unsigned)ps.isShadow << 30) | ((unsigned)ps.pathAlive << 31));
     PT_PF(PF_HT) = ps.h.t; PT_PF(PF_HOBJ) = __int_as_float(ps.h.objectID);
     PoolStoreMarch(e, ms);
@@ -2016,7 +2016,7 @@ PT_DEV void PoolPickup(const float* e, PathState& ps, int& item) {
     ps.ray.origin = mk3(PT_PF(PF_OX), PT_PF(PF_OY), PT_PF(PF_OZ));
     ps.ray.dir = mk3(PT_PF(PF_DX), PT_PF(PF_DY), PT_PF(PF_DZ));
     ps.shDir = mk3(PT_PF(PF_SX), PT_PF(PF_SY), PT_PF(PF_SZ));
-    ps.traceDir = ps.ray.dir; /* a READY path goes through PhaseTrivial / SHADE, which set it, before anything reads it */
+    ps.traceDir = ps.shDir; /* (a READY path goes through PhaseTrivial / SHADE, which set it again, before anything reads it) */
     const unsigned pk = __float_as_uint(PT_PF(PF_FLAGS));
     ps.bounce = (int)(pk & 0x1fffffffu); ps.inside = PT_EXT_BSDF ? (((pk >> 29) & 1u) != 0u) : false; ps.isShadow = ((pk >> 30) & 1u) != 0u; ps.pathAlive = (pk >> 31) != 0u;
     ps.pendingFinish = false;
@@ -2152,13 +2152,13 @@ __device__ __forceinline__ void pt_render_body_v2m(const PtDevScene& sc, const P
             PathState js; /* the marching ray: only ray.origin, the direction, isShadow and h are read / written */
             MarchState jm = ms;
             js.ray.origin = ps.ray.origin;
-            js.ray.dir = ps.isShadow ? ps.shDir : ps.ray.dir;
+            js.ray.dir = ps.traceDir;
             js.isShadow = ps.isShadow;
             js.h = ps.h;
             if (job) {
                 js.ray.origin = mk3(PT_PF(PF_OX), PT_PF(PF_OY), PT_PF(PF_OZ));
                 js.isShadow = ((__float_as_uint(PT_PF(PF_FLAGS)) >> 30) & 1u) != 0u;
-                js.ray.dir = js.isShadow ? mk3(PT_PF(PF_SX), PT_PF(PF_SY), PT_PF(PF_SZ)) : mk3(PT_PF(PF_DX), PT_PF(PF_DY), PT_PF(PF_DZ));
+                js.ray.dir = mk3(PT_PF(PF_SX), PT_PF(PF_SY), PT_PF(PF_SZ)); /* the traced direction, shadow or path ray alike */
                 js.h.t = PT_PF(PF_HT);
                 js.h.objectID = __float_as_int(PT_PF(PF_HOBJ));
                 PoolLoadMarch(e, jm);

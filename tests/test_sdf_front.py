@@ -187,7 +187,7 @@ def test_every_driver_of_the_megakernel_builds(ptlib, name, mode, options):
     assert smem <= 48 * 1024
     assert regs <= 128
     spills = [int(x) for x in re.findall(r'(\d+) bytes spill stores', log)]
-    assert max(spills) <= 192, log
+    assert max(spills) <= (256 if options.get('sched') == 8 else 192), log  # v2m (not a default) carries a pool's worth of state
 
 
 def test_generation_kernel_is_built_where_it_pays(ptlib):
