@@ -149,6 +149,8 @@ int pt_bvh_active(const pt_ctx* ctx);
  *                 over two such buffers and two streams (4K x 64 spp: 17 GiB of records; bands of 4 / 2 / 1 GiB cost
  *                 0.2 / 0.7 / 4.5 %)                                                                          [4096]
  *   "stats"       1 builds the scheduling counters in (pt_debug_stats)                                      [0]
+ *   "wf_sort"     wavefront pipeline, scenes with surface extensions: 1 = SHADE's path rays grouped by lobe by a
+ *                 two-pass counting sort ("material-sorted shading"); same image; measured slower, hence           [0]
  *   "wf_refill", "wf_max_paths"   wavefront pipeline: evaluations between refills; paths in flight per chunk (a chunk is
  *                                 a band of consecutive pixels x some samples; 0 = auto: 4 Mi without SDFs, 32 Mi with)
  *   "bvh_while_while"             BVH traversal loop shape */

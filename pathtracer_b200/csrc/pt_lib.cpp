@@ -30,6 +30,7 @@ struct JitKernel {
     cudaKernel_t gen = nullptr;      /* option "pregen": the camera-ray generation kernel (pt_gen_body) */
     cudaKernel_t resolve = nullptr;  /* option "resolve": radiance -> XYZ and the per-pixel sums (pt_resolve_body) */
     /* wavefront pipeline (pt_wavefront.cuh); wf_march only with SDF snippets */
+    cudaKernel_t wf_sort = nullptr; /* surface extensions: SHADE's path rays grouped by lobe (option wf_sort) */
     cudaKernel_t wf_gen = nullptr, wf_isect = nullptr, wf_march = nullptr, wf_shade = nullptr, wf_final = nullptr,
                  wf_ctl = nullptr;
 };
@@ -53,6 +54,7 @@ struct pt_ctx {
     bool gen_clamped = false; /* the buffer is smaller than asked for because memory was short */
     cudaStream_t gen_stream = nullptr; /* second stream of a banded pregen dispatch */
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    long long wf_sort = 0;      /* wavefront pipeline with surface extensions: sort SHADE's path rays by lobe (measured: slower) */
     long long wf_max_paths = 0; /* wavefront pipeline: paths in flight per chunk; 0 = auto (4 Mi without SDFs, 32 Mi with:
                                    profiles/r02_wf_l2) */
     bool bvh_active = false;
@@ -286,7 +288,15 @@ int launch_wavefront(pt_ctx* ctx, const PtDevParams& dp0) {
             const int identity = (depth == 0) ? 1 : 0;
             PT_CUDA(ctx, run(k->wf_isect, grid, 0, identity, 6));
             if (has_sdf) PT_CUDA(ctx, run(k->wf_march, grid, 0, 0, 4));
-            PT_CUDA(ctx, run(k->wf_shade, grid, 0, identity, 6));
+            if (ctx->wf_sort && ctx->dev_scene.nSurfaceExt > 0) { /* material-sorted shading: path rays grouped by lobe */
+                PT_CUDA(ctx, run(k->wf_sort, grid, identity, 0, 6));
+                PT_CUDA(ctx, ctl(3));
+                PT_CUDA(ctx, run(k->wf_sort, grid, identity, 1, 6));
+                PT_CUDA(ctx, ctl(4));
+                PT_CUDA(ctx, run(k->wf_shade, grid, 2, identity, 6));
+            } else {
+                PT_CUDA(ctx, run(k->wf_shade, grid, 0, identity, 6));
+            }
             if (ctx->dev_scene.numLights > 0.0f) { /* shadow rays of this depth */
                 if (has_sdf) PT_CUDA(ctx, ctl(1));
                 PT_CUDA(ctx, run(k->wf_isect, grid, 1, 0, 6));
@@ -415,6 +425,11 @@ int pt_set_option(pt_ctx* ctx, const char* key, long long value) {
         ctx->pregen_max_mb = value;
         return PT_OK;
     }
+    if (std::string(key) == "wf_sort") {
+        if (value < 0 || value > 1) return fail(ctx, PT_ERR_ARG, "pt_set_option: wf_sort is 0 or 1");
+        ctx->wf_sort = value;
+        return PT_OK;
+    }
     if (std::string(key) == "wf_max_paths") {
         if (value < 0) return fail(ctx, PT_ERR_ARG, "pt_set_option: wf_max_paths must be positive (or 0 = auto)");
         ctx->wf_max_paths = value;
@@ -428,6 +443,7 @@ int pt_set_option(pt_ctx* ctx, const char* key, long long value) {
 int pt_get_option(const pt_ctx* ctx, const char* key, long long* value) {
     if (!ctx || !key || !value) return PT_ERR_ARG;
     if (std::string(key) == "wf_max_paths") { *value = ctx->wf_max_paths; return PT_OK; }
+    if (std::string(key) == "wf_sort") { *value = ctx->wf_sort; return PT_OK; }
     if (std::string(key) == "pregen_max_mb") { *value = ctx->pregen_max_mb; return PT_OK; }
     return pt_knob_get(&ctx->knobs, key, value) == 0 ? PT_OK : PT_ERR_ARG;
 }
@@ -534,7 +550,8 @@ int pt_set_scene(pt_ctx* ctx, const pt_ubo* ubo, const char* const* sdf_glsl, in
             if (wavefront) {
                 struct { const char* name; cudaKernel_t* k; bool need; } wk[] = {
                     {"pt_wf_gen", &jk.wf_gen, true}, {"pt_wf_isect", &jk.wf_isect, true}, {"pt_wf_march", &jk.wf_march, n_sdf > 0},
-                    {"pt_wf_shade", &jk.wf_shade, true}, {"pt_wf_final", &jk.wf_final, true}, {"pt_wf_ctl", &jk.wf_ctl, true}};
+                    {"pt_wf_shade", &jk.wf_shade, true}, {"pt_wf_final", &jk.wf_final, true}, {"pt_wf_ctl", &jk.wf_ctl, true},
+                    {"pt_wf_sort", &jk.wf_sort, true}};
                 for (auto& x : wk) {
                     if (!x.need) continue;
                     if ((e = cudaLibraryGetKernel(x.k, jk.lib, x.name)) != cudaSuccess) {

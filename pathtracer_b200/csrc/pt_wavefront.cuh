@@ -255,6 +255,47 @@ PT_DEV void WfShade(const Ctx& c, const PtWf& w, const unsigned* __restrict__ q,
     }
 }
 
+/* ---- SORT (surface extensions only, option wf_sort): the path rays about to be shaded, grouped by the lobe of the surface
+ * they hit -- 0 = the reference's Lambertian, misses and emitters, 1 mirror, 2 glossy, 3 dielectric -- so a warp of the SHADE
+ * kernel runs one lobe's code instead of up to four (the "material-sorted shading" of the wavefront design; with the
+ * reference's single surface model there is nothing to sort).  A counting sort in two passes over the queue: pass 0 counts
+ * the classes (one atomic per warp and class), pt_wf_ctl(3) turns the counts into bases, pass 1 scatters into the march
+ * queue's buffer, idle at this point.  The order inside a class follows the atomics; nothing depends on it (FINAL sums by
+ * sample index). */
+enum { PT_WF_BIN0 = 8, PT_WF_BASE0 = 12 };
+PT_DEV int WfLobeClass(const Ctx& c, const PtWf& w, unsigned p) {
+#if PT_EXT_BSDF
+    const float4 a = w.hit0[p], b = w.hit1[p];
+    if (!(a.x < 1e5f)) return 0;
+    float emitT, emitL;
+    GetLightMix(c, b.y, emitT, emitL);
+    if (emitL > 0.0f) return 0;
+    return SurfaceExtOf(c, b.x).bsdf & 3;
+#else
+    (void)c; (void)w; (void)p;
+    return 0;
+#endif
+}
+PT_DEV void WfSort(const Ctx& c, const PtWf& w, const unsigned* __restrict__ q, unsigned count, int identity, int pass) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    const unsigned rounds = (count + stride - 1u) / stride;
+    for (unsigned r = 0; r < rounds; r++) {
+        const unsigned i = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const bool valid = i < count;
+        const unsigned p = valid ? (identity ? i : q[i]) : 0u;
+        const int cls = valid ? WfLobeClass(c, w, p) : -1;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (pass == 0) {
+                const unsigned m = __ballot_sync(0xffffffffu, cls == k);
+                if (m != 0u && LaneId() == (unsigned)(__ffs(m) - 1)) atomicAdd(w.cnt + PT_WF_BIN0 + k, (unsigned)__popc(m));
+            } else {
+                QueuePush(w.qM + w.cnt[PT_WF_BASE0 + k], w.cnt + PT_WF_BIN0 + k, cls == k, p);
+            }
+        }
+    }
+}
+
 /* ---- FINAL: per pixel, add the chunk's finished paths in sample-index order; after the last chunk, Rendering()'s
  * tail + Accumulate() + imageStore (StoreTexel) ------------------------------------------------------------------- */
 PT_DEV void WfFinal(const PtDevParams& pr, const PtWf& w, float4* __restrict__ image) {
@@ -312,12 +353,21 @@ PT_DEV void WfFinal(const PtDevParams& pr, const PtWf& w, float4* __restrict__ i
     extern "C" __global__ void __launch_bounds__(PT_BLOCK_THREADS, PT_MIN_BLOCKS)                              \
     pt_wf_shade(PT_WF_SIG, int which, int identity) {                                                          \
         PT_WF_CTX();                                                                                           \
-        const unsigned n = identity ? w.P : w.cnt[which ? PT_WF_NS : PT_WF_NA];                                \
-        PT_KERNEL_NS::WfShade(c, w, which ? w.qS : w.qA, n, identity);                                         \
+        const unsigned n = identity ? w.P : w.cnt[which == 1 ? PT_WF_NS : PT_WF_NA];                           \
+        PT_KERNEL_NS::WfShade(c, w, which == 2 ? w.qM : (which ? w.qS : w.qA), n, which == 2 ? 0 : identity);  \
+    }                                                                                                          \
+    extern "C" __global__ void __launch_bounds__(PT_BLOCK_THREADS, PT_MIN_BLOCKS)                              \
+    pt_wf_sort(PT_WF_SIG, int identity, int pass) {                                                            \
+        PT_WF_CTX();                                                                                           \
+        const unsigned n = identity ? w.P : w.cnt[PT_WF_NA];                                                   \
+        PT_KERNEL_NS::WfSort(c, w, w.qA, n, identity, pass);                                                   \
     }                                                                                                          \
     extern "C" __global__ void pt_wf_ctl(const __grid_constant__ PtWf w, int op) {                             \
         if (threadIdx.x != 0 || blockIdx.x != 0) return;                                                       \
-        if (op == 0) { for (int i = 0; i < 8; i++) w.cnt[i] = 0u; }              /* start of a chunk */       \
+        if (op == 0) { for (int i = 0; i < 16; i++) w.cnt[i] = 0u; }             /* start of a chunk */       \
+        else if (op == 3) { unsigned b = 0u;                                      /* SORT: counts -> bases */  \
+            for (int k = 0; k < 4; k++) { w.cnt[12 + k] = b; b += w.cnt[8 + k]; w.cnt[8 + k] = 0u; } }        \
+        else if (op == 4) { for (int k = 0; k < 4; k++) w.cnt[8 + k] = 0u; }     /* after SORT's scatter */   \
         else if (op == 1) { w.cnt[PT_WF_NM] = 0u; w.cnt[PT_WF_HEAD] = 0u; }      /* before the next march */   \
         else { w.cnt[PT_WF_NA] = w.cnt[PT_WF_NB]; w.cnt[PT_WF_NB] = 0u; w.cnt[PT_WF_NS] = 0u;                  \
                w.cnt[PT_WF_NM] = 0u; w.cnt[PT_WF_HEAD] = 0u; }                   /* next depth (host swaps qA/qB) */ \

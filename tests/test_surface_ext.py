@@ -288,6 +288,25 @@ def test_cuda_strict_bit_exact_with_extensions(ptlib, options, pipeline, name, w
 
 
 @pytest.mark.gpu
+def test_wavefront_material_sorted_shading(ptlib):
+    """The wavefront pipeline groups SHADE's path rays by lobe (option wf_sort; off by default: it measured slower): the same image bit for bit with and without the sort, strict and fast -- only the order in which paths
+    are shaded changes -- and equal to the oracle's in strict mode."""
+    import time
+    for name, w, h, spp, spf, pl in (('surfaces_ext', 160, 90, 8, 4, 8), ('surfaces_ext_sdf', 96, 64, 4, 2, 8)):
+        for mode in (ptlib.MODE_STRICT, ptlib.MODE_FAST):
+            images, secs = [], []
+            for sort in (1, 0):
+                t0 = time.perf_counter()
+                got, ubo, p, src, t = gpu_render_ext(ptlib, name, w, h, spp, spf, pl, mode, {'wf_sort': sort}, pipeline=1)
+                secs.append(time.perf_counter() - t0)
+                images.append(got)
+            assert np.array_equal(images[0].view(np.uint32), images[1].view(np.uint32)), (name, mode)
+            if mode == ptlib.MODE_STRICT:
+                ref = oracle.Oracle(ubo, src, surface_ext=t).render(p, spp, spf)
+                assert np.array_equal(images[0].view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.gpu
 def test_cuda_reference_shading_returns_when_the_table_is_cleared(ptlib):
     """set_surface_ext(None) after an extended scene: the next set_scene builds the reference kernel again, and an
     all-reference table equals no table."""
