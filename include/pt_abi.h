@@ -143,6 +143,7 @@ int pt_bvh_active(const pt_ctx* ctx);
  *   "sin_poly_every"  fast mode: every k-th sin( of the SDF snippets runs on the FMA pipe instead of MUFU     [0]
  *   "pregen"      v2s / v3s: 1 = a generation kernel computes every sample's camera ray (seed, jitter, aperture, hero
  *                 wavelength, camera lens) with all lanes busy and the render kernel reads 32-byte records      [-1]
+ *   "pathcolor_unroll"  SDF builds: the four CIE look-ups of a finished sample unrolled (auto: with pregen)      [-1]
  *   "resolve"     with pregen: 1 = the render kernel stores each sample's radiance bundle and a resolve kernel projects
  *                 to XYZ and sums per pixel in sample order (schedule-independent sums in fast mode; speed-neutral) [-1 = 0]
  *   "pregen_max_mb"  record buffer of one band in MiB; a dispatch that needs more runs as bands of 8-pixel rows

@@ -55,7 +55,7 @@ std::string g_load_error;
 #define PT_DEFAULT_PATHCOLOR_UNROLL_WITH_PREGEN 1 /* cfg5 4.53 -> 4.58 Gsamples/s, cfg3 unchanged (profiles/r02_alu) */
 #endif
 #ifndef PT_DEFAULT_RESOLVE
-#define PT_DEFAULT_RESOLVE 0 /* until measured */
+#define PT_DEFAULT_RESOLVE 0 /* measured speed-neutral (cfg5 4.26 -> 4.30, cfg1 9.10 -> 8.94: profiles/r02_pregen); an option for schedule-independent sums */
 #endif
 #ifndef PT_DEFAULT_SCHED_ANALYTIC
 #define PT_DEFAULT_SCHED_ANALYTIC 7 /* v3s: 10.73 vs v1's 9.96 Gsamples/s on cfg2, 8.10 vs 7.62 on cfg1 (profiles/r02_gpu1) */
