@@ -243,7 +243,9 @@ from test_simt_emulation import DRIVERS, build_emulator, emulate  # noqa: E402
 
 @pytest.mark.parametrize('driver,name,w,h,spp,spf,pl', [
     ('v1', 'surfaces_ext', 48, 32, 6, 3, 8), ('v3s_table3', 'surfaces_ext', 48, 32, 6, 3, 8), ('v2s_table16', 'surfaces_ext', 40, 24, 4, 4, 12),
-    ('v1', 'surfaces_ext_sdf', 32, 20, 2, 2, 8), ('v2s_table2', 'surfaces_ext_sdf', 32, 20, 4, 2, 8), ('v2m', 'surfaces_ext_sdf', 32, 20, 4, 4, 8)])
+    ('v1', 'surfaces_ext_sdf', 32, 20, 2, 2, 8), ('v2s_table2', 'surfaces_ext_sdf', 32, 20, 4, 2, 8), ('v2m', 'surfaces_ext_sdf', 32, 20, 4, 4, 8),
+    # with the generation / resolve kernels, the configuration the JIT picks for this scene (it has a cyclide)
+    ('v2s_pregen', 'surfaces_ext_sdf', 32, 20, 4, 2, 8), ('v2s_resolve', 'surfaces_ext_sdf', 32, 20, 4, 4, 8), ('v3s_resolve', 'surfaces_ext', 48, 32, 6, 3, 8)])
 def test_emulated_strict_kernel_equals_the_oracle_with_extensions(ptlib, driver, name, w, h, spp, spf, pl):
     scene, ubo, p, src, table = ext_inputs(name, w, h, spf, pl)
     defs = dict(DRIVERS[driver])
