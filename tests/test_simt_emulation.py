@@ -35,7 +35,7 @@ def build_emulator(ptlib, defines, sdf_sources=(), sdf_raw=None):
     if sdf_sources:
         unit = api.sdf_translate(list(sdf_sources), sdf_raw)
         defs['PT_HAS_SDF'] = 1
-    srcs = [os.path.join(SIMT, 'simt_main.cpp'), os.path.join(SIMT, 'cuda_shim.h'), os.path.join(CSRC, 'pt_kernel.cuh'),
+    srcs = [os.path.join(SIMT, 'simt_main.cpp'), os.path.join(SIMT, 'cuda_shim.h'), os.path.join(CSRC, 'pt_kernel.cuh'), os.path.join(CSRC, 'pt_driver_v2m.cuh'),
             os.path.join(CSRC, 'pt_prepare.cpp'), os.path.join(CSRC, 'pt_dev_scene.h'), os.path.join(ROOT, 'include', 'pt_math.h')]
     h = hashlib.sha1((repr(sorted(defs.items())) + unit + ''.join(open(f).read() for f in srcs)).encode()).hexdigest()[:16]
     so = os.path.join(BUILD, 'simt_%s.so' % h)
@@ -46,7 +46,7 @@ def build_emulator(ptlib, defines, sdf_sources=(), sdf_raw=None):
             obj = cpp[:-4] + '.o'
             subprocess.run([sdf_build.CXX, *[f for f in sdf_build.CXXFLAGS if f != '-shared'], '-c', '-o', obj, cpp], check=True)
             objs.append(obj)
-        ph = hashlib.sha1(''.join(open(f).read() for f in srcs[3:]).encode()).hexdigest()[:16]
+        ph = hashlib.sha1(''.join(open(f).read() for f in srcs[4:]).encode()).hexdigest()[:16]
         prep = os.path.join(BUILD, 'pt_prepare_%s.o' % ph)   # the product's host-side preparation, compiled once
         if not os.path.exists(prep):
             subprocess.run(['g++', *FLAGS, '-c', os.path.join(CSRC, 'pt_prepare.cpp'), '-o', prep + '.tmp.o'], check=True)
